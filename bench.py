@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Exposure hot path on B200 (driver contract: one JSON line).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                  [--workload chain8] [--batch B] [--size S]
+
+Workload `chain8` (default; BASELINE.json configs[1]): the 8-filter chain
+E,G,W,S+,T,Ct,BW,C applied in sequence to a batch of B x S x S x 3 fp32 linear-RGB images,
+forward + backward (image gradient and per-image parameter gradients), B=64, S=512 per GPU.
+A "step" is one such pass over one batch.  Multi-GPU: the batch shards by image, one
+process per GPU, no data-path collective (weak scaling: 64 images per GPU).
+
+Reported:
+  value     images/s, whole job, inputs resident in HBM (CUDA events, max over ranks)
+  e2e       images/s through the public API with HOST (pinned) buffers: H2D of the batch and
+            D2H of the filtered batch + parameter gradients inside the timed region
+  roofline  the dominant kernel's achieved algorithmic GB/s vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU restatement of the reference TF graph (oracle/, torch fp32,
+            op by op + autograd) on a bounded sample, all host threads
+`--impl reference` times only that CPU restatement (the TF-1.6 reference cannot run here).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHAIN_IDS = [0, 1, 2, 3, 4, 5, 6, 7]         # E,G,W,S+,T,Ct,BW,C = cfg.filters order
+FWD_B, BWD_B = 24, 36                        # algorithmic bytes / pixel / step
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=200)
+  ap.add_argument("--warmup", type=int, default=10)
+  ap.add_argument("--impl", default="native", choices=["native", "reference"])
+  ap.add_argument("--workload", default="chain8", choices=["chain8"])
+  ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+  ap.add_argument("--size", type=int, default=512)
+  ap.add_argument("--variant", type=int, default=0)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+def peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    with open(p) as fh:
+      d = json.load(fh)
+    return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+  return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle = CPU restatement of the reference TF graph (NOT TensorFlow)
+# ------------------------------------------------------------------------------------------
+def cpu_chain_step(x, logits, gout):
+  """One chain8 fwd+bwd the way the reference executes: op by op, unfused, tf.gradients ==
+  autograd of the forward graph (oracle/filters.py)."""
+  import torch
+  from oracle import filters as F
+  xs = x.clone().requires_grad_(True)
+  lg = [l.clone().requires_grad_(True) for l in logits]
+  y = F.chain_fwd(CHAIN_IDS, xs, lg)[-1]
+  torch.autograd.grad(y, [xs] + lg, grad_outputs=gout)
+  return y
+
+
+def cpu_baseline(size, budget_s=20.0, batch=2):
+  import torch
+  from oracle import filters as F
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  x = F.synth_images(batch, size, size, seed=1234, stress=False)
+  logits = [F.synth_logits(f, batch) for f in CHAIN_IDS]
+  gout = torch.ones_like(x)
+  cpu_chain_step(x, logits, gout)                      # warm-up
+  times = []
+  t_end = time.time() + budget_s
+  while len(times) < 10 and (time.time() < t_end or len(times) < 2):
+    t0 = time.time()
+    cpu_chain_step(x, logits, gout)
+    times.append(time.time() - t0)
+  med = statistics.median(times)
+  return {
+      "value": batch / med, "unit": "images/s", "cores": cores, "kind": "port",
+      "sample": "chain8 fwd+bwd on %dx%dx%dx3 fp32, median of %d reps (min %.3fs); CPU restatement of the "
+                "reference TF graph (oracle/filters.py, torch-CPU op-by-op + autograd), not TensorFlow" %
+                (batch, size, size, len(times), min(times)),
+  }
+
+
+def run_reference(args):
+  """--impl reference: the reference's CPU path (oracle port) on the host cores; rank 0 only."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import torch
+  from oracle import filters as F
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  sample_b = 2
+  x = F.synth_images(sample_b, args.size, args.size, seed=1234, stress=False)
+  logits = [F.synth_logits(f, sample_b) for f in CHAIN_IDS]
+  gout = torch.ones_like(x)
+  for _ in range(max(1, min(args.warmup, 2))):
+    cpu_chain_step(x, logits, gout)
+  t0 = time.time()
+  for _ in range(args.steps):
+    cpu_chain_step(x, logits, gout)
+  dt = time.time() - t0
+  val = sample_b * args.steps / dt
+  sample = ("each step = chain8 fwd+bwd on a bounded sample of %d of the %d images (%dx%dx3 fp32); CPU "
+            "restatement of the reference TF graph (oracle port), torch-CPU, %d threads" %
+            (sample_b, args.batch, args.size, args.size, cores))
+  print(json.dumps({
+      "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": workload_config(args),
+      "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+      "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }))
+
+
+def workload_config(args):
+  return {
+      "workload": "chain8: 8-filter chain E,G,W,S+,T,Ct,BW,C fwd+bwd (BASELINE.json configs[1])",
+      "batch_per_gpu": args.batch, "height": args.size, "width": args.size, "channels": 3,
+      "filters": "E,G,W,S+,T,Ct,BW,C", "parallelism": "dp%d (batch sharded by image, no data-path collective)" % args.gpus,
+      "l2_policy": "working set (9 activations x %.0f MB + 2 gradient buffers) exceeds the 126 MB L2; no flush needed"
+                   % (args.batch * args.size * args.size * 12 / 1e6),
+  }
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+  Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+       "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.idx = gpu_index
+    self.proc = None
+    self.path = None
+
+  def start(self):
+    try:
+      fd, self.path = tempfile.mkstemp(suffix=".csv")
+      os.close(fd)
+      self.fh = open(self.path, "w")
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                   stderr=subprocess.DEVNULL)
+    except Exception:
+      self.proc = None
+
+  def stop(self, t0=None, t1=None):
+    """Summary of the samples taken in the wall-clock window [t0, t1] (the timed region);
+    falls back to every sample taken while the bench was under load when the window holds
+    fewer than 3."""
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    self.fh.close()
+    import datetime
+    rows = []
+    for line in open(self.path):
+      f = [t.strip() for t in line.split(",")]
+      if len(f) < 9:
+        continue
+      try:
+        ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[5:9]))
+      except ValueError:
+        continue
+    os.unlink(self.path)
+    window = "timed region"
+    sel = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+    if len(sel) < 3:
+      sel, window = rows, "whole loaded run (timed region too short for 3 samples)"
+    if not sel:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+    reasons = set()
+    for r in sel:
+      for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+        if v.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": statistics.median(r[1] for r in sel), "sm_max_mhz": max(r[2] for r in sel),
+            "reasons": sorted(reasons), "samples": len(sel), "power_w_max": max(r[3] for r in sel),
+            "window": window}
+
+
+def run_native(args):
+  import torch
+  import torch.distributed as dist
+  from exposure_b200 import ops
+  from exposure_b200.chain import FilterChain
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  B, S = args.batch, args.size
+
+  # synthetic linear-RGB batch, generated on the device for the resident leg
+  g = torch.Generator(device=dev).manual_seed(1234 + rank)
+  chain = FilterChain(CHAIN_IDS, variant=args.variant)
+  x0 = chain.input_buffer((B, S, S, 3), dev)
+  x0.copy_(torch.exp(torch.randn(B, S, S, 3, device=dev, generator=g) - 3.2).clamp_(0, 4))
+  stress = torch.rand(B, S, S, 3, device=dev, generator=g)
+  x0.copy_(torch.where(stress < 0.01, 1 + 3 * torch.rand(B, S, S, 3, device=dev, generator=g), x0))
+  del stress
+  gl = torch.Generator().manual_seed(4321)
+  logits = [torch.randn(B, ops.NUM_PARAMS[f], generator=gl).to(dev) for f in CHAIN_IDS]
+  gout = torch.randn(B, S, S, 3, device=dev, generator=g)
+
+  def step():
+    chain.forward_resident(logits)
+    return chain.backward(gout)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+
+  # ---- timed region (device resident) -----------------------------------------------------
+  ops.event_log = []
+  l0 = ops.launch_count
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  wall0 = time.time()
+  e0.record()
+  for _ in range(args.steps):
+    step()
+  e1.record()
+  barrier()
+  wall1 = time.time()
+  elapsed_ms = e0.elapsed_time(e1)
+  launches = ops.launch_count - l0
+  log, ops.event_log = ops.event_log, None
+  t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  elapsed_ms = float(t.item())
+  value = world * B * args.steps / (elapsed_ms / 1e3)
+
+  # ---- per-kernel roofline from the events recorded inside the timed region -----------------
+  per = {}
+  for name, nbytes, a, b in log:
+    d = per.setdefault(name, {"ms": 0.0, "bytes": 0, "n": 0})
+    d["ms"] += a.elapsed_time(b); d["bytes"] += nbytes; d["n"] += 1
+  peak, peak_src = peaks()
+  kernels = []
+  for name, d in sorted(per.items(), key=lambda kv: -kv[1]["ms"]):
+    kernels.append({"kernel": name, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
+                    "algorithmic_bytes_per_launch": d["bytes"] // d["n"],
+                    "achieved_gbs": d["bytes"] / d["ms"] / 1e6, "frac": d["bytes"] / d["ms"] / 1e6 / peak})
+  tot_ms = sum(d["ms"] for d in per.values())
+  tot_bytes = sum(d["bytes"] for d in per.values())
+  dom = kernels[0]
+  roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
+              "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+              "share_of_step": dom["avg_ms"] * dom["launches"] / (elapsed_ms) if elapsed_ms else None,
+              "chain": {"achieved": tot_bytes / tot_ms / 1e6, "frac": tot_bytes / tot_ms / 1e6 / peak,
+                        "algorithmic_bytes_per_step": B * S * S * (FWD_B + BWD_B) * len(CHAIN_IDS),
+                        "kernel_ms_per_step": tot_ms / args.steps},
+              "kernels": kernels}
+
+  # ---- end-to-end leg: host (pinned) buffers through the public API ------------------------
+  hx = torch.empty(B, S, S, 3, dtype=torch.float32).pin_memory()
+  hx.copy_(x0.cpu())
+  hy = torch.empty(B, S, S, 3, dtype=torch.float32).pin_memory()
+  hg = [torch.empty(B, ops.NUM_PARAMS[f]).pin_memory() for f in CHAIN_IDS]
+  xin = chain.input_buffer((B, S, S, 3), dev)
+
+  def e2e_step():
+    xin.copy_(hx, non_blocking=True)                 # H2D of this step's inputs
+    y = chain.forward_resident(logits)
+    _, glogits = chain.backward(gout, need_input_grad=True)
+    hy.copy_(y, non_blocking=True)                   # D2H: filtered batch (net.py:330 fetches fake_output)
+    for h, gq in zip(hg, glogits):
+      h.copy_(gq, non_blocking=True)                 # D2H: parameter gradients
+    torch.cuda.current_stream().synchronize()
+
+  e2e_steps = max(3, min(args.steps, 10))
+  for _ in range(2):
+    e2e_step()
+  barrier()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(e2e_steps):
+    e2e_step()
+  b.record()
+  barrier()
+  e2e_ms = a.elapsed_time(b)                     # device clock
+  t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_ms = float(t.item())
+  e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": "images/s",
+         "h2d_bytes_per_step": hx.numel() * 4,
+         "d2h_bytes_per_step": hy.numel() * 4 + sum(h.numel() * 4 for h in hg), "steps": e2e_steps,
+         "ms_per_step": e2e_ms / e2e_steps}
+
+  clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+  out = None
+  if rank == 0:
+    out = {
+        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      out["cpu_baseline"] = cpu_baseline(S)
+    elif world == 1:
+      out["cpu_baseline"] = None
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  if out is not None:
+    print(json.dumps(out))
+
+
+def main():
+  args = parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_native(args)
+
+
+if __name__ == "__main__":
+  main()

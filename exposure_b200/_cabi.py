@@ -1,0 +1,58 @@
+"""ctypes binding of include/exposure_b200.h.  No torch types cross this boundary.
+
+The product path has NO CPU fallback: if the shared library is missing or a call fails,
+an exception is raised (ExposureLibError)."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libexposure_b200.so")
+
+EXP_OK = 0
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA, VARIANT_SCALAR = 0, 1, 2, 3
+MAX_FILTER_PARAMS = 24
+NUM_FILTERS = 8
+
+
+class ExposureLibError(RuntimeError):
+  pass
+
+
+_c_void_p, _c_int, _c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/exposure_b200.h declares
+SIGNATURES = {
+    "exp_version": (_c_int, []),
+    "exp_last_error": (ctypes.c_char_p, []),
+    "exp_num_filter_params": (_c_int, [_c_int]),
+    "exp_filter_regress_fwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "exp_filter_regress_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "exp_filter_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_filter_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "exp_filter_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
+                                _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_int, _c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+  """The loaded C-ABI library (loads on first use; raises if it was never built)."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise ExposureLibError(
+          "%s not found: run `python -m exposure_b200.build` (there is no CPU fallback)" % LIB_PATH)
+    l = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+      fn = getattr(l, name)   # AttributeError if the symbol is missing
+      fn.restype = res
+      fn.argtypes = args
+    _lib = l
+  return _lib
+
+
+def check(rc, what=""):
+  if rc != EXP_OK:
+    msg = lib().exp_last_error()
+    raise ExposureLibError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

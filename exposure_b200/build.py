@@ -1,0 +1,61 @@
+"""In-tree build of the C-ABI CUDA library (sm_100a only).
+
+``python -m exposure_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
+without a GPU; the resulting ``exposure_b200/_lib/libexposure_b200.so`` is git-ignored but
+travels to the GPU box with the gpurun snapshot.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_lib")
+LIB_PATH = os.path.join(OUT_DIR, "libexposure_b200.so")
+STAMP = os.path.join(OUT_DIR, "build.stamp")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+]
+
+
+def _sources():
+  return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _digest():
+  h = hashlib.sha256()
+  for root in (CSRC, os.path.join(HERE, "..", "include")):
+    for f in sorted(os.listdir(root)):
+      if f.endswith((".cu", ".cuh", ".h")):
+        with open(os.path.join(root, f), "rb") as fh:
+          h.update(f.encode() + b"\0" + fh.read())
+  h.update(" ".join(NVCC_FLAGS).encode())
+  return h.hexdigest()
+
+
+def build_lib(force=False, verbose=False):
+  """Compile every .cu under csrc/ into one shared library.  Returns its path."""
+  os.makedirs(OUT_DIR, exist_ok=True)
+  digest = _digest()
+  if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
+    with open(STAMP) as fh:
+      if fh.read().strip() == digest:
+        return LIB_PATH
+  nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+  cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+  res = subprocess.run(cmd, capture_output=True, text=True)
+  if res.returncode != 0:
+    sys.stderr.write(res.stdout + res.stderr)
+    raise RuntimeError("nvcc failed building %s" % LIB_PATH)
+  if verbose:
+    sys.stderr.write(res.stderr)
+  with open(STAMP, "w") as fh:
+    fh.write(digest)
+  return LIB_PATH
+
+
+if __name__ == "__main__":
+  print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,316 @@
+// Per-pixel arithmetic of the eight Exposure filters (forward + hand-derived backward).
+//
+// Reference: yuanming-hu/exposure filters.py (process() of each Filter subclass) and the
+// TF-1.6 kernels it lowers to; see include/exposure_b200.h for the file:line map and
+// DESIGN.md section 4 for the derivations of the backward closed forms.
+//
+// Numerics policy: chains that the reference's fp32 formula makes ill-conditioned
+// (SaturationPlus' 1-s', the curve prefix sums) are written with explicit __f*_rn
+// intrinsics in the reference's op order so that ptxas cannot contract them into FMAs and
+// the result tracks the fp32 restatement to ~1 ulp.  Everything else may use FMA.
+#pragma once
+#include "common.cuh"
+
+namespace expo {
+
+constexpr int kCurveSteps = 8;              // cfg.curve_steps (config_example.py:27)
+constexpr float kInvL = 0.125f;             // 1 / curve_steps
+constexpr float kLn2 = 0.69314718f;         // float32(np.log(2))      filters.py:182
+constexpr float kPi = 3.14159274f;          // float32(math.pi)        filters.py:417
+constexpr float kLumR = 0.27f, kLumG = 0.67f, kLumB = 0.06f;   // util.py:271-274
+constexpr int kAccStride = 32;              // floats per partial-sum record
+
+__host__ __device__ constexpr int num_params(int fid) {
+  return fid == EXP_FILTER_WB ? 3 : fid == EXP_FILTER_TONE ? 8 : fid == EXP_FILTER_COLOR ? 24 : 1;
+}
+// number of per-thread accumulators the backward of filter `fid` carries
+__host__ __device__ constexpr int num_acc(int fid) {
+  return fid == EXP_FILTER_WB ? 3 : fid == EXP_FILTER_TONE ? 9 : fid == EXP_FILTER_COLOR ? 27 : 1;
+}
+
+// Per-image constants, built once per CTA in shared memory from params[b, :].
+struct __align__(16) FilterConsts {
+  float p[EXP_MAX_FILTER_PARAMS];   // regressed parameters
+  float cum[3][kCurveSteps + 1];    // curve prefix sums  sum_{i<k} t_i / L   (T uses row 0)
+  float scale[3];                   // L / (sum_i t_i + 1e-30)
+  float S[3];                       // sum_i t_i + 1e-30
+  float e;                          // Exposure: exp(p * ln2)
+};
+
+// Executed by the first warp of a CTA; followed by __syncthreads() at the call site.
+__device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __restrict__ prow, int fid) {
+  const int t = threadIdx.x;
+  const int n = num_params(fid);
+  if (t < EXP_MAX_FILTER_PARAMS) sc.p[t] = (t < n) ? prow[t] : 0.f;
+  __syncwarp();
+  if (t == 0) sc.e = expf(sc.p[0] * kLn2);                        // filters.py:182
+  if (t < 3) {                                                    // filters.py:264-273 / 312-322
+    float cum = 0.f, sum = 0.f;
+    sc.cum[t][0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kCurveSteps; ++i) {
+      const float ti = sc.p[t * kCurveSteps + i];
+      cum = __fadd_rn(cum, __fmul_rn(kInvL, ti));
+      sum = __fadd_rn(sum, ti);
+      sc.cum[t][i + 1] = cum;
+    }
+    const float S = __fadd_rn(sum, 1e-30f);
+    sc.S[t] = S;
+    sc.scale[t] = __fdiv_rn((float)kCurveSteps, S);
+  }
+}
+
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// ---- monotone piecewise-linear curve (ToneFilter / ColorFilter) ---------------------
+// y = (L/S) * sum_i clip(x - i/L, 0, 1/L) * t_i ; evaluated through the prefix sums:
+// segment k = floor(L * clamp(x,0,1)), y = (cum[k] + (xc - k/L) * t_k) * (L/S).
+__device__ __forceinline__ float curve_eval(float x, const FilterConsts& sc, int row) {
+  const float xc = clamp01(x);
+  const int k = min((int)(xc * (float)kCurveSteps), kCurveSteps - 1);
+  const float frac = xc - (float)k * kInvL;                 // exact (Sterbenz)
+  const float tot = __fadd_rn(sc.cum[row][k], __fmul_rn(frac, sc.p[row * kCurveSteps + k]));
+  return __fmul_rn(tot, sc.scale[row]);
+}
+
+// ---- TF colour-space round trip of SaturationPlusFilter (filters.py:484-498) ----------
+// Returns xm = min(x,1) and full = hsv_to_rgb(h, s', v) in the op order of
+// tensorflow/core/kernels/colorspace_op.h.
+__device__ __forceinline__ void satplus_full(const float (&x)[3], float (&xm)[3], float (&full)[3]) {
+  const float r = fminf(x[0], 1.f), g = fminf(x[1], 1.f), b = fminf(x[2], 1.f);
+  xm[0] = r; xm[1] = g; xm[2] = b;
+  const float V = fmaxf(r, fmaxf(g, b));
+  const float m = fminf(r, fminf(g, b));
+  const float rng = __fsub_rn(V, m);
+  const float S = V > 0.f ? __fdiv_rn(rng, V) : 0.f;
+  const float norm = __fmul_rn(__frcp_rn(rng), (float)(1.0 / 6.0));
+  float H;
+  if (r == V) H = __fmul_rn(norm, __fsub_rn(g, b));
+  else if (g == V) H = __fadd_rn(__fmul_rn(norm, __fsub_rn(b, r)), (float)(2.0 / 6.0));
+  else H = __fadd_rn(__fmul_rn(norm, __fsub_rn(r, g)), (float)(4.0 / 6.0));
+  H = rng > 0.f ? H : 0.f;
+  H = H < 0.f ? __fadd_rn(H, 1.f) : H;
+  const float kk = __fsub_rn(0.5f, fabsf(__fsub_rn(0.5f, V)));
+  const float s2 = __fadd_rn(S, __fmul_rn(__fmul_rn(__fsub_rn(1.f, S), kk), 0.8f));
+  const float dh = __fmul_rn(H, 6.f);
+  const float dr = clamp01(__fsub_rn(fabsf(__fsub_rn(dh, 3.f)), 1.f));
+  const float dg = clamp01(__fadd_rn(-fabsf(__fsub_rn(dh, 2.f)), 2.f));
+  const float db = clamp01(__fadd_rn(-fabsf(__fsub_rn(dh, 4.f)), 2.f));
+  const float one_s = __fadd_rn(-s2, 1.f);
+  full[0] = __fmul_rn(__fadd_rn(one_s, __fmul_rn(s2, dr)), V);
+  full[1] = __fmul_rn(__fadd_rn(one_s, __fmul_rn(s2, dg)), V);
+  full[2] = __fmul_rn(__fadd_rn(one_s, __fmul_rn(s2, db)), V);
+}
+
+// =======================================================================================
+// forward of one pixel
+// =======================================================================================
+template <int FID>
+__device__ __forceinline__ void px_fwd(const float (&x)[3], float (&y)[3], const FilterConsts& sc) {
+  if constexpr (FID == EXP_FILTER_EXPOSURE) {          // filters.py:181-182
+    const float e = sc.e;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = x[c] * e;
+  } else if constexpr (FID == EXP_FILTER_GAMMA) {      // filters.py:205-206  max(x,1e-3)^gamma
+    const float gm = sc.p[0];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = exp2f(gm * log2f(fmaxf(x[c], 0.001f)));
+  } else if constexpr (FID == EXP_FILTER_WB) {         // filters.py:237-238
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = x[c] * sc.p[c];
+  } else if constexpr (FID == EXP_FILTER_SATPLUS) {    // filters.py:484-498
+    float xm[3], full[3];
+    satplus_full(x, xm, full);
+    const float p = sc.p[0];
+    const float q = __fsub_rn(1.f, p);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = __fadd_rn(__fmul_rn(xm[c], q), __fmul_rn(full[c], p));
+  } else if constexpr (FID == EXP_FILTER_TONE) {       // filters.py:312-322
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = curve_eval(x[c], sc, 0);
+  } else if constexpr (FID == EXP_FILTER_COLOR) {      // filters.py:264-273
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = curve_eval(x[c], sc, c);
+  } else if constexpr (FID == EXP_FILTER_CONTRAST) {   // filters.py:415-419
+    const float p = sc.p[0];
+    const float lum = __fadd_rn(__fadd_rn(__fmul_rn(kLumR, x[0]), __fmul_rn(kLumG, x[1])), __fmul_rn(kLumB, x[2]));
+    const float l = clamp01(lum);
+    const float cl = __fadd_rn(__fmul_rn(-cosf(__fmul_rn(kPi, l)), 0.5f), 0.5f);
+    const float den = __fadd_rn(l, 1e-6f);
+    const float q = __fsub_rn(1.f, p);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float ci = __fmul_rn(__fdiv_rn(x[c], den), cl);
+      y[c] = __fadd_rn(__fmul_rn(q, x[c]), __fmul_rn(p, ci));
+    }
+  } else {                                             // WNB  filters.py:438-440
+    const float p = sc.p[0];
+    const float lum = __fadd_rn(__fadd_rn(__fmul_rn(kLumR, x[0]), __fmul_rn(kLumG, x[1])), __fmul_rn(kLumB, x[2]));
+    const float q = __fsub_rn(1.f, p);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = __fadd_rn(__fmul_rn(q, x[c]), __fmul_rn(p, lum));
+  }
+}
+
+// =======================================================================================
+// backward of one pixel: gx = (dy/dx)^T gy ; acc += per-parameter partial sums
+// (final transform of the sums is finalize_gparams()).
+// =======================================================================================
+template <int FID, bool HAS_GX>
+__device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3], float (&gx)[3],
+                                       float* __restrict__ acc, const FilterConsts& sc) {
+  if constexpr (FID == EXP_FILTER_EXPOSURE) {
+    // y = x e ; dy/dp = y ln2 (ln2 applied at finalize) ; dy/dx = e
+    const float e = sc.e;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      s = fmaf(gy[c] * x[c], e, s);
+      if (HAS_GX) gx[c] = gy[c] * e;
+    }
+    acc[0] += s;
+  } else if constexpr (FID == EXP_FILTER_GAMMA) {
+    // y = xc^g ; dy/dg = y ln xc ; dy/dx = g y / xc [x >= 1e-3]   (TF MaximumGrad tie -> x)
+    const float gm = sc.p[0];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xc = fmaxf(x[c], 0.001f);
+      const float l2 = log2f(xc);
+      const float y = exp2f(gm * l2);
+      s = fmaf(gy[c] * y, l2, s);
+      if (HAS_GX) gx[c] = x[c] >= 0.001f ? gy[c] * gm * __fdividef(y, xc) : 0.f;
+    }
+    acc[0] = fmaf(s, kLn2, acc[0]);
+  } else if constexpr (FID == EXP_FILTER_WB) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      acc[c] = fmaf(gy[c], x[c], acc[c]);
+      if (HAS_GX) gx[c] = gy[c] * sc.p[c];
+    }
+  } else if constexpr (FID == EXP_FILTER_SATPLUS) {
+    // closed form of the HSV round trip:
+    //   full_c = xm_c - k(V) m u_c,  u_c = (V - xm_c)/(V - m),  k = 0.8 (0.5 - |0.5 - V|)
+    const float p = sc.p[0];
+    const float r = fminf(x[0], 1.f), g = fminf(x[1], 1.f), b = fminf(x[2], 1.f);
+    const bool is_r = (r >= g) && (r >= b);
+    const bool is_g = !is_r && (g >= b);
+    const bool mn_r = (r <= g) && (r <= b);
+    const bool mn_g = !mn_r && (g <= b);
+    const float V = is_r ? r : (is_g ? g : b);
+    const float m = mn_r ? r : (mn_g ? g : b);
+    const float rng = V - m;
+    const float k = (0.5f - fabsf(0.5f - V)) * 0.8f;
+    const float kp = V < 0.5f ? 0.8f : (V > 0.5f ? -0.8f : 0.f);
+    const float xm[3] = {r, g, b};
+    float gF[3] = {gy[0] * p, gy[1] * p, gy[2] * p};
+    float gxm[3], gV, gm;
+    float dp;   // sum_c gy_c (full_c - xm_c)
+    if (rng > 0.f) {
+      const float inv = 1.f / rng;
+      const float Q = k * m;
+      float Tt = 0.f, sg = 0.f, sgy_u = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float u = (V - xm[c]) * inv;
+        Tt = fmaf(gF[c], u, Tt);
+        sgy_u = fmaf(gy[c], u, sgy_u);
+        sg += gF[c];
+        gxm[c] = fmaf(Q * inv, gF[c], gy[c]);
+      }
+      dp = -Q * sgy_u;
+      gV = -Tt * kp * m - Q * (sg - Tt) * inv;
+      gm = -Tt * k - Q * Tt * inv;
+    } else {
+      // grey pixel: TF's hue == 0 gives full = (V, (1-k)V, (1-k)V)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gxm[c] = gy[c] * (1.f - p);
+      gV = gF[0] + (gF[1] + gF[2]) * (1.f - k - kp * V);
+      gm = 0.f;
+      dp = -(gy[1] + gy[2]) * k * V;
+    }
+    acc[0] += dp;
+    if (HAS_GX) {
+      gxm[0] += (is_r ? gV : 0.f) + (mn_r ? gm : 0.f);
+      gxm[1] += (is_g ? gV : 0.f) + (mn_g ? gm : 0.f);
+      gxm[2] += ((!is_r && !is_g) ? gV : 0.f) + ((!mn_r && !mn_g) ? gm : 0.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gx[c] = x[c] <= 1.f ? gxm[c] : 0.f;
+    }
+  } else if constexpr (FID == EXP_FILTER_TONE || FID == EXP_FILTER_COLOR) {
+    // y = (L/S) sum_i clip_i(x) t_i ;  dy/dt_j = (L clip_j - y)/S ;  dy/dx = (L/S) sum_{pass} t_j
+    // acc[row*9 + j] = sum gy clip_j ; acc[row*9 + 8] = sum gy y    (row = 0 for Tone)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int row = (FID == EXP_FILTER_COLOR) ? c : 0;
+      float* a = acc + row * (kCurveSteps + 1);
+      const float y = curve_eval(x[c], sc, row);
+      a[kCurveSteps] = fmaf(gy[c], y, a[kCurveSteps]);
+      float slope = 0.f;
+#pragma unroll
+      for (int j = 0; j < kCurveSteps; ++j) {
+        const float v = x[c] - (float)j * kInvL;
+        const float cj = fminf(fmaxf(v, 0.f), kInvL);
+        a[j] = fmaf(gy[c], cj, a[j]);
+        if (HAS_GX) slope += (v >= 0.f && v <= kInvL) ? sc.p[row * kCurveSteps + j] : 0.f;
+      }
+      if (HAS_GX) gx[c] = gy[c] * slope * sc.scale[row];
+    }
+  } else if constexpr (FID == EXP_FILTER_CONTRAST) {
+    // y_c = (1-p) x_c + p x_c w(l),  w = cl/(l+eps),  cl = sin^2(pi l / 2)  (== -cos(pi l)/2 + 1/2)
+    const float p = sc.p[0];
+    const float lum = fmaf(kLumB, x[2], fmaf(kLumG, x[1], kLumR * x[0]));
+    const float l = clamp01(lum);
+    float sn, cs;
+    sincosf(0.5f * kPi * l, &sn, &cs);
+    const float cl = sn * sn;
+    const float dcl = kPi * sn * cs;                 // 0.5 pi sin(pi l)
+    const float iden = 1.f / (l + 1e-6f);
+    const float w = cl * iden;
+    const float dw = (dcl - w) * iden;
+    const float sgx = fmaf(gy[2], x[2], fmaf(gy[1], x[1], gy[0] * x[0]));
+    acc[0] = fmaf(sgx, w - 1.f, acc[0]);
+    if (HAS_GX) {
+      const float a = fmaf(p, w, 1.f - p);
+      const float bq = (lum >= 0.f && lum <= 1.f) ? p * sgx * dw : 0.f;
+      gx[0] = fmaf(bq, kLumR, gy[0] * a);
+      gx[1] = fmaf(bq, kLumG, gy[1] * a);
+      gx[2] = fmaf(bq, kLumB, gy[2] * a);
+    }
+  } else {                                           // WNB
+    const float p = sc.p[0];
+    const float lum = fmaf(kLumB, x[2], fmaf(kLumG, x[1], kLumR * x[0]));
+    const float sg = gy[0] + gy[1] + gy[2];
+    acc[0] += sg * lum - fmaf(gy[2], x[2], fmaf(gy[1], x[1], gy[0] * x[0]));
+    if (HAS_GX) {
+      const float q = 1.f - p;
+      const float ps = p * sg;
+      gx[0] = fmaf(ps, kLumR, q * gy[0]);
+      gx[1] = fmaf(ps, kLumG, q * gy[1]);
+      gx[2] = fmaf(ps, kLumB, q * gy[2]);
+    }
+  }
+}
+
+// Final transform from reduced sums (double) to dL/dparam for image b.  `sum[a]` holds the
+// image-wide total of accumulator a.  Writes n = num_params(fid) floats.
+__device__ __forceinline__ void finalize_gparams(int fid, const double* sum, const float* p, float* out) {
+  if (fid == EXP_FILTER_EXPOSURE) {
+    out[0] = (float)(sum[0] * (double)kLn2);
+  } else if (fid == EXP_FILTER_TONE || fid == EXP_FILTER_COLOR) {
+    const int rows = fid == EXP_FILTER_TONE ? 1 : 3;
+    for (int r = 0; r < rows; ++r) {
+      float s = 0.f;
+      for (int i = 0; i < kCurveSteps; ++i) s = __fadd_rn(s, p[r * kCurveSteps + i]);
+      const double S = (double)__fadd_rn(s, 1e-30f);
+      const double Bs = sum[r * (kCurveSteps + 1) + kCurveSteps];
+      for (int j = 0; j < kCurveSteps; ++j)
+        out[r * kCurveSteps + j] = (float)(((double)kCurveSteps * sum[r * (kCurveSteps + 1) + j] - Bs) / S);
+    }
+  } else {
+    const int n = num_params(fid);
+    for (int i = 0; i < n; ++i) out[i] = (float)sum[i];
+  }
+}
+
+}  // namespace expo

@@ -1,0 +1,416 @@
+// Fused per-pixel filter step of the Exposure hot path: kernels + C-ABI entry points.
+//
+// One launch = one filter step over a whole batch (forward: read x, write y = 24 B/pixel;
+// backward: read x, read gy, write gx = 36 B/pixel, per-image parameter gradients reduced
+// warp-shuffle -> shared memory -> per-CTA partial -> fixed-order fp64 finish by the last
+// CTA of each image).  HBM-bandwidth bound by construction; see DESIGN.md section 5.
+//
+// Replaces the unfused TF-1.6 Eigen launches behind filters.py process() (2..43 launches
+// per filter) and the 8-way stack/one_hot/reduce_sum select of agent.py:77,118-129.
+#include "filter_math.cuh"
+
+namespace expo {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kPixPerBlockFwd = 4096;    // 256 threads x 4 pixels x 4 iterations
+constexpr int kPixPerBlockBwd = 8192;    // fewer, fatter CTAs: one partial record per CTA
+
+static thread_local char g_err[512] = "";
+char* last_error_buf() { return g_err; }
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct FilterArgs {
+  const float* x;
+  const float* gy;       // backward only
+  float* out;            // y (forward) or gx (backward, nullable)
+  const float* params;
+  int pstride;
+  const int* ids;        // per-image filter ids or nullptr
+  int P;                 // pixels per image
+  int pix_per_block;
+  float* partials;       // [B][nblk][kAccStride]
+  unsigned* counters;    // [B]
+  float* gparams;        // [B][pstride]
+};
+
+// ---- 4 pixels <-> 3 float4 ------------------------------------------------------------
+struct Px4 { float4 a, b, c; };
+__device__ __forceinline__ Px4 load_px4(const float* __restrict__ base, size_t q) {
+  const float4* p = reinterpret_cast<const float4*>(base) + q * 3;
+  Px4 v;
+  v.a = __ldg(p);
+  v.b = __ldg(p + 1);
+  v.c = __ldg(p + 2);
+  return v;
+}
+__device__ __forceinline__ void store_px4(float* __restrict__ base, size_t q, const Px4& v) {
+  float4* p = reinterpret_cast<float4*>(base) + q * 3;
+  p[0] = v.a;
+  p[1] = v.b;
+  p[2] = v.c;
+}
+__device__ __forceinline__ void unpack(const Px4& v, float (&px)[4][3]) {
+  px[0][0] = v.a.x; px[0][1] = v.a.y; px[0][2] = v.a.z;
+  px[1][0] = v.a.w; px[1][1] = v.b.x; px[1][2] = v.b.y;
+  px[2][0] = v.b.z; px[2][1] = v.b.w; px[2][2] = v.c.x;
+  px[3][0] = v.c.y; px[3][1] = v.c.z; px[3][2] = v.c.w;
+}
+__device__ __forceinline__ Px4 pack(const float (&px)[4][3]) {
+  Px4 v;
+  v.a = make_float4(px[0][0], px[0][1], px[0][2], px[1][0]);
+  v.b = make_float4(px[1][1], px[1][2], px[2][0], px[2][1]);
+  v.c = make_float4(px[2][2], px[3][0], px[3][1], px[3][2]);
+  return v;
+}
+
+// ---- per-CTA reduction of the parameter-gradient accumulators + last-CTA finish --------
+template <int FID>
+__device__ __forceinline__ void reduce_and_finish(float* acc, const FilterArgs& A, const FilterConsts& sc,
+                                                  float (*red)[kAccStride], int b, int nblk) {
+  constexpr int NACC = num_acc(FID);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    const float v = warp_sum(acc[a]);
+    if (lane == 0) red[warp][a] = v;
+  }
+  __syncthreads();
+  float* rec = A.partials + ((size_t)b * nblk + blockIdx.x) * kAccStride;
+  if (threadIdx.x < NACC) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+    rec[threadIdx.x] = s;
+  }
+  __shared__ unsigned ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(A.counters + b, 1u);
+  __syncthreads();
+  if (ticket != (unsigned)(nblk - 1)) return;
+  // last CTA of image b: fixed-order fp64 sum over the CTA partials (deterministic)
+  __threadfence();
+  __shared__ double tot[kAccStride];
+  if (threadIdx.x < NACC) {
+    const float* base = A.partials + (size_t)b * nblk * kAccStride + threadIdx.x;
+    double s = 0.0;
+    for (int i = 0; i < nblk; ++i) s += (double)__ldcg(base + (size_t)i * kAccStride);
+    tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    finalize_gparams(FID, tot, sc.p, A.gparams + (size_t)b * A.pstride);
+    A.counters[b] = 0u;      // leave the workspace ready for the next launch
+  }
+}
+
+// ---- the CTA body: VEC = 4 pixels / thread via 3 float4, else 1 pixel / thread ---------
+template <int FID, bool BWD, bool HAS_GX, bool VEC>
+__device__ __forceinline__ void filter_body(const FilterArgs& A) {
+  __shared__ FilterConsts sc;
+  __shared__ float red[BWD ? kWarps : 1][kAccStride];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID);
+  __syncthreads();
+
+  const size_t img = (size_t)b * A.P * 3;
+  const float* __restrict__ x = A.x + img;
+  const float* __restrict__ gy = BWD ? A.gy + img : nullptr;
+  float* __restrict__ out = (!BWD || HAS_GX) ? A.out + img : nullptr;
+  const int p0 = blockIdx.x * A.pix_per_block;
+  const int p1 = min(A.P, p0 + A.pix_per_block);
+
+  constexpr int NACC = num_acc(FID);
+  float acc[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+
+  if constexpr (VEC) {
+    const int q1 = p1 >> 2;
+#pragma unroll 2
+    for (int q = (p0 >> 2) + threadIdx.x; q < q1; q += kThreads) {
+      float px[4][3], py[4][3];
+      unpack(load_px4(x, q), px);
+      if constexpr (BWD) {
+        float pg[4][3];
+        unpack(load_px4(gy, q), pg);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) px_bwd<FID, HAS_GX>(px[i], pg[i], py[i], acc, sc);
+        if constexpr (HAS_GX) store_px4(out, q, pack(py));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) px_fwd<FID>(px[i], py[i], sc);
+        store_px4(out, q, pack(py));
+      }
+    }
+  } else {
+    for (int q = p0 + threadIdx.x; q < p1; q += kThreads) {
+      float px[3] = {x[3 * (size_t)q], x[3 * (size_t)q + 1], x[3 * (size_t)q + 2]};
+      float py[3];
+      if constexpr (BWD) {
+        float pg[3] = {gy[3 * (size_t)q], gy[3 * (size_t)q + 1], gy[3 * (size_t)q + 2]};
+        px_bwd<FID, HAS_GX>(px, pg, py, acc, sc);
+      } else {
+        px_fwd<FID>(px, py, sc);
+      }
+      if constexpr (!BWD || HAS_GX) {
+        out[3 * (size_t)q] = py[0];
+        out[3 * (size_t)q + 1] = py[1];
+        out[3 * (size_t)q + 2] = py[2];
+      }
+    }
+  }
+  if constexpr (BWD) reduce_and_finish<FID>(acc, A, sc, red, b, gridDim.x);
+}
+
+// One kernel per filter for uniform steps (tight register allocation per filter) ...
+template <int FID, bool BWD, bool HAS_GX, bool VEC>
+__global__ void __launch_bounds__(kThreads) filter_step_kernel(const FilterArgs A) {
+  filter_body<FID, BWD, HAS_GX, VEC>(A);
+}
+
+// ... and one dispatching kernel for per-image filter ids (agent.py:113-125 selection).
+template <bool BWD, bool HAS_GX, bool VEC>
+__global__ void __launch_bounds__(kThreads) filter_step_select_kernel(const FilterArgs A) {
+  switch (A.ids[blockIdx.y]) {
+    case 0: filter_body<0, BWD, HAS_GX, VEC>(A); break;
+    case 1: filter_body<1, BWD, HAS_GX, VEC>(A); break;
+    case 2: filter_body<2, BWD, HAS_GX, VEC>(A); break;
+    case 3: filter_body<3, BWD, HAS_GX, VEC>(A); break;
+    case 4: filter_body<4, BWD, HAS_GX, VEC>(A); break;
+    case 5: filter_body<5, BWD, HAS_GX, VEC>(A); break;
+    case 6: filter_body<6, BWD, HAS_GX, VEC>(A); break;
+    case 7: filter_body<7, BWD, HAS_GX, VEC>(A); break;
+    default: break;   // id -1 (pdf_sample u==0 quirk, pdf_sample_layer.py:5-10) is handled by the caller
+  }
+}
+
+template <bool BWD, bool HAS_GX, bool VEC>
+static void launch_uniform(int fid, dim3 grid, cudaStream_t st, const FilterArgs& A) {
+  switch (fid) {
+#define EXP_CASE(F) \
+  case F: filter_step_kernel<F, BWD, HAS_GX, VEC><<<grid, kThreads, 0, st>>>(A); break;
+    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7)
+#undef EXP_CASE
+  }
+}
+
+template <bool BWD, bool HAS_GX>
+static void launch_step(bool vec, const int* ids, int fid, dim3 grid, cudaStream_t st, const FilterArgs& A) {
+  if (ids) {
+    if (vec) filter_step_select_kernel<BWD, HAS_GX, true><<<grid, kThreads, 0, st>>>(A);
+    else filter_step_select_kernel<BWD, HAS_GX, false><<<grid, kThreads, 0, st>>>(A);
+  } else {
+    if (vec) launch_uniform<BWD, HAS_GX, true>(fid, grid, st, A);
+    else launch_uniform<BWD, HAS_GX, false>(fid, grid, st, A);
+  }
+}
+
+// ---- filter_param_regressor kernels (one thread per image) -----------------------------
+__device__ __forceinline__ float tanh_range_f(float f, float l, float r, float* dpdf) {
+  // util.py:281-294 with bias == 0 for every range the configs use (initial at mid-range)
+  const float a = tanhf(f);
+  *dpdf = 0.5f * (r - l) * (1.f - a * a);
+  return (a * 0.5f + 0.5f) * (r - l) + l;
+}
+__device__ __forceinline__ float sigmoid_f(float f, float* d) {
+  const float s = 1.f / (1.f + expf(-f));
+  *d = s * (1.f - s);
+  return s;
+}
+
+template <bool BWD>
+__global__ void regress_kernel(const float* __restrict__ logits, int lstride, float* __restrict__ params,
+                               const float* __restrict__ gparams, int pstride, float* __restrict__ glogits,
+                               const int* __restrict__ ids, int uniform_id, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int fid = ids ? ids[b] : uniform_id;
+  const float* f = logits + (size_t)b * lstride;
+  float* po = BWD ? nullptr : params + (size_t)b * pstride;
+  const float* gp = BWD ? gparams + (size_t)b * pstride : nullptr;
+  float* gf = BWD ? glogits + (size_t)b * lstride : nullptr;
+  if (BWD) for (int i = 0; i < lstride; ++i) gf[i] = 0.f;
+  if (fid < 0 || fid >= EXP_NUM_FILTERS) return;
+  float d;
+  switch (fid) {
+    case EXP_FILTER_EXPOSURE: {                      // filters.py:177-179
+      const float p = tanh_range_f(f[0], -3.5f, 3.5f, &d);
+      if (BWD) gf[0] = gp[0] * d; else po[0] = p;
+    } break;
+    case EXP_FILTER_GAMMA: {                         // filters.py:201-203
+      const float lg = 1.0986123f;                   // float32(np.log(3))
+      const float g = expf(tanh_range_f(f[0], -lg, lg, &d));
+      if (BWD) gf[0] = gp[0] * g * d; else po[0] = g;
+    } break;
+    case EXP_FILTER_WB: {                            // filters.py:223-235
+      float s[3], ds[3];
+      for (int c = 0; c < 3; ++c) {
+        const float fm = c == 0 ? 0.f : f[c];        // mask (0,1,1)
+        s[c] = expf(tanh_range_f(fm, -0.5f, 0.5f, &ds[c]));
+        ds[c] = c == 0 ? 0.f : ds[c] * s[c];
+      }
+      const float D = 1e-5f + kLumR * s[0] + kLumG * s[1] + kLumB * s[2];
+      const float inv = 1.0f / D;
+      if (!BWD) {
+        for (int c = 0; c < 3; ++c) po[c] = s[c] * inv;
+      } else {
+        const float dot = (gp[0] * s[0] + gp[1] * s[1] + gp[2] * s[2]) * inv * inv;
+        const float coef[3] = {kLumR, kLumG, kLumB};
+        for (int c = 0; c < 3; ++c) gf[c] = (gp[c] * inv - dot * coef[c]) * ds[c];
+      }
+    } break;
+    case EXP_FILTER_SATPLUS:
+    case EXP_FILTER_WNB: {                           // filters.py:481-482, 435-436
+      const float p = sigmoid_f(f[0], &d);
+      if (BWD) gf[0] = gp[0] * d; else po[0] = p;
+    } break;
+    case EXP_FILTER_CONTRAST: {                      // filters.py:411-413
+      const float a = tanhf(f[0]);
+      if (BWD) gf[0] = gp[0] * (1.f - a * a); else po[0] = a;
+    } break;
+    case EXP_FILTER_TONE:                            // filters.py:306-310
+      for (int i = 0; i < 8; ++i) {
+        const float p = tanh_range_f(f[i], 0.5f, 2.f, &d);
+        if (BWD) gf[i] = gp[i] * d; else po[i] = p;
+      }
+      break;
+    case EXP_FILTER_COLOR:                           // filters.py:256-262
+      for (int i = 0; i < 24; ++i) {
+        const float p = tanh_range_f(f[i], 0.90f, 1.10f, &d);
+        if (BWD) gf[i] = gp[i] * d; else po[i] = p;
+      }
+      break;
+  }
+}
+
+static int check_common(const void* x, const float* params, int pstride, const int* ids, int uniform_id,
+                        int B, int H, int W) {
+  EXP_CHECK_ARG(x && params, "null image or params pointer");
+  EXP_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
+  EXP_CHECK_ARG((long long)H * W < (1ll << 29), "image too large: %dx%d", H, W);
+  EXP_CHECK_ARG(B <= 65535, "B=%d exceeds gridDim.y limit 65535", B);
+  EXP_CHECK_ARG(pstride >= 1, "pstride=%d", pstride);
+  if (!ids) {
+    EXP_CHECK_ARG(uniform_id >= 0 && uniform_id < EXP_NUM_FILTERS, "bad filter id %d", uniform_id);
+    EXP_CHECK_ARG(pstride >= num_params(uniform_id), "pstride=%d < %d params of filter %d", pstride,
+                  num_params(uniform_id), uniform_id);
+  } else {
+    EXP_CHECK_ARG(pstride >= EXP_MAX_FILTER_PARAMS, "per-image ids need pstride >= %d (got %d)",
+                  EXP_MAX_FILTER_PARAMS, pstride);
+  }
+  return EXP_OK;
+}
+
+// decide vector (4 px / thread) vs scalar path
+static int pick_vec(int variant, int P, const void* a, const void* b, const void* c, bool* vec) {
+  const bool ok = (P % 4 == 0) && aligned16(a) && (!b || aligned16(b)) && (!c || aligned16(c));
+  if (variant == EXP_VARIANT_SCALAR) { *vec = false; return EXP_OK; }
+  if (variant == EXP_VARIANT_DIRECT || variant == EXP_VARIANT_TMA) {
+    if (!ok) return set_error(EXP_ERR_ALIGNMENT,
+                              "vector variants need H*W %% 4 == 0 and 16-byte aligned images (H*W=%d)", P);
+    *vec = true;
+    return EXP_OK;
+  }
+  if (variant != EXP_VARIANT_AUTO) return set_error(EXP_ERR_INVALID_ARG, "unknown variant %d", variant);
+  *vec = ok;
+  return EXP_OK;
+}
+
+}  // namespace expo
+
+using namespace expo;
+
+extern "C" {
+
+int exp_version(void) { return 1; }
+const char* exp_last_error(void) { return last_error_buf(); }
+int exp_num_filter_params(int fid) {
+  if (fid < 0 || fid >= EXP_NUM_FILTERS) return set_error(EXP_ERR_INVALID_ARG, "bad filter id %d", fid);
+  return num_params(fid);
+}
+
+int exp_filter_regress_fwd(const float* logits, int lstride, float* params, int pstride, const int* ids,
+                           int uniform_id, int B, void* stream) {
+  EXP_CHECK_ARG(logits && params && B > 0, "null pointer or B=%d", B);
+  const int need = ids ? EXP_MAX_FILTER_PARAMS : exp_num_filter_params(uniform_id);
+  if (need < 0) return need;
+  EXP_CHECK_ARG(lstride >= need && pstride >= need, "strides (%d,%d) < %d", lstride, pstride, need);
+  regress_kernel<false><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      logits, lstride, params, nullptr, pstride, nullptr, ids, uniform_id, B);
+  EXP_CHECK_LAUNCH("exp_filter_regress_fwd");
+  return EXP_OK;
+}
+
+int exp_filter_regress_bwd(const float* logits, int lstride, const float* gparams, int pstride,
+                           float* glogits, const int* ids, int uniform_id, int B, void* stream) {
+  EXP_CHECK_ARG(logits && gparams && glogits && B > 0, "null pointer or B=%d", B);
+  const int need = ids ? EXP_MAX_FILTER_PARAMS : exp_num_filter_params(uniform_id);
+  if (need < 0) return need;
+  EXP_CHECK_ARG(lstride >= need && pstride >= need, "strides (%d,%d) < %d", lstride, pstride, need);
+  regress_kernel<true><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      logits, lstride, nullptr, gparams, pstride, glogits, ids, uniform_id, B);
+  EXP_CHECK_LAUNCH("exp_filter_regress_bwd");
+  return EXP_OK;
+}
+
+int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, const int* ids,
+                   int uniform_id, int B, int H, int W, int variant, void* stream) {
+  int rc = check_common(x, params, pstride, ids, uniform_id, B, H, W);
+  if (rc) return rc;
+  EXP_CHECK_ARG(y, "null output pointer");
+  const int P = H * W;
+  bool vec;
+  rc = pick_vec(variant, P, x, y, nullptr, &vec);
+  if (rc) return rc;
+  FilterArgs A{};
+  A.x = x; A.out = y; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
+  A.pix_per_block = kPixPerBlockFwd;
+  dim3 grid((P + kPixPerBlockFwd - 1) / kPixPerBlockFwd, B);
+  launch_step<false, false>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);
+  EXP_CHECK_LAUNCH("exp_filter_fwd");
+  return EXP_OK;
+}
+
+size_t exp_filter_bwd_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  const size_t nblk = ((size_t)H * W + kPixPerBlockBwd - 1) / kPixPerBlockBwd;
+  return (size_t)B * nblk * kAccStride * sizeof(float) + (size_t)B * sizeof(unsigned);
+}
+
+int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, const float* params,
+                   int pstride, const int* ids, int uniform_id, int B, int H, int W, void* workspace,
+                   size_t workspace_bytes, int variant, void* stream) {
+  int rc = check_common(x, params, pstride, ids, uniform_id, B, H, W);
+  if (rc) return rc;
+  EXP_CHECK_ARG(gy && gparams && workspace, "null gy / gparams / workspace pointer");
+  const size_t need = exp_filter_bwd_workspace_bytes(B, H, W);
+  if (workspace_bytes < need)
+    return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  if (!aligned16(workspace)) return set_error(EXP_ERR_ALIGNMENT, "workspace must be 16-byte aligned");
+  const int P = H * W;
+  bool vec;
+  rc = pick_vec(variant, P, x, gy, gx, &vec);
+  if (rc) return rc;
+  const int nblk = (P + kPixPerBlockBwd - 1) / kPixPerBlockBwd;
+  FilterArgs A{};
+  A.x = x; A.gy = gy; A.out = gx; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
+  A.pix_per_block = kPixPerBlockBwd;
+  A.partials = reinterpret_cast<float*>(workspace);
+  A.counters = reinterpret_cast<unsigned*>(A.partials + (size_t)B * nblk * kAccStride);
+  A.gparams = gparams;
+  dim3 grid(nblk, B);
+  if (gx) launch_step<true, true>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);
+  else launch_step<true, false>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);
+  EXP_CHECK_LAUNCH("exp_filter_bwd");
+  return EXP_OK;
+}
+
+}  // extern "C"

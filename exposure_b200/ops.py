@@ -1,0 +1,174 @@
+"""torch-tensor front end of the C ABI (device pointers, current stream, autograd glue).
+
+PyTorch here is plumbing only: it owns device memory and streams.  Every function enqueues
+exactly the CUDA kernels of exposure_b200/csrc on torch's current stream."""
+import torch
+
+from . import _cabi
+from ._cabi import MAX_FILTER_PARAMS, VARIANT_AUTO
+
+NUM_PARAMS = (1, 1, 3, 1, 8, 1, 1, 24)      # cfg.filters order (config_example.py:22-25)
+PSTRIDE = MAX_FILTER_PARAMS
+
+# running count of kernels launched through this module (bench.py reports it)
+launch_count = 0
+# when set to a list, every filter-step launch appends (name, algorithmic_bytes, ev0, ev1)
+# with CUDA events recorded on the launching stream (bench.py's live roofline measurement)
+event_log = None
+FILTER_NAMES = ("exposure", "gamma", "wb", "satplus", "tone", "contrast", "wnb", "color")
+
+
+class _Timed:
+  """Brackets one launch with CUDA events on the current stream when event_log is active."""
+
+  def __init__(self, kind, ids, nbytes):
+    self.on = event_log is not None
+    if self.on:
+      self.name = "%s_%s" % (kind, FILTER_NAMES[ids] if isinstance(ids, int) else "select")
+      self.nbytes = nbytes
+      self.e0 = torch.cuda.Event(enable_timing=True)
+      self.e1 = torch.cuda.Event(enable_timing=True)
+
+  def __enter__(self):
+    if self.on:
+      self.e0.record()
+
+  def __exit__(self, *a):
+    if self.on:
+      self.e1.record()
+      event_log.append((self.name, self.nbytes, self.e0, self.e1))
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_img(t, name):
+  if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 4 and t.shape[3] == 3 and t.is_contiguous()):
+    raise ValueError("%s must be a contiguous CUDA float32 NHWC [B,H,W,3] tensor, got %s %s %s" %
+                     (name, tuple(t.shape), t.dtype, t.device))
+
+
+def _ids_arg(ids, B):
+  """ids: int (uniform filter id) or CUDA int32 tensor [B] -> (device ptr or None, uniform id)."""
+  if isinstance(ids, int):
+    return None, ids
+  if not (ids.is_cuda and ids.dtype == torch.int32 and ids.shape == (B,) and ids.is_contiguous()):
+    raise ValueError("ids must be an int or a contiguous CUDA int32 tensor [B]")
+  return ids.data_ptr(), 0
+
+
+def _chk_mat(t, B, name):
+  if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[0] == B and t.stride(1) == 1):
+    raise ValueError("%s must be CUDA float32 [B, n] with unit inner stride" % name)
+  return t.stride(0)
+
+
+def filter_regress_fwd(logits, ids):
+  """filter_param_regressor: logits [B, >=n] -> params [B, 24] (entries >= n are 0)."""
+  global launch_count
+  B = logits.shape[0]
+  ls = _chk_mat(logits, B, "logits")
+  params = torch.zeros(B, PSTRIDE, device=logits.device, dtype=torch.float32)
+  idp, uid = _ids_arg(ids, B)
+  _cabi.check(_cabi.lib().exp_filter_regress_fwd(logits.data_ptr(), ls, params.data_ptr(), PSTRIDE, idp, uid, B,
+                                                 _stream()), "exp_filter_regress_fwd")
+  launch_count += 1
+  return params
+
+
+def filter_regress_bwd(logits, gparams, ids):
+  global launch_count
+  B = logits.shape[0]
+  ls = _chk_mat(logits, B, "logits")
+  ps = _chk_mat(gparams, B, "gparams")
+  if not logits.is_contiguous():
+    raise ValueError("logits must be contiguous")
+  glogits = torch.empty_like(logits)
+  idp, uid = _ids_arg(ids, B)
+  _cabi.check(_cabi.lib().exp_filter_regress_bwd(logits.data_ptr(), ls, gparams.data_ptr(), ps, glogits.data_ptr(),
+                                                 idp, uid, B, _stream()), "exp_filter_regress_bwd")
+  launch_count += 1
+  return glogits
+
+
+def filter_fwd(x, params, ids, out=None, variant=VARIANT_AUTO):
+  """y = process_{ids}(x, params).  x: [B,H,W,3]; params: [B, >=n]; ids: int or int32 [B]."""
+  global launch_count
+  _chk_img(x, "x")
+  B, H, W, _ = x.shape
+  ps = _chk_mat(params, B, "params")
+  y = torch.empty_like(x) if out is None else out
+  idp, uid = _ids_arg(ids, B)
+  with _Timed("filter_fwd", ids, B * H * W * 24):
+    _cabi.check(_cabi.lib().exp_filter_fwd(x.data_ptr(), y.data_ptr(), params.data_ptr(), ps, idp, uid, B, H, W,
+                                           variant, _stream()), "exp_filter_fwd")
+  launch_count += 1
+  return y
+
+
+_workspaces = {}
+
+
+def _workspace(dev, nbytes):
+  """Zero-initialised, self-cleaning workspace per (device, stream)."""
+  key = (dev, torch.cuda.current_stream().cuda_stream)
+  ws = _workspaces.get(key)
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=dev)
+    _workspaces[key] = ws
+  return ws
+
+
+def filter_bwd(x, gy, params, ids, need_gx=True, gx_out=None, variant=VARIANT_AUTO):
+  """Returns (gx or None, gparams [B,24]).  Deterministic parameter-gradient reduction."""
+  global launch_count
+  _chk_img(x, "x")
+  _chk_img(gy, "gy")
+  B, H, W, _ = x.shape
+  ps = _chk_mat(params, B, "params")
+  gx = (torch.empty_like(x) if gx_out is None else gx_out) if need_gx else None
+  gparams = torch.zeros(B, PSTRIDE, device=x.device, dtype=torch.float32)
+  l = _cabi.lib()
+  nbytes = l.exp_filter_bwd_workspace_bytes(B, H, W)
+  ws = _workspace(x.device, nbytes)
+  idp, uid = _ids_arg(ids, B)
+  with _Timed("filter_bwd" if need_gx else "filter_bwd_paramonly", ids, B * H * W * (36 if need_gx else 24)):
+    _cabi.check(l.exp_filter_bwd(x.data_ptr(), gy.data_ptr(), gx.data_ptr() if need_gx else None,
+                                 gparams.data_ptr(), params.data_ptr(), ps, idp, uid, B, H, W, ws.data_ptr(),
+                                 ws.numel(), variant, _stream()), "exp_filter_bwd")
+  launch_count += 1
+  return gx, gparams
+
+
+class FilterProcessFn(torch.autograd.Function):
+  """autograd node for one filter step: (x, params) -> y, backward through exp_filter_bwd."""
+
+  @staticmethod
+  def forward(ctx, x, params, ids):
+    ctx.ids = ids
+    ctx.save_for_backward(x, params)
+    return filter_fwd(x.contiguous(), params, ids)
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, params = ctx.saved_tensors
+    need_gx = ctx.needs_input_grad[0]
+    gx, gparams = filter_bwd(x.contiguous(), gy.contiguous(), params, ctx.ids, need_gx=need_gx)
+    return gx, gparams[:, :params.shape[1]] if params.shape[1] != PSTRIDE else gparams, None
+
+
+class FilterRegressFn(torch.autograd.Function):
+  """autograd node for filter_param_regressor: logits -> params[B,24]."""
+
+  @staticmethod
+  def forward(ctx, logits, ids):
+    ctx.ids = ids
+    logits = logits.contiguous()
+    ctx.save_for_backward(logits)
+    return filter_regress_fwd(logits, ids)
+
+  @staticmethod
+  def backward(ctx, gparams):
+    (logits,) = ctx.saved_tensors
+    return filter_regress_bwd(logits, gparams.contiguous(), ctx.ids), None

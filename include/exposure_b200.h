@@ -1,0 +1,114 @@
+/*
+ * exposure_b200 -- C ABI of the B200-native Exposure hot path.
+ *
+ * The reference (yuanming-hu/exposure @ 7bb838a) has NO native code and NO FFI: every op
+ * below replaces a chain of stock TensorFlow-1.6 kernels that the Python graph in
+ * filters.py / critics.py / agent.py / net.py lowers to.  Each entry point cites the
+ * reference lines whose arithmetic it replaces.  The reference-side binding a maintainer
+ * would add (a ctypes stub inside Filter.process etc.) is shown in INTEGRATION.md.
+ *
+ * Conventions (tested in tests/test_cabi_*.py):
+ *   - plain pointers and sizes only; all `float*` / `int*` are DEVICE pointers unless
+ *     the name ends in `_host`;
+ *   - the caller owns every buffer; the library never allocates, frees or synchronises;
+ *     all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream);
+ *   - images are NHWC contiguous fp32 `[B, H, W, 3]` (replay_memory.py:16-20 layout);
+ *   - return value: 0 = EXP_OK, negative = error (see enum); exp_last_error() returns a
+ *     thread-local human readable message.  No exceptions cross the ABI;
+ *   - outputs are OVERWRITTEN, never accumulated into;
+ *   - re-entrant / thread-safe given distinct streams and distinct workspaces.
+ */
+#ifndef EXPOSURE_B200_H_
+#define EXPOSURE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  EXP_OK = 0,
+  EXP_ERR_INVALID_ARG = -1, /* null pointer, bad size, bad filter id                */
+  EXP_ERR_ALIGNMENT = -2,   /* pointer not aligned as documented                    */
+  EXP_ERR_WORKSPACE = -3,   /* workspace too small                                  */
+  EXP_ERR_CUDA = -4,        /* a CUDA runtime call failed (message has the reason)  */
+  EXP_ERR_UNSUPPORTED = -5  /* shape outside what the kernel family supports        */
+};
+
+/* Filter ids = index in cfg.filters (config_example.py:22-25). */
+enum {
+  EXP_FILTER_EXPOSURE = 0,   /* ExposureFilter              filters.py:170-182 */
+  EXP_FILTER_GAMMA = 1,      /* GammaFilter                 filters.py:194-206 */
+  EXP_FILTER_WB = 2,         /* ImprovedWhiteBalanceFilter  filters.py:215-238 */
+  EXP_FILTER_SATPLUS = 3,    /* SaturationPlusFilter        filters.py:474-498 */
+  EXP_FILTER_TONE = 4,       /* ToneFilter                  filters.py:298-322 */
+  EXP_FILTER_CONTRAST = 5,   /* ContrastFilter              filters.py:404-419 */
+  EXP_FILTER_WNB = 6,        /* WNBFilter                   filters.py:428-440 */
+  EXP_FILTER_COLOR = 7,      /* ColorFilter                 filters.py:247-273 */
+  EXP_NUM_FILTERS = 8
+};
+#define EXP_MAX_FILTER_PARAMS 24 /* ColorFilter: 3 channels x cfg.curve_steps(8) */
+
+/* Kernel variants of the per-pixel filter step (all produce identical results up to the
+ * documented tolerance; AUTO picks the fastest legal one for the shape). */
+enum {
+  EXP_VARIANT_AUTO = 0,
+  EXP_VARIANT_DIRECT = 1, /* register-resident float4 loads/stores                     */
+  EXP_VARIANT_TMA = 2,    /* cp.async.bulk (TMA) -> shared-memory ring -> bulk store    */
+  EXP_VARIANT_SCALAR = 3  /* one pixel per thread; any H*W, any 4-byte alignment        */
+};
+
+/* ---- library ------------------------------------------------------------------- */
+int exp_version(void);               /* ABI version, currently 1                       */
+const char* exp_last_error(void);    /* thread-local message of the last failure       */
+int exp_num_filter_params(int filter_id); /* n of the table above, or EXP_ERR_INVALID_ARG */
+
+/* ---- filter_param_regressor (per image, tiny) -------------------------------------
+ * logits [B, lstride] -> params [B, pstride] for the filter given by ids[b] (device
+ * int32 [B]) or, when ids == NULL, by `uniform_id` for every image.
+ * Replaces: ExposureFilter/GammaFilter/.../ColorFilter.filter_param_regressor
+ * (filters.py:177-179, 201-203, 223-235, 256-262, 306-310, 411-413, 435-436, 481-482)
+ * and util.tanh_range (util.py:281-294). */
+int exp_filter_regress_fwd(const float* logits, int lstride, float* params, int pstride,
+                           const int* ids, int uniform_id, int B, void* stream);
+/* glogits [B, lstride] = d<gparams, params>/dlogits (entries >= n are written as 0). */
+int exp_filter_regress_bwd(const float* logits, int lstride, const float* gparams, int pstride,
+                           float* glogits, const int* ids, int uniform_id, int B, void* stream);
+
+/* ---- Filter.process forward (the hot path) -----------------------------------------
+ * y[b] = process_{id(b)}(x[b], params[b]) ; with cfg.masking == False this is exactly
+ * Filter.apply's low_res_output / high_res_output (filters.py:62-99: lerp with
+ * mask == ones(1,1,1,1)).  Also replaces the stack / one_hot / reduce_sum select of
+ * agent.py:77,118-129 (only the selected filter is evaluated per image).
+ * x, y: [B,H,W,3] fp32, 16-byte aligned for the DIRECT/TMA variants (else SCALAR).
+ * x == y (in place) is allowed.  Algorithmic HBM traffic: 24 B / pixel. */
+int exp_filter_fwd(const float* x, float* y, const float* params, int pstride,
+                   const int* ids, int uniform_id, int B, int H, int W, int variant,
+                   void* stream);
+
+/* Bytes of device workspace exp_filter_bwd needs for this shape (partial sums of the
+ * per-image parameter gradients + one ticket counter per image).  The workspace must be
+ * zero-filled once before first use; the kernel leaves it zeroed for the next call. */
+size_t exp_filter_bwd_workspace_bytes(int B, int H, int W);
+
+/* ---- Filter.process backward ----------------------------------------------------------
+ * Given gy = dL/dy, computes
+ *   gparams[b, 0:n] = dL/dparams[b]   (what tf.gradients builds for filters.py process();
+ *                                      deterministic two-stage reduction, fixed order)
+ *   gx = dL/dx                        (nullable; needed only for the N-step chain of
+ *                                      BASELINE.json -- the reference never differentiates
+ *                                      w.r.t. the image, replay_memory.py:16 placeholder).
+ * Outputs are recomputed from x, not re-read.  gx may alias gy (in place).
+ * Algorithmic HBM traffic: 36 B / pixel with gx, 24 B / pixel without. */
+int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams,
+                   const float* params, int pstride, const int* ids, int uniform_id,
+                   int B, int H, int W, void* workspace, size_t workspace_bytes, int variant,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXPOSURE_B200_H_ */

@@ -1,0 +1,220 @@
+"""GPU parity: the CUDA filter step (through the C ABI) against the CPU oracle.
+
+Tolerances (stated once, used everywhere below):
+  forward pixels   |y - ref32| <= 1e-5 * max(|ref32|, 1e-4)        (north_star: <=1e-5 rel)
+     ContrastFilter additionally gets the propagated effect of a 2-ulp difference in
+     cosf(pi*l) between host and device libm, because the reference formula
+     -cos(pi l)*0.5+0.5 cancels catastrophically for dark pixels; the CUDA
+     result must also be no farther from the fp64 oracle than 4x the fp32 oracle is.
+  image gradient   |gx - ref64| <= 1e-4 * max(|ref64|, 1e-3 * max|ref64|)
+  param gradient   |gp - ref64| <= 1e-4 * max(|ref64|, 1e-3 * sum|terms|)
+ref32 / ref64 = oracle/filters.py in float32 / float64.  PARITY UNPINNED (see oracle/)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import filters as F
+
+pytestmark = pytest.mark.gpu
+ALL = list(range(8))
+SHAPES = [(4, 64, 64), (2, 33, 31), (3, 1, 1), (1, 7, 5), (2, 128, 96), (5, 2, 2)]
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+  assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+  from exposure_b200 import ops as o
+  return o
+
+
+def _fwd_tol(fid, x, p, ref32):
+  tol = 1e-5 * ref32.abs().clamp_min(1e-4)
+  if fid == F.CT:
+    lum = F.rgb2lum(x).clamp(0, 1)
+    tol = tol + p.abs()[:, :, None, None] * x.abs() / (lum + 1e-6) * (2 * 2.0 ** -24)
+  return tol
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("fid", ALL)
+def test_forward_matches_oracle(ops, fid, shape):
+  B, H, W = shape
+  x = F.synth_images(B, H, W, seed=11 + fid)
+  lg = F.synth_logits(fid, B)
+  p32 = F.regress(fid, lg)
+  ref32 = F.process(fid, x, p32)
+  ref64 = F.process(fid, x.double(), F.regress(fid, lg.double()))
+  params = ops.filter_regress_fwd(lg.cuda(), fid)
+  assert torch.allclose(params[:, :F.NUM_PARAMS[fid]].cpu(), p32, rtol=2e-6, atol=1e-7)
+  y = ops.filter_fwd(x.cuda(), params, fid).cpu()
+  err = (y - ref32).abs()
+  tol = _fwd_tol(fid, x, p32, ref32)
+  assert (err <= tol).all(), "fid %d: max err/tol %.3g" % (fid, float((err / tol).max()))
+  e_cuda = (y.double() - ref64).abs()
+  e_ref = (ref32.double() - ref64).abs()
+  assert (e_cuda <= 4 * e_ref + tol.double()).all()
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("fid", ALL)
+def test_backward_matches_oracle(ops, fid, shape):
+  B, H, W = shape
+  x = F.synth_images(B, H, W, seed=23 + fid)
+  lg = F.synth_logits(fid, B)
+  g = torch.Generator().manual_seed(5)
+  gy = torch.randn(B, H, W, 3, generator=g)
+  p32 = F.regress(fid, lg)
+  gx64, gp64 = F.process_bwd_analytic(fid, x.double(), p32.double(), gy.double())
+  params = torch.zeros(B, 24)
+  params[:, :p32.shape[1]] = p32
+  gx, gp = ops.filter_bwd(x.cuda(), gy.cuda(), params.cuda(), fid)
+  gx, gp = gx.cpu().double(), gp.cpu().double()[:, :F.NUM_PARAMS[fid]]
+  tolx = 1e-4 * gx64.abs().clamp_min(1e-3 * float(gx64.abs().max()) + 1e-30)
+  assert ((gx - gx64).abs() <= tolx).all(), "gx fid %d: %.3g" % (fid, float(((gx - gx64).abs() / tolx).max()))
+  # scale of the summed terms (a cancelling sum cannot be more accurate than its terms)
+  _, gp_abs = F.process_bwd_analytic(fid, x.double(), p32.double(), gy.double().abs())
+  scale = gp_abs.abs().max(dim=1, keepdim=True).values
+  tolp = 1e-4 * torch.maximum(gp64.abs(), 1e-3 * scale + 1e-30)
+  assert ((gp - gp64).abs() <= tolp).all(), "gp fid %d: %.3g" % (fid, float(((gp - gp64).abs() / tolp).max()))
+  # param-gradient-only backward (the reference's actual training need) gives the same gparams
+  _, gp2 = ops.filter_bwd(x.cuda(), gy.cuda(), params.cuda(), fid, need_gx=False)
+  assert torch.equal(gp2.cpu().double()[:, :F.NUM_PARAMS[fid]], gp)
+
+
+@pytest.mark.parametrize("fid", ALL)
+def test_regressor_backward(ops, fid):
+  B = 9
+  lg = F.synth_logits(fid, B, seed=99)
+  gp = torch.randn(B, 24)
+  gp[:, F.NUM_PARAMS[fid]:] = 0
+  ref = F.regress_bwd(fid, lg.double(), gp[:, :F.NUM_PARAMS[fid]].double())
+  lgp = torch.zeros(B, 24)
+  lgp[:, :F.NUM_PARAMS[fid]] = lg
+  out = ops.filter_regress_bwd(lgp.cuda(), gp.cuda(), fid).cpu().double()
+  assert torch.allclose(out[:, :F.NUM_PARAMS[fid]], ref, rtol=1e-4, atol=1e-7)
+  assert (out[:, F.NUM_PARAMS[fid]:] == 0).all()
+
+
+def test_per_image_filter_ids(ops):
+  """agent.py:113-125: each image gets its own selected filter (ids tensor)."""
+  B, H, W = 16, 32, 32
+  x = F.synth_images(B, H, W, seed=3)
+  ids = torch.arange(B, dtype=torch.int32) % 8
+  lg = torch.randn(B, 24, generator=torch.Generator().manual_seed(1))
+  params = ops.filter_regress_fwd(lg.cuda(), ids.cuda())
+  y = ops.filter_fwd(x.cuda(), params, ids.cuda()).cpu()
+  gy = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(2))
+  gx, gp = ops.filter_bwd(x.cuda(), gy.cuda(), params, ids.cuda())
+  for b in range(B):
+    fid = int(ids[b])
+    n = F.NUM_PARAMS[fid]
+    # uniform-id launch on the single image must agree bit for bit with the select kernel
+    pu = ops.filter_regress_fwd(lg[b:b + 1].cuda(), fid)
+    yu = ops.filter_fwd(x[b:b + 1].cuda(), pu, fid).cpu()
+    assert torch.equal(yu[0], y[b]), (b, fid)
+    gxu, gpu = ops.filter_bwd(x[b:b + 1].cuda(), gy[b:b + 1].cuda(), pu, fid)
+    assert torch.equal(gxu.cpu()[0], gx.cpu()[b]) and torch.equal(gpu.cpu()[0, :n], gp.cpu()[b, :n])
+    ref = F.process(fid, x[b:b + 1], F.regress(fid, lg[b:b + 1, :n]))
+    assert torch.allclose(y[b], ref[0], rtol=1e-5, atol=1e-7) or fid == F.CT
+
+
+def test_scalar_and_vector_variants_agree(ops):
+  from exposure_b200 import _cabi
+  B, H, W = 3, 40, 36
+  x = F.synth_images(B, H, W, seed=8).cuda()
+  gy = torch.randn(B, H, W, 3, device="cuda")
+  for fid in ALL:
+    params = ops.filter_regress_fwd(F.synth_logits(fid, B).cuda(), fid)
+    yv = ops.filter_fwd(x, params, fid, variant=_cabi.VARIANT_DIRECT)
+    ys = ops.filter_fwd(x, params, fid, variant=_cabi.VARIANT_SCALAR)
+    assert torch.equal(yv, ys), fid
+    gxv, gpv = ops.filter_bwd(x, gy, params, fid, variant=_cabi.VARIANT_DIRECT)
+    gxs, gps = ops.filter_bwd(x, gy, params, fid, variant=_cabi.VARIANT_SCALAR)
+    assert torch.equal(gxv, gxs), fid
+    assert torch.allclose(gpv, gps, rtol=1e-5, atol=1e-6), fid
+
+
+def test_in_place_and_determinism(ops):
+  B, H, W = 2, 64, 64
+  x = F.synth_images(B, H, W, seed=4).cuda()
+  gy = torch.randn(B, H, W, 3, device="cuda")
+  for fid in ALL:
+    params = ops.filter_regress_fwd(F.synth_logits(fid, B).cuda(), fid)
+    y = ops.filter_fwd(x, params, fid)
+    xi = x.clone()
+    ops.filter_fwd(xi, params, fid, out=xi)
+    assert torch.equal(xi, y)
+    gx1, gp1 = ops.filter_bwd(x, gy, params, fid)
+    gx2, gp2 = ops.filter_bwd(x, gy, params, fid)
+    assert torch.equal(gx1, gx2) and torch.equal(gp1, gp2)      # deterministic reduction
+    gi = gy.clone()
+    ops.filter_bwd(x, gi, params, fid, gx_out=gi)
+    assert torch.equal(gi, gx1)
+
+
+def test_chain_fwd_bwd_matches_oracle(ops):
+  """BASELINE configs[1] at oracle size: E,G,W,S+,T,Ct,BW,C applied in sequence, fwd+bwd."""
+  ids = [F.E, F.G, F.W, F.SP, F.T, F.CT, F.BW, F.C]
+  B, H, W = 4, 64, 64
+  x = F.synth_images(B, H, W, seed=77)
+  lgs = [F.synth_logits(f, B, seed=1000) * 0.5 for f in ids]
+  gout = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(9))
+  y64, gx64, glg64 = F.chain_fwd_bwd(ids, x.double(), [l.double() for l in lgs], gout.double())
+  y32 = F.chain_fwd(ids, x, lgs)[-1]
+  from exposure_b200.chain import FilterChain
+  chain = FilterChain(ids)
+  lg_dev = [l.cuda() for l in lgs]
+  y = chain.forward(x.cuda(), lg_dev)
+  gx, glg = chain.backward(gout.cuda())
+  y, gx = y.cpu(), gx.cpu().double()
+  # errors compound over 8 steps (pow/cos amplification): 5e-5 on the final pixels
+  assert ((y - y32).abs() <= 5e-5 * y32.abs().clamp_min(1e-3)).all(), float(((y - y32).abs() / y32.abs().clamp_min(1e-3)).max())
+  assert ((gx - gx64).abs() <= 1e-3 * gx64.abs().clamp_min(1e-3 * float(gx64.abs().max()))).all()
+  for k, (a, b) in enumerate(zip(glg, glg64)):
+    a = a.cpu().double()[:, :b.shape[1]]
+    assert torch.allclose(a, b, rtol=2e-3, atol=2e-3 * float(b.abs().max()) + 1e-12), (k, (a - b).abs().max(), b.abs().max())
+
+
+def test_full_size_properties(ops):
+  """BASELINE configs[1] full size (64x512x512x3): size-independent properties."""
+  B, H, W = 64, 512, 512
+  g = torch.Generator(device="cuda").manual_seed(1)
+  x = torch.exp(torch.randn(B, H, W, 3, device="cuda", generator=g) - 3.2).clamp_(0, 4)
+  z = lambda fid: ops.filter_regress_fwd(torch.zeros(B, 24, device="cuda"), fid)
+  # identities at default parameters
+  assert torch.equal(ops.filter_fwd(x, z(F.E), F.E), x)
+  assert torch.equal(ops.filter_fwd(x, z(F.CT), F.CT), x)
+  assert torch.allclose(ops.filter_fwd(x, z(F.T), F.T), x.clamp(0, 1), rtol=0, atol=2e-7)
+  assert torch.allclose(ops.filter_fwd(x, z(F.C), F.C), x.clamp(0, 1), rtol=0, atol=2e-7)
+  # exact homogeneity of the linear filters under power-of-two scaling
+  for fid in (F.E, F.W, F.BW):
+    p = ops.filter_regress_fwd(torch.randn(B, 24, device="cuda", generator=g), fid)
+    assert torch.equal(ops.filter_fwd(x * 0.5, p, fid), ops.filter_fwd(x, p, fid) * 0.5)
+  # exposure round trip E(+p) then E(-p)
+  lg = torch.randn(B, 24, device="cuda", generator=g)
+  p = ops.filter_regress_fwd(lg, F.E)
+  back = ops.filter_fwd(ops.filter_fwd(x, p, F.E), -p, F.E)
+  assert torch.allclose(back, x, rtol=1e-6, atol=0)
+  # parameter-gradient reduction: whole image == sum of its two halves; deterministic
+  gy = torch.randn(B, H, W, 3, device="cuda", generator=g)
+  for fid in (F.E, F.T, F.C):
+    p = ops.filter_regress_fwd(torch.randn(B, 24, device="cuda", generator=g), fid)
+    _, gp = ops.filter_bwd(x, gy, p, fid, need_gx=False)
+    _, gpa = ops.filter_bwd(x[:, :256].contiguous(), gy[:, :256].contiguous(), p, fid, need_gx=False)
+    _, gpb = ops.filter_bwd(x[:, 256:].contiguous(), gy[:, 256:].contiguous(), p, fid, need_gx=False)
+    if fid == F.E:
+      assert torch.allclose(gp, gpa + gpb, rtol=1e-4, atol=1e-3)
+    _, gp_again = ops.filter_bwd(x, gy, p, fid, need_gx=False)
+    assert torch.equal(gp, gp_again)
+
+
+def test_errors_are_loud(ops):
+  from exposure_b200._cabi import ExposureLibError
+  x = torch.zeros(1, 3, 3, 3, device="cuda")
+  p = torch.zeros(1, 24, device="cuda")
+  with pytest.raises(ExposureLibError):
+    ops.filter_fwd(x, p, 11)
+  with pytest.raises(ExposureLibError):
+    ops.filter_fwd(x, p, 0, variant=1)       # DIRECT needs H*W % 4 == 0
+  with pytest.raises(ValueError):
+    ops.filter_fwd(x.cpu(), p, 0)            # no CPU fallback

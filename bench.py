@@ -44,7 +44,7 @@ def parse_args():
   ap.add_argument("--workload", default="chain8", choices=["chain8"])
   ap.add_argument("--batch", type=int, default=64, help="images per GPU")
   ap.add_argument("--size", type=int, default=512)
-  ap.add_argument("--variant", type=int, default=0)
+  ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 tma (exposure_b200.h)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   return ap.parse_args()
 

@@ -65,11 +65,13 @@ __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 
 // ---- monotone piecewise-linear curve (ToneFilter / ColorFilter) ---------------------
 // y = (L/S) * sum_i clip(x - i/L, 0, 1/L) * t_i ; evaluated through the prefix sums:
 // segment k = floor(L * clamp(x,0,1)), y = (cum[k] + (xc - k/L) * t_k) * (L/S).
-__device__ __forceinline__ float curve_eval(float x, const FilterConsts& sc, int row) {
-  const float xc = clamp01(x);
+// `k` is returned for the backward's slope lookup.
+__device__ __forceinline__ float curve_eval(float x, const FilterConsts& sc, int row, int* kout = nullptr) {
+  const float xc = __saturatef(x);
   const int k = min((int)(xc * (float)kCurveSteps), kCurveSteps - 1);
   const float frac = xc - (float)k * kInvL;                 // exact (Sterbenz)
   const float tot = __fadd_rn(sc.cum[row][k], __fmul_rn(frac, sc.p[row * kCurveSteps + k]));
+  if (kout) *kout = k;
   return __fmul_rn(tot, sc.scale[row]);
 }
 
@@ -239,22 +241,29 @@ __device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3]
     }
   } else if constexpr (FID == EXP_FILTER_TONE || FID == EXP_FILTER_COLOR) {
     // y = (L/S) sum_i clip_i(x) t_i ;  dy/dt_j = (L clip_j - y)/S ;  dy/dx = (L/S) sum_{pass} t_j
-    // acc[row*9 + j] = sum gy clip_j ; acc[row*9 + 8] = sum gy y    (row = 0 for Tone)
+    // acc[row*9 + j] = sum gy * (L clip_j) with L clip_j = sat(L x - j)  (one FADD.SAT + one FFMA;
+    // scaling by L = 8 is exact so this equals clamp(x - j/L, 0, 1/L) * L bit for bit);
+    // acc[row*9 + 8] = sum gy y                                  (row = 0 for Tone)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int row = (FID == EXP_FILTER_COLOR) ? c : 0;
       float* a = acc + row * (kCurveSteps + 1);
-      const float y = curve_eval(x[c], sc, row);
+      int k;
+      const float y = curve_eval(x[c], sc, row, &k);
       a[kCurveSteps] = fmaf(gy[c], y, a[kCurveSteps]);
-      float slope = 0.f;
+      const float xs = x[c] * (float)kCurveSteps;
 #pragma unroll
-      for (int j = 0; j < kCurveSteps; ++j) {
-        const float v = x[c] - (float)j * kInvL;
-        const float cj = fminf(fmaxf(v, 0.f), kInvL);
-        a[j] = fmaf(gy[c], cj, a[j]);
-        if (HAS_GX) slope += (v >= 0.f && v <= kInvL) ? sc.p[row * kCurveSteps + j] : 0.f;
+      for (int j = 0; j < kCurveSteps; ++j) a[j] = fmaf(gy[c], __saturatef(xs - (float)j), a[j]);
+      if (HAS_GX) {
+        // TF clip_by_value passes the gradient on ties (x - j/L == 0 or == 1/L): at an exact
+        // interior knot both neighbouring segments pass.
+        float slope = 0.f;
+        if (x[c] >= 0.f && x[c] <= 1.f) {
+          slope = sc.p[row * kCurveSteps + k];
+          if (xs == (float)k && k >= 1) slope += sc.p[row * kCurveSteps + k - 1];
+        }
+        gx[c] = gy[c] * slope * sc.scale[row];
       }
-      if (HAS_GX) gx[c] = gy[c] * slope * sc.scale[row];
     }
   } else if constexpr (FID == EXP_FILTER_CONTRAST) {
     // y_c = (1-p) x_c + p x_c w(l),  w = cl/(l+eps),  cl = sin^2(pi l / 2)  (== -cos(pi l)/2 + 1/2)
@@ -304,8 +313,8 @@ __device__ __forceinline__ void finalize_gparams(int fid, const double* sum, con
       for (int i = 0; i < kCurveSteps; ++i) s = __fadd_rn(s, p[r * kCurveSteps + i]);
       const double S = (double)__fadd_rn(s, 1e-30f);
       const double Bs = sum[r * (kCurveSteps + 1) + kCurveSteps];
-      for (int j = 0; j < kCurveSteps; ++j)
-        out[r * kCurveSteps + j] = (float)(((double)kCurveSteps * sum[r * (kCurveSteps + 1) + j] - Bs) / S);
+      for (int j = 0; j < kCurveSteps; ++j)      // sum[j] already carries the factor L
+        out[r * kCurveSteps + j] = (float)((sum[r * (kCurveSteps + 1) + j] - Bs) / S);
     }
   } else {
     const int n = num_params(fid);

@@ -13,8 +13,14 @@ namespace expo {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kPixPerBlockFwd = 4096;    // 256 threads x 4 pixels x 4 iterations
-constexpr int kPixPerBlockBwd = 8192;    // fewer, fatter CTAs: one partial record per CTA
+constexpr int kPixPerBlockFwd = 2048;    // 256 threads x 4 pixels x 2 iterations
+constexpr int kPixPerBlockBwd = 4096;    // fatter CTAs: one partial record per CTA
+// Workspace layout: [kMaxImages ticket counters][partial-sum records].  The counter block has
+// a FIXED size and position so that records of an earlier, differently shaped launch can
+// never be mistaken for tickets.
+constexpr int kMaxImages = 65536;
+constexpr size_t kCounterBytes = (size_t)kMaxImages * sizeof(unsigned);
+constexpr int kMaxPersistentCtas = 4096;  // upper bound on the TMA variant's grid
 
 static thread_local char g_err[512] = "";
 char* last_error_buf() { return g_err; }
@@ -69,6 +75,10 @@ __device__ __forceinline__ Px4 pack(const float (&px)[4][3]) {
   v.c = make_float4(px[2][2], px[3][0], px[3][1], px[3][2]);
   return v;
 }
+
+}  // namespace expo
+#include "filters_tma.cuh"
+namespace expo {
 
 // ---- per-CTA reduction of the parameter-gradient accumulators + last-CTA finish --------
 template <int FID>
@@ -291,6 +301,53 @@ __global__ void regress_kernel(const float* __restrict__ logits, int lstride, fl
   }
 }
 
+// ---- host side of the persistent TMA variant ---------------------------------------------
+template <int FID, bool BWD, bool HAS_GX>
+static int launch_tma_one(const TmaArgs& A0, cudaStream_t st) {
+  constexpr int STAGES = 3;
+  constexpr size_t smem = (size_t)STAGES * kTileBytes * (BWD ? 2 : 1);
+  auto kern = filter_step_tma_kernel<FID, BWD, HAS_GX, STAGES>;
+  static int ctas_per_sm[64];          // per device
+  static int num_sms[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+    return set_error(EXP_ERR_CUDA, "cudaGetDevice failed");
+  if (ctas_per_sm[dev] == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int nb = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kTmaThreads, smem);
+    if (e != cudaSuccess || nb < 1) return set_error(EXP_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    num_sms[dev] = sms;
+    ctas_per_sm[dev] = nb;
+  }
+  int grid = num_sms[dev] * ctas_per_sm[dev];
+  if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
+  if (grid > A0.total_tiles) grid = A0.total_tiles;
+  kern<<<grid, kTmaThreads, smem, st>>>(A0);
+  return EXP_OK;
+}
+
+template <bool BWD, bool HAS_GX>
+static int launch_tma(int fid, const TmaArgs& A, cudaStream_t st) {
+  switch (fid) {
+#define EXP_CASE(F) case F: return launch_tma_one<F, BWD, HAS_GX>(A, st);
+    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7)
+#undef EXP_CASE
+  }
+  return set_error(EXP_ERR_INVALID_ARG, "bad filter id %d", fid);
+}
+
+static TmaArgs make_tma_args(const float* x, const float* gy, float* out, const float* params, int pstride,
+                             int B, int P) {
+  TmaArgs T{};
+  T.x = x; T.gy = gy; T.out = out; T.params = params; T.pstride = pstride; T.P = P; T.B = B;
+  T.tiles_per_image = (P + kTilePx - 1) / kTilePx;
+  T.total_tiles = B * T.tiles_per_image;
+  return T;
+}
+
 static int check_common(const void* x, const float* params, int pstride, const int* ids, int uniform_id,
                         int B, int H, int W) {
   EXP_CHECK_ARG(x && params, "null image or params pointer");
@@ -370,6 +427,15 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, c
   bool vec;
   rc = pick_vec(variant, P, x, y, nullptr, &vec);
   if (rc) return rc;
+  if (variant == EXP_VARIANT_TMA) {
+    if (ids) return set_error(EXP_ERR_UNSUPPORTED, "the TMA variant needs a uniform filter id");
+    if ((long long)B * ((P + kTilePx - 1) / kTilePx) > 0x7fffffffll) return set_error(EXP_ERR_UNSUPPORTED, "too many tiles");
+    TmaArgs T = make_tma_args(x, nullptr, y, params, pstride, B, P);
+    rc = launch_tma<false, false>(uniform_id, T, (cudaStream_t)stream);
+    if (rc) return rc;
+    EXP_CHECK_LAUNCH("exp_filter_fwd[tma]");
+    return EXP_OK;
+  }
   FilterArgs A{};
   A.x = x; A.out = y; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockFwd;
@@ -382,7 +448,9 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, c
 size_t exp_filter_bwd_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
   const size_t nblk = ((size_t)H * W + kPixPerBlockBwd - 1) / kPixPerBlockBwd;
-  return (size_t)B * nblk * kAccStride * sizeof(float) + (size_t)B * sizeof(unsigned);
+  size_t recs = (size_t)B * nblk;
+  if (recs < (size_t)B + kMaxPersistentCtas) recs = (size_t)B + kMaxPersistentCtas;
+  return kCounterBytes + recs * kAccStride * sizeof(float);
 }
 
 int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, const float* params,
@@ -399,12 +467,24 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, c
   bool vec;
   rc = pick_vec(variant, P, x, gy, gx, &vec);
   if (rc) return rc;
+  if (variant == EXP_VARIANT_TMA) {
+    if (ids) return set_error(EXP_ERR_UNSUPPORTED, "the TMA variant needs a uniform filter id");
+    TmaArgs T = make_tma_args(x, gy, gx, params, pstride, B, P);
+    T.counters = reinterpret_cast<unsigned*>(workspace);
+    T.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
+    T.gparams = gparams;
+    rc = gx ? launch_tma<true, true>(uniform_id, T, (cudaStream_t)stream)
+            : launch_tma<true, false>(uniform_id, T, (cudaStream_t)stream);
+    if (rc) return rc;
+    EXP_CHECK_LAUNCH("exp_filter_bwd[tma]");
+    return EXP_OK;
+  }
   const int nblk = (P + kPixPerBlockBwd - 1) / kPixPerBlockBwd;
   FilterArgs A{};
   A.x = x; A.gy = gy; A.out = gx; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockBwd;
-  A.partials = reinterpret_cast<float*>(workspace);
-  A.counters = reinterpret_cast<unsigned*>(A.partials + (size_t)B * nblk * kAccStride);
+  A.counters = reinterpret_cast<unsigned*>(workspace);
+  A.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
   A.gparams = gparams;
   dim3 grid(nblk, B);
   if (gx) launch_step<true, true>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);

@@ -89,9 +89,11 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride,
                    const int* ids, int uniform_id, int B, int H, int W, int variant,
                    void* stream);
 
-/* Bytes of device workspace exp_filter_bwd needs for this shape (partial sums of the
- * per-image parameter gradients + one ticket counter per image).  The workspace must be
- * zero-filled once before first use; the kernel leaves it zeroed for the next call. */
+/* Bytes of device workspace exp_filter_bwd needs for this shape: a fixed 256 KiB block of
+ * per-image ticket counters followed by the partial-sum records of the per-image parameter
+ * gradients.  The counter block must be zero-filled once before first use; every launch
+ * leaves it zeroed, so one workspace can be reused across shapes and filters (but not by two
+ * launches that may run concurrently). */
 size_t exp_filter_bwd_workspace_bytes(int B, int H, int W);
 
 /* ---- Filter.process backward ----------------------------------------------------------

@@ -37,7 +37,7 @@ def test_python_binding_covers_header(built_lib):
   assert [l.exp_num_filter_params(i) for i in range(8)] == [1, 1, 3, 1, 8, 1, 1, 24]
   assert l.exp_num_filter_params(8) < 0 and b"bad filter id" in l.exp_last_error()
   assert l.exp_filter_bwd_workspace_bytes(0, 1, 1) == 0
-  assert l.exp_filter_bwd_workspace_bytes(2, 64, 64) == 2 * 32 * 4 + 2 * 4
+  assert l.exp_filter_bwd_workspace_bytes(2, 64, 64) == 65536 * 4 + (2 + 4096) * 32 * 4
 
 
 def test_argument_validation_needs_no_gpu(built_lib):

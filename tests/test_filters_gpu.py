@@ -134,6 +134,33 @@ def test_scalar_and_vector_variants_agree(ops):
     assert torch.allclose(gpv, gps, rtol=1e-5, atol=1e-6), fid
 
 
+@pytest.mark.parametrize("shape", [(3, 40, 36), (2, 64, 64), (1, 2, 2), (9, 512, 512), (5, 333, 500)])
+def test_tma_variant_matches_direct(ops, shape):
+  """EXP_VARIANT_TMA (persistent cp.async.bulk ring) == EXP_VARIANT_DIRECT: identical per-pixel
+  code, so pixels and image gradients are bit-equal; parameter gradients differ only in the
+  (deterministic) summation order.  Shapes cover partial tiles, 1 tile and many tiles per CTA."""
+  from exposure_b200 import _cabi
+  B, H, W = shape
+  g = torch.Generator(device="cuda").manual_seed(3)
+  x = torch.exp(torch.randn(B, H, W, 3, device="cuda", generator=g) - 3.2).clamp_(0, 4)
+  x = torch.where(torch.rand(B, H, W, 3, device="cuda", generator=g) < 0.02, x * 8, x)
+  gy = torch.randn(B, H, W, 3, device="cuda", generator=g)
+  for fid in ALL:
+    params = ops.filter_regress_fwd(F.synth_logits(fid, B).cuda(), fid)
+    yd = ops.filter_fwd(x, params, fid, variant=_cabi.VARIANT_DIRECT)
+    yt = ops.filter_fwd(x, params, fid, variant=_cabi.VARIANT_TMA)
+    assert torch.equal(yd, yt), fid
+    gxd, gpd = ops.filter_bwd(x, gy, params, fid, variant=_cabi.VARIANT_DIRECT)
+    gxt, gpt = ops.filter_bwd(x, gy, params, fid, variant=_cabi.VARIANT_TMA)
+    assert torch.equal(gxd, gxt), fid
+    scale = gpd.abs().max() + 1e-6
+    assert ((gpd - gpt).abs() <= 2e-5 * scale + 1e-4 * gpd.abs()).all(), (fid, (gpd - gpt).abs().max(), scale)
+    _, gpt2 = ops.filter_bwd(x, gy, params, fid, need_gx=False, variant=_cabi.VARIANT_TMA)
+    assert torch.equal(gpt, gpt2), fid
+    gxt3, gpt3 = ops.filter_bwd(x, gy, params, fid, variant=_cabi.VARIANT_TMA)
+    assert torch.equal(gxt3, gxt) and torch.equal(gpt3, gpt), fid        # deterministic
+
+
 def test_in_place_and_determinism(ops):
   B, H, W = 2, 64, 64
   x = F.synth_images(B, H, W, seed=4).cuda()

@@ -49,6 +49,19 @@ def parse_args():
   return ap.parse_args()
 
 
+def host_threads():
+  """Host threads this process may really use: min(affinity mask, cgroup cpu quota)."""
+  n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+  try:
+    with open("/sys/fs/cgroup/cpu.max") as fh:
+      quota, period = fh.read().split()
+    if quota != "max":
+      n = max(1, min(n, int(float(quota) / float(period))))
+  except Exception:
+    pass
+  return n
+
+
 def peaks():
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(p):
@@ -76,7 +89,7 @@ def cpu_chain_step(x, logits, gout):
 def cpu_baseline(size, budget_s=20.0, batch=2):
   import torch
   from oracle import filters as F
-  cores = os.cpu_count() or 1
+  cores = host_threads()
   torch.set_num_threads(cores)
   x = F.synth_images(batch, size, size, seed=1234, stress=False)
   logits = [F.synth_logits(f, batch) for f in CHAIN_IDS]
@@ -104,7 +117,7 @@ def run_reference(args):
     return
   import torch
   from oracle import filters as F
-  cores = os.cpu_count() or 1
+  cores = host_threads()
   torch.set_num_threads(cores)
   sample_b = 2
   x = F.synth_images(sample_b, args.size, args.size, seed=1234, stress=False)

@@ -77,8 +77,9 @@ def test_backward_matches_oracle(ops, fid, shape):
   tolp = 1e-4 * torch.maximum(gp64.abs(), 1e-3 * scale + 1e-30)
   assert ((gp - gp64).abs() <= tolp).all(), "gp fid %d: %.3g" % (fid, float(((gp - gp64).abs() / tolp).max()))
   # param-gradient-only backward (the reference's actual training need) gives the same gparams
+  # (separately compiled instantiation: FMA contraction may differ in the last bit)
   _, gp2 = ops.filter_bwd(x.cuda(), gy.cuda(), params.cuda(), fid, need_gx=False)
-  assert torch.equal(gp2.cpu().double()[:, :F.NUM_PARAMS[fid]], gp)
+  assert ((gp2.cpu().double()[:, :F.NUM_PARAMS[fid]] - gp).abs() <= 0.1 * tolp).all()
 
 
 @pytest.mark.parametrize("fid", ALL)
@@ -156,7 +157,7 @@ def test_tma_variant_matches_direct(ops, shape):
     scale = gpd.abs().max() + 1e-6
     assert ((gpd - gpt).abs() <= 2e-5 * scale + 1e-4 * gpd.abs()).all(), (fid, (gpd - gpt).abs().max(), scale)
     _, gpt2 = ops.filter_bwd(x, gy, params, fid, need_gx=False, variant=_cabi.VARIANT_TMA)
-    assert torch.equal(gpt, gpt2), fid
+    assert ((gpt - gpt2).abs() <= 2e-5 * scale + 1e-4 * gpt.abs()).all(), fid
     gxt3, gpt3 = ops.filter_bwd(x, gy, params, fid, variant=_cabi.VARIANT_TMA)
     assert torch.equal(gxt3, gxt) and torch.equal(gpt3, gpt), fid        # deterministic
 

@@ -1,0 +1,426 @@
+// Policy / critic / value network primitives: 4x4 stride-2 SAME convolutions (fprop, dgrad,
+// wgrad), fully connected layers (fwd, dgrad, wgrad), their forward-mode "tangent" variants
+// used by the WGAN-GP second-order term, and column sums for bias gradients.
+//
+// Replaces the cuDNN / cuBLAS calls TF-1.6 issues for ly.conv2d / ly.fully_connected in
+// agent.py:11-37,87-99, critics.py:6-38,94-97, filters.py:28-44 and their tf.gradients
+// (Conv2DBackpropInput / Conv2DBackpropFilter), including the gradient-penalty double
+// backward of net.py:174-194 (see DESIGN.md section 6 for the JVP formulation).
+//
+// Layouts follow the reference checkpoint: activations NHWC, conv weights HWIO
+// [4,4,Cin,Cout], FC weights [in,out], flatten order (h*4+w)*256+c.
+#include "gemm_engine.cuh"
+
+namespace expo {
+
+__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
+
+// ------------------------------------------------------------------------------------------
+// conv fprop:  y[b,oy,ox,co] = act( sum_{ky,kx,ci} in[b,2oy-1+ky,2ox-1+kx,ci] W[ky,kx,ci,co] + bias )
+// in = concat(x[B,IH,IW,Cx], tile(vec[B,Cv])) - shift  (zero padding applied after the shift)
+// ------------------------------------------------------------------------------------------
+struct ConvFprop {
+  const float* x; const float* vec; const float* W; const float* bias; const float* mask_ref;
+  const float* post_mul; float* y; float* y2;
+  int B, IH, IW, Cx, Cv, Cin, Cout, OH, OW, chunks, mode, lgOW, lgOHW;
+  float shift;
+  struct RowA { int b, iy0, ix0; };
+  struct KS { int ky, kx, ci0, tap; };
+  __device__ void init(int) {}
+  __device__ int k_iters() const { return 16 * chunks; }
+  __device__ RowA row_a(int m) const {
+    RowA r;
+    if (m >= B * OH * OW) { r.b = -1; r.iy0 = r.ix0 = 0; return r; }
+    r.b = m >> lgOHW;
+    const int rem = m & ((1 << lgOHW) - 1);
+    r.iy0 = 2 * (rem >> lgOW) - 1;
+    r.ix0 = 2 * (rem & (OW - 1)) - 1;
+    return r;
+  }
+  __device__ KS kstate(int ki) const {
+    KS s;
+    s.tap = ki / chunks;
+    s.ci0 = (ki - s.tap * chunks) * kBK;
+    s.ky = s.tap >> 2; s.kx = s.tap & 3;
+    return s;
+  }
+  __device__ float load_a(const RowA& r, const KS& s, int kk) const {
+    const int ci = s.ci0 + kk, iy = r.iy0 + s.ky, ix = r.ix0 + s.kx;
+    if (r.b < 0 || ci >= Cin || (unsigned)iy >= (unsigned)IH || (unsigned)ix >= (unsigned)IW) return 0.f;
+    const float v = ci < Cx ? __ldg(x + ((size_t)(r.b * IH + iy) * IW + ix) * Cx + ci)
+                            : __ldg(vec + (size_t)r.b * Cv + (ci - Cx));
+    return v - shift;
+  }
+  __device__ float load_b(const KS& s, int kk, int n) const {
+    const int ci = s.ci0 + kk;
+    if (ci >= Cin || n >= Cout) return 0.f;
+    return __ldg(W + ((size_t)s.tap * Cin + ci) * Cout + n);
+  }
+  __device__ void store(int m, int n, float v) const {
+    if (m >= B * OH * OW || n >= Cout) return;
+    const size_t idx = (size_t)m * Cout + n;
+    if (mode == 0) { v = lrelu_f(v + (bias ? __ldg(bias + n) : 0.f)); }
+    else { v *= dlrelu_from_out(__ldg(mask_ref + idx)); }
+    y[idx] = v;
+    if (y2) y2[idx] = v * __ldg(post_mul + idx);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// conv dgrad (transposed conv), one parity class (py,px) of the input grid per blockIdx.z:
+// dx[b,2a+py,2c+px,ci] = sum_{j,l,co} dy[b,a+dy_j,c+dx_l,co] W[ky_j,kx_l,ci,co]
+// ------------------------------------------------------------------------------------------
+struct ConvDgrad {
+  const float* dy; const float* W; const float* a_in; float* dx;
+  int B, IH, IW, Cin, OH, OW, Cout, chunks, py, px, lgHW2, lgW2;
+  struct RowA { int b, a, c; };
+  struct KS { int oy_off, ox_off, tap, co0; };
+  __device__ void init(int z) { py = z >> 1; px = z & 1; }
+  __device__ int k_iters() const { return 4 * chunks; }
+  __device__ RowA row_a(int m) const {
+    RowA r;
+    if (m >= B * (IH / 2) * (IW / 2)) { r.b = -1; r.a = r.c = 0; return r; }
+    r.b = m >> lgHW2;
+    const int rem = m & ((1 << lgHW2) - 1);
+    r.a = rem >> lgW2;
+    r.c = rem & ((IW / 2) - 1);
+    return r;
+  }
+  __device__ KS kstate(int ki) const {
+    KS s;
+    const int t = ki / chunks;
+    s.co0 = (ki - t * chunks) * kBK;
+    const int j = t >> 1, l = t & 1;
+    // iy = 2a+py: valid ky have parity (py+1)&1;  oy = (iy + 1 - ky) / 2
+    const int ky = py == 0 ? (j == 0 ? 1 : 3) : (j == 0 ? 0 : 2);
+    const int kx = px == 0 ? (l == 0 ? 1 : 3) : (l == 0 ? 0 : 2);
+    s.oy_off = py == 0 ? (j == 0 ? 0 : -1) : (j == 0 ? 1 : 0);
+    s.ox_off = px == 0 ? (l == 0 ? 0 : -1) : (l == 0 ? 1 : 0);
+    s.tap = ky * 4 + kx;
+    return s;
+  }
+  __device__ float load_a(const RowA& r, const KS& s, int kk) const {
+    const int oy = r.a + s.oy_off, ox = r.c + s.ox_off;
+    if (r.b < 0 || (unsigned)oy >= (unsigned)OH || (unsigned)ox >= (unsigned)OW) return 0.f;
+    return __ldg(dy + ((size_t)(r.b * OH + oy) * OW + ox) * Cout + s.co0 + kk);
+  }
+  __device__ float load_b(const KS& s, int kk, int n) const {
+    if (n >= Cin) return 0.f;
+    return __ldg(W + ((size_t)s.tap * Cin + n) * Cout + s.co0 + kk);
+  }
+  __device__ void store(int m, int n, float v) const {
+    if (m >= B * (IH / 2) * (IW / 2) || n >= Cin) return;
+    const int b = m >> lgHW2;
+    const int rem = m & ((1 << lgHW2) - 1);
+    const int iy = 2 * (rem >> lgW2) + py, ix = 2 * (rem & ((IW / 2) - 1)) + px;
+    const size_t idx = ((size_t)(b * IH + iy) * IW + ix) * Cin + n;
+    if (a_in) v *= dlrelu_from_out(__ldg(a_in + idx));
+    dx[idx] = v;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// conv wgrad: gW[(tap,ci),co] = sum_{pixels} in[pixel shifted by tap, ci] * dy[pixel, co]
+// split over blockIdx.z pixel ranges; partial sums go to part[z][16*Cin][Cout]
+// ------------------------------------------------------------------------------------------
+struct ConvWgrad {
+  const float* x; const float* vec; const float* dy; float* part;
+  int B, IH, IW, Cx, Cv, Cin, Cout, OH, OW, lgOW, lgOHW, pix_per_split, p_begin;
+  float shift;
+  struct RowA { int tap_ky, tap_kx, ci; };
+  struct KS { int p0; };
+  __device__ void init(int z) { p_begin = z * pix_per_split; part += (size_t)z * 16 * Cin * Cout; }
+  __device__ int k_iters() const { return pix_per_split / kBK; }
+  __device__ RowA row_a(int m) const {
+    RowA r;
+    if (m >= 16 * Cin) { r.ci = -1; r.tap_ky = r.tap_kx = 0; return r; }
+    const int tap = m / Cin;
+    r.ci = m - tap * Cin;
+    r.tap_ky = tap >> 2; r.tap_kx = tap & 3;
+    return r;
+  }
+  __device__ KS kstate(int ki) const { KS s; s.p0 = p_begin + ki * kBK; return s; }
+  __device__ float load_a(const RowA& r, const KS& s, int kk) const {
+    const int p = s.p0 + kk;
+    if (r.ci < 0 || p >= B * OH * OW) return 0.f;
+    const int b = p >> lgOHW;
+    const int rem = p & ((1 << lgOHW) - 1);
+    const int iy = 2 * (rem >> lgOW) - 1 + r.tap_ky, ix = 2 * (rem & (OW - 1)) - 1 + r.tap_kx;
+    if ((unsigned)iy >= (unsigned)IH || (unsigned)ix >= (unsigned)IW) return 0.f;
+    const float v = r.ci < Cx ? __ldg(x + ((size_t)(b * IH + iy) * IW + ix) * Cx + r.ci)
+                              : __ldg(vec + (size_t)b * Cv + (r.ci - Cx));
+    return v - shift;
+  }
+  __device__ float load_b(const KS& s, int kk, int n) const {
+    const int p = s.p0 + kk;
+    if (p >= B * OH * OW || n >= Cout) return 0.f;
+    return __ldg(dy + (size_t)p * Cout + n);
+  }
+  __device__ void store(int m, int n, float v) const {
+    if (m >= 16 * Cin || n >= Cout) return;
+    part[(size_t)m * Cout + n] = v;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// fully connected: y = x[M,K] W[K,N] (split-K over blockIdx.z -> part[z][M][N])
+// ------------------------------------------------------------------------------------------
+struct FcFwd {
+  const float* x; const float* W; float* part;
+  int M, K, N, k_per_split, k_begin;
+  struct RowA { int m; };
+  struct KS { int k0; };
+  __device__ void init(int z) { k_begin = z * k_per_split; part += (size_t)z * M * N; }
+  __device__ int k_iters() const { return k_per_split / kBK; }
+  __device__ RowA row_a(int m) const { RowA r; r.m = m < M ? m : -1; return r; }
+  __device__ KS kstate(int ki) const { KS s; s.k0 = k_begin + ki * kBK; return s; }
+  __device__ float load_a(const RowA& r, const KS& s, int kk) const {
+    const int k = s.k0 + kk;
+    return (r.m < 0 || k >= K) ? 0.f : __ldg(x + (size_t)r.m * K + k);
+  }
+  __device__ float load_b(const KS& s, int kk, int n) const {
+    const int k = s.k0 + kk;
+    return (k >= K || n >= N) ? 0.f : __ldg(W + (size_t)k * N + n);
+  }
+  __device__ void store(int m, int n, float v) const {
+    if (m < M && n < N) part[(size_t)m * N + n] = v;
+  }
+};
+
+// dx[M,K] = dy[M,N] W^T ; epilogue multiplier: mul_mode 0 none, 1 dlrelu(mul), 2 plain * mul
+struct FcDgrad {
+  const float* dy; const float* W; const float* mul; float* dx;
+  int M, K, N, mul_mode;
+  struct RowA { int m; };
+  struct KS { int n0; };
+  __device__ void init(int) {}
+  __device__ int k_iters() const { return (N + kBK - 1) / kBK; }
+  __device__ RowA row_a(int m) const { RowA r; r.m = m < M ? m : -1; return r; }
+  __device__ KS kstate(int ki) const { KS s; s.n0 = ki * kBK; return s; }
+  __device__ float load_a(const RowA& r, const KS& s, int kk) const {
+    const int n = s.n0 + kk;
+    return (r.m < 0 || n >= N) ? 0.f : __ldg(dy + (size_t)r.m * N + n);
+  }
+  __device__ float load_b(const KS& s, int kk, int col) const {   // B[k'=n][col=k] = W[k][n]
+    const int n = s.n0 + kk;
+    return (n >= N || col >= K) ? 0.f : __ldg(W + (size_t)col * N + n);
+  }
+  __device__ void store(int m, int k, float v) const {
+    if (m >= M || k >= K) return;
+    const size_t idx = (size_t)m * K + k;
+    if (mul_mode == 1) v *= dlrelu_from_out(__ldg(mul + idx));
+    else if (mul_mode == 2) v *= __ldg(mul + idx);
+    dx[idx] = v;
+  }
+};
+
+// gW[K,N] = x^T[K,M] dy[M,N]
+struct FcWgrad {
+  const float* x; const float* dy; float* gW;
+  int M, K, N;
+  struct RowA { int k; };
+  struct KS { int s0; };
+  __device__ void init(int) {}
+  __device__ int k_iters() const { return (M + kBK - 1) / kBK; }
+  __device__ RowA row_a(int m) const { RowA r; r.k = m < K ? m : -1; return r; }
+  __device__ KS kstate(int ki) const { KS s; s.s0 = ki * kBK; return s; }
+  __device__ float load_a(const RowA& r, const KS& s, int kk) const {
+    const int smp = s.s0 + kk;
+    return (r.k < 0 || smp >= M) ? 0.f : __ldg(x + (size_t)smp * K + r.k);
+  }
+  __device__ float load_b(const KS& s, int kk, int n) const {
+    const int smp = s.s0 + kk;
+    return (smp >= M || n >= N) ? 0.f : __ldg(dy + (size_t)smp * N + n);
+  }
+  __device__ void store(int k, int n, float v) const {
+    if (k < K && n < N) gW[(size_t)k * N + n] = v;
+  }
+};
+
+// out[i] = epi( sum_s part[s][i] ), fixed order (deterministic).
+// mode 0: lrelu(v + bias[col]); 1: v * dlrelu(mask_ref[i]); 2: v + bias[col]; 3: v
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t count, int ncols,
+                                     const float* __restrict__ bias, const float* __restrict__ mask_ref, int mode,
+                                     float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += part[(size_t)s * count + i];
+  const int col = (int)(i % ncols);
+  if (mode == 0) v = lrelu_f(v + (bias ? bias[col] : 0.f));
+  else if (mode == 1) v *= dlrelu_from_out(mask_ref[i]);
+  else if (mode == 2) v += (bias ? bias[col] : 0.f);
+  out[i] = v;
+}
+
+// column sums of a row-major [rows, cols] matrix (bias gradients): one CTA per 32 columns
+__global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float s = 0.f;
+  if (col < cols)
+    for (int r = ry; r < rows; r += 8) s += a[(size_t)r * cols + col];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && col < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[col] = t;
+  }
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static int host_ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+static int wgrad_splits(int B, int OH, int OW, int Cin, int Cout) {
+  const int pixels = B * OH * OW;
+  const int tiles = ((16 * Cin + kBM - 1) / kBM) * ((Cout + 63) / 64);
+  int s = (592 + tiles - 1) / tiles;            // aim at ~4 CTAs per SM
+  const int max_s = pixels / 64 > 0 ? pixels / 64 : 1;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  return s;
+}
+static int fc_splits(int M, int K, int N) {
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + 63) / 64);
+  int s = (296 + tiles - 1) / tiles;
+  const int max_s = K / 64 > 0 ? K / 64 : 1;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  return s;
+}
+
+}  // namespace expo
+
+using namespace expo;
+
+extern "C" {
+
+int exp_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, const float* W, const float* bias,
+                 const float* mask_ref, const float* post_mul, float* y, float* y2, int B, int IH, int IW, int Cout,
+                 int mode, void* stream) {
+  EXP_CHECK_ARG(x && W && y, "null pointer");
+  EXP_CHECK_ARG(B > 0 && is_pow2(IH) && is_pow2(IW) && IH >= 2 && IW >= 2, "IH/IW must be powers of two >= 2 (got %dx%d)", IH, IW);
+  EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cout > 0, "bad channel counts");
+  EXP_CHECK_ARG(mode == 0 || (mode == 1 && mask_ref), "mode 1 needs mask_ref");
+  EXP_CHECK_ARG(!y2 || post_mul, "y2 needs post_mul");
+  ConvFprop p{};
+  p.x = x; p.vec = vec; p.W = W; p.bias = bias; p.mask_ref = mask_ref; p.post_mul = post_mul; p.y = y; p.y2 = y2;
+  p.B = B; p.IH = IH; p.IW = IW; p.Cx = Cx; p.Cv = Cv; p.Cin = Cx + Cv; p.Cout = Cout; p.OH = IH / 2; p.OW = IW / 2;
+  p.chunks = (p.Cin + kBK - 1) / kBK; p.mode = mode; p.shift = shift;
+  p.lgOW = host_ilog2(p.OW); p.lgOHW = host_ilog2(p.OH * p.OW);
+  const int M = B * p.OH * p.OW;
+  if (Cout <= 32) launch_gemm<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
+  else launch_gemm<ConvFprop, 64, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
+  EXP_CHECK_LAUNCH("exp_conv_fwd");
+  return EXP_OK;
+}
+
+int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH, int IW, int Cin,
+                   int Cout, void* stream) {
+  EXP_CHECK_ARG(dy && W && dx, "null pointer");
+  EXP_CHECK_ARG(B > 0 && is_pow2(IH) && is_pow2(IW) && IH >= 2 && IW >= 2, "IH/IW must be powers of two >= 2");
+  EXP_CHECK_ARG(Cin > 0 && Cout > 0 && Cout % kBK == 0, "Cout must be a multiple of %d", kBK);
+  ConvDgrad p{};
+  p.dy = dy; p.W = W; p.a_in = a_in; p.dx = dx; p.B = B; p.IH = IH; p.IW = IW; p.Cin = Cin; p.OH = IH / 2;
+  p.OW = IW / 2; p.Cout = Cout; p.chunks = Cout / kBK;
+  p.lgW2 = host_ilog2(IW / 2); p.lgHW2 = host_ilog2((IH / 2) * (IW / 2));
+  const int M = B * (IH / 2) * (IW / 2);
+  if (Cin <= 32) launch_gemm<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
+  else launch_gemm<ConvDgrad, 64, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
+  EXP_CHECK_LAUNCH("exp_conv_dgrad");
+  return EXP_OK;
+}
+
+size_t exp_conv_wgrad_workspace_bytes(int B, int IH, int IW, int Cin, int Cout) {
+  if (B <= 0 || IH < 2 || IW < 2 || Cin <= 0 || Cout <= 0) return 0;
+  return (size_t)wgrad_splits(B, IH / 2, IW / 2, Cin, Cout) * 16 * Cin * Cout * sizeof(float);
+}
+
+int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift, const float* dy, float* gW, int B,
+                   int IH, int IW, int Cout, void* workspace, size_t workspace_bytes, void* stream) {
+  EXP_CHECK_ARG(x && dy && gW && workspace, "null pointer");
+  EXP_CHECK_ARG(B > 0 && is_pow2(IH) && is_pow2(IW) && IH >= 2 && IW >= 2, "IH/IW must be powers of two >= 2");
+  EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cout > 0, "bad channel counts");
+  const int Cin = Cx + Cv, OH = IH / 2, OW = IW / 2;
+  const int splits = wgrad_splits(B, OH, OW, Cin, Cout);
+  const size_t need = (size_t)splits * 16 * Cin * Cout * sizeof(float);
+  if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  ConvWgrad p{};
+  p.x = x; p.vec = vec; p.dy = dy; p.part = reinterpret_cast<float*>(workspace);
+  p.B = B; p.IH = IH; p.IW = IW; p.Cx = Cx; p.Cv = Cv; p.Cin = Cin; p.Cout = Cout; p.OH = OH; p.OW = OW;
+  p.lgOW = host_ilog2(OW); p.lgOHW = host_ilog2(OH * OW); p.shift = shift;
+  const int pixels = B * OH * OW;
+  int pps = (pixels + splits - 1) / splits;
+  pps = ((pps + kBK - 1) / kBK) * kBK;
+  p.pix_per_split = pps;
+  if (Cout <= 32) launch_gemm<ConvWgrad, 32, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
+  else launch_gemm<ConvWgrad, 64, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
+  EXP_CHECK_LAUNCH("exp_conv_wgrad");
+  const size_t count = (size_t)16 * Cin * Cout;
+  splitk_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      p.part, splits, count, Cout, nullptr, nullptr, 3, gW);
+  EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
+  return EXP_OK;
+}
+
+size_t exp_fc_workspace_bytes(int M, int K, int N) {
+  if (M <= 0 || K <= 0 || N <= 0) return 0;
+  return (size_t)fc_splits(M, K, N) * M * N * sizeof(float);
+}
+
+int exp_fc_fwd(const float* x, const float* W, const float* bias, const float* mask_ref, float* y, int M, int K, int N,
+               int mode, void* workspace, size_t workspace_bytes, void* stream) {
+  EXP_CHECK_ARG(x && W && y && workspace, "null pointer");
+  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0, "bad shape");
+  EXP_CHECK_ARG(mode >= 0 && mode <= 3 && (mode != 1 || mask_ref), "bad mode");
+  const int splits = fc_splits(M, K, N);
+  const size_t need = (size_t)splits * M * N * sizeof(float);
+  if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  FcFwd p{};
+  p.x = x; p.W = W; p.part = reinterpret_cast<float*>(workspace); p.M = M; p.K = K; p.N = N;
+  int kps = (K + splits - 1) / splits;
+  kps = ((kps + kBK - 1) / kBK) * kBK;
+  p.k_per_split = kps;
+  if (N <= 32) launch_gemm<FcFwd, 32, false, false>(p, M, N, splits, (cudaStream_t)stream);
+  else launch_gemm<FcFwd, 64, false, false>(p, M, N, splits, (cudaStream_t)stream);
+  EXP_CHECK_LAUNCH("exp_fc_fwd");
+  const size_t count = (size_t)M * N;
+  splitk_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      p.part, splits, count, N, bias, mask_ref, mode, y);
+  EXP_CHECK_LAUNCH("exp_fc_fwd[reduce]");
+  return EXP_OK;
+}
+
+int exp_fc_dgrad(const float* dy, const float* W, const float* mul, int mul_mode, float* dx, int M, int K, int N,
+                 void* stream) {
+  EXP_CHECK_ARG(dy && W && dx, "null pointer");
+  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && mul_mode >= 0 && mul_mode <= 2 && (mul_mode == 0 || mul), "bad args");
+  FcDgrad p{};
+  p.dy = dy; p.W = W; p.mul = mul; p.dx = dx; p.M = M; p.K = K; p.N = N; p.mul_mode = mul_mode;
+  launch_gemm<FcDgrad, 64, false, true>(p, M, K, 1, (cudaStream_t)stream);
+  EXP_CHECK_LAUNCH("exp_fc_dgrad");
+  return EXP_OK;
+}
+
+int exp_fc_wgrad(const float* x, const float* dy, float* gW, int M, int K, int N, void* stream) {
+  EXP_CHECK_ARG(x && dy && gW, "null pointer");
+  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0, "bad shape");
+  FcWgrad p{};
+  p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N;
+  if (N <= 32) launch_gemm<FcWgrad, 32, true, false>(p, K, N, 1, (cudaStream_t)stream);
+  else launch_gemm<FcWgrad, 64, true, false>(p, K, N, 1, (cudaStream_t)stream);
+  EXP_CHECK_LAUNCH("exp_fc_wgrad");
+  return EXP_OK;
+}
+
+int exp_colsum(const float* a, int rows, int cols, float* out, void* stream) {
+  EXP_CHECK_ARG(a && out && rows > 0 && cols > 0, "bad args");
+  colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, out);
+  EXP_CHECK_LAUNCH("exp_colsum");
+  return EXP_OK;
+}
+
+}  // extern "C"

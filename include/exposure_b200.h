@@ -110,6 +110,54 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams,
                    int B, int H, int W, void* workspace, size_t workspace_bytes, int variant,
                    void* stream);
 
+/* ======================================================================================
+ * Policy / critic / value network primitives.
+ * Replace ly.conv2d (kernel 4, stride 2, SAME, lrelu) and ly.fully_connected of
+ * agent.py:11-37, 87-99, critics.py:6-38, 94-97, filters.py:28-44 and their tf.gradients,
+ * including the WGAN-GP second-order term of net.py:174-194 (tangent modes).
+ * Activations NHWC, conv weights HWIO [4,4,Cin,Cout], FC weights [in,out] -- the layouts
+ * of the reference checkpoint.  IH, IW must be powers of two (cfg.source_img_size = 64).
+ * lrelu(v) = 0.6 v + 0.4 |v| (util.py:225-229); its derivative is recovered from the sign
+ * of the stored output (1, 0.2, or 0.6 at exactly 0).
+ * ==================================================================================== */
+
+/* y[B,IH/2,IW/2,Cout] = epi( conv4x4s2( concat(x[B,IH,IW,Cx], tile(vec[B,Cv])) - shift ) )
+ *   `vec` (nullable when Cv == 0) is a per-image vector broadcast over the pixels: the
+ *   states of util.enrich_image_input (util.py:31-36) and the 3 global statistics of
+ *   critics.py:48-87, so the concatenated input tensor is never materialised; `shift` is the
+ *   `net - 0.5` of agent.py:12 / critics.py:7 (0 for inner layers).
+ *   mode 0: epi(v) = lrelu(v + bias[co])                      (forward)
+ *   mode 1: epi(v) = v * lrelu'(mask_ref[...])  (no bias)     (forward-mode tangent, GP)
+ *   y2 (nullable) additionally receives y * post_mul (tf.nn.dropout mask*2, agent.py:36). */
+int exp_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, const float* W,
+                 const float* bias, const float* mask_ref, const float* post_mul, float* y, float* y2,
+                 int B, int IH, int IW, int Cout, int mode, void* stream);
+
+/* dx[B,IH,IW,Cin] = conv4x4s2^T(dy[B,IH/2,IW/2,Cout]) (* lrelu'(a_in) when a_in != NULL):
+ * Conv2DBackpropInput fused with the previous layer's activation derivative. */
+int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH,
+                   int IW, int Cin, int Cout, void* stream);
+
+/* gW[4,4,Cin,Cout] = Conv2DBackpropFilter(input as in exp_conv_fwd, dy); deterministic
+ * split-K through `workspace` (size from exp_conv_wgrad_workspace_bytes). */
+size_t exp_conv_wgrad_workspace_bytes(int B, int IH, int IW, int Cin, int Cout);
+int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift, const float* dy,
+                   float* gW, int B, int IH, int IW, int Cout, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* y[M,N] = epi(x[M,K] W[K,N]); mode 0: lrelu(v+bias), 1: v*lrelu'(mask_ref) (tangent),
+ * 2: v+bias, 3: v.  Deterministic split-K through `workspace`. */
+size_t exp_fc_workspace_bytes(int M, int K, int N);
+int exp_fc_fwd(const float* x, const float* W, const float* bias, const float* mask_ref, float* y,
+               int M, int K, int N, int mode, void* workspace, size_t workspace_bytes, void* stream);
+/* dx[M,K] = dy[M,N] W^T, then * lrelu'(mul) (mul_mode 1) or * mul (mul_mode 2, dropout). */
+int exp_fc_dgrad(const float* dy, const float* W, const float* mul, int mul_mode, float* dx, int M,
+                 int K, int N, void* stream);
+/* gW[K,N] = x^T dy */
+int exp_fc_wgrad(const float* x, const float* dy, float* gW, int M, int K, int N, void* stream);
+/* out[cols] = column sums of a[rows, cols] (bias gradients) */
+int exp_colsum(const float* a, int rows, int cols, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ class ExposureLibError(RuntimeError):
   pass
 
 
-_c_void_p, _c_int, _c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+_c_void_p, _c_int, _c_size_t, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
 
 # name -> (restype, argtypes); must list every symbol include/exposure_b200.h declares
 SIGNATURES = {
@@ -37,13 +37,30 @@ SIGNATURES = {
                                 _c_void_p]),
     "exp_conv_wgrad_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int, _c_int]),
     "exp_conv_wgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, ctypes.c_float, _c_void_p, _c_void_p, _c_int,
-                                _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+                                _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "exp_fc_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
-    "exp_fc_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
-                            _c_void_p, _c_size_t, _c_void_p]),
-    "exp_fc_dgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
-    "exp_fc_wgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
-    "exp_colsum": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "exp_fc_fwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int,
+                            _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "exp_fc_dgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int,
+                              _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_fc_wgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_colsum": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "exp_stats_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_stats_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_stats_jvp": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_policy_head_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
+                                     _c_float, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                     _c_void_p, _c_void_p, _c_void_p]),
+    "exp_policy_head_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_float, _c_float,
+                                     _c_float, _c_void_p, _c_void_p]),
+    "exp_overexposure_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_overexposure_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_rl_losses": (_c_int, [_c_void_p] * 7 + [_c_int, _c_int, _c_float, _c_float, _c_float, _c_float, _c_int, _c_int,
+                               _c_void_p, _c_void_p, _c_void_p]),
+    "exp_interpolate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "exp_gp_scale": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int, _c_void_p]),
+    "exp_adam": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_float, _c_float, _c_float,
+                          _c_size_t, _c_void_p]),
 }
 
 _lib = None

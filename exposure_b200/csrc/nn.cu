@@ -167,7 +167,7 @@ struct ConvWgrad {
 // ------------------------------------------------------------------------------------------
 struct FcFwd {
   const float* x; const float* W; float* part;
-  int M, K, N, k_per_split, k_begin;
+  int M, K, N, ldx, k_per_split, k_begin;
   struct RowA { int m; };
   struct KS { int k0; };
   __device__ void init(int z) { k_begin = z * k_per_split; part += (size_t)z * M * N; }
@@ -176,7 +176,7 @@ struct FcFwd {
   __device__ KS kstate(int ki) const { KS s; s.k0 = k_begin + ki * kBK; return s; }
   __device__ float load_a(const RowA& r, const KS& s, int kk) const {
     const int k = s.k0 + kk;
-    return (r.m < 0 || k >= K) ? 0.f : __ldg(x + (size_t)r.m * K + k);
+    return (r.m < 0 || k >= K) ? 0.f : __ldg(x + (size_t)r.m * ldx + k);
   }
   __device__ float load_b(const KS& s, int kk, int n) const {
     const int k = s.k0 + kk;
@@ -187,10 +187,10 @@ struct FcFwd {
   }
 };
 
-// dx[M,K] = dy[M,N] W^T ; epilogue multiplier: mul_mode 0 none, 1 dlrelu(mul), 2 plain * mul
+// dx[M,K] = (accumulate ? dx : 0) + dy[M,N] W^T * [lrelu'(mul_act)] * [mul_plain]
 struct FcDgrad {
-  const float* dy; const float* W; const float* mul; float* dx;
-  int M, K, N, mul_mode;
+  const float* dy; const float* W; const float* mul_act; const float* mul_plain; float* dx;
+  int M, K, N, ldy, lddx, ldmul, accumulate;
   struct RowA { int m; };
   struct KS { int n0; };
   __device__ void init(int) {}
@@ -199,7 +199,7 @@ struct FcDgrad {
   __device__ KS kstate(int ki) const { KS s; s.n0 = ki * kBK; return s; }
   __device__ float load_a(const RowA& r, const KS& s, int kk) const {
     const int n = s.n0 + kk;
-    return (r.m < 0 || n >= N) ? 0.f : __ldg(dy + (size_t)r.m * N + n);
+    return (r.m < 0 || n >= N) ? 0.f : __ldg(dy + (size_t)r.m * ldy + n);
   }
   __device__ float load_b(const KS& s, int kk, int col) const {   // B[k'=n][col=k] = W[k][n]
     const int n = s.n0 + kk;
@@ -207,17 +207,18 @@ struct FcDgrad {
   }
   __device__ void store(int m, int k, float v) const {
     if (m >= M || k >= K) return;
-    const size_t idx = (size_t)m * K + k;
-    if (mul_mode == 1) v *= dlrelu_from_out(__ldg(mul + idx));
-    else if (mul_mode == 2) v *= __ldg(mul + idx);
-    dx[idx] = v;
+    const size_t im = (size_t)m * ldmul + k;
+    if (mul_act) v *= dlrelu_from_out(__ldg(mul_act + im));
+    if (mul_plain) v *= __ldg(mul_plain + im);
+    const size_t idx = (size_t)m * lddx + k;
+    dx[idx] = accumulate ? dx[idx] + v : v;
   }
 };
 
 // gW[K,N] = x^T[K,M] dy[M,N]
 struct FcWgrad {
   const float* x; const float* dy; float* gW;
-  int M, K, N;
+  int M, K, N, ldx, ldy, accumulate;
   struct RowA { int k; };
   struct KS { int s0; };
   __device__ void init(int) {}
@@ -226,36 +227,39 @@ struct FcWgrad {
   __device__ KS kstate(int ki) const { KS s; s.s0 = ki * kBK; return s; }
   __device__ float load_a(const RowA& r, const KS& s, int kk) const {
     const int smp = s.s0 + kk;
-    return (r.k < 0 || smp >= M) ? 0.f : __ldg(x + (size_t)smp * K + r.k);
+    return (r.k < 0 || smp >= M) ? 0.f : __ldg(x + (size_t)smp * ldx + r.k);
   }
   __device__ float load_b(const KS& s, int kk, int n) const {
     const int smp = s.s0 + kk;
-    return (smp >= M || n >= N) ? 0.f : __ldg(dy + (size_t)smp * N + n);
+    return (smp >= M || n >= N) ? 0.f : __ldg(dy + (size_t)smp * ldy + n);
   }
   __device__ void store(int k, int n, float v) const {
-    if (k < K && n < N) gW[(size_t)k * N + n] = v;
+    if (k < K && n < N) { const size_t i = (size_t)k * N + n; gW[i] = accumulate ? gW[i] + v : v; }
   }
 };
 
-// out[i] = epi( sum_s part[s][i] ), fixed order (deterministic).
-// mode 0: lrelu(v + bias[col]); 1: v * dlrelu(mask_ref[i]); 2: v + bias[col]; 3: v
+// out[row*ldo + col] = epi( sum_s part[s][row*ncols + col] ) (+ out when accumulate), fixed order.
+// mode 0: lrelu(v + bias[col]); 1: v * dlrelu(mask_ref[row*ldmask+col]); 2: v + bias[col]; 3: v
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t count, int ncols,
-                                     const float* __restrict__ bias, const float* __restrict__ mask_ref, int mode,
-                                     float* __restrict__ out) {
+                                     const float* __restrict__ bias, const float* __restrict__ mask_ref, int ldmask,
+                                     int mode, float* __restrict__ out, int ldo, int accumulate) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float v = 0.f;
   for (int s = 0; s < splits; ++s) v += part[(size_t)s * count + i];
   const int col = (int)(i % ncols);
+  const size_t row = i / ncols;
   if (mode == 0) v = lrelu_f(v + (bias ? bias[col] : 0.f));
-  else if (mode == 1) v *= dlrelu_from_out(mask_ref[i]);
+  else if (mode == 1) v *= dlrelu_from_out(mask_ref[row * ldmask + col]);
   else if (mode == 2) v += (bias ? bias[col] : 0.f);
-  out[i] = v;
+  const size_t o = row * ldo + col;
+  out[o] = accumulate ? out[o] + v : v;
 }
 
-// column sums of a row-major [rows, cols] matrix (bias gradients): one CTA per 32 columns
+// out[batch, cols] = column sums of a[batch, rows, cols] (bias gradients, per-image channel sums)
 __global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, float* __restrict__ out) {
   __shared__ float red[8][33];
+  a += (size_t)blockIdx.y * rows * cols;
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
   float s = 0.f;
@@ -267,7 +271,7 @@ __global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, f
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[col] = t;
+    out[(size_t)blockIdx.y * cols + col] = t;
   }
 }
 
@@ -340,7 +344,7 @@ size_t exp_conv_wgrad_workspace_bytes(int B, int IH, int IW, int Cin, int Cout) 
 }
 
 int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift, const float* dy, float* gW, int B,
-                   int IH, int IW, int Cout, void* workspace, size_t workspace_bytes, void* stream) {
+                   int IH, int IW, int Cout, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   EXP_CHECK_ARG(x && dy && gW && workspace, "null pointer");
   EXP_CHECK_ARG(B > 0 && is_pow2(IH) && is_pow2(IW) && IH >= 2 && IW >= 2, "IH/IW must be powers of two >= 2");
   EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cout > 0, "bad channel counts");
@@ -361,7 +365,7 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
   EXP_CHECK_LAUNCH("exp_conv_wgrad");
   const size_t count = (size_t)16 * Cin * Cout;
   splitk_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      p.part, splits, count, Cout, nullptr, nullptr, 3, gW);
+      p.part, splits, count, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
   EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
   return EXP_OK;
 }
@@ -371,16 +375,16 @@ size_t exp_fc_workspace_bytes(int M, int K, int N) {
   return (size_t)fc_splits(M, K, N) * M * N * sizeof(float);
 }
 
-int exp_fc_fwd(const float* x, const float* W, const float* bias, const float* mask_ref, float* y, int M, int K, int N,
-               int mode, void* workspace, size_t workspace_bytes, void* stream) {
+int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const float* mask_ref, int ldmask, float* y,
+               int ldy, int M, int K, int N, int mode, void* workspace, size_t workspace_bytes, void* stream) {
   EXP_CHECK_ARG(x && W && y && workspace, "null pointer");
-  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0, "bad shape");
-  EXP_CHECK_ARG(mode >= 0 && mode <= 3 && (mode != 1 || mask_ref), "bad mode");
+  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "bad shape");
+  EXP_CHECK_ARG(mode >= 0 && mode <= 3 && (mode != 1 || (mask_ref && ldmask >= N)), "bad mode");
   const int splits = fc_splits(M, K, N);
   const size_t need = (size_t)splits * M * N * sizeof(float);
   if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
   FcFwd p{};
-  p.x = x; p.W = W; p.part = reinterpret_cast<float*>(workspace); p.M = M; p.K = K; p.N = N;
+  p.x = x; p.W = W; p.part = reinterpret_cast<float*>(workspace); p.M = M; p.K = K; p.N = N; p.ldx = ldx;
   int kps = (K + splits - 1) / splits;
   kps = ((kps + kBK - 1) / kBK) * kBK;
   p.k_per_split = kps;
@@ -389,36 +393,40 @@ int exp_fc_fwd(const float* x, const float* W, const float* bias, const float* m
   EXP_CHECK_LAUNCH("exp_fc_fwd");
   const size_t count = (size_t)M * N;
   splitk_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      p.part, splits, count, N, bias, mask_ref, mode, y);
+      p.part, splits, count, N, bias, mask_ref, ldmask, mode, y, ldy, 0);
   EXP_CHECK_LAUNCH("exp_fc_fwd[reduce]");
   return EXP_OK;
 }
 
-int exp_fc_dgrad(const float* dy, const float* W, const float* mul, int mul_mode, float* dx, int M, int K, int N,
-                 void* stream) {
+int exp_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act, const float* mul_plain, int ldmul,
+                 float* dx, int lddx, int M, int K, int N, int accumulate, void* stream) {
   EXP_CHECK_ARG(dy && W && dx, "null pointer");
-  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && mul_mode >= 0 && mul_mode <= 2 && (mul_mode == 0 || mul), "bad args");
+  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldy >= N && lddx >= K, "bad shape");
+  EXP_CHECK_ARG((!mul_act && !mul_plain) || ldmul >= K, "bad ldmul");
   FcDgrad p{};
-  p.dy = dy; p.W = W; p.mul = mul; p.dx = dx; p.M = M; p.K = K; p.N = N; p.mul_mode = mul_mode;
+  p.dy = dy; p.W = W; p.mul_act = mul_act; p.mul_plain = mul_plain; p.dx = dx; p.M = M; p.K = K; p.N = N;
+  p.ldy = ldy; p.lddx = lddx; p.ldmul = ldmul; p.accumulate = accumulate;
   launch_gemm<FcDgrad, 64, false, true>(p, M, K, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_dgrad");
   return EXP_OK;
 }
 
-int exp_fc_wgrad(const float* x, const float* dy, float* gW, int M, int K, int N, void* stream) {
+int exp_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, int M, int K, int N, int accumulate,
+                 void* stream) {
   EXP_CHECK_ARG(x && dy && gW, "null pointer");
-  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0, "bad shape");
+  EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "bad shape");
   FcWgrad p{};
-  p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N;
+  p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N; p.ldx = ldx; p.ldy = ldy; p.accumulate = accumulate;
   if (N <= 32) launch_gemm<FcWgrad, 32, true, false>(p, K, N, 1, (cudaStream_t)stream);
   else launch_gemm<FcWgrad, 64, true, false>(p, K, N, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_wgrad");
   return EXP_OK;
 }
 
-int exp_colsum(const float* a, int rows, int cols, float* out, void* stream) {
-  EXP_CHECK_ARG(a && out && rows > 0 && cols > 0, "bad args");
-  colsum_kernel<<<(cols + 31) / 32, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, out);
+int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* stream) {
+  EXP_CHECK_ARG(a && out && batch > 0 && batch <= 65535 && rows > 0 && cols > 0, "bad args");
+  dim3 grid((cols + 31) / 32, batch);
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, out);
   EXP_CHECK_LAUNCH("exp_colsum");
   return EXP_OK;
 }

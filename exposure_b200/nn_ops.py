@@ -1,7 +1,9 @@
-"""torch-tensor front end of the network primitives of the C ABI (conv / FC / colsum).
+"""torch-tensor front end of the network / head primitives of the C ABI.
 
 Plumbing only: device pointers, current stream, output allocation.  See
-include/exposure_b200.h for the semantics of every call."""
+include/exposure_b200.h for the semantics of every call.  2-D operands may be column
+slices of a wider matrix (unit inner stride); their row stride is passed as the leading
+dimension."""
 import torch
 
 from . import _cabi
@@ -34,6 +36,19 @@ def _chk(t, name, dims=None):
     raise ValueError("%s must have %d dims, got %s" % (name, dims, tuple(t.shape)))
 
 
+def _mat(t, name):
+  """2-D float32 CUDA matrix with unit inner stride -> leading dimension."""
+  if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1)):
+    raise ValueError("%s must be a CUDA float32 matrix with unit inner stride, got %s/%s" %
+                     (name, tuple(t.shape), t.stride()))
+  return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _n(k=1):
+  _ops.launch_count += k
+
+
+# ---- convolutions -----------------------------------------------------------------------
 def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None, out=None, out2=None):
   """4x4 stride-2 SAME conv over concat(x, tile(vec)) - shift.  Forward (bias + lrelu) or,
   with mask_ref, the forward-mode tangent (no bias, times lrelu'(mask_ref)).
@@ -42,6 +57,8 @@ def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None,
   B, IH, IW, Cx = x.shape
   Cv = 0 if vec is None else vec.shape[1]
   assert W.shape[0] == 4 and W.shape[1] == 4 and W.shape[2] == Cx + Cv, (W.shape, Cx, Cv)
+  if vec is not None:
+    _chk(vec, "vec", 2)
   Cout = W.shape[3]
   y = torch.empty(B, IH // 2, IW // 2, Cout, device=x.device, dtype=torch.float32) if out is None else out
   y2 = None
@@ -51,7 +68,7 @@ def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None,
   _cabi.check(_cabi.lib().exp_conv_fwd(x.data_ptr(), Cx, _p(vec), Cv, float(shift), W.data_ptr(), _p(bias),
                                        _p(mask_ref), _p(post_mul), y.data_ptr(), _p(y2), B, IH, IW, Cout, mode,
                                        _stream()), "exp_conv_fwd")
-  _ops.launch_count += 1
+  _n()
   return y if post_mul is None else (y, y2)
 
 
@@ -60,74 +77,213 @@ def conv_dgrad(dy, W, in_shape, a_in=None, out=None):
   _chk(dy, "dy", 4); _chk(W, "W", 4)
   B, IH, IW, Cin = in_shape
   Cout = W.shape[3]
-  assert W.shape[2] == Cin and dy.shape == (B, IH // 2, IW // 2, Cout)
+  assert W.shape[2] == Cin and tuple(dy.shape) == (B, IH // 2, IW // 2, Cout)
   dx = torch.empty(B, IH, IW, Cin, device=dy.device, dtype=torch.float32) if out is None else out
   _cabi.check(_cabi.lib().exp_conv_dgrad(dy.data_ptr(), W.data_ptr(), _p(a_in), dx.data_ptr(), B, IH, IW, Cin, Cout,
                                          _stream()), "exp_conv_dgrad")
-  _ops.launch_count += 1
+  _n()
   return dx
 
 
-def conv_wgrad(x, dy, vec=None, shift=0.0, out=None):
-  """gW[4,4,Cin,Cout] for the conv whose input was concat(x, tile(vec)) - shift."""
+def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False):
+  """gW[4,4,Cin,Cout] (+= when accumulate) for the conv whose input was concat(x, tile(vec)) - shift."""
   _chk(x, "x", 4); _chk(dy, "dy", 4)
   B, IH, IW, Cx = x.shape
   Cv = 0 if vec is None else vec.shape[1]
   Cout = dy.shape[3]
   gW = torch.empty(4, 4, Cx + Cv, Cout, device=x.device, dtype=torch.float32) if out is None else out
+  assert not accumulate or out is not None
   l = _cabi.lib()
   nbytes = l.exp_conv_wgrad_workspace_bytes(B, IH, IW, Cx + Cv, Cout)
   ws = _workspace(x.device, nbytes)
   _cabi.check(l.exp_conv_wgrad(x.data_ptr(), Cx, _p(vec), Cv, float(shift), dy.data_ptr(), gW.data_ptr(), B, IH, IW,
-                               Cout, ws.data_ptr(), ws.numel(), _stream()), "exp_conv_wgrad")
-  _ops.launch_count += 2
+                               Cout, int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "exp_conv_wgrad")
+  _n(2)
   return gW
 
 
+# ---- fully connected --------------------------------------------------------------------
 FC_LRELU, FC_TANGENT, FC_LINEAR, FC_NOBIAS = 0, 1, 2, 3
 
 
 def fc_fwd(x, W, bias=None, mode=FC_LRELU, mask_ref=None, out=None):
-  _chk(x, "x", 2); _chk(W, "W", 2)
+  ldx = _mat(x, "x"); _chk(W, "W", 2)
   M, K = x.shape
   N = W.shape[1]
   assert W.shape[0] == K
   y = torch.empty(M, N, device=x.device, dtype=torch.float32) if out is None else out
+  ldy = _mat(y, "y")
+  ldm = _mat(mask_ref, "mask_ref") if mask_ref is not None else 0
   l = _cabi.lib()
   ws = _workspace(x.device, l.exp_fc_workspace_bytes(M, K, N))
-  _cabi.check(l.exp_fc_fwd(x.data_ptr(), W.data_ptr(), _p(bias), _p(mask_ref), y.data_ptr(), M, K, N, mode,
-                           ws.data_ptr(), ws.numel(), _stream()), "exp_fc_fwd")
-  _ops.launch_count += 2
+  _cabi.check(l.exp_fc_fwd(x.data_ptr(), ldx, W.data_ptr(), _p(bias), _p(mask_ref), ldm, y.data_ptr(), ldy, M, K, N,
+                           mode, ws.data_ptr(), ws.numel(), _stream()), "exp_fc_fwd")
+  _n(2)
   return y
 
 
-def fc_dgrad(dy, W, mul=None, mul_mode=0, out=None):
-  _chk(dy, "dy", 2); _chk(W, "W", 2)
+def fc_dgrad(dy, W, mul_act=None, mul_plain=None, out=None, accumulate=False):
+  """dx = (out if accumulate else 0) + dy W^T * lrelu'(mul_act) * mul_plain."""
+  ldy = _mat(dy, "dy"); _chk(W, "W", 2)
   M, N = dy.shape
   K = W.shape[0]
+  assert W.shape[1] == N
   dx = torch.empty(M, K, device=dy.device, dtype=torch.float32) if out is None else out
-  _cabi.check(_cabi.lib().exp_fc_dgrad(dy.data_ptr(), W.data_ptr(), _p(mul), mul_mode, dx.data_ptr(), M, K, N,
-                                       _stream()), "exp_fc_dgrad")
-  _ops.launch_count += 1
+  lddx = _mat(dx, "dx")
+  ldmul = 0
+  for m in (mul_act, mul_plain):
+    if m is not None:
+      l_ = _mat(m, "mul")
+      assert ldmul in (0, l_), "both multipliers must share a leading dimension"
+      ldmul = l_
+  _cabi.check(_cabi.lib().exp_fc_dgrad(dy.data_ptr(), ldy, W.data_ptr(), _p(mul_act), _p(mul_plain), ldmul,
+                                       dx.data_ptr(), lddx, M, K, N, int(accumulate), _stream()), "exp_fc_dgrad")
+  _n()
   return dx
 
 
-def fc_wgrad(x, dy, out=None):
-  _chk(x, "x", 2); _chk(dy, "dy", 2)
+def fc_wgrad(x, dy, out=None, accumulate=False):
+  ldx = _mat(x, "x"); ldy = _mat(dy, "dy")
   M, K = x.shape
   N = dy.shape[1]
   gW = torch.empty(K, N, device=x.device, dtype=torch.float32) if out is None else out
-  _cabi.check(_cabi.lib().exp_fc_wgrad(x.data_ptr(), dy.data_ptr(), gW.data_ptr(), M, K, N, _stream()), "exp_fc_wgrad")
-  _ops.launch_count += 1
+  _chk(gW, "gW", 2)
+  _cabi.check(_cabi.lib().exp_fc_wgrad(x.data_ptr(), ldx, dy.data_ptr(), ldy, gW.data_ptr(), M, K, N, int(accumulate),
+                                       _stream()), "exp_fc_wgrad")
+  _n()
   return gW
 
 
-def colsum(a, out=None):
-  """Column sums of a [rows, cols] (any leading dims are flattened into rows)."""
+def colsum(a, batch=1, out=None):
+  """out[batch, cols] = column sums of a viewed as [batch, rows, cols] (cols = last dim)."""
   _chk(a, "a")
   cols = a.shape[-1]
-  rows = a.numel() // cols
-  o = torch.empty(cols, device=a.device, dtype=torch.float32) if out is None else out
-  _cabi.check(_cabi.lib().exp_colsum(a.data_ptr(), rows, cols, o.data_ptr(), _stream()), "exp_colsum")
-  _ops.launch_count += 1
+  rows = a.numel() // cols // batch
+  o = torch.empty((batch, cols) if batch > 1 else (cols,), device=a.device, dtype=torch.float32) if out is None else out
+  _cabi.check(_cabi.lib().exp_colsum(a.data_ptr(), batch, rows, cols, o.data_ptr(), _stream()), "exp_colsum")
+  _n()
   return o
+
+
+# ---- per-image heads --------------------------------------------------------------------
+def stats_fwd(img):
+  _chk(img, "img", 4)
+  B, H, W, _ = img.shape
+  s = torch.empty(B, 3, device=img.device, dtype=torch.float32)
+  _cabi.check(_cabi.lib().exp_stats_fwd(img.data_ptr(), s.data_ptr(), B, H, W, _stream()), "exp_stats_fwd")
+  _n()
+  return s
+
+
+def stats_bwd(img, stats, g_stat, g_direct=None, out=None):
+  _chk(img, "img", 4); _chk(g_stat, "g_stat", 2)
+  B, H, W, _ = img.shape
+  g = torch.empty_like(img) if out is None else out
+  _cabi.check(_cabi.lib().exp_stats_bwd(img.data_ptr(), stats.data_ptr(), g_stat.data_ptr(), _p(g_direct), g.data_ptr(),
+                                        B, H, W, _stream()), "exp_stats_bwd")
+  _n()
+  return g
+
+
+def stats_jvp(img, stats, u):
+  _chk(img, "img", 4); _chk(u, "u", 4)
+  B, H, W, _ = img.shape
+  d = torch.empty(B, 3, device=img.device, dtype=torch.float32)
+  _cabi.check(_cabi.lib().exp_stats_jvp(img.data_ptr(), stats.data_ptr(), u.data_ptr(), d.data_ptr(), B, H, W, _stream()),
+              "exp_stats_jvp")
+  _n()
+  return d
+
+
+def policy_head_fwd(logits, noise, states, is_train, progress, cfg):
+  _chk(logits, "logits", 2); _chk(noise, "noise"); _chk(states, "states", 2)
+  B, n = logits.shape
+  dev = logits.device
+  pdf = torch.empty(B, n, device=dev)
+  ids = torch.empty(B, dtype=torch.int32, device=dev)
+  sur = torch.empty(B, device=dev); ent = torch.empty(B, device=dev); pen = torch.empty(B, device=dev)
+  ns = torch.empty_like(states)
+  _cabi.check(_cabi.lib().exp_policy_head_fwd(
+      logits.data_ptr(), noise.data_ptr(), states.data_ptr(), B, n, states.shape[1], int(is_train), int(cfg.test_steps),
+      float(cfg.exploration), float(cfg.exploration_penalty), float(cfg.filter_usage_penalty), float(progress),
+      pdf.data_ptr(), ids.data_ptr(), sur.data_ptr(), ent.data_ptr(), pen.data_ptr(), ns.data_ptr(), _stream()),
+      "exp_policy_head_fwd")
+  _n()
+  return pdf, ids, sur, ent, pen, ns
+
+
+def policy_head_bwd(logits, ids, g_surrogate, g_penalty, progress, cfg):
+  B, n = logits.shape
+  g = torch.empty_like(logits)
+  _cabi.check(_cabi.lib().exp_policy_head_bwd(logits.data_ptr(), ids.data_ptr(), g_surrogate.data_ptr(),
+                                              g_penalty.data_ptr(), B, n, float(cfg.exploration),
+                                              float(cfg.exploration_penalty), float(progress), g.data_ptr(), _stream()),
+              "exp_policy_head_bwd")
+  _n()
+  return g
+
+
+def overexposure_fwd(img):
+  _chk(img, "img", 4)
+  B, H, W, _ = img.shape
+  pen = torch.empty(B, device=img.device)
+  _cabi.check(_cabi.lib().exp_overexposure_fwd(img.data_ptr(), pen.data_ptr(), B, H, W, _stream()), "exp_overexposure_fwd")
+  _n()
+  return pen
+
+
+def overexposure_bwd(img, g_pen, g_in=None, out=None):
+  B, H, W, _ = img.shape
+  g = torch.empty_like(img) if out is None else out
+  _cabi.check(_cabi.lib().exp_overexposure_bwd(img.data_ptr(), g_pen.data_ptr(), _p(g_in), g.data_ptr(), B, H, W, _stream()),
+              "exp_overexposure_bwd")
+  _n()
+  return g
+
+
+def rl_losses(fake_logit, fake_input_logit, old_value, new_value, penalty, surrogate, new_states, cfg):
+  """Returns (seeds[5,B], losses[2]); see exp_rl_losses."""
+  B = fake_logit.numel()
+  dev = fake_logit.device
+  seeds = torch.empty(5, B, device=dev)
+  losses = torch.empty(2, device=dev)
+  _cabi.check(_cabi.lib().exp_rl_losses(
+      fake_logit.data_ptr(), fake_input_logit.data_ptr(), old_value.data_ptr(), new_value.data_ptr(), penalty.data_ptr(),
+      surrogate.data_ptr(), new_states.data_ptr(), B, new_states.shape[1], float(cfg.all_reward),
+      float(cfg.critic_logit_multiplier), float(cfg.discount_factor), float(cfg.parameter_lr_mul),
+      int(cfg.maximum_trajectory_length), int(bool(cfg.use_penalty)), seeds.data_ptr(), losses.data_ptr(), _stream()),
+      "exp_rl_losses")
+  _n()
+  return seeds, losses
+
+
+def interpolate(real, fake, alpha, out=None):
+  B = real.shape[0]
+  n = real.numel() // B
+  o = torch.empty_like(real) if out is None else out
+  _cabi.check(_cabi.lib().exp_interpolate(real.data_ptr(), fake.data_ptr(), alpha.data_ptr(), o.data_ptr(), B, n, _stream()),
+              "exp_interpolate")
+  _n()
+  return o
+
+
+def gp_scale(g, lam, batch_for_mean=None, out=None):
+  """Returns (u, norm): u = g * lam * 2 max(norm-1,0) / (B norm)."""
+  B = g.shape[0]
+  n = g.numel() // B
+  u = torch.empty_like(g) if out is None else out
+  norm = torch.empty(B, device=g.device)
+  _cabi.check(_cabi.lib().exp_gp_scale(g.data_ptr(), u.data_ptr(), norm.data_ptr(), float(lam),
+                                       int(batch_for_mean or B), n, _stream()), "exp_gp_scale")
+  _n()
+  return u, norm
+
+
+def adam(params, grads, m, v, hyper, beta1, beta2, eps=1e-8, grad_scale=1.0):
+  """In-place fused Adam on flat buffers; hyper[0] = lr_t (device scalar)."""
+  for t in (params, grads, m, v):
+    _chk(t, "adam buffer")
+  _cabi.check(_cabi.lib().exp_adam(params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), hyper.data_ptr(),
+                                   float(beta1), float(beta2), float(eps), float(grad_scale), params.numel(), _stream()),
+              "exp_adam")
+  _n()

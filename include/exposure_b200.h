@@ -139,24 +139,85 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
                    int IW, int Cin, int Cout, void* stream);
 
 /* gW[4,4,Cin,Cout] = Conv2DBackpropFilter(input as in exp_conv_fwd, dy); deterministic
- * split-K through `workspace` (size from exp_conv_wgrad_workspace_bytes). */
+ * split-K through `workspace` (size from exp_conv_wgrad_workspace_bytes); accumulate != 0
+ * adds to gW instead of overwriting (gradient-penalty term, several losses). */
 size_t exp_conv_wgrad_workspace_bytes(int B, int IH, int IW, int Cin, int Cout);
 int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift, const float* dy,
-                   float* gW, int B, int IH, int IW, int Cout, void* workspace,
+                   float* gW, int B, int IH, int IW, int Cout, int accumulate, void* workspace,
                    size_t workspace_bytes, void* stream);
 
-/* y[M,N] = epi(x[M,K] W[K,N]); mode 0: lrelu(v+bias), 1: v*lrelu'(mask_ref) (tangent),
+/* FC layers take leading dimensions (row strides, in floats) so that several heads can share
+ * one activation matrix: element (m,k) of x is x[m*ldx + k], etc.
+ * y[M,N] = epi(x[M,K] W[K,N]); mode 0: lrelu(v+bias), 1: v*lrelu'(mask_ref) (tangent),
  * 2: v+bias, 3: v.  Deterministic split-K through `workspace`. */
 size_t exp_fc_workspace_bytes(int M, int K, int N);
-int exp_fc_fwd(const float* x, const float* W, const float* bias, const float* mask_ref, float* y,
-               int M, int K, int N, int mode, void* workspace, size_t workspace_bytes, void* stream);
-/* dx[M,K] = dy[M,N] W^T, then * lrelu'(mul) (mul_mode 1) or * mul (mul_mode 2, dropout). */
-int exp_fc_dgrad(const float* dy, const float* W, const float* mul, int mul_mode, float* dx, int M,
-                 int K, int N, void* stream);
-/* gW[K,N] = x^T dy */
-int exp_fc_wgrad(const float* x, const float* dy, float* gW, int M, int K, int N, void* stream);
-/* out[cols] = column sums of a[rows, cols] (bias gradients) */
-int exp_colsum(const float* a, int rows, int cols, float* out, void* stream);
+int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const float* mask_ref,
+               int ldmask, float* y, int ldy, int M, int K, int N, int mode, void* workspace,
+               size_t workspace_bytes, void* stream);
+/* dx[M,K] = (accumulate ? dx : 0) + dy[M,N] W^T * lrelu'(mul_act) * mul_plain
+ * (either multiplier may be NULL; mul_plain is the tf.nn.dropout mask*2 of agent.py:36). */
+int exp_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act, const float* mul_plain,
+                 int ldmul, float* dx, int lddx, int M, int K, int N, int accumulate, void* stream);
+/* gW[K,N] = (accumulate ? gW : 0) + x^T dy */
+int exp_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, int M, int K, int N,
+                 int accumulate, void* stream);
+/* out[batch, cols] = column sums of a[batch, rows, cols] (bias gradients; per-image channel
+ * sums of the layer-1 input gradient that feed exp_stats_bwd). */
+int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* stream);
+
+/* ======================================================================================
+ * Per-image head math of the train step (all enqueue-only, no host round trip).
+ * ==================================================================================== */
+
+/* stats[B,3] = (mean luminance, population variance of luminance, mean saturation) of
+ * critics.py:48-76 (the three channels the critic / value CNN input is enriched with). */
+int exp_stats_fwd(const float* img, float* stats, int B, int H, int W, void* stream);
+/* g_out[B,H,W,3] = (g_direct ? g_direct : 0) + J_stats^T g_stat   (tf.gradients through
+ * tf.nn.moments / reduce_max / reduce_min / clip_by_value with TF's tie rules). */
+int exp_stats_bwd(const float* img, const float* stats, const float* g_stat, const float* g_direct,
+                  float* g_out, int B, int H, int W, void* stream);
+/* dstat[B,3] = J_stats u : forward-mode tangent used by the gradient-penalty term. */
+int exp_stats_jvp(const float* img, const float* stats, const float* u, float* dstat, int B, int H,
+                  int W, void* stream);
+
+/* Action-selection head, agent.py:100-122 + 208-252 + pdf_sample_layer.py:5-10:
+ * logits[B,n] (selector_fc2 output), noise[B] (= z[:,0]), states[B,3+n] ->
+ * pdf[B,n], ids[B] (int32; -1 reproduces the u==0 quirk of pdf_sample), surrogate[B],
+ * entropy[B], penalty_head[B] (entropy + filter-usage penalties), new_states[B,3+n]. */
+int exp_policy_head_fwd(const float* logits, const float* noise, const float* states, int B,
+                        int n_filters, int n_states, int is_train, int test_steps, float exploration,
+                        float exploration_penalty, float filter_usage_penalty, float progress,
+                        float* pdf, int* ids, float* surrogate, float* entropy, float* penalty_head,
+                        float* new_states, void* stream);
+int exp_policy_head_bwd(const float* logits, const int* ids, const float* g_surrogate,
+                        const float* g_penalty, int B, int n_filters, float exploration,
+                        float exploration_penalty, float progress, float* g_logits, void* stream);
+
+/* pen[b] = mean(max(img-1,0)^2) (agent.py:247) and its backward
+ * g_out = (g_in ? g_in : 0) + g_pen[b] * 2 max(img-1,0) / (H*W*3). */
+int exp_overexposure_fwd(const float* img, float* pen, int B, int H, int W, void* stream);
+int exp_overexposure_bwd(const float* img, const float* g_pen, const float* g_in, float* g_out, int B,
+                         int H, int W, void* stream);
+
+/* Reward / TD / advantage / losses of net.py:92-163 and the gradient seeds of g_loss and
+ * v_loss: seeds[5][B] = d g_loss/d fake_logit, d g_loss/d new_value, d v_loss/d old_value,
+ * d g_loss/d penalty, d g_loss/d surrogate; losses[2] = (g_loss, v_loss). */
+int exp_rl_losses(const float* fake_logit, const float* fake_input_logit, const float* old_value,
+                  const float* new_value, const float* penalty, const float* surrogate,
+                  const float* new_states, int B, int n_states, float all_reward,
+                  float critic_logit_multiplier, float discount_factor, float parameter_lr_mul,
+                  int max_traj_len, int use_penalty, float* seeds, float* losses, void* stream);
+
+/* WGAN-GP helpers, net.py:174-187: out = real + alpha[b] (fake - real) over n floats per
+ * image; norm[b] = sqrt(1e-6 + sum g^2), u = g * lambda * 2 max(norm-1,0) / (B norm). */
+int exp_interpolate(const float* real, const float* fake, const float* alpha, float* out, int B, int n,
+                    void* stream);
+int exp_gp_scale(const float* g, float* u, float* norm, float lambda, int B, int n, void* stream);
+
+/* Fused Adam over one flat buffer (tf.train.AdamOptimizer, config_example.py:158):
+ * hyper[0] (device) = lr * sqrt(1-beta2^t) / (1-beta1^t); g is multiplied by grad_scale. */
+int exp_adam(float* params, const float* grads, float* m, float* v, const float* hyper, float beta1,
+             float beta2, float eps, float grad_scale, size_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,8 +50,8 @@ def critic_stats(images):
   luminance = lum.mean(dim=(1, 2))
   contrast = ((lum - luminance[:, None, None]) ** 2).mean(dim=(1, 2))     # tf.nn.moments: population variance
   c = images.clamp(0.0, 1.0)
-  i_max = c.max(dim=3).values
-  i_min = c.min(dim=3).values
+  i_max = c.amax(dim=3)          # amax/amin split the gradient evenly among ties, like TF's reduce_max
+  i_min = c.amin(dim=3)
   sat = (i_max - i_min) / (torch.minimum(i_max + i_min, 2.0 - i_max - i_min) + 1e-2)
   saturation = sat.mean(dim=(1, 2))
   return torch.stack([luminance, contrast, saturation], dim=1)
@@ -86,3 +86,42 @@ def gradient_penalty(interpolated, params, lam=10.0):
   (g,) = torch.autograd.grad(logit.sum(), [x], create_graph=True)
   norm = torch.sqrt(1e-6 + (g ** 2).sum(dim=(1, 2, 3)))
   return lam * torch.mean(torch.clamp(norm - 1.0, min=0.0) ** 2), norm, g
+
+
+def policy_head(logits, u, states, is_train, progress, cfg):
+  """agent.py:100-122, 208-252: pdf, sampled id, surrogate, entropy, head penalties, new states.
+  cfg needs: exploration, test_steps, exploration_penalty, filter_usage_penalty."""
+  n = logits.shape[1]
+  pdf = torch.softmax(logits, dim=1) + 1e-37
+  pdf = pdf * (1 - cfg.exploration) + cfg.exploration * 1.0 / n
+  pdf = pdf / (pdf.sum(dim=1, keepdim=True) + 1e-30)
+  entropy = (-pdf * torch.log(pdf)).sum(dim=1, keepdim=True)
+  random_id = pdf_sample(pdf, u)
+  max_id = torch.argmax(pdf, dim=1).to(torch.int32)
+  ids = is_train * random_id + (1 - is_train) * max_id
+  onehot = torch.zeros_like(pdf)
+  valid = ids >= 0
+  onehot[valid, ids[valid].long()] = 1.0
+  surrogate = (onehot * torch.log(pdf + 1e-10)).sum(dim=1, keepdim=True)
+  is_last = (torch.abs(states[:, 2:3] + 1 - cfg.test_steps) < 1e-4).to(logits.dtype)
+  usage = states[:, 3:]
+  usage_penalty = (usage * onehot).sum(dim=1, keepdim=True)
+  new_states = torch.cat([is_last, is_last, states[:, 2:3] + 1, torch.maximum(usage, onehot)], dim=1)
+  entropy_penalty = (1.0 - progress) * cfg.exploration_penalty * (-entropy + math.log(n))
+  penalty_head = entropy_penalty + usage_penalty * cfg.filter_usage_penalty
+  return pdf, ids, surrogate, entropy, penalty_head, new_states
+
+
+def rl_losses(fake_logit, fake_input_logit, old_value, new_value, penalty, surrogate, new_states, cfg):
+  """net.py:92-163 (WGAN branch, use_TD).  All inputs [B,1]; returns (g_loss, v_loss)."""
+  stopped = new_states[:, 1:2]
+  clear_final = (new_states[:, 2:3] > cfg.maximum_trajectory_length).to(fake_logit.dtype)
+  new_value = new_value * (1.0 - clear_final)
+  raw_reward = (cfg.all_reward + (1 - cfg.all_reward) * stopped) * \
+      (fake_logit - fake_input_logit.detach()) * cfg.critic_logit_multiplier
+  reward = raw_reward - penalty if cfg.use_penalty else raw_reward
+  q = reward + (1.0 - stopped) * cfg.discount_factor * new_value
+  advantage = q.detach() - old_value
+  v_loss = (advantage ** 2).mean()
+  g_loss = (-q * cfg.parameter_lr_mul + surrogate * (-advantage).detach()).mean()
+  return g_loss, v_loss

@@ -1,0 +1,338 @@
+"""Explicit (hand-scheduled) forward / backward of the Exposure networks on the C-ABI kernels.
+
+  CriticNet  -- critics.py:42-98: global statistics -> enriched input -> 4 x [conv4x4s2 + lrelu]
+                -> fc(128, lrelu) -> fc(1).  Used as WGAN critic (6 input channels) and, with the
+                11 state channels, as value network (17 channels), exactly like cfg.critic /
+                cfg.value = critic in config_example.py:98-99.
+  PolicyNet  -- agent.py:41-125: shared filter feature extractor + 8 filter heads
+                (filters.py:28-44), action-selection extractor + selector head, dropout always on.
+
+No autograd: every backward signal is produced by an explicit call sequence (hard
+part 2), so a train step is a fixed list of kernel launches (CUDA-graph capturable).  Variable
+names and layouts follow the reference checkpoint so weights map 1:1."""
+import math
+
+import torch
+
+from . import nn_ops as K
+from . import ops as F
+
+FEATURE_DIM = 4096            # cfg.feature_extractor_dims
+FC1 = 128                     # cfg.fc1_size
+CONV_CH = (32, 64, 128, 256)  # cfg.base_channels doubling (agent.py:24-33)
+NUM_PARAMS = F.NUM_PARAMS
+MASK_PARAMS = 6               # Filter.get_num_mask_parameters (filters.py:107-108)
+
+
+class ParamStore:
+  """All variables of one optimizer in ONE flat fp32 buffer (+ flat grads / Adam slots), with
+  named views.  One NCCL all-reduce and one fused Adam launch per optimizer step."""
+
+  def __init__(self, device):
+    self.device = device
+    self.specs = []          # (name, shape, fan_in, fan_out) ; fan_in == 0 -> zeros (biases)
+    self.flat = None
+
+  def add(self, name, shape, fan_in=0, fan_out=0):
+    assert self.flat is None
+    self.specs.append((name, tuple(shape), fan_in, fan_out))
+
+  def finalize(self, seed=0):
+    n = sum(int(math.prod(s[1])) for s in self.specs)
+    n_pad = (n + 3) // 4 * 4
+    dev = self.device
+    self.flat = torch.zeros(n_pad, device=dev)
+    self.grad = torch.zeros(n_pad, device=dev)
+    self.m = torch.zeros(n_pad, device=dev)
+    self.v = torch.zeros(n_pad, device=dev)
+    self.p, self.g, self.offsets = {}, {}, {}
+    g = torch.Generator().manual_seed(seed)
+    off = 0
+    for name, shape, fi, fo in self.specs:
+      k = int(math.prod(shape))
+      self.p[name] = self.flat[off:off + k].view(shape)
+      self.g[name] = self.grad[off:off + k].view(shape)
+      self.offsets[name] = (off, k)
+      if fi:   # tf.contrib.layers.xavier_initializer(uniform=True)
+        lim = math.sqrt(6.0 / (fi + fo))
+        self.p[name].copy_(((torch.rand(shape, generator=g) * 2 - 1) * lim).to(dev))
+      off += k
+    self.numel = n
+    return self
+
+  def zero_grad(self):
+    self.grad.zero_()
+
+
+def _add_conv_stack(store, scope, cin):
+  names = []
+  c = cin
+  for i, co in enumerate(CONV_CH):
+    base = "%s/Conv%s" % (scope, "" if i == 0 else "_%d" % i)
+    store.add(base + "/weights", (4, 4, c, co), 16 * c, 16 * co)
+    store.add(base + "/biases", (co,))
+    names.append(base)
+    c = co
+  return names
+
+
+class _Ctx:
+  pass
+
+
+class ConvStack:
+  """(x, vec) -> a1..a4 (post-lrelu activations) and everything needed to go back."""
+
+  def __init__(self, store, scope, cin):
+    self.store = store
+    self.cin = cin
+    self.names = _add_conv_stack(store, scope, cin)
+
+  def W(self, i):
+    return self.store.p[self.names[i] + "/weights"]
+
+  def b(self, i):
+    return self.store.p[self.names[i] + "/biases"]
+
+  def forward(self, img, vec, drop_mul=None):
+    """img [N,64,64,3], vec [N,cin-3].  Returns ctx with acts[0..3]; when drop_mul [N,4,4,256] is
+    given ctx.feat = a4 * drop_mul (tf.nn.dropout, agent.py:36) else ctx.feat = a4 (flattened)."""
+    c = _Ctx()
+    c.img, c.vec = img, vec
+    a = K.conv_fwd(img, self.W(0), self.b(0), vec=vec, shift=0.5)
+    acts = [a]
+    for i in (1, 2):
+      a = K.conv_fwd(a, self.W(i), self.b(i))
+      acts.append(a)
+    if drop_mul is None:
+      a = K.conv_fwd(a, self.W(3), self.b(3))
+      c.feat = a.view(a.shape[0], -1)
+    else:
+      a, d = K.conv_fwd(a, self.W(3), self.b(3), post_mul=drop_mul)
+      c.feat = d.view(d.shape[0], -1)
+    acts.append(a)
+    c.acts = acts
+    return c
+
+  def backward(self, c, delta4, param_grads=True, accumulate=False, sl=None):
+    """delta4 [N,4,4,256] = dL/d(pre-activation of conv 4).  Fills c.deltas[0..3]."""
+    d = delta4
+    deltas = [None, None, None, d]
+    for i in (3, 2, 1):
+      a_in = c.acts[i - 1]
+      d = K.conv_dgrad(d, self.W(i), tuple(a_in.shape), a_in=a_in)
+      deltas[i - 1] = d
+    c.deltas = deltas
+    if param_grads:
+      self.param_grads(c, accumulate=accumulate, sl=sl)
+
+  def param_grads(self, c, accumulate=False, sl=None):
+    """wgrad + bias grads from the samples in `sl` (a slice over the batch; default all)."""
+    s = sl if sl is not None else slice(None)
+    g = self.store.g
+    for i in range(4):
+      d = c.deltas[i][s]
+      if i == 0:
+        K.conv_wgrad(c.img[s], d, vec=c.vec[s], shift=0.5, out=g[self.names[0] + "/weights"], accumulate=accumulate)
+      else:
+        K.conv_wgrad(c.acts[i - 1][s], d, out=g[self.names[i] + "/weights"], accumulate=accumulate)
+      gb = g[self.names[i] + "/biases"]
+      if accumulate:
+        gb += K.colsum(d)
+      else:
+        K.colsum(d, out=gb)
+
+  def input_grad(self, c, sl=None):
+    """dL/d(enriched, shifted layer-1 input) [n,64,64,cin] for the samples in sl."""
+    s = sl if sl is not None else slice(None)
+    d1 = c.deltas[0][s]
+    n = d1.shape[0]
+    return K.conv_dgrad(d1, self.W(0), (n, 64, 64, self.cin))
+
+  def tangent(self, c, sl, t_img, t_vec):
+    """Forward-mode tangents t1..t4 of the samples in sl for input tangent (t_img, t_vec)."""
+    s = sl
+    t = K.conv_fwd(t_img, self.W(0), None, vec=t_vec, shift=0.0, mask_ref=c.acts[0][s])
+    ts = [t]
+    for i in (1, 2, 3):
+      t = K.conv_fwd(t, self.W(i), None, mask_ref=c.acts[i][s])
+      ts.append(t)
+    return ts
+
+  def tangent_param_grads(self, c, sl, t_img, t_vec, ts):
+    """Accumulate d<u, dD/dx>/dW_k = wgrad(t_{k-1}, delta_k)."""
+    g = self.store.g
+    K.conv_wgrad(t_img, c.deltas[0][sl], vec=t_vec, shift=0.0, out=g[self.names[0] + "/weights"], accumulate=True)
+    for i in (1, 2, 3):
+      K.conv_wgrad(ts[i - 1], c.deltas[i][sl], out=g[self.names[i] + "/weights"], accumulate=True)
+
+
+class CriticNet:
+  """critics.py:42-98 (critic when n_states == 0, value network when n_states == 11)."""
+
+  def __init__(self, store, scope, n_states=0):
+    self.store = store
+    self.n_states = n_states
+    self.conv = ConvStack(store, scope, 3 + n_states + 3)
+    self.fc1 = scope + "/fully_connected"
+    self.fc2 = scope + "/fully_connected_1"
+    store.add(self.fc1 + "/weights", (FEATURE_DIM, FC1), FEATURE_DIM, FC1)
+    store.add(self.fc1 + "/biases", (FC1,))
+    store.add(self.fc2 + "/weights", (FC1, 1), FC1, 1)
+    store.add(self.fc2 + "/biases", (1,))
+
+  def forward(self, images, states=None):
+    p = self.store.p
+    stats = K.stats_fwd(images)
+    vec = stats if states is None else torch.cat([states, stats], dim=1)
+    c = self.conv.forward(images, vec)
+    c.stats = stats
+    c.h = K.fc_fwd(c.feat, p[self.fc1 + "/weights"], p[self.fc1 + "/biases"], mode=K.FC_LRELU)
+    c.logit = K.fc_fwd(c.h, p[self.fc2 + "/weights"], p[self.fc2 + "/biases"], mode=K.FC_LINEAR)
+    return c
+
+  def backward(self, c, g_logit, param_grads=True, accumulate=False, sl=None):
+    """g_logit [N] = dL/dlogit.  Computes all deltas; parameter gradients from slice sl."""
+    p = self.store.p
+    c.d_fc2 = g_logit.reshape(-1, 1).contiguous()
+    c.d_h = K.fc_dgrad(c.d_fc2, p[self.fc2 + "/weights"], mul_act=c.h)
+    d4 = K.fc_dgrad(c.d_h, p[self.fc1 + "/weights"], mul_act=c.feat)
+    self.conv.backward(c, d4.view(-1, 4, 4, CONV_CH[3]), param_grads=False)
+    if param_grads:
+      self.param_grads(c, accumulate=accumulate, sl=sl)
+
+  def param_grads(self, c, accumulate=False, sl=None):
+    s = sl if sl is not None else slice(None)
+    g = self.store.g
+    self.conv.param_grads(c, accumulate=accumulate, sl=sl)
+    K.fc_wgrad(c.feat[s], c.d_h[s], out=g[self.fc1 + "/weights"], accumulate=accumulate)
+    K.fc_wgrad(c.h[s], c.d_fc2[s], out=g[self.fc2 + "/weights"], accumulate=accumulate)
+    for name, d in ((self.fc1, c.d_h[s]), (self.fc2, c.d_fc2[s])):
+      if accumulate:
+        g[name + "/biases"] += K.colsum(d)
+      else:
+        K.colsum(d, out=g[name + "/biases"])
+
+  def image_grad(self, c, sl=None, g_direct_extra=None):
+    """dL/dimages for the samples in sl: layer-1 dgrad, image channels + J_stats^T of the
+    three statistic channels (tf.gradients through critics.py:48-87)."""
+    s = sl if sl is not None else slice(None)
+    g_in = self.conv.input_grad(c, sl)                         # [n,64,64,cin]
+    n = g_in.shape[0]
+    g_vec = K.colsum(g_in, batch=n).reshape(n, -1)             # per-image channel sums
+    g_stat = g_vec[:, -3:].contiguous()
+    g_img = g_in[..., :3].contiguous()
+    return K.stats_bwd(c.img[s], c.stats[s], g_stat, g_direct=g_img)
+
+  def gradient_penalty_grads(self, c, sl, u):
+    """Accumulate d<u, d logit/d image>/dtheta for the samples in sl (net.py:181-194):
+    forward-mode tangent pass, then wgrad(tangent_{k-1}, delta_k)."""
+    p, g = self.store.p, self.store.g
+    img, stats = c.img[sl], c.stats[sl]
+    dstat = K.stats_jvp(img, stats, u)
+    if self.n_states:
+      dstat = torch.cat([torch.zeros(u.shape[0], self.n_states, device=u.device), dstat], dim=1)
+    ts = self.conv.tangent(c, sl, u, dstat)
+    t4 = ts[3].view(ts[3].shape[0], -1)
+    th = K.fc_fwd(t4, p[self.fc1 + "/weights"], None, mode=K.FC_TANGENT, mask_ref=c.h[sl])
+    self.conv.tangent_param_grads(c, sl, u, dstat, ts)
+    K.fc_wgrad(t4, c.d_h[sl], out=g[self.fc1 + "/weights"], accumulate=True)
+    K.fc_wgrad(th, c.d_fc2[sl], out=g[self.fc2 + "/weights"], accumulate=True)
+
+
+class PolicyNet:
+  """agent.py:41-125 with cfg.shared_feature_extractor = True."""
+
+  def __init__(self, store, n_states=11, scope="generator"):
+    self.store = store
+    self.n_filters = len(NUM_PARAMS)
+    self.fe = ConvStack(store, scope, 3 + n_states)
+    self.se = ConvStack(store, scope + "/action_selection", 3 + n_states)
+    # the 8 fc1 layers of the filter heads are stored as ONE [4096, 8*128] matrix (column block j
+    # == generator/filter_j/fc1/weights) so that they run as a single GEMM
+    self.fc1_all = scope + "/filter_fc1_all"
+    store.add(self.fc1_all + "/weights", (FEATURE_DIM, self.n_filters * FC1), FEATURE_DIM, FC1)
+    store.add(self.fc1_all + "/biases", (self.n_filters * FC1,))
+    self.fc2 = []
+    self.out_dims = [n + MASK_PARAMS for n in NUM_PARAMS]
+    for j, od in enumerate(self.out_dims):
+      name = "%s/filter_%d/fc2" % (scope, j)
+      store.add(name + "/weights", (FC1, od), FC1, od)
+      store.add(name + "/biases", (od,))
+      self.fc2.append(name)
+    self.sfc1 = scope + "/action_selection/selector_fc1"
+    self.sfc2 = scope + "/action_selection/selector_fc2"
+    store.add(self.sfc1 + "/weights", (FEATURE_DIM, FC1), FEATURE_DIM, FC1)
+    store.add(self.sfc1 + "/biases", (FC1,))
+    store.add(self.sfc2 + "/weights", (FC1, self.n_filters), FC1, self.n_filters)
+    store.add(self.sfc2 + "/biases", (self.n_filters,))
+    self.ostride = max(self.out_dims)          # 30
+
+  def forward(self, img, states, noise, drop_f, drop_s, is_train, progress, cfg, high_res=None):
+    """img [B,64,64,3], states [B,11], noise [B] (= z[:,0]), drop_* [B,4,4,256] in {0,2}.
+    Returns ctx with .out (filtered image), .new_states, .surrogate, .penalty, .ids, .pdf, ..."""
+    p = self.store.p
+    B = img.shape[0]
+    c = _Ctx()
+    c.img, c.states, c.progress, c.cfg = img, states, progress, cfg
+    c.drop_f, c.drop_s = drop_f, drop_s
+    c.f = self.fe.forward(img, states, drop_mul=drop_f)
+    c.s = self.se.forward(img, states, drop_mul=drop_s)
+    # filter heads (filters.py:28-44)
+    c.H = K.fc_fwd(c.f.feat, p[self.fc1_all + "/weights"], p[self.fc1_all + "/biases"], mode=K.FC_LRELU)
+    c.O = torch.zeros(B, self.n_filters, self.ostride, device=img.device)
+    Oflat = c.O.view(B, -1)
+    for j, name in enumerate(self.fc2):
+      K.fc_fwd(c.H[:, j * FC1:(j + 1) * FC1], p[name + "/weights"], p[name + "/biases"], mode=K.FC_LINEAR,
+               out=Oflat[:, j * self.ostride:j * self.ostride + self.out_dims[j]])
+    # action selection (agent.py:80-122)
+    c.hs = K.fc_fwd(c.s.feat, p[self.sfc1 + "/weights"], p[self.sfc1 + "/biases"], mode=K.FC_LRELU)
+    c.sel_logits = K.fc_fwd(c.hs, p[self.sfc2 + "/weights"], p[self.sfc2 + "/biases"], mode=K.FC_LINEAR)
+    c.pdf, c.ids, c.surrogate, c.entropy, c.pen_head, c.new_states = K.policy_head_fwd(
+        c.sel_logits, noise, states, is_train, progress, cfg)
+    # only the selected filter is evaluated (agent.py:124-125 computes all 8 and one-hot sums)
+    safe = c.ids.clamp(min=0).long()
+    c.logits_sel = c.O[torch.arange(B, device=img.device), safe][:, :F.PSTRIDE].contiguous()
+    c.params = F.filter_regress_fwd(c.logits_sel, c.ids)
+    c.out = F.filter_fwd(img, c.params, c.ids)
+    if high_res is not None:
+      c.high_res_out = F.filter_fwd(high_res, c.params, c.ids)
+    c.pen_img = K.overexposure_fwd(c.out)
+    c.penalty = c.pen_img + c.pen_head
+    return c
+
+  def backward(self, c, g_out, g_surrogate, g_penalty):
+    """g_out [B,64,64,3] = dL/d filtered image EXCLUDING the over-exposure penalty path (added
+    here), g_surrogate / g_penalty [B].  Fills the generator gradients (overwrite)."""
+    p, g = self.store.p, self.store.g
+    B = c.img.shape[0]
+    g_img = K.overexposure_bwd(c.out, g_penalty, g_in=g_out)
+    _, g_params = F.filter_bwd(c.img, g_img, c.params, c.ids, need_gx=False)
+    g_logits_sel = F.filter_regress_bwd(c.logits_sel, g_params, c.ids)           # [B,24]
+    G_O = torch.zeros_like(c.O)
+    safe = c.ids.clamp(min=0).long()
+    valid = (c.ids >= 0).to(g_logits_sel.dtype)[:, None]
+    G_O[torch.arange(B, device=c.img.device), safe, :F.PSTRIDE] = g_logits_sel * valid
+    G_Oflat = G_O.view(B, -1)
+    d_H = torch.empty_like(c.H)
+    for j, name in enumerate(self.fc2):
+      dy = G_Oflat[:, j * self.ostride:j * self.ostride + self.out_dims[j]]
+      Hj = c.H[:, j * FC1:(j + 1) * FC1]
+      K.fc_wgrad(Hj, dy, out=g[name + "/weights"])
+      g[name + "/biases"].copy_(dy.sum(dim=0))
+      K.fc_dgrad(dy, p[name + "/weights"], mul_act=Hj, out=d_H[:, j * FC1:(j + 1) * FC1])
+    K.fc_wgrad(c.f.feat, d_H, out=g[self.fc1_all + "/weights"])
+    K.colsum(d_H, out=g[self.fc1_all + "/biases"])
+    a4f = c.f.acts[3].view(B, -1)
+    d4 = K.fc_dgrad(d_H, p[self.fc1_all + "/weights"], mul_act=a4f, mul_plain=c.drop_f.view(B, -1))
+    self.fe.backward(c.f, d4.view(B, 4, 4, CONV_CH[3]))
+    # selector
+    g_sel = K.policy_head_bwd(c.sel_logits, c.ids, g_surrogate, g_penalty, c.progress, c.cfg)
+    K.fc_wgrad(c.hs, g_sel, out=g[self.sfc2 + "/weights"])
+    K.colsum(g_sel, out=g[self.sfc2 + "/biases"])
+    d_hs = K.fc_dgrad(g_sel, p[self.sfc2 + "/weights"], mul_act=c.hs)
+    K.fc_wgrad(c.s.feat, d_hs, out=g[self.sfc1 + "/weights"])
+    K.colsum(d_hs, out=g[self.sfc1 + "/biases"])
+    a4s = c.s.acts[3].view(B, -1)
+    d4s = K.fc_dgrad(d_hs, p[self.sfc1 + "/weights"], mul_act=a4s, mul_plain=c.drop_s.view(B, -1))
+    self.se.backward(c.s, d4s.view(B, 4, 4, CONV_CH[3]))

@@ -1,0 +1,132 @@
+"""Train-step driver: the generator+value step and the WGAN-GP critic step of net.py:298-403 as
+explicit kernel schedules, with one all-reduce per optimizer over NVLink (data parallel).
+
+Reference mapping
+  generator_step  == sess.run([(opt_g, opt_v), g_loss, v_loss, fake_output, new_states])  net.py:330
+  critic_step     == sess.run([opt_c, emd, critic_gradient_norm])                         net.py:362
+Losses / rewards follow net.py:92-199 (WGAN branch, use_TD), optimizers config_example.py:134-161
+(Adam beta1 0.5, beta2 0.9, lr_g = 0.3*5e-5*0.1^(3t/T), lr_v = 10 lr_g, lr_c = 5e-5*0.1^(3t/T))."""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import nn_ops as K
+from .nets import CriticNet, ParamStore, PolicyNet
+
+
+def default_cfg():
+  """The hot-path subset of config_example.py (same key names, same values)."""
+  from .util import Dict
+  cfg = Dict()
+  cfg.curve_steps = 8; cfg.gamma_range = 3; cfg.exposure_range = 3.5
+  cfg.color_curve_range = (0.90, 1.10); cfg.tone_curve_range = (0.5, 2)
+  cfg.masking = False; cfg.clamp = False
+  cfg.critic_logit_multiplier = 0.05; cfg.discount_factor = 1.0; cfg.filter_usage_penalty = 1.0
+  cfg.use_TD = True; cfg.replay_memory_size = 128; cfg.maximum_trajectory_length = 7
+  cfg.over_length_keep_prob = 0.5; cfg.all_reward = 1.0; cfg.img_include_states = True
+  cfg.exploration = 0.05; cfg.exploration_penalty = 0.05; cfg.early_stop_penalty = 1.0
+  cfg.source_img_size = 64; cfg.base_channels = 32; cfg.dropout_keep_prob = 0.5
+  cfg.shared_feature_extractor = True; cfg.fc1_size = 128; cfg.feature_extractor_dims = 4096
+  cfg.use_penalty = True; cfg.gan = "w"; cfg.giters = 1; cfg.gradient_penalty_lambda = 10
+  cfg.citers = 5; cfg.critic_initialization = 10; cfg.num_state_dim = 11; cfg.z_dim = 3 + 8 * 16
+  cfg.test_steps = 5; cfg.real_img_size = 64; cfg.supervised = False; cfg.batch_size = 64
+  cfg.max_iter_step = 20000; cfg.parameter_lr_mul = 1; cfg.value_lr_mul = 10
+  cfg.lr_g = lambda t: 0.3 * 5e-5 * 0.1 ** (1.0 * t * 3 / cfg.max_iter_step)
+  cfg.lr_c = lambda t: 1 * 5e-5 * 0.1 ** (1.0 * t * 3 / cfg.max_iter_step)
+  cfg.adam_beta1 = 0.5; cfg.adam_beta2 = 0.9
+  return cfg
+
+
+class Trainer:
+  """Owns theta_g / theta_v / theta_c (net.py:205-210), their Adam state and the step schedules."""
+
+  def __init__(self, cfg=None, device=None, seed=0):
+    self.cfg = cfg or default_cfg()
+    self.device = device or torch.device("cuda", torch.cuda.current_device())
+    self.gen = ParamStore(self.device)
+    self.policy = PolicyNet(self.gen, n_states=self.cfg.num_state_dim, scope="generator")
+    self.gen.finalize(seed)
+    self.val = ParamStore(self.device)
+    self.value = CriticNet(self.val, "rl_value/critic", n_states=self.cfg.num_state_dim)
+    self.val.finalize(seed + 1)
+    self.cri = ParamStore(self.device)
+    self.critic = CriticNet(self.cri, "critic", n_states=0)
+    self.cri.finalize(seed + 2)
+    self.counter_g = self.counter_v = self.counter_c = 0        # net.py:216-241 global steps
+    self._hyper = {k: torch.zeros(1, device=self.device) for k in "gvc"}
+    self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+  # ---- optimizer --------------------------------------------------------------------------
+  def _adam(self, store, key, lr, t):
+    b1, b2 = self.cfg.adam_beta1, self.cfg.adam_beta2
+    lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+    self._hyper[key].fill_(lr_t)
+    if self.world > 1:
+      dist.all_reduce(store.grad)                                # ONE all-reduce per optimizer step
+    K.adam(store.flat, store.grad, store.m, store.v, self._hyper[key], b1, b2, 1e-8, 1.0 / self.world)
+
+  # ---- generator + value step (net.py:56-163, 222-239, 330) ---------------------------------
+  def generator_forward(self, fake_input, states, noise, drop_f, drop_s, progress, is_train=1):
+    c = self.policy.forward(fake_input, states, noise, drop_f, drop_s, is_train, progress, self.cfg)
+    return c
+
+  def generator_step(self, fake_input, states, noise, drop_f, drop_s, progress, lr_g, is_train=1, apply=True):
+    """Returns dict(fake_output, new_states, g_loss, v_loss, ...) (device tensors, no sync)."""
+    c = self.policy.forward(fake_input, states, noise, drop_f, drop_s, is_train, progress, self.cfg)
+    cc_out = self.critic.forward(c.out)                          # fake_logit            net.py:70-71
+    cc_in = self.critic.forward(fake_input)                      # fake_input_logit (stop_gradient) net.py:72-73
+    v_old = self.value.forward(fake_input, states)               # old_value             net.py:79-84
+    v_new = self.value.forward(c.out, c.new_states)              # new_value             net.py:85-90
+    seeds, losses = K.rl_losses(cc_out.logit.view(-1), cc_in.logit.view(-1), v_old.logit.view(-1),
+                                v_new.logit.view(-1), c.penalty, c.surrogate, c.new_states, self.cfg)
+    # theta_v: v_loss = mean(advantage^2), advantage = stop_gradient(q) - old_value
+    self.value.backward(v_old, seeds[2], param_grads=True)
+    # theta_g: pathwise gradient through critic(fake_output) and value(fake_output, new_states)
+    self.critic.backward(cc_out, seeds[0], param_grads=False)
+    g_img = self.critic.image_grad(cc_out)
+    self.value.backward(v_new, seeds[1], param_grads=False)
+    g_img = g_img + self.value.image_grad(v_new)
+    self.policy.backward(c, g_img, seeds[4], seeds[3])
+    if apply:
+      self.counter_g += 1
+      self.counter_v += 1
+      self._adam(self.gen, "g", lr_g, self.counter_g)
+      self._adam(self.val, "v", self.cfg.value_lr_mul * lr_g, self.counter_v)
+    return dict(fake_output=c.out, new_states=c.new_states, g_loss=losses[0], v_loss=losses[1], ctx=c,
+                fake_logit=cc_out.logit, old_value=v_old.logit, new_value=v_new.logit, seeds=seeds)
+
+  # ---- critic step (net.py:68-71, 151, 174-194, 245-251, 362) -------------------------------
+  def critic_step(self, real, fake, alpha, lr_c, apply=True):
+    """real, fake [B,64,64,3]; alpha [B] ~ U[0,1).  c_loss = mean(D(fake) - D(real)) + GP."""
+    B = real.shape[0]
+    lam = float(self.cfg.gradient_penalty_lambda)
+    xhat = K.interpolate(real, fake, alpha)
+    X = torch.cat([real, fake, xhat], dim=0)
+    c = self.critic.forward(X)
+    g_logit = torch.empty(3 * B, device=real.device)
+    g_logit[:B] = -1.0 / B
+    g_logit[B:2 * B] = 1.0 / B
+    g_logit[2 * B:] = 1.0
+    self.critic.backward(c, g_logit, param_grads=True, sl=slice(0, 2 * B))
+    sl = slice(2 * B, 3 * B)
+    g = self.critic.image_grad(c, sl)                            # d inte_logit / d interpolated  net.py:181-183
+    u, norm = K.gp_scale(g, lam)                                 # d GP / d gradients             net.py:185-187
+    if lam > 0:
+      self.critic.gradient_penalty_grads(c, sl, u)
+    logit = c.logit.view(-1)
+    emd = logit[:B].mean() - logit[B:2 * B].mean()               # net.py:164  emd = -c_loss (before GP)
+    gp = lam * (torch.clamp(norm - 1.0, min=0.0) ** 2).mean()
+    if apply:
+      self.counter_c += 1
+      self._adam(self.cri, "c", lr_c, self.counter_c)
+    return dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit)
+
+  # ---- random draws the reference makes per step (explicit so tests can inject them) -------
+  def draw(self, B, generator=None):
+    dev = self.device
+    noise = torch.rand(B, device=dev, generator=generator)                                     # z[:,0]  replay_memory.py:176-184
+    keep = float(self.cfg.dropout_keep_prob)
+    mk = lambda: torch.floor(keep + torch.rand(B, 4, 4, 256, device=dev, generator=generator)) / keep   # tf.nn.dropout
+    alpha = torch.rand(B, device=dev, generator=generator)                                     # net.py:175-176
+    return noise, mk(), mk(), alpha

@@ -153,7 +153,7 @@ def test_stats_fwd_bwd_jvp(nn):
   _close(sd, st.detach(), tol=1e-5)
   gs = _rand(B, 3, seed=4)
   gdir = _rand(B, H, W, 3, seed=5)
-  (gx,) = torch.autograd.grad(st, [xr], grad_outputs=gs)
+  (gx,) = torch.autograd.grad(st, [xr], grad_outputs=gs, retain_graph=True)
   gd = nn.stats_bwd(x.float().cuda(), sd, gs.float().cuda(), g_direct=gdir.float().cuda())
   _close(gd, gx + gdir, tol=1e-5)
   u = _rand(B, H, W, 3, seed=6)

@@ -41,7 +41,7 @@ def parse_args():
   ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=10)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
-  ap.add_argument("--workload", default="chain8", choices=["chain8"])
+  ap.add_argument("--workload", default="chain8", choices=["chain8", "train"])
   ap.add_argument("--batch", type=int, default=64, help="images per GPU")
   ap.add_argument("--size", type=int, default=512)
   ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 tma (exposure_b200.h)")
@@ -362,10 +362,224 @@ def run_native(args):
     print(json.dumps(out))
 
 
+def train_config(args):
+  return {
+      "workload": "train: 1 generator+value step + 5 WGAN-GP critic steps per iteration, replay memory on device "
+                  "(BASELINE.json configs[3]; net.py:307-370)",
+      "batch_per_gpu": args.batch, "height": 64, "width": 64, "channels": 3, "filters": "E,G,W,S+,T,Ct,BW,C",
+      "giters": 1, "citers": 5,
+      "parallelism": "dp%d (batch sharded by image; one NCCL all-reduce per optimizer step)" % args.gpus,
+      "l2_policy": "working set is L2 resident by nature (3 MB batches); every iteration draws fresh replay "
+                   "batches, dropout masks and noise",
+  }
+
+
+def run_train(args):
+  """configs[3]: full train iteration at batch 64x64x64 per GPU, data parallel."""
+  import torch
+  import torch.distributed as dist
+  from exposure_b200 import ops
+  from exposure_b200.replay import ReplayMemory, SyntheticProvider
+  from exposure_b200.trainer import Trainer, default_cfg
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  cfg = default_cfg()
+  cfg.batch_size = args.batch
+  cfg.replay_memory_size = 2 * args.batch
+  B = args.batch
+  t = Trainer(cfg, dev, seed=0)                       # identical initial weights on every rank
+  mem = ReplayMemory(cfg, SyntheticProvider(dev, "raw", 100 + rank), SyntheticProvider(dev, "real", 200 + rank), dev,
+                     seed=rank)
+  t.attach_memory(mem, torch.Generator(device=dev).manual_seed(300 + rank))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # bootstrap like iteration 0 of net.py:318-328 (generator steps with lr 0 until terminated
+  # records exist), shortened: 2 * test_steps generator steps are enough to terminate records
+  t.train_iteration(0, giters=2 * cfg.test_steps + 2, citers=1)
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  it = 1
+  for _ in range(max(args.warmup, 3)):
+    t.train_iteration(it, giters=1, citers=5)
+    it += 1
+  barrier()
+  ops.event_log = []
+  l0 = ops.launch_count
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  wall0 = time.time()
+  e0.record()
+  last = None
+  for _ in range(args.steps):
+    last = t.train_iteration(it, giters=1, citers=5)
+    it += 1
+  e1.record()
+  barrier()
+  wall1 = time.time()
+  elapsed_ms = e0.elapsed_time(e1)
+  launches = ops.launch_count - l0
+  log, ops.event_log = ops.event_log, None
+  tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  elapsed_ms = float(tt.item())
+  value = world * B * args.steps / (elapsed_ms / 1e3)
+
+  per = {}
+  for name, flops, a, b in log:
+    d = per.setdefault(name, {"ms": 0.0, "flops": 0, "n": 0})
+    d["ms"] += a.elapsed_time(b); d["flops"] += flops; d["n"] += 1
+  kernels = [{"kernel": k, "launches": d["n"], "avg_ms": d["ms"] / d["n"], "tflops": d["flops"] / d["ms"] / 1e9}
+             for k, d in sorted(per.items(), key=lambda kv: -kv[1]["ms"])]
+  peak_tf = 1389.9
+  pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(pk):
+    peak_tf = float(json.load(open(pk)).get("bf16_tflops_sustained", peak_tf))
+  tot_ms = sum(d["ms"] for d in per.values()) or 1.0
+  tot_fl = sum(d["flops"] for d in per.values())
+  roofline = {"bound": "tensor", "kernel": "gemm_kernel family (conv fprop/dgrad/wgrad; exact-fp32 CUDA-core path, "
+                                            "tcgen05 not yet used -- DESIGN.md section 7)",
+              "achieved": tot_fl / tot_ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": tot_fl / tot_ms / 1e9 / peak_tf,
+              "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16)",
+              "share_of_step": tot_ms / elapsed_ms, "kernels": kernels}
+
+  # end-to-end leg: fresh RAW and real batches come from pinned host memory every step, the
+  # filtered batch and the losses go back to the host (what net.py:330-342 does per sess.run)
+  hraw = torch.empty(B, 64, 64, 3).pin_memory(); hraw.copy_(mem.fake_dataset.get_next_batch(B).cpu())
+  hreal = torch.empty(B, 64, 64, 3).pin_memory(); hreal.copy_(mem.real_dataset.get_next_batch(B).cpu())
+  hout = torch.empty(B, 64, 64, 3).pin_memory()
+  hloss = torch.empty(4).pin_memory()
+
+  class HostProvider:
+    def __init__(self, h):
+      self.h = h
+    def get_next_batch(self, n):
+      return self.h[:n].to(dev, non_blocking=True)
+
+  mem.fake_dataset, mem.real_dataset = HostProvider(hraw), HostProvider(hreal)
+  h2d = [0]
+
+  def e2e_iter():
+    nonlocal it
+    out = t.train_iteration(it, giters=1, citers=5)
+    it += 1
+    hloss.copy_(torch.stack([out["g_loss"], out["v_loss"], out["emd"], out["critic_gradient_norm"]]), non_blocking=True)
+    hout.copy_(mem.images[:B], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+  for _ in range(2):
+    e2e_iter()
+  barrier()
+  n_e2e = max(3, min(args.steps, 20))
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(n_e2e):
+    e2e_iter()
+  b.record()
+  barrier()
+  tt = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  e2e_ms = float(tt.item())
+  e2e = {"value": world * B * n_e2e / (e2e_ms / 1e3), "unit": "images/s",
+         "h2d_bytes_per_step": 6 * B * 64 * 64 * 3 * 4, "d2h_bytes_per_step": B * 64 * 64 * 3 * 4 + 16,
+         "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
+         "note": "h2d upper bound: 5 real batches + up to 1 fresh RAW batch per iteration"}
+  clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+  if rank == 0:
+    out = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(args),
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+           "losses": {k: (float(v) if v is not None else None) for k, v in last.items()}}
+    if world == 1:
+      out["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline_train(B)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+  if rank == 0:
+    print(json.dumps(out))
+
+
+def cpu_baseline_train(B, budget_s=25.0):
+  """The reference's CPU path for one train iteration: oracle generator step + 5 critic steps
+  (autograd, all 8 filters + one-hot select), on a bounded sample of the batch."""
+  import torch
+  from oracle import filters as OF
+  from oracle import train_step as OT
+  from exposure_b200.trainer import default_cfg
+  cores = host_threads()
+  torch.set_num_threads(cores)
+  cfg = default_cfg()
+  sb = min(B, 8)
+  g = torch.Generator().manual_seed(0)
+  shapes_c = {"critic": 6, "rl_value/critic": 17}
+  def make(scope, cin):
+    P = {}
+    c = cin
+    for i, co in enumerate((32, 64, 128, 256)):
+      n = "%s/Conv%s" % (scope, "" if i == 0 else "_%d" % i)
+      P[n + "/weights"] = torch.randn(4, 4, c, co, generator=g) * 0.05
+      P[n + "/biases"] = torch.zeros(co)
+      c = co
+    return P
+  Pc = make("critic", 6); Pv = make("rl_value/critic", 17)
+  for P, s in ((Pc, "critic"), (Pv, "rl_value/critic")):
+    P[s + "/fully_connected/weights"] = torch.randn(4096, 128, generator=g) * 0.02; P[s + "/fully_connected/biases"] = torch.zeros(128)
+    P[s + "/fully_connected_1/weights"] = torch.randn(128, 1, generator=g) * 0.1; P[s + "/fully_connected_1/biases"] = torch.zeros(1)
+  Pg = make("generator", 14); Pg.update(make("generator/action_selection", 14))
+  for j, n in enumerate(OF.NUM_PARAMS):
+    Pg["generator/filter_%d/fc1/weights" % j] = torch.randn(4096, 128, generator=g) * 0.02
+    Pg["generator/filter_%d/fc1/biases" % j] = torch.zeros(128)
+    Pg["generator/filter_%d/fc2/weights" % j] = torch.randn(128, n + 6, generator=g) * 0.1
+    Pg["generator/filter_%d/fc2/biases" % j] = torch.zeros(n + 6)
+  Pg["generator/action_selection/selector_fc1/weights"] = torch.randn(4096, 128, generator=g) * 0.02
+  Pg["generator/action_selection/selector_fc1/biases"] = torch.zeros(128)
+  Pg["generator/action_selection/selector_fc2/weights"] = torch.randn(128, 8, generator=g) * 0.1
+  Pg["generator/action_selection/selector_fc2/biases"] = torch.zeros(8)
+  img = OF.synth_images(sb, 64, 64, stress=False)
+  real = OF.synth_images(sb, 64, 64, seed=9, stress=False) * 4
+  states = torch.zeros(sb, 11)
+  noise = torch.rand(sb, generator=g)
+  dm = lambda: (torch.rand(sb, 4, 4, 256, generator=g) < 0.5).float() * 2
+  alpha = torch.rand(sb, generator=g)
+
+  def iteration():
+    out = OT.generator_step(Pg, Pv, Pc, img, states, noise, dm(), dm(), 0.1, cfg)
+    for _ in range(5):
+      OT.critic_step(Pc, real, out["fake_output"], alpha, cfg)
+
+  iteration()
+  times = []
+  t_end = time.time() + budget_s
+  while len(times) < 5 and (time.time() < t_end or len(times) < 2):
+    t0 = time.time()
+    iteration()
+    times.append(time.time() - t0)
+  med = statistics.median(times)
+  return {"value": sb / med, "unit": "images/s", "cores": cores, "kind": "port",
+          "sample": "1 generator+value step + 5 critic steps on %d of the %d images, median of %d reps; CPU restatement of "
+                    "the reference TF graph (oracle/train_step.py, torch-CPU autograd), not TensorFlow" % (sb, B, len(times))}
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
     run_reference(args)
+  elif args.workload == "train":
+    run_train(args)
   else:
     run_native(args)
 

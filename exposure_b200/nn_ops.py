@@ -65,9 +65,10 @@ def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None,
   if post_mul is not None:
     y2 = torch.empty_like(y) if out2 is None else out2
   mode = 0 if mask_ref is None else 1
-  _cabi.check(_cabi.lib().exp_conv_fwd(x.data_ptr(), Cx, _p(vec), Cv, float(shift), W.data_ptr(), _p(bias),
-                                       _p(mask_ref), _p(post_mul), y.data_ptr(), _p(y2), B, IH, IW, Cout, mode,
-                                       _stream()), "exp_conv_fwd")
+  with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+    _cabi.check(_cabi.lib().exp_conv_fwd(x.data_ptr(), Cx, _p(vec), Cv, float(shift), W.data_ptr(), _p(bias),
+                                         _p(mask_ref), _p(post_mul), y.data_ptr(), _p(y2), B, IH, IW, Cout, mode,
+                                         _stream()), "exp_conv_fwd")
   _n()
   return y if post_mul is None else (y, y2)
 
@@ -79,8 +80,9 @@ def conv_dgrad(dy, W, in_shape, a_in=None, out=None):
   Cout = W.shape[3]
   assert W.shape[2] == Cin and tuple(dy.shape) == (B, IH // 2, IW // 2, Cout)
   dx = torch.empty(B, IH, IW, Cin, device=dy.device, dtype=torch.float32) if out is None else out
-  _cabi.check(_cabi.lib().exp_conv_dgrad(dy.data_ptr(), W.data_ptr(), _p(a_in), dx.data_ptr(), B, IH, IW, Cin, Cout,
-                                         _stream()), "exp_conv_dgrad")
+  with _ops._Timed("conv_dgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * Cin):
+    _cabi.check(_cabi.lib().exp_conv_dgrad(dy.data_ptr(), W.data_ptr(), _p(a_in), dx.data_ptr(), B, IH, IW, Cin, Cout,
+                                           _stream()), "exp_conv_dgrad")
   _n()
   return dx
 
@@ -96,8 +98,9 @@ def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False):
   l = _cabi.lib()
   nbytes = l.exp_conv_wgrad_workspace_bytes(B, IH, IW, Cx + Cv, Cout)
   ws = _workspace(x.device, nbytes)
-  _cabi.check(l.exp_conv_wgrad(x.data_ptr(), Cx, _p(vec), Cv, float(shift), dy.data_ptr(), gW.data_ptr(), B, IH, IW,
-                               Cout, int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "exp_conv_wgrad")
+  with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+    _cabi.check(l.exp_conv_wgrad(x.data_ptr(), Cx, _p(vec), Cv, float(shift), dy.data_ptr(), gW.data_ptr(), B, IH, IW,
+                                 Cout, int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "exp_conv_wgrad")
   _n(2)
   return gW
 

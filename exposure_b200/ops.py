@@ -24,7 +24,8 @@ class _Timed:
   def __init__(self, kind, ids, nbytes):
     self.on = event_log is not None
     if self.on:
-      self.name = "%s_%s" % (kind, FILTER_NAMES[ids] if isinstance(ids, int) else "select")
+      self.name = "%s_%s" % (kind, ids if isinstance(ids, str) else
+                             (FILTER_NAMES[ids] if isinstance(ids, int) else "select"))
       self.nbytes = nbytes
       self.e0 = torch.cuda.Event(enable_timing=True)
       self.e1 = torch.cuda.Event(enable_timing=True)

@@ -1,0 +1,126 @@
+"""Replay memory with the image pool resident in HBM.
+
+Semantics of replay_memory.py:8-282 (pool of cfg.replay_memory_size records; generator batches
+pop non-terminated records and drop terminated ones; critic batches read terminated records;
+outputs are re-inserted while step < maximum_trajectory_length, else with probability
+over_length_keep_prob; the pool is topped up with fresh RAW images), but records are SLOTS of two
+device tensors -- images [cap,64,64,3] and states [cap,11] -- and a step costs one index upload
+plus gather/scatter on the device instead of O(pool) Python list slicing, np.stack and an
+H2D + D2H of every image.  The host keeps only what it can know without reading the device:
+`step` and `stopped` evolve deterministically (agent.py:208-222), so the reference's selection
+logic runs on host integers with no synchronisation."""
+import random
+
+import torch
+
+from .util import STATE_STEP_DIM, STATE_STOPPED_DIM
+
+
+class SyntheticProvider:
+  """Stand-in for FiveKDataProvider / ArtistDataProvider (out of scope): seeded
+  linear-RGB-like 64x64 batches generated on the device (SURVEY 8d statistics)."""
+
+  def __init__(self, device, kind="raw", seed=0, size=64):
+    self.device, self.kind, self.size = device, kind, size
+    self.gen = torch.Generator(device=device).manual_seed(seed)
+
+  def get_next_batch(self, n):
+    s = self.size
+    z = torch.randn(n, s, s, 3, device=self.device, generator=self.gen)
+    if self.kind == "raw":       # dark linear RAW: median ~0.04
+      return torch.exp(z - 3.2).clamp_(0, 4)
+    return torch.exp(0.7 * z - 1.2).clamp_(0, 1)   # retouched targets: brighter, display range
+
+
+class ReplayMemory:
+
+  def __init__(self, cfg, fake_provider, real_provider, device, seed=0):
+    self.cfg = cfg
+    self.fake_dataset = fake_provider
+    self.real_dataset = real_provider
+    self.device = device
+    self.rng = random.Random(seed)
+    self.target_pool_size = cfg.replay_memory_size
+    cap = cfg.replay_memory_size + 2 * cfg.batch_size
+    s = cfg.source_img_size
+    self.images = torch.zeros(cap, s, s, 3, device=device)
+    self.states = torch.zeros(cap, cfg.num_state_dim, device=device)
+    self.free = list(range(cap))
+    self.image_pool = []                 # slot ids, in the reference's list order
+    self.step = [0] * cap                # host mirror of states[:, STATE_STEP_DIM]
+    self.stopped = [False] * cap         # host mirror of states[:, STATE_STOPPED_DIM]
+    self.fill_pool()
+
+  def _idx(self, slots):
+    return torch.tensor(slots, dtype=torch.long).to(self.device, non_blocking=True)
+
+  def _release(self, slots):
+    self.free.extend(slots)
+
+  def fill_pool(self):                   # replay_memory.py:64-75
+    while len(self.image_pool) < self.target_pool_size:
+      batch = self.fake_dataset.get_next_batch(self.cfg.batch_size)
+      slots = [self.free.pop() for _ in range(batch.shape[0])]
+      idx = self._idx(slots)
+      self.images.index_copy_(0, idx, batch)
+      self.states.index_fill_(0, idx, 0.0)
+      for sl in slots:
+        self.step[sl], self.stopped[sl] = 0, False
+      self.image_pool.extend(slots)
+    self._release(self.image_pool[self.target_pool_size:])
+    self.image_pool = self.image_pool[:self.target_pool_size]
+
+  def get_next_fake_batch(self, batch_size):     # replay_memory.py:230-246
+    self.rng.shuffle(self.image_pool)
+    batch = []
+    while len(batch) < batch_size:
+      if not self.image_pool:
+        self.fill_pool()
+      slot = self.image_pool.pop(0)
+      if not self.stopped[slot]:
+        batch.append(slot)
+      else:
+        self._release([slot])            # finished images are dropped here
+    idx = self._idx(batch)
+    return self.images.index_select(0, idx), self.states.index_select(0, idx), batch
+
+  def replace_memory(self, new_images, new_states, old_slots):    # replay_memory.py:187-196
+    """new_images / new_states: device outputs of the generator step for the records `old_slots`."""
+    self.rng.shuffle(self.image_pool)
+    keep_rows, keep_slots = [], []
+    for row, slot in enumerate(old_slots):
+      step = self.step[slot] + 1
+      stopped = abs(step - self.cfg.test_steps) < 1e-4          # agent.py:210-218
+      if step < self.cfg.maximum_trajectory_length or self.rng.random() < self.cfg.over_length_keep_prob:
+        self.step[slot], self.stopped[slot] = step, stopped
+        keep_rows.append(row)
+        keep_slots.append(slot)
+      else:
+        self._release([slot])
+    if keep_slots:
+      rows, idx = self._idx(keep_rows), self._idx(keep_slots)
+      self.images.index_copy_(0, idx, new_images.index_select(0, rows))
+      self.states.index_copy_(0, idx, new_states.index_select(0, rows))
+      self.image_pool.extend(keep_slots)
+    self.fill_pool()
+    self.rng.shuffle(self.image_pool)
+
+  def replay_fake_batch(self, batch_size):       # replay_memory.py:249-273
+    self.fill_pool()
+    self.rng.shuffle(self.image_pool)
+    batch = []
+    counter = 0
+    while len(batch) < batch_size:
+      counter += 1
+      assert counter <= batch_size * 10, "No terminated states discovered"
+      for slot in self.image_pool:
+        if self.stopped[slot]:
+          batch.append(slot)
+          if len(batch) >= batch_size:
+            break
+    idx = self._idx(batch)
+    return self.images.index_select(0, idx), self.states.index_select(0, idx)
+
+  def debug(self):                               # replay_memory.py:275-282
+    tot = sum(self.step[s] for s in self.image_pool)
+    return len(self.image_pool), 1.0 * tot / max(1, len(self.image_pool))

@@ -122,6 +122,37 @@ class Trainer:
       self._adam(self.cri, "c", lr_c, self.counter_c)
     return dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit)
 
+  # ---- GAN.train's inner loop (net.py:307-370): 1 generator+value step, cfg.citers critic steps
+  def attach_memory(self, memory, generator=None):
+    self.memory = memory
+    self.rng = generator
+
+  def train_iteration(self, it, giters=None, citers=None, lr_g=None):
+    """One iteration of net.py:307-370 on the attached replay memory.  Returns device scalars
+    (no host synchronisation inside)."""
+    cfg = self.cfg
+    B = cfg.batch_size
+    progress = float(it) / cfg.max_iter_step
+    if citers is None:
+      citers = 100 if (it < cfg.critic_initialization or it % 500 == 0) else cfg.citers     # net.py:312-316
+    if giters is None:
+      giters = 100 if it == 0 else cfg.giters                                               # net.py:318-322
+    lr_g = (0.0 if it == 0 else cfg.lr_g(it)) if lr_g is None else lr_g                      # net.py:327-328
+    out = None
+    for _ in range(giters):
+      img, states, slots = self.memory.get_next_fake_batch(B)
+      noise, drop_f, drop_s, _ = self.draw(B, self.rng)
+      out = self.generator_step(img, states, noise, drop_f, drop_s, progress, lr_g)
+      self.memory.replace_memory(out["fake_output"], out["new_states"], slots)              # net.py:340-342
+    cout = None
+    for _ in range(citers):
+      fake, _ = self.memory.replay_fake_batch(B)                                            # replay_memory.py:159-173
+      real = self.memory.real_dataset.get_next_batch(B)
+      alpha = torch.rand(B, device=self.device, generator=self.rng)
+      cout = self.critic_step(real, fake, alpha, cfg.lr_c(it))
+    return dict(g_loss=out["g_loss"], v_loss=out["v_loss"], emd=cout["emd"] if cout else None,
+                critic_gradient_norm=cout["critic_gradient_norm"] if cout else None)
+
   # ---- random draws the reference makes per step (explicit so tests can inject them) -------
   def draw(self, B, generator=None):
     dev = self.device

@@ -31,6 +31,7 @@ SIGNATURES = {
     "exp_filter_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "exp_filter_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
                                 _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_int, _c_void_p]),
+    "exp_set_gemm_backend": (_c_int, [_c_int]),
     "exp_conv_fwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, ctypes.c_float, _c_void_p, _c_void_p, _c_void_p,
                               _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "exp_conv_dgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,

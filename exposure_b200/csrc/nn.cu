@@ -10,8 +10,15 @@
 // Layouts follow the reference checkpoint: activations NHWC, conv weights HWIO
 // [4,4,Cin,Cout], FC weights [in,out], flatten order (h*4+w)*256+c.
 #include "gemm_engine.cuh"
+#include "nn_tc.h"
 
 namespace expo {
+
+static int g_gemm_backend = kBackendAuto;
+int gemm_backend() { return g_gemm_backend; }
+// AUTO currently resolves to the CUDA-core engine; the tcgen05 engine is opt-in until every
+// primitive has a validated tensor-core instantiation.
+bool use_tcgen05() { return g_gemm_backend == kBackendTcgen05; }
 
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
@@ -316,6 +323,13 @@ int exp_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, 
   p.chunks = (p.Cin + kBK - 1) / kBK; p.mode = mode; p.shift = shift;
   p.lgOW = host_ilog2(p.OW); p.lgOHW = host_ilog2(p.OH * p.OW);
   const int M = B * p.OH * p.OW;
+  if (use_tcgen05() && tc_conv_fwd_supported(Cout)) {
+    const cudaError_t e = tc_conv_fwd(x, Cx, vec, Cv, shift, W, bias, mask_ref, post_mul, y, y2, B, IH, IW, Cout, mode,
+                                      (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_fwd[tcgen05]: %s", cudaGetErrorString(e));
+    EXP_CHECK_LAUNCH("exp_conv_fwd[tcgen05]");
+    return EXP_OK;
+  }
   if (Cout <= 32) launch_gemm<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
   else launch_gemm<ConvFprop, 64, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_conv_fwd");
@@ -372,7 +386,14 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
 
 size_t exp_fc_workspace_bytes(int M, int K, int N) {
   if (M <= 0 || K <= 0 || N <= 0) return 0;
-  return (size_t)fc_splits(M, K, N) * M * N * sizeof(float);
+  const int a = fc_splits(M, K, N), b = tc_fc_splits(M, K, N);
+  return (size_t)(a > b ? a : b) * M * N * sizeof(float);
+}
+
+int exp_set_gemm_backend(int backend) {
+  EXP_CHECK_ARG(backend >= kBackendAuto && backend <= kBackendTcgen05, "backend must be 0 (auto), 1 (cuda cores) or 2 (tcgen05)");
+  g_gemm_backend = backend;
+  return EXP_OK;
 }
 
 int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const float* mask_ref, int ldmask, float* y,
@@ -380,9 +401,21 @@ int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const
   EXP_CHECK_ARG(x && W && y && workspace, "null pointer");
   EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "bad shape");
   EXP_CHECK_ARG(mode >= 0 && mode <= 3 && (mode != 1 || (mask_ref && ldmask >= N)), "bad mode");
-  const int splits = fc_splits(M, K, N);
+  const bool tcg = use_tcgen05() && N >= 16;
+  const int splits = tcg ? tc_fc_splits(M, K, N) : fc_splits(M, K, N);
   const size_t need = (size_t)splits * M * N * sizeof(float);
   if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  if (tcg) {
+    const cudaError_t e = tc_fc_fwd_partials(x, ldx, W, reinterpret_cast<float*>(workspace), M, K, N, splits,
+                                             (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_fc_fwd[tcgen05]: %s", cudaGetErrorString(e));
+    EXP_CHECK_LAUNCH("exp_fc_fwd[tcgen05]");
+    const size_t cnt = (size_t)M * N;
+    splitk_reduce_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float*>(workspace), splits, cnt, N, bias, mask_ref, ldmask, mode, y, ldy, 0);
+    EXP_CHECK_LAUNCH("exp_fc_fwd[reduce]");
+    return EXP_OK;
+  }
   FcFwd p{};
   p.x = x; p.W = W; p.part = reinterpret_cast<float*>(workspace); p.M = M; p.K = K; p.N = N; p.ldx = ldx;
   int kps = (K + splits - 1) / splits;

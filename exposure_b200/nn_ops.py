@@ -290,3 +290,11 @@ def adam(params, grads, m, v, hyper, beta1, beta2, eps=1e-8, grad_scale=1.0):
                                    float(beta1), float(beta2), float(eps), float(grad_scale), params.numel(), _stream()),
               "exp_adam")
   _n()
+
+
+BACKEND_AUTO, BACKEND_CUDA_CORES, BACKEND_TCGEN05 = 0, 1, 2
+
+
+def set_gemm_backend(backend):
+  """Process-wide GEMM backend of the conv / FC primitives (exp_set_gemm_backend)."""
+  _cabi.check(_cabi.lib().exp_set_gemm_backend(int(backend)), "exp_set_gemm_backend")

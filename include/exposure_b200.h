@@ -121,6 +121,11 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams,
  * of the stored output (1, 0.2, or 0.6 at exactly 0).
  * ==================================================================================== */
 
+/* GEMM backend of the conv / FC primitives: 0 = auto, 1 = exact-fp32 CUDA-core engine,
+ * 2 = tcgen05 tensor cores (kind::tf32 with 3xTF32 split accumulation, accumulators in TMEM)
+ * for the primitives that have a tensor-core instantiation.  Process-wide. */
+int exp_set_gemm_backend(int backend);
+
 /* y[B,IH/2,IW/2,Cout] = epi( conv4x4s2( concat(x[B,IH,IW,Cx], tile(vec[B,Cv])) - shift ) )
  *   `vec` (nullable when Cv == 0) is a per-image vector broadcast over the pixels: the
  *   states of util.enrich_image_input (util.py:31-36) and the 3 global statistics of

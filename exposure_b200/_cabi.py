@@ -80,6 +80,9 @@ def lib():
       fn.restype = res
       fn.argtypes = args
     _lib = l
+    be = os.environ.get("EXPOSURE_GEMM_BACKEND")      # 0 auto, 1 CUDA cores, 2 tcgen05
+    if be:
+      check(l.exp_set_gemm_backend(int(be)), "exp_set_gemm_backend")
   return _lib
 
 

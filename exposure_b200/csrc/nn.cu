@@ -346,6 +346,12 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
   p.OW = IW / 2; p.Cout = Cout; p.chunks = Cout / kBK;
   p.lgW2 = host_ilog2(IW / 2); p.lgHW2 = host_ilog2((IH / 2) * (IW / 2));
   const int M = B * (IH / 2) * (IW / 2);
+  if (use_tcgen05() && tc_conv_dgrad_supported(Cout) && aligned16(dy) && aligned16(W)) {
+    const cudaError_t e = tc_conv_dgrad(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[tcgen05]: %s", cudaGetErrorString(e));
+    EXP_CHECK_LAUNCH("exp_conv_dgrad[tcgen05]");
+    return EXP_OK;
+  }
   if (Cin <= 32) launch_gemm<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
   else launch_gemm<ConvDgrad, 64, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_conv_dgrad");
@@ -354,7 +360,8 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
 
 size_t exp_conv_wgrad_workspace_bytes(int B, int IH, int IW, int Cin, int Cout) {
   if (B <= 0 || IH < 2 || IW < 2 || Cin <= 0 || Cout <= 0) return 0;
-  return (size_t)wgrad_splits(B, IH / 2, IW / 2, Cin, Cout) * 16 * Cin * Cout * sizeof(float);
+  const int a = wgrad_splits(B, IH / 2, IW / 2, Cin, Cout), b = tc_wgrad_splits(B, IH / 2, IW / 2, Cin, Cout);
+  return (size_t)(a > b ? a : b) * 16 * Cin * Cout * sizeof(float);
 }
 
 int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift, const float* dy, float* gW, int B,
@@ -363,9 +370,21 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
   EXP_CHECK_ARG(B > 0 && is_pow2(IH) && is_pow2(IW) && IH >= 2 && IW >= 2, "IH/IW must be powers of two >= 2");
   EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cout > 0, "bad channel counts");
   const int Cin = Cx + Cv, OH = IH / 2, OW = IW / 2;
-  const int splits = wgrad_splits(B, OH, OW, Cin, Cout);
+  const bool tcg = use_tcgen05();
+  const int splits = tcg ? tc_wgrad_splits(B, OH, OW, Cin, Cout) : wgrad_splits(B, OH, OW, Cin, Cout);
   const size_t need = (size_t)splits * 16 * Cin * Cout * sizeof(float);
   if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  if (tcg) {
+    const cudaError_t e = tc_conv_wgrad_partials(x, Cx, vec, Cv, shift, dy, reinterpret_cast<float*>(workspace), B, IH, IW,
+                                                 Cout, splits, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_wgrad[tcgen05]: %s", cudaGetErrorString(e));
+    EXP_CHECK_LAUNCH("exp_conv_wgrad[tcgen05]");
+    const size_t cnt = (size_t)16 * Cin * Cout;
+    splitk_reduce_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float*>(workspace), splits, cnt, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
+    EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
+    return EXP_OK;
+  }
   ConvWgrad p{};
   p.x = x; p.vec = vec; p.dy = dy; p.part = reinterpret_cast<float*>(workspace);
   p.B = B; p.IH = IH; p.IW = IW; p.Cx = Cx; p.Cv = Cv; p.Cin = Cin; p.Cout = Cout; p.OH = OH; p.OW = OW;
@@ -439,6 +458,13 @@ int exp_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act,
   FcDgrad p{};
   p.dy = dy; p.W = W; p.mul_act = mul_act; p.mul_plain = mul_plain; p.dx = dx; p.M = M; p.K = K; p.N = N;
   p.ldy = ldy; p.lddx = lddx; p.ldmul = ldmul; p.accumulate = accumulate;
+  if (use_tcgen05() && K >= 16) {
+    const cudaError_t e = tc_fc_dgrad(dy, ldy, W, mul_act, mul_plain, ldmul, dx, lddx, M, K, N, accumulate,
+                                      (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_fc_dgrad[tcgen05]: %s", cudaGetErrorString(e));
+    EXP_CHECK_LAUNCH("exp_fc_dgrad[tcgen05]");
+    return EXP_OK;
+  }
   launch_gemm<FcDgrad, 64, false, true>(p, M, K, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_dgrad");
   return EXP_OK;
@@ -450,6 +476,12 @@ int exp_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, i
   EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "bad shape");
   FcWgrad p{};
   p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N; p.ldx = ldx; p.ldy = ldy; p.accumulate = accumulate;
+  if (use_tcgen05() && N >= 16) {
+    const cudaError_t e = tc_fc_wgrad(x, ldx, dy, ldy, gW, M, K, N, accumulate, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_fc_wgrad[tcgen05]: %s", cudaGetErrorString(e));
+    EXP_CHECK_LAUNCH("exp_fc_wgrad[tcgen05]");
+    return EXP_OK;
+  }
   if (N <= 32) launch_gemm<FcWgrad, 32, true, false>(p, K, N, 1, (cudaStream_t)stream);
   else launch_gemm<FcWgrad, 64, true, false>(p, K, N, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_wgrad");

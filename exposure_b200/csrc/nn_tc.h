@@ -18,3 +18,16 @@ cudaError_t tc_fc_fwd_partials(const float* x, int ldx, const float* W, float* p
                                cudaStream_t st);
 
 }  // namespace expo
+
+namespace expo {
+bool tc_conv_dgrad_supported(int Cout);
+cudaError_t tc_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH, int IW, int Cin,
+                          int Cout, cudaStream_t st);
+int tc_wgrad_splits(int B, int OH, int OW, int Cin, int Cout);
+cudaError_t tc_conv_wgrad_partials(const float* x, int Cx, const float* vec, int Cv, float shift, const float* dy,
+                                   float* part, int B, int IH, int IW, int Cout, int splits, cudaStream_t st);
+cudaError_t tc_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act, const float* mul_plain, int ldmul,
+                        float* dx, int lddx, int M, int K, int N, int accumulate, cudaStream_t st);
+cudaError_t tc_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, int M, int K, int N, int accumulate,
+                        cudaStream_t st);
+}  // namespace expo

@@ -92,7 +92,9 @@ __device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned cha
 //   float4 load_a4(RowA, KS, int c)        A[m, ki*32 + 4c .. +3]
 //   float4 load_b4(KS, int n, int c)       B[n, ki*32 + 4c .. +3]     (B is N x K, "K-major")
 //   void   store16(int m, int n0, const float (&v)[16])   C[m, n0..n0+15]
-template <class P, int BN>
+// A_ROWFAST: consecutive lanes gather consecutive A rows (operands whose contiguous dimension is
+// M, e.g. wgrad) instead of the 8 chunks of one row.
+template <class P, int BN, bool A_ROWFAST = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const P p_in) {
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
   extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const P p_in) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int idx = tid + kThreads * j;
-    a_row[j] = idx >> 3; a_c[j] = idx & 7;
+    if (A_ROWFAST) { a_row[j] = idx & (kBM - 1); a_c[j] = idx >> 7; }
+    else { a_row[j] = idx >> 3; a_c[j] = idx & 7; }
     ra[j] = p.row_a(m0 + a_row[j]);
   }
   constexpr int NBV = (BN * 8) / kThreads;   // float4 of B per thread per stage
@@ -185,17 +188,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const P p_in) {
   if (warp == 0) tmem_dealloc(tmem_acc, BN);
 }
 
-template <class P, int BN>
+template <class P, int BN, bool A_ROWFAST = false>
 inline cudaError_t launch_tc_gemm(const P& p, int M, int N, int Z, cudaStream_t st) {
   constexpr size_t smem = 2 * (2 * (size_t)kTileABytes + 2 * (size_t)BN * 128) + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<P, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<P, BN, A_ROWFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
-  tc_gemm_kernel<P, BN><<<grid, kThreads, smem, st>>>(p);
+  tc_gemm_kernel<P, BN, A_ROWFAST><<<grid, kThreads, smem, st>>>(p);
   return cudaSuccess;
 }
 

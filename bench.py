@@ -46,6 +46,7 @@ def parse_args():
   ap.add_argument("--size", type=int, default=512)
   ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 tma (exposure_b200.h)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-graphs", action="store_true", help="train workload: launch kernels eagerly instead of CUDA graphs")
   return ap.parse_args()
 
 
@@ -408,6 +409,8 @@ def run_train(args):
   # bootstrap like iteration 0 of net.py:318-328 (generator steps with lr 0 until terminated
   # records exist), shortened: 2 * test_steps generator steps are enough to terminate records
   t.train_iteration(0, giters=2 * cfg.test_steps + 2, citers=1)
+  if not args.no_graphs:
+    t.enable_graphs(B)                              # each step = one CUDA-graph replay
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
@@ -431,6 +434,28 @@ def run_train(args):
   elapsed_ms = e0.elapsed_time(e1)
   launches = ops.launch_count - l0
   log, ops.event_log = ops.event_log, None
+  graphs = getattr(t, "_ggraph", None) is not None
+  roof_note = "per-kernel CUDA events recorded inside the timed region"
+  if graphs:
+    # kernels replayed from a CUDA graph are not launched through Python: count them from the
+    # capture, and time the kernel families in a short eager (non-graph) pass right after
+    launches = args.steps * (t.graph_launches["generator"] + 5 * t.graph_launches["critic"])
+    saved = (t._ggraph, t._cgraph)
+    t._ggraph = t._cgraph = None
+    ops.event_log = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    n_probe = 3
+    for _ in range(n_probe):
+      t.train_iteration(it, giters=1, citers=5)
+      it += 1
+    ev1.record()
+    torch.cuda.synchronize()
+    log, ops.event_log = ops.event_log, None
+    t._ggraph, t._cgraph = saved
+    probe_ms = ev0.elapsed_time(ev1)
+    roof_note = ("timed region replays CUDA graphs; kernel families timed with CUDA events in %d eager iterations "
+                 "right after it (%.2f ms/iteration eager)" % (n_probe, probe_ms / n_probe))
   tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
   if world > 1:
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -449,11 +474,17 @@ def run_train(args):
     peak_tf = float(json.load(open(pk)).get("bf16_tflops_sustained", peak_tf))
   tot_ms = sum(d["ms"] for d in per.values()) or 1.0
   tot_fl = sum(d["flops"] for d in per.values())
-  roofline = {"bound": "tensor", "kernel": "gemm_kernel family (conv fprop/dgrad/wgrad; exact-fp32 CUDA-core path, "
-                                            "tcgen05 not yet used -- DESIGN.md section 7)",
+  backend = os.environ.get("EXPOSURE_GEMM_BACKEND", "0")
+  kname = ("tc_gemm_kernel family (conv fprop/dgrad/wgrad on tcgen05, kind::tf32 x3 split, TMEM accumulators)"
+           if backend == "2" else
+           "gemm_kernel family (conv fprop/dgrad/wgrad; exact-fp32 CUDA-core engine)")
+  n_timed_iters = 3 if graphs else args.steps
+  roofline = {"bound": "tensor", "kernel": kname, "gemm_backend": {"0": "auto", "1": "cuda-cores", "2": "tcgen05"}.get(backend, backend),
               "achieved": tot_fl / tot_ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": tot_fl / tot_ms / 1e9 / peak_tf,
-              "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16)",
-              "share_of_step": tot_ms / elapsed_ms, "kernels": kernels}
+              "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16; the fp32-accurate "
+                                              "3xTF32 path can reach at most 1/6 of it)",
+              "share_of_step": (tot_ms / n_timed_iters) / (elapsed_ms / args.steps), "note": roof_note,
+              "kernels": kernels}
 
   # end-to-end leg: fresh RAW and real batches come from pinned host memory every step, the
   # filtered batch and the losses go back to the host (what net.py:330-342 does per sess.run)

@@ -50,10 +50,10 @@ SIGNATURES = {
     "exp_stats_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "exp_stats_jvp": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "exp_policy_head_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float,
-                                     _c_float, _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                     _c_float, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                      _c_void_p, _c_void_p, _c_void_p]),
     "exp_policy_head_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_float, _c_float,
-                                     _c_float, _c_void_p, _c_void_p]),
+                                     _c_void_p, _c_void_p, _c_void_p]),
     "exp_overexposure_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "exp_overexposure_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "exp_rl_losses": (_c_int, [_c_void_p] * 7 + [_c_int, _c_int, _c_float, _c_float, _c_float, _c_float, _c_int, _c_int,

@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256) stats_jvp_kernel(const float* __restrict_
 // ---- action selection head (one thread per image) ---------------------------------------
 struct HeadCfg {
   int n_filters, n_states, is_train, test_steps;
-  float exploration, exploration_penalty, filter_usage_penalty, progress;
+  float exploration, exploration_penalty, filter_usage_penalty;
+  const float* progress;   // device scalar (a captured CUDA graph can be replayed with a new value)
 };
 constexpr int kMaxFilters = 16;
 
@@ -186,7 +187,7 @@ __global__ void policy_head_fwd_kernel(const float* __restrict__ logits, const f
     usage_pen += st[3 + k] * oh;                                    // agent.py:230-233
     ns[3 + k] = fmaxf(st[3 + k], oh);
   }
-  const float ent_pen = (1.0f - c.progress) * c.exploration_penalty * (-ent + logf((float)c.n_filters));
+  const float ent_pen = (1.0f - __ldg(c.progress)) * c.exploration_penalty * (-ent + logf((float)c.n_filters));
   penalty_head[b] = ent_pen + usage_pen * c.filter_usage_penalty;   // agent.py:246-252 (early stop term == 0)
 }
 
@@ -200,7 +201,7 @@ __global__ void policy_head_bwd_kernel(const float* __restrict__ logits, const i
   head_pdf(logits + (size_t)b * c.n_filters, c, sm, pdf, &Z);
   const int id = ids[b];
   const float gs = g_surrogate[b];
-  const float ge = g_penalty[b] * (1.0f - c.progress) * c.exploration_penalty;   // d pen / d(-entropy)
+  const float ge = g_penalty[b] * (1.0f - __ldg(c.progress)) * c.exploration_penalty;   // d pen / d(-entropy)
   float gp[kMaxFilters];
   float dot_pq = 0.f;
   for (int k = 0; k < c.n_filters; ++k) {
@@ -348,9 +349,10 @@ int exp_stats_jvp(const float* img, const float* stats, const float* u, float* d
 
 int exp_policy_head_fwd(const float* logits, const float* noise, const float* states, int B, int n_filters, int n_states,
                         int is_train, int test_steps, float exploration, float exploration_penalty,
-                        float filter_usage_penalty, float progress, float* pdf, int* ids, float* surrogate,
+                        float filter_usage_penalty, const float* progress, float* pdf, int* ids, float* surrogate,
                         float* entropy, float* penalty_head, float* new_states, void* stream) {
-  EXP_CHECK_ARG(logits && noise && states && pdf && ids && surrogate && entropy && penalty_head && new_states, "null pointer");
+  EXP_CHECK_ARG(logits && noise && states && progress && pdf && ids && surrogate && entropy && penalty_head && new_states,
+                "null pointer");
   EXP_CHECK_ARG(B > 0 && n_filters > 0 && n_filters <= kMaxFilters && n_states == 3 + n_filters, "bad sizes");
   HeadCfg c{n_filters, n_states, is_train, test_steps, exploration, exploration_penalty, filter_usage_penalty, progress};
   policy_head_fwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(logits, noise, states, c, B, pdf, ids, surrogate,
@@ -359,9 +361,9 @@ int exp_policy_head_fwd(const float* logits, const float* noise, const float* st
   return EXP_OK;
 }
 int exp_policy_head_bwd(const float* logits, const int* ids, const float* g_surrogate, const float* g_penalty, int B,
-                        int n_filters, float exploration, float exploration_penalty, float progress, float* g_logits,
+                        int n_filters, float exploration, float exploration_penalty, const float* progress, float* g_logits,
                         void* stream) {
-  EXP_CHECK_ARG(logits && ids && g_surrogate && g_penalty && g_logits, "null pointer");
+  EXP_CHECK_ARG(logits && ids && g_surrogate && g_penalty && progress && g_logits, "null pointer");
   EXP_CHECK_ARG(B > 0 && n_filters > 0 && n_filters <= kMaxFilters, "bad sizes");
   HeadCfg c{n_filters, 3 + n_filters, 1, 0, exploration, exploration_penalty, 0.f, progress};
   policy_head_bwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(logits, ids, g_surrogate, g_penalty, c, B, g_logits);

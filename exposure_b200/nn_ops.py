@@ -198,8 +198,16 @@ def stats_jvp(img, stats, u):
   return d
 
 
+def _progress_dev(progress, dev):
+  """progress may be a python float (uploaded) or a device scalar tensor (graph-friendly)."""
+  if torch.is_tensor(progress):
+    return progress
+  return torch.full((1,), float(progress), device=dev)
+
+
 def policy_head_fwd(logits, noise, states, is_train, progress, cfg):
   _chk(logits, "logits", 2); _chk(noise, "noise"); _chk(states, "states", 2)
+  progress = _progress_dev(progress, logits.device)
   B, n = logits.shape
   dev = logits.device
   pdf = torch.empty(B, n, device=dev)
@@ -208,7 +216,7 @@ def policy_head_fwd(logits, noise, states, is_train, progress, cfg):
   ns = torch.empty_like(states)
   _cabi.check(_cabi.lib().exp_policy_head_fwd(
       logits.data_ptr(), noise.data_ptr(), states.data_ptr(), B, n, states.shape[1], int(is_train), int(cfg.test_steps),
-      float(cfg.exploration), float(cfg.exploration_penalty), float(cfg.filter_usage_penalty), float(progress),
+      float(cfg.exploration), float(cfg.exploration_penalty), float(cfg.filter_usage_penalty), progress.data_ptr(),
       pdf.data_ptr(), ids.data_ptr(), sur.data_ptr(), ent.data_ptr(), pen.data_ptr(), ns.data_ptr(), _stream()),
       "exp_policy_head_fwd")
   _n()
@@ -218,9 +226,10 @@ def policy_head_fwd(logits, noise, states, is_train, progress, cfg):
 def policy_head_bwd(logits, ids, g_surrogate, g_penalty, progress, cfg):
   B, n = logits.shape
   g = torch.empty_like(logits)
+  progress = _progress_dev(progress, logits.device)
   _cabi.check(_cabi.lib().exp_policy_head_bwd(logits.data_ptr(), ids.data_ptr(), g_surrogate.data_ptr(),
                                               g_penalty.data_ptr(), B, n, float(cfg.exploration),
-                                              float(cfg.exploration_penalty), float(progress), g.data_ptr(), _stream()),
+                                              float(cfg.exploration_penalty), progress.data_ptr(), g.data_ptr(), _stream()),
               "exp_policy_head_bwd")
   _n()
   return g

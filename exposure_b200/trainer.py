@@ -58,13 +58,57 @@ class Trainer:
     self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
   # ---- optimizer --------------------------------------------------------------------------
-  def _adam(self, store, key, lr, t):
+  def _set_lr(self, key, lr, t):
+    """lr_t of tf.train.AdamOptimizer into the device scalar the fused Adam reads (so that a
+    captured graph can be replayed with a new learning rate / step count)."""
     b1, b2 = self.cfg.adam_beta1, self.cfg.adam_beta2
-    lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
-    self._hyper[key].fill_(lr_t)
+    self._hyper[key].fill_(lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
+
+  def _adam(self, store, key):
+    b1, b2 = self.cfg.adam_beta1, self.cfg.adam_beta2
     if self.world > 1:
       dist.all_reduce(store.grad)                                # ONE all-reduce per optimizer step
     K.adam(store.flat, store.grad, store.m, store.v, self._hyper[key], b1, b2, 1e-8, 1.0 / self.world)
+
+  # ---- CUDA graphs: each step is a fixed launch sequence, captured once and replayed ---------
+  def enable_graphs(self, B=None):
+    """Capture the generator+value step and the critic step (forward, backward, all-reduce,
+    Adam) into two CUDA graphs over static input buffers.  Per-step scalars (progress, lr_t)
+    live in device memory, random draws are made outside and copied in."""
+    B = B or self.cfg.batch_size
+    dev = self.device
+    z = lambda *s: torch.zeros(*s, device=dev)
+    self._gi = dict(img=z(B, 64, 64, 3), states=z(B, self.cfg.num_state_dim), noise=z(B), drop_f=z(B, 4, 4, 256),
+                    drop_s=z(B, 4, 4, 256), progress=z(1))
+    self._ci = dict(real=z(B, 64, 64, 3), fake=z(B, 64, 64, 3), alpha=z(B))
+    snap = [t.clone() for s in (self.gen, self.val, self.cri) for t in (s.flat, s.m, s.v)]
+    for k in "gvc":
+      self._hyper[k].zero_()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                                  # warm-up (allocations, lazy attributes)
+      for _ in range(2):
+        self._generator_impl(self._gi["img"], self._gi["states"], self._gi["noise"], self._gi["drop_f"],
+                             self._gi["drop_s"], self._gi["progress"], 1, True)
+        self._critic_impl(self._ci["real"], self._ci["fake"], self._ci["alpha"], True)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    from . import ops as _ops
+    l0 = _ops.launch_count
+    self._ggraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self._ggraph):
+      self._gout = self._generator_impl(self._gi["img"], self._gi["states"], self._gi["noise"], self._gi["drop_f"],
+                                        self._gi["drop_s"], self._gi["progress"], 1, True)
+    l1 = _ops.launch_count
+    self._cgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self._cgraph):
+      self._cout = self._critic_impl(self._ci["real"], self._ci["fake"], self._ci["alpha"], True)
+    self.graph_launches = {"generator": l1 - l0, "critic": _ops.launch_count - l1}   # own kernels per replay
+    it = iter(snap)
+    for s in (self.gen, self.val, self.cri):
+      for t in (s.flat, s.m, s.v):
+        t.copy_(next(it))
+    self._graph_B = B
 
   # ---- generator + value step (net.py:56-163, 222-239, 330) ---------------------------------
   def generator_forward(self, fake_input, states, noise, drop_f, drop_s, progress, is_train=1):
@@ -72,7 +116,25 @@ class Trainer:
     return c
 
   def generator_step(self, fake_input, states, noise, drop_f, drop_s, progress, lr_g, is_train=1, apply=True):
-    """Returns dict(fake_output, new_states, g_loss, v_loss, ...) (device tensors, no sync)."""
+    """Returns dict(fake_output, new_states, g_loss, v_loss, ...) (device tensors, no sync).
+    With enable_graphs() the returned tensors are the graph's static outputs: consume them
+    before the next call."""
+    if apply:
+      self.counter_g += 1
+      self.counter_v += 1
+      self._set_lr("g", lr_g, self.counter_g)
+      self._set_lr("v", self.cfg.value_lr_mul * lr_g, self.counter_v)
+    graph = getattr(self, "_ggraph", None)
+    if graph is not None and apply and is_train == 1 and fake_input.shape[0] == self._graph_B:
+      gi = self._gi
+      gi["img"].copy_(fake_input); gi["states"].copy_(states); gi["noise"].copy_(noise)
+      gi["drop_f"].copy_(drop_f); gi["drop_s"].copy_(drop_s); gi["progress"].fill_(float(progress))
+      graph.replay()
+      return self._gout
+    prog = torch.full((1,), float(progress), device=self.device)
+    return self._generator_impl(fake_input, states, noise, drop_f, drop_s, prog, is_train, apply)
+
+  def _generator_impl(self, fake_input, states, noise, drop_f, drop_s, progress, is_train, apply):
     c = self.policy.forward(fake_input, states, noise, drop_f, drop_s, is_train, progress, self.cfg)
     cc_out = self.critic.forward(c.out)                          # fake_logit            net.py:70-71
     cc_in = self.critic.forward(fake_input)                      # fake_input_logit (stop_gradient) net.py:72-73
@@ -89,16 +151,26 @@ class Trainer:
     g_img = g_img + self.value.image_grad(v_new)
     self.policy.backward(c, g_img, seeds[4], seeds[3])
     if apply:
-      self.counter_g += 1
-      self.counter_v += 1
-      self._adam(self.gen, "g", lr_g, self.counter_g)
-      self._adam(self.val, "v", self.cfg.value_lr_mul * lr_g, self.counter_v)
+      self._adam(self.gen, "g")
+      self._adam(self.val, "v")
     return dict(fake_output=c.out, new_states=c.new_states, g_loss=losses[0], v_loss=losses[1], ctx=c,
                 fake_logit=cc_out.logit, old_value=v_old.logit, new_value=v_new.logit, seeds=seeds)
 
   # ---- critic step (net.py:68-71, 151, 174-194, 245-251, 362) -------------------------------
   def critic_step(self, real, fake, alpha, lr_c, apply=True):
     """real, fake [B,64,64,3]; alpha [B] ~ U[0,1).  c_loss = mean(D(fake) - D(real)) + GP."""
+    if apply:
+      self.counter_c += 1
+      self._set_lr("c", lr_c, self.counter_c)
+    graph = getattr(self, "_cgraph", None)
+    if graph is not None and apply and real.shape[0] == self._graph_B:
+      ci = self._ci
+      ci["real"].copy_(real); ci["fake"].copy_(fake); ci["alpha"].copy_(alpha)
+      graph.replay()
+      return self._cout
+    return self._critic_impl(real, fake, alpha, apply)
+
+  def _critic_impl(self, real, fake, alpha, apply):
     B = real.shape[0]
     lam = float(self.cfg.gradient_penalty_lambda)
     xhat = K.interpolate(real, fake, alpha)
@@ -118,8 +190,7 @@ class Trainer:
     emd = logit[:B].mean() - logit[B:2 * B].mean()               # net.py:164  emd = -c_loss (before GP)
     gp = lam * (torch.clamp(norm - 1.0, min=0.0) ** 2).mean()
     if apply:
-      self.counter_c += 1
-      self._adam(self.cri, "c", lr_c, self.counter_c)
+      self._adam(self.cri, "c")
     return dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit)
 
   # ---- GAN.train's inner loop (net.py:307-370): 1 generator+value step, cfg.citers critic steps

@@ -188,15 +188,16 @@ int exp_stats_jvp(const float* img, const float* stats, const float* u, float* d
 /* Action-selection head, agent.py:100-122 + 208-252 + pdf_sample_layer.py:5-10:
  * logits[B,n] (selector_fc2 output), noise[B] (= z[:,0]), states[B,3+n] ->
  * pdf[B,n], ids[B] (int32; -1 reproduces the u==0 quirk of pdf_sample), surrogate[B],
- * entropy[B], penalty_head[B] (entropy + filter-usage penalties), new_states[B,3+n]. */
+ * entropy[B], penalty_head[B] (entropy + filter-usage penalties), new_states[B,3+n].
+ * `progress` (replay_memory.py:33 placeholder, iter / max_iter_step) is a DEVICE scalar. */
 int exp_policy_head_fwd(const float* logits, const float* noise, const float* states, int B,
                         int n_filters, int n_states, int is_train, int test_steps, float exploration,
-                        float exploration_penalty, float filter_usage_penalty, float progress,
+                        float exploration_penalty, float filter_usage_penalty, const float* progress,
                         float* pdf, int* ids, float* surrogate, float* entropy, float* penalty_head,
                         float* new_states, void* stream);
 int exp_policy_head_bwd(const float* logits, const int* ids, const float* g_surrogate,
                         const float* g_penalty, int B, int n_filters, float exploration,
-                        float exploration_penalty, float progress, float* g_logits, void* stream);
+                        float exploration_penalty, const float* progress, float* g_logits, void* stream);
 
 /* pen[b] = mean(max(img-1,0)^2) (agent.py:247) and its backward
  * g_out = (g_in ? g_in : 0) + g_pen[b] * 2 max(img-1,0) / (H*W*3). */

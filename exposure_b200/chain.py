@@ -3,10 +3,13 @@
 The chain x_0 -> f_{id_0} -> x_1 -> ... -> x_N is a benchmark construct built from the
 reference's per-filter maths (filters.py process()); in the reference one step applies one
 selected filter (agent.py:113-125) and an episode is cfg.test_steps such steps.  Each step is
-ONE fused CUDA kernel forward and ONE backward (exposure_b200/csrc/filters.cu); activations
-x_0..x_{N-1} stay resident in HBM for the backward (12 B/pixel/step), outputs are recomputed.
+ONE fused CUDA kernel forward and ONE backward (exposure_b200/csrc/filters*.cu): the
+filter_param_regressor runs in the kernel prologue (EXP_OPT_LOGITS) and its chain rule in the
+backward's finishing CTA, so a chain step is exactly 2N launches.  Activations x_0..x_{N-1} stay
+resident in HBM for the backward (12 B/pixel/step); outputs are recomputed, never re-read.
 
-Explicit schedule, no autograd: forward() then backward()."""
+Explicit schedule, no autograd: forward() then backward(); capture() records both into one CUDA
+graph over the chain's static buffers."""
 import torch
 
 from . import ops
@@ -14,43 +17,56 @@ from . import ops
 
 class FilterChain:
 
-  def __init__(self, ids, variant=ops.VARIANT_AUTO):
+  def __init__(self, ids, variant=ops.VARIANT_AUTO, fused_regressor=True):
     """ids: list of N entries, each an int filter id (uniform over the batch) or a CUDA int32
     tensor [B] of per-image ids."""
     self.ids = list(ids)
     self.variant = variant
+    self.fused = fused_regressor
     self._acts = None
     self._params = None
     self._logits = None
     self._gbuf = None
+    self._glog = None
+    self._graph = None
 
-  def _alloc(self, x):
+  def _alloc(self, shape, device):
     n = len(self.ids)
-    if self._acts is None or self._acts[0].shape != x.shape or self._acts[0].device != x.device:
-      self._acts = [torch.empty_like(x) for _ in range(n + 1)]
-      self._gbuf = [torch.empty_like(x) for _ in range(2)]
+    if self._acts is None or tuple(self._acts[0].shape) != tuple(shape) or self._acts[0].device != device:
+      mk = lambda: torch.empty(shape, device=device, dtype=torch.float32)
+      self._acts = [mk() for _ in range(n + 1)]
+      self._gbuf = [mk() for _ in range(2)]
+      self._glog = [torch.zeros(shape[0], ops.PSTRIDE, device=device) for _ in range(n)]
+      self._graph = None
+
+  def input_buffer(self, shape, device):
+    self._alloc(shape, device)
+    return self._acts[0]
+
+  def _nparams(self, k):
+    fid = self.ids[k]
+    return ops.NUM_PARAMS[fid] if isinstance(fid, int) else ops.PSTRIDE
 
   def forward(self, x, logits_list):
     """x: [B,H,W,3]; logits_list[k]: [B, >= n_k] raw regressor inputs.  Returns x_N."""
     assert len(logits_list) == len(self.ids)
-    self._alloc(x)
-    self._acts[0].copy_(x) if self._acts[0].data_ptr() != x.data_ptr() else None
+    self._alloc(x.shape, x.device)
+    if self._acts[0].data_ptr() != x.data_ptr():
+      self._acts[0].copy_(x)
     self._logits = [l.contiguous() for l in logits_list]
     self._params = []
     for k, fid in enumerate(self.ids):
-      p = ops.filter_regress_fwd(self._logits[k], fid)
+      if self.fused:
+        p = self._logits[k]
+      else:
+        p = ops.filter_regress_fwd(self._logits[k], fid)
       self._params.append(p)
-      ops.filter_fwd(self._acts[k], p, fid, out=self._acts[k + 1], variant=self.variant)
+      ops.filter_fwd(self._acts[k], p, fid, out=self._acts[k + 1], variant=self.variant, logits=self.fused)
     return self._acts[-1]
 
   def forward_resident(self, logits_list):
-    """Same as forward() with x_0 already resident in the chain's first activation buffer
-    (see input_buffer()); used by the benchmark's device-resident leg."""
+    """forward() with x_0 already resident in input_buffer()."""
     return self.forward(self._acts[0], logits_list)
-
-  def input_buffer(self, shape, device):
-    self._alloc(torch.empty(shape, device=device, dtype=torch.float32))
-    return self._acts[0]
 
   def backward(self, gout, need_input_grad=True):
     """gout = dL/dx_N.  Returns (dL/dx_0 or None, [dL/dlogits_k])."""
@@ -60,9 +76,38 @@ class FilterChain:
     for k in reversed(range(n)):
       fid = self.ids[k]
       need_gx = need_input_grad or k > 0
-      gx, gparams = ops.filter_bwd(self._acts[k], g, self._params[k], fid, need_gx=need_gx,
-                                   gx_out=self._gbuf[k & 1] if need_gx else None, variant=self.variant)
-      glogits[k] = ops.filter_regress_bwd(self._logits[k], gparams, fid)
+      gx, gp = ops.filter_bwd(self._acts[k], g, self._params[k], fid, need_gx=need_gx,
+                              gx_out=self._gbuf[k & 1] if need_gx else None, variant=self.variant,
+                              logits=self.fused, gparams_out=self._glog[k])
+      if self.fused:
+        glogits[k] = gp[:, :self._logits[k].shape[1]]
+      else:
+        glogits[k] = ops.filter_regress_bwd(self._logits[k], gp, fid)
       g = gx
     return g, glogits
 
+  # ---- CUDA graph of one fwd+bwd over the static buffers --------------------------------
+  def capture(self, logits_list, gout):
+    """Record forward_resident(logits_list) + backward(gout) into a CUDA graph.  `logits_list`
+    and `gout` become the graph's static inputs (update them in place), x_0 is input_buffer().
+    Returns (y, gx, glogits) static outputs."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for _ in range(2):
+        self.forward_resident(logits_list)
+        self.backward(gout)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    self._graph = torch.cuda.CUDAGraph()
+    l0 = ops.launch_count
+    with torch.cuda.graph(self._graph):
+      y = self.forward_resident(logits_list)
+      gx, gl = self.backward(gout)
+    self.graph_launches = ops.launch_count - l0
+    self._graph_out = (y, gx, gl)
+    return self._graph_out
+
+  def replay(self):
+    self._graph.replay()
+    return self._graph_out

@@ -35,13 +35,91 @@ struct __align__(16) FilterConsts {
   float scale[3];                   // L / (sum_i t_i + 1e-30)
   float S[3];                       // sum_i t_i + 1e-30
   float e;                          // Exposure: exp(p * ln2)
+  float raw[EXP_MAX_FILTER_PARAMS]; // raw regressor logits (EXP_OPT_LOGITS mode only)
 };
 
+// ---- filter_param_regressor of one image (filters.py:177-179, 201-203, 223-235, 256-262,
+// 306-310, 411-413, 435-436, 481-482; util.tanh_range util.py:281-294 with bias == 0, which
+// holds for every range the configs use).  Single-thread helpers: n <= 24 values.
+__device__ __forceinline__ float tanh_range_f(float f, float l, float r, float* dpdf) {
+  const float a = tanhf(f);
+  *dpdf = 0.5f * (r - l) * (1.f - a * a);
+  return (a * 0.5f + 0.5f) * (r - l) + l;
+}
+__device__ __forceinline__ float sigmoid_f(float f, float* d) {
+  const float s = 1.f / (1.f + expf(-f));
+  *d = s * (1.f - s);
+  return s;
+}
+// p[0..n) = regress(f[0..n)); BWD: gf[0..n) = J^T gp
+template <bool BWD>
+__device__ __forceinline__ void regress_image(int fid, const float* f, float* po, const float* gp, float* gf) {
+  float d;
+  switch (fid) {
+    case EXP_FILTER_EXPOSURE: {
+      const float p = tanh_range_f(f[0], -3.5f, 3.5f, &d);
+      if (BWD) gf[0] = gp[0] * d; else po[0] = p;
+    } break;
+    case EXP_FILTER_GAMMA: {
+      const float lg = 1.0986123f;                   // float32(np.log(3))
+      const float g = expf(tanh_range_f(f[0], -lg, lg, &d));
+      if (BWD) gf[0] = gp[0] * g * d; else po[0] = g;
+    } break;
+    case EXP_FILTER_WB: {
+      float s[3], ds[3];
+      for (int c = 0; c < 3; ++c) {
+        const float fm = c == 0 ? 0.f : f[c];        // mask (0,1,1)
+        s[c] = expf(tanh_range_f(fm, -0.5f, 0.5f, &ds[c]));
+        ds[c] = c == 0 ? 0.f : ds[c] * s[c];
+      }
+      const float D = 1e-5f + kLumR * s[0] + kLumG * s[1] + kLumB * s[2];
+      const float inv = 1.0f / D;
+      if (!BWD) {
+        for (int c = 0; c < 3; ++c) po[c] = s[c] * inv;
+      } else {
+        const float dot = (gp[0] * s[0] + gp[1] * s[1] + gp[2] * s[2]) * inv * inv;
+        const float coef[3] = {kLumR, kLumG, kLumB};
+        for (int c = 0; c < 3; ++c) gf[c] = (gp[c] * inv - dot * coef[c]) * ds[c];
+      }
+    } break;
+    case EXP_FILTER_SATPLUS:
+    case EXP_FILTER_WNB: {
+      const float p = sigmoid_f(f[0], &d);
+      if (BWD) gf[0] = gp[0] * d; else po[0] = p;
+    } break;
+    case EXP_FILTER_CONTRAST: {
+      const float a = tanhf(f[0]);
+      if (BWD) gf[0] = gp[0] * (1.f - a * a); else po[0] = a;
+    } break;
+    case EXP_FILTER_TONE:
+      for (int i = 0; i < 8; ++i) {
+        const float p = tanh_range_f(f[i], 0.5f, 2.f, &d);
+        if (BWD) gf[i] = gp[i] * d; else po[i] = p;
+      }
+      break;
+    case EXP_FILTER_COLOR:
+      for (int i = 0; i < 24; ++i) {
+        const float p = tanh_range_f(f[i], 0.90f, 1.10f, &d);
+        if (BWD) gf[i] = gp[i] * d; else po[i] = p;
+      }
+      break;
+    default: break;
+  }
+}
+
 // Executed by the first warp of a CTA; followed by __syncthreads() at the call site.
-__device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __restrict__ prow, int fid) {
+// logits != 0: prow holds raw regressor logits; the regressed parameters are computed here
+// (fused filter_param_regressor) and the logits kept for the backward's chain rule.
+__device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits = 0) {
   const int t = threadIdx.x;
   const int n = num_params(fid);
-  if (t < EXP_MAX_FILTER_PARAMS) sc.p[t] = (t < n) ? prow[t] : 0.f;
+  if (logits) {
+    if (t < EXP_MAX_FILTER_PARAMS) { sc.raw[t] = (t < n) ? prow[t] : 0.f; sc.p[t] = 0.f; }
+    __syncwarp();
+    if (t == 0) regress_image<false>(fid, sc.raw, sc.p, nullptr, nullptr);
+  } else {
+    if (t < EXP_MAX_FILTER_PARAMS) sc.p[t] = (t < n) ? prow[t] : 0.f;
+  }
   __syncwarp();
   if (t == 0) sc.e = expf(sc.p[0] * kLn2);                        // filters.py:182
   if (t < 3) {                                                    // filters.py:264-273 / 312-322
@@ -320,6 +398,17 @@ __device__ __forceinline__ void finalize_gparams(int fid, const double* sum, con
     const int n = num_params(fid);
     for (int i = 0; i < n; ++i) out[i] = (float)sum[i];
   }
+}
+
+// Same, followed (EXP_OPT_LOGITS mode) by the regressor's chain rule: out = dL/dlogits.
+__device__ __forceinline__ void finalize_grads(int fid, const double* sum, const FilterConsts& sc, int logits, float* out) {
+  if (!logits) {
+    finalize_gparams(fid, sum, sc.p, out);
+    return;
+  }
+  float gp[EXP_MAX_FILTER_PARAMS];
+  finalize_gparams(fid, sum, sc.p, gp);
+  regress_image<true>(fid, sc.raw, nullptr, gp, out);
 }
 
 }  // namespace expo

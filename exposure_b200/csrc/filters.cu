@@ -44,6 +44,7 @@ struct FilterArgs {
   float* partials;       // [B][nblk][kAccStride]
   unsigned* counters;    // [B]
   float* gparams;        // [B][pstride]
+  int logits;            // params are raw regressor logits (EXP_OPT_LOGITS)
 };
 
 // ---- 4 pixels <-> 3 float4 ------------------------------------------------------------
@@ -116,7 +117,7 @@ __device__ __forceinline__ void reduce_and_finish(float* acc, const FilterArgs& 
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    finalize_gparams(FID, tot, sc.p, A.gparams + (size_t)b * A.pstride);
+    finalize_grads(FID, tot, sc, A.logits, A.gparams + (size_t)b * A.pstride);
     A.counters[b] = 0u;      // leave the workspace ready for the next launch
   }
 }
@@ -127,7 +128,7 @@ __device__ __forceinline__ void filter_body(const FilterArgs& A) {
   __shared__ FilterConsts sc;
   __shared__ float red[BWD ? kWarps : 1][kAccStride];
   const int b = blockIdx.y;
-  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID);
+  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits);
   __syncthreads();
 
   const size_t img = (size_t)b * A.P * 3;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) filter_step_select_kernel(const Filt
     case 5: filter_body<5, BWD, HAS_GX, VEC>(A); break;
     case 6: filter_body<6, BWD, HAS_GX, VEC>(A); break;
     case 7: filter_body<7, BWD, HAS_GX, VEC>(A); break;
-    default: break;   // id -1 (pdf_sample u==0 quirk, pdf_sample_layer.py:5-10) is handled by the caller
+    default: break;   // id -1 (pdf_sample u==0 quirk, pdf_sample_layer.py:5-10): the caller pre-zeroes the output
   }
 }
 
@@ -223,19 +224,7 @@ static void launch_step(bool vec, const int* ids, int fid, dim3 grid, cudaStream
   }
 }
 
-// ---- filter_param_regressor kernels (one thread per image) -----------------------------
-__device__ __forceinline__ float tanh_range_f(float f, float l, float r, float* dpdf) {
-  // util.py:281-294 with bias == 0 for every range the configs use (initial at mid-range)
-  const float a = tanhf(f);
-  *dpdf = 0.5f * (r - l) * (1.f - a * a);
-  return (a * 0.5f + 0.5f) * (r - l) + l;
-}
-__device__ __forceinline__ float sigmoid_f(float f, float* d) {
-  const float s = 1.f / (1.f + expf(-f));
-  *d = s * (1.f - s);
-  return s;
-}
-
+// ---- filter_param_regressor kernels (one thread per image; math in filter_math.cuh) ------
 template <bool BWD>
 __global__ void regress_kernel(const float* __restrict__ logits, int lstride, float* __restrict__ params,
                                const float* __restrict__ gparams, int pstride, float* __restrict__ glogits,
@@ -249,56 +238,7 @@ __global__ void regress_kernel(const float* __restrict__ logits, int lstride, fl
   float* gf = BWD ? glogits + (size_t)b * lstride : nullptr;
   if (BWD) for (int i = 0; i < lstride; ++i) gf[i] = 0.f;
   if (fid < 0 || fid >= EXP_NUM_FILTERS) return;
-  float d;
-  switch (fid) {
-    case EXP_FILTER_EXPOSURE: {                      // filters.py:177-179
-      const float p = tanh_range_f(f[0], -3.5f, 3.5f, &d);
-      if (BWD) gf[0] = gp[0] * d; else po[0] = p;
-    } break;
-    case EXP_FILTER_GAMMA: {                         // filters.py:201-203
-      const float lg = 1.0986123f;                   // float32(np.log(3))
-      const float g = expf(tanh_range_f(f[0], -lg, lg, &d));
-      if (BWD) gf[0] = gp[0] * g * d; else po[0] = g;
-    } break;
-    case EXP_FILTER_WB: {                            // filters.py:223-235
-      float s[3], ds[3];
-      for (int c = 0; c < 3; ++c) {
-        const float fm = c == 0 ? 0.f : f[c];        // mask (0,1,1)
-        s[c] = expf(tanh_range_f(fm, -0.5f, 0.5f, &ds[c]));
-        ds[c] = c == 0 ? 0.f : ds[c] * s[c];
-      }
-      const float D = 1e-5f + kLumR * s[0] + kLumG * s[1] + kLumB * s[2];
-      const float inv = 1.0f / D;
-      if (!BWD) {
-        for (int c = 0; c < 3; ++c) po[c] = s[c] * inv;
-      } else {
-        const float dot = (gp[0] * s[0] + gp[1] * s[1] + gp[2] * s[2]) * inv * inv;
-        const float coef[3] = {kLumR, kLumG, kLumB};
-        for (int c = 0; c < 3; ++c) gf[c] = (gp[c] * inv - dot * coef[c]) * ds[c];
-      }
-    } break;
-    case EXP_FILTER_SATPLUS:
-    case EXP_FILTER_WNB: {                           // filters.py:481-482, 435-436
-      const float p = sigmoid_f(f[0], &d);
-      if (BWD) gf[0] = gp[0] * d; else po[0] = p;
-    } break;
-    case EXP_FILTER_CONTRAST: {                      // filters.py:411-413
-      const float a = tanhf(f[0]);
-      if (BWD) gf[0] = gp[0] * (1.f - a * a); else po[0] = a;
-    } break;
-    case EXP_FILTER_TONE:                            // filters.py:306-310
-      for (int i = 0; i < 8; ++i) {
-        const float p = tanh_range_f(f[i], 0.5f, 2.f, &d);
-        if (BWD) gf[i] = gp[i] * d; else po[i] = p;
-      }
-      break;
-    case EXP_FILTER_COLOR:                           // filters.py:256-262
-      for (int i = 0; i < 24; ++i) {
-        const float p = tanh_range_f(f[i], 0.90f, 1.10f, &d);
-        if (BWD) gf[i] = gp[i] * d; else po[i] = p;
-      }
-      break;
-  }
+  regress_image<BWD>(fid, f, po, gp, gf);
 }
 
 // ---- host side of the persistent TMA variant ---------------------------------------------
@@ -419,7 +359,9 @@ int exp_filter_regress_bwd(const float* logits, int lstride, const float* gparam
 }
 
 int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, const int* ids,
-                   int uniform_id, int B, int H, int W, int variant, void* stream) {
+                   int uniform_id, int B, int H, int W, int options, void* stream) {
+  const int logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
+  int variant = options & 0xFF;
   int rc = check_common(x, params, pstride, ids, uniform_id, B, H, W);
   if (rc) return rc;
   EXP_CHECK_ARG(y, "null output pointer");
@@ -432,6 +374,7 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, c
     if (ids) return set_error(EXP_ERR_UNSUPPORTED, "the TMA variant needs a uniform filter id");
     if ((long long)B * ((P + kTilePx - 1) / kTilePx) > 0x7fffffffll) return set_error(EXP_ERR_UNSUPPORTED, "too many tiles");
     TmaArgs T = make_tma_args(x, nullptr, y, params, pstride, B, P);
+    T.logits = logits;
     rc = launch_tma<false, false>(uniform_id, T, (cudaStream_t)stream);
     if (rc) return rc;
     EXP_CHECK_LAUNCH("exp_filter_fwd[tma]");
@@ -440,6 +383,7 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, c
   FilterArgs A{};
   A.x = x; A.out = y; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockFwd;
+  A.logits = logits;
   dim3 grid((P + kPixPerBlockFwd - 1) / kPixPerBlockFwd, B);
   launch_step<false, false>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);
   EXP_CHECK_LAUNCH("exp_filter_fwd");
@@ -456,7 +400,9 @@ size_t exp_filter_bwd_workspace_bytes(int B, int H, int W) {
 
 int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, const float* params,
                    int pstride, const int* ids, int uniform_id, int B, int H, int W, void* workspace,
-                   size_t workspace_bytes, int variant, void* stream) {
+                   size_t workspace_bytes, int options, void* stream) {
+  const int logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
+  int variant = options & 0xFF;
   int rc = check_common(x, params, pstride, ids, uniform_id, B, H, W);
   if (rc) return rc;
   EXP_CHECK_ARG(gy && gparams && workspace, "null gy / gparams / workspace pointer");
@@ -475,6 +421,7 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, c
     T.counters = reinterpret_cast<unsigned*>(workspace);
     T.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
     T.gparams = gparams;
+    T.logits = logits;
     rc = gx ? launch_tma<true, true>(uniform_id, T, (cudaStream_t)stream)
             : launch_tma<true, false>(uniform_id, T, (cudaStream_t)stream);
     if (rc) return rc;
@@ -485,6 +432,7 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, c
   FilterArgs A{};
   A.x = x; A.gy = gy; A.out = gx; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockBwd;
+  A.logits = logits;
   A.counters = reinterpret_cast<unsigned*>(workspace);
   A.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
   A.gparams = gparams;

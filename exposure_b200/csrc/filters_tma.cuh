@@ -37,6 +37,7 @@ struct TmaArgs {
   float* partials;        // [(grid + B)][kAccStride]
   unsigned* counters;     // [B]
   float* gparams;
+  int logits;             // params are raw regressor logits (EXP_OPT_LOGITS)
 };
 
 // Balanced static partition of the flat tile sequence: CTA i owns [floor(i*total/grid),
@@ -84,7 +85,7 @@ __device__ __forceinline__ void tma_flush(float* acc, const TmaArgs& A, const Fi
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      finalize_gparams(FID, tot, sc.p, A.gparams + (size_t)b * A.pstride);
+      finalize_grads(FID, tot, sc, A.logits, A.gparams + (size_t)b * A.pstride);
       A.counters[b] = 0u;
     }
   }
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kTmaThreads) filter_step_tma_kernel(const TmaA
         if (cur_b >= 0) tma_flush<FID>(acc, A, sc, red, tot, &ticket, cur_b);
       }
       __syncthreads();                                 // everyone done with the old constants
-      if (tid < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID);
+      if (tid < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits);
       __syncthreads();
       cur_b = b;
     }

@@ -93,8 +93,12 @@ def filter_regress_bwd(logits, gparams, ids):
   return glogits
 
 
-def filter_fwd(x, params, ids, out=None, variant=VARIANT_AUTO):
-  """y = process_{ids}(x, params).  x: [B,H,W,3]; params: [B, >=n]; ids: int or int32 [B]."""
+OPT_LOGITS = 0x100     # EXP_OPT_LOGITS: params are raw regressor logits (regressor fused in-kernel)
+
+
+def filter_fwd(x, params, ids, out=None, variant=VARIANT_AUTO, logits=False):
+  """y = process_{ids}(x, params).  x: [B,H,W,3]; params: [B, >=n]; ids: int or int32 [B].
+  logits=True: `params` are the raw regressor logits (filter_param_regressor runs in-kernel)."""
   global launch_count
   _chk_img(x, "x")
   B, H, W, _ = x.shape
@@ -103,7 +107,7 @@ def filter_fwd(x, params, ids, out=None, variant=VARIANT_AUTO):
   idp, uid = _ids_arg(ids, B)
   with _Timed("filter_fwd", ids, B * H * W * 24):
     _cabi.check(_cabi.lib().exp_filter_fwd(x.data_ptr(), y.data_ptr(), params.data_ptr(), ps, idp, uid, B, H, W,
-                                           variant, _stream()), "exp_filter_fwd")
+                                           variant | (OPT_LOGITS if logits else 0), _stream()), "exp_filter_fwd")
   launch_count += 1
   return y
 
@@ -121,15 +125,16 @@ def _workspace(dev, nbytes):
   return ws
 
 
-def filter_bwd(x, gy, params, ids, need_gx=True, gx_out=None, variant=VARIANT_AUTO):
-  """Returns (gx or None, gparams [B,24]).  Deterministic parameter-gradient reduction."""
+def filter_bwd(x, gy, params, ids, need_gx=True, gx_out=None, variant=VARIANT_AUTO, logits=False, gparams_out=None):
+  """Returns (gx or None, gparams [B,24]).  Deterministic parameter-gradient reduction.
+  logits=True: `params` are raw regressor logits and the returned gparams are dL/dlogits."""
   global launch_count
   _chk_img(x, "x")
   _chk_img(gy, "gy")
   B, H, W, _ = x.shape
   ps = _chk_mat(params, B, "params")
   gx = (torch.empty_like(x) if gx_out is None else gx_out) if need_gx else None
-  gparams = torch.zeros(B, PSTRIDE, device=x.device, dtype=torch.float32)
+  gparams = torch.zeros(B, PSTRIDE, device=x.device, dtype=torch.float32) if gparams_out is None else gparams_out
   l = _cabi.lib()
   nbytes = l.exp_filter_bwd_workspace_bytes(B, H, W)
   ws = _workspace(x.device, nbytes)
@@ -137,7 +142,7 @@ def filter_bwd(x, gy, params, ids, need_gx=True, gx_out=None, variant=VARIANT_AU
   with _Timed("filter_bwd" if need_gx else "filter_bwd_paramonly", ids, B * H * W * (36 if need_gx else 24)):
     _cabi.check(l.exp_filter_bwd(x.data_ptr(), gy.data_ptr(), gx.data_ptr() if need_gx else None,
                                  gparams.data_ptr(), params.data_ptr(), ps, idp, uid, B, H, W, ws.data_ptr(),
-                                 ws.numel(), variant, _stream()), "exp_filter_bwd")
+                                 ws.numel(), variant | (OPT_LOGITS if logits else 0), _stream()), "exp_filter_bwd")
   launch_count += 1
   return gx, gparams
 

@@ -60,6 +60,11 @@ enum {
   EXP_VARIANT_TMA = 2,    /* cp.async.bulk (TMA) -> shared-memory ring -> bulk store    */
   EXP_VARIANT_SCALAR = 3  /* one pixel per thread; any H*W, any 4-byte alignment        */
 };
+/* `options` of exp_filter_fwd / exp_filter_bwd = variant | flags.  EXP_OPT_LOGITS: `params`
+ * holds the RAW regressor logits (the input of exp_filter_regress_fwd); the kernel applies
+ * filter_param_regressor in its prologue and exp_filter_bwd returns dL/dlogits in `gparams`
+ * (regressor fused into the filter step: no separate per-image launches). */
+#define EXP_OPT_LOGITS 0x100
 
 /* ---- library ------------------------------------------------------------------- */
 int exp_version(void);               /* ABI version, currently 1                       */
@@ -86,7 +91,7 @@ int exp_filter_regress_bwd(const float* logits, int lstride, const float* gparam
  * x, y: [B,H,W,3] fp32, 16-byte aligned for the DIRECT/TMA variants (else SCALAR).
  * x == y (in place) is allowed.  Algorithmic HBM traffic: 24 B / pixel. */
 int exp_filter_fwd(const float* x, float* y, const float* params, int pstride,
-                   const int* ids, int uniform_id, int B, int H, int W, int variant,
+                   const int* ids, int uniform_id, int B, int H, int W, int options,
                    void* stream);
 
 /* Bytes of device workspace exp_filter_bwd needs for this shape: a fixed 256 KiB block of
@@ -107,7 +112,7 @@ size_t exp_filter_bwd_workspace_bytes(int B, int H, int W);
  * Algorithmic HBM traffic: 36 B / pixel with gx, 24 B / pixel without. */
 int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams,
                    const float* params, int pstride, const int* ids, int uniform_id,
-                   int B, int H, int W, void* workspace, size_t workspace_bytes, int variant,
+                   int B, int H, int W, void* workspace, size_t workspace_bytes, int options,
                    void* stream);
 
 /* ======================================================================================

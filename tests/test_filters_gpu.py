@@ -236,6 +236,49 @@ def test_full_size_properties(ops):
     assert torch.equal(gp, gp_again)
 
 
+def test_fused_regressor_matches_separate_kernels(ops):
+  """EXP_OPT_LOGITS: filter_param_regressor fused into the filter step == regress kernel + filter kernel."""
+  from exposure_b200 import _cabi
+  B, H, W = 3, 48, 40
+  x = F.synth_images(B, H, W, seed=14).cuda()
+  gy = torch.randn(B, H, W, 3, device="cuda")
+  for fid in ALL:
+    lg = F.synth_logits(fid, B).cuda()
+    params = ops.filter_regress_fwd(lg, fid)
+    for variant in (_cabi.VARIANT_DIRECT, _cabi.VARIANT_TMA, _cabi.VARIANT_SCALAR):
+      y0 = ops.filter_fwd(x, params, fid, variant=variant)
+      y1 = ops.filter_fwd(x, lg, fid, variant=variant, logits=True)
+      assert torch.equal(y0, y1), (fid, variant)
+      gx0, gp0 = ops.filter_bwd(x, gy, params, fid, variant=variant)
+      gl0 = ops.filter_regress_bwd(lg, gp0, fid)
+      gx1, gl1 = ops.filter_bwd(x, gy, lg, fid, variant=variant, logits=True)
+      assert torch.equal(gx0, gx1), (fid, variant)
+      n = F.NUM_PARAMS[fid]
+      assert torch.allclose(gl0, gl1[:, :n], rtol=1e-6, atol=1e-7), (fid, variant)
+
+
+def test_chain_graph_replay(ops):
+  from exposure_b200.chain import FilterChain
+  ids = [F.E, F.G, F.W, F.SP, F.T, F.CT, F.BW, F.C]
+  B, H, W = 4, 64, 64
+  x = F.synth_images(B, H, W, seed=3).cuda()
+  lgs = [(F.synth_logits(f, B, seed=5) * 0.5).cuda() for f in ids]
+  gout = torch.randn(B, H, W, 3, device="cuda")
+  eager = FilterChain(ids)
+  y = eager.forward(x, lgs).clone()
+  gx, gl = eager.backward(gout)
+  gx = gx.clone(); gl = [g.clone() for g in gl]
+  ch = FilterChain(ids)
+  ch.input_buffer(x.shape, x.device).copy_(x)
+  ch.capture(lgs, gout)
+  assert ch.graph_launches == 2 * len(ids)
+  for _ in range(2):
+    y2, gx2, gl2 = ch.replay()
+  assert torch.equal(y2, y) and torch.equal(gx2, gx)
+  for a, b in zip(gl2, gl):
+    assert torch.equal(a, b)
+
+
 def test_errors_are_loud(ops):
   from exposure_b200._cabi import ExposureLibError
   x = torch.zeros(1, 3, 3, 3, device="cuda")

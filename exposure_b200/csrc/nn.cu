@@ -263,23 +263,49 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
   out[o] = accumulate ? out[o] + v : v;
 }
 
-// out[batch, cols] = column sums of a[batch, rows, cols] (bias gradients, per-image channel sums)
-__global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, float* __restrict__ out) {
+// out[batch, cols] = column sums of a[batch, rows, cols] (bias gradients, per-image channel sums).
+// Rows are split into gridDim.z chunks; chunk z of batch y writes out[(y * gridDim.z + z) * cols + col].
+__global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, int rows_per_chunk,
+                              float* __restrict__ out) {
   __shared__ float red[8][33];
   a += (size_t)blockIdx.y * rows * cols;
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
-  float s = 0.f;
-  if (col < cols)
-    for (int r = ry; r < rows; r += 8) s += a[(size_t)r * cols + col];
-  red[ry][threadIdx.x & 31] = s;
+  const int r0 = blockIdx.z * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (col < cols) {
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {       // 4 independent loads in flight per thread
+      s0 += a[(size_t)r * cols + col];
+      s1 += a[(size_t)(r + 8) * cols + col];
+      s2 += a[(size_t)(r + 16) * cols + col];
+      s3 += a[(size_t)(r + 24) * cols + col];
+    }
+    for (; r < r1; r += 8) s0 += a[(size_t)r * cols + col];
+  }
+  red[ry][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (ry == 0 && col < cols) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[(size_t)blockIdx.y * cols + col] = t;
+    out[((size_t)blockIdx.y * gridDim.z + blockIdx.z) * cols + col] = t;
   }
+}
+// out[b, col] = sum_z part[(b * chunks + z) * cols + col]   (fixed order)
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int chunks, int cols, int batch,
+                                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * cols) return;
+  const int b = i / cols, col = i - b * cols;
+  float s = 0.f;
+  for (int z = 0; z < chunks; ++z) s += part[((size_t)b * chunks + z) * cols + col];
+  out[i] = s;
+}
+static int colsum_chunks(int rows) {
+  int c = (rows + 1023) / 1024;
+  return c < 1 ? 1 : (c > 128 ? 128 : c);
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -488,11 +514,30 @@ int exp_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, i
   return EXP_OK;
 }
 
-int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* stream) {
+size_t exp_colsum_workspace_bytes(int batch, int rows, int cols) {
+  if (batch <= 0 || rows <= 0 || cols <= 0) return 0;
+  const int chunks = colsum_chunks(rows);
+  return chunks > 1 ? (size_t)batch * chunks * cols * sizeof(float) : 0;
+}
+
+int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* workspace, size_t workspace_bytes,
+               void* stream) {
   EXP_CHECK_ARG(a && out && batch > 0 && batch <= 65535 && rows > 0 && cols > 0, "bad args");
-  dim3 grid((cols + 31) / 32, batch);
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, out);
+  int chunks = colsum_chunks(rows);
+  const size_t need = (size_t)batch * chunks * cols * sizeof(float);
+  if (chunks > 1 && (!workspace || workspace_bytes < need)) chunks = 1;   // single pass (slower, still exact)
+  const int rpc = (rows + chunks - 1) / chunks;
+  dim3 grid((cols + 31) / 32, batch, chunks);
+  if (chunks == 1) {
+    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, rpc, out);
+    EXP_CHECK_LAUNCH("exp_colsum");
+    return EXP_OK;
+  }
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, rpc, reinterpret_cast<float*>(workspace));
   EXP_CHECK_LAUNCH("exp_colsum");
+  colsum_finish_kernel<<<(batch * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float*>(workspace), chunks, cols, batch, out);
+  EXP_CHECK_LAUNCH("exp_colsum[finish]");
   return EXP_OK;
 }
 

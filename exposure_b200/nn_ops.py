@@ -163,8 +163,12 @@ def colsum(a, batch=1, out=None):
   cols = a.shape[-1]
   rows = a.numel() // cols // batch
   o = torch.empty((batch, cols) if batch > 1 else (cols,), device=a.device, dtype=torch.float32) if out is None else out
-  _cabi.check(_cabi.lib().exp_colsum(a.data_ptr(), batch, rows, cols, o.data_ptr(), _stream()), "exp_colsum")
-  _n()
+  l = _cabi.lib()
+  nbytes = l.exp_colsum_workspace_bytes(batch, rows, cols)
+  ws = _workspace(a.device, nbytes) if nbytes else None
+  _cabi.check(l.exp_colsum(a.data_ptr(), batch, rows, cols, o.data_ptr(), _p(ws), ws.numel() if ws is not None else 0,
+                           _stream()), "exp_colsum")
+  _n(2 if nbytes else 1)
   return o
 
 

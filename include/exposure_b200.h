@@ -172,8 +172,11 @@ int exp_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act,
 int exp_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, int M, int K, int N,
                  int accumulate, void* stream);
 /* out[batch, cols] = column sums of a[batch, rows, cols] (bias gradients; per-image channel
- * sums of the layer-1 input gradient that feed exp_stats_bwd). */
-int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* stream);
+ * sums of the layer-1 input gradient that feed exp_stats_bwd).  Long columns are reduced in
+ * row chunks through `workspace` (deterministic two-stage; NULL workspace = single pass). */
+size_t exp_colsum_workspace_bytes(int batch, int rows, int cols);
+int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* workspace,
+               size_t workspace_bytes, void* stream);
 
 /* ======================================================================================
  * Per-image head math of the train step (all enqueue-only, no host round trip).

@@ -49,7 +49,7 @@ def test_tc_conv_forward_and_tangent(nn, case):
   nn.set_gemm_backend(nn.BACKEND_CUDA_CORES)
   ys = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=shift)
   nn.set_gemm_backend(nn.BACKEND_TCGEN05)
-  _close(yd, ys.double().cpu(), tol=1e-5)
+  _close(yd, ys.double().cpu(), tol=3e-5)    # two different fp32 summation orders over K up to 2048
   pm = (torch.rand(y.shape, generator=torch.Generator().manual_seed(9)) < 0.5).float() * 2
   y1, y2 = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=shift, post_mul=pm.cuda())
   assert torch.equal(y1, yd) and torch.equal(y2, yd * pm.cuda())

@@ -224,6 +224,78 @@ static void launch_step(bool vec, const int* ids, int fid, dim3 grid, cudaStream
   }
 }
 
+// ---- S filter steps fused into ONE pass over the pixels (inference / high-resolution path) --
+// y[b] = f_{ids[S-1][b]}( ... f_{ids[0][b]}(x[b]) ... ): intermediates stay in registers, so the
+// whole episode costs 24 B/pixel of HBM traffic instead of 24*S (net.py:796-820 applies the
+// test_steps selected filters to the full-resolution image one sess.run at a time).
+constexpr int kMaxChain = 8;
+struct ChainArgs {
+  const float* x; float* y; const float* params; const int* ids;   // params [S][B][pstride], ids [S][B]
+  int S, B, P, pstride, pix_per_block, logits;
+};
+
+template <int FID>
+__device__ __forceinline__ void chain_apply(float (&px)[4][3], const FilterConsts& sc, int npx) {
+  float py[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < npx) {
+      px_fwd<FID>(px[i], py, sc);
+      px[i][0] = py[0]; px[i][1] = py[1]; px[i][2] = py[2];
+    }
+  }
+}
+__device__ __forceinline__ void chain_apply_any(int fid, float (&px)[4][3], const FilterConsts& sc, int npx) {
+  switch (fid) {
+    case 0: chain_apply<0>(px, sc, npx); break;
+    case 1: chain_apply<1>(px, sc, npx); break;
+    case 2: chain_apply<2>(px, sc, npx); break;
+    case 3: chain_apply<3>(px, sc, npx); break;
+    case 4: chain_apply<4>(px, sc, npx); break;
+    case 5: chain_apply<5>(px, sc, npx); break;
+    case 6: chain_apply<6>(px, sc, npx); break;
+    case 7: chain_apply<7>(px, sc, npx); break;
+    default:                                   // id -1: all-zero one-hot -> black (pdf_sample quirk)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) px[i][0] = px[i][1] = px[i][2] = 0.f;
+      break;
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) filter_chain_fwd_kernel(const ChainArgs A) {
+  __shared__ FilterConsts sc[kMaxChain];
+  __shared__ int fids[kMaxChain];
+  const int b = blockIdx.y;
+  for (int s = 0; s < A.S; ++s) {
+    const int f = A.ids ? A.ids[s * A.B + b] : -1;
+    if (threadIdx.x == 0) fids[s] = f;
+    if (threadIdx.x < 32 && f >= 0 && f < EXP_NUM_FILTERS)
+      setup_consts(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits);
+  }
+  __syncthreads();
+  const size_t img = (size_t)b * A.P * 3;
+  const float* __restrict__ x = A.x + img;
+  float* __restrict__ y = A.y + img;
+  const int p0 = blockIdx.x * A.pix_per_block;
+  const int p1 = min(A.P, p0 + A.pix_per_block);
+  if constexpr (VEC) {
+    for (int q = (p0 >> 2) + threadIdx.x; q < (p1 >> 2); q += kThreads) {
+      float px[4][3];
+      unpack(load_px4(x, q), px);
+      for (int s = 0; s < A.S; ++s) chain_apply_any(fids[s], px, sc[s], 4);
+      store_px4(y, q, pack(px));
+    }
+  } else {
+    for (int q = p0 + threadIdx.x; q < p1; q += kThreads) {
+      float px[4][3];
+      px[0][0] = x[3 * (size_t)q]; px[0][1] = x[3 * (size_t)q + 1]; px[0][2] = x[3 * (size_t)q + 2];
+      for (int s = 0; s < A.S; ++s) chain_apply_any(fids[s], px, sc[s], 1);
+      y[3 * (size_t)q] = px[0][0]; y[3 * (size_t)q + 1] = px[0][1]; y[3 * (size_t)q + 2] = px[0][2];
+    }
+  }
+}
+
 // ---- filter_param_regressor kernels (one thread per image; math in filter_math.cuh) ------
 template <bool BWD>
 __global__ void regress_kernel(const float* __restrict__ logits, int lstride, float* __restrict__ params,
@@ -387,6 +459,28 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, c
   dim3 grid((P + kPixPerBlockFwd - 1) / kPixPerBlockFwd, B);
   launch_step<false, false>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);
   EXP_CHECK_LAUNCH("exp_filter_fwd");
+  return EXP_OK;
+}
+
+int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstride, const int* ids, int S, int B,
+                         int H, int W, int options, void* stream) {
+  EXP_CHECK_ARG(x && y && params && ids, "null pointer");
+  EXP_CHECK_ARG(S >= 1 && S <= kMaxChain, "S must be in [1, %d] (got %d)", kMaxChain, S);
+  EXP_CHECK_ARG(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 29), "bad shape");
+  EXP_CHECK_ARG(pstride >= EXP_MAX_FILTER_PARAMS, "per-image ids need pstride >= %d (got %d)", EXP_MAX_FILTER_PARAMS, pstride);
+  const int P = H * W;
+  bool vec;
+  int variant = options & 0xFF;
+  if (variant == EXP_VARIANT_TMA) variant = EXP_VARIANT_DIRECT;
+  int rc = pick_vec(variant, P, x, y, nullptr, &vec);
+  if (rc) return rc;
+  ChainArgs A{};
+  A.x = x; A.y = y; A.params = params; A.ids = ids; A.S = S; A.B = B; A.P = P; A.pstride = pstride;
+  A.pix_per_block = kPixPerBlockFwd; A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
+  dim3 grid((P + kPixPerBlockFwd - 1) / kPixPerBlockFwd, B);
+  if (vec) filter_chain_fwd_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
+  else filter_chain_fwd_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
+  EXP_CHECK_LAUNCH("exp_filter_chain_fwd");
   return EXP_OK;
 }
 

@@ -112,6 +112,25 @@ def filter_fwd(x, params, ids, out=None, variant=VARIANT_AUTO, logits=False):
   return y
 
 
+def filter_chain_fwd(x, params, ids, out=None, logits=False):
+  """S filter steps in ONE pass: x [B,H,W,3]; params [S,B,24]; ids int32 [S,B]."""
+  global launch_count
+  _chk_img(x, "x")
+  B, H, W, _ = x.shape
+  S = ids.shape[0]
+  if not (params.is_cuda and params.dtype == torch.float32 and params.is_contiguous() and tuple(params.shape) == (S, B, PSTRIDE)):
+    raise ValueError("params must be a contiguous CUDA float32 [S,B,%d] tensor" % PSTRIDE)
+  if not (ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous() and tuple(ids.shape) == (S, B)):
+    raise ValueError("ids must be a contiguous CUDA int32 [S,B] tensor")
+  y = torch.empty_like(x) if out is None else out
+  with _Timed("filter_chain_fwd", "fused%d" % S, B * H * W * 24):
+    _cabi.check(_cabi.lib().exp_filter_chain_fwd(x.data_ptr(), y.data_ptr(), params.data_ptr(), PSTRIDE, ids.data_ptr(),
+                                                 S, B, H, W, OPT_LOGITS if logits else 0, _stream()),
+                "exp_filter_chain_fwd")
+  launch_count += 1
+  return y
+
+
 _workspaces = {}
 
 

@@ -94,6 +94,15 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride,
                    const int* ids, int uniform_id, int B, int H, int W, int options,
                    void* stream);
 
+/* ---- S filter steps in ONE pass (inference / high-resolution path) ----------------------
+ * y[b] = f_{ids[S-1][b]}( ... f_{ids[0][b]}(x[b]) ... ) with params [S][B][pstride] and
+ * ids int32 [S][B] (id -1 = black, the pdf_sample u==0 quirk).  Intermediates stay in
+ * registers: 24 B/pixel for the whole episode instead of 24*S.  Replaces the per-step
+ * high_res_output of Filter.apply (filters.py:89-96) driven by net.py:796-820 (one sess.run
+ * per step on the full-resolution image).  S <= 8. */
+int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstride, const int* ids,
+                         int S, int B, int H, int W, int options, void* stream);
+
 /* Bytes of device workspace exp_filter_bwd needs for this shape: a fixed 256 KiB block of
  * per-image ticket counters followed by the partial-sum records of the per-image parameter
  * gradients.  The counter block must be zero-filled once before first use; every launch

@@ -36,7 +36,7 @@ class FilterChain:
       mk = lambda: torch.empty(shape, device=device, dtype=torch.float32)
       self._acts = [mk() for _ in range(n + 1)]
       self._gbuf = [mk() for _ in range(2)]
-      self._glog = [torch.zeros(shape[0], ops.PSTRIDE, device=device) for _ in range(n)]
+      self._glog = None
       self._graph = None
 
   def input_buffer(self, shape, device):
@@ -54,6 +54,9 @@ class FilterChain:
     if self._acts[0].data_ptr() != x.data_ptr():
       self._acts[0].copy_(x)
     self._logits = [l.contiguous() for l in logits_list]
+    if self._glog is None or any(g.shape != l.shape for g, l in zip(self._glog, self._logits)):
+      self._glog = [torch.zeros_like(l) if self.fused else torch.zeros(l.shape[0], ops.PSTRIDE, device=l.device)
+                    for l in self._logits]
     self._params = []
     for k, fid in enumerate(self.ids):
       if self.fused:
@@ -80,7 +83,7 @@ class FilterChain:
                               gx_out=self._gbuf[k & 1] if need_gx else None, variant=self.variant,
                               logits=self.fused, gparams_out=self._glog[k])
       if self.fused:
-        glogits[k] = gp[:, :self._logits[k].shape[1]]
+        glogits[k] = gp
       else:
         glogits[k] = ops.filter_regress_bwd(self._logits[k], gp, fid)
       g = gx

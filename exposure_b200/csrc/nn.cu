@@ -10,6 +10,7 @@
 // Layouts follow the reference checkpoint: activations NHWC, conv weights HWIO
 // [4,4,Cin,Cout], FC weights [in,out], flatten order (h*4+w)*256+c.
 #include "gemm_engine.cuh"
+#include "gemm_engine_v4.cuh"
 #include "nn_tc.h"
 
 namespace expo {
@@ -63,6 +64,27 @@ struct ConvFprop {
     if (ci >= Cin || n >= Cout) return 0.f;
     return __ldg(W + ((size_t)s.tap * Cin + ci) * Cout + n);
   }
+  // ---- vectorised engine (Cv == 0, Cx % 16 == 0, Cout % 4 == 0): K steps of 16 inside one tap
+  __device__ int k_iters16() const { return 16 * (Cin / kBK4); }
+  __device__ KS kstate16(int ki) const {
+    KS s;
+    const int c16 = Cin / kBK4;
+    s.tap = ki / c16;
+    s.ci0 = (ki - s.tap * c16) * kBK4;
+    s.ky = s.tap >> 2; s.kx = s.tap & 3;
+    return s;
+  }
+  __device__ float4 load_a_k4(const RowA& r, const KS& s, int c) const {
+    const int iy = r.iy0 + s.ky, ix = r.ix0 + s.kx;
+    if (r.b < 0 || (unsigned)iy >= (unsigned)IH || (unsigned)ix >= (unsigned)IW) return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(r.b * IH + iy) * IW + ix) * Cx + s.ci0 + 4 * c));
+    v.x -= shift; v.y -= shift; v.z -= shift; v.w -= shift;
+    return v;
+  }
+  __device__ float4 load_b_n4(const KS& s, int kk, int n) const {
+    if (n >= Cout) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(W + ((size_t)s.tap * Cin + s.ci0 + kk) * Cout + n));
+  }
   __device__ void store(int m, int n, float v) const {
     if (m >= B * OH * OW || n >= Cout) return;
     const size_t idx = (size_t)m * Cout + n;
@@ -115,6 +137,30 @@ struct ConvDgrad {
     if (n >= Cin) return 0.f;
     return __ldg(W + ((size_t)s.tap * Cin + n) * Cout + s.co0 + kk);
   }
+  // ---- vectorised engine (Cout % 16 == 0)
+  __device__ int k_iters16() const { return 4 * (Cout / kBK4); }
+  __device__ KS kstate16(int ki) const {
+    KS s;
+    const int c16 = Cout / kBK4;
+    const int t = ki / c16;
+    s.co0 = (ki - t * c16) * kBK4;
+    const int j = t >> 1, l = t & 1;
+    const int ky = py == 0 ? (j == 0 ? 1 : 3) : (j == 0 ? 0 : 2);
+    const int kx = px == 0 ? (l == 0 ? 1 : 3) : (l == 0 ? 0 : 2);
+    s.oy_off = py == 0 ? (j == 0 ? 0 : -1) : (j == 0 ? 1 : 0);
+    s.ox_off = px == 0 ? (l == 0 ? 0 : -1) : (l == 0 ? 1 : 0);
+    s.tap = ky * 4 + kx;
+    return s;
+  }
+  __device__ float4 load_a_k4(const RowA& r, const KS& s, int c) const {
+    const int oy = r.a + s.oy_off, ox = r.c + s.ox_off;
+    if (r.b < 0 || (unsigned)oy >= (unsigned)OH || (unsigned)ox >= (unsigned)OW) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(dy + ((size_t)(r.b * OH + oy) * OW + ox) * Cout + s.co0 + 4 * c));
+  }
+  __device__ float4 load_b_k4(const KS& s, int c, int n) const {
+    if (n >= Cin) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(W + ((size_t)s.tap * Cin + n) * Cout + s.co0 + 4 * c));
+  }
   __device__ void store(int m, int n, float v) const {
     if (m >= B * (IH / 2) * (IW / 2) || n >= Cin) return;
     const int b = m >> lgHW2;
@@ -162,6 +208,27 @@ struct ConvWgrad {
     const int p = s.p0 + kk;
     if (p >= B * OH * OW || n >= Cout) return 0.f;
     return __ldg(dy + (size_t)p * Cout + n);
+  }
+  // ---- vectorised engine (Cv == 0, Cx % 4 == 0, Cout % 4 == 0): 4 consecutive ci per load
+  __device__ int k_iters16() const { return pix_per_split / kBK4; }
+  __device__ KS kstate16(int ki) const { KS s; s.p0 = p_begin + ki * kBK4; return s; }
+  __device__ float4 load_a_m4(const KS& s, int kk, int m) const {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int p = s.p0 + kk;
+    if (m >= 16 * Cin || p >= B * OH * OW) return z;
+    const int tap = m / Cin, ci = m - tap * Cin;
+    const int b = p >> lgOHW;
+    const int rem = p & ((1 << lgOHW) - 1);
+    const int iy = 2 * (rem >> lgOW) - 1 + (tap >> 2), ix = 2 * (rem & (OW - 1)) - 1 + (tap & 3);
+    if ((unsigned)iy >= (unsigned)IH || (unsigned)ix >= (unsigned)IW) return z;
+    float4 v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(b * IH + iy) * IW + ix) * Cx + ci));
+    v.x -= shift; v.y -= shift; v.z -= shift; v.w -= shift;
+    return v;
+  }
+  __device__ float4 load_b_n4(const KS& s, int kk, int n) const {
+    const int p = s.p0 + kk;
+    if (p >= B * OH * OW || n >= Cout) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return __ldg(reinterpret_cast<const float4*>(dy + (size_t)p * Cout + n));
   }
   __device__ void store(int m, int n, float v) const {
     if (m >= 16 * Cin || n >= Cout) return;
@@ -356,7 +423,10 @@ int exp_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, 
     EXP_CHECK_LAUNCH("exp_conv_fwd[tcgen05]");
     return EXP_OK;
   }
-  if (Cout <= 32) launch_gemm<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
+  if (Cv == 0 && Cx % kBK4 == 0 && Cout % 4 == 0 && aligned16(x) && aligned16(W)) {   // 16-byte gathers
+    if (Cout <= 32) launch_gemm_v4<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
+    else launch_gemm_v4<ConvFprop, 64, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
+  } else if (Cout <= 32) launch_gemm<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
   else launch_gemm<ConvFprop, 64, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_conv_fwd");
   return EXP_OK;
@@ -378,7 +448,10 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
     EXP_CHECK_LAUNCH("exp_conv_dgrad[tcgen05]");
     return EXP_OK;
   }
-  if (Cin <= 32) launch_gemm<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
+  if (Cout % kBK4 == 0 && aligned16(dy) && aligned16(W)) {                             // 16-byte gathers
+    if (Cin <= 32) launch_gemm_v4<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
+    else launch_gemm_v4<ConvDgrad, 64, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
+  } else if (Cin <= 32) launch_gemm<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
   else launch_gemm<ConvDgrad, 64, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_conv_dgrad");
   return EXP_OK;
@@ -417,9 +490,12 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
   p.lgOW = host_ilog2(OW); p.lgOHW = host_ilog2(OH * OW); p.shift = shift;
   const int pixels = B * OH * OW;
   int pps = (pixels + splits - 1) / splits;
-  pps = ((pps + kBK - 1) / kBK) * kBK;
+  pps = ((pps + kBK4 - 1) / kBK4) * kBK4;
   p.pix_per_split = pps;
-  if (Cout <= 32) launch_gemm<ConvWgrad, 32, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
+  if (Cv == 0 && Cx % 4 == 0 && Cout % 4 == 0 && aligned16(x) && aligned16(dy)) {         // 16-byte gathers
+    if (Cout <= 32) launch_gemm_v4<ConvWgrad, 32, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
+    else launch_gemm_v4<ConvWgrad, 64, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
+  } else if (Cout <= 32) launch_gemm<ConvWgrad, 32, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
   else launch_gemm<ConvWgrad, 64, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_conv_wgrad");
   const size_t count = (size_t)16 * Cin * Cout;

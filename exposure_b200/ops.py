@@ -153,7 +153,13 @@ def filter_bwd(x, gy, params, ids, need_gx=True, gx_out=None, variant=VARIANT_AU
   B, H, W, _ = x.shape
   ps = _chk_mat(params, B, "params")
   gx = (torch.empty_like(x) if gx_out is None else gx_out) if need_gx else None
-  gparams = torch.zeros(B, PSTRIDE, device=x.device, dtype=torch.float32) if gparams_out is None else gparams_out
+  # the ABI uses ONE row stride for params and gparams
+  if gparams_out is None:
+    gparams = torch.zeros(B, ps, device=x.device, dtype=torch.float32)
+  else:
+    gparams = gparams_out
+    if _chk_mat(gparams, B, "gparams_out") != ps:
+      raise ValueError("gparams_out must have the same row stride as params (%d)" % ps)
   l = _cabi.lib()
   nbytes = l.exp_filter_bwd_workspace_bytes(B, H, W)
   ws = _workspace(x.device, nbytes)

@@ -144,6 +144,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const P p_in) {
   const int KI = p.k_iters();
   constexpr uint32_t idesc = idesc_tf32(kBM, BN);
 
+  // register prefetch: the global gathers of K step ki+1 are in flight while step ki is split,
+  // stored, fenced and handed to the tensor core (the gather latency was fully exposed before)
+  float4 areg[4], breg[NBV];
+  auto gather = [&](int ki) {
+    const typename P::KS ks = p.kstate(ki);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) areg[j] = p.load_a4(ra[j], ks, a_c[j]);
+#pragma unroll
+    for (int j = 0; j < NBV; ++j) {
+      const int idx = tid + kThreads * j;
+      breg[j] = p.load_b4(ks, n0 + idx % BN, idx / BN);
+    }
+  };
+  if (KI > 0) gather(0);
+
   for (int ki = 0; ki < KI; ++ki) {
     const int s = ki & 1;
     unsigned char* a_hi = base + (size_t)s * kStageBytes;
@@ -151,15 +166,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const P p_in) {
     unsigned char* b_hi = a_lo + kTileABytes;
     unsigned char* b_lo = b_hi + kTileBBytes;
     if (ki >= 2) mbar_wait(&mbar[s], (uint32_t)(((ki >> 1) - 1) & 1));   // MMAs of step ki-2 done with this stage
-    const typename P::KS ks = p.kstate(ki);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split_store(a_hi, a_lo, sw128_off(a_row[j], a_c[j]), p.load_a4(ra[j], ks, a_c[j]));
+    for (int j = 0; j < 4; ++j) split_store(a_hi, a_lo, sw128_off(a_row[j], a_c[j]), areg[j]);
 #pragma unroll
     for (int j = 0; j < NBV; ++j) {
       const int idx = tid + kThreads * j;
-      const int n = idx % BN, c = idx / BN;
-      split_store(b_hi, b_lo, sw128_off(n, c), p.load_b4(ks, n0 + n, c));
+      split_store(b_hi, b_lo, sw128_off(idx % BN, idx / BN), breg[j]);
     }
+    if (ki + 1 < KI) gather(ki + 1);
     fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {

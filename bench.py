@@ -335,16 +335,17 @@ def run_native(args):
   hx.copy_(x0.cpu())
   hy = torch.empty(B, S, S, 3, dtype=torch.float32).pin_memory()
   hg = [torch.empty(B, ops.NUM_PARAMS[f]).pin_memory() for f in CHAIN_IDS]
-  xin = chain.input_buffer((B, S, S, 3), dev)
+  # public host-buffer API: H2D of the batch, chain fwd+bwd, D2H of the filtered batch (net.py:330
+  # fetches fake_output every step) and of the parameter gradients, software-pipelined over 4
+  # sub-batches on three streams (exposure_b200/chain.py HostPipelinedChain)
+  from exposure_b200.chain import HostPipelinedChain
+  n_chunks = 4 if B % 4 == 0 else 1
+  del chain                                          # free the resident chain's activations first
+  torch.cuda.empty_cache()
+  pipe = HostPipelinedChain(CHAIN_IDS, B, S, S, dev, chunks=n_chunks, variant=args.variant)
 
   def e2e_step():
-    xin.copy_(hx, non_blocking=True)                 # H2D of this step's inputs
-    y = chain.forward_resident(logits)
-    _, glogits = chain.backward(gout, need_input_grad=True)
-    hy.copy_(y, non_blocking=True)                   # D2H: filtered batch (net.py:330 fetches fake_output)
-    for h, gq in zip(hg, glogits):
-      h.copy_(gq, non_blocking=True)                 # D2H: parameter gradients
-    torch.cuda.current_stream().synchronize()
+    pipe.step(hx, logits, gout, hy, hg)
 
   e2e_steps = max(3, min(args.steps, 10))
   for _ in range(2):

@@ -114,3 +114,55 @@ class FilterChain:
   def replay(self):
     self._graph.replay()
     return self._graph_out
+
+
+class HostPipelinedChain:
+  """chain fwd+bwd for batches that live in HOST (pinned) memory: the batch is cut into `chunks`
+  sub-batches and H2D copy / compute / D2H copy of consecutive sub-batches overlap on three CUDA
+  streams (PCIe is full duplex), so a step costs ~max(H2D, compute, D2H) instead of their sum.
+
+  This is the public end-to-end entry point bench.py's `e2e` leg times."""
+
+  def __init__(self, ids, batch, height, width, device, chunks=4, variant=ops.VARIANT_AUTO):
+    assert batch % chunks == 0
+    self.ids, self.chunks, self.cb = list(ids), chunks, batch // chunks
+    self.device = device
+    self.sub = [FilterChain(ids, variant=variant) for _ in range(chunks)]
+    for ch in self.sub:
+      ch.input_buffer((self.cb, height, width, 3), device)
+    self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
+    self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
+    self.ev_cmp = [torch.cuda.Event() for _ in range(chunks)]
+    self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
+    self._first = True
+
+  def step(self, hx, logits_list, gout, hy, hglogits):
+    """hx, hy: pinned host [B,H,W,3]; logits_list[k]: device [B,n_k]; gout: device [B,H,W,3];
+    hglogits[k]: pinned host [B,n_k].  Blocks until the results are in host memory."""
+    cb = self.cb
+    cur = torch.cuda.current_stream()
+    for s in (self.s_in, self.s_cmp, self.s_out):
+      s.wait_stream(cur)
+    for c, ch in enumerate(self.sub):
+      sl = slice(c * cb, (c + 1) * cb)
+      with torch.cuda.stream(self.s_in):
+        if not self._first:
+          self.s_in.wait_event(self.ev_cmp[c])          # previous step's compute on this buffer is done
+        ch._acts[0].copy_(hx[sl], non_blocking=True)
+        self.ev_in[c].record(self.s_in)
+      with torch.cuda.stream(self.s_cmp):
+        self.s_cmp.wait_event(self.ev_in[c])
+        if not self._first:
+          self.s_cmp.wait_event(self.ev_out[c])         # previous step's D2H of this chunk's outputs is done
+        y = ch.forward_resident([l[sl] for l in logits_list])
+        _, gl = ch.backward(gout[sl], need_input_grad=True)
+        self.ev_cmp[c].record(self.s_cmp)
+      with torch.cuda.stream(self.s_out):
+        self.s_out.wait_event(self.ev_cmp[c])
+        hy[sl].copy_(y, non_blocking=True)
+        for h, g in zip(hglogits, gl):
+          h[sl].copy_(g, non_blocking=True)
+        self.ev_out[c].record(self.s_out)
+    self._first = False
+    cur.wait_stream(self.s_out)
+    cur.synchronize()

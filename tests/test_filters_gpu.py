@@ -279,6 +279,28 @@ def test_chain_graph_replay(ops):
     assert torch.equal(a, b)
 
 
+def test_host_pipelined_chain_matches_resident(ops):
+  from exposure_b200.chain import FilterChain, HostPipelinedChain
+  ids = [F.E, F.G, F.W, F.SP, F.T, F.CT, F.BW, F.C]
+  B, H, W = 8, 64, 64
+  x = F.synth_images(B, H, W, seed=31)
+  lgs = [(F.synth_logits(f, B, seed=7) * 0.5).cuda() for f in ids]
+  gout = torch.randn(B, H, W, 3, device="cuda")
+  ref = FilterChain(ids)
+  y = ref.forward(x.cuda(), lgs).clone()
+  _, gl = ref.backward(gout)
+  hx = x.pin_memory()
+  hy = torch.empty(B, H, W, 3).pin_memory()
+  hg = [torch.empty(B, F.NUM_PARAMS[f]).pin_memory() for f in ids]
+  pipe = HostPipelinedChain(ids, B, H, W, torch.device("cuda"), chunks=4)
+  for _ in range(3):                                   # buffers are reused across steps
+    hy.zero_()
+    pipe.step(hx, lgs, gout, hy, hg)
+    assert torch.equal(hy, y.cpu())
+    for a, b in zip(hg, gl):
+      assert torch.equal(a, b.cpu())
+
+
 def test_errors_are_loud(ops):
   from exposure_b200._cabi import ExposureLibError
   x = torch.zeros(1, 3, 3, 3, device="cuda")

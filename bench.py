@@ -433,9 +433,17 @@ def run_train(args):
 
   # bootstrap like iteration 0 of net.py:318-328 (generator steps with lr 0 until terminated
   # records exist), shortened: 2 * test_steps generator steps are enough to terminate records
+  def note(msg):
+    if rank == 0:
+      print("[bench train] " + msg, file=sys.stderr, flush=True)
+
   t.train_iteration(0, giters=2 * cfg.test_steps + 2, citers=1)
+  torch.cuda.synchronize()
+  note("bootstrap done")
   if not args.no_graphs:
     t.enable_graphs(B)                              # each step = one CUDA-graph replay
+    torch.cuda.synchronize()
+    note("graphs captured (optimizer inside the graph: %s)" % t._graph_apply)
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
@@ -444,6 +452,7 @@ def run_train(args):
     t.train_iteration(it, giters=1, citers=5)
     it += 1
   barrier()
+  note("warm-up done")
   ops.event_log = []
   l0 = ops.launch_count
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -84,13 +84,18 @@ class Trainer:
     snap = [t.clone() for s in (self.gen, self.val, self.cri) for t in (s.flat, s.m, s.v)]
     for k in "gvc":
       self._hyper[k].zero_()
+    # world > 1: the graphs hold forward + backward only; the NCCL all-reduce and the fused Adam
+    # are enqueued right after each replay (3 more launches per step) -- collectives inside a
+    # captured graph hung on this stack, and keeping NCCL out of the capture is always legal
+    self._graph_apply = self.world == 1
+    ga = self._graph_apply
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):                                  # warm-up (allocations, lazy attributes)
       for _ in range(2):
         self._generator_impl(self._gi["img"], self._gi["states"], self._gi["noise"], self._gi["drop_f"],
-                             self._gi["drop_s"], self._gi["progress"], 1, True)
-        self._critic_impl(self._ci["real"], self._ci["fake"], self._ci["alpha"], True)
+                             self._gi["drop_s"], self._gi["progress"], 1, ga)
+        self._critic_impl(self._ci["real"], self._ci["fake"], self._ci["alpha"], ga)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     from . import ops as _ops
@@ -98,11 +103,11 @@ class Trainer:
     self._ggraph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(self._ggraph):
       self._gout = self._generator_impl(self._gi["img"], self._gi["states"], self._gi["noise"], self._gi["drop_f"],
-                                        self._gi["drop_s"], self._gi["progress"], 1, True)
+                                        self._gi["drop_s"], self._gi["progress"], 1, ga)
     l1 = _ops.launch_count
     self._cgraph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(self._cgraph):
-      self._cout = self._critic_impl(self._ci["real"], self._ci["fake"], self._ci["alpha"], True)
+      self._cout = self._critic_impl(self._ci["real"], self._ci["fake"], self._ci["alpha"], ga)
     self.graph_launches = {"generator": l1 - l0, "critic": _ops.launch_count - l1}   # own kernels per replay
     it = iter(snap)
     for s in (self.gen, self.val, self.cri):
@@ -130,6 +135,9 @@ class Trainer:
       gi["img"].copy_(fake_input); gi["states"].copy_(states); gi["noise"].copy_(noise)
       gi["drop_f"].copy_(drop_f); gi["drop_s"].copy_(drop_s); gi["progress"].fill_(float(progress))
       graph.replay()
+      if not self._graph_apply:
+        self._adam(self.gen, "g")
+        self._adam(self.val, "v")
       return self._gout
     prog = torch.full((1,), float(progress), device=self.device)
     return self._generator_impl(fake_input, states, noise, drop_f, drop_s, prog, is_train, apply)
@@ -167,6 +175,8 @@ class Trainer:
       ci = self._ci
       ci["real"].copy_(real); ci["fake"].copy_(fake); ci["alpha"].copy_(alpha)
       graph.replay()
+      if not self._graph_apply:
+        self._adam(self.cri, "c")
       return self._cout
     return self._critic_impl(real, fake, alpha, apply)
 

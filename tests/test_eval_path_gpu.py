@@ -26,17 +26,26 @@ def test_fused_chain_forward_matches_step_by_step_and_oracle(built_lib, shape):
     nxt[ids[s].cuda() < 0] = 0
     cur = nxt
   assert torch.equal(cur.cpu(), y)
-  # and the oracle, image by image
+  # and the oracle, image by image.  Five random filters in sequence amplify the per-step 1e-5
+  # differences (gamma up to x3, contrast's cancellation): the fp32 oracle itself is up to 2e-4
+  # away from the fp64 oracle here, so require the CUDA result to be about as close to fp64 as
+  # the fp32 restatement is (bit-equality with the validated single-step kernels is asserted above)
   for b in range(B):
-    ref = x[b:b + 1]
+    r32, r64 = x[b:b + 1], x[b:b + 1].double()
     for s in range(S):
       f = int(ids[s, b])
-      ref = torch.zeros_like(ref) if f < 0 else OF.process(f, ref, OF.regress(f, logits[s, b:b + 1, :OF.NUM_PARAMS[f]]))
-    # 5 random filters in sequence amplify the per-step 1e-5 differences (gamma up to x3, contrast's
-    # cancellation): bit-equality with the validated single-step kernels is asserted above; against
-    # the oracle require 99.9 % of the values within 1e-4 and all within 2e-2
-    rel = (y[b] - ref[0]).abs() / ref[0].abs().clamp_min(1e-3)
-    assert float((rel <= 1e-4).float().mean()) >= 0.999 and float(rel.max()) <= 2e-2, (b, float(rel.max()))
+      if f < 0:
+        r32, r64 = torch.zeros_like(r32), torch.zeros_like(r64)
+        continue
+      n = OF.NUM_PARAMS[f]
+      r32 = OF.process(f, r32, OF.regress(f, logits[s, b:b + 1, :n]))
+      r64 = OF.process(f, r64, OF.regress(f, logits[s, b:b + 1, :n].double()))
+    floor = r64.abs().clamp_min(1e-3)
+    e_cuda = (y[b].double() - r64[0]).abs()
+    e_ref = (r32[0].double() - r64[0]).abs()
+    ok = e_cuda <= 4 * e_ref + 5e-5 * floor[0]
+    assert float(ok.float().mean()) >= 0.999 and float((e_cuda / floor[0]).max()) <= 2e-2, \
+        (b, float(ok.float().mean()), float((e_cuda / floor[0]).max()))
 
 
 def test_retouch_high_resolution(built_lib):

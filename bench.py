@@ -41,9 +41,11 @@ def parse_args():
   ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=10)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
-  ap.add_argument("--workload", default="chain8", choices=["chain8", "train"])
+  ap.add_argument("--workload", default="chain8", choices=["chain8", "train", "eval"])
   ap.add_argument("--batch", type=int, default=64, help="images per GPU")
   ap.add_argument("--size", type=int, default=512)
+  ap.add_argument("--height", type=int, default=0, help="chain8: image height (default --size); 2160 for the 4K config")
+  ap.add_argument("--width", type=int, default=0, help="chain8: image width (default --size); 3840 for the 4K config")
   ap.add_argument("--variant", type=int, default=0, help="0 auto, 1 direct, 2 tma (exposure_b200.h)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-graphs", action="store_true", help="train workload: launch kernels eagerly instead of CUDA graphs")
@@ -148,10 +150,10 @@ def run_reference(args):
 def workload_config(args):
   return {
       "workload": "chain8: 8-filter chain E,G,W,S+,T,Ct,BW,C fwd+bwd (BASELINE.json configs[1])",
-      "batch_per_gpu": args.batch, "height": args.size, "width": args.size, "channels": 3,
+      "batch_per_gpu": args.batch, "height": args.height or args.size, "width": args.width or args.size, "channels": 3,
       "filters": "E,G,W,S+,T,Ct,BW,C", "parallelism": "dp%d (batch sharded by image, no data-path collective)" % args.gpus,
       "l2_policy": "working set (9 activations x %.0f MB + 2 gradient buffers) exceeds the 126 MB L2; no flush needed"
-                   % (args.batch * args.size * args.size * 12 / 1e6),
+                   % (args.batch * (args.height or args.size) * (args.width or args.size) * 12 / 1e6),
   }
 
 
@@ -234,18 +236,19 @@ def run_native(args):
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
   B, S = args.batch, args.size
+  H, W = args.height or S, args.width or S
 
   # synthetic linear-RGB batch, generated on the device for the resident leg
   g = torch.Generator(device=dev).manual_seed(1234 + rank)
   chain = FilterChain(CHAIN_IDS, variant=args.variant)
-  x0 = chain.input_buffer((B, S, S, 3), dev)
-  x0.copy_(torch.exp(torch.randn(B, S, S, 3, device=dev, generator=g) - 3.2).clamp_(0, 4))
-  stress = torch.rand(B, S, S, 3, device=dev, generator=g)
-  x0.copy_(torch.where(stress < 0.01, 1 + 3 * torch.rand(B, S, S, 3, device=dev, generator=g), x0))
+  x0 = chain.input_buffer((B, H, W, 3), dev)
+  x0.copy_(torch.exp(torch.randn(B, H, W, 3, device=dev, generator=g) - 3.2).clamp_(0, 4))
+  stress = torch.rand(B, H, W, 3, device=dev, generator=g)
+  x0.copy_(torch.where(stress < 0.01, 1 + 3 * torch.rand(B, H, W, 3, device=dev, generator=g), x0))
   del stress
   gl = torch.Generator().manual_seed(4321)
   logits = [torch.randn(B, ops.NUM_PARAMS[f], generator=gl).to(dev) for f in CHAIN_IDS]
-  gout = torch.randn(B, S, S, 3, device=dev, generator=g)
+  gout = torch.randn(B, H, W, 3, device=dev, generator=g)
 
   def step():
     chain.forward_resident(logits)
@@ -321,9 +324,9 @@ def run_native(args):
               "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
               "share_of_step": dom["avg_ms"] * dom["launches"] / eager_ms if eager_ms else None,
               "chain": {"achieved": tot_bytes / tot_ms / 1e6, "frac": tot_bytes / tot_ms / 1e6 / peak,
-                        "algorithmic_bytes_per_step": B * S * S * (FWD_B + BWD_B) * len(CHAIN_IDS),
+                        "algorithmic_bytes_per_step": B * H * W * (FWD_B + BWD_B) * len(CHAIN_IDS),
                         "kernel_ms_per_step": tot_ms / args.steps,
-                        "step_frac": B * S * S * (FWD_B + BWD_B) * len(CHAIN_IDS) / (elapsed_ms / args.steps) / 1e6 / peak},
+                        "step_frac": B * H * W * (FWD_B + BWD_B) * len(CHAIN_IDS) / (elapsed_ms / args.steps) / 1e6 / peak},
               "note": "kernel durations: CUDA events around every launch of the eager K-step loop; `value` and "
                       "chain.step_frac: the same K steps replayed from one CUDA graph" if graph_info else
                       "kernel durations: CUDA events around every launch inside the timed region",
@@ -331,9 +334,9 @@ def run_native(args):
               "kernels": kernels}
 
   # ---- end-to-end leg: host (pinned) buffers through the public API ------------------------
-  hx = torch.empty(B, S, S, 3, dtype=torch.float32).pin_memory()
+  hx = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
   hx.copy_(x0.cpu())
-  hy = torch.empty(B, S, S, 3, dtype=torch.float32).pin_memory()
+  hy = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
   hg = [torch.empty(B, ops.NUM_PARAMS[f]).pin_memory() for f in CHAIN_IDS]
   # public host-buffer API: H2D of the batch, chain fwd+bwd, D2H of the filtered batch (net.py:330
   # fetches fake_output every step) and of the parameter gradients, software-pipelined over 4
@@ -342,7 +345,7 @@ def run_native(args):
   n_chunks = 4 if B % 4 == 0 else 1
   del chain                                          # free the resident chain's activations first
   torch.cuda.empty_cache()
-  pipe = HostPipelinedChain(CHAIN_IDS, B, S, S, dev, chunks=n_chunks, variant=args.variant)
+  pipe = HostPipelinedChain(CHAIN_IDS, B, H, W, dev, chunks=n_chunks, variant=args.variant)
 
   def e2e_step():
     pipe.step(hx, logits, gout, hy, hg)
@@ -639,10 +642,63 @@ def cpu_baseline_train(B, budget_s=25.0):
                     "the reference TF graph (oracle/train_step.py, torch-CPU autograd), not TensorFlow" % (sb, B, len(times))}
 
 
+def run_eval(args):
+  """configs[2] (evaluate.py inference): cfg.test_steps policy steps on 64x64 thumbnails + the
+  selected filters applied to the (optionally high-resolution) batch by ONE fused kernel."""
+  import torch
+  from exposure_b200 import ops
+  from exposure_b200.evaluate import retouch
+  from exposure_b200.trainer import Trainer
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  B = args.batch
+  H, W = args.height or 64, args.width or 64
+  t = Trainer(device=dev, seed=0)
+  g = torch.Generator(device=dev).manual_seed(77)
+  hi = torch.exp(torch.randn(B, H, W, 3, device=dev, generator=g) - 3.2).clamp_(0, 4)
+  for _ in range(max(args.warmup, 3)):
+    retouch(t, hi, generator=g)
+  torch.cuda.synchronize()
+  ops.event_log = []
+  l0 = ops.launch_count
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    out = retouch(t, hi, generator=g)
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1)
+  log, ops.event_log = ops.event_log, None
+  fused = [(a.elapsed_time(b), nb) for name, nb, a, b in log if name.startswith("filter_chain_fwd")]
+  peak, peak_src = peaks()
+  fms = sum(x[0] for x in fused) / max(1, len(fused))
+  fbytes = fused[0][1] if fused else 0
+  S = int(out["ids"].shape[0])
+  print(json.dumps({
+      "metric": "images/sec", "value": B * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+      "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": {"workload": "eval: %d policy steps on 64x64 thumbnails + fused %d-step filter apply on the %dx%d batch "
+                             "(BASELINE.json configs[2]; net.py:796-820)" % (S, S, H, W),
+                 "batch_per_gpu": B, "height": H, "width": W, "policy_steps": S},
+      "gpu_launches": ops.launch_count - l0,
+      "roofline": {"bound": "hbm", "kernel": "filter_chain_fwd_kernel (all %d steps in one pass)" % S,
+                   "achieved": fbytes / fms / 1e6 if fms else None, "peak": peak, "unit": "GB/s",
+                   "frac": fbytes / fms / 1e6 / peak if fms else None, "traffic": None, "peak_source": peak_src,
+                   "avg_ms": fms, "algorithmic_bytes_per_launch": fbytes,
+                   "note": "24 B/pixel for the whole episode; the unfused schedule moves %d B/pixel" % (24 * S)},
+  }))
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
     run_reference(args)
+  elif args.workload == "eval":
+    run_eval(args)
   elif args.workload == "train":
     run_train(args)
   else:

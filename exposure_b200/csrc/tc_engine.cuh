@@ -104,7 +104,7 @@ __device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned cha
 // A_ROWFAST: consecutive lanes gather consecutive A rows (operands whose contiguous dimension is
 // M, e.g. wgrad) instead of the 8 chunks of one row.
 template <class P, int BN, bool A_ROWFAST = false>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const P p_in) {
+__global__ void __launch_bounds__(kThreads, (BN <= 64) ? 2 : 1) tc_gemm_kernel(const P p_in) {   // 2 CTAs/SM fit for BN <= 64
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   constexpr int kTileBBytes = BN * 128;

@@ -695,6 +695,12 @@ def run_eval(args):
 
 def main():
   args = parse_args()
+  # stdout must carry exactly ONE JSON line: native libraries write banners to fd 1 (NCCL prints
+  # "NCCL version ..." there), so fd 1 is pointed at stderr and Python's stdout keeps the real one
+  sys.stdout.flush()
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+  sys.stdout = os.fdopen(real_stdout, "w")
   if args.impl == "reference":
     run_reference(args)
   elif args.workload == "eval":

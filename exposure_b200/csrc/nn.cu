@@ -19,7 +19,7 @@ static int g_gemm_backend = kBackendAuto;
 int gemm_backend() { return g_gemm_backend; }
 // AUTO currently resolves to the CUDA-core engine; the tcgen05 engine is opt-in until every
 // primitive has a validated tensor-core instantiation.
-bool use_tcgen05() { return g_gemm_backend == kBackendTcgen05; }
+bool use_tcgen05() { return g_gemm_backend == kBackendTcgen05 || g_gemm_backend == kBackendTcgen05Ws; }
 
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
@@ -512,7 +512,8 @@ size_t exp_fc_workspace_bytes(int M, int K, int N) {
 }
 
 int exp_set_gemm_backend(int backend) {
-  EXP_CHECK_ARG(backend >= kBackendAuto && backend <= kBackendTcgen05, "backend must be 0 (auto), 1 (cuda cores) or 2 (tcgen05)");
+  EXP_CHECK_ARG(backend >= kBackendAuto && backend <= kBackendTcgen05Ws,
+                "backend must be 0 (auto), 1 (cuda cores), 2 (tcgen05) or 3 (tcgen05, warp-specialised)");
   g_gemm_backend = backend;
   return EXP_OK;
 }

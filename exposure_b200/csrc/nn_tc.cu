@@ -4,6 +4,7 @@
 // engine runs.  Both backends implement the same C-ABI entry points (include/exposure_b200.h).
 #include "nn_tc.h"
 #include "tc_engine.cuh"
+#include "tc_engine_ws.cuh"
 
 namespace expo {
 
@@ -330,12 +331,19 @@ struct TcFcWgrad {
 
 static int host_ilog2_tc(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-template <class P>
-static cudaError_t launch_by_bn(const P& p, int M, int N, int Z, cudaStream_t st) {
-  if (N <= 32) return tc::launch_tc_gemm<P, 32>(p, M, N, Z, st);
-  if (N <= 64) return tc::launch_tc_gemm<P, 64>(p, M, N, Z, st);
-  if (N <= 128) return tc::launch_tc_gemm<P, 128>(p, M, N, Z, st);
-  return tc::launch_tc_gemm<P, 256>(p, M, N, Z, st);
+// Picks the N tile and the engine generation: backend 3 = warp-specialised engine (BN <= 128),
+// backend 2 = first-generation engine (BN up to 256).
+template <class P, bool ROWFAST = false, int MAXBN = 256>
+static cudaError_t launch_auto(const P& p, int M, int N, int Z, cudaStream_t st) {
+  if (gemm_backend() == kBackendTcgen05Ws) {
+    if (N <= 32) return tc::launch_tc_gemm_ws<P, 32, ROWFAST>(p, M, N, Z, st);
+    if (N <= 64) return tc::launch_tc_gemm_ws<P, 64, ROWFAST>(p, M, N, Z, st);
+    return tc::launch_tc_gemm_ws<P, 128, ROWFAST>(p, M, N, Z, st);
+  }
+  if (N <= 32) return tc::launch_tc_gemm<P, 32, ROWFAST>(p, M, N, Z, st);
+  if (N <= 64) return tc::launch_tc_gemm<P, 64, ROWFAST>(p, M, N, Z, st);
+  if (N <= 128 || MAXBN < 256) return tc::launch_tc_gemm<P, 128, ROWFAST>(p, M, N, Z, st);
+  return tc::launch_tc_gemm<P, 256, ROWFAST>(p, M, N, Z, st);
 }
 
 bool tc_conv_fwd_supported(int Cout) { return Cout >= 16 && Cout <= 1024; }
@@ -350,13 +358,13 @@ cudaError_t tc_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float 
     p.x = x; p.vec = vec; p.W = W; p.bias = bias; p.mask_ref = mask_ref; p.post_mul = post_mul; p.y = y; p.y2 = y2;
     p.B = B; p.IH = IH; p.IW = IW; p.Cx = Cx; p.Cv = Cv; p.Cin = Cx + Cv; p.Cout = Cout; p.OH = OH; p.OW = OW;
     p.Ktot = 16 * p.Cin; p.mode = mode; p.shift = shift; p.lgOW = host_ilog2_tc(OW); p.lgOHW = host_ilog2_tc(OH * OW);
-    return launch_by_bn(p, M, Cout, 1, st);
+    return launch_auto(p, M, Cout, 1, st);
   }
   TcConvFprop<false> p{};
   p.x = x; p.vec = vec; p.W = W; p.bias = bias; p.mask_ref = mask_ref; p.post_mul = post_mul; p.y = y; p.y2 = y2;
   p.B = B; p.IH = IH; p.IW = IW; p.Cx = Cx; p.Cv = Cv; p.Cin = Cx + Cv; p.Cout = Cout; p.OH = OH; p.OW = OW;
   p.Ktot = 16 * p.Cin; p.mode = mode; p.shift = shift; p.lgOW = host_ilog2_tc(OW); p.lgOHW = host_ilog2_tc(OH * OW);
-  return launch_by_bn(p, M, Cout, 1, st);
+  return launch_auto(p, M, Cout, 1, st);
 }
 
 bool tc_conv_dgrad_supported(int Cout) { return Cout % 32 == 0; }
@@ -367,7 +375,7 @@ cudaError_t tc_conv_dgrad(const float* dy, const float* W, const float* a_in, fl
   p.dy = dy; p.W = W; p.a_in = a_in; p.dx = dx; p.B = B; p.IH = IH; p.IW = IW; p.Cin = Cin; p.OH = IH / 2; p.OW = IW / 2;
   p.Cout = Cout; p.lgW2 = host_ilog2_tc(IW / 2); p.lgHW2 = host_ilog2_tc((IH / 2) * (IW / 2));
   const int M = B * (IH / 2) * (IW / 2);
-  return launch_by_bn(p, M, Cin, 4, st);
+  return launch_auto(p, M, Cin, 4, st);
 }
 
 int tc_wgrad_splits(int B, int OH, int OW, int Cin, int Cout) {
@@ -391,10 +399,7 @@ cudaError_t tc_conv_wgrad_partials(const float* x, int Cx, const float* vec, int
   pps = ((pps + tc::kBK - 1) / tc::kBK) * tc::kBK;
   p.pix_per_split = pps;
   const int M = 16 * p.Cin;
-  if (Cout <= 32) return tc::launch_tc_gemm<TcConvWgrad, 32, true>(p, M, Cout, splits, st);
-  if (Cout <= 64) return tc::launch_tc_gemm<TcConvWgrad, 64, true>(p, M, Cout, splits, st);
-  if (Cout <= 128) return tc::launch_tc_gemm<TcConvWgrad, 128, true>(p, M, Cout, splits, st);
-  return tc::launch_tc_gemm<TcConvWgrad, 256, true>(p, M, Cout, splits, st);
+  return launch_auto<TcConvWgrad, true>(p, M, Cout, splits, st);
 }
 
 cudaError_t tc_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act, const float* mul_plain, int ldmul,
@@ -402,18 +407,14 @@ cudaError_t tc_fc_dgrad(const float* dy, int ldy, const float* W, const float* m
   TcFcDgrad p{};
   p.dy = dy; p.W = W; p.mul_act = mul_act; p.mul_plain = mul_plain; p.dx = dx; p.M = M; p.K = K; p.N = N;
   p.ldy = ldy; p.lddx = lddx; p.ldmul = ldmul; p.accumulate = accumulate;
-  if (K <= 32) return tc::launch_tc_gemm<TcFcDgrad, 32>(p, M, K, 1, st);
-  if (K <= 64) return tc::launch_tc_gemm<TcFcDgrad, 64>(p, M, K, 1, st);
-  return tc::launch_tc_gemm<TcFcDgrad, 128>(p, M, K, 1, st);
+  return launch_auto<TcFcDgrad, false, 128>(p, M, K, 1, st);
 }
 
 cudaError_t tc_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, int M, int K, int N, int accumulate,
                         cudaStream_t st) {
   TcFcWgrad p{};
   p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N; p.ldx = ldx; p.ldy = ldy; p.accumulate = accumulate;
-  if (N <= 32) return tc::launch_tc_gemm<TcFcWgrad, 32, true>(p, K, N, 1, st);
-  if (N <= 64) return tc::launch_tc_gemm<TcFcWgrad, 64, true>(p, K, N, 1, st);
-  return tc::launch_tc_gemm<TcFcWgrad, 128, true>(p, K, N, 1, st);
+  return launch_auto<TcFcWgrad, true, 128>(p, K, N, 1, st);
 }
 
 int tc_fc_splits(int M, int K, int N) {
@@ -432,9 +433,7 @@ cudaError_t tc_fc_fwd_partials(const float* x, int ldx, const float* W, float* p
   int kps = (K + splits - 1) / splits;
   kps = ((kps + tc::kBK - 1) / tc::kBK) * tc::kBK;
   p.k_per_split = kps;
-  if (N <= 32) return tc::launch_tc_gemm<TcFcFwd, 32>(p, M, N, splits, st);
-  if (N <= 64) return tc::launch_tc_gemm<TcFcFwd, 64>(p, M, N, splits, st);
-  return tc::launch_tc_gemm<TcFcFwd, 128>(p, M, N, splits, st);
+  return launch_auto<TcFcFwd, false, 128>(p, M, N, splits, st);
 }
 
 }  // namespace expo

@@ -5,7 +5,7 @@
 
 namespace expo {
 
-enum { kBackendAuto = 0, kBackendSimt = 1, kBackendTcgen05 = 2 };
+enum { kBackendAuto = 0, kBackendSimt = 1, kBackendTcgen05 = 2, kBackendTcgen05Ws = 3 };
 int gemm_backend();          // current setting (exp_set_gemm_backend)
 bool use_tcgen05();          // resolves AUTO
 

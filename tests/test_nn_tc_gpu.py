@@ -10,11 +10,12 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 TOL = 2e-5
 
 
-@pytest.fixture()
-def nn(built_lib):
+@pytest.fixture(params=[2, 3], ids=["tcgen05", "tcgen05-warp-specialised"])
+def nn(built_lib, request):
   assert torch.cuda.is_available()
   from exposure_b200 import nn_ops
-  nn_ops.set_gemm_backend(nn_ops.BACKEND_TCGEN05)
+  nn_ops.BACKEND_UNDER_TEST = request.param
+  nn_ops.set_gemm_backend(request.param)
   yield nn_ops
   nn_ops.set_gemm_backend(nn_ops.BACKEND_AUTO)
 
@@ -48,7 +49,7 @@ def test_tc_conv_forward_and_tangent(nn, case):
   _close(yd, y)
   nn.set_gemm_backend(nn.BACKEND_CUDA_CORES)
   ys = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=shift)
-  nn.set_gemm_backend(nn.BACKEND_TCGEN05)
+  nn.set_gemm_backend(nn.BACKEND_UNDER_TEST)
   _close(yd, ys.double().cpu(), tol=3e-5)    # two different fp32 summation orders over K up to 2048
   pm = (torch.rand(y.shape, generator=torch.Generator().manual_seed(9)) < 0.5).float() * 2
   y1, y2 = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=shift, post_mul=pm.cuda())
@@ -75,3 +76,25 @@ def test_tc_fc_forward(nn, case):
   big = torch.zeros(M, 2 * K)
   big[:, K:] = x.float()
   _close(nn.fc_fwd(big.cuda()[:, K:], f32(W), f32(b), mode=nn.FC_LINEAR), pre)
+
+
+def test_tc_backward_primitives(nn):
+  """conv dgrad / wgrad and FC dgrad / wgrad on the tensor-core engines vs the fp64 oracle."""
+  B, IH, Cin, Cout = 3, 16, 64, 128
+  x = _rand(B, IH, IH, Cin, seed=1) * 0.3
+  W = _rand(4, 4, Cin, Cout, seed=2, scale=0.05).requires_grad_(True)
+  xin = x.clone().requires_grad_(True)
+  y = N.conv4x4s2(xin, W)
+  gy = _rand(*y.shape, seed=3)
+  gin, gW = torch.autograd.grad(y, [xin, W], grad_outputs=gy)
+  f32 = lambda t: t.detach().float().cuda().contiguous()
+  _close(nn.conv_dgrad(f32(gy), f32(W), (B, IH, IH, Cin)), gin)
+  _close(nn.conv_wgrad(f32(x), f32(gy)), gW)
+  M, K, Nn = 96, 4096, 128
+  a = _rand(M, K, seed=4).requires_grad_(True)
+  Wf = _rand(K, Nn, seed=5, scale=K ** -0.5).requires_grad_(True)
+  out = a @ Wf
+  go = _rand(M, Nn, seed=6)
+  ga, gWf = torch.autograd.grad(out, [a, Wf], grad_outputs=go)
+  _close(nn.fc_dgrad(f32(go), f32(Wf)), ga)
+  _close(nn.fc_wgrad(f32(a), f32(go)), gWf)

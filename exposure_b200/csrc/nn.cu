@@ -424,7 +424,10 @@ int exp_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, 
     return EXP_OK;
   }
   if (Cv == 0 && Cx % kBK4 == 0 && Cout % 4 == 0 && aligned16(x) && aligned16(W)) {   // 16-byte gathers
-    if (Cout <= 32) launch_gemm_v4<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
+    // the deep layers have few output rows: prefer the narrow N tile while the 64-wide grid
+    // would leave SMs idle (2 x 148 CTAs), A is simply re-gathered from L2 per N tile
+    const bool narrow = Cout <= 32 || ((M + kBM - 1) / kBM) * ((Cout + 63) / 64) < 296;
+    if (narrow) launch_gemm_v4<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
     else launch_gemm_v4<ConvFprop, 64, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
   } else if (Cout <= 32) launch_gemm<ConvFprop, 32, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
   else launch_gemm<ConvFprop, 64, false, false>(p, M, Cout, 1, (cudaStream_t)stream);
@@ -449,7 +452,8 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
     return EXP_OK;
   }
   if (Cout % kBK4 == 0 && aligned16(dy) && aligned16(W)) {                             // 16-byte gathers
-    if (Cin <= 32) launch_gemm_v4<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
+    const bool narrow = Cin <= 32 || 4 * ((M + kBM - 1) / kBM) * ((Cin + 63) / 64) < 296;
+    if (narrow) launch_gemm_v4<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
     else launch_gemm_v4<ConvDgrad, 64, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
   } else if (Cin <= 32) launch_gemm<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
   else launch_gemm<ConvDgrad, 64, false, true>(p, M, Cin, 4, (cudaStream_t)stream);

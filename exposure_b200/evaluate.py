@@ -52,3 +52,51 @@ def retouch(trainer, high_res, generator=None, steps=None, fused=True):
       p = ops.filter_regress_fwd(logits[s], ids[s])
       out = ops.filter_fwd(out, p, ids[s])
   return dict(output=out, ids=ids, logits=logits, thumbnails=thumb, states=states)
+
+
+# ---- image I/O around the hot path (net.py:731-747, 825-877; util.py:311-323, 495-501) --------
+def load_linear_image(path):
+  """Reads a tif/tiff (ProPhoto RGB, linearised with x^1.8 like util.linearize_ProPhotoRGB) or a
+  jpg/png (sRGB: x^2.2 then / (2 max), net.py:739-747) into a float32 HxWx3 RGB array."""
+  import cv2
+  import numpy as np
+  img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+  if img is None:
+    raise IOError("cannot read %s" % path)
+  if img.ndim == 2:
+    img = np.stack([img] * 3, axis=2)
+  img = img[:, :, :3][:, :, ::-1]
+  depth = 16 if img.dtype == np.uint16 else 8
+  img = img.astype(np.float32) * (1.0 / (2 ** depth - 1))          # util.read_tiff16
+  if path.lower().endswith((".tif", ".tiff")):
+    return np.power(img, 1.8).astype(np.float32)
+  lin = np.power(img, 2.2)
+  return (lin / (2 * lin.max())).astype(np.float32)
+
+
+def save_png(path, img):
+  """net.py:771-774 show_and_save: RGB float [0,1] -> 8-bit PNG."""
+  import cv2
+  import numpy as np
+  cv2.imwrite(path, np.clip(img[:, :, ::-1] * 255.0, 0, 255).astype(np.uint8))
+
+
+def evaluate_files(trainer, files, output_dir="./outputs", generator=None):
+  """GAN.eval (net.py:711-877) on a list of image files: images of equal resolution are retouched
+  as one batch.  Writes <name>.retouched.png; returns {file: (ids per step)}."""
+  import os
+  import numpy as np
+  os.makedirs(output_dir, exist_ok=True)
+  groups = {}
+  for fn in files:
+    im = load_linear_image(fn)
+    groups.setdefault(im.shape[:2], []).append((fn, im))
+  result = {}
+  for res, items in groups.items():
+    batch = torch.from_numpy(np.stack([im for _, im in items])).to(trainer.device)
+    out = retouch(trainer, batch, generator=generator)
+    o = out["output"].cpu().numpy()
+    for k, (fn, _) in enumerate(items):
+      save_png(os.path.join(output_dir, os.path.basename(fn) + ".retouched.png"), o[k])
+      result[fn] = out["ids"][:, k].tolist()
+  return result

@@ -20,6 +20,7 @@ int gemm_backend() { return g_gemm_backend; }
 // AUTO currently resolves to the CUDA-core engine; the tcgen05 engine is opt-in until every
 // primitive has a validated tensor-core instantiation.
 bool use_tcgen05() { return g_gemm_backend == kBackendTcgen05 || g_gemm_backend == kBackendTcgen05Ws; }
+bool use_tma() { return g_gemm_backend == kBackendTcgen05Tma; }
 
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
@@ -416,6 +417,11 @@ int exp_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, 
   p.chunks = (p.Cin + kBK - 1) / kBK; p.mode = mode; p.shift = shift;
   p.lgOW = host_ilog2(p.OW); p.lgOHW = host_ilog2(p.OH * p.OW);
   const int M = B * p.OH * p.OW;
+  if (use_tma() && tma_conv_fwd_supported(x, Cx, Cv, shift, W, bias, mask_ref, post_mul, y, y2, Cout)) {
+    const cudaError_t e = tma_conv_fwd(x, Cx, W, bias, mask_ref, post_mul, y, y2, B, IH, IW, Cout, mode, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_fwd[tma]: %s", cudaGetErrorString(e));
+    return EXP_OK;
+  }
   if (use_tcgen05() && tc_conv_fwd_supported(Cout)) {
     const cudaError_t e = tc_conv_fwd(x, Cx, vec, Cv, shift, W, bias, mask_ref, post_mul, y, y2, B, IH, IW, Cout, mode,
                                       (cudaStream_t)stream);
@@ -445,6 +451,11 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
   p.OW = IW / 2; p.Cout = Cout; p.chunks = Cout / kBK;
   p.lgW2 = host_ilog2(IW / 2); p.lgHW2 = host_ilog2((IH / 2) * (IW / 2));
   const int M = B * (IH / 2) * (IW / 2);
+  if (use_tma() && tma_conv_dgrad_supported(dy, W, a_in, dx, Cin, Cout)) {
+    const cudaError_t e = tma_conv_dgrad(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[tma]: %s", cudaGetErrorString(e));
+    return EXP_OK;
+  }
   if (use_tcgen05() && tc_conv_dgrad_supported(Cout) && aligned16(dy) && aligned16(W)) {
     const cudaError_t e = tc_conv_dgrad(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[tcgen05]: %s", cudaGetErrorString(e));
@@ -464,7 +475,9 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
 size_t exp_conv_wgrad_workspace_bytes(int B, int IH, int IW, int Cin, int Cout) {
   if (B <= 0 || IH < 2 || IW < 2 || Cin <= 0 || Cout <= 0) return 0;
   const int a = wgrad_splits(B, IH / 2, IW / 2, Cin, Cout), b = tc_wgrad_splits(B, IH / 2, IW / 2, Cin, Cout);
-  return (size_t)(a > b ? a : b) * 16 * Cin * Cout * sizeof(float);
+  const int c = tma_wgrad_splits(B, IH / 2, IW / 2, Cin, Cout);
+  const int m = a > b ? (a > c ? a : c) : (b > c ? b : c);
+  return (size_t)m * 16 * Cin * Cout * sizeof(float);
 }
 
 int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift, const float* dy, float* gW, int B,
@@ -474,9 +487,21 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
   EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cout > 0, "bad channel counts");
   const int Cin = Cx + Cv, OH = IH / 2, OW = IW / 2;
   const bool tcg = use_tcgen05();
-  const int splits = tcg ? tc_wgrad_splits(B, OH, OW, Cin, Cout) : wgrad_splits(B, OH, OW, Cin, Cout);
+  const bool tmab = use_tma() && tma_conv_wgrad_supported(x, Cx, Cv, shift, dy, Cout) && aligned16(workspace);
+  const int splits = tmab ? tma_wgrad_splits(B, OH, OW, Cin, Cout)
+                          : (tcg ? tc_wgrad_splits(B, OH, OW, Cin, Cout) : wgrad_splits(B, OH, OW, Cin, Cout));
   const size_t need = (size_t)splits * 16 * Cin * Cout * sizeof(float);
   if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  if (tmab) {
+    const cudaError_t e = tma_conv_wgrad_partials(x, Cx, dy, reinterpret_cast<float*>(workspace), B, IH, IW, Cout, splits,
+                                                  (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_wgrad[tma]: %s", cudaGetErrorString(e));
+    const size_t cnt = (size_t)16 * Cin * Cout;
+    splitk_reduce_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float*>(workspace), splits, cnt, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
+    EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
+    return EXP_OK;
+  }
   if (tcg) {
     const cudaError_t e = tc_conv_wgrad_partials(x, Cx, vec, Cv, shift, dy, reinterpret_cast<float*>(workspace), B, IH, IW,
                                                  Cout, splits, (cudaStream_t)stream);
@@ -516,8 +541,8 @@ size_t exp_fc_workspace_bytes(int M, int K, int N) {
 }
 
 int exp_set_gemm_backend(int backend) {
-  EXP_CHECK_ARG(backend >= kBackendAuto && backend <= kBackendTcgen05Ws,
-                "backend must be 0 (auto), 1 (cuda cores), 2 (tcgen05) or 3 (tcgen05, warp-specialised)");
+  EXP_CHECK_ARG(backend >= kBackendAuto && backend <= kBackendTcgen05Tma,
+                "backend must be 0 (auto), 1 (cuda cores), 2 (tcgen05), 3 (tcgen05, warp-specialised) or 4 (tcgen05, TMA-fed)");
   g_gemm_backend = backend;
   return EXP_OK;
 }

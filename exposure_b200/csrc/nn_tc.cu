@@ -8,17 +8,6 @@
 
 namespace expo {
 
-// 4 consecutive floats p[0..3] of which the first `valid` exist (16-byte load when possible)
-__device__ __forceinline__ float4 ld4_guarded(const float* p, int valid) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (valid >= 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) return __ldg(reinterpret_cast<const float4*>(p));
-  if (valid > 0) v.x = __ldg(p);
-  if (valid > 1) v.y = __ldg(p + 1);
-  if (valid > 2) v.z = __ldg(p + 2);
-  if (valid > 3) v.w = __ldg(p + 3);
-  return v;
-}
-
 __device__ __forceinline__ float tc_lrelu(float v) { return 0.6f * v + 0.4f * fabsf(v); }
 __device__ __forceinline__ float tc_dlrelu(float a) { return a > 0.f ? 1.0f : (a < 0.f ? 0.2f : 0.6f); }
 
@@ -78,12 +67,6 @@ struct TcConvFprop {
     if (k + 3 < Ktot) v.w = __ldg(W + (size_t)(k + 3) * Cout + n);
     return v;
   }
-  // MN-major B: W[k][n..n+3] is contiguous (HWIO weights) -> one 16-byte load
-  __device__ float4 load_b_mn4(const KS& s, int kk, int n) const {
-    const int k = s.k0 + kk;
-    if (k >= Ktot || n >= Cout) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return ld4_guarded(W + (size_t)k * Cout + n, Cout - n);
-  }
   __device__ void store16(int m, int n0, const float (&v)[16]) const {
     if (m >= B * OH * OW) return;
 #pragma unroll
@@ -133,11 +116,6 @@ struct TcFcFwd {
     if (k + 2 < K) v.z = __ldg(W + (size_t)(k + 2) * N + n);
     if (k + 3 < K) v.w = __ldg(W + (size_t)(k + 3) * N + n);
     return v;
-  }
-  __device__ float4 load_b_mn4(const KS& s, int kk, int n) const {      // W[k][n..n+3]
-    const int k = s.k0 + kk;
-    if (k >= K || k >= k_begin + k_per_split || n >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return ld4_guarded(W + (size_t)k * N + n, N - n);
   }
   __device__ void store16(int m, int n0, const float (&v)[16]) const {
     if (m >= M) return;
@@ -254,34 +232,6 @@ struct TcConvWgrad {
     if (p + 3 < P) v.w = __ldg(dy + (size_t)(p + 3) * Cout + n);
     return v;
   }
-  // MN-major operands: A rows (tap, ci..ci+3) of one pixel are contiguous in the NHWC input when
-  // Cin % 4 == 0 and there is no per-image vector; B = delta[p][n..n+3] is always contiguous
-  __device__ float4 load_a_mn4(const KS& s, int kk, int m) const {
-    const int p = s.p0 + kk;
-    if (m >= 16 * Cin || p >= B * OH * OW) return make_float4(0.f, 0.f, 0.f, 0.f);
-    if (Cv == 0 && (Cx & 3) == 0) {
-      const int tap = m / Cin, ci = m - tap * Cin;
-      const int b = p >> lgOHW;
-      const int rem = p & ((1 << lgOHW) - 1);
-      const int iy = 2 * (rem >> lgOW) - 1 + (tap >> 2), ix = 2 * (rem & (OW - 1)) - 1 + (tap & 3);
-      if ((unsigned)iy >= (unsigned)IH || (unsigned)ix >= (unsigned)IW) return make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 v = ld4_guarded(x + ((size_t)(b * IH + iy) * IW + ix) * Cx + ci, 4);
-      v.x -= shift; v.y -= shift; v.z -= shift; v.w -= shift;
-      return v;
-    }
-    float4 v;                       // layer 1 (Cin = 14 / 6 / 17): element-wise
-    const int R = 16 * Cin;
-    v.x = a_elem(row_a(m), p);
-    v.y = m + 1 < R ? a_elem(row_a(m + 1), p) : 0.f;
-    v.z = m + 2 < R ? a_elem(row_a(m + 2), p) : 0.f;
-    v.w = m + 3 < R ? a_elem(row_a(m + 3), p) : 0.f;
-    return v;
-  }
-  __device__ float4 load_b_mn4(const KS& s, int kk, int n) const {
-    const int p = s.p0 + kk;
-    if (p >= B * OH * OW || n >= Cout) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return ld4_guarded(dy + (size_t)p * Cout + n, Cout - n);
-  }
   __device__ void store16(int m, int n0, const float (&v)[16]) const {
     if (m >= 16 * Cin) return;
 #pragma unroll
@@ -304,13 +254,23 @@ struct TcFcDgrad {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r.m < 0) return v;
     const int n = s.n0 + 4 * c;
-    return n < N ? ld4_guarded(dy + (size_t)r.m * ldy + n, N - n) : v;
+    const float* p = dy + (size_t)r.m * ldy + n;
+    if (n + 0 < N) v.x = __ldg(p + 0);
+    if (n + 1 < N) v.y = __ldg(p + 1);
+    if (n + 2 < N) v.z = __ldg(p + 2);
+    if (n + 3 < N) v.w = __ldg(p + 3);
+    return v;
   }
   __device__ float4 load_b4(const KS& s, int col, int c) const {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col >= K) return v;
     const int n = s.n0 + 4 * c;
-    return n < N ? ld4_guarded(W + (size_t)col * N + n, N - n) : v;
+    const float* p = W + (size_t)col * N + n;
+    if (n + 0 < N) v.x = __ldg(p + 0);
+    if (n + 1 < N) v.y = __ldg(p + 1);
+    if (n + 2 < N) v.z = __ldg(p + 2);
+    if (n + 3 < N) v.w = __ldg(p + 3);
+    return v;
   }
   __device__ void store16(int m, int k0, const float (&v)[16]) const {
     if (m >= M) return;
@@ -358,17 +318,6 @@ struct TcFcWgrad {
     if (sm + 3 < M) v.w = __ldg(dy + (size_t)(sm + 3) * ldy + n);
     return v;
   }
-  // MN-major: x[sample][k..k+3] and dy[sample][n..n+3] are contiguous
-  __device__ float4 load_a_mn4(const KS& s, int kk, int m) const {
-    const int sm = s.s0 + kk;
-    if (sm >= M || m >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return ld4_guarded(x + (size_t)sm * ldx + m, K - m);
-  }
-  __device__ float4 load_b_mn4(const KS& s, int kk, int n) const {
-    const int sm = s.s0 + kk;
-    if (sm >= M || n >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return ld4_guarded(dy + (size_t)sm * ldy + n, N - n);
-  }
   __device__ void store16(int k, int n0, const float (&v)[16]) const {
     if (k >= K) return;
 #pragma unroll
@@ -382,17 +331,15 @@ struct TcFcWgrad {
 
 static int host_ilog2_tc(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-// Picks the N tile and the engine generation: backend 3 = warp-specialised engine (BN <= 128,
-// operands staged K-major or MN-major as given), backend 2 = first-generation engine (K-major
-// tiles only, BN up to 256; ROWFAST = its row-fast gather mapping for M-contiguous operands).
-template <class P, bool A_MN, bool B_MN, int MAXBN = 256>
+// Picks the N tile and the engine generation: backend 3 = warp-specialised engine (BN <= 128),
+// backend 2 = first-generation engine (BN up to 256).
+template <class P, bool ROWFAST = false, int MAXBN = 256>
 static cudaError_t launch_auto(const P& p, int M, int N, int Z, cudaStream_t st) {
   if (gemm_backend() == kBackendTcgen05Ws) {
-    if (N <= 32) return tc::launch_tc_gemm_ws<P, 32, A_MN, B_MN>(p, M, N, Z, st);
-    if (N <= 64) return tc::launch_tc_gemm_ws<P, 64, A_MN, B_MN>(p, M, N, Z, st);
-    return tc::launch_tc_gemm_ws<P, 128, A_MN, B_MN>(p, M, N, Z, st);
+    if (N <= 32) return tc::launch_tc_gemm_ws<P, 32, ROWFAST>(p, M, N, Z, st);
+    if (N <= 64) return tc::launch_tc_gemm_ws<P, 64, ROWFAST>(p, M, N, Z, st);
+    return tc::launch_tc_gemm_ws<P, 128, ROWFAST>(p, M, N, Z, st);
   }
-  constexpr bool ROWFAST = A_MN;
   if (N <= 32) return tc::launch_tc_gemm<P, 32, ROWFAST>(p, M, N, Z, st);
   if (N <= 64) return tc::launch_tc_gemm<P, 64, ROWFAST>(p, M, N, Z, st);
   if (N <= 128 || MAXBN < 256) return tc::launch_tc_gemm<P, 128, ROWFAST>(p, M, N, Z, st);
@@ -411,13 +358,13 @@ cudaError_t tc_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float 
     p.x = x; p.vec = vec; p.W = W; p.bias = bias; p.mask_ref = mask_ref; p.post_mul = post_mul; p.y = y; p.y2 = y2;
     p.B = B; p.IH = IH; p.IW = IW; p.Cx = Cx; p.Cv = Cv; p.Cin = Cx + Cv; p.Cout = Cout; p.OH = OH; p.OW = OW;
     p.Ktot = 16 * p.Cin; p.mode = mode; p.shift = shift; p.lgOW = host_ilog2_tc(OW); p.lgOHW = host_ilog2_tc(OH * OW);
-    return launch_auto<decltype(p), false, true>(p, M, Cout, 1, st);
+    return launch_auto(p, M, Cout, 1, st);
   }
   TcConvFprop<false> p{};
   p.x = x; p.vec = vec; p.W = W; p.bias = bias; p.mask_ref = mask_ref; p.post_mul = post_mul; p.y = y; p.y2 = y2;
   p.B = B; p.IH = IH; p.IW = IW; p.Cx = Cx; p.Cv = Cv; p.Cin = Cx + Cv; p.Cout = Cout; p.OH = OH; p.OW = OW;
   p.Ktot = 16 * p.Cin; p.mode = mode; p.shift = shift; p.lgOW = host_ilog2_tc(OW); p.lgOHW = host_ilog2_tc(OH * OW);
-  return launch_auto<decltype(p), false, true>(p, M, Cout, 1, st);
+  return launch_auto(p, M, Cout, 1, st);
 }
 
 bool tc_conv_dgrad_supported(int Cout) { return Cout % 32 == 0; }
@@ -428,7 +375,7 @@ cudaError_t tc_conv_dgrad(const float* dy, const float* W, const float* a_in, fl
   p.dy = dy; p.W = W; p.a_in = a_in; p.dx = dx; p.B = B; p.IH = IH; p.IW = IW; p.Cin = Cin; p.OH = IH / 2; p.OW = IW / 2;
   p.Cout = Cout; p.lgW2 = host_ilog2_tc(IW / 2); p.lgHW2 = host_ilog2_tc((IH / 2) * (IW / 2));
   const int M = B * (IH / 2) * (IW / 2);
-  return launch_auto<TcConvDgrad, false, false>(p, M, Cin, 4, st);
+  return launch_auto(p, M, Cin, 4, st);
 }
 
 int tc_wgrad_splits(int B, int OH, int OW, int Cin, int Cout) {
@@ -452,7 +399,7 @@ cudaError_t tc_conv_wgrad_partials(const float* x, int Cx, const float* vec, int
   pps = ((pps + tc::kBK - 1) / tc::kBK) * tc::kBK;
   p.pix_per_split = pps;
   const int M = 16 * p.Cin;
-  return launch_auto<TcConvWgrad, true, true>(p, M, Cout, splits, st);
+  return launch_auto<TcConvWgrad, true>(p, M, Cout, splits, st);
 }
 
 cudaError_t tc_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act, const float* mul_plain, int ldmul,
@@ -460,14 +407,14 @@ cudaError_t tc_fc_dgrad(const float* dy, int ldy, const float* W, const float* m
   TcFcDgrad p{};
   p.dy = dy; p.W = W; p.mul_act = mul_act; p.mul_plain = mul_plain; p.dx = dx; p.M = M; p.K = K; p.N = N;
   p.ldy = ldy; p.lddx = lddx; p.ldmul = ldmul; p.accumulate = accumulate;
-  return launch_auto<TcFcDgrad, false, false, 128>(p, M, K, 1, st);
+  return launch_auto<TcFcDgrad, false, 128>(p, M, K, 1, st);
 }
 
 cudaError_t tc_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, int M, int K, int N, int accumulate,
                         cudaStream_t st) {
   TcFcWgrad p{};
   p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N; p.ldx = ldx; p.ldy = ldy; p.accumulate = accumulate;
-  return launch_auto<TcFcWgrad, true, true, 128>(p, K, N, 1, st);
+  return launch_auto<TcFcWgrad, true, 128>(p, K, N, 1, st);
 }
 
 int tc_fc_splits(int M, int K, int N) {
@@ -486,7 +433,7 @@ cudaError_t tc_fc_fwd_partials(const float* x, int ldx, const float* W, float* p
   int kps = (K + splits - 1) / splits;
   kps = ((kps + tc::kBK - 1) / tc::kBK) * tc::kBK;
   p.k_per_split = kps;
-  return launch_auto<TcFcFwd, false, true, 128>(p, M, N, splits, st);
+  return launch_auto<TcFcFwd, false, 128>(p, M, N, splits, st);
 }
 
 }  // namespace expo

@@ -5,9 +5,10 @@
 
 namespace expo {
 
-enum { kBackendAuto = 0, kBackendSimt = 1, kBackendTcgen05 = 2, kBackendTcgen05Ws = 3 };
+enum { kBackendAuto = 0, kBackendSimt = 1, kBackendTcgen05 = 2, kBackendTcgen05Ws = 3, kBackendTcgen05Tma = 4 };
 int gemm_backend();          // current setting (exp_set_gemm_backend)
-bool use_tcgen05();          // resolves AUTO
+bool use_tcgen05();          // register-gather tcgen05 engines (backends 2, 3)
+bool use_tma();              // TMA-fed tcgen05 engine where the shape allows it (backend 4)
 
 bool tc_conv_fwd_supported(int Cout);
 cudaError_t tc_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, const float* W,
@@ -30,4 +31,21 @@ cudaError_t tc_fc_dgrad(const float* dy, int ldy, const float* W, const float* m
                         float* dx, int lddx, int M, int K, int N, int accumulate, cudaStream_t st);
 cudaError_t tc_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, int M, int K, int N, int accumulate,
                         cudaStream_t st);
+}  // namespace expo
+
+// nn_tma.cu: TMA-fed tcgen05 engine (backend 4); *_supported() decide per call, callers fall back
+// to the CUDA-core engine for the shapes it does not take (first layer: Cin not a multiple of 32)
+namespace expo {
+bool tma_conv_fwd_supported(const float* x, int Cx, int Cv, float shift, const float* W, const float* bias,
+                            const float* mask_ref, const float* post_mul, const float* y, const float* y2, int Cout);
+cudaError_t tma_conv_fwd(const float* x, int Cx, const float* W, const float* bias, const float* mask_ref,
+                         const float* post_mul, float* y, float* y2, int B, int IH, int IW, int Cout, int mode,
+                         cudaStream_t st);
+bool tma_conv_dgrad_supported(const float* dy, const float* W, const float* a_in, const float* dx, int Cin, int Cout);
+cudaError_t tma_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH, int IW, int Cin,
+                           int Cout, cudaStream_t st);
+bool tma_conv_wgrad_supported(const float* x, int Cx, int Cv, float shift, const float* dy, int Cout);
+int tma_wgrad_splits(int B, int OH, int OW, int Cin, int Cout);
+cudaError_t tma_conv_wgrad_partials(const float* x, int Cx, const float* dy, float* part, int B, int IH, int IW, int Cout,
+                                    int splits, cudaStream_t st);
 }  // namespace expo

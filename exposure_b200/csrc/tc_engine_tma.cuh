@@ -1,0 +1,230 @@
+// TMA-fed tcgen05 GEMM engine (third generation; backend 4).
+//
+// The first two engines gather operands through registers: even warp-specialised, the producers
+// spend ~50 instructions per 16 bytes on im2col address arithmetic and the tensor pipe idles
+// (profiles/r1_layer_bench_*.md).  Here NO thread computes an operand address:
+//
+//   warp 0, one lane   TMA PRODUCER   one cp.async.bulk.tensor per operand block and K step:
+//                                     * K-major operands (im2col rows, delta rows, dgrad weights):
+//                                       4-D boxes {32 ch, w, h, b} with SWIZZLE_128B -- for the
+//                                       4x4 stride-2 convolution the box walks the input with
+//                                       element strides {1,2,2,1} and the -1 padding, the image
+//                                       border and the batch tail are the TMA's out-of-bounds
+//                                       zero fill;
+//                                     * MN-major operands (weights [K][N], wgrad activations and
+//                                       deltas [pixel][channel]): boxes {32 ch, 32 k rows} with
+//                                       SWIZZLE_128B_ATOM_32B, which is the only layout
+//                                       tcgen05.mma accepts for MN-major TF32
+//                                       (UMMA layout_type 1, "128B_BASE32B"; verified with
+//                                       tools/probe_umma.cu, profiles/r1_probe_umma.txt)
+//   warps 2-5          CONVERTERS     3xTF32 split in shared memory: kind::tf32 TRUNCATES fp32
+//                                     inputs (probe), so the raw TMA tile already is the "hi"
+//                                     operand; the converters only write lo = rna(v - trunc(v))
+//                                     at the same byte offset of a second tile (layout-agnostic)
+//   warp 1, one lane   MMA ISSUER     4 x 3 tcgen05.mma.kind::tf32 per K step
+//                                     (hi*hi + hi*lo + lo*hi), tcgen05.commit frees the stage
+//   warps 2-5          EPILOGUE       tcgen05.ld 32x32b (warp w owns TMEM lanes 32*(w%4)..)
+//
+// mbarriers per stage: raw_full (TMA transaction bytes) -> conv_full (128 converter arrivals)
+// -> empty (tcgen05.commit).
+#pragma once
+#include <cuda.h>
+
+#include "tc_engine.cuh"
+
+namespace expo {
+namespace tma {
+
+constexpr int kThreads = 192;
+constexpr int kConverters = 128;
+constexpr int kBM = 128;
+constexpr int kBK = 32;
+constexpr int kTileA = kBM * 128;        // bytes of one A tile (128 x 32 fp32)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+// MN-major TF32 tile: blocks of 32 (MN) x 32 (K rows of 128 B) = 4 KiB; LBO = 4096 B between
+// MN blocks, SBO = 512 B between groups of 4 K rows, layout_type 1 (SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_major(int M, int N, bool a_mn, bool b_mn) {
+  return tc::idesc_tf32(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN >= 128 ? 3 : 4;
+  static constexpr int kTileB = BN * 128;
+  static constexpr int kStageBytes = 2 * kTileA + 2 * kTileB;       // raw + lo for A and B
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024;
+  static constexpr int kVecPerThread = (kTileA + kTileB) / 16 / kConverters;
+};
+
+// Problem functor P (passed as a __grid_constant__ parameter: the CUtensorMaps inside it must stay
+// in parameter space):
+//   static constexpr bool kAMn, kBMn            operand majorness
+//   int  k_iters(int z)                          K steps of 32 for grid slice z
+//   void load<BN>(ki, z, m0, n0, a_dst, b_dst, bar)   issue the TMA loads of one stage
+//                                                (exactly kTileA + BN * 128 bytes in total)
+//   void store16(z, m, n0, v[16])                C[m, n0..n0+15]
+template <class P, int BN>
+__global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_constant__ P p) {
+  static_assert(BN == 32 || BN == 64 || BN == 128, "BN must be 32, 64 or 128");
+  using C = Cfg<BN>;
+  constexpr int NS = C::kStages;
+  extern __shared__ __align__(1024) unsigned char tma_smem[];
+  __shared__ __align__(8) uint64_t raw_full[NS];
+  __shared__ __align__(8) uint64_t conv_full[NS];
+  __shared__ __align__(8) uint64_t empty[NS];
+  __shared__ __align__(8) uint64_t accum;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  unsigned char* base = tma_smem + ((1024u - (smem_u32(tma_smem) & 1023u)) & 1023u);
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, BN);
+  if (tid == 32) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&conv_full[s], kConverters);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&accum, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.ta);
+    tma_prefetch_desc(&p.tb);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_acc = tmem_base_s;
+  const int KI = p.k_iters(z);
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      for (int ki = 0; ki < KI; ++ki) {
+        const int s = ki % NS, use = ki / NS;
+        if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+        unsigned char* a_raw = base + (size_t)s * C::kStageBytes;
+        unsigned char* b_raw = a_raw + 2 * kTileA;
+        mbar_expect_tx(&raw_full[s], (uint32_t)(kTileA + C::kTileB));
+        p.template load<BN>(ki, z, m0, n0, a_raw, b_raw, &raw_full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32_major(kBM, BN, P::kAMn, P::kBMn);
+      for (int ki = 0; ki < KI; ++ki) {
+        const int s = ki % NS, use = ki / NS;
+        mbar_wait(&conv_full[s], (uint32_t)(use & 1));
+        tc::fence_after_sync();
+        const uint32_t sa_hi = smem_u32(base + (size_t)s * C::kStageBytes), sa_lo = sa_hi + kTileA,
+                       sb_hi = sa_lo + kTileA, sb_lo = sb_hi + C::kTileB;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {             // 4 x (K = 8) per stage
+          const uint32_t ao = P::kAMn ? k * 1024 : k * 32, bo = P::kBMn ? k * 1024 : k * 32;
+          const uint64_t dah = P::kAMn ? smem_desc_mn32(sa_hi + ao) : tc::smem_desc_sw128(sa_hi + ao);
+          const uint64_t dal = P::kAMn ? smem_desc_mn32(sa_lo + ao) : tc::smem_desc_sw128(sa_lo + ao);
+          const uint64_t dbh = P::kBMn ? smem_desc_mn32(sb_hi + bo) : tc::smem_desc_sw128(sb_hi + bo);
+          const uint64_t dbl = P::kBMn ? smem_desc_mn32(sb_lo + bo) : tc::smem_desc_sw128(sb_lo + bo);
+          tc::mma_tf32(tmem_acc, dah, dbh, idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          tc::mma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+          tc::mma_tf32(tmem_acc, dal, dbh, idesc, 1u);
+        }
+        tc::mma_commit(&empty[s]);
+      }
+      tc::mma_commit(&accum);
+    }
+    __syncwarp();
+  } else {
+    // ================================ converters ================================
+    const int t = tid - 64;
+    for (int ki = 0; ki < KI; ++ki) {
+      const int s = ki % NS, use = ki / NS;
+      unsigned char* a_raw = base + (size_t)s * C::kStageBytes;
+      mbar_wait(&raw_full[s], (uint32_t)(use & 1));
+#pragma unroll
+      for (int j = 0; j < C::kVecPerThread; ++j) {
+        // flat 16-byte index over [A raw | A lo | B raw | B lo]: raw at off, lo at off + tile size
+        const int i = t + kConverters * j;
+        const bool is_a = i < kTileA / 16;
+        unsigned char* src = is_a ? a_raw + (size_t)i * 16 : a_raw + 2 * kTileA + (size_t)(i - kTileA / 16) * 16;
+        const float4 v = *reinterpret_cast<const float4*>(src);
+        float4 l;
+        l.x = tc::rn_tf32(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+        l.y = tc::rn_tf32(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+        l.z = tc::rn_tf32(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+        l.w = tc::rn_tf32(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        *reinterpret_cast<float4*>(src + (is_a ? kTileA : C::kTileB)) = l;
+      }
+      fence_proxy_async();
+      mbar_arrive(&conv_full[s]);
+    }
+    // ================================ epilogue ================================
+    if (KI > 0) mbar_wait(&accum, 0u);
+    tc::fence_after_sync();
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      if (KI > 0) tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      p.store16(z, m, n0 + c0, v);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_acc, BN);
+}
+
+template <class P, int BN>
+inline cudaError_t launch_tma_gemm(const P& p, int M, int N, int Z, cudaStream_t st) {
+  constexpr size_t smem = Cfg<BN>::kSmem;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tma_gemm_kernel<P, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
+  tma_gemm_kernel<P, BN><<<grid, kThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace tma
+}  // namespace expo

@@ -305,7 +305,7 @@ def adam(params, grads, m, v, hyper, beta1, beta2, eps=1e-8, grad_scale=1.0):
   _n()
 
 
-BACKEND_AUTO, BACKEND_CUDA_CORES, BACKEND_TCGEN05 = 0, 1, 2
+BACKEND_AUTO, BACKEND_CUDA_CORES, BACKEND_TCGEN05, BACKEND_TCGEN05_WS, BACKEND_TCGEN05_TMA = 0, 1, 2, 3, 4
 
 
 def set_gemm_backend(backend):

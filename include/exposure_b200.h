@@ -137,7 +137,10 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams,
 
 /* GEMM backend of the conv / FC primitives: 0 = auto, 1 = exact-fp32 CUDA-core engine,
  * 2 = tcgen05 tensor cores (kind::tf32 with 3xTF32 split accumulation, accumulators in TMEM)
- * for the primitives that have a tensor-core instantiation.  Process-wide. */
+ * for the primitives that have a tensor-core instantiation, 3 = the same with warp-specialised
+ * producer / MMA-issuer roles, 4 = TMA-fed tcgen05 (im2col boxes by cp.async.bulk.tensor; the
+ * convolutions whose channel counts are multiples of 32, the rest runs as backend 1).
+ * Process-wide. */
 int exp_set_gemm_backend(int backend);
 
 /* y[B,IH/2,IW/2,Cout] = epi( conv4x4s2( concat(x[B,IH,IW,Cx], tile(vec[B,Cv])) - shift ) )

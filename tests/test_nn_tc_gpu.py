@@ -10,7 +10,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 TOL = 2e-5
 
 
-@pytest.fixture(params=[2, 3], ids=["tcgen05", "tcgen05-warp-specialised"])
+@pytest.fixture(params=[2, 3, 4], ids=["tcgen05", "tcgen05-warp-specialised", "tcgen05-tma"])
 def nn(built_lib, request):
   assert torch.cuda.is_available()
   from exposure_b200 import nn_ops

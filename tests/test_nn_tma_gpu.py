@@ -1,0 +1,89 @@
+"""GPU parity of the TMA-fed tcgen05 convolution engine (backend 4: im2col boxes loaded by
+cp.async.bulk.tensor, MN-major TF32 operands in the 128B_BASE32B layout) against the fp64 oracle
+and the exact-fp32 CUDA-core engine, over the layer shapes of the policy / value / critic stacks
+(agent.py:12-41) plus ragged batches and tiny images that exercise the out-of-bounds fill."""
+import pytest
+import torch
+
+from oracle import nets as N
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+TOL = 2e-5
+
+
+@pytest.fixture()
+def nn(built_lib):
+  assert torch.cuda.is_available()
+  from exposure_b200 import nn_ops
+  nn_ops.set_gemm_backend(nn_ops.BACKEND_TCGEN05_TMA)
+  yield nn_ops
+  nn_ops.set_gemm_backend(nn_ops.BACKEND_AUTO)
+
+
+def _rand(*shape, seed=0, scale=1.0):
+  return torch.randn(*shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float64) * scale
+
+
+def _close(a, ref, tol=TOL):
+  a = a.detach().cpu().double()
+  scale = float(ref.abs().max()) + 1e-30
+  err = float((a - ref).abs().max())
+  assert err <= tol * scale, "max err %.3g vs scale %.3g (rel %.3g)" % (err, scale, err / scale)
+
+
+# (B, IH, Cin, Cout): the three deep layers at a ragged batch, a 130-image batch (two M tiles per
+# 64-pixel image group), tiny images (tile spans many images), non-power-of-two channel counts
+SHAPES = [(3, 32, 32, 64), (5, 16, 64, 128), (7, 8, 128, 256), (130, 8, 32, 32), (9, 4, 32, 64), (33, 2, 64, 32),
+          (2, 32, 96, 160), (1, 64, 32, 32)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tma_conv_fprop_dgrad_wgrad(nn, shape):
+  B, IH, Cin, Cout = shape
+  x = _rand(B, IH, IH, Cin, seed=1) * 0.3
+  W = _rand(4, 4, Cin, Cout, seed=2, scale=0.05).requires_grad_(True)
+  b = _rand(Cout, seed=3, scale=0.1)
+  xin = x.clone().requires_grad_(True)
+  pre = N.conv4x4s2(xin, W)
+  gy = _rand(*pre.shape, seed=4)
+  gin, gW = torch.autograd.grad(pre, [xin, W], grad_outputs=gy)
+  f32 = lambda t: t.detach().float().cuda().contiguous()
+  # forward (bias + lrelu), dropout side output, tangent mode
+  y = nn.conv_fwd(f32(x), f32(W), f32(b))
+  _close(y, N.lrelu(pre.detach() + b))
+  pm = (torch.rand(pre.shape, generator=torch.Generator().manual_seed(9)) < 0.5).float() * 2
+  y1, y2 = nn.conv_fwd(f32(x), f32(W), f32(b), post_mul=pm.cuda())
+  assert torch.equal(y1, y) and torch.equal(y2, y * pm.cuda())
+  mask = torch.where(y.double().cpu() > 0, 1.0, torch.where(y.double().cpu() < 0, 0.2, 0.6))
+  _close(nn.conv_fwd(f32(x), f32(W), None, shift=0.0, mask_ref=y), pre.detach() * mask)
+  # dgrad with and without the fused lrelu' of the layer input
+  _close(nn.conv_dgrad(f32(gy), f32(W), (B, IH, IH, Cin)), gin)
+  a_in = _rand(B, IH, IH, Cin, seed=5)
+  a_in[0, 0, 0, :4] = 0.0
+  d_mask = torch.where(a_in > 0, 1.0, torch.where(a_in < 0, 0.2, 0.6))
+  _close(nn.conv_dgrad(f32(gy), f32(W), (B, IH, IH, Cin), a_in=f32(a_in)), gin * d_mask)
+  # wgrad, overwrite and accumulate
+  g = nn.conv_wgrad(f32(x), f32(gy))
+  _close(g, gW)
+  g2 = nn.conv_wgrad(f32(x), f32(gy), out=g.clone(), accumulate=True)
+  _close(g2, 2 * gW)
+  # and against the CUDA-core engine (same inputs, different summation order)
+  nn.set_gemm_backend(nn.BACKEND_CUDA_CORES)
+  ys = nn.conv_fwd(f32(x), f32(W), f32(b))
+  gs = nn.conv_wgrad(f32(x), f32(gy))
+  nn.set_gemm_backend(nn.BACKEND_TCGEN05_TMA)
+  _close(y, ys.double().cpu(), tol=3e-5)
+  _close(g, gs.double().cpu(), tol=3e-5)
+
+
+def test_tma_first_layer_falls_back_to_cuda_cores(nn):
+  """Cin = 14 (3 image + 11 state channels) is not a multiple of 32: backend 4 must still give
+  the right answer (the call is served by the CUDA-core engine)."""
+  B, IH, Cx, Cv, Cout = 2, 64, 3, 11, 32
+  x = _rand(B, IH, IH, Cx, seed=1).abs() * 0.3
+  vec = _rand(B, Cv, seed=2)
+  W = _rand(4, 4, Cx + Cv, Cout, seed=3, scale=0.1)
+  b = _rand(Cout, seed=4, scale=0.1)
+  f32 = lambda t: t.float().cuda().contiguous()
+  y = N.lrelu(N.conv4x4s2(N.enrich(x, vec) - 0.5, W, b))
+  _close(nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=0.5), y)

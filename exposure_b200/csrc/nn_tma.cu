@@ -84,7 +84,7 @@ __device__ __forceinline__ float dlrelu(float a) { return a > 0.f ? 1.0f : (a < 
 struct TmaConvFprop {
   CUtensorMap ta, tb;
   const float* bias; const float* mask_ref; const float* post_mul; float* y; float* y2;
-  int M, Cin, Cout, OW, lgOW, lgOHW, mode;
+  int M, Cin, Cout, OW, lgOW, lgOHW, mode, splits;
   static constexpr bool kAMn = false, kBMn = true;
   __device__ int k_iters(int) const { return 16 * Cin / tma::kBK; }
   template <int BN>
@@ -97,28 +97,28 @@ struct TmaConvFprop {
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) tma::tma_load_2d(b_dst + j * 4096, &tb, n0 + 32 * j, k, bar);
   }
-  __device__ void store16(int, int m, int n0, const float (&v)[16]) const {
-    if (m >= M || n0 >= Cout) return;                          // Cout % 32 == 0: whole 16-wide groups
-    const size_t idx = (size_t)m * Cout + n0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-      if (mode == 0) {
-        if (bias) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0) + g);
-          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-        }
-        o.x = lrelu(o.x); o.y = lrelu(o.y); o.z = lrelu(o.z); o.w = lrelu(o.w);
-      } else {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(mask_ref + idx) + g);
-        o.x *= dlrelu(a.x); o.y *= dlrelu(a.y); o.z *= dlrelu(a.z); o.w *= dlrelu(a.w);
+  __device__ void store4(int, int m, int n, float4 o) const {
+    if (m >= M || n >= Cout) return;                           // Cout % 32 == 0: whole groups of 4
+    const size_t idx = (size_t)m * Cout + n;
+    if (mode == 0) {
+      if (bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n));
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
       }
-      reinterpret_cast<float4*>(y + idx)[g] = o;
-      if (y2) {
-        const float4 pm = __ldg(reinterpret_cast<const float4*>(post_mul + idx) + g);
-        reinterpret_cast<float4*>(y2 + idx)[g] = make_float4(o.x * pm.x, o.y * pm.y, o.z * pm.z, o.w * pm.w);
-      }
+      o.x = lrelu(o.x); o.y = lrelu(o.y); o.z = lrelu(o.z); o.w = lrelu(o.w);
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(mask_ref + idx));
+      o.x *= dlrelu(a.x); o.y *= dlrelu(a.y); o.z *= dlrelu(a.z); o.w *= dlrelu(a.w);
     }
+    *reinterpret_cast<float4*>(y + idx) = o;
+    if (y2) {
+      const float4 pm = __ldg(reinterpret_cast<const float4*>(post_mul + idx));
+      *reinterpret_cast<float4*>(y2 + idx) = make_float4(o.x * pm.x, o.y * pm.y, o.z * pm.z, o.w * pm.w);
+    }
+  }
+  __device__ void store16(int z, int m, int n0, const float (&v)[16]) const {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) store4(z, m, n0 + 4 * g, make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
   }
 };
 
@@ -141,16 +141,24 @@ cudaError_t tma_conv_fwd(const float* x, int Cx, const float* W, const float* bi
   if (!make_map(&p.tb, W, 2, wd, ws, wb, we, true)) return cudaErrorInvalidValue;
   p.bias = bias; p.mask_ref = mask_ref; p.post_mul = post_mul; p.y = y; p.y2 = y2;
   p.M = B * OH * OW; p.Cin = Cx; p.Cout = Cout; p.OW = OW; p.lgOW = ilog2(OW); p.lgOHW = ilog2(OH * OW); p.mode = mode;
-  if (Cout % 128 == 0 && (p.M / 128) * (Cout / 128) >= 96) return tma::launch_tma_gemm<TmaConvFprop, 128>(p, p.M, Cout, 1, st);
-  if (Cout % 64 == 0) return tma::launch_tma_gemm<TmaConvFprop, 64>(p, p.M, Cout, 1, st);
-  return tma::launch_tma_gemm<TmaConvFprop, 32>(p, p.M, Cout, 1, st);
+  const int mt = (p.M + tma::kBM - 1) / tma::kBM, ki = 16 * Cx / tma::kBK;
+  if (Cout % 128 == 0) {
+    p.splits = tma::pick_splits(mt * (Cout / 128), ki, 128);
+    return tma::launch_tma_gemm<TmaConvFprop, 128>(p, p.M, Cout, p.splits, st);
+  }
+  if (Cout % 64 == 0) {
+    p.splits = tma::pick_splits(mt * (Cout / 64), ki, 64);
+    return tma::launch_tma_gemm<TmaConvFprop, 64>(p, p.M, Cout, p.splits, st);
+  }
+  p.splits = tma::pick_splits(mt * (Cout / 32), ki, 32);
+  return tma::launch_tma_gemm<TmaConvFprop, 32>(p, p.M, Cout, p.splits, st);
 }
 
 // ------------------------------------------------------------------------------------------
 struct TmaConvDgrad {
   CUtensorMap ta, tb;
   const float* a_in; float* dx;
-  int M, IH, IW, Cin, Cout, lgW2, lgHW2;
+  int M, IH, IW, Cin, Cout, lgW2, lgHW2, splits;
   static constexpr bool kAMn = false, kBMn = false;
   __device__ int k_iters(int) const { return 4 * Cout / tma::kBK; }
   template <int BN>
@@ -168,34 +176,21 @@ struct TmaConvDgrad {
     tma::tma_load_4d(a_dst, &ta, co0, c0 + ox_off, a0 + oy_off, b0, bar);
     tma::tma_load_3d(b_dst, &tb, co0, n0, ky * 4 + kx, bar);
   }
-  __device__ void store16(int z, int m, int n0, const float (&v)[16]) const {
-    if (m >= M) return;
+  __device__ void store4(int z, int m, int n, float4 o) const {
+    if (m >= M || n >= Cin) return;                            // Cin % 4 == 0
     const int py = z >> 1, px = z & 1;
     const int b = m >> lgHW2, rem = m & ((1 << lgHW2) - 1);
     const int iy = 2 * (rem >> lgW2) + py, ix = 2 * (rem & ((IW / 2) - 1)) + px;
-    const size_t base = ((size_t)(b * IH + iy) * IW + ix) * Cin;
-    if ((Cin & 3) == 0) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int n = n0 + 4 * g;
-        if (n >= Cin) break;
-        float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-        if (a_in) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(a_in + base + n));
-          o.x *= dlrelu(a.x); o.y *= dlrelu(a.y); o.z *= dlrelu(a.z); o.w *= dlrelu(a.w);
-        }
-        *reinterpret_cast<float4*>(dx + base + n) = o;
-      }
-      return;
+    const size_t idx = ((size_t)(b * IH + iy) * IW + ix) * Cin + n;
+    if (a_in) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(a_in + idx));
+      o.x *= dlrelu(a.x); o.y *= dlrelu(a.y); o.z *= dlrelu(a.z); o.w *= dlrelu(a.w);
     }
+    *reinterpret_cast<float4*>(dx + idx) = o;
+  }
+  __device__ void store16(int z, int m, int n0, const float (&v)[16]) const {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int n = n0 + i;
-      if (n >= Cin) break;
-      float o = v[i];
-      if (a_in) o *= dlrelu(__ldg(a_in + base + n));
-      dx[base + n] = o;
-    }
+    for (int g = 0; g < 4; ++g) store4(z, m, n0 + 4 * g, make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
   }
 };
 
@@ -221,16 +216,17 @@ cudaError_t tma_conv_dgrad(const float* dy, const float* W, const float* a_in, f
   if (!make_map(&p.tb, W, 3, wd, ws, wb, we, false)) return cudaErrorInvalidValue;
   p.a_in = a_in; p.dx = dx; p.M = B * OH * OW; p.IH = IH; p.IW = IW; p.Cin = Cin; p.Cout = Cout;
   p.lgW2 = ilog2(OW); p.lgHW2 = ilog2(OH * OW);
-  if (BN == 128) return tma::launch_tma_gemm<TmaConvDgrad, 128>(p, p.M, N, 4, st);
-  if (BN == 64) return tma::launch_tma_gemm<TmaConvDgrad, 64>(p, p.M, N, 4, st);
-  return tma::launch_tma_gemm<TmaConvDgrad, 32>(p, p.M, N, 4, st);
+  p.splits = tma::pick_splits(4 * ((p.M + tma::kBM - 1) / tma::kBM) * ((N + BN - 1) / BN), 4 * Cout / tma::kBK, BN);
+  if (BN == 128) return tma::launch_tma_gemm<TmaConvDgrad, 128>(p, p.M, N, 4 * p.splits, st);
+  if (BN == 64) return tma::launch_tma_gemm<TmaConvDgrad, 64>(p, p.M, N, 4 * p.splits, st);
+  return tma::launch_tma_gemm<TmaConvDgrad, 32>(p, p.M, N, 4 * p.splits, st);
 }
 
 // ------------------------------------------------------------------------------------------
 struct TmaConvWgrad {
   CUtensorMap ta, tb;
   float* part;
-  int Cin, Cout, OW, lgOW, lgOHW, steps_per_split, total_steps;
+  int Cin, Cout, OW, lgOW, lgOHW, steps_per_split, total_steps, splits;   // splits: cluster split-K, unused (= 1): z already splits K
   static constexpr bool kAMn = true, kBMn = true;
   __device__ int k_iters(int z) const {
     const int left = total_steps - z * steps_per_split;
@@ -250,6 +246,10 @@ struct TmaConvWgrad {
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) tma::tma_load_2d(b_dst + j * 4096, &tb, n0 + 32 * j, p0, bar);
   }
+  __device__ void store4(int z, int m, int n, float4 o) const {
+    if (m >= 16 * Cin || n >= Cout) return;
+    *reinterpret_cast<float4*>(part + ((size_t)z * 16 * Cin + m) * Cout + n) = o;
+  }
   __device__ void store16(int z, int m, int n0, const float (&v)[16]) const {
     if (m >= 16 * Cin || n0 >= Cout) return;
     float4* dst = reinterpret_cast<float4*>(part + ((size_t)z * 16 * Cin + m) * Cout + n0);
@@ -266,9 +266,10 @@ bool tma_conv_wgrad_supported(const float* x, int Cx, int Cv, float shift, const
 int tma_wgrad_splits(int B, int OH, int OW, int Cin, int Cout) {
   const int steps = (B * OH * OW + tma::kBK - 1) / tma::kBK;
   const int BN = Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
-  const int tiles = ((16 * Cin + tma::kBM - 1) / tma::kBM) * (Cout / BN);
+  const int tiles = ((16 * Cin + tma::kBM - 1) / tma::kBM) * ((Cout + BN - 1) / BN);
   int splits = (2 * 148 + tiles - 1) / tiles;                   // ~2 waves of CTAs
   if (splits > steps / 4) splits = steps / 4;                   // at least 4 K steps per CTA
+  if (splits < 1) splits = 1;
   if (splits < 1) splits = 1;
   if (splits > 64) splits = 64;
   return splits;
@@ -285,6 +286,7 @@ cudaError_t tma_conv_wgrad_partials(const float* x, int Cx, const float* dy, flo
   if (!make_map(&p.tb, dy, 2, dd, ds, db, de, true)) return cudaErrorInvalidValue;
   p.part = part; p.Cin = Cx; p.Cout = Cout; p.OW = OW; p.lgOW = ilog2(OW); p.lgOHW = ilog2(OH * OW);
   p.total_steps = (P + tma::kBK - 1) / tma::kBK;
+  p.splits = 1;
   p.steps_per_split = (p.total_steps + splits - 1) / splits;
   const int M = 16 * Cx;
   if (Cout % 128 == 0) return tma::launch_tma_gemm<TmaConvWgrad, 128>(p, M, Cout, splits, st);

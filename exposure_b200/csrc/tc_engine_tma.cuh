@@ -30,6 +30,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "tc_engine.cuh"
 
 namespace expo {
@@ -85,13 +87,51 @@ struct Cfg {
   static constexpr int kVecPerThread = (kTileA + kTileB) / 16 / kConverters;
 };
 
+// thread-block cluster helpers (split-K reduction through distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
+
+// sum of the float4 at local shared address `a` over ranks 0..S-1, in rank order; the DSMEM loads
+// are issued back to back before the first add (a remote load costs ~1 us)
+template <int S>
+__device__ __forceinline__ float4 dsmem_sum4(uint32_t a) {
+  float4 t[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) t[s] = ld_dsmem_v4(a, (uint32_t)s);
+  float4 v = t[0];
+#pragma unroll
+  for (int s = 1; s < S; ++s) { v.x += t[s].x; v.y += t[s].y; v.z += t[s].z; v.w += t[s].w; }
+  return v;
+}
+
 // Problem functor P (passed as a __grid_constant__ parameter: the CUtensorMaps inside it must stay
 // in parameter space):
 //   static constexpr bool kAMn, kBMn            operand majorness
-//   int  k_iters(int z)                          K steps of 32 for grid slice z
-//   void load<BN>(ki, z, m0, n0, a_dst, b_dst, bar)   issue the TMA loads of one stage
+//   int  splits                                  cluster split-K factor S (1, 2, 4 or 8; BN / S >= 16):
+//                                                blockIdx.z = slice * S + rank, the S CTAs of a cluster
+//                                                each take 1/S of the K steps, park their accumulators in
+//                                                their own shared memory, and after a cluster barrier CTA
+//                                                `rank` sums column chunk `rank` over all S CTAs in rank
+//                                                order (deterministic) through DSMEM and stores it
+//   int  k_iters(int slice)                      K steps of 32 for grid slice `slice`
+//   void load<BN>(ki, slice, m0, n0, a_dst, b_dst, bar)   issue the TMA loads of K step ki
 //                                                (exactly kTileA + BN * 128 bytes in total)
-//   void store16(z, m, n0, v[16])                C[m, n0..n0+15]
+//   void store16(slice, m, n0, v[16])            C[m, n0..n0+15]
+//   void store4(slice, m, n, float4)             C[m, n..n+3]          (cluster split-K epilogue)
 template <class P, int BN>
 __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_constant__ P p) {
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN must be 32, 64 or 128");
@@ -105,7 +145,9 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int z = blockIdx.z;
+  const int S = p.splits;
+  const int z = blockIdx.z / S;                               // problem slice
+  const int rank = S > 1 ? (int)cluster_ctarank() : 0;       // == blockIdx.z % S
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
   unsigned char* base = tma_smem + ((1024u - (smem_u32(tma_smem) & 1023u)) & 1023u);
 
@@ -126,7 +168,12 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_acc = tmem_base_s;
-  const int KI = p.k_iters(z);
+  const int KI_all = p.k_iters(z);
+  const int per = (KI_all + S - 1) / S;
+  const int kb = rank * per;                                  // first K step of this CTA
+  const int KI = KI_all - kb < per ? (KI_all - kb > 0 ? KI_all - kb : 0) : per;
+  float* park = reinterpret_cast<float*>(base);               // [128][BN + 4] accumulators (S > 1), reuses the stage ring
+  constexpr int kParkLd = BN + 4;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -137,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
         unsigned char* a_raw = base + (size_t)s * C::kStageBytes;
         unsigned char* b_raw = a_raw + 2 * kTileA;
         mbar_expect_tx(&raw_full[s], (uint32_t)(kTileA + C::kTileB));
-        p.template load<BN>(ki, z, m0, n0, a_raw, b_raw, &raw_full[s]);
+        p.template load<BN>(kb + ki, z, m0, n0, a_raw, b_raw, &raw_full[s]);
       }
     }
     __syncwarp();
@@ -195,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
     if (KI > 0) mbar_wait(&accum, 0u);
     tc::fence_after_sync();
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
+    const int row = q * 32 + lane;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
@@ -204,8 +251,28 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
-      p.store16(z, m, n0 + c0, v);
+      if (S == 1) p.store16(z, m0 + row, n0 + c0, v);
+      else {
+        float4* dst = reinterpret_cast<float4*>(park + (size_t)row * kParkLd + c0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
     }
+  }
+  if (S > 1) {
+    cluster_sync_all();                               // every CTA of the cluster has parked its partial tile
+    if (warp >= 2) {
+      // CTA `rank` owns columns [rank*W, (rank+1)*W): consecutive threads take consecutive float4 of a
+      // row chunk, so both the DSMEM reads and the global stores are contiguous runs of W*4 bytes
+      const int W = BN / S, lgW4 = 31 - __clz(W >> 2);
+      for (int idx = tid - 64; idx < (kBM << lgW4); idx += kConverters) {
+        const int row = idx >> lgW4, col = rank * W + ((idx & ((1 << lgW4) - 1)) << 2);
+        const uint32_t a = smem_u32(park + (size_t)row * kParkLd + col);
+        const float4 v = S == 2 ? dsmem_sum4<2>(a) : (S == 4 ? dsmem_sum4<4>(a) : dsmem_sum4<8>(a));   // fixed order: reproducible
+        p.store4(z, m0 + row, n0 + col, v);
+      }
+    }
+    cluster_sync_all();                               // nobody leaves while its shared memory is still being read
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -221,9 +288,41 @@ inline cudaError_t launch_tma_gemm(const P& p, int M, int N, int Z, cudaStream_t
     if (e != cudaSuccess) return e;
     configured = true;
   }
+  // Z = slices * p.splits; the p.splits CTAs that share a tile form one cluster along z
   dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
-  tma_gemm_kernel<P, BN><<<grid, kThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  if (p.splits <= 1) {
+    tma_gemm_kernel<P, BN><<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 1;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = (unsigned)p.splits;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tma_gemm_kernel<P, BN>, p);
+}
+
+// cluster split-K factor: double while the doubled grid fits the 148 SMs, every CTA keeps >= 4 K
+// steps and every rank keeps >= 16 output columns
+inline int pick_splits(int base_ctas, int k_iters, int BN) {
+  static const int forced = [] { const char* e = getenv("EXPOSURE_TMA_SPLITS"); return e ? atoi(e) : 0; }();   // tuning aid
+  if (forced > 0) {
+    int f = 1;
+    while (f < forced && f < 8 && BN / (2 * f) >= 16 && k_iters / (2 * f) >= 1) f *= 2;
+    return f;
+  }
+  int s = 1;
+  // measured (profiles/r1_layer_bench_tma.md): a split pays only while the doubled grid still fits one
+  // wave, and clusters of 8 schedule poorly with 1 CTA per SM
+  while (s < 4 && 2 * base_ctas * s <= 148 && k_iters / (2 * s) >= 4 && BN / (2 * s) >= 16) s *= 2;
+  return s;
 }
 
 }  // namespace tma

@@ -3,7 +3,7 @@
 
   python profiles/layer_bench.py [--batch 64] [--backends 1,2,3] > gpurun_out/layer_bench.md
 
-Times each layer shape of the policy / value / critic stacks (agent.py:12-41, 64x64 input, 4x4
+Times (CUDA-graph replay, device clock) each layer shape of the policy / value / critic stacks (agent.py:12-41, 64x64 input, 4x4
 stride-2 convolutions, channels 32-64-128-256) with CUDA events on the launching stream, inputs
 rotated through buffers larger than L2 is NOT attempted here: the activations of one layer are a
 few MB and live in L2 in the training step too, so the warm numbers are the relevant ones.
@@ -17,17 +17,28 @@ sys.path.insert(0, ".")
 from exposure_b200 import nn_ops as K  # noqa: E402
 
 
-def timed(fn, iters=20):
+def timed(fn, iters=20, reps=5):
+  """us per call, device time of a CUDA graph holding `iters` calls (no host launch overhead)."""
   for _ in range(3):
     fn()
   torch.cuda.synchronize()
+  g = torch.cuda.CUDAGraph()
+  side = torch.cuda.Stream()
+  side.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(side):
+    with torch.cuda.graph(g, stream=side):
+      for _ in range(iters):
+        fn()
+  torch.cuda.current_stream().wait_stream(side)
+  g.replay()
+  torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
-  for _ in range(iters):
-    fn()
+  for _ in range(reps):
+    g.replay()
   e1.record()
   torch.cuda.synchronize()
-  return e0.elapsed_time(e1) / iters * 1e3   # us
+  return e0.elapsed_time(e1) / (iters * reps) * 1e3   # us
 
 
 def main():

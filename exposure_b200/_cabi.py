@@ -46,6 +46,19 @@ SIGNATURES = {
     "exp_fc_dgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int,
                               _c_int, _c_int, _c_int, _c_void_p]),
     "exp_fc_wgrad": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_conv1_supported": (_c_int, [_c_int, _c_int]),
+    "exp_conv1_padded_input_elems": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "exp_conv1_pad_input": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, ctypes.c_float, _c_void_p, _c_int, _c_int, _c_int,
+                                     _c_void_p]),
+    "exp_conv1_pad_weights": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "exp_conv1_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                               _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_conv1_wgrad_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
+    "exp_conv1_wgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                 _c_size_t, _c_void_p]),
+    "exp_conv_enrich32": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, ctypes.c_float, _c_void_p, _c_int, _c_int, _c_int,
+                                   _c_void_p]),
+    "exp_conv_pad_weights32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
     "exp_colsum_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "exp_colsum": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "exp_stats_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),

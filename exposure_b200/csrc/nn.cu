@@ -17,10 +17,12 @@ namespace expo {
 
 static int g_gemm_backend = kBackendAuto;
 int gemm_backend() { return g_gemm_backend; }
-// AUTO currently resolves to the CUDA-core engine; the tcgen05 engine is opt-in until every
-// primitive has a validated tensor-core instantiation.
+// AUTO resolves per call: the TMA-fed tcgen05 engine for the convolutions it supports (channel
+// counts that are multiples of 32: 2-3x faster than CUDA cores, profiles/r1_layer_bench_tma.md),
+// the exact-fp32 CUDA-core engine for everything else.  The register-gather tcgen05 engines
+// (backends 2, 3) stay opt-in: they are slower than both.
 bool use_tcgen05() { return g_gemm_backend == kBackendTcgen05 || g_gemm_backend == kBackendTcgen05Ws; }
-bool use_tma() { return g_gemm_backend == kBackendTcgen05Tma; }
+bool use_tma() { return g_gemm_backend == kBackendTcgen05Tma || g_gemm_backend == kBackendAuto; }
 
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
@@ -344,11 +346,13 @@ __global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, i
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (col < cols) {
     int r = r0 + ry;
-    for (; r + 24 < r1; r += 32) {       // 4 independent loads in flight per thread
-      s0 += a[(size_t)r * cols + col];
-      s1 += a[(size_t)(r + 8) * cols + col];
-      s2 += a[(size_t)(r + 16) * cols + col];
-      s3 += a[(size_t)(r + 24) * cols + col];
+    for (; r + 56 < r1; r += 64) {       // 8 independent loads in flight per thread
+      const float v0 = a[(size_t)r * cols + col], v1 = a[(size_t)(r + 8) * cols + col];
+      const float v2 = a[(size_t)(r + 16) * cols + col], v3 = a[(size_t)(r + 24) * cols + col];
+      const float v4 = a[(size_t)(r + 32) * cols + col], v5 = a[(size_t)(r + 40) * cols + col];
+      const float v6 = a[(size_t)(r + 48) * cols + col], v7 = a[(size_t)(r + 56) * cols + col];
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+      s0 += v4; s1 += v5; s2 += v6; s3 += v7;
     }
     for (; r < r1; r += 8) s0 += a[(size_t)r * cols + col];
   }
@@ -371,9 +375,11 @@ __global__ void colsum_finish_kernel(const float* __restrict__ part, int chunks,
   for (int z = 0; z < chunks; ++z) s += part[((size_t)b * chunks + z) * cols + col];
   out[i] = s;
 }
+// 256-row chunks: a thread then walks 32 rows (4 rounds of 8 loads); the partials [chunks][cols] are
+// summed by the same kernel in a second pass (the serial 1024-row walk used to cost ~24 us a call)
 static int colsum_chunks(int rows) {
-  int c = (rows + 1023) / 1024;
-  return c < 1 ? 1 : (c > 128 ? 128 : c);
+  int c = (rows + 255) / 256;
+  return c < 1 ? 1 : (c > 512 ? 512 : c);
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -641,8 +647,13 @@ int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* 
   }
   colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, rpc, reinterpret_cast<float*>(workspace));
   EXP_CHECK_LAUNCH("exp_colsum");
-  colsum_finish_kernel<<<(batch * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float*>(workspace), chunks, cols, batch, out);
+  if (chunks <= 16) {
+    colsum_finish_kernel<<<(batch * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float*>(workspace), chunks, cols, batch, out);
+  } else {
+    colsum_kernel<<<dim3((cols + 31) / 32, batch, 1), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float*>(workspace), chunks, cols, chunks, out);
+  }
   EXP_CHECK_LAUNCH("exp_colsum[finish]");
   return EXP_OK;
 }

@@ -85,6 +85,7 @@ struct TmaConvFprop {
   CUtensorMap ta, tb;
   const float* bias; const float* mask_ref; const float* post_mul; float* y; float* y2;
   int M, Cin, Cout, OW, lgOW, lgOHW, mode, splits;
+  int first;   // 1: first layer on the zero-bordered 16-channel staging copy (see exp_conv1_pad_input)
   static constexpr bool kAMn = false, kBMn = true;
   __device__ int k_iters(int) const { return 16 * Cin / tma::kBK; }
   template <int BN>
@@ -93,7 +94,10 @@ struct TmaConvFprop {
     const int tap = k / Cin, ci0 = k - tap * Cin;
     const int b0 = m0 >> lgOHW, rem = m0 & ((1 << lgOHW) - 1);
     const int oy0 = rem >> lgOW, ox0 = rem & (OW - 1);
-    tma::tma_load_4d(a_dst, &ta, ci0, 2 * ox0 - 1 + (tap & 3), 2 * oy0 - 1 + (tap >> 2), b0, bar);
+    // first layer: K step ki = (ky, half); the 32 floats are padded pixels 2(ox+half), 2(ox+half)+1
+    // x 16 channels = chunk ox+half of the row viewed as 32-float chunks, row 2oy+ky
+    if (first) tma::tma_load_4d(a_dst, &ta, 0, ox0 + (ki & 1), 2 * oy0 + (ki >> 1), b0, bar);
+    else tma::tma_load_4d(a_dst, &ta, ci0, 2 * ox0 - 1 + (tap & 3), 2 * oy0 - 1 + (tap >> 2), b0, bar);
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) tma::tma_load_2d(b_dst + j * 4096, &tb, n0 + 32 * j, k, bar);
   }
@@ -227,6 +231,7 @@ struct TmaConvWgrad {
   CUtensorMap ta, tb;
   float* part;
   int Cin, Cout, OW, lgOW, lgOHW, steps_per_split, total_steps, splits;   // splits: cluster split-K, unused (= 1): z already splits K
+  int first;   // 1: first layer on the zero-bordered 16-channel staging copy
   static constexpr bool kAMn = true, kBMn = true;
   __device__ int k_iters(int z) const {
     const int left = total_steps - z * steps_per_split;
@@ -239,9 +244,11 @@ struct TmaConvWgrad {
     const int oy0 = rem >> lgOW, ox0 = rem & (OW - 1);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int r = m0 + 32 * j;                    // row (tap, ci) of the weight gradient
-      const int tap = r / Cin, ci0 = r - tap * Cin; // rows past 16*Cin: tap >= 16 -> iy far out of bounds -> zeros
-      tma::tma_load_4d(a_dst + j * 4096, &ta, ci0, 2 * ox0 - 1 + (tap & 3), 2 * oy0 - 1 + (tap >> 2), b0, bar);
+      const int r = m0 + 32 * j;                    // row (tap, ci) of the weight gradient (16*Cin % 128 == 0: no tail)
+      const int tap = r / Cin, ci0 = r - tap * Cin;
+      // first layer (staging copy, Cin = 16): the 32 rows are (ky, 2 taps x 16 ch) = chunk ox+half of row 2oy+ky
+      if (first) tma::tma_load_4d(a_dst + j * 4096, &ta, 0, ox0 + ((r >> 5) & 1), 2 * oy0 + (r >> 6), b0, bar);
+      else tma::tma_load_4d(a_dst + j * 4096, &ta, ci0, 2 * ox0 - 1 + (tap & 3), 2 * oy0 - 1 + (tap >> 2), b0, bar);
     }
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) tma::tma_load_2d(b_dst + j * 4096, &tb, n0 + 32 * j, p0, bar);
@@ -294,4 +301,207 @@ cudaError_t tma_conv_wgrad_partials(const float* x, int Cx, const float* dy, flo
   return tma::launch_tma_gemm<TmaConvWgrad, 32>(p, M, Cout, splits, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// First layer (Cin = 3 + states = 6 / 14 / 17 channels of which all but 3 are per-image constants,
+// util.py enrich_image_input; ly.conv2d SAME padding).  Cin is not a multiple of 32, so the layer
+// runs on a STAGING COPY xp[B][IH+2][IW+2][16]: zero border (the SAME padding made explicit), the
+// enriched input minus `shift` in channels [0,Cin), zeros above.  One padded row is a sequence of
+// 32-float chunks (2 pixels x 16 channels); output pixel ox and tap pair `half` read chunk ox+half,
+// so the im2col box needs no element stride in x and K = 4 ky x 2 halves x 32 = 256 with weights
+// padded to Wp[4][4][16][Cout].
+// ------------------------------------------------------------------------------------------
+constexpr int kC1 = 16;
+
+static bool make_conv1_map(CUtensorMap* m, const float* xp, int B, int IH, int IW, int count, bool mn_major) {
+  const PixTile t = pix_tile(count, IH / 2, IW / 2);
+  const cuuint64_t dims[4] = {32, (cuuint64_t)(IW + 2) / 2, (cuuint64_t)IH + 2, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {128, (cuuint64_t)(IW + 2) * kC1 * 4, (cuuint64_t)(IH + 2) * (IW + 2) * kC1 * 4};
+  const cuuint32_t box[4] = {32, (cuuint32_t)t.tw, (cuuint32_t)(2 * t.th), (cuuint32_t)t.tb};
+  const cuuint32_t estr[4] = {1, 1, 2, 1};
+  return make_map(m, xp, 4, dims, strides, box, estr, mn_major);
+}
+
+// out[b][y][x][CP] = concat(x, tile(vec)) - shift in channels [0, Cx+Cv), 0 above; BORDER adds a
+// one-pixel zero frame (out is [B][IH+2][IW+2][CP])
+template <int CP, int BORDER>
+__global__ void conv_stage_input_kernel(const float* __restrict__ x, const float* __restrict__ vec, float shift,
+                                        float* __restrict__ xp, int B, int IH, int IW, int Cx, int Cv) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // one (padded) pixel per thread
+  const int PW = IW + 2 * BORDER, PH = IH + 2 * BORDER;
+  const size_t total = (size_t)B * PH * PW;
+  if (i >= total) return;
+  const int xx = (int)(i % PW) - BORDER, yy = (int)((i / PW) % PH) - BORDER, b = (int)(i / ((size_t)PW * PH));
+  float v[CP];
+#pragma unroll
+  for (int c = 0; c < CP; ++c) v[c] = 0.f;
+  if (xx >= 0 && xx < IW && yy >= 0 && yy < IH) {
+    const float* px = x + (((size_t)b * IH + yy) * IW + xx) * Cx;
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < Cx) v[c] = __ldg(px + c) - shift;
+      else if (c < Cx + Cv) v[c] = __ldg(vec + (size_t)b * Cv + (c - Cx)) - shift;
+  }
+  float4* dst = reinterpret_cast<float4*>(xp + i * CP);
+#pragma unroll
+  for (int g = 0; g < CP / 4; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+}
+
+// Wp[tap][cp][co] = W[tap][c][co] for c < Cin, 0 above
+__global__ void conv_pad_weights_kernel(const float* __restrict__ W, float* __restrict__ Wp, int Cin, int Cout, int CP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;                     // over [16 taps][CP][Cout]
+  if (i >= 16 * CP * Cout) return;
+  const int co = i % Cout, c = (i / Cout) % CP, tap = i / (Cout * CP);
+  Wp[i] = c < Cin ? __ldg(W + ((size_t)tap * Cin + c) * Cout + co) : 0.f;
+}
+
+// gW[tap][ci][co] (=|+=) sum_z part[z][tap*16 + ci][co], ci < Cin, in z order
+__global__ void conv1_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Cin, int Cout,
+                                          float* __restrict__ gW, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16 * Cin * Cout) return;
+  const int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
+  const size_t src = ((size_t)tap * kC1 + ci) * Cout + co, stride = (size_t)16 * kC1 * Cout;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[src + (size_t)z * stride];
+  gW[i] = accumulate ? gW[i] + s : s;
+}
+
+static int conv1_wgrad_splits(int B, int OH, int OW, int Cout) {
+  const int steps = (B * OH * OW + tma::kBK - 1) / tma::kBK;
+  const int tiles = 2 * ((Cout + 127) / 128);                      // M = 256 rows
+  int splits = (148 + tiles - 1) / tiles;
+  if (splits > steps / 4) splits = steps / 4;
+  if (splits < 1) splits = 1;
+  if (splits > 128) splits = 128;
+  return splits;
+}
+
 }  // namespace expo
+
+using namespace expo;
+
+extern "C" {
+
+size_t exp_conv1_padded_input_elems(int B, int IH, int IW) {
+  if (B <= 0 || IH <= 0 || IW <= 0) return 0;
+  return (size_t)B * (IH + 2) * (IW + 2) * kC1;
+}
+
+int exp_conv1_pad_input(const float* x, int Cx, const float* vec, int Cv, float shift, float* xp, int B, int IH, int IW,
+                        void* stream) {
+  EXP_CHECK_ARG(x && xp && B > 0 && IH >= 2 && IW >= 2 && IW % 2 == 0, "bad args");
+  EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cx + Cv <= kC1, "first-layer staging holds at most %d channels", kC1);
+  EXP_CHECK_ARG((reinterpret_cast<uintptr_t>(xp) & 15u) == 0, "xp must be 16-byte aligned");
+  const size_t total = (size_t)B * (IH + 2) * (IW + 2);
+  conv_stage_input_kernel<kC1, 1><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, vec, shift, xp, B, IH, IW, Cx, Cv);
+  EXP_CHECK_LAUNCH("exp_conv1_pad_input");
+  return EXP_OK;
+}
+
+int exp_conv1_pad_weights(const float* W, int Cin, int Cout, float* Wp, void* stream) {
+  EXP_CHECK_ARG(W && Wp && Cin > 0 && Cin <= kC1 && Cout > 0, "bad args");
+  const int n = 16 * kC1 * Cout;
+  conv_pad_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, Wp, Cin, Cout, kC1);
+  EXP_CHECK_LAUNCH("exp_conv1_pad_weights");
+  return EXP_OK;
+}
+
+int exp_conv_enrich32(const float* x, int Cx, const float* vec, int Cv, float shift, float* out, int B, int IH, int IW,
+                      void* stream) {
+  EXP_CHECK_ARG(x && out && B > 0 && IH > 0 && IW > 0, "bad args");
+  EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cx + Cv <= 32, "at most 32 channels");
+  EXP_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "out must be 16-byte aligned");
+  const size_t total = (size_t)B * IH * IW;
+  conv_stage_input_kernel<32, 0><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, vec, shift, out, B, IH, IW, Cx, Cv);
+  EXP_CHECK_LAUNCH("exp_conv_enrich32");
+  return EXP_OK;
+}
+
+int exp_conv_pad_weights32(const float* W, int Cin, int Cout, float* Wp, void* stream) {
+  EXP_CHECK_ARG(W && Wp && Cin > 0 && Cin <= 32 && Cout > 0, "bad args");
+  const int n = 16 * 32 * Cout;
+  conv_pad_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, Wp, Cin, Cout, 32);
+  EXP_CHECK_LAUNCH("exp_conv_pad_weights32");
+  return EXP_OK;
+}
+
+int exp_conv1_supported(int Cin, int Cout) { return encode_fn() != nullptr && Cin > 0 && Cin <= kC1 && Cout > 0 && Cout % 32 == 0; }
+
+int exp_conv1_fwd(const float* xp, const float* Wp, const float* bias, const float* mask_ref, const float* post_mul, float* y,
+                  float* y2, int B, int IH, int IW, int Cout, int mode, void* stream) {
+  EXP_CHECK_ARG(xp && Wp && y && B > 0 && IH >= 2 && IW >= 2, "bad args");
+  EXP_CHECK_ARG((IH & (IH - 1)) == 0 && (IW & (IW - 1)) == 0, "IH/IW must be powers of two");
+  EXP_CHECK_ARG(Cout % 32 == 0, "Cout must be a multiple of 32");
+  EXP_CHECK_ARG(mode == 0 || (mode == 1 && mask_ref), "mode 1 needs mask_ref");
+  EXP_CHECK_ARG(!y2 || post_mul, "y2 needs post_mul");
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!(al(xp) && al(Wp) && al(bias) && al(mask_ref) && al(post_mul) && al(y) && al(y2)))
+    return set_error(EXP_ERR_ALIGNMENT, "exp_conv1_fwd: pointers must be 16-byte aligned");
+  if (!encode_fn()) return set_error(EXP_ERR_UNSUPPORTED, "exp_conv1_fwd: cuTensorMapEncodeTiled not available");
+  TmaConvFprop p{};
+  const int OH = IH / 2, OW = IW / 2;
+  const cuuint64_t wd[2] = {(cuuint64_t)Cout, (cuuint64_t)16 * kC1};
+  const cuuint64_t ws[1] = {(cuuint64_t)Cout * 4};
+  const cuuint32_t wb[2] = {32, 32}, we[2] = {1, 1};
+  if (!make_conv1_map(&p.ta, xp, B, IH, IW, tma::kBM, false) || !make_map(&p.tb, Wp, 2, wd, ws, wb, we, true))
+    return set_error(EXP_ERR_CUDA, "exp_conv1_fwd: tensor map encode failed");
+  p.bias = bias; p.mask_ref = mask_ref; p.post_mul = post_mul; p.y = y; p.y2 = y2;
+  p.M = B * OH * OW; p.Cin = kC1; p.Cout = Cout; p.OW = OW; p.lgOW = ilog2(OW); p.lgOHW = ilog2(OH * OW); p.mode = mode;
+  p.first = 1;
+  const int mt = (p.M + tma::kBM - 1) / tma::kBM, ki = 16 * kC1 / tma::kBK;
+  cudaError_t e;
+  if (Cout % 128 == 0) {
+    p.splits = tma::pick_splits(mt * (Cout / 128), ki, 128);
+    e = tma::launch_tma_gemm<TmaConvFprop, 128>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
+  } else if (Cout % 64 == 0) {
+    p.splits = tma::pick_splits(mt * (Cout / 64), ki, 64);
+    e = tma::launch_tma_gemm<TmaConvFprop, 64>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
+  } else {
+    p.splits = tma::pick_splits(mt * (Cout / 32), ki, 32);
+    e = tma::launch_tma_gemm<TmaConvFprop, 32>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv1_fwd: %s", cudaGetErrorString(e));
+  return EXP_OK;
+}
+
+size_t exp_conv1_wgrad_workspace_bytes(int B, int IH, int IW, int Cout) {
+  if (B <= 0 || IH < 2 || IW < 2 || Cout <= 0) return 0;
+  return (size_t)conv1_wgrad_splits(B, IH / 2, IW / 2, Cout) * 16 * kC1 * Cout * sizeof(float);
+}
+
+int exp_conv1_wgrad(const float* xp, const float* dy, float* gW, int Cin, int B, int IH, int IW, int Cout, int accumulate,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  EXP_CHECK_ARG(xp && dy && gW && workspace && B > 0 && IH >= 2 && IW >= 2, "bad args");
+  EXP_CHECK_ARG((IH & (IH - 1)) == 0 && (IW & (IW - 1)) == 0, "IH/IW must be powers of two");
+  EXP_CHECK_ARG(Cin > 0 && Cin <= kC1 && Cout % 32 == 0, "Cin <= %d and Cout %% 32 == 0 required", kC1);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!(al(xp) && al(dy) && al(workspace))) return set_error(EXP_ERR_ALIGNMENT, "exp_conv1_wgrad: pointers must be 16-byte aligned");
+  if (!encode_fn()) return set_error(EXP_ERR_UNSUPPORTED, "exp_conv1_wgrad: cuTensorMapEncodeTiled not available");
+  const int OH = IH / 2, OW = IW / 2, P = B * OH * OW;
+  const int splits = conv1_wgrad_splits(B, OH, OW, Cout);
+  const size_t need = (size_t)splits * 16 * kC1 * Cout * sizeof(float);
+  if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  TmaConvWgrad p{};
+  const cuuint64_t dd[2] = {(cuuint64_t)Cout, (cuuint64_t)P};
+  const cuuint64_t ds[1] = {(cuuint64_t)Cout * 4};
+  const cuuint32_t db[2] = {32, 32}, de[2] = {1, 1};
+  if (!make_conv1_map(&p.ta, xp, B, IH, IW, tma::kBK, true) || !make_map(&p.tb, dy, 2, dd, ds, db, de, true))
+    return set_error(EXP_ERR_CUDA, "exp_conv1_wgrad: tensor map encode failed");
+  p.part = reinterpret_cast<float*>(workspace); p.Cin = kC1; p.Cout = Cout; p.OW = OW; p.lgOW = ilog2(OW); p.lgOHW = ilog2(OH * OW);
+  p.total_steps = (P + tma::kBK - 1) / tma::kBK;
+  p.splits = 1;
+  p.first = 1;
+  p.steps_per_split = (p.total_steps + splits - 1) / splits;
+  const int M = 16 * kC1;
+  cudaError_t e;
+  if (Cout % 128 == 0) e = tma::launch_tma_gemm<TmaConvWgrad, 128>(p, M, Cout, splits, (cudaStream_t)stream);
+  else if (Cout % 64 == 0) e = tma::launch_tma_gemm<TmaConvWgrad, 64>(p, M, Cout, splits, (cudaStream_t)stream);
+  else e = tma::launch_tma_gemm<TmaConvWgrad, 32>(p, M, Cout, splits, (cudaStream_t)stream);
+  if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv1_wgrad: %s", cudaGetErrorString(e));
+  const int n = 16 * Cin * Cout;
+  conv1_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p.part, splits, Cin, Cout, gW, accumulate);
+  EXP_CHECK_LAUNCH("exp_conv1_wgrad[reduce]");
+  return EXP_OK;
+}
+
+}  // extern "C"

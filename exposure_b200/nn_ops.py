@@ -4,6 +4,8 @@ Plumbing only: device pointers, current stream, output allocation.  See
 include/exposure_b200.h for the semantics of every call.  2-D operands may be column
 slices of a wider matrix (unit inner stride); their row stride is passed as the leading
 dimension."""
+import os
+
 import torch
 
 from . import _cabi
@@ -23,6 +25,20 @@ def _workspace(dev, nbytes):
     ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=dev)
     _ws[key] = ws
   return ws
+
+
+_scratch_bufs = {}
+
+
+def _scratch(dev, tag, numel):
+  """Persistent float32 scratch per (device, stream, tag): staging copies that must outlive one call
+  (safe inside CUDA-graph capture once the eager warm-up has sized them)."""
+  key = (dev, torch.cuda.current_stream().cuda_stream, tag)
+  buf = _scratch_bufs.get(key)
+  if buf is None or buf.numel() < numel:
+    buf = torch.empty(int(numel), dtype=torch.float32, device=dev)
+    _scratch_bufs[key] = buf
+  return buf
 
 
 def _p(t):
@@ -49,6 +65,44 @@ def _n(k=1):
 
 
 # ---- convolutions -----------------------------------------------------------------------
+def _conv1_path(Cx, Cv, Cout):
+  """First-layer tensor-core path (staging copy + padded weights, exp_conv1_*): used by the AUTO and
+  TMA backends for inputs the generic TMA path cannot take (state channels / Cin not a multiple of 32)."""
+  if _backend not in (BACKEND_AUTO, BACKEND_TCGEN05_TMA):
+    return False
+  if Cv == 0 and Cx % 32 == 0:
+    return False
+  return bool(_cabi.lib().exp_conv1_supported(Cx + Cv, Cout))
+
+
+def _enrich32_path(Cx, Cv, Cout):
+  """16 < Cin <= 32 (value network, 17 channels): enrich to 32 channels, pad the weights, then the
+  generic TMA path (exp_conv_enrich32 / exp_conv_pad_weights32)."""
+  if _backend not in (BACKEND_AUTO, BACKEND_TCGEN05_TMA):
+    return False
+  Cin = Cx + Cv
+  return (Cv > 0 or Cx % 32 != 0) and 16 < Cin <= 32 and Cout % 32 == 0
+
+
+def _enrich32(x, vec, shift):
+  B, IH, IW, Cx = x.shape
+  Cv = 0 if vec is None else vec.shape[1]
+  xs = _scratch(x.device, "enrich32", B * IH * IW * 32)[:B * IH * IW * 32].view(B, IH, IW, 32)
+  _cabi.check(_cabi.lib().exp_conv_enrich32(x.data_ptr(), Cx, _p(vec), Cv, float(shift), xs.data_ptr(), B, IH, IW, _stream()),
+              "exp_conv_enrich32")
+  return xs
+
+
+def _conv1_stage(x, vec, shift):
+  B, IH, IW, Cx = x.shape
+  Cv = 0 if vec is None else vec.shape[1]
+  l = _cabi.lib()
+  xp = _scratch(x.device, "conv1_xp", l.exp_conv1_padded_input_elems(B, IH, IW))
+  _cabi.check(l.exp_conv1_pad_input(x.data_ptr(), Cx, _p(vec), Cv, float(shift), xp.data_ptr(), B, IH, IW, _stream()),
+              "exp_conv1_pad_input")
+  return xp
+
+
 def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None, out=None, out2=None):
   """4x4 stride-2 SAME conv over concat(x, tile(vec)) - shift.  Forward (bias + lrelu) or,
   with mask_ref, the forward-mode tangent (no bias, times lrelu'(mask_ref)).
@@ -65,6 +119,26 @@ def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None,
   if post_mul is not None:
     y2 = torch.empty_like(y) if out2 is None else out2
   mode = 0 if mask_ref is None else 1
+  if _conv1_path(Cx, Cv, Cout):
+    l = _cabi.lib()
+    with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+      xp = _conv1_stage(x, vec, shift)
+      Wp = _scratch(x.device, "conv1_wp", 16 * 16 * Cout)
+      _cabi.check(l.exp_conv1_pad_weights(W.data_ptr(), Cx + Cv, Cout, Wp.data_ptr(), _stream()), "exp_conv1_pad_weights")
+      _cabi.check(l.exp_conv1_fwd(xp.data_ptr(), Wp.data_ptr(), _p(bias), _p(mask_ref), _p(post_mul), y.data_ptr(), _p(y2),
+                                  B, IH, IW, Cout, mode, _stream()), "exp_conv1_fwd")
+    _n(3)
+    return y if post_mul is None else (y, y2)
+  if _enrich32_path(Cx, Cv, Cout):
+    l = _cabi.lib()
+    with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+      xs = _enrich32(x, vec, shift)
+      Wp = _scratch(x.device, "wp32", 16 * 32 * Cout)
+      _cabi.check(l.exp_conv_pad_weights32(W.data_ptr(), Cx + Cv, Cout, Wp.data_ptr(), _stream()), "exp_conv_pad_weights32")
+      _cabi.check(l.exp_conv_fwd(xs.data_ptr(), 32, None, 0, 0.0, Wp.data_ptr(), _p(bias), _p(mask_ref), _p(post_mul),
+                                 y.data_ptr(), _p(y2), B, IH, IW, Cout, mode, _stream()), "exp_conv_fwd")
+    _n(3)
+    return y if post_mul is None else (y, y2)
   with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
     _cabi.check(_cabi.lib().exp_conv_fwd(x.data_ptr(), Cx, _p(vec), Cv, float(shift), W.data_ptr(), _p(bias),
                                          _p(mask_ref), _p(post_mul), y.data_ptr(), _p(y2), B, IH, IW, Cout, mode,
@@ -96,6 +170,28 @@ def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False):
   gW = torch.empty(4, 4, Cx + Cv, Cout, device=x.device, dtype=torch.float32) if out is None else out
   assert not accumulate or out is not None
   l = _cabi.lib()
+  if _conv1_path(Cx, Cv, Cout):
+    ws = _workspace(x.device, l.exp_conv1_wgrad_workspace_bytes(B, IH, IW, Cout))
+    with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+      xp = _conv1_stage(x, vec, shift)
+      _cabi.check(l.exp_conv1_wgrad(xp.data_ptr(), dy.data_ptr(), gW.data_ptr(), Cx + Cv, B, IH, IW, Cout, int(accumulate),
+                                    ws.data_ptr(), ws.numel(), _stream()), "exp_conv1_wgrad")
+    _n(3)
+    return gW
+  if _enrich32_path(Cx, Cv, Cout):
+    Cin = Cx + Cv
+    ws = _workspace(x.device, l.exp_conv_wgrad_workspace_bytes(B, IH, IW, 32, Cout))
+    gWp = _scratch(x.device, "gwp32", 16 * 32 * Cout)[:16 * 32 * Cout].view(4, 4, 32, Cout)
+    with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * Cin):
+      xs = _enrich32(x, vec, shift)
+      _cabi.check(l.exp_conv_wgrad(xs.data_ptr(), 32, None, 0, 0.0, dy.data_ptr(), gWp.data_ptr(), B, IH, IW, Cout, 0,
+                                   ws.data_ptr(), ws.numel(), _stream()), "exp_conv_wgrad")
+      if accumulate:
+        gW.add_(gWp[:, :, :Cin, :])
+      else:
+        gW.copy_(gWp[:, :, :Cin, :])
+    _n(4)
+    return gW
   nbytes = l.exp_conv_wgrad_workspace_bytes(B, IH, IW, Cx + Cv, Cout)
   ws = _workspace(x.device, nbytes)
   with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
@@ -306,8 +402,11 @@ def adam(params, grads, m, v, hyper, beta1, beta2, eps=1e-8, grad_scale=1.0):
 
 
 BACKEND_AUTO, BACKEND_CUDA_CORES, BACKEND_TCGEN05, BACKEND_TCGEN05_WS, BACKEND_TCGEN05_TMA = 0, 1, 2, 3, 4
+_backend = int(os.environ.get("EXPOSURE_GEMM_BACKEND") or 0)     # mirrors _cabi.lib()'s initial setting
 
 
 def set_gemm_backend(backend):
   """Process-wide GEMM backend of the conv / FC primitives (exp_set_gemm_backend)."""
+  global _backend
   _cabi.check(_cabi.lib().exp_set_gemm_backend(int(backend)), "exp_set_gemm_backend")
+  _backend = int(backend)

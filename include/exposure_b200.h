@@ -168,6 +168,35 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
                    float* gW, int B, int IH, int IW, int Cout, int accumulate, void* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* First convolution layer on the tensor cores.  Its input is concat(image[3], per-image state
+ * constants) - shift (util.py enrich_image_input, agent.py:17 / critics.py:51) with Cin = 6 / 14 /
+ * 17 channels: not a multiple of 32, so it runs on a STAGING COPY
+ *   xp[B][IH+2][IW+2][16]: zero border (ly.conv2d SAME padding made explicit), channels [0,Cin) =
+ *   enriched input - shift, channels [Cin,16) = 0            (exp_conv1_pad_input)
+ * and zero-padded weights Wp[4][4][16][Cout] (exp_conv1_pad_weights), both consumed by TMA im2col
+ * boxes.  exp_conv1_fwd has the epilogue modes of exp_conv_fwd; exp_conv1_wgrad writes the
+ * UNPADDED gradient gW[4][4][Cin][Cout] (deterministic split-K through `workspace`).
+ * exp_conv1_supported(Cin, Cout) != 0 when this path can be used (Cin <= 16, Cout % 32 == 0). */
+int exp_conv1_supported(int Cin, int Cout);
+size_t exp_conv1_padded_input_elems(int B, int IH, int IW);
+int exp_conv1_pad_input(const float* x, int Cx, const float* vec, int Cv, float shift, float* xp, int B,
+                        int IH, int IW, void* stream);
+int exp_conv1_pad_weights(const float* W, int Cin, int Cout, float* Wp, void* stream);
+int exp_conv1_fwd(const float* xp, const float* Wp, const float* bias, const float* mask_ref,
+                  const float* post_mul, float* y, float* y2, int B, int IH, int IW, int Cout, int mode,
+                  void* stream);
+size_t exp_conv1_wgrad_workspace_bytes(int B, int IH, int IW, int Cout);
+int exp_conv1_wgrad(const float* xp, const float* dy, float* gW, int Cin, int B, int IH, int IW, int Cout,
+                    int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* First layers with 16 < Cin <= 32 (value network: 17 channels): materialise the enriched input
+ * out[B][IH][IW][32] = concat(x, tile(vec)) - shift, zero above Cin (exp_conv_enrich32) and the
+ * weights padded to Wp[4][4][32][Cout] (exp_conv_pad_weights32); exp_conv_fwd / exp_conv_wgrad then
+ * run on them with Cx = 32, Cv = 0, shift = 0 (the TMA-fed tensor-core path). */
+int exp_conv_enrich32(const float* x, int Cx, const float* vec, int Cv, float shift, float* out, int B,
+                      int IH, int IW, void* stream);
+int exp_conv_pad_weights32(const float* W, int Cin, int Cout, float* Wp, void* stream);
+
 /* FC layers take leading dimensions (row strides, in floats) so that several heads can share
  * one activation matrix: element (m,k) of x is x[m*ldx + k], etc.
  * y[M,N] = epi(x[M,K] W[K,N]); mode 0: lrelu(v+bias), 1: v*lrelu'(mask_ref) (tangent),

@@ -76,14 +76,37 @@ def test_tma_conv_fprop_dgrad_wgrad(nn, shape):
   _close(g, gs.double().cpu(), tol=3e-5)
 
 
-def test_tma_first_layer_falls_back_to_cuda_cores(nn):
-  """Cin = 14 (3 image + 11 state channels) is not a multiple of 32: backend 4 must still give
-  the right answer (the call is served by the CUDA-core engine)."""
-  B, IH, Cx, Cv, Cout = 2, 64, 3, 11, 32
+@pytest.mark.parametrize("case", [(3, 64, 3, 3, 32), (5, 64, 3, 11, 32), (2, 64, 3, 14, 32), (2, 32, 3, 11, 64), (67, 8, 5, 4, 32)])
+def test_tma_first_layer_staged(nn, case):
+  """First layers (Cin = 6 / 14 / 17: image + per-image state constants, shift 0.5) run on the tensor
+  cores through a staging copy (zero-bordered 16 channels, or 32 channels for Cin > 16) and padded
+  weights; forward, dropout side output, tangent mode, wgrad (overwrite / accumulate)."""
+  B, IH, Cx, Cv, Cout = case
   x = _rand(B, IH, IH, Cx, seed=1).abs() * 0.3
   vec = _rand(B, Cv, seed=2)
-  W = _rand(4, 4, Cx + Cv, Cout, seed=3, scale=0.1)
+  W = _rand(4, 4, Cx + Cv, Cout, seed=3, scale=0.1).requires_grad_(True)
   b = _rand(Cout, seed=4, scale=0.1)
-  f32 = lambda t: t.float().cuda().contiguous()
-  y = N.lrelu(N.conv4x4s2(N.enrich(x, vec) - 0.5, W, b))
-  _close(nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=0.5), y)
+  f32 = lambda t: t.detach().float().cuda().contiguous()
+  xin = N.enrich(x, vec) - 0.5
+  pre = N.conv4x4s2(xin, W)
+  gy = _rand(*pre.shape, seed=5)
+  (gW,) = torch.autograd.grad(pre, [W], grad_outputs=gy)
+  y = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=0.5)
+  _close(y, N.lrelu(pre.detach() + b))
+  pm = (torch.rand(pre.shape, generator=torch.Generator().manual_seed(9)) < 0.5).float() * 2
+  y1, y2 = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=0.5, post_mul=pm.cuda())
+  assert torch.equal(y1, y) and torch.equal(y2, y * pm.cuda())
+  t_img, t_vec = _rand(B, IH, IH, Cx, seed=7), _rand(B, Cv, seed=8)
+  mask = torch.where(y.double().cpu() > 0, 1.0, torch.where(y.double().cpu() < 0, 0.2, 0.6))
+  _close(nn.conv_fwd(f32(t_img), f32(W), None, vec=f32(t_vec), shift=0.0, mask_ref=y),
+         N.conv4x4s2(N.enrich(t_img, t_vec), W.detach()) * mask)
+  g = nn.conv_wgrad(f32(x), f32(gy), vec=f32(vec), shift=0.5)
+  _close(g, gW)
+  g2 = nn.conv_wgrad(f32(x), f32(gy), vec=f32(vec), shift=0.5, out=g.clone(), accumulate=True)
+  _close(g2, 2 * gW)
+  nn.set_gemm_backend(nn.BACKEND_CUDA_CORES)
+  ys = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=0.5)
+  gs = nn.conv_wgrad(f32(x), f32(gy), vec=f32(vec), shift=0.5)
+  nn.set_gemm_backend(nn.BACKEND_TCGEN05_TMA)
+  _close(y, ys.double().cpu(), tol=3e-5)
+  _close(g, gs.double().cpu(), tol=3e-5)

@@ -382,6 +382,67 @@ static int colsum_chunks(int rows) {
   return c < 1 ? 1 : (c > 512 ? 512 : c);
 }
 
+// ------------------------------------------------------------------------------------------
+// dgrad into a FEW input channels (first layer: Cin = 6 critic / 17 value network; the gradient
+// w.r.t. the image, critics.py:48-87 through tf.gradients).  A 64 x 32 GEMM tile wastes most of
+// its columns on N = 6, and the op is tiny (0.4 GFLOP, 15 MB): one thread per input pixel of a
+// parity class instead, the class's 4 x Cin x Cout weights broadcast from shared memory, the
+// deltas read as float4 over co.
+// ------------------------------------------------------------------------------------------
+template <int CMAX>
+__global__ void __launch_bounds__(256) conv_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                                               const float* __restrict__ a_in, float* __restrict__ dx,
+                                                               int B, int IH, int IW, int Cin, int Cout, int lgW2, int lgHW2) {
+  extern __shared__ float4 w_s4[];                       // [4 taps of the class][Cin][Cout]
+  float* w_s = reinterpret_cast<float*>(w_s4);
+  const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
+  const int OH = IH / 2, OW = IW / 2;
+  int oy_off[4], ox_off[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = t >> 1, l = t & 1;
+    const int ky = py == 0 ? (j == 0 ? 1 : 3) : (j == 0 ? 0 : 2);
+    const int kx = px == 0 ? (l == 0 ? 1 : 3) : (l == 0 ? 0 : 2);
+    oy_off[t] = py == 0 ? (j == 0 ? 0 : -1) : (j == 0 ? 1 : 0);
+    ox_off[t] = px == 0 ? (l == 0 ? 0 : -1) : (l == 0 ? 1 : 0);
+    const float* src = W + (size_t)(ky * 4 + kx) * Cin * Cout;
+    for (int i = threadIdx.x; i < Cin * Cout; i += blockDim.x) w_s[t * Cin * Cout + i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= B * OH * OW) return;
+  const int b = m >> lgHW2, rem = m & ((1 << lgHW2) - 1);
+  const int a = rem >> lgW2, c = rem & (OW - 1);
+  float acc[CMAX];
+#pragma unroll
+  for (int ci = 0; ci < CMAX; ++ci) acc[ci] = 0.f;
+  const int co4n = Cout >> 2;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int oy = a + oy_off[t], ox = c + ox_off[t];
+    if ((unsigned)oy >= (unsigned)OH || (unsigned)ox >= (unsigned)OW) continue;
+    const float4* dp = reinterpret_cast<const float4*>(dy + ((size_t)(b * OH + oy) * OW + ox) * Cout);
+    const float4* wp = w_s4 + (size_t)t * Cin * co4n;
+    for (int q = 0; q < co4n; ++q) {
+      const float4 d = __ldg(dp + q);
+#pragma unroll
+      for (int ci = 0; ci < CMAX; ++ci)
+        if (ci < Cin) {
+          const float4 w = wp[ci * co4n + q];
+          acc[ci] = fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, fmaf(d.w, w.w, acc[ci]))));
+        }
+    }
+  }
+  const size_t base = ((size_t)(b * IH + 2 * a + py) * IW + 2 * c + px) * Cin;
+#pragma unroll
+  for (int ci = 0; ci < CMAX; ++ci)
+    if (ci < Cin) {
+      float o = acc[ci];
+      if (a_in) o *= dlrelu_from_out(__ldg(a_in + base + ci));
+      dx[base + ci] = o;
+    }
+}
+
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 static int host_ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -457,6 +518,16 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
   p.OW = IW / 2; p.Cout = Cout; p.chunks = Cout / kBK;
   p.lgW2 = host_ilog2(IW / 2); p.lgHW2 = host_ilog2((IH / 2) * (IW / 2));
   const int M = B * (IH / 2) * (IW / 2);
+  if (use_tma() && Cin <= 20 && Cout % 4 == 0 && 4 * Cin * Cout * sizeof(float) <= 48 * 1024 && aligned16(dy)) {
+    const dim3 grid((M + 255) / 256, 1, 4);
+    const size_t smem = (size_t)4 * Cin * Cout * sizeof(float);
+    if (Cin <= 8)
+      conv_dgrad_small_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
+    else
+      conv_dgrad_small_kernel<20><<<grid, 256, smem, (cudaStream_t)stream>>>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
+    EXP_CHECK_LAUNCH("exp_conv_dgrad[small]");
+    return EXP_OK;
+  }
   if (use_tma() && tma_conv_dgrad_supported(dy, W, a_in, dx, Cin, Cout)) {
     const cudaError_t e = tma_conv_dgrad(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[tma]: %s", cudaGetErrorString(e));

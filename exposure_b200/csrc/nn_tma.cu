@@ -87,7 +87,7 @@ struct TmaConvFprop {
   int M, Cin, Cout, OW, lgOW, lgOHW, mode, splits;
   int first;   // 1: first layer on the zero-bordered 16-channel staging copy (see exp_conv1_pad_input)
   static constexpr bool kAMn = false, kBMn = true;
-  __device__ int k_iters(int) const { return 16 * Cin / tma::kBK; }
+  __host__ __device__ int k_iters(int) const { return 16 * Cin / tma::kBK; }
   template <int BN>
   __device__ void load(int ki, int, int m0, int n0, unsigned char* a_dst, unsigned char* b_dst, uint64_t* bar) const {
     const int k = ki * tma::kBK;
@@ -164,7 +164,7 @@ struct TmaConvDgrad {
   const float* a_in; float* dx;
   int M, IH, IW, Cin, Cout, lgW2, lgHW2, splits;
   static constexpr bool kAMn = false, kBMn = false;
-  __device__ int k_iters(int) const { return 4 * Cout / tma::kBK; }
+  __host__ __device__ int k_iters(int) const { return 4 * Cout / tma::kBK; }
   template <int BN>
   __device__ void load(int ki, int z, int m0, int n0, unsigned char* a_dst, unsigned char* b_dst, uint64_t* bar) const {
     const int py = z >> 1, px = z & 1;
@@ -233,7 +233,7 @@ struct TmaConvWgrad {
   int Cin, Cout, OW, lgOW, lgOHW, steps_per_split, total_steps, splits;   // splits: cluster split-K, unused (= 1): z already splits K
   int first;   // 1: first layer on the zero-bordered 16-channel staging copy
   static constexpr bool kAMn = true, kBMn = true;
-  __device__ int k_iters(int z) const {
+  __host__ __device__ int k_iters(int z) const {
     const int left = total_steps - z * steps_per_split;
     return left < steps_per_split ? (left > 0 ? left : 0) : steps_per_split;
   }

@@ -78,9 +78,13 @@ __host__ __device__ constexpr uint32_t idesc_tf32_major(int M, int N, bool a_mn,
   return tc::idesc_tf32(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
 }
 
-template <int BN>
+// NS = 0: deepest ring that fits one CTA per SM (3 stages at BN = 128, else 4).  NS = 2: a two-stage ring
+// small enough for two CTAs per SM -- used for multi-wave grids of short CTAs, where the second
+// resident CTA hides the prologue / epilogue of the first (BN <= 64 only).
+template <int BN, int NS_ = 0>
 struct Cfg {
-  static constexpr int kStages = BN >= 128 ? 3 : 4;
+  static constexpr int kStages = NS_ > 0 ? NS_ : (BN >= 128 ? 3 : 4);
+  static constexpr int kCtasPerSm = (NS_ == 2 && BN <= 64) ? 2 : 1;
   static constexpr int kTileB = BN * 128;
   static constexpr int kStageBytes = 2 * kTileA + 2 * kTileB;       // raw + lo for A and B
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024;
@@ -132,10 +136,10 @@ __device__ __forceinline__ float4 dsmem_sum4(uint32_t a) {
 //                                                (exactly kTileA + BN * 128 bytes in total)
 //   void store16(slice, m, n0, v[16])            C[m, n0..n0+15]
 //   void store4(slice, m, n, float4)             C[m, n..n+3]          (cluster split-K epilogue)
-template <class P, int BN>
-__global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_constant__ P p) {
+template <class P, int BN, int NS_ = 0>
+__global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_kernel(const __grid_constant__ P p) {
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN must be 32, 64 or 128");
-  using C = Cfg<BN>;
+  using C = Cfg<BN, NS_>;
   constexpr int NS = C::kStages;
   extern __shared__ __align__(1024) unsigned char tma_smem[];
   __shared__ __align__(8) uint64_t raw_full[NS];
@@ -279,19 +283,17 @@ __global__ void __launch_bounds__(kThreads, 1) tma_gemm_kernel(const __grid_cons
   if (warp == 0) tc::tmem_dealloc(tmem_acc, BN);
 }
 
-template <class P, int BN>
-inline cudaError_t launch_tma_gemm(const P& p, int M, int N, int Z, cudaStream_t st) {
-  constexpr size_t smem = Cfg<BN>::kSmem;
+template <class P, int BN, int NS_>
+inline cudaError_t launch_tma_gemm_ns(const P& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = Cfg<BN, NS_>::kSmem;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tma_gemm_kernel<P, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tma_gemm_kernel<P, BN, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  // Z = slices * p.splits; the p.splits CTAs that share a tile form one cluster along z
-  dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
   if (p.splits <= 1) {
-    tma_gemm_kernel<P, BN><<<grid, kThreads, smem, st>>>(p);
+    tma_gemm_kernel<P, BN, NS_><<<grid, kThreads, smem, st>>>(p);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
@@ -306,7 +308,21 @@ inline cudaError_t launch_tma_gemm(const P& p, int M, int N, int Z, cudaStream_t
   attr.val.clusterDim.z = (unsigned)p.splits;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tma_gemm_kernel<P, BN>, p);
+  return cudaLaunchKernelEx(&cfg, tma_gemm_kernel<P, BN, NS_>, p);
+}
+
+// Z = slices * p.splits; the p.splits CTAs that share a tile form one cluster along z
+template <class P, int BN>
+inline cudaError_t launch_tma_gemm(const P& p, int M, int N, int Z, cudaStream_t st) {
+  const dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
+  if constexpr (BN <= 64) {
+    static const int forced = [] { const char* e = getenv("EXPOSURE_TMA_2CTA"); return e ? atoi(e) : -1; }();   // tuning aid
+    const long ctas = (long)grid.x * grid.y * grid.z;
+    // measured (profiles/r1_layer_bench_tma.md): pays for more than 1.5 waves of CTAs with <= 8 K steps each
+    const bool two = forced >= 0 ? forced != 0 : (ctas > 222 && p.k_iters(0) <= 8 * p.splits);
+    if (two && p.splits <= 1) return launch_tma_gemm_ns<P, BN, 2>(p, grid, st);
+  }
+  return launch_tma_gemm_ns<P, BN, 0>(p, grid, st);
 }
 
 // cluster split-K factor: double while the doubled grid fits the 148 SMs, every CTA keeps >= 4 K

@@ -110,3 +110,20 @@ def test_tma_first_layer_staged(nn, case):
   nn.set_gemm_backend(nn.BACKEND_TCGEN05_TMA)
   _close(y, ys.double().cpu(), tol=3e-5)
   _close(g, gs.double().cpu(), tol=3e-5)
+
+
+@pytest.mark.parametrize("case", [(3, 64, 6, 32), (2, 64, 17, 32), (5, 16, 14, 32), (2, 8, 3, 64), (66, 4, 20, 32)])
+def test_dgrad_into_few_channels(nn, case):
+  """Layer-1 dgrad (gradient w.r.t. the enriched image, Cin = 6 critic / 17 value network) runs on the
+  dedicated thread-per-pixel kernel under the AUTO / TMA backends; exact fp32."""
+  B, IH, Cin, Cout = case
+  W = _rand(4, 4, Cin, Cout, seed=2, scale=0.05)
+  xin = _rand(B, IH, IH, Cin, seed=1).requires_grad_(True)
+  pre = N.conv4x4s2(xin, W)
+  gy = _rand(*pre.shape, seed=4)
+  (gin,) = torch.autograd.grad(pre, [xin], grad_outputs=gy)
+  f32 = lambda t: t.detach().float().cuda().contiguous()
+  _close(nn.conv_dgrad(f32(gy), f32(W), (B, IH, IH, Cin)), gin, tol=2e-6)
+  a_in = _rand(B, IH, IH, Cin, seed=5)
+  d_mask = torch.where(a_in > 0, 1.0, torch.where(a_in < 0, 0.2, 0.6))
+  _close(nn.conv_dgrad(f32(gy), f32(W), (B, IH, IH, Cin), a_in=f32(a_in)), gin * d_mask, tol=2e-6)

@@ -274,7 +274,9 @@ int tma_wgrad_splits(int B, int OH, int OW, int Cin, int Cout) {
   const int steps = (B * OH * OW + tma::kBK - 1) / tma::kBK;
   const int BN = Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32);
   const int tiles = ((16 * Cin + tma::kBM - 1) / tma::kBM) * ((Cout + BN - 1) / BN);
-  int splits = (2 * 148 + tiles - 1) / tiles;                   // ~2 waves of CTAs
+  // ONE wave: a CTA costs ~10 us before its first K step (profiles/r1_tma_gemm_ncu.md), so a second
+  // wave of shorter CTAs is slower than one wave of longer ones
+  int splits = 148 / tiles;
   if (splits > steps / 4) splits = steps / 4;                   // at least 4 K steps per CTA
   if (splits < 1) splits = 1;
   if (splits < 1) splits = 1;

@@ -115,32 +115,44 @@ class ConvStack:
     return c
 
   def backward(self, c, delta4, param_grads=True, accumulate=False, sl=None):
-    """delta4 [N,4,4,256] = dL/d(pre-activation of conv 4).  Fills c.deltas[0..3]."""
+    """delta4 [N,4,4,256] = dL/d(pre-activation of conv 4).  Fills c.deltas[0..3].  The weight / bias
+    gradients of layer i only need delta_i: they are forked onto side streams and overlap the rest of
+    the dgrad chain (parallel branches of the CUDA graph)."""
     d = delta4
     deltas = [None, None, None, d]
+    c.deltas = deltas
     for i in (3, 2, 1):
+      if param_grads:
+        with K.fork(i & 1):
+          self._layer_grads(c, i, accumulate, sl)
       a_in = c.acts[i - 1]
       d = K.conv_dgrad(d, self.W(i), tuple(a_in.shape), a_in=a_in)
       deltas[i - 1] = d
-    c.deltas = deltas
     if param_grads:
-      self.param_grads(c, accumulate=accumulate, sl=sl)
+      with K.fork(0):
+        self._layer_grads(c, 0, accumulate, sl)
+      K.join()
+
+  def _layer_grads(self, c, i, accumulate, sl):
+    s = sl if sl is not None else slice(None)
+    g = self.store.g
+    d = c.deltas[i][s]
+    if i == 0:
+      K.conv_wgrad(c.img[s], d, vec=c.vec[s], shift=0.5, out=g[self.names[0] + "/weights"], accumulate=accumulate)
+    else:
+      K.conv_wgrad(c.acts[i - 1][s], d, out=g[self.names[i] + "/weights"], accumulate=accumulate)
+    gb = g[self.names[i] + "/biases"]
+    if accumulate:
+      gb += K.colsum(d)
+    else:
+      K.colsum(d, out=gb)
 
   def param_grads(self, c, accumulate=False, sl=None):
     """wgrad + bias grads from the samples in `sl` (a slice over the batch; default all)."""
-    s = sl if sl is not None else slice(None)
-    g = self.store.g
     for i in range(4):
-      d = c.deltas[i][s]
-      if i == 0:
-        K.conv_wgrad(c.img[s], d, vec=c.vec[s], shift=0.5, out=g[self.names[0] + "/weights"], accumulate=accumulate)
-      else:
-        K.conv_wgrad(c.acts[i - 1][s], d, out=g[self.names[i] + "/weights"], accumulate=accumulate)
-      gb = g[self.names[i] + "/biases"]
-      if accumulate:
-        gb += K.colsum(d)
-      else:
-        K.colsum(d, out=gb)
+      with K.fork(i & 1):
+        self._layer_grads(c, i, accumulate, sl)
+    K.join()
 
   def input_grad(self, c, sl=None):
     """dL/d(enriched, shifted layer-1 input) [n,64,64,cin] for the samples in sl."""
@@ -162,9 +174,12 @@ class ConvStack:
   def tangent_param_grads(self, c, sl, t_img, t_vec, ts):
     """Accumulate d<u, dD/dx>/dW_k = wgrad(t_{k-1}, delta_k)."""
     g = self.store.g
-    K.conv_wgrad(t_img, c.deltas[0][sl], vec=t_vec, shift=0.0, out=g[self.names[0] + "/weights"], accumulate=True)
+    with K.fork(0):
+      K.conv_wgrad(t_img, c.deltas[0][sl], vec=t_vec, shift=0.0, out=g[self.names[0] + "/weights"], accumulate=True)
     for i in (1, 2, 3):
-      K.conv_wgrad(ts[i - 1], c.deltas[i][sl], out=g[self.names[i] + "/weights"], accumulate=True)
+      with K.fork(i & 1):
+        K.conv_wgrad(ts[i - 1], c.deltas[i][sl], out=g[self.names[i] + "/weights"], accumulate=True)
+    K.join()
 
 
 class CriticNet:
@@ -196,15 +211,22 @@ class CriticNet:
     p = self.store.p
     c.d_fc2 = g_logit.reshape(-1, 1).contiguous()
     c.d_h = K.fc_dgrad(c.d_fc2, p[self.fc2 + "/weights"], mul_act=c.h)
-    d4 = K.fc_dgrad(c.d_h, p[self.fc1 + "/weights"], mul_act=c.feat)
-    self.conv.backward(c, d4.view(-1, 4, 4, CONV_CH[3]), param_grads=False)
     if param_grads:
-      self.param_grads(c, accumulate=accumulate, sl=sl)
+      with K.fork(2):
+        self._fc_grads(c, accumulate, sl)
+    d4 = K.fc_dgrad(c.d_h, p[self.fc1 + "/weights"], mul_act=c.feat)
+    self.conv.backward(c, d4.view(-1, 4, 4, CONV_CH[3]), param_grads=param_grads, accumulate=accumulate, sl=sl)
+    K.join()
 
   def param_grads(self, c, accumulate=False, sl=None):
+    with K.fork(2):
+      self._fc_grads(c, accumulate, sl)
+    self.conv.param_grads(c, accumulate=accumulate, sl=sl)
+    K.join()
+
+  def _fc_grads(self, c, accumulate, sl):
     s = sl if sl is not None else slice(None)
     g = self.store.g
-    self.conv.param_grads(c, accumulate=accumulate, sl=sl)
     K.fc_wgrad(c.feat[s], c.d_h[s], out=g[self.fc1 + "/weights"], accumulate=accumulate)
     K.fc_wgrad(c.h[s], c.d_fc2[s], out=g[self.fc2 + "/weights"], accumulate=accumulate)
     for name, d in ((self.fc1, c.d_h[s]), (self.fc2, c.d_fc2[s])):
@@ -235,9 +257,11 @@ class CriticNet:
     ts = self.conv.tangent(c, sl, u, dstat)
     t4 = ts[3].view(ts[3].shape[0], -1)
     th = K.fc_fwd(t4, p[self.fc1 + "/weights"], None, mode=K.FC_TANGENT, mask_ref=c.h[sl])
+    with K.fork(2):
+      K.fc_wgrad(t4, c.d_h[sl], out=g[self.fc1 + "/weights"], accumulate=True)
+      K.fc_wgrad(th, c.d_fc2[sl], out=g[self.fc2 + "/weights"], accumulate=True)
     self.conv.tangent_param_grads(c, sl, u, dstat, ts)
-    K.fc_wgrad(t4, c.d_h[sl], out=g[self.fc1 + "/weights"], accumulate=True)
-    K.fc_wgrad(th, c.d_fc2[sl], out=g[self.fc2 + "/weights"], accumulate=True)
+    K.join()
 
 
 class PolicyNet:
@@ -306,6 +330,8 @@ class PolicyNet:
     here), g_surrogate / g_penalty [B].  Fills the generator gradients (overwrite)."""
     p, g = self.store.p, self.store.g
     B = c.img.shape[0]
+    with K.fork(3):                      # the selector tower is independent of the filter-head tower
+      self._selector_backward(c, g_surrogate, g_penalty)
     g_img = K.overexposure_bwd(c.out, g_penalty, g_in=g_out)
     _, g_params = F.filter_bwd(c.img, g_img, c.params, c.ids, need_gx=False)
     g_logits_sel = F.filter_regress_bwd(c.logits_sel, g_params, c.ids)           # [B,24]
@@ -326,7 +352,11 @@ class PolicyNet:
     a4f = c.f.acts[3].view(B, -1)
     d4 = K.fc_dgrad(d_H, p[self.fc1_all + "/weights"], mul_act=a4f, mul_plain=c.drop_f.view(B, -1))
     self.fe.backward(c.f, d4.view(B, 4, 4, CONV_CH[3]))
-    # selector
+    K.join()
+
+  def _selector_backward(self, c, g_surrogate, g_penalty):
+    p, g = self.store.p, self.store.g
+    B = c.img.shape[0]
     g_sel = K.policy_head_bwd(c.sel_logits, c.ids, g_surrogate, g_penalty, c.progress, c.cfg)
     K.fc_wgrad(c.hs, g_sel, out=g[self.sfc2 + "/weights"])
     K.colsum(g_sel, out=g[self.sfc2 + "/biases"])

@@ -4,6 +4,7 @@ Plumbing only: device pointers, current stream, output allocation.  See
 include/exposure_b200.h for the semantics of every call.  2-D operands may be column
 slices of a wider matrix (unit inner stride); their row stride is passed as the leading
 dimension."""
+import contextlib
 import os
 
 import torch
@@ -43,6 +44,44 @@ def _scratch(dev, tag, numel):
 
 def _p(t):
   return None if t is None else t.data_ptr()
+
+
+# ---- parallel branches ------------------------------------------------------------------
+# `with fork(i): ...` runs the block on side stream i, ordered after everything queued so far on the
+# current stream; `join()` makes the current stream wait for the blocks it forked.  Under CUDA-graph
+# capture this turns independent work (weight / bias gradients vs. the dgrad chain, the two towers of
+# the policy network) into parallel graph branches, which matters because most kernels of the train
+# step are single-wave and 15-20 us long.  Discipline (keeps the caching allocator safe without
+# record_stream): a forked block only reads tensors that stay alive until the join, and every block
+# starts with wait_stream(parent).  EXPOSURE_FORK=0 serialises everything (A/B switch).
+FORK_ENABLED = os.environ.get("EXPOSURE_FORK", "1") != "0"
+_side_streams = {}
+_pending = {}
+
+
+@contextlib.contextmanager
+def fork(idx=0):
+  if not FORK_ENABLED:
+    yield
+    return
+  parent = torch.cuda.current_stream()
+  key = (parent.device, idx)
+  side = _side_streams.get(key)
+  if side is None:
+    side = _side_streams[key] = torch.cuda.Stream(device=parent.device)
+  if side.cuda_stream == parent.cuda_stream:          # already on that side stream: run inline
+    yield
+    return
+  side.wait_stream(parent)
+  with torch.cuda.stream(side):
+    yield
+  _pending.setdefault(parent.cuda_stream, []).append(side)
+
+
+def join():
+  cur = torch.cuda.current_stream()
+  for side in _pending.pop(cur.cuda_stream, []):
+    cur.wait_stream(side)
 
 
 def _chk(t, name, dims=None):

@@ -143,11 +143,15 @@ class Trainer:
     return self._generator_impl(fake_input, states, noise, drop_f, drop_s, prog, is_train, apply)
 
   def _generator_impl(self, fake_input, states, noise, drop_f, drop_s, progress, is_train, apply):
+    # the two passes over the INPUT batch do not depend on the policy: parallel graph branches
+    with K.fork(4):
+      cc_in = self.critic.forward(fake_input)                    # fake_input_logit (stop_gradient) net.py:72-73
+    with K.fork(5):
+      v_old = self.value.forward(fake_input, states)             # old_value             net.py:79-84
     c = self.policy.forward(fake_input, states, noise, drop_f, drop_s, is_train, progress, self.cfg)
     cc_out = self.critic.forward(c.out)                          # fake_logit            net.py:70-71
-    cc_in = self.critic.forward(fake_input)                      # fake_input_logit (stop_gradient) net.py:72-73
-    v_old = self.value.forward(fake_input, states)               # old_value             net.py:79-84
     v_new = self.value.forward(c.out, c.new_states)              # new_value             net.py:85-90
+    K.join()
     seeds, losses = K.rl_losses(cc_out.logit.view(-1), cc_in.logit.view(-1), v_old.logit.view(-1),
                                 v_new.logit.view(-1), c.penalty, c.surrogate, c.new_states, self.cfg)
     # theta_v: v_loss = mean(advantage^2), advantage = stop_gradient(q) - old_value

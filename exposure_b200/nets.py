@@ -257,6 +257,7 @@ class CriticNet:
     ts = self.conv.tangent(c, sl, u, dstat)
     t4 = ts[3].view(ts[3].shape[0], -1)
     th = K.fc_fwd(t4, p[self.fc1 + "/weights"], None, mode=K.FC_TANGENT, mask_ref=c.h[sl])
+    c.gp_keep = (ts, t4, th, dstat, u)       # read by forked blocks: alive until the caller's join
     with K.fork(2):
       K.fc_wgrad(t4, c.d_h[sl], out=g[self.fc1 + "/weights"], accumulate=True)
       K.fc_wgrad(th, c.d_fc2[sl], out=g[self.fc2 + "/weights"], accumulate=True)

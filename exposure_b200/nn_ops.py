@@ -78,10 +78,32 @@ def fork(idx=0):
   _pending.setdefault(parent.cuda_stream, []).append(side)
 
 
+_deferred = set()
+
+
 def join():
   cur = torch.cuda.current_stream()
+  if cur.cuda_stream in _deferred:
+    return
   for side in _pending.pop(cur.cuda_stream, []):
     cur.wait_stream(side)
+
+
+@contextlib.contextmanager
+def deferred_join():
+  """Inside the block, join() on the CURRENT stream is postponed to the end of the block, so forked
+  work keeps overlapping whatever the current stream does next.  Only safe when later forks that touch
+  the same outputs go to the same side stream (nets.py sends layer i to stream i & 1 every time) and
+  every tensor a forked block reads stays alive until the block ends."""
+  cur = torch.cuda.current_stream()
+  nested = cur.cuda_stream in _deferred
+  _deferred.add(cur.cuda_stream)
+  try:
+    yield
+  finally:
+    if not nested:
+      _deferred.discard(cur.cuda_stream)
+      join()
 
 
 def _chk(t, name, dims=None):

@@ -155,12 +155,17 @@ class Trainer:
     seeds, losses = K.rl_losses(cc_out.logit.view(-1), cc_in.logit.view(-1), v_old.logit.view(-1),
                                 v_new.logit.view(-1), c.penalty, c.surrogate, c.new_states, self.cfg)
     # theta_v: v_loss = mean(advantage^2), advantage = stop_gradient(q) - old_value
-    self.value.backward(v_old, seeds[2], param_grads=True)
-    # theta_g: pathwise gradient through critic(fake_output) and value(fake_output, new_states)
+    with K.fork(4):
+      self.value.backward(v_old, seeds[2], param_grads=True)
+    # theta_g: pathwise gradient through critic(fake_output) and value(fake_output, new_states):
+    # two independent backward passes, parallel graph branches
+    with K.fork(5):
+      self.value.backward(v_new, seeds[1], param_grads=False)
+      g_img_v = self.value.image_grad(v_new)
     self.critic.backward(cc_out, seeds[0], param_grads=False)
     g_img = self.critic.image_grad(cc_out)
-    self.value.backward(v_new, seeds[1], param_grads=False)
-    g_img = g_img + self.value.image_grad(v_new)
+    K.join()
+    g_img = g_img + g_img_v
     self.policy.backward(c, g_img, seeds[4], seeds[3])
     if apply:
       self._adam(self.gen, "g")
@@ -194,12 +199,16 @@ class Trainer:
     g_logit[:B] = -1.0 / B
     g_logit[B:2 * B] = 1.0 / B
     g_logit[2 * B:] = 1.0
-    self.critic.backward(c, g_logit, param_grads=True, sl=slice(0, 2 * B))
-    sl = slice(2 * B, 3 * B)
-    g = self.critic.image_grad(c, sl)                            # d inte_logit / d interpolated  net.py:181-183
-    u, norm = K.gp_scale(g, lam)                                 # d GP / d gradients             net.py:185-187
-    if lam > 0:
-      self.critic.gradient_penalty_grads(c, sl, u)
+    # the weight / bias gradients forked inside backward() keep running on their side streams while
+    # the gradient-penalty chain (image gradient -> tangent pass) proceeds; the penalty's own wgrads
+    # go to the same side stream per layer, so the accumulation order is fixed
+    with K.deferred_join():
+      self.critic.backward(c, g_logit, param_grads=True, sl=slice(0, 2 * B))
+      sl = slice(2 * B, 3 * B)
+      g = self.critic.image_grad(c, sl)                          # d inte_logit / d interpolated  net.py:181-183
+      u, norm = K.gp_scale(g, lam)                               # d GP / d gradients             net.py:185-187
+      if lam > 0:
+        self.critic.gradient_penalty_grads(c, sl, u)
     logit = c.logit.view(-1)
     emd = logit[:B].mean() - logit[B:2 * B].mean()               # net.py:164  emd = -c_loss (before GP)
     gp = lam * (torch.clamp(norm - 1.0, min=0.0) ** 2).mean()

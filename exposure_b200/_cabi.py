@@ -59,6 +59,7 @@ SIGNATURES = {
     "exp_conv_enrich32": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, ctypes.c_float, _c_void_p, _c_int, _c_int, _c_int,
                                    _c_void_p]),
     "exp_conv_pad_weights32": (_c_int, [_c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
+    "exp_crc32c": (ctypes.c_uint32, [ctypes.c_uint32, _c_void_p, _c_size_t]),
     "exp_colsum_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "exp_colsum": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "exp_stats_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),

@@ -274,6 +274,13 @@ int exp_gp_scale(const float* g, float* u, float* norm, float lambda, int B, int
 int exp_adam(float* params, const float* grads, float* m, float* v, const float* hyper, float beta1,
              float beta2, float eps, float grad_scale, size_t n, void* stream);
 
+/* ======================================================================================
+ * Host-side helper (no device work): CRC-32C of `n` bytes, continuing from `crc` (0 to start).
+ * The checksum of TensorFlow checkpoint bundles (table blocks, BundleEntryProto.crc32c), used by
+ * exposure_b200/tf_bundle.py to write / verify files tf.train.Saver can restore (net.py:271,405).
+ * ==================================================================================== */
+unsigned int exp_crc32c(unsigned int crc, const void* data, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

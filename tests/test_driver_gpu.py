@@ -1,0 +1,61 @@
+"""GAN driver mirror (exposure_b200/net.py == net.py:18-877): a short training run, checkpoint
+round trip through the TF-bundle writer / reader, and the reference-signature callables
+cfg.generator / cfg.critic (agent.py:41, critics.py:42)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+def test_gan_train_save_restore_eval(built_lib, tmp_path, monkeypatch):
+  monkeypatch.chdir(tmp_path)
+  from exposure_b200.net import GAN
+  from exposure_b200.trainer import default_cfg
+  from exposure_b200 import tf_bundle
+  cfg = default_cfg()
+  cfg.name = "t"
+  cfg.batch_size = 16
+  cfg.replay_memory_size = 32
+  cfg.max_iter_step = 3
+  cfg.critic_initialization = 0
+  gan = GAN(cfg, seed=3)
+  t = gan.trainer
+  # keep iteration 0 short: the reference does 100 + 100 warm-up steps there (net.py:312-322);
+  # at least test_steps generator steps are needed before the pool holds terminated records
+  orig = t.train_iteration
+  t.train_iteration = lambda it, **kw: orig(it, giters=14 if it == 0 else 1, citers=2)
+  gan.train(graphs=False, log_every=1, save_every=2)
+  assert len(gan.log) == 4 and all(np.isfinite(float(l.split("g_loss=")[1].split(",")[0])) for l in gan.log)
+  prefix = os.path.join("models", "t", "model.ckpt-2")
+  assert os.path.exists(prefix + ".index") and os.path.exists(prefix + ".data-00000-of-00001")
+  assert tf_bundle.verify_bundle(prefix) == 240                       # same variable count as the shipped checkpoint
+  names = set(tf_bundle.read_index(prefix))
+  assert {"generator/Conv/weights", "generator/filter_7/fc2/weights", "critic/fully_connected_1/biases",
+          "OptimizeLoss/rl_value/critic/Conv/weights/Adam_1", "OptimizeLoss_1/beta1_power", "Variable_2"} <= names
+  gan.save(99)
+  snap = [s.flat.clone() for s in (t.gen, t.val, t.cri)] + [s.m.clone() for s in (t.gen, t.val, t.cri)]
+  counters = (t.counter_g, t.counter_v, t.counter_c)
+  gan2 = GAN(cfg, restore=True, seed=5)
+  gan2.restore(99)
+  t2 = gan2.trainer
+  for a, b in zip(snap, [s.flat for s in (t2.gen, t2.val, t2.cri)] + [s.m for s in (t2.gen, t2.val, t2.cri)]):
+    assert torch.equal(a, b)
+  assert (t2.counter_g, t2.counter_v, t2.counter_c) == counters
+  # reference-signature callables
+  B = 4
+  img = torch.rand(B, 64, 64, 3, device=t.device) * 0.2
+  z = torch.rand(B, cfg.z_dim, device=t.device)
+  states = torch.zeros(B, cfg.num_state_dim, device=t.device)
+  (net, new_states, surrogate, penalty), info, _ = cfg.generator(inp=[img, z, states], is_train=0, progress=0.5, cfg=cfg)
+  assert net.shape == (B, 64, 64, 3) and new_states.shape == (B, 11) and surrogate.shape == (B, 1) and penalty.shape == (B, 1)
+  assert info["selected_filter_id"].shape == (B,)
+  logit, _, _ = cfg.critic(images=net, cfg=cfg)
+  assert logit.shape == (B, 1) and torch.isfinite(logit).all()
+  value, _, _ = cfg.value(images=net, cfg=cfg, states=new_states)
+  assert value.shape == (B, 1)
+  hi = torch.rand(B, 96, 128, 3, device=t.device) * 0.2
+  (net_h, _, hr), _, _ = cfg.generator(inp=[img, z, states], is_train=0, progress=0.5, cfg=cfg, high_res=hi)
+  assert hr.shape == hi.shape

@@ -46,3 +46,37 @@ def test_pretrained_policy_brightens_dark_raw_first():
                                                            ones * 2 * 0.5 * 2, ones * 2 * 0.5 * 2, 0, 0.0, cfg)
   assert ids.tolist() == [0, 0], (ids, pdf)                                # Exposure
   assert float(out.mean()) > 2 * float(img.mean())                         # ~ +1.4 .. +2 EV
+
+
+def test_bundle_writer_checksums_match_the_shipped_checkpoint():
+  """CRC-32C + TF's mask reproduce the checksums TF 1.6 stored in the reference's own checkpoint
+  (golden bytes extracted by tests/golden/make_bundle_golden.py), and the header / footer layout the
+  writer emits is the one found there."""
+  import os
+  import struct
+  import numpy as np
+  from exposure_b200 import tf_bundle as tb
+  g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bundle_golden.npz"))
+  assert tb.crc32c(b"123456789") == 0xE3069283                       # CRC-32C check value
+  assert tb._mask_crc(tb.crc32c(g["block"].tobytes())) == int(g["block_crc"])
+  assert tb._mask_crc(tb.crc32c(g["tensor"].tobytes())) == int(g["tensor_crc"])
+  assert bytes(g["header"]) == tb._field(1, 0, tb._put_varint(1)) + tb._field(3, 2, tb._put_varint(2) + tb._field(1, 0, tb._put_varint(1)))
+  assert struct.unpack_from("<Q", bytes(g["footer"]), 40)[0] == tb._MAGIC
+
+
+def test_bundle_write_read_round_trip(tmp_path):
+  import numpy as np
+  from exposure_b200 import tf_bundle as tb
+  rng = np.random.default_rng(0)
+  t = {"generator/Conv/weights": rng.standard_normal((4, 4, 14, 32)).astype(np.float32),
+       "generator/Conv/biases": np.zeros(32, np.float32), "Variable": np.int32(20099).reshape(()),
+       "OptimizeLoss/beta1_power": np.float32(0.5 ** 7).reshape(())}
+  for i in range(300):                                                # several table blocks
+    t["pad/%03d/Adam_1" % i] = rng.standard_normal((i % 5 + 1, 3)).astype(np.float32)
+  p = str(tmp_path / "model.ckpt-1")
+  tb.save_bundle(p, t)
+  assert tb.verify_bundle(p) == len(t)
+  back = tb.load_bundle(p, include_optimizer_slots=True)
+  assert set(back) == set(t)
+  for k in t:
+    assert back[k].shape == np.asarray(t[k]).shape and back[k].dtype == np.asarray(t[k]).dtype and np.array_equal(back[k], t[k])

@@ -19,7 +19,7 @@
 
 #include "common.cuh"
 #include "nn_tc.h"
-#include "tc_engine_tma.cuh"
+#include "tc_engine_tma_persistent.cuh"
 
 namespace expo {
 
@@ -148,14 +148,14 @@ cudaError_t tma_conv_fwd(const float* x, int Cx, const float* W, const float* bi
   const int mt = (p.M + tma::kBM - 1) / tma::kBM, ki = 16 * Cx / tma::kBK;
   if (Cout % 128 == 0) {
     p.splits = tma::pick_splits(mt * (Cout / 128), ki, 128);
-    return tma::launch_tma_gemm<TmaConvFprop, 128>(p, p.M, Cout, p.splits, st);
+    return tma::launch_tma_auto<TmaConvFprop, 128>(p, p.M, Cout, p.splits, st);
   }
   if (Cout % 64 == 0) {
     p.splits = tma::pick_splits(mt * (Cout / 64), ki, 64);
-    return tma::launch_tma_gemm<TmaConvFprop, 64>(p, p.M, Cout, p.splits, st);
+    return tma::launch_tma_auto<TmaConvFprop, 64>(p, p.M, Cout, p.splits, st);
   }
   p.splits = tma::pick_splits(mt * (Cout / 32), ki, 32);
-  return tma::launch_tma_gemm<TmaConvFprop, 32>(p, p.M, Cout, p.splits, st);
+  return tma::launch_tma_auto<TmaConvFprop, 32>(p, p.M, Cout, p.splits, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -221,9 +221,9 @@ cudaError_t tma_conv_dgrad(const float* dy, const float* W, const float* a_in, f
   p.a_in = a_in; p.dx = dx; p.M = B * OH * OW; p.IH = IH; p.IW = IW; p.Cin = Cin; p.Cout = Cout;
   p.lgW2 = ilog2(OW); p.lgHW2 = ilog2(OH * OW);
   p.splits = tma::pick_splits(4 * ((p.M + tma::kBM - 1) / tma::kBM) * ((N + BN - 1) / BN), 4 * Cout / tma::kBK, BN);
-  if (BN == 128) return tma::launch_tma_gemm<TmaConvDgrad, 128>(p, p.M, N, 4 * p.splits, st);
-  if (BN == 64) return tma::launch_tma_gemm<TmaConvDgrad, 64>(p, p.M, N, 4 * p.splits, st);
-  return tma::launch_tma_gemm<TmaConvDgrad, 32>(p, p.M, N, 4 * p.splits, st);
+  if (BN == 128) return tma::launch_tma_auto<TmaConvDgrad, 128>(p, p.M, N, 4 * p.splits, st);
+  if (BN == 64) return tma::launch_tma_auto<TmaConvDgrad, 64>(p, p.M, N, 4 * p.splits, st);
+  return tma::launch_tma_auto<TmaConvDgrad, 32>(p, p.M, N, 4 * p.splits, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -298,9 +298,9 @@ cudaError_t tma_conv_wgrad_partials(const float* x, int Cx, const float* dy, flo
   p.splits = 1;
   p.steps_per_split = (p.total_steps + splits - 1) / splits;
   const int M = 16 * Cx;
-  if (Cout % 128 == 0) return tma::launch_tma_gemm<TmaConvWgrad, 128>(p, M, Cout, splits, st);
-  if (Cout % 64 == 0) return tma::launch_tma_gemm<TmaConvWgrad, 64>(p, M, Cout, splits, st);
-  return tma::launch_tma_gemm<TmaConvWgrad, 32>(p, M, Cout, splits, st);
+  if (Cout % 128 == 0) return tma::launch_tma_auto<TmaConvWgrad, 128>(p, M, Cout, splits, st);
+  if (Cout % 64 == 0) return tma::launch_tma_auto<TmaConvWgrad, 64>(p, M, Cout, splits, st);
+  return tma::launch_tma_auto<TmaConvWgrad, 32>(p, M, Cout, splits, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -454,13 +454,13 @@ int exp_conv1_fwd(const float* xp, const float* Wp, const float* bias, const flo
   cudaError_t e;
   if (Cout % 128 == 0) {
     p.splits = tma::pick_splits(mt * (Cout / 128), ki, 128);
-    e = tma::launch_tma_gemm<TmaConvFprop, 128>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
+    e = tma::launch_tma_auto<TmaConvFprop, 128>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
   } else if (Cout % 64 == 0) {
     p.splits = tma::pick_splits(mt * (Cout / 64), ki, 64);
-    e = tma::launch_tma_gemm<TmaConvFprop, 64>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
+    e = tma::launch_tma_auto<TmaConvFprop, 64>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
   } else {
     p.splits = tma::pick_splits(mt * (Cout / 32), ki, 32);
-    e = tma::launch_tma_gemm<TmaConvFprop, 32>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
+    e = tma::launch_tma_auto<TmaConvFprop, 32>(p, p.M, Cout, p.splits, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv1_fwd: %s", cudaGetErrorString(e));
   return EXP_OK;
@@ -496,9 +496,9 @@ int exp_conv1_wgrad(const float* xp, const float* dy, float* gW, int Cin, int B,
   p.steps_per_split = (p.total_steps + splits - 1) / splits;
   const int M = 16 * kC1;
   cudaError_t e;
-  if (Cout % 128 == 0) e = tma::launch_tma_gemm<TmaConvWgrad, 128>(p, M, Cout, splits, (cudaStream_t)stream);
-  else if (Cout % 64 == 0) e = tma::launch_tma_gemm<TmaConvWgrad, 64>(p, M, Cout, splits, (cudaStream_t)stream);
-  else e = tma::launch_tma_gemm<TmaConvWgrad, 32>(p, M, Cout, splits, (cudaStream_t)stream);
+  if (Cout % 128 == 0) e = tma::launch_tma_auto<TmaConvWgrad, 128>(p, M, Cout, splits, (cudaStream_t)stream);
+  else if (Cout % 64 == 0) e = tma::launch_tma_auto<TmaConvWgrad, 64>(p, M, Cout, splits, (cudaStream_t)stream);
+  else e = tma::launch_tma_auto<TmaConvWgrad, 32>(p, M, Cout, splits, (cudaStream_t)stream);
   if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv1_wgrad: %s", cudaGetErrorString(e));
   const int n = 16 * Cin * Cout;
   conv1_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p.part, splits, Cin, Cout, gW, accumulate);

@@ -11,7 +11,9 @@ LIB_PATH = os.path.join(HERE, "_lib", "libexposure_b200.so")
 EXP_OK = 0
 VARIANT_AUTO, VARIANT_DIRECT, VARIANT_TMA, VARIANT_SCALAR = 0, 1, 2, 3
 MAX_FILTER_PARAMS = 24
-NUM_FILTERS = 8
+NUM_FILTERS = 8          # shipped cfg.filters (= number of actions)
+NUM_FILTER_KINDS = 10    # + LevelFilter (8), VignetFilter (9)
+MASK_PARAMS = 6
 
 
 class ExposureLibError(RuntimeError):
@@ -32,6 +34,11 @@ SIGNATURES = {
     "exp_filter_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "exp_filter_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
                                 _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_int, _c_void_p]),
+    "exp_filter_masked_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p,
+                                       _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_int, _c_void_p]),
+    "exp_filter_masked_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
+                                       _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                       _c_int, _c_void_p, _c_size_t, _c_int, _c_void_p]),
     "exp_set_gemm_backend": (_c_int, [_c_int]),
     "exp_conv_fwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, ctypes.c_float, _c_void_p, _c_void_p, _c_void_p,
                               _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

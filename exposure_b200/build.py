@@ -17,8 +17,9 @@ STAMP = os.path.join(OUT_DIR, "build.stamp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
+OBJ_DIR = os.path.join(OUT_DIR, "obj")
 
 
 def _sources():
@@ -45,13 +46,27 @@ def build_lib(force=False, verbose=False):
       if fh.read().strip() == digest:
         return LIB_PATH
   nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-  cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
-  res = subprocess.run(cmd, capture_output=True, text=True)
+  os.makedirs(OBJ_DIR, exist_ok=True)
+  # one translation unit per .cu, compiled concurrently (nvcc is single-threaded per file), then linked
+  jobs = []
+  for src in _sources():
+    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    jobs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+  failed = False
+  for src, obj, proc in jobs:
+    out, _ = proc.communicate()
+    if proc.returncode != 0:
+      failed = True
+      sys.stderr.write(out)
+    elif verbose:
+      sys.stderr.write(out)
+  if failed:
+    raise RuntimeError("nvcc failed building %s" % LIB_PATH)
+  res = subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + [j[1] for j in jobs], capture_output=True, text=True)
   if res.returncode != 0:
     sys.stderr.write(res.stdout + res.stderr)
-    raise RuntimeError("nvcc failed building %s" % LIB_PATH)
-  if verbose:
-    sys.stderr.write(res.stderr)
+    raise RuntimeError("nvcc failed linking %s" % LIB_PATH)
   with open(STAMP, "w") as fh:
     fh.write(digest)
   return LIB_PATH

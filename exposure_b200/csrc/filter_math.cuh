@@ -9,7 +9,9 @@
 // intrinsics in the reference's op order so that ptxas cannot contract them into FMAs and
 // the result tracks the fp32 restatement to ~1 ulp.  Everything else may use FMA.
 #pragma once
+#ifndef EXPO_HOST_MATH   // tests/host_math/px_harness.cpp compiles this header for the host
 #include "common.cuh"
+#endif
 
 namespace expo {
 
@@ -21,11 +23,11 @@ constexpr float kLumR = 0.27f, kLumG = 0.67f, kLumB = 0.06f;   // util.py:271-27
 constexpr int kAccStride = 32;              // floats per partial-sum record
 
 __host__ __device__ constexpr int num_params(int fid) {
-  return fid == EXP_FILTER_WB ? 3 : fid == EXP_FILTER_TONE ? 8 : fid == EXP_FILTER_COLOR ? 24 : 1;
+  return fid == EXP_FILTER_WB ? 3 : fid == EXP_FILTER_TONE ? 8 : fid == EXP_FILTER_COLOR ? 24 : fid == EXP_FILTER_LEVEL ? 2 : 1;
 }
 // number of per-thread accumulators the backward of filter `fid` carries
 __host__ __device__ constexpr int num_acc(int fid) {
-  return fid == EXP_FILTER_WB ? 3 : fid == EXP_FILTER_TONE ? 9 : fid == EXP_FILTER_COLOR ? 27 : 1;
+  return fid == EXP_FILTER_WB ? 3 : fid == EXP_FILTER_TONE ? 8 : fid == EXP_FILTER_COLOR ? 24 : fid == EXP_FILTER_LEVEL ? 2 : 1;
 }
 
 // Per-image constants, built once per CTA in shared memory from params[b, :].
@@ -34,7 +36,11 @@ struct __align__(16) FilterConsts {
   float cum[3][kCurveSteps + 1];    // curve prefix sums  sum_{i<k} t_i / L   (T uses row 0)
   float scale[3];                   // L / (sum_i t_i + 1e-30)
   float S[3];                       // sum_i t_i + 1e-30
-  float e;                          // Exposure: exp(p * ln2)
+  // backward slope lookup, index = (k+1) + (L x == k ? 10 : 0) with k = clamp(floor(L x), -1, L):
+  //   [0..9]   = {0, t_0 .. t_7, 0} L/S            x strictly inside segment k (0 outside [0,1])
+  //   [10..19] = {0, t_0, t_0+t_1, .., t_6+t_7, t_7} L/S   x exactly on knot k (TF tie rule)
+  float slope[3][2 * (kCurveSteps + 2)];
+  float e;                          // Exposure: exp(p * ln2) ; Level: upper - lower + 1e-6
   float raw[EXP_MAX_FILTER_PARAMS]; // raw regressor logits (EXP_OPT_LOGITS mode only)
 };
 
@@ -83,10 +89,17 @@ __device__ __forceinline__ void regress_image(int fid, const float* f, float* po
       }
     } break;
     case EXP_FILTER_SATPLUS:
-    case EXP_FILTER_WNB: {
+    case EXP_FILTER_WNB:
+    case EXP_FILTER_VIGNET: {                        // filters.py:481-482, 435-436, 348-349
       const float p = sigmoid_f(f[0], &d);
       if (BWD) gf[0] = gp[0] * d; else po[0] = p;
     } break;
+    case EXP_FILTER_LEVEL:                           // filters.py:456-457
+      for (int i = 0; i < 2; ++i) {
+        const float p = sigmoid_f(f[i], &d);
+        if (BWD) gf[i] = gp[i] * d; else po[i] = p;
+      }
+      break;
     case EXP_FILTER_CONTRAST: {
       const float a = tanhf(f[0]);
       if (BWD) gf[0] = gp[0] * (1.f - a * a); else po[0] = a;
@@ -121,7 +134,12 @@ __device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __re
     if (t < EXP_MAX_FILTER_PARAMS) sc.p[t] = (t < n) ? prow[t] : 0.f;
   }
   __syncwarp();
-  if (t == 0) sc.e = expf(sc.p[0] * kLn2);                        // filters.py:182
+  if (t == 0) {
+    if (fid == EXP_FILTER_LEVEL)                                  // filters.py:460-464: upper = p1 + 1
+      sc.e = __fadd_rn(__fsub_rn(__fadd_rn(sc.p[1], 1.f), sc.p[0]), 1e-6f);
+    else
+      sc.e = expf(sc.p[0] * kLn2);                                // filters.py:182
+  }
   if (t < 3) {                                                    // filters.py:264-273 / 312-322
     float cum = 0.f, sum = 0.f;
     sc.cum[t][0] = 0.f;
@@ -134,7 +152,16 @@ __device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __re
     }
     const float S = __fadd_rn(sum, 1e-30f);
     sc.S[t] = S;
-    sc.scale[t] = __fdiv_rn((float)kCurveSteps, S);
+    const float scale = __fdiv_rn((float)kCurveSteps, S);
+    sc.scale[t] = scale;
+    sc.slope[t][0] = sc.slope[t][kCurveSteps + 1] = sc.slope[t][kCurveSteps + 2] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kCurveSteps; ++i) {
+      const float ti = sc.p[t * kCurveSteps + i];
+      sc.slope[t][i + 1] = ti * scale;
+      sc.slope[t][kCurveSteps + 3 + i] = (i ? ti + sc.p[t * kCurveSteps + i - 1] : ti) * scale;
+    }
+    sc.slope[t][2 * kCurveSteps + 3] = sc.p[t * kCurveSteps + kCurveSteps - 1] * scale;
   }
 }
 
@@ -223,6 +250,13 @@ __device__ __forceinline__ void px_fwd(const float (&x)[3], float (&y)[3], const
       const float ci = __fmul_rn(__fdiv_rn(x[c], den), cl);
       y[c] = __fadd_rn(__fmul_rn(q, x[c]), __fmul_rn(p, ci));
     }
+  } else if constexpr (FID == EXP_FILTER_LEVEL) {      // filters.py:459-464
+    const float lo = sc.p[0], d = sc.e;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = clamp01(__fdiv_rn(__fsub_rn(x[c], lo), d));
+  } else if constexpr (FID == EXP_FILTER_VIGNET) {     // filters.py:351-352  `img * 0`
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = x[c] * 0.f;
   } else {                                             // WNB  filters.py:438-440
     const float p = sc.p[0];
     const float lum = __fadd_rn(__fadd_rn(__fmul_rn(kLumR, x[0]), __fmul_rn(kLumG, x[1])), __fmul_rn(kLumB, x[2]));
@@ -318,29 +352,25 @@ __device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3]
       for (int c = 0; c < 3; ++c) gx[c] = x[c] <= 1.f ? gxm[c] : 0.f;
     }
   } else if constexpr (FID == EXP_FILTER_TONE || FID == EXP_FILTER_COLOR) {
-    // y = (L/S) sum_i clip_i(x) t_i ;  dy/dt_j = (L clip_j - y)/S ;  dy/dx = (L/S) sum_{pass} t_j
-    // acc[row*9 + j] = sum gy * (L clip_j) with L clip_j = sat(L x - j)  (one FADD.SAT + one FFMA;
-    // scaling by L = 8 is exact so this equals clamp(x - j/L, 0, 1/L) * L bit for bit);
-    // acc[row*9 + 8] = sum gy y                                  (row = 0 for Tone)
+    // y = (1/S) sum_i c_i t_i with c_i = L clip_i(x) = sat(L x - i)  (scaling by L = 8 is exact, so
+    // c_i equals clamp(x - i/L, 0, 1/L) * L bit for bit; one FADD.SAT).
+    //   dy/dt_j = (c_j - y)/S    ->  acc[row*8 + j] = A_j = sum gy c_j ; sum gy y = (sum_i t_i A_i)/S
+    //                                is a linear combination of the A_j and is formed once per image
+    //                                in finalize_gparams (fp64), not per pixel.
+    //   dy/dx   = (L/S) sum_{j passes} t_j : TF clip_by_value passes the gradient on ties
+    //             (x - j/L == 0 or == 1/L), so on an exact interior knot BOTH neighbouring segments
+    //             pass; every case (inside / on a knot / outside [0,1]) is ONE branch-free lookup in
+    //             sc.slope.  row = 0 for Tone.
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int row = (FID == EXP_FILTER_COLOR) ? c : 0;
-      float* a = acc + row * (kCurveSteps + 1);
-      int k;
-      const float y = curve_eval(x[c], sc, row, &k);
-      a[kCurveSteps] = fmaf(gy[c], y, a[kCurveSteps]);
+      float* a = acc + row * kCurveSteps;
       const float xs = x[c] * (float)kCurveSteps;
 #pragma unroll
       for (int j = 0; j < kCurveSteps; ++j) a[j] = fmaf(gy[c], __saturatef(xs - (float)j), a[j]);
       if (HAS_GX) {
-        // TF clip_by_value passes the gradient on ties (x - j/L == 0 or == 1/L): at an exact
-        // interior knot both neighbouring segments pass.
-        float slope = 0.f;
-        if (x[c] >= 0.f && x[c] <= 1.f) {
-          slope = sc.p[row * kCurveSteps + k];
-          if (xs == (float)k && k >= 1) slope += sc.p[row * kCurveSteps + k - 1];
-        }
-        gx[c] = gy[c] * slope * sc.scale[row];
+        const int k = min(max(__float2int_rd(xs), -1), kCurveSteps);
+        gx[c] = gy[c] * sc.slope[row][xs == (float)k ? k + kCurveSteps + 3 : k + 1];
       }
     }
   } else if constexpr (FID == EXP_FILTER_CONTRAST) {
@@ -364,6 +394,22 @@ __device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3]
       gx[1] = fmaf(bq, kLumG, gy[1] * a);
       gx[2] = fmaf(bq, kLumB, gy[2] * a);
     }
+  } else if constexpr (FID == EXP_FILTER_LEVEL) {
+    // v = (x - lo)/d, y = clip(v,0,1), d = up - lo + 1e-6 ; on 0 <= v <= 1 (ties pass, TF clip):
+    // dy/dx = 1/d ; dy/dlo = (v - 1)/d ; dy/dup = -v/d   (the 1/d is applied at finalize)
+    const float lo = sc.p[0], d = sc.e;
+    const float inv = 1.f / d;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn(__fsub_rn(x[c], lo), d);
+      const float g = (v >= 0.f && v <= 1.f) ? gy[c] : 0.f;
+      acc[0] = fmaf(g, v - 1.f, acc[0]);
+      acc[1] = fmaf(g, -v, acc[1]);
+      if (HAS_GX) gx[c] = g * inv;
+    }
+  } else if constexpr (FID == EXP_FILTER_VIGNET) {
+    // y = x * 0: no parameter dependence; dy/dx = 0
+    if (HAS_GX) gx[0] = gx[1] = gx[2] = 0.f;
   } else {                                           // WNB
     const float p = sc.p[0];
     const float lum = fmaf(kLumB, x[2], fmaf(kLumG, x[1], kLumR * x[0]));
@@ -390,10 +436,16 @@ __device__ __forceinline__ void finalize_gparams(int fid, const double* sum, con
       float s = 0.f;
       for (int i = 0; i < kCurveSteps; ++i) s = __fadd_rn(s, p[r * kCurveSteps + i]);
       const double S = (double)__fadd_rn(s, 1e-30f);
-      const double Bs = sum[r * (kCurveSteps + 1) + kCurveSteps];
-      for (int j = 0; j < kCurveSteps; ++j)      // sum[j] already carries the factor L
-        out[r * kCurveSteps + j] = (float)((sum[r * (kCurveSteps + 1) + j] - Bs) / S);
+      double Bs = 0.0;                           // sum gy y = (sum_i t_i A_i) / S
+      for (int i = 0; i < kCurveSteps; ++i) Bs += (double)p[r * kCurveSteps + i] * sum[r * kCurveSteps + i];
+      Bs /= S;
+      for (int j = 0; j < kCurveSteps; ++j)      // A_j already carries the factor L
+        out[r * kCurveSteps + j] = (float)((sum[r * kCurveSteps + j] - Bs) / S);
     }
+  } else if (fid == EXP_FILTER_LEVEL) {
+    const double d = (double)__fadd_rn(__fsub_rn(__fadd_rn(p[1], 1.f), p[0]), 1e-6f);
+    out[0] = (float)(sum[0] / d);
+    out[1] = (float)(sum[1] / d);
   } else {
     const int n = num_params(fid);
     for (int i = 0; i < n; ++i) out[i] = (float)sum[i];

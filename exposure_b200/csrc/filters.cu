@@ -8,6 +8,7 @@
 // Replaces the unfused TF-1.6 Eigen launches behind filters.py process() (2..43 launches
 // per filter) and the 8-way stack/one_hot/reduce_sum select of agent.py:77,118-129.
 #include "filter_math.cuh"
+#include "filter_mask.cuh"
 
 namespace expo {
 
@@ -45,6 +46,12 @@ struct FilterArgs {
   unsigned* counters;    // [B]
   float* gparams;        // [B][pstride]
   int logits;            // params are raw regressor logits (EXP_OPT_LOGITS)
+  // masked steps only (exp_filter_masked_*):
+  const float* mask_logits;   // [B][mstride] raw fc2 outputs [:, n:]  (nullable: zeros)
+  float* gmask;               // [B][mstride] dL/dmask_logits (backward)
+  float* mask_out;            // [B][P] (forward, nullable)
+  int mstride, H, W, uniform_id, masking;
+  float max_sharp, min_strength;
 };
 
 // ---- 4 pixels <-> 3 float4 ------------------------------------------------------------
@@ -82,10 +89,12 @@ __device__ __forceinline__ Px4 pack(const float (&px)[4][3]) {
 namespace expo {
 
 // ---- per-CTA reduction of the parameter-gradient accumulators + last-CTA finish --------
-template <int FID>
+template <int FID, int NEXTRA = 0>
 __device__ __forceinline__ void reduce_and_finish(float* acc, const FilterArgs& A, const FilterConsts& sc,
-                                                  float (*red)[kAccStride], int b, int nblk) {
-  constexpr int NACC = num_acc(FID);
+                                                  float (*red)[kAccStride], int b, int nblk,
+                                                  const MaskConsts* mc = nullptr) {
+  constexpr int NACC = num_acc(FID) + NEXTRA;
+  static_assert(NACC <= kAccStride, "partial-sum record too small");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int a = 0; a < NACC; ++a) {
@@ -118,6 +127,7 @@ __device__ __forceinline__ void reduce_and_finish(float* acc, const FilterArgs& 
   __syncthreads();
   if (threadIdx.x == 0) {
     finalize_grads(FID, tot, sc, A.logits, A.gparams + (size_t)b * A.pstride);
+    if constexpr (NEXTRA > 0) finalize_mask_grads(tot + num_acc(FID), *mc, A.gmask + (size_t)b * A.mstride);
     A.counters[b] = 0u;      // leave the workspace ready for the next launch
   }
 }
@@ -199,7 +209,107 @@ __global__ void __launch_bounds__(kThreads) filter_step_select_kernel(const Filt
     case 5: filter_body<5, BWD, HAS_GX, VEC>(A); break;
     case 6: filter_body<6, BWD, HAS_GX, VEC>(A); break;
     case 7: filter_body<7, BWD, HAS_GX, VEC>(A); break;
+    case 8: filter_body<8, BWD, HAS_GX, VEC>(A); break;
+    case 9: filter_body<9, BWD, HAS_GX, VEC>(A); break;
     default: break;   // id -1 (pdf_sample u==0 quirk, pdf_sample_layer.py:5-10): the caller pre-zeroes the output
+  }
+}
+
+
+// ---- masked step (cfg.masking == True, filters.py:62-99 + get_mask): out = lerp(x, proc, mask) ----
+template <int FID, bool BWD, bool HAS_GX, bool VEC>
+__device__ __forceinline__ void masked_body(const FilterArgs& A) {
+  __shared__ FilterConsts sc;
+  __shared__ MaskConsts mc;
+  __shared__ float red[BWD ? kWarps : 1][kAccStride];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits);
+  if (threadIdx.x == 32)
+    setup_mask(mc, A.mask_logits ? A.mask_logits + (size_t)b * A.mstride : nullptr, FID, A.H, A.W, A.max_sharp,
+               A.min_strength, A.masking);
+  __syncthreads();
+
+  const size_t img = (size_t)b * A.P * 3;
+  const float* __restrict__ x = A.x + img;
+  const float* __restrict__ gy = BWD ? A.gy + img : nullptr;
+  float* __restrict__ out = (!BWD || HAS_GX) ? A.out + img : nullptr;
+  float* __restrict__ mout = (!BWD && A.mask_out) ? A.mask_out + (size_t)b * A.P : nullptr;
+  const int p0 = blockIdx.x * A.pix_per_block;
+  const int p1 = min(A.P, p0 + A.pix_per_block);
+
+  constexpr int NF = num_acc(FID);
+  float acc[NF + kMaskParams];
+#pragma unroll
+  for (int a = 0; a < NF + kMaskParams; ++a) acc[a] = 0.f;
+
+  auto one = [&](const float (&px)[3], const float* pg, float (&py)[3], int q) {
+    const int i = q / A.W, j = q - i * A.W;
+    if constexpr (BWD) {
+      const float g3[3] = {pg[0], pg[1], pg[2]};
+      px_bwd_masked<FID, HAS_GX>(px, g3, py, acc, acc + NF, sc, mc, i, j);
+    } else {
+      float proc[3];
+      px_fwd<FID>(px, proc, sc);
+      const MaskPx r = mask_eval(mc, i, j, px);
+      mask_blend(px, proc, r.mask, py);
+      if (mout) mout[q] = r.mask;
+    }
+  };
+
+  if constexpr (VEC) {
+    const int q1 = p1 >> 2;
+    for (int q = (p0 >> 2) + threadIdx.x; q < q1; q += kThreads) {
+      float px[4][3], py[4][3], pg[4][3];
+      unpack(load_px4(x, q), px);
+      if constexpr (BWD) unpack(load_px4(gy, q), pg);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) one(px[k], pg[k], py[k], 4 * q + k);
+      if constexpr (!BWD || HAS_GX) store_px4(out, q, pack(py));
+    }
+  } else {
+    for (int q = p0 + threadIdx.x; q < p1; q += kThreads) {
+      float px[3] = {x[3 * (size_t)q], x[3 * (size_t)q + 1], x[3 * (size_t)q + 2]};
+      float py[3], pg[3] = {0.f, 0.f, 0.f};
+      if constexpr (BWD) {
+        pg[0] = gy[3 * (size_t)q]; pg[1] = gy[3 * (size_t)q + 1]; pg[2] = gy[3 * (size_t)q + 2];
+      }
+      one(px, pg, py, q);
+      if constexpr (!BWD || HAS_GX) {
+        out[3 * (size_t)q] = py[0];
+        out[3 * (size_t)q + 1] = py[1];
+        out[3 * (size_t)q + 2] = py[2];
+      }
+    }
+  }
+  if constexpr (BWD) reduce_and_finish<FID, kMaskParams>(acc, A, sc, red, b, gridDim.x, &mc);
+}
+
+template <bool BWD, bool HAS_GX, bool VEC>
+__global__ void __launch_bounds__(kThreads) filter_step_masked_kernel(const FilterArgs A) {
+  switch (A.ids ? A.ids[blockIdx.y] : A.uniform_id) {
+#define EXP_CASE(F) case F: masked_body<F, BWD, HAS_GX, VEC>(A); break;
+    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7) EXP_CASE(8) EXP_CASE(9)
+#undef EXP_CASE
+    default: break;   // id -1: the caller pre-zeroes the outputs
+  }
+}
+
+// Filter.get_mask alone (debug_info['mask'], filters.py:85-87): mask [B][P]
+__global__ void __launch_bounds__(kThreads) mask_only_kernel(const FilterArgs A) {
+  __shared__ MaskConsts mc;
+  const int b = blockIdx.y;
+  const int fid = A.ids ? A.ids[b] : A.uniform_id;
+  if (threadIdx.x == 0)
+    setup_mask(mc, A.mask_logits ? A.mask_logits + (size_t)b * A.mstride : nullptr, fid, A.H, A.W, A.max_sharp,
+               A.min_strength, A.masking);
+  __syncthreads();
+  const float* __restrict__ x = A.x + (size_t)b * A.P * 3;
+  const int p0 = blockIdx.x * A.pix_per_block;
+  const int p1 = min(A.P, p0 + A.pix_per_block);
+  for (int q = p0 + threadIdx.x; q < p1; q += kThreads) {
+    const float px[3] = {x[3 * (size_t)q], x[3 * (size_t)q + 1], x[3 * (size_t)q + 2]};
+    const int i = q / A.W;
+    A.mask_out[(size_t)b * A.P + q] = mask_eval(mc, i, q - i * A.W, px).mask;
   }
 }
 
@@ -208,7 +318,7 @@ static void launch_uniform(int fid, dim3 grid, cudaStream_t st, const FilterArgs
   switch (fid) {
 #define EXP_CASE(F) \
   case F: filter_step_kernel<F, BWD, HAS_GX, VEC><<<grid, kThreads, 0, st>>>(A); break;
-    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7)
+    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7) EXP_CASE(8) EXP_CASE(9)
 #undef EXP_CASE
   }
 }
@@ -255,6 +365,8 @@ __device__ __forceinline__ void chain_apply_any(int fid, float (&px)[4][3], cons
     case 5: chain_apply<5>(px, sc, npx); break;
     case 6: chain_apply<6>(px, sc, npx); break;
     case 7: chain_apply<7>(px, sc, npx); break;
+    case 8: chain_apply<8>(px, sc, npx); break;
+    case 9: chain_apply<9>(px, sc, npx); break;
     default:                                   // id -1: all-zero one-hot -> black (pdf_sample quirk)
 #pragma unroll
       for (int i = 0; i < 4; ++i) px[i][0] = px[i][1] = px[i][2] = 0.f;
@@ -270,7 +382,7 @@ __global__ void __launch_bounds__(kThreads) filter_chain_fwd_kernel(const ChainA
   for (int s = 0; s < A.S; ++s) {
     const int f = A.ids ? A.ids[s * A.B + b] : -1;
     if (threadIdx.x == 0) fids[s] = f;
-    if (threadIdx.x < 32 && f >= 0 && f < EXP_NUM_FILTERS)
+    if (threadIdx.x < 32 && f >= 0 && f < EXP_NUM_FILTER_KINDS)
       setup_consts(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits);
   }
   __syncthreads();
@@ -309,7 +421,7 @@ __global__ void regress_kernel(const float* __restrict__ logits, int lstride, fl
   const float* gp = BWD ? gparams + (size_t)b * pstride : nullptr;
   float* gf = BWD ? glogits + (size_t)b * lstride : nullptr;
   if (BWD) for (int i = 0; i < lstride; ++i) gf[i] = 0.f;
-  if (fid < 0 || fid >= EXP_NUM_FILTERS) return;
+  if (fid < 0 || fid >= EXP_NUM_FILTER_KINDS) return;
   regress_image<BWD>(fid, f, po, gp, gf);
 }
 
@@ -345,7 +457,7 @@ template <bool BWD, bool HAS_GX>
 static int launch_tma(int fid, const TmaArgs& A, cudaStream_t st) {
   switch (fid) {
 #define EXP_CASE(F) case F: return launch_tma_one<F, BWD, HAS_GX>(A, st);
-    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7)
+    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7) EXP_CASE(8) EXP_CASE(9)
 #undef EXP_CASE
   }
   return set_error(EXP_ERR_INVALID_ARG, "bad filter id %d", fid);
@@ -368,7 +480,7 @@ static int check_common(const void* x, const float* params, int pstride, const i
   EXP_CHECK_ARG(B <= 65535, "B=%d exceeds gridDim.y limit 65535", B);
   EXP_CHECK_ARG(pstride >= 1, "pstride=%d", pstride);
   if (!ids) {
-    EXP_CHECK_ARG(uniform_id >= 0 && uniform_id < EXP_NUM_FILTERS, "bad filter id %d", uniform_id);
+    EXP_CHECK_ARG(uniform_id >= 0 && uniform_id < EXP_NUM_FILTER_KINDS, "bad filter id %d", uniform_id);
     EXP_CHECK_ARG(pstride >= num_params(uniform_id), "pstride=%d < %d params of filter %d", pstride,
                   num_params(uniform_id), uniform_id);
   } else {
@@ -402,7 +514,7 @@ extern "C" {
 int exp_version(void) { return 1; }
 const char* exp_last_error(void) { return last_error_buf(); }
 int exp_num_filter_params(int fid) {
-  if (fid < 0 || fid >= EXP_NUM_FILTERS) return set_error(EXP_ERR_INVALID_ARG, "bad filter id %d", fid);
+  if (fid < 0 || fid >= EXP_NUM_FILTER_KINDS) return set_error(EXP_ERR_INVALID_ARG, "bad filter id %d", fid);
   return num_params(fid);
 }
 
@@ -534,6 +646,87 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, c
   if (gx) launch_step<true, true>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);
   else launch_step<true, false>(vec, ids, uniform_id, grid, (cudaStream_t)stream, A);
   EXP_CHECK_LAUNCH("exp_filter_bwd");
+  return EXP_OK;
+}
+
+/* ---- masked step: Filter.apply with cfg.masking == True ------------------------------------ */
+static void fill_mask_args(FilterArgs& A, const float* mask_logits, int mstride, int H, int W, int uniform_id,
+                           float max_sharpness, float min_strength, int masking) {
+  A.mask_logits = mask_logits; A.mstride = mstride; A.H = H; A.W = W; A.uniform_id = uniform_id;
+  A.max_sharp = max_sharpness; A.min_strength = min_strength; A.masking = masking ? 1 : 0;
+}
+
+int exp_filter_masked_fwd(const float* x, float* y, float* mask_out, const float* params, int pstride,
+                          const float* mask_logits, int mstride, const int* ids, int uniform_id, int B, int H,
+                          int W, float max_sharpness, float min_strength, int masking, int options, void* stream) {
+  EXP_CHECK_ARG(x && (y || mask_out), "null image pointer, or neither y nor mask_out given");
+  EXP_CHECK_ARG(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 29), "bad shape B=%d H=%d W=%d", B, H, W);
+  EXP_CHECK_ARG(!mask_logits || mstride >= kMaskParams, "mstride=%d < %d", mstride, kMaskParams);
+  if (!ids) EXP_CHECK_ARG(uniform_id >= 0 && uniform_id < EXP_NUM_FILTER_KINDS, "bad filter id %d", uniform_id);
+  const int P = H * W;
+  FilterArgs A{};
+  A.x = x; A.out = y; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
+  A.pix_per_block = kPixPerBlockFwd;
+  A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
+  A.mask_out = mask_out;
+  fill_mask_args(A, mask_logits, mstride, H, W, uniform_id, max_sharpness, min_strength, masking);
+  dim3 grid((P + kPixPerBlockFwd - 1) / kPixPerBlockFwd, B);
+  if (!y) {                                   // get_mask only
+    mask_only_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
+    EXP_CHECK_LAUNCH("exp_filter_masked_fwd[mask only]");
+    return EXP_OK;
+  }
+  int rc = check_common(x, params, pstride, ids, uniform_id, B, H, W);
+  if (rc) return rc;
+  bool vec;
+  int variant = options & 0xFF;
+  if (variant == EXP_VARIANT_TMA) variant = EXP_VARIANT_DIRECT;
+  rc = pick_vec(variant, P, x, y, nullptr, &vec);
+  if (rc) return rc;
+  if (vec) filter_step_masked_kernel<false, false, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
+  else filter_step_masked_kernel<false, false, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
+  EXP_CHECK_LAUNCH("exp_filter_masked_fwd");
+  return EXP_OK;
+}
+
+int exp_filter_masked_bwd(const float* x, const float* gy, float* gx, float* gparams, float* gmask_logits,
+                          const float* params, int pstride, const float* mask_logits, int mstride, const int* ids,
+                          int uniform_id, int B, int H, int W, float max_sharpness, float min_strength, int masking,
+                          void* workspace, size_t workspace_bytes, int options, void* stream) {
+  int rc = check_common(x, params, pstride, ids, uniform_id, B, H, W);
+  if (rc) return rc;
+  EXP_CHECK_ARG(gy && gparams && gmask_logits && workspace, "null gy / gparams / gmask_logits / workspace pointer");
+  EXP_CHECK_ARG(mstride >= kMaskParams, "mstride=%d < %d", mstride, kMaskParams);
+  const size_t need = exp_filter_bwd_workspace_bytes(B, H, W);
+  if (workspace_bytes < need)
+    return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  if (!aligned16(workspace)) return set_error(EXP_ERR_ALIGNMENT, "workspace must be 16-byte aligned");
+  const int P = H * W;
+  bool vec;
+  int variant = options & 0xFF;
+  if (variant == EXP_VARIANT_TMA) variant = EXP_VARIANT_DIRECT;
+  rc = pick_vec(variant, P, x, gy, gx, &vec);
+  if (rc) return rc;
+  const int nblk = (P + kPixPerBlockBwd - 1) / kPixPerBlockBwd;
+  FilterArgs A{};
+  A.x = x; A.gy = gy; A.out = gx; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
+  A.pix_per_block = kPixPerBlockBwd;
+  A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
+  A.counters = reinterpret_cast<unsigned*>(workspace);
+  A.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
+  A.gparams = gparams;
+  A.gmask = gmask_logits;
+  fill_mask_args(A, mask_logits, mstride, H, W, uniform_id, max_sharpness, min_strength, masking);
+  dim3 grid(nblk, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gx) {
+    if (vec) filter_step_masked_kernel<true, true, true><<<grid, kThreads, 0, st>>>(A);
+    else filter_step_masked_kernel<true, true, false><<<grid, kThreads, 0, st>>>(A);
+  } else {
+    if (vec) filter_step_masked_kernel<true, false, true><<<grid, kThreads, 0, st>>>(A);
+    else filter_step_masked_kernel<true, false, false><<<grid, kThreads, 0, st>>>(A);
+  }
+  EXP_CHECK_LAUNCH("exp_filter_masked_bwd");
   return EXP_OK;
 }
 

@@ -38,7 +38,8 @@ enum {
   EXP_ERR_UNSUPPORTED = -5  /* shape outside what the kernel family supports        */
 };
 
-/* Filter ids = index in cfg.filters (config_example.py:22-25). */
+/* Filter ids.  0..7 = index in the shipped cfg.filters (config_example.py:22-25); 8, 9 = the two
+ * Filter subclasses of filters.py that no shipped config lists. */
 enum {
   EXP_FILTER_EXPOSURE = 0,   /* ExposureFilter              filters.py:170-182 */
   EXP_FILTER_GAMMA = 1,      /* GammaFilter                 filters.py:194-206 */
@@ -48,7 +49,11 @@ enum {
   EXP_FILTER_CONTRAST = 5,   /* ContrastFilter              filters.py:404-419 */
   EXP_FILTER_WNB = 6,        /* WNBFilter                   filters.py:428-440 */
   EXP_FILTER_COLOR = 7,      /* ColorFilter                 filters.py:247-273 */
-  EXP_NUM_FILTERS = 8
+  EXP_NUM_FILTERS = 8,       /* length of the shipped cfg.filters = number of actions      */
+  EXP_FILTER_LEVEL = 8,      /* LevelFilter                 filters.py:449-464 */
+  EXP_FILTER_VIGNET = 9,     /* VignetFilter                filters.py:341-352 (process == img*0;
+                                its own 5-parameter mask: exp_filter_masked_*)            */
+  EXP_NUM_FILTER_KINDS = 10
 };
 #define EXP_MAX_FILTER_PARAMS 24 /* ColorFilter: 3 channels x cfg.curve_steps(8) */
 
@@ -123,6 +128,33 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams,
                    const float* params, int pstride, const int* ids, int uniform_id,
                    int B, int H, int W, void* workspace, size_t workspace_bytes, int options,
                    void* stream);
+
+/* ---- Filter.apply with a spatial mask (cfg.masking == True) -------------------------------
+ * Replaces filters.py:62-99 (`lerp(img, self.process(img, p), self.get_mask(img, mask_p))`,
+ * util.py:307-308) with Filter.get_mask (filters.py:110-148) or, for EXP_FILTER_VIGNET,
+ * VignetFilter.get_mask (filters.py:354-396) evaluated per pixel in the same pass; the mask
+ * image is never materialised unless `mask_out` asks for it.
+ *   mask_logits [B, mstride>=6]: the RAW fc2 outputs `features[:, n:]` of extract_parameters
+ *     (filters.py:43-44); tanh_range(-5, 5) (filters.py:123-125) is applied in-kernel.  NULL = zeros
+ *     (the `specified_parameter` branch, filters.py:73-75).
+ *   max_sharpness, min_strength: cfg.maximum_sharpness, cfg.minimum_strength
+ *     (config_example.py:37-38);  masking: cfg.masking (0 -> mask == 1, i.e. exp_filter_fwd).
+ *   mask_out (nullable) [B,H,W]: debug_info['mask'] / Filter.mask (filters.py:85-87).
+ *   y == NULL with mask_out != NULL computes the mask alone (Filter.get_mask); params may be NULL.
+ * Other arguments, variants (TMA is served by DIRECT) and EXP_OPT_LOGITS as in exp_filter_fwd. */
+int exp_filter_masked_fwd(const float* x, float* y, float* mask_out, const float* params, int pstride,
+                          const float* mask_logits, int mstride, const int* ids, int uniform_id, int B,
+                          int H, int W, float max_sharpness, float min_strength, int masking, int options,
+                          void* stream);
+/* Backward of the above: gparams as exp_filter_bwd (the mask scales the filter's own gradient),
+ * gmask_logits [B, mstride] = dL/dmask_logits (first 6 entries written; what tf.gradients builds
+ * through get_mask), gx (nullable) = dL/dx including the path through the mask's luminance term.
+ * Same workspace as exp_filter_bwd. */
+int exp_filter_masked_bwd(const float* x, const float* gy, float* gx, float* gparams, float* gmask_logits,
+                          const float* params, int pstride, const float* mask_logits, int mstride,
+                          const int* ids, int uniform_id, int B, int H, int W, float max_sharpness,
+                          float min_strength, int masking, void* workspace, size_t workspace_bytes,
+                          int options, void* stream);
 
 /* ======================================================================================
  * Policy / critic / value network primitives.

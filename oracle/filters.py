@@ -23,8 +23,12 @@ Layout: images are NHWC ``[B, H, W, 3]``; ``param`` is the *regressed* filter pa
     5   ContrastFilter               1   p                          filters.py:404-419
     6   WNBFilter                    1   p                          filters.py:428-440
     7   ColorFilter                 24   t_{c,i} at index c*8+i     filters.py:247-273
+    8   LevelFilter                  2   lower, upper-1             filters.py:449-464
+    9   VignetFilter                 1   (unused: process == img*0) filters.py:341-352
 
-The id order is ``cfg.filters`` in config_example.py:22-25.
+Ids 0..7 are ``cfg.filters`` in config_example.py:22-25; 8 and 9 are the two Filter subclasses
+no shipped config lists.  ``get_mask`` / ``apply_masked`` restate Filter.apply with
+cfg.masking == True (filters.py:62-99, 110-148; VignetFilter.get_mask filters.py:354-396).
 """
 import math
 
@@ -34,9 +38,12 @@ import torch
 # --------------------------------------------------------------------------------------
 # constants (config_example.py:27-33) and helpers (util.py)
 # --------------------------------------------------------------------------------------
-FILTER_NAMES = ["E", "G", "W", "S+", "T", "Ct", "BW", "C"]
-NUM_PARAMS = [1, 1, 3, 1, 8, 1, 1, 24]
-E, G, W, SP, T, CT, BW, C = range(8)
+FILTER_NAMES = ["E", "G", "W", "S+", "T", "Ct", "BW", "C", "Le", "V"]
+NUM_PARAMS = [1, 1, 3, 1, 8, 1, 1, 24, 2, 1]
+E, G, W, SP, T, CT, BW, C, LE, VG = range(10)
+MASK_PARAMS = 6                 # Filter.get_num_mask_parameters (filters.py:107-108); Vignet uses 5
+MAXIMUM_SHARPNESS = 1           # cfg.maximum_sharpness (config_example.py:38)
+MINIMUM_STRENGTH = 0.3          # cfg.minimum_strength  (config_example.py:37)
 
 CURVE_STEPS = 8                 # cfg.curve_steps
 EXPOSURE_RANGE = 3.5            # cfg.exposure_range
@@ -109,7 +116,7 @@ def regress(fid, f):
     s = torch.exp(tanh_range(-0.5, 0.5)(f))
     s = s * (1.0 / (1e-5 + LUM_R * s[:, 0] + LUM_G * s[:, 1] + LUM_B * s[:, 2]))[:, None]
     return s
-  if fid in (SP, BW):   # filters.py:481-482, 435-436
+  if fid in (SP, BW, LE, VG):   # filters.py:481-482, 435-436, 456-457, 348-349
     return torch.sigmoid(f)
   if fid == T:     # filters.py:306-310
     return tanh_range(*TONE_CURVE_RANGE)(f)
@@ -197,7 +204,71 @@ def process(fid, img, param):
     return lerp(img, rgb2lum(img), param[:, :, None, None])
   if fid == C:      # filters.py:264-273
     return _curve(img, param.reshape(B, 3, CURVE_STEPS))
+  if fid == LE:     # filters.py:459-464
+    lower = param[:, 0][:, None, None, None]
+    upper = (param[:, 1] + 1)[:, None, None, None]
+    return tf_clip((img - lower) / (upper - lower + 1e-6), 0.0, 1.0)
+  if fid == VG:     # filters.py:351-352
+    return img * 0
   raise ValueError(fid)
+
+
+def mask_grid(H, W):
+  """The centred unit grid of filters.py:126-135 (computed in float64 by numpy, stored float32)."""
+  grid = np.zeros(shape=[1, H, W, 2], dtype=np.float32)
+  shorter_edge = min(H, W)
+  ii = (np.arange(H) + (shorter_edge - H) / 2.0) / shorter_edge - 0.5
+  jj = (np.arange(W) + (shorter_edge - W) / 2.0) / shorter_edge - 0.5
+  grid[0, :, :, 0] = ii[:, None]
+  grid[0, :, :, 1] = jj[None, :]
+  return grid
+
+
+def get_mask(fid, img, mask_logits, masking=True, maximum_sharpness=MAXIMUM_SHARPNESS,
+             minimum_strength=MINIMUM_STRENGTH):
+  """Filter.get_mask (filters.py:110-148) or, for fid == VG, VignetFilter.get_mask
+  (filters.py:354-396).  mask_logits [B, 6 | 5] raw; returns [B,H,W,1] (or ones(1,1,1,1))."""
+  if fid != VG and not masking:
+    return torch.ones(1, 1, 1, 1, dtype=img.dtype)
+  filter_input_range = 5
+  mp = tanh_range(l=-filter_input_range, r=filter_input_range, initial=0)(mask_logits)
+  H, Wd = img.shape[1:3]
+  grid = torch.from_numpy(mask_grid(H, Wd)).to(img.dtype)
+  if fid != VG:
+    inp = grid[:, :, :, 0, None] * mp[:, None, None, 0, None] + \
+          grid[:, :, :, 1, None] * mp[:, None, None, 1, None] + \
+          mp[:, None, None, 2, None] * (rgb2lum(img) - 0.5) + \
+          mp[:, None, None, 3, None] * 2
+    inp = inp * (maximum_sharpness * mp[:, None, None, 4, None] / filter_input_range)
+    mask = torch.sigmoid(inp)
+    mask = mask * (mp[:, None, None, 5, None] / filter_input_range * 0.5 + 0.5) * (1 - minimum_strength) + minimum_strength
+    return mask
+  inp = (grid[:, :, :, 0, None] * mp[:, None, None, 0, None]) ** 2 + \
+        (grid[:, :, :, 1, None] * mp[:, None, None, 1, None]) ** 2 + \
+        mp[:, None, None, 2, None] - filter_input_range
+  inp = inp * (maximum_sharpness * mp[:, None, None, 3, None] / filter_input_range)
+  mask = torch.sigmoid(inp)
+  mask = mask * (mp[:, None, None, 4, None] / filter_input_range * 0.5 + 0.5)
+  if not masking:
+    mask = mask * 0 + 1
+  return mask
+
+
+def apply_masked(fid, img, logits, mask_logits, masking=True, **kw):
+  """Filter.apply (filters.py:62-99): lerp(img, process(img, regress(logits)), get_mask(...))."""
+  param = regress(fid, logits)
+  return lerp(img, process(fid, img, param), get_mask(fid, img, mask_logits, masking, **kw))
+
+
+def apply_masked_bwd_autograd(fid, img, logits, mask_logits, gy, masking=True, **kw):
+  """(gx, glogits, gmask_logits) of <gy, apply_masked(...)> by autograd of the restatement."""
+  x = img.detach().clone().requires_grad_(True)
+  f = logits.detach().clone().requires_grad_(True)
+  m = mask_logits.detach().clone().requires_grad_(True)
+  y = apply_masked(fid, x, f, m, masking, **kw)
+  gx, gf, gm = torch.autograd.grad(y, [x, f, m], grad_outputs=gy, allow_unused=True)
+  z = lambda g, t: torch.zeros_like(t) if g is None else g
+  return z(gx, x), z(gf, f), z(gm, m)
 
 
 def apply_filter(fid, img, logits):
@@ -324,6 +395,15 @@ def process_bwd_analytic(fid, img, param, gy):
     gx = (1 - p) * gy + p * sg * coef
     gparam = sum_hw((gy * (lum - x)).sum(-1, keepdim=True))
     return gx, gparam
+  if fid == LE:
+    lo = param[:, 0][:, None, None, None]
+    d = (param[:, 1] + 1)[:, None, None, None] - lo + 1e-6
+    v = (x - lo) / d
+    g = gy * ((v >= 0) & (v <= 1)).to(x.dtype)              # TF clip_by_value passes ties
+    gparam = torch.stack([(g * (v - 1) / d).sum(dim=(1, 2, 3)), (g * (-v) / d).sum(dim=(1, 2, 3))], dim=1)
+    return g / d, gparam
+  if fid == VG:
+    return gy * 0, torch.zeros_like(param)
   raise ValueError(fid)
 
 

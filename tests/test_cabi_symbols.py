@@ -34,8 +34,8 @@ def test_python_binding_covers_header(built_lib):
   assert sorted(_cabi.SIGNATURES) == _declared()
   l = _cabi.lib()
   assert l.exp_version() == 1
-  assert [l.exp_num_filter_params(i) for i in range(8)] == [1, 1, 3, 1, 8, 1, 1, 24]
-  assert l.exp_num_filter_params(8) < 0 and b"bad filter id" in l.exp_last_error()
+  assert [l.exp_num_filter_params(i) for i in range(10)] == [1, 1, 3, 1, 8, 1, 1, 24, 2, 1]
+  assert l.exp_num_filter_params(10) < 0 and b"bad filter id" in l.exp_last_error()
   assert l.exp_filter_bwd_workspace_bytes(0, 1, 1) == 0
   assert l.exp_filter_bwd_workspace_bytes(2, 64, 64) == 65536 * 4 + (2 + 4096) * 32 * 4
 
@@ -45,7 +45,10 @@ def test_argument_validation_needs_no_gpu(built_lib):
   from exposure_b200 import _cabi
   l = _cabi.lib()
   assert l.exp_filter_fwd(None, None, None, 24, None, 0, 1, 4, 4, 0, None) == -1
-  assert l.exp_filter_fwd(16, 16, 16, 24, None, 9, 1, 4, 4, 0, None) == -1          # bad id
+  assert l.exp_filter_fwd(16, 16, 16, 24, None, 10, 1, 4, 4, 0, None) == -1         # bad id
+  assert l.exp_filter_masked_fwd(16, None, None, 16, 24, 16, 6, None, 0, 1, 4, 4, 1.0, 0.3, 1, 0, None) == -1   # no output
+  assert l.exp_filter_masked_fwd(16, 16, None, 16, 24, 16, 5, None, 0, 1, 4, 4, 1.0, 0.3, 1, 0, None) == -1     # mstride < 6
+  assert l.exp_filter_masked_bwd(16, 16, 16, 16, 16, 16, 24, 16, 6, None, 0, 1, 4, 4, 1.0, 0.3, 1, 16, 1, 0, None) == -3
   assert l.exp_filter_fwd(16, 16, 16, 2, None, 7, 1, 4, 4, 0, None) == -1           # pstride < 24
   assert l.exp_filter_fwd(16, 16, 16, 24, None, 0, 1, 3, 3, 1, None) == -2          # DIRECT, H*W%4 != 0
   assert l.exp_filter_fwd(20, 16, 16, 24, None, 0, 1, 4, 4, 1, None) == -2          # misaligned

@@ -612,7 +612,7 @@ def cpu_baseline_train(B, budget_s=25.0):
     P[s + "/fully_connected/weights"] = torch.randn(4096, 128, generator=g) * 0.02; P[s + "/fully_connected/biases"] = torch.zeros(128)
     P[s + "/fully_connected_1/weights"] = torch.randn(128, 1, generator=g) * 0.1; P[s + "/fully_connected_1/biases"] = torch.zeros(1)
   Pg = make("generator", 14); Pg.update(make("generator/action_selection", 14))
-  for j, n in enumerate(OF.NUM_PARAMS):
+  for j, n in enumerate(OF.NUM_PARAMS[:8]):
     Pg["generator/filter_%d/fc1/weights" % j] = torch.randn(4096, 128, generator=g) * 0.02
     Pg["generator/filter_%d/fc1/biases" % j] = torch.zeros(128)
     Pg["generator/filter_%d/fc2/weights" % j] = torch.randn(128, n + 6, generator=g) * 0.1

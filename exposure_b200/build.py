@@ -33,7 +33,7 @@ def _digest():
       if f.endswith((".cu", ".cuh", ".h")):
         with open(os.path.join(root, f), "rb") as fh:
           h.update(f.encode() + b"\0" + fh.read())
-  h.update(" ".join(NVCC_FLAGS).encode())
+  h.update((" ".join(NVCC_FLAGS) + " link:gencode-sm_100a").encode())
   return h.hexdigest()
 
 
@@ -63,7 +63,8 @@ def build_lib(force=False, verbose=False):
       sys.stderr.write(out)
   if failed:
     raise RuntimeError("nvcc failed building %s" % LIB_PATH)
-  res = subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + [j[1] for j in jobs], capture_output=True, text=True)
+  res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + [j[1] for j in jobs],
+                       capture_output=True, text=True)
   if res.returncode != 0:
     sys.stderr.write(res.stdout + res.stderr)
     raise RuntimeError("nvcc failed linking %s" % LIB_PATH)

@@ -35,16 +35,26 @@ def retouch(trainer, high_res, generator=None, steps=None, fused=True):
   S = steps or cfg.test_steps
   thumb = center_thumbnail(high_res, cfg.source_img_size)
   states = torch.zeros(B, cfg.num_state_dim, device=dev)
-  ids, logits = [], []
+  masking = bool(getattr(cfg, "masking", False))
+  ids, logits, mask_logits = [], [], []
   for _ in range(S):
     noise, drop_f, drop_s, _ = trainer.draw(B, generator)
     c = trainer.policy.forward(thumb, states, noise, drop_f, drop_s, 0, 0.0, cfg)
     ids.append(c.ids)
     logits.append(c.logits_sel)
+    if masking:
+      mask_logits.append(c.mask_logits_sel)
     thumb, states = c.out, c.new_states
   ids = torch.stack(ids).contiguous()
   logits = torch.stack(logits).contiguous()
-  if fused:
+  if masking:
+    # cfg.masking: each step's mask depends on the full-resolution pixels' luminance AFTER the
+    # previous steps (filters.py:92-96), so the steps run as S masked launches
+    out = high_res.contiguous()
+    for s in range(S):
+      out = ops.filter_masked_fwd(out, logits[s], mask_logits[s], ids[s], float(cfg.maximum_sharpness),
+                                  float(cfg.minimum_strength), True, out=torch.zeros_like(out), logits=True)
+  elif fused:
     out = ops.filter_chain_fwd(high_res.contiguous(), logits, ids, logits=True)
   else:
     out = high_res.contiguous()

@@ -12,10 +12,9 @@ import torch
 
 from . import nn_ops as K
 from . import ops
-from .util import lerp
 
 __all__ = ["Filter", "ExposureFilter", "GammaFilter", "ImprovedWhiteBalanceFilter", "SaturationPlusFilter",
-           "ToneFilter", "ContrastFilter", "WNBFilter", "ColorFilter", "FILTER_IDS"]
+           "ToneFilter", "ContrastFilter", "WNBFilter", "ColorFilter", "LevelFilter", "VignetFilter", "FILTER_IDS"]
 
 
 class Filter:
@@ -91,19 +90,35 @@ class Filter:
     self.mask_parameters = mask_parameters
     self.mask = self.get_mask(img, mask_parameters)
     debug_info["mask"] = self.mask[0]
-    processed = self.process(img, filter_parameters)
-    # mask == ones(1,1,1,1): lerp(img, processed, 1) == processed for finite img (filters.py:88)
-    low_res_output = processed if not self.use_masking() else lerp(img, processed, self.mask)
+    low_res_output = self._apply_masked(img, filter_parameters, mask_parameters)
     if high_res is not None:
       if self.no_high_res():
         high_res_output = high_res
       else:
         self.high_res_mask = self.get_mask(high_res, mask_parameters)
-        hp = self.process(high_res, filter_parameters)
-        high_res_output = hp if not self.use_masking() else lerp(high_res, hp, self.high_res_mask)
+        high_res_output = self._apply_masked(high_res, filter_parameters, mask_parameters)
     else:
       high_res_output = None
     return low_res_output, high_res_output, debug_info
+
+  def _masks_pixels(self):
+    return self.use_masking()
+
+  def _apply_masked(self, img, filter_parameters, mask_parameters):
+    """lerp(img, process(img, p), get_mask(img, mask_p)) (filters.py:88).  With masking off the mask
+    is ones(1,1,1,1) and lerp(img, processed, 1) == processed for finite img; with masking on the
+    mask is evaluated inside the masked step kernel (never materialised)."""
+    if not self._masks_pixels():
+      return self.process(img, filter_parameters)
+    B = img.shape[0]
+    flat = filter_parameters.reshape(B, -1)
+    if flat.shape[1] != ops.PSTRIDE:
+      flat = torch.nn.functional.pad(flat, (0, ops.PSTRIDE - flat.shape[1]))
+    ml = mask_parameters.expand(B, mask_parameters.shape[1])
+    if ml.shape[1] < ops.MASK_PARAMS:
+      ml = torch.nn.functional.pad(ml, (0, ops.MASK_PARAMS - ml.shape[1]))
+    return ops.FilterMaskedFn.apply(img.contiguous(), flat.contiguous(), ml.contiguous(), self.filter_id,
+                                    float(self.cfg.maximum_sharpness), float(self.cfg.minimum_strength))
 
   def use_masking(self):
     return self.cfg.masking
@@ -112,10 +127,19 @@ class Filter:
     return 6
 
   def get_mask(self, img, mask_parameters):
-    """filters.py:110-148.  Masking is disabled in every shipped config (config_example.py:36)."""
+    """filters.py:110-148: mask_parameters are the RAW fc2 outputs [B, 6] (tanh_range inside).
+    Returns ones(1,1,1,1) with masking off (every shipped config, config_example.py:36), else the
+    [B,H,W,1] mask (debug / visualisation; `apply` evaluates it inside the step kernel instead).
+    Not differentiable here -- gradients flow through `apply`."""
     if not self.use_masking():
       return torch.ones(1, 1, 1, 1, device=img.device)
-    raise NotImplementedError("cfg.masking=True is outside the round-1 hot path (DESIGN.md section 10)")
+    assert mask_parameters.shape[1] == self.get_num_mask_parameters()
+    B = img.shape[0]
+    ml = mask_parameters.detach().expand(B, mask_parameters.shape[1])
+    if ml.shape[1] < ops.MASK_PARAMS:
+      ml = torch.nn.functional.pad(ml, (0, ops.MASK_PARAMS - ml.shape[1]))
+    return ops.filter_mask(img.detach().contiguous(), ml.contiguous(), self.filter_id,
+                           float(self.cfg.maximum_sharpness), float(self.cfg.minimum_strength), True)
 
   def visualize_filter(self, debug_info, canvas):
     raise NotImplementedError("visualisation is out of scope (DESIGN.md section 10)")
@@ -210,5 +234,45 @@ class ColorFilter(Filter):             # filters.py:247-273
     return p.reshape(-1, self.channels, self.cfg.curve_steps)[:, None, None, :]
 
 
+class LevelFilter(Filter):             # filters.py:449-464
+  filter_id = 8
+
+  def __init__(self, net, cfg):
+    Filter.__init__(self, net, cfg)
+    self.short_name = "Le"
+    self.num_filter_parameters = 2
+
+
+class VignetFilter(Filter):            # filters.py:341-396
+  """process == img * 0 and a mask of its own (5 parameters, quadratic in the grid) that is
+  applied whether or not cfg.masking is set -- with masking off the reference multiplies it by 0
+  and adds 1, i.e. the output is black (filters.py:390-394)."""
+  filter_id = 9
+
+  def __init__(self, net, cfg):
+    Filter.__init__(self, net, cfg)
+    self.short_name = "V"
+    self.num_filter_parameters = 1
+
+  def get_num_mask_parameters(self):
+    return 5
+
+  def _masks_pixels(self):
+    return True
+
+  def _apply_masked(self, img, filter_parameters, mask_parameters):
+    if self.use_masking():
+      return Filter._apply_masked(self, img, filter_parameters, mask_parameters)
+    return self.process(img, filter_parameters)            # mask*0+1 -> lerp(img, 0, 1)
+
+  def get_mask(self, img, mask_parameters):
+    assert mask_parameters.shape[1] == self.get_num_mask_parameters()
+    B = img.shape[0]
+    ml = torch.nn.functional.pad(mask_parameters.detach().expand(B, 5), (0, 1))
+    return ops.filter_mask(img.detach().contiguous(), ml.contiguous(), self.filter_id,
+                           float(self.cfg.maximum_sharpness), float(self.cfg.minimum_strength), self.use_masking())
+
+
 FILTER_IDS = {cls: cls.filter_id for cls in (ExposureFilter, GammaFilter, ImprovedWhiteBalanceFilter,
-                                             SaturationPlusFilter, ToneFilter, ContrastFilter, WNBFilter, ColorFilter)}
+                                             SaturationPlusFilter, ToneFilter, ContrastFilter, WNBFilter, ColorFilter,
+                                             LevelFilter, VignetFilter)}

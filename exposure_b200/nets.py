@@ -292,6 +292,7 @@ class PolicyNet:
     store.add(self.sfc2 + "/weights", (FC1, self.n_filters), FC1, self.n_filters)
     store.add(self.sfc2 + "/biases", (self.n_filters,))
     self.ostride = max(self.out_dims)          # 30
+    self._n_of_id = torch.tensor(NUM_PARAMS, device=store.device, dtype=torch.long)
 
   def forward(self, img, states, noise, drop_f, drop_s, is_train, progress, cfg, high_res=None):
     """img [B,64,64,3], states [B,11], noise [B] (= z[:,0]), drop_* [B,4,4,256] in {0,2}.
@@ -319,9 +320,21 @@ class PolicyNet:
     safe = c.ids.clamp(min=0).long()
     c.logits_sel = c.O[torch.arange(B, device=img.device), safe][:, :F.PSTRIDE].contiguous()
     c.params = F.filter_regress_fwd(c.logits_sel, c.ids)
-    c.out = F.filter_fwd(img, c.params, c.ids)
-    if high_res is not None:
-      c.high_res_out = F.filter_fwd(high_res, c.params, c.ids)
+    c.masking = bool(getattr(cfg, "masking", False))
+    if not c.masking:
+      c.out = F.filter_fwd(img, c.params, c.ids)
+      if high_res is not None:
+        c.high_res_out = F.filter_fwd(high_res, c.params, c.ids)
+    else:
+      # cfg.masking (filters.py:62-148): the 6 mask logits of the selected filter are its fc2
+      # outputs [n, n+6); the mask is evaluated inside the masked step kernel
+      c.mask_idx = self._n_of_id[safe][:, None] + torch.arange(MASK_PARAMS, device=img.device)[None, :]
+      c.mask_logits_sel = torch.gather(c.O[torch.arange(B, device=img.device), safe], 1, c.mask_idx).contiguous()
+      c.mask_cfg = (float(cfg.maximum_sharpness), float(cfg.minimum_strength))
+      c.out = F.filter_masked_fwd(img, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True, out=torch.zeros_like(img))
+      if high_res is not None:
+        c.high_res_out = F.filter_masked_fwd(high_res, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True,
+                                             out=torch.zeros_like(high_res))
     c.pen_img = K.overexposure_fwd(c.out)
     c.penalty = c.pen_img + c.pen_head
     return c
@@ -334,12 +347,22 @@ class PolicyNet:
     with K.fork(3):                      # the selector tower is independent of the filter-head tower
       self._selector_backward(c, g_surrogate, g_penalty)
     g_img = K.overexposure_bwd(c.out, g_penalty, g_in=g_out)
-    _, g_params = F.filter_bwd(c.img, g_img, c.params, c.ids, need_gx=False)
+    if not c.masking:
+      _, g_params = F.filter_bwd(c.img, g_img, c.params, c.ids, need_gx=False)
+    else:
+      _, g_params, g_mask = F.filter_masked_bwd(c.img, g_img, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True,
+                                                need_gx=False)
     g_logits_sel = F.filter_regress_bwd(c.logits_sel, g_params, c.ids)           # [B,24]
     G_O = torch.zeros_like(c.O)
     safe = c.ids.clamp(min=0).long()
     valid = (c.ids >= 0).to(g_logits_sel.dtype)[:, None]
-    G_O[torch.arange(B, device=c.img.device), safe, :F.PSTRIDE] = g_logits_sel * valid
+    if not c.masking:
+      G_O[torch.arange(B, device=c.img.device), safe, :F.PSTRIDE] = g_logits_sel * valid
+    else:
+      row = torch.zeros(B, self.ostride, device=c.img.device)
+      row[:, :F.PSTRIDE] = g_logits_sel * valid                                  # entries >= n are 0
+      row.scatter_add_(1, c.mask_idx, g_mask[:, :MASK_PARAMS] * valid)
+      G_O[torch.arange(B, device=c.img.device), safe] = row
     G_Oflat = G_O.view(B, -1)
     d_H = torch.empty_like(c.H)
     for j, name in enumerate(self.fc2):

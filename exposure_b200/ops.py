@@ -8,14 +8,16 @@ from . import _cabi
 from ._cabi import MAX_FILTER_PARAMS, VARIANT_AUTO
 
 NUM_PARAMS = (1, 1, 3, 1, 8, 1, 1, 24)      # cfg.filters order (config_example.py:22-25)
+NUM_PARAMS_ALL = NUM_PARAMS + (2, 1)        # + LevelFilter (id 8), VignetFilter (id 9)
 PSTRIDE = MAX_FILTER_PARAMS
+MASK_PARAMS = 6                             # Filter.get_num_mask_parameters (filters.py:107-108)
 
 # running count of kernels launched through this module (bench.py reports it)
 launch_count = 0
 # when set to a list, every filter-step launch appends (name, algorithmic_bytes, ev0, ev1)
 # with CUDA events recorded on the launching stream (bench.py's live roofline measurement)
 event_log = None
-FILTER_NAMES = ("exposure", "gamma", "wb", "satplus", "tone", "contrast", "wnb", "color")
+FILTER_NAMES = ("exposure", "gamma", "wb", "satplus", "tone", "contrast", "wnb", "color", "level", "vignet")
 
 
 class _Timed:
@@ -170,6 +172,90 @@ def filter_bwd(x, gy, params, ids, need_gx=True, gx_out=None, variant=VARIANT_AU
                                  ws.numel(), variant | (OPT_LOGITS if logits else 0), _stream()), "exp_filter_bwd")
   launch_count += 1
   return gx, gparams
+
+
+def _chk_mask_logits(mask_logits, B):
+  if mask_logits is None:
+    return None, MASK_PARAMS
+  return mask_logits.data_ptr(), _chk_mat(mask_logits, B, "mask_logits")
+
+
+def filter_masked_fwd(x, params, mask_logits, ids, max_sharpness=1.0, min_strength=0.3, masking=True, out=None,
+                      want_mask=False, logits=False):
+  """Filter.apply with cfg.masking (filters.py:62-99): y = lerp(x, process(x, params), get_mask(x, mask_logits)).
+  mask_logits: raw fc2 outputs [B, >=6] (None = zeros).  Returns y, or (y, mask [B,H,W,1]) with want_mask."""
+  global launch_count
+  _chk_img(x, "x")
+  B, H, W, _ = x.shape
+  ps = _chk_mat(params, B, "params")
+  mp, ms = _chk_mask_logits(mask_logits, B)
+  y = torch.empty_like(x) if out is None else out
+  mask = torch.empty(B, H, W, 1, device=x.device, dtype=torch.float32) if want_mask else None
+  idp, uid = _ids_arg(ids, B)
+  with _Timed("filter_masked_fwd", ids, B * H * W * 24):
+    _cabi.check(_cabi.lib().exp_filter_masked_fwd(
+        x.data_ptr(), y.data_ptr(), mask.data_ptr() if want_mask else None, params.data_ptr(), ps, mp, ms, idp, uid,
+        B, H, W, float(max_sharpness), float(min_strength), int(bool(masking)), OPT_LOGITS if logits else 0, _stream()),
+                "exp_filter_masked_fwd")
+  launch_count += 1
+  return (y, mask) if want_mask else y
+
+
+def filter_mask(x, mask_logits, ids, max_sharpness=1.0, min_strength=0.3, masking=True):
+  """Filter.get_mask alone (filters.py:110-148 / 354-396): [B,H,W,1]."""
+  global launch_count
+  _chk_img(x, "x")
+  B, H, W, _ = x.shape
+  mp, ms = _chk_mask_logits(mask_logits, B)
+  mask = torch.empty(B, H, W, 1, device=x.device, dtype=torch.float32)
+  idp, uid = _ids_arg(ids, B)
+  _cabi.check(_cabi.lib().exp_filter_masked_fwd(
+      x.data_ptr(), None, mask.data_ptr(), None, PSTRIDE, mp, ms, idp, uid, B, H, W, float(max_sharpness),
+      float(min_strength), int(bool(masking)), 0, _stream()), "exp_filter_masked_fwd[mask]")
+  launch_count += 1
+  return mask
+
+
+def filter_masked_bwd(x, gy, params, mask_logits, ids, max_sharpness=1.0, min_strength=0.3, masking=True,
+                      need_gx=True, logits=False):
+  """Returns (gx or None, gparams [B, pstride], gmask_logits [B, mstride])."""
+  global launch_count
+  _chk_img(x, "x")
+  _chk_img(gy, "gy")
+  B, H, W, _ = x.shape
+  ps = _chk_mat(params, B, "params")
+  mp, ms = _chk_mask_logits(mask_logits, B)
+  gx = torch.empty_like(x) if need_gx else None
+  gparams = torch.zeros(B, ps, device=x.device, dtype=torch.float32)
+  gmask = torch.zeros(B, ms, device=x.device, dtype=torch.float32)
+  l = _cabi.lib()
+  ws = _workspace(x.device, l.exp_filter_bwd_workspace_bytes(B, H, W))
+  idp, uid = _ids_arg(ids, B)
+  with _Timed("filter_masked_bwd" if need_gx else "filter_masked_bwd_paramonly", ids, B * H * W * (36 if need_gx else 24)):
+    _cabi.check(l.exp_filter_masked_bwd(
+        x.data_ptr(), gy.data_ptr(), gx.data_ptr() if need_gx else None, gparams.data_ptr(), gmask.data_ptr(),
+        params.data_ptr(), ps, mp, ms, idp, uid, B, H, W, float(max_sharpness), float(min_strength),
+        int(bool(masking)), ws.data_ptr(), ws.numel(), OPT_LOGITS if logits else 0, _stream()), "exp_filter_masked_bwd")
+  launch_count += 1
+  return gx, gparams, gmask
+
+
+class FilterMaskedFn(torch.autograd.Function):
+  """autograd node for one masked filter step: (x, params, mask_logits) -> y."""
+
+  @staticmethod
+  def forward(ctx, x, params, mask_logits, ids, max_sharpness, min_strength):
+    ctx.ids, ctx.cfgv = ids, (max_sharpness, min_strength)
+    x, mask_logits = x.contiguous(), mask_logits.contiguous()
+    ctx.save_for_backward(x, params, mask_logits)
+    return filter_masked_fwd(x, params, mask_logits, ids, max_sharpness, min_strength, True)
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, params, mask_logits = ctx.saved_tensors
+    gx, gparams, gmask = filter_masked_bwd(x, gy.contiguous(), params, mask_logits, ctx.ids, ctx.cfgv[0], ctx.cfgv[1],
+                                           True, need_gx=ctx.needs_input_grad[0])
+    return gx, gparams, gmask, None, None, None
 
 
 class FilterProcessFn(torch.autograd.Function):

@@ -21,7 +21,7 @@ def default_cfg():
   cfg = Dict()
   cfg.curve_steps = 8; cfg.gamma_range = 3; cfg.exposure_range = 3.5
   cfg.color_curve_range = (0.90, 1.10); cfg.tone_curve_range = (0.5, 2)
-  cfg.masking = False; cfg.clamp = False
+  cfg.masking = False; cfg.minimum_strength = 0.3; cfg.maximum_sharpness = 1; cfg.clamp = False
   cfg.critic_logit_multiplier = 0.05; cfg.discount_factor = 1.0; cfg.filter_usage_penalty = 1.0
   cfg.use_TD = True; cfg.replay_memory_size = 128; cfg.maximum_trajectory_length = 7
   cfg.over_length_keep_prob = 0.5; cfg.all_reward = 1.0; cfg.img_include_states = True

@@ -36,7 +36,11 @@ def agent_generator(Pg, img, states, noise, drop_f, drop_s, is_train, progress, 
     n = OF.NUM_PARAMS[j]
     h = ON.fc(feat, Pg["generator/filter_%d/fc1/weights" % j], Pg["generator/filter_%d/fc1/biases" % j])
     o = ON.fc(h, Pg["generator/filter_%d/fc2/weights" % j], Pg["generator/filter_%d/fc2/biases" % j], act=False)
-    filtered.append(OF.apply_filter(j, img, o[:, :n]))
+    if getattr(cfg, "masking", False):      # filters.py:62-148: lerp with the 6-parameter spatial mask
+      filtered.append(OF.apply_masked(j, img, o[:, :n], o[:, n:], True, maximum_sharpness=cfg.maximum_sharpness,
+                                      minimum_strength=cfg.minimum_strength))
+    else:
+      filtered.append(OF.apply_filter(j, img, o[:, :n]))
   filtered = torch.stack(filtered, dim=1)
   w, b = _stack(Pg, "generator/action_selection")
   sfeat = ON.cnn(ON.enrich(img, states), w, b) * drop_s.reshape(B, -1)

@@ -16,7 +16,7 @@ import torch
 from oracle import filters as F
 
 pytestmark = pytest.mark.gpu
-ALL = list(range(8))
+ALL = list(range(10))      # 0..7 = cfg.filters; 8 LevelFilter, 9 VignetFilter
 SHAPES = [(4, 64, 64), (2, 33, 31), (3, 1, 1), (1, 7, 5), (2, 128, 96), (5, 2, 2)]
 
 
@@ -299,6 +299,74 @@ def test_host_pipelined_chain_matches_resident(ops):
     assert torch.equal(hy, y.cpu())
     for a, b in zip(hg, gl):
       assert torch.equal(a, b.cpu())
+
+
+MASK_KW = dict(maximum_sharpness=1.5, minimum_strength=0.3)
+
+
+@pytest.mark.parametrize("masking", [True, False])
+@pytest.mark.parametrize("shape", [(2, 64, 64), (2, 24, 40), (3, 21, 9), (1, 130, 70)])
+@pytest.mark.parametrize("fid", ALL)
+def test_masked_apply_matches_oracle(ops, fid, shape, masking):
+  """Filter.apply with cfg.masking (filters.py:62-99, 110-148; Vignet 354-396): pixels, mask,
+  image / filter-logit / mask-logit gradients against the oracle (autograd of the restatement)."""
+  B, H, W = shape
+  x = F.synth_images(B, H, W, seed=60 + fid)
+  lg = F.synth_logits(fid, B) * 0.7
+  nm = 5 if fid == F.VG else 6
+  ml = torch.randn(B, nm, generator=torch.Generator().manual_seed(3 + fid)) * 0.8
+  gy = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(9 + fid))
+  ref32 = F.apply_masked(fid, x, lg, ml, masking, **MASK_KW)
+  mask32 = F.get_mask(fid, x, ml, masking, **MASK_KW).expand(B, H, W, 1)
+  gx64, gl64, gm64 = F.apply_masked_bwd_autograd(fid, x.double(), lg.double(), ml.double(), gy.double(), masking, **MASK_KW)
+  lgp = torch.zeros(B, 24); lgp[:, :lg.shape[1]] = lg
+  mlp = torch.zeros(B, 6); mlp[:, :nm] = ml
+  xd, lgd, mld, gyd = x.cuda(), lgp.cuda(), mlp.cuda(), gy.cuda()
+  y, mask = ops.filter_masked_fwd(xd, lgd, mld, fid, 1.5, 0.3, masking, want_mask=True, logits=True)
+  assert torch.allclose(mask.cpu(), mask32, rtol=0, atol=3e-6)
+  assert torch.equal(ops.filter_mask(xd, mld, fid, 1.5, 0.3, masking), mask)
+  proc = F.process(fid, x, F.regress(fid, lg))
+  tol = 1e-5 * ref32.abs().clamp_min(1e-4) + 4e-6 * (proc - x).abs()
+  if fid == F.CT:
+    tol = tol + _fwd_tol(fid, x, F.regress(fid, lg), proc) - 1e-5 * proc.abs().clamp_min(1e-4)
+  err = (y.cpu() - ref32).abs()
+  assert (err <= tol).all(), float((err / tol).max())
+  gx, gl, gm = ops.filter_masked_bwd(xd, gyd, lgd, mld, fid, 1.5, 0.3, masking, logits=True)
+  if fid != F.SP:      # TF defines no S+ image gradient (closed form checked in test_backward_matches_oracle)
+    e = (gx.cpu().double() - gx64).abs()
+    assert (e <= 1e-4 * gx64.abs().clamp_min(1e-3 * float(gx64.abs().max()) + 1e-30)).all(), float(e.max())
+  n = F.NUM_PARAMS[fid]
+  for got, ref in ((gl.cpu()[:, :n], gl64), (gm.cpu()[:, :nm], gm64)):
+    eg = (got.double() - ref).abs()
+    scale = ref.abs().max(dim=1, keepdim=True).values.clamp_min(1e-6)
+    assert (eg <= 2e-4 * scale).all(), (fid, float((eg / scale).max()))
+  # parameter-only backward and determinism
+  _, gl2, gm2 = ops.filter_masked_bwd(xd, gyd, lgd, mld, fid, 1.5, 0.3, masking, need_gx=False, logits=True)
+  assert torch.allclose(gl2, gl, rtol=1e-5, atol=1e-6) and torch.allclose(gm2, gm, rtol=1e-5, atol=1e-6)
+  gx3, gl3, gm3 = ops.filter_masked_bwd(xd, gyd, lgd, mld, fid, 1.5, 0.3, masking, logits=True)
+  assert torch.equal(gx3, gx) and torch.equal(gl3, gl) and torch.equal(gm3, gm)
+  if not masking and fid != F.VG:      # mask == 1: the masked kernels reduce to the plain step
+    assert torch.allclose(y, ops.filter_fwd(xd, lgd, fid, logits=True), rtol=1e-6, atol=1e-7)
+    assert float(gm.abs().max()) == 0.0
+
+
+def test_masked_per_image_ids(ops):
+  """Per-image filter ids through the masked kernels == uniform launches image by image."""
+  B, H, W = 10, 32, 32
+  x = F.synth_images(B, H, W, seed=5).cuda()
+  ids = torch.arange(B, dtype=torch.int32).cuda()
+  lg = (torch.randn(B, 24, generator=torch.Generator().manual_seed(1)) * 0.7).cuda()
+  ml = (torch.randn(B, 6, generator=torch.Generator().manual_seed(2)) * 0.8).cuda()
+  gy = torch.randn(B, H, W, 3, device="cuda")
+  y = ops.filter_masked_fwd(x, lg, ml, ids, 1.0, 0.3, True, logits=True)
+  gx, gl, gm = ops.filter_masked_bwd(x, gy, lg, ml, ids, 1.0, 0.3, True, logits=True)
+  for b in range(B):
+    s = slice(b, b + 1)
+    yu = ops.filter_masked_fwd(x[s].contiguous(), lg[s].contiguous(), ml[s].contiguous(), b, 1.0, 0.3, True, logits=True)
+    assert torch.equal(yu[0], y[b]), b
+    gxu, glu, gmu = ops.filter_masked_bwd(x[s].contiguous(), gy[s].contiguous(), lg[s].contiguous(), ml[s].contiguous(),
+                                          b, 1.0, 0.3, True, logits=True)
+    assert torch.equal(gxu[0], gx[b]) and torch.equal(glu[0], gl[b]) and torch.equal(gmu[0], gm[b]), b
 
 
 def test_errors_are_loud(ops):

@@ -31,9 +31,13 @@ def _rel(a, ref):
   return float((a.double().cpu() - ref).abs().max() / (ref.abs().max() + 1e-30))
 
 
-def test_generator_step_matches_oracle(trainer):
+@pytest.mark.parametrize("masking", [False, True])
+def test_generator_step_matches_oracle(trainer, masking):
+  """masking=True: cfg.masking (filters.py:62-148) -- the selected filter is blended through its
+  spatial mask and the six mask logits of its fc2 head receive gradients."""
   B = 8
   cfg = trainer.cfg
+  cfg.masking = masking
   g = torch.Generator().manual_seed(5)
   img = OF.synth_images(B, 64, 64, seed=21, stress=False).double() * 3
   states = torch.zeros(B, 11, dtype=torch.float64)
@@ -60,7 +64,11 @@ def test_generator_step_matches_oracle(trainer):
     for name, gr in refg.items():
       worst[name] = _rel(G[key][name], gr) if float(gr.abs().max()) > 0 else float(G[key][name].abs().max())
   bad = {k: v for k, v in worst.items() if v > 2e-3}
+  cfg.masking = False
   assert not bad, bad
+  if masking:    # the mask columns [n, n+6) of the selected filters' fc2 heads are trained
+    got = [float(G["generator"]["generator/filter_%d/fc2/weights" % j][:, OF.NUM_PARAMS[j]:].abs().max()) for j in range(8)]
+    assert max(got) > 0, got
 
 
 def test_critic_step_matches_oracle(trainer):

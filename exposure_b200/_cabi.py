@@ -27,6 +27,7 @@ SIGNATURES = {
     "exp_version": (_c_int, []),
     "exp_last_error": (ctypes.c_char_p, []),
     "exp_num_filter_params": (_c_int, [_c_int]),
+    "exp_set_pdl": (_c_int, [_c_int]),
     "exp_filter_regress_fwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p]),
     "exp_filter_regress_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "exp_filter_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

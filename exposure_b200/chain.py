@@ -136,9 +136,12 @@ class HostPipelinedChain:
     self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
     self._first = True
 
-  def step(self, hx, logits_list, gout, hy, hglogits):
+  def step(self, hx, logits_list, gout, hy, hglogits, wait=True):
     """hx, hy: pinned host [B,H,W,3]; logits_list[k]: device [B,n_k]; gout: device [B,H,W,3];
-    hglogits[k]: pinned host [B,n_k].  Blocks until the results are in host memory."""
+    hglogits[k]: pinned host [B,n_k].  Blocks until the results are in host memory, unless
+    wait=False: then the step is only enqueued (call wait() before reading hy / hglogits) and the
+    H2D copies of the next step overlap this step's compute and D2H -- consecutive steps keep both
+    PCIe directions busy without a fill / drain bubble per step."""
     cb = self.cb
     cur = torch.cuda.current_stream()
     for s in (self.s_in, self.s_cmp, self.s_out):
@@ -164,5 +167,11 @@ class HostPipelinedChain:
           h[sl].copy_(g, non_blocking=True)
         self.ev_out[c].record(self.s_out)
     self._first = False
+    if wait:
+      self.wait()
+
+  def wait(self):
+    """Block until every enqueued step has delivered its results to host memory."""
+    cur = torch.cuda.current_stream()
     cur.wait_stream(self.s_out)
     cur.synchronize()

@@ -7,6 +7,8 @@
 //
 // Replaces the unfused TF-1.6 Eigen launches behind filters.py process() (2..43 launches
 // per filter) and the 8-way stack/one_hot/reduce_sum select of agent.py:77,118-129.
+#include <cstdlib>
+
 #include "filter_math.cuh"
 #include "filter_mask.cuh"
 
@@ -22,6 +24,11 @@ constexpr int kPixPerBlockBwd = 4096;    // fatter CTAs: one partial record per 
 constexpr int kMaxImages = 65536;
 constexpr size_t kCounterBytes = (size_t)kMaxImages * sizeof(unsigned);
 constexpr int kMaxPersistentCtas = 4096;  // upper bound on the TMA variant's grid
+
+// process-wide PDL switch (common.cuh launch_pdl): default on, EXPOSURE_PDL=0 or exp_set_pdl(0) turns it off
+static int g_pdl = [] { const char* e = getenv("EXPOSURE_PDL"); return e ? atoi(e) : 1; }();
+bool pdl_enabled() { return g_pdl != 0; }
+void set_pdl(int on) { g_pdl = on; }
 
 static thread_local char g_err[512] = "";
 char* last_error_buf() { return g_err; }
@@ -194,12 +201,14 @@ __device__ __forceinline__ void filter_body(const FilterArgs& A) {
 // One kernel per filter for uniform steps (tight register allocation per filter) ...
 template <int FID, bool BWD, bool HAS_GX, bool VEC>
 __global__ void __launch_bounds__(kThreads) filter_step_kernel(const FilterArgs A) {
+  EXP_PDL_ENTRY();
   filter_body<FID, BWD, HAS_GX, VEC>(A);
 }
 
 // ... and one dispatching kernel for per-image filter ids (agent.py:113-125 selection).
 template <bool BWD, bool HAS_GX, bool VEC>
 __global__ void __launch_bounds__(kThreads) filter_step_select_kernel(const FilterArgs A) {
+  EXP_PDL_ENTRY();
   switch (A.ids[blockIdx.y]) {
     case 0: filter_body<0, BWD, HAS_GX, VEC>(A); break;
     case 1: filter_body<1, BWD, HAS_GX, VEC>(A); break;
@@ -286,6 +295,7 @@ __device__ __forceinline__ void masked_body(const FilterArgs& A) {
 
 template <bool BWD, bool HAS_GX, bool VEC>
 __global__ void __launch_bounds__(kThreads) filter_step_masked_kernel(const FilterArgs A) {
+  EXP_PDL_ENTRY();
   switch (A.ids ? A.ids[blockIdx.y] : A.uniform_id) {
 #define EXP_CASE(F) case F: masked_body<F, BWD, HAS_GX, VEC>(A); break;
     EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7) EXP_CASE(8) EXP_CASE(9)
@@ -317,7 +327,7 @@ template <bool BWD, bool HAS_GX, bool VEC>
 static void launch_uniform(int fid, dim3 grid, cudaStream_t st, const FilterArgs& A) {
   switch (fid) {
 #define EXP_CASE(F) \
-  case F: filter_step_kernel<F, BWD, HAS_GX, VEC><<<grid, kThreads, 0, st>>>(A); break;
+  case F: launch_pdl(filter_step_kernel<F, BWD, HAS_GX, VEC>, grid, dim3(kThreads), 0, st, A); break;
     EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7) EXP_CASE(8) EXP_CASE(9)
 #undef EXP_CASE
   }
@@ -326,8 +336,8 @@ static void launch_uniform(int fid, dim3 grid, cudaStream_t st, const FilterArgs
 template <bool BWD, bool HAS_GX>
 static void launch_step(bool vec, const int* ids, int fid, dim3 grid, cudaStream_t st, const FilterArgs& A) {
   if (ids) {
-    if (vec) filter_step_select_kernel<BWD, HAS_GX, true><<<grid, kThreads, 0, st>>>(A);
-    else filter_step_select_kernel<BWD, HAS_GX, false><<<grid, kThreads, 0, st>>>(A);
+    if (vec) launch_pdl(filter_step_select_kernel<BWD, HAS_GX, true>, grid, dim3(kThreads), 0, st, A);
+    else launch_pdl(filter_step_select_kernel<BWD, HAS_GX, false>, grid, dim3(kThreads), 0, st, A);
   } else {
     if (vec) launch_uniform<BWD, HAS_GX, true>(fid, grid, st, A);
     else launch_uniform<BWD, HAS_GX, false>(fid, grid, st, A);
@@ -413,6 +423,7 @@ template <bool BWD>
 __global__ void regress_kernel(const float* __restrict__ logits, int lstride, float* __restrict__ params,
                                const float* __restrict__ gparams, int pstride, float* __restrict__ glogits,
                                const int* __restrict__ ids, int uniform_id, int B) {
+  EXP_PDL_ENTRY();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int fid = ids ? ids[b] : uniform_id;
@@ -449,7 +460,7 @@ static int launch_tma_one(const TmaArgs& A0, cudaStream_t st) {
   int grid = num_sms[dev] * ctas_per_sm[dev];
   if (grid > kMaxPersistentCtas) grid = kMaxPersistentCtas;
   if (grid > A0.total_tiles) grid = A0.total_tiles;
-  kern<<<grid, kTmaThreads, smem, st>>>(A0);
+  launch_pdl(kern, dim3(grid), dim3(kTmaThreads), smem, st, A0);
   return EXP_OK;
 }
 
@@ -512,6 +523,10 @@ using namespace expo;
 extern "C" {
 
 int exp_version(void) { return 1; }
+int exp_set_pdl(int enable) {
+  set_pdl(enable ? 1 : 0);
+  return EXP_OK;
+}
 const char* exp_last_error(void) { return last_error_buf(); }
 int exp_num_filter_params(int fid) {
   if (fid < 0 || fid >= EXP_NUM_FILTER_KINDS) return set_error(EXP_ERR_INVALID_ARG, "bad filter id %d", fid);
@@ -524,7 +539,7 @@ int exp_filter_regress_fwd(const float* logits, int lstride, float* params, int 
   const int need = ids ? EXP_MAX_FILTER_PARAMS : exp_num_filter_params(uniform_id);
   if (need < 0) return need;
   EXP_CHECK_ARG(lstride >= need && pstride >= need, "strides (%d,%d) < %d", lstride, pstride, need);
-  regress_kernel<false><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  launch_pdl(regress_kernel<false>, dim3((B + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
       logits, lstride, params, nullptr, pstride, nullptr, ids, uniform_id, B);
   EXP_CHECK_LAUNCH("exp_filter_regress_fwd");
   return EXP_OK;
@@ -536,7 +551,7 @@ int exp_filter_regress_bwd(const float* logits, int lstride, const float* gparam
   const int need = ids ? EXP_MAX_FILTER_PARAMS : exp_num_filter_params(uniform_id);
   if (need < 0) return need;
   EXP_CHECK_ARG(lstride >= need && pstride >= need, "strides (%d,%d) < %d", lstride, pstride, need);
-  regress_kernel<true><<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  launch_pdl(regress_kernel<true>, dim3((B + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
       logits, lstride, nullptr, gparams, pstride, glogits, ids, uniform_id, B);
   EXP_CHECK_LAUNCH("exp_filter_regress_bwd");
   return EXP_OK;
@@ -683,8 +698,8 @@ int exp_filter_masked_fwd(const float* x, float* y, float* mask_out, const float
   if (variant == EXP_VARIANT_TMA) variant = EXP_VARIANT_DIRECT;
   rc = pick_vec(variant, P, x, y, nullptr, &vec);
   if (rc) return rc;
-  if (vec) filter_step_masked_kernel<false, false, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
-  else filter_step_masked_kernel<false, false, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
+  if (vec) launch_pdl(filter_step_masked_kernel<false, false, true>, grid, dim3(kThreads), 0, (cudaStream_t)stream, A);
+  else launch_pdl(filter_step_masked_kernel<false, false, false>, grid, dim3(kThreads), 0, (cudaStream_t)stream, A);
   EXP_CHECK_LAUNCH("exp_filter_masked_fwd");
   return EXP_OK;
 }
@@ -720,11 +735,11 @@ int exp_filter_masked_bwd(const float* x, const float* gy, float* gx, float* gpa
   dim3 grid(nblk, B);
   cudaStream_t st = (cudaStream_t)stream;
   if (gx) {
-    if (vec) filter_step_masked_kernel<true, true, true><<<grid, kThreads, 0, st>>>(A);
-    else filter_step_masked_kernel<true, true, false><<<grid, kThreads, 0, st>>>(A);
+    if (vec) launch_pdl(filter_step_masked_kernel<true, true, true>, grid, dim3(kThreads), 0, st, A);
+    else launch_pdl(filter_step_masked_kernel<true, true, false>, grid, dim3(kThreads), 0, st, A);
   } else {
-    if (vec) filter_step_masked_kernel<true, false, true><<<grid, kThreads, 0, st>>>(A);
-    else filter_step_masked_kernel<true, false, false><<<grid, kThreads, 0, st>>>(A);
+    if (vec) launch_pdl(filter_step_masked_kernel<true, false, true>, grid, dim3(kThreads), 0, st, A);
+    else launch_pdl(filter_step_masked_kernel<true, false, false>, grid, dim3(kThreads), 0, st, A);
   }
   EXP_CHECK_LAUNCH("exp_filter_masked_bwd");
   return EXP_OK;

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kTmaThreads) filter_step_tma_kernel(const TmaA
   __shared__ double tot[BWD ? kAccStride : 1];
   __shared__ unsigned ticket;
 
+  pdl_trigger();             // the next step's CTAs may be scheduled as ours drain
   const int t0 = cta_first_tile(blockIdx.x, gridDim.x, A.total_tiles);
   const int t1 = cta_first_tile(blockIdx.x + 1, gridDim.x, A.total_tiles);
   if (t0 >= t1) return;      // only when grid > total_tiles (the host never launches that)
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(kTmaThreads) filter_step_tma_kernel(const TmaA
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();                // x / gy / params of this step are the previous kernel's outputs
 
   // tile n (global index) -> image, pixel offset, byte count
   auto tile_info = [&](int n, int& b, size_t& off_floats, uint32_t& bytes) {

@@ -31,6 +31,7 @@ constexpr int kBK = 8;
 
 template <class P, int BN, bool A_MFAST, bool B_KFAST>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const P p_in) {
+  EXP_PDL_ENTRY();
   constexpr int TN = BN / 16;
   constexpr int NB = (kBK * BN) / kGemmThreads;   // B elements per thread per K step (2 or 1)
   __shared__ __align__(16) float As[2][kBK][kBM + 4];
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const P p_in) {
 template <class P, int BN, bool A_MFAST, bool B_KFAST>
 inline void launch_gemm(const P& p, int M, int N, int Z, cudaStream_t st) {
   dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
-  gemm_kernel<P, BN, A_MFAST, B_KFAST><<<grid, kGemmThreads, 0, st>>>(p);
+  launch_pdl(gemm_kernel<P, BN, A_MFAST, B_KFAST>, dim3(grid), dim3(kGemmThreads), 0, st, p);
 }
 
 __device__ __forceinline__ float lrelu_f(float v) { return 0.6f * v + 0.4f * fabsf(v); }   // util.py:225-229

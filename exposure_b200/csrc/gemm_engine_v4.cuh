@@ -22,6 +22,7 @@ constexpr int kBK4 = 16;
 
 template <class P, int BN, bool A_MVEC, bool B_KVEC>
 __global__ void __launch_bounds__(kGemmThreads) gemm_v4_kernel(const P p_in) {
+  EXP_PDL_ENTRY();
   constexpr int TN = BN / 16;
   __shared__ __align__(16) float As[2][kBK4][kBM + 4];
   __shared__ __align__(16) float Bs[2][kBK4][BN + 4];
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_v4_kernel(const P p_in) {
 template <class P, int BN, bool A_MVEC, bool B_KVEC>
 inline void launch_gemm_v4(const P& p, int M, int N, int Z, cudaStream_t st) {
   dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
-  gemm_v4_kernel<P, BN, A_MVEC, B_KVEC><<<grid, kGemmThreads, 0, st>>>(p);
+  launch_pdl(gemm_v4_kernel<P, BN, A_MVEC, B_KVEC>, dim3(grid), dim3(kGemmThreads), 0, st, p);
 }
 
 }  // namespace expo

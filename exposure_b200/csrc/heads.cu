@@ -56,6 +56,7 @@ __device__ __forceinline__ float sat_of(const float* p, float* w /*nullable [3]*
 
 // stats[b] = (mean lum, population variance of lum, mean saturation)   one CTA per image
 __global__ void __launch_bounds__(256) stats_fwd_kernel(const float* __restrict__ img, float* __restrict__ stats, int P) {
+  EXP_PDL_ENTRY();
   __shared__ double sh[8];
   const float* x = img + (size_t)blockIdx.x * P * 3;
   double sl = 0.0, ss = 0.0;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) stats_bwd_kernel(const float* __restrict_
                                                         const float* __restrict__ g_stat,
                                                         const float* __restrict__ g_direct, float* __restrict__ g_out,
                                                         int P) {
+  EXP_PDL_ENTRY();
   const int b = blockIdx.y;
   const float mean = stats[b * 3], gm = g_stat[b * 3], gv = g_stat[b * 3 + 1], gs = g_stat[b * 3 + 2];
   const float invP = 1.0f / (float)P;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) stats_bwd_kernel(const float* __restrict_
 // dstat[b] = J_stats u   (forward-mode tangent)   one CTA per image
 __global__ void __launch_bounds__(256) stats_jvp_kernel(const float* __restrict__ img, const float* __restrict__ stats,
                                                         const float* __restrict__ u, float* __restrict__ dstat, int P) {
+  EXP_PDL_ENTRY();
   __shared__ double sh[8];
   const size_t base = (size_t)blockIdx.x * P * 3;
   const float mean = stats[blockIdx.x * 3];
@@ -153,6 +156,7 @@ __global__ void policy_head_fwd_kernel(const float* __restrict__ logits, const f
                                        const float* __restrict__ states, HeadCfg c, int B, float* __restrict__ pdf_out,
                                        int* __restrict__ id_out, float* __restrict__ surrogate, float* __restrict__ entropy,
                                        float* __restrict__ penalty_head, float* __restrict__ new_states) {
+  EXP_PDL_ENTRY();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float sm[kMaxFilters], pdf[kMaxFilters], Z;
@@ -195,6 +199,7 @@ __global__ void policy_head_fwd_kernel(const float* __restrict__ logits, const f
 __global__ void policy_head_bwd_kernel(const float* __restrict__ logits, const int* __restrict__ ids,
                                        const float* __restrict__ g_surrogate, const float* __restrict__ g_penalty,
                                        HeadCfg c, int B, float* __restrict__ g_logits) {
+  EXP_PDL_ENTRY();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float sm[kMaxFilters], pdf[kMaxFilters], Z;
@@ -219,6 +224,7 @@ __global__ void policy_head_bwd_kernel(const float* __restrict__ logits, const i
 
 // pen[b] = mean_{h,w,c} max(x-1,0)^2   (agent.py:247)          one CTA per image
 __global__ void __launch_bounds__(256) overexposure_fwd_kernel(const float* __restrict__ img, float* __restrict__ pen, int n) {
+  EXP_PDL_ENTRY();
   __shared__ double sh[8];
   const float* x = img + (size_t)blockIdx.x * n;
   double s = 0.0;
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(256) overexposure_fwd_kernel(const float* __re
 __global__ void __launch_bounds__(256) overexposure_bwd_kernel(const float* __restrict__ img, const float* __restrict__ g_pen,
                                                                const float* __restrict__ g_in, float* __restrict__ g_out,
                                                                int n) {
+  EXP_PDL_ENTRY();
   const int b = blockIdx.y;
   const float k = g_pen[b] * 2.f / (float)n;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
@@ -253,6 +260,7 @@ __global__ void __launch_bounds__(256) rl_losses_kernel(const float* __restrict_
                                                         const float* __restrict__ penalty, const float* __restrict__ surrogate,
                                                         const float* __restrict__ new_states, RlCfg c, int B,
                                                         float* __restrict__ seeds, float* __restrict__ losses) {
+  EXP_PDL_ENTRY();
   __shared__ double sh[8];
   double gl = 0.0, vl = 0.0;
   const float invB = 1.0f / (float)B;
@@ -282,6 +290,7 @@ __global__ void __launch_bounds__(256) rl_losses_kernel(const float* __restrict_
 // ---- WGAN-GP helpers (net.py:174-187) -----------------------------------------------------
 __global__ void __launch_bounds__(256) interpolate_kernel(const float* __restrict__ real, const float* __restrict__ fake,
                                                           const float* __restrict__ alpha, float* __restrict__ out, int n) {
+  EXP_PDL_ENTRY();
   const int b = blockIdx.y;
   const float a = alpha[b];
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
@@ -292,6 +301,7 @@ __global__ void __launch_bounds__(256) interpolate_kernel(const float* __restric
 // norm[b] = sqrt(1e-6 + sum g^2); u = g * lambda * 2 max(norm-1,0) / (B norm)   (u may alias g)
 __global__ void __launch_bounds__(256) gp_scale_kernel(const float* __restrict__ g, float* __restrict__ u,
                                                        float* __restrict__ norm, float lambda, int B, int n) {
+  EXP_PDL_ENTRY();
   __shared__ double sh[8];
   const size_t base = (size_t)blockIdx.x * n;
   double s = 0.0;
@@ -309,6 +319,7 @@ __global__ void __launch_bounds__(256) gp_scale_kernel(const float* __restrict__
 // (1/world_size after the all-reduce sum).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ hyper, float beta1, float beta2, float eps, float grad_scale, size_t n) {
+  EXP_PDL_ENTRY();
   const float lr_t = hyper[0];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
@@ -327,7 +338,7 @@ extern "C" {
 
 int exp_stats_fwd(const float* img, float* stats, int B, int H, int W, void* stream) {
   EXP_CHECK_ARG(img && stats && B > 0 && H > 0 && W > 0, "bad args");
-  stats_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(img, stats, H * W);
+  launch_pdl(stats_fwd_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, img, stats, H * W);
   EXP_CHECK_LAUNCH("exp_stats_fwd");
   return EXP_OK;
 }
@@ -336,13 +347,13 @@ int exp_stats_bwd(const float* img, const float* stats, const float* g_stat, con
   EXP_CHECK_ARG(img && stats && g_stat && g_out && B > 0 && H > 0 && W > 0 && B <= 65535, "bad args");
   const int P = H * W;
   dim3 grid(min((P + 255) / 256, 64), B);
-  stats_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, stats, g_stat, g_direct, g_out, P);
+  launch_pdl(stats_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, img, stats, g_stat, g_direct, g_out, P);
   EXP_CHECK_LAUNCH("exp_stats_bwd");
   return EXP_OK;
 }
 int exp_stats_jvp(const float* img, const float* stats, const float* u, float* dstat, int B, int H, int W, void* stream) {
   EXP_CHECK_ARG(img && stats && u && dstat && B > 0 && H > 0 && W > 0, "bad args");
-  stats_jvp_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(img, stats, u, dstat, H * W);
+  launch_pdl(stats_jvp_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, img, stats, u, dstat, H * W);
   EXP_CHECK_LAUNCH("exp_stats_jvp");
   return EXP_OK;
 }
@@ -355,7 +366,7 @@ int exp_policy_head_fwd(const float* logits, const float* noise, const float* st
                 "null pointer");
   EXP_CHECK_ARG(B > 0 && n_filters > 0 && n_filters <= kMaxFilters && n_states == 3 + n_filters, "bad sizes");
   HeadCfg c{n_filters, n_states, is_train, test_steps, exploration, exploration_penalty, filter_usage_penalty, progress};
-  policy_head_fwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(logits, noise, states, c, B, pdf, ids, surrogate,
+  launch_pdl(policy_head_fwd_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)stream, logits, noise, states, c, B, pdf, ids, surrogate,
                                                                          entropy, penalty_head, new_states);
   EXP_CHECK_LAUNCH("exp_policy_head_fwd");
   return EXP_OK;
@@ -366,14 +377,14 @@ int exp_policy_head_bwd(const float* logits, const int* ids, const float* g_surr
   EXP_CHECK_ARG(logits && ids && g_surrogate && g_penalty && progress && g_logits, "null pointer");
   EXP_CHECK_ARG(B > 0 && n_filters > 0 && n_filters <= kMaxFilters, "bad sizes");
   HeadCfg c{n_filters, 3 + n_filters, 1, 0, exploration, exploration_penalty, 0.f, progress};
-  policy_head_bwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(logits, ids, g_surrogate, g_penalty, c, B, g_logits);
+  launch_pdl(policy_head_bwd_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)stream, logits, ids, g_surrogate, g_penalty, c, B, g_logits);
   EXP_CHECK_LAUNCH("exp_policy_head_bwd");
   return EXP_OK;
 }
 
 int exp_overexposure_fwd(const float* img, float* pen, int B, int H, int W, void* stream) {
   EXP_CHECK_ARG(img && pen && B > 0 && H > 0 && W > 0, "bad args");
-  overexposure_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(img, pen, H * W * 3);
+  launch_pdl(overexposure_fwd_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, img, pen, H * W * 3);
   EXP_CHECK_LAUNCH("exp_overexposure_fwd");
   return EXP_OK;
 }
@@ -382,7 +393,7 @@ int exp_overexposure_bwd(const float* img, const float* g_pen, const float* g_in
   EXP_CHECK_ARG(img && g_pen && g_out && B > 0 && H > 0 && W > 0 && B <= 65535, "bad args");
   const int n = H * W * 3;
   dim3 grid(min((n + 255) / 256, 64), B);
-  overexposure_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, g_pen, g_in, g_out, n);
+  launch_pdl(overexposure_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, img, g_pen, g_in, g_out, n);
   EXP_CHECK_LAUNCH("exp_overexposure_bwd");
   return EXP_OK;
 }
@@ -395,7 +406,7 @@ int exp_rl_losses(const float* fake_logit, const float* fake_input_logit, const 
                 "null pointer");
   EXP_CHECK_ARG(B > 0 && n_states >= 3, "bad sizes");
   RlCfg c{all_reward, critic_logit_multiplier, discount_factor, parameter_lr_mul, max_traj_len, n_states, use_penalty};
-  rl_losses_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(fake_logit, fake_input_logit, old_value, new_value, penalty, surrogate,
+  launch_pdl(rl_losses_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, fake_logit, fake_input_logit, old_value, new_value, penalty, surrogate,
                                                         new_states, c, B, seeds, losses);
   EXP_CHECK_LAUNCH("exp_rl_losses");
   return EXP_OK;
@@ -404,13 +415,13 @@ int exp_rl_losses(const float* fake_logit, const float* fake_input_logit, const 
 int exp_interpolate(const float* real, const float* fake, const float* alpha, float* out, int B, int n, void* stream) {
   EXP_CHECK_ARG(real && fake && alpha && out && B > 0 && n > 0 && B <= 65535, "bad args");
   dim3 grid(min((n + 255) / 256, 64), B);
-  interpolate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(real, fake, alpha, out, n);
+  launch_pdl(interpolate_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, real, fake, alpha, out, n);
   EXP_CHECK_LAUNCH("exp_interpolate");
   return EXP_OK;
 }
 int exp_gp_scale(const float* g, float* u, float* norm, float lambda, int B, int n, void* stream) {
   EXP_CHECK_ARG(g && u && norm && B > 0 && n > 0, "bad args");
-  gp_scale_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(g, u, norm, lambda, B, n);
+  launch_pdl(gp_scale_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, g, u, norm, lambda, B, n);
   EXP_CHECK_LAUNCH("exp_gp_scale");
   return EXP_OK;
 }
@@ -419,7 +430,7 @@ int exp_adam(float* params, const float* grads, float* m, float* v, const float*
              float eps, float grad_scale, size_t n, void* stream) {
   EXP_CHECK_ARG(params && grads && m && v && hyper && n > 0, "bad args");
   const unsigned blocks = (unsigned)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
-  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, hyper, beta1, beta2, eps, grad_scale, n);
+  launch_pdl(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, params, grads, m, v, hyper, beta1, beta2, eps, grad_scale, n);
   EXP_CHECK_LAUNCH("exp_adam");
   return EXP_OK;
 }

@@ -320,6 +320,7 @@ struct FcWgrad {
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t count, int ncols,
                                      const float* __restrict__ bias, const float* __restrict__ mask_ref, int ldmask,
                                      int mode, float* __restrict__ out, int ldo, int accumulate) {
+  EXP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float v = 0.f;
@@ -337,6 +338,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
 // Rows are split into gridDim.z chunks; chunk z of batch y writes out[(y * gridDim.z + z) * cols + col].
 __global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, int rows_per_chunk,
                               float* __restrict__ out) {
+  EXP_PDL_ENTRY();
   __shared__ float red[8][33];
   a += (size_t)blockIdx.y * rows * cols;
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -368,6 +370,7 @@ __global__ void colsum_kernel(const float* __restrict__ a, int rows, int cols, i
 // out[b, col] = sum_z part[(b * chunks + z) * cols + col]   (fixed order)
 __global__ void colsum_finish_kernel(const float* __restrict__ part, int chunks, int cols, int batch,
                                      float* __restrict__ out) {
+  EXP_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * cols) return;
   const int b = i / cols, col = i - b * cols;
@@ -393,6 +396,7 @@ template <int CMAX>
 __global__ void __launch_bounds__(256) conv_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                                const float* __restrict__ a_in, float* __restrict__ dx,
                                                                int B, int IH, int IW, int Cin, int Cout, int lgW2, int lgHW2) {
+  EXP_PDL_ENTRY();
   extern __shared__ float4 w_s4[];                       // [4 taps of the class][Cin][Cout]
   float* w_s = reinterpret_cast<float*>(w_s4);
   const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
@@ -522,9 +526,9 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
     const dim3 grid((M + 255) / 256, 1, 4);
     const size_t smem = (size_t)4 * Cin * Cout * sizeof(float);
     if (Cin <= 8)
-      conv_dgrad_small_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
+      launch_pdl(conv_dgrad_small_kernel<8>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
     else
-      conv_dgrad_small_kernel<20><<<grid, 256, smem, (cudaStream_t)stream>>>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
+      launch_pdl(conv_dgrad_small_kernel<20>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
     EXP_CHECK_LAUNCH("exp_conv_dgrad[small]");
     return EXP_OK;
   }
@@ -574,7 +578,7 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
                                                   (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_wgrad[tma]: %s", cudaGetErrorString(e));
     const size_t cnt = (size_t)16 * Cin * Cout;
-    splitk_reduce_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(splitk_reduce_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<float*>(workspace), splits, cnt, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
     EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
     return EXP_OK;
@@ -585,7 +589,7 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_wgrad[tcgen05]: %s", cudaGetErrorString(e));
     EXP_CHECK_LAUNCH("exp_conv_wgrad[tcgen05]");
     const size_t cnt = (size_t)16 * Cin * Cout;
-    splitk_reduce_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(splitk_reduce_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<float*>(workspace), splits, cnt, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
     EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
     return EXP_OK;
@@ -605,7 +609,7 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
   else launch_gemm<ConvWgrad, 64, true, false>(p, 16 * Cin, Cout, splits, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_conv_wgrad");
   const size_t count = (size_t)16 * Cin * Cout;
-  splitk_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(splitk_reduce_kernel, dim3((unsigned)((count + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       p.part, splits, count, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
   EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
   return EXP_OK;
@@ -639,7 +643,7 @@ int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_fc_fwd[tcgen05]: %s", cudaGetErrorString(e));
     EXP_CHECK_LAUNCH("exp_fc_fwd[tcgen05]");
     const size_t cnt = (size_t)M * N;
-    splitk_reduce_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(splitk_reduce_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<float*>(workspace), splits, cnt, N, bias, mask_ref, ldmask, mode, y, ldy, 0);
     EXP_CHECK_LAUNCH("exp_fc_fwd[reduce]");
     return EXP_OK;
@@ -653,7 +657,7 @@ int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const
   else launch_gemm<FcFwd, 64, false, false>(p, M, N, splits, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_fwd");
   const size_t count = (size_t)M * N;
-  splitk_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(splitk_reduce_kernel, dim3((unsigned)((count + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       p.part, splits, count, N, bias, mask_ref, ldmask, mode, y, ldy, 0);
   EXP_CHECK_LAUNCH("exp_fc_fwd[reduce]");
   return EXP_OK;
@@ -712,17 +716,17 @@ int exp_colsum(const float* a, int batch, int rows, int cols, float* out, void* 
   const int rpc = (rows + chunks - 1) / chunks;
   dim3 grid((cols + 31) / 32, batch, chunks);
   if (chunks == 1) {
-    colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, rpc, out);
+    launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a, rows, cols, rpc, out);
     EXP_CHECK_LAUNCH("exp_colsum");
     return EXP_OK;
   }
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, rows, cols, rpc, reinterpret_cast<float*>(workspace));
+  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, a, rows, cols, rpc, reinterpret_cast<float*>(workspace));
   EXP_CHECK_LAUNCH("exp_colsum");
   if (chunks <= 16) {
-    colsum_finish_kernel<<<(batch * cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(colsum_finish_kernel, dim3((batch * cols + 255) / 256), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<const float*>(workspace), chunks, cols, batch, out);
   } else {
-    colsum_kernel<<<dim3((cols + 31) / 32, batch, 1), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(colsum_kernel, dim3(dim3((cols + 31) / 32, batch, 1)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<const float*>(workspace), chunks, cols, chunks, out);
   }
   EXP_CHECK_LAUNCH("exp_colsum[finish]");

@@ -328,6 +328,7 @@ static bool make_conv1_map(CUtensorMap* m, const float* xp, int B, int IH, int I
 template <int CP, int BORDER>
 __global__ void conv_stage_input_kernel(const float* __restrict__ x, const float* __restrict__ vec, float shift,
                                         float* __restrict__ xp, int B, int IH, int IW, int Cx, int Cv) {
+  EXP_PDL_ENTRY();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;          // one (padded) pixel per thread
   const int PW = IW + 2 * BORDER, PH = IH + 2 * BORDER;
   const size_t total = (size_t)B * PH * PW;
@@ -350,6 +351,7 @@ __global__ void conv_stage_input_kernel(const float* __restrict__ x, const float
 
 // Wp[tap][cp][co] = W[tap][c][co] for c < Cin, 0 above
 __global__ void conv_pad_weights_kernel(const float* __restrict__ W, float* __restrict__ Wp, int Cin, int Cout, int CP) {
+  EXP_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;                     // over [16 taps][CP][Cout]
   if (i >= 16 * CP * Cout) return;
   const int co = i % Cout, c = (i / Cout) % CP, tap = i / (Cout * CP);
@@ -359,6 +361,7 @@ __global__ void conv_pad_weights_kernel(const float* __restrict__ W, float* __re
 // gW[tap][ci][co] (=|+=) sum_z part[z][tap*16 + ci][co], ci < Cin, in z order
 __global__ void conv1_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int Cin, int Cout,
                                           float* __restrict__ gW, int accumulate) {
+  EXP_PDL_ENTRY();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 16 * Cin * Cout) return;
   const int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
@@ -395,7 +398,7 @@ int exp_conv1_pad_input(const float* x, int Cx, const float* vec, int Cv, float 
   EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cx + Cv <= kC1, "first-layer staging holds at most %d channels", kC1);
   EXP_CHECK_ARG((reinterpret_cast<uintptr_t>(xp) & 15u) == 0, "xp must be 16-byte aligned");
   const size_t total = (size_t)B * (IH + 2) * (IW + 2);
-  conv_stage_input_kernel<kC1, 1><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, vec, shift, xp, B, IH, IW, Cx, Cv);
+  launch_pdl(conv_stage_input_kernel<kC1, 1>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, vec, shift, xp, B, IH, IW, Cx, Cv);
   EXP_CHECK_LAUNCH("exp_conv1_pad_input");
   return EXP_OK;
 }
@@ -403,7 +406,7 @@ int exp_conv1_pad_input(const float* x, int Cx, const float* vec, int Cv, float 
 int exp_conv1_pad_weights(const float* W, int Cin, int Cout, float* Wp, void* stream) {
   EXP_CHECK_ARG(W && Wp && Cin > 0 && Cin <= kC1 && Cout > 0, "bad args");
   const int n = 16 * kC1 * Cout;
-  conv_pad_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, Wp, Cin, Cout, kC1);
+  launch_pdl(conv_pad_weights_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, W, Wp, Cin, Cout, kC1);
   EXP_CHECK_LAUNCH("exp_conv1_pad_weights");
   return EXP_OK;
 }
@@ -414,7 +417,7 @@ int exp_conv_enrich32(const float* x, int Cx, const float* vec, int Cv, float sh
   EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cx + Cv <= 32, "at most 32 channels");
   EXP_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "out must be 16-byte aligned");
   const size_t total = (size_t)B * IH * IW;
-  conv_stage_input_kernel<32, 0><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, vec, shift, out, B, IH, IW, Cx, Cv);
+  launch_pdl(conv_stage_input_kernel<32, 0>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, vec, shift, out, B, IH, IW, Cx, Cv);
   EXP_CHECK_LAUNCH("exp_conv_enrich32");
   return EXP_OK;
 }
@@ -422,7 +425,7 @@ int exp_conv_enrich32(const float* x, int Cx, const float* vec, int Cv, float sh
 int exp_conv_pad_weights32(const float* W, int Cin, int Cout, float* Wp, void* stream) {
   EXP_CHECK_ARG(W && Wp && Cin > 0 && Cin <= 32 && Cout > 0, "bad args");
   const int n = 16 * 32 * Cout;
-  conv_pad_weights_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, Wp, Cin, Cout, 32);
+  launch_pdl(conv_pad_weights_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, W, Wp, Cin, Cout, 32);
   EXP_CHECK_LAUNCH("exp_conv_pad_weights32");
   return EXP_OK;
 }
@@ -501,7 +504,7 @@ int exp_conv1_wgrad(const float* xp, const float* dy, float* gW, int Cin, int B,
   else e = tma::launch_tma_auto<TmaConvWgrad, 32>(p, M, Cout, splits, (cudaStream_t)stream);
   if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv1_wgrad: %s", cudaGetErrorString(e));
   const int n = 16 * Cin * Cout;
-  conv1_wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p.part, splits, Cin, Cout, gW, accumulate);
+  launch_pdl(conv1_wgrad_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, p.part, splits, Cin, Cout, gW, accumulate);
   EXP_CHECK_LAUNCH("exp_conv1_wgrad[reduce]");
   return EXP_OK;
 }

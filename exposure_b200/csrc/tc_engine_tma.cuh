@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
   __shared__ __align__(8) uint64_t accum;
   __shared__ uint32_t tmem_base_s;
 
+  pdl_trigger();                                              // dependents may start their prologue now
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.splits;
   const int z = blockIdx.z / S;                               // problem slice
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();                                                 // prologue done; the predecessor's writes are visible from here
   const uint32_t tmem_acc = tmem_base_s;
   const int KI_all = p.k_iters(z);
   const int per = (KI_all + S - 1) / S;
@@ -292,22 +294,24 @@ inline cudaError_t launch_tma_gemm_ns(const P& p, dim3 grid, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (p.splits <= 1) {
-    tma_gemm_kernel<P, BN, NS_><<<grid, kThreads, smem, st>>>(p);
-    return cudaGetLastError();
-  }
+  if (p.splits <= 1) return launch_pdl(tma_gemm_kernel<P, BN, NS_>, grid, dim3(kThreads), smem, st, p);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = 1;
-  attr.val.clusterDim.y = 1;
-  attr.val.clusterDim.z = (unsigned)p.splits;
-  cfg.attrs = &attr;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)p.splits;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
   return cudaLaunchKernelEx(&cfg, tma_gemm_kernel<P, BN, NS_>, p);
 }
 

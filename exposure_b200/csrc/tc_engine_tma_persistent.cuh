@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* base = tma_smem_p + ((1024u - (smem_u32(tma_smem_p) & 1023u)) & 1023u);
 
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  pdl_wait();                                                 // the predecessor's writes are visible from here
   const uint32_t tmem_acc = tmem_base_s;
 
   // tile t -> (mx, ny, z): M fastest so that neighbouring CTAs share the B (weight) tile in L2
@@ -200,7 +202,7 @@ inline cudaError_t launch_tma_gemm_persistent(const P& p, int M, int N, int Z, c
   const int MX = (M + kBM - 1) / kBM, NY = (N + BN - 1) / BN;
   const int tiles = MX * NY * Z;
   const int grid = tiles < 148 ? tiles : 148;
-  tma_gemm_persistent_kernel<P, BN><<<grid, kPersistThreads, smem, st>>>(p, MX, NY, tiles);
+  launch_pdl(tma_gemm_persistent_kernel<P, BN>, dim3(grid), dim3(kPersistThreads), smem, st, p, MX, NY, tiles);
   return cudaGetLastError();
 }
 

@@ -299,6 +299,14 @@ def test_host_pipelined_chain_matches_resident(ops):
     assert torch.equal(hy, y.cpu())
     for a, b in zip(hg, gl):
       assert torch.equal(a, b.cpu())
+  # enqueue-only steps (consecutive steps overlap), results after wait()
+  hy.zero_()
+  for _ in range(3):
+    pipe.step(hx, lgs, gout, hy, hg, wait=False)
+  pipe.wait()
+  assert torch.equal(hy, y.cpu())
+  for a, b in zip(hg, gl):
+    assert torch.equal(a, b.cpu())
 
 
 MASK_KW = dict(maximum_sharpness=1.5, minimum_strength=0.3)

@@ -302,8 +302,13 @@ class PolicyNet:
     c = _Ctx()
     c.img, c.states, c.progress, c.cfg = img, states, progress, cfg
     c.drop_f, c.drop_s = drop_f, drop_s
+    # the action-selection tower (agent.py:80-99) has its own weights and only meets the filter-head
+    # tower at the policy head: a parallel branch
+    with K.fork(6):
+      c.s = self.se.forward(img, states, drop_mul=drop_s)
+      c.hs = K.fc_fwd(c.s.feat, p[self.sfc1 + "/weights"], p[self.sfc1 + "/biases"], mode=K.FC_LRELU)
+      c.sel_logits = K.fc_fwd(c.hs, p[self.sfc2 + "/weights"], p[self.sfc2 + "/biases"], mode=K.FC_LINEAR)
     c.f = self.fe.forward(img, states, drop_mul=drop_f)
-    c.s = self.se.forward(img, states, drop_mul=drop_s)
     # filter heads (filters.py:28-44)
     c.H = K.fc_fwd(c.f.feat, p[self.fc1_all + "/weights"], p[self.fc1_all + "/biases"], mode=K.FC_LRELU)
     c.O = torch.zeros(B, self.n_filters, self.ostride, device=img.device)
@@ -311,9 +316,8 @@ class PolicyNet:
     for j, name in enumerate(self.fc2):
       K.fc_fwd(c.H[:, j * FC1:(j + 1) * FC1], p[name + "/weights"], p[name + "/biases"], mode=K.FC_LINEAR,
                out=Oflat[:, j * self.ostride:j * self.ostride + self.out_dims[j]])
-    # action selection (agent.py:80-122)
-    c.hs = K.fc_fwd(c.s.feat, p[self.sfc1 + "/weights"], p[self.sfc1 + "/biases"], mode=K.FC_LRELU)
-    c.sel_logits = K.fc_fwd(c.hs, p[self.sfc2 + "/weights"], p[self.sfc2 + "/biases"], mode=K.FC_LINEAR)
+    K.join()
+    # action selection (agent.py:100-122)
     c.pdf, c.ids, c.surrogate, c.entropy, c.pen_head, c.new_states = K.policy_head_fwd(
         c.sel_logits, noise, states, is_train, progress, cfg)
     # only the selected filter is evaluated (agent.py:124-125 computes all 8 and one-hot sums)
@@ -368,8 +372,9 @@ class PolicyNet:
     for j, name in enumerate(self.fc2):
       dy = G_Oflat[:, j * self.ostride:j * self.ostride + self.out_dims[j]]
       Hj = c.H[:, j * FC1:(j + 1) * FC1]
-      K.fc_wgrad(Hj, dy, out=g[name + "/weights"])
-      g[name + "/biases"].copy_(dy.sum(dim=0))
+      with K.fork(j & 1):                 # the head's own gradients are leaves: off the dgrad chain
+        K.fc_wgrad(Hj, dy, out=g[name + "/weights"])
+        g[name + "/biases"].copy_(dy.sum(dim=0))
       K.fc_dgrad(dy, p[name + "/weights"], mul_act=Hj, out=d_H[:, j * FC1:(j + 1) * FC1])
     K.fc_wgrad(c.f.feat, d_H, out=g[self.fc1_all + "/weights"])
     K.colsum(d_H, out=g[self.fc1_all + "/biases"])

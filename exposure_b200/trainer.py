@@ -54,6 +54,7 @@ class Trainer:
     self.critic = CriticNet(self.cri, "critic", n_states=0)
     self.cri.finalize(seed + 2)
     self.counter_g = self.counter_v = self.counter_c = 0        # net.py:216-241 global steps
+    self._g_logit_cache = {}
     self._hyper = {k: torch.zeros(1, device=self.device) for k in "gvc"}
     self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
@@ -149,8 +150,9 @@ class Trainer:
     with K.fork(5):
       v_old = self.value.forward(fake_input, states)             # old_value             net.py:79-84
     c = self.policy.forward(fake_input, states, noise, drop_f, drop_s, is_train, progress, self.cfg)
+    with K.fork(5):                                              # the two passes over the OUTPUT batch: parallel
+      v_new = self.value.forward(c.out, c.new_states)            # new_value             net.py:85-90
     cc_out = self.critic.forward(c.out)                          # fake_logit            net.py:70-71
-    v_new = self.value.forward(c.out, c.new_states)              # new_value             net.py:85-90
     K.join()
     seeds, losses = K.rl_losses(cc_out.logit.view(-1), cc_in.logit.view(-1), v_old.logit.view(-1),
                                 v_new.logit.view(-1), c.penalty, c.surrogate, c.new_states, self.cfg)
@@ -195,10 +197,13 @@ class Trainer:
     xhat = K.interpolate(real, fake, alpha)
     X = torch.cat([real, fake, xhat], dim=0)
     c = self.critic.forward(X)
-    g_logit = torch.empty(3 * B, device=real.device)
-    g_logit[:B] = -1.0 / B
-    g_logit[B:2 * B] = 1.0 / B
-    g_logit[2 * B:] = 1.0
+    g_logit = self._g_logit_cache.get(B)                          # constant seeds: d c_loss / d logit
+    if g_logit is None:
+      g_logit = torch.empty(3 * B, device=real.device)
+      g_logit[:B] = -1.0 / B
+      g_logit[B:2 * B] = 1.0 / B
+      g_logit[2 * B:] = 1.0
+      self._g_logit_cache[B] = g_logit
     # the weight / bias gradients forked inside backward() keep running on their side streams while
     # the gradient-penalty chain (image gradient -> tangent pass) proceeds; the penalty's own wgrads
     # go to the same side stream per layer, so the accumulation order is fixed
@@ -210,11 +215,14 @@ class Trainer:
       if lam > 0:
         self.critic.gradient_penalty_grads(c, sl, u)
     logit = c.logit.view(-1)
-    emd = logit[:B].mean() - logit[B:2 * B].mean()               # net.py:164  emd = -c_loss (before GP)
-    gp = lam * (torch.clamp(norm - 1.0, min=0.0) ** 2).mean()
+    with K.fork(7):                                              # logging scalars: off the optimizer's path
+      emd = logit[:B].mean() - logit[B:2 * B].mean()             # net.py:164  emd = -c_loss (before GP)
+      gp = lam * (torch.clamp(norm - 1.0, min=0.0) ** 2).mean()
+      out = dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit)
     if apply:
       self._adam(self.cri, "c")
-    return dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit)
+    K.join()
+    return out
 
   # ---- GAN.train's inner loop (net.py:307-370): 1 generator+value step, cfg.citers critic steps
   def attach_memory(self, memory, generator=None):

@@ -76,5 +76,34 @@ def full(src, dst, note=""):
   print(open(dst).read()[:3000])
 
 
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+FNAMES = ("exposure", "gamma", "wb", "satplus", "tone", "contrast", "wnb", "color", "level", "vignet")
+
+
+def traffic(src, dst, config):
+  """DRAM bytes per launch of every filter_step_tma_kernel in an `ncu --set full` report ->
+  the small JSON bench.py reads to fill roofline.traffic (keys = bench.py's kernel names)."""
+  import json
+  out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+  rows = list(csv.reader(out.splitlines()))
+  hdr, units = rows[0], rows[1]
+  idx = {h: i for i, h in enumerate(hdr)}
+  res = {}
+  for r in rows[2:]:
+    m = re.search(r"filter_step_tma_kernel<(?:\(int\))?(\d+), (?:\(bool\))?(\w+), (?:\(bool\))?(\w+)", r[idx["Kernel Name"]])
+    if not m:
+      continue
+    fid, bwd, gx = int(m.group(1)), m.group(2) in ("1", "true"), m.group(3) in ("1", "true")
+    name = ("filter_bwd_" if bwd and gx else "filter_bwd_paramonly_" if bwd else "filter_fwd_") + FNAMES[fid]
+    rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT[units[idx["dram__bytes_read.sum"]]]
+    wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
+    res[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
+                 "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]])}
+  json.dump({"source": src, "config": config, "note": "ncu --set full --clock-control none, one launch each; "
+             "writes still in L2 at kernel end are not counted by dram__bytes_write", "kernels": res},
+            open(dst, "w"), indent=1, sort_keys=True)
+  print(open(dst).read()[:1500])
+
+
 if __name__ == "__main__":
-  {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
+  {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

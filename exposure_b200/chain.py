@@ -128,8 +128,18 @@ class HostPipelinedChain:
     self.ids, self.chunks, self.cb = list(ids), chunks, batch // chunks
     self.device = device
     self.sub = [FilterChain(ids, variant=variant) for _ in range(chunks)]
+    # the parameter gradients of all steps of a sub-batch live in ONE flat device buffer so that they
+    # leave in one D2H copy per sub-batch (a copy per step costs more in launch overhead than in bytes)
+    self.nk = [ops.NUM_PARAMS[f] if isinstance(f, int) else ops.PSTRIDE for f in self.ids]
+    self.off = [0]
+    for n in self.nk:
+      self.off.append(self.off[-1] + self.cb * n)
     for ch in self.sub:
       ch.input_buffer((self.cb, height, width, 3), device)
+      ch._glog_flat = torch.zeros(self.off[-1], device=device)
+      ch._glog = [ch._glog_flat[self.off[k]:self.off[k + 1]].view(self.cb, n) for k, n in enumerate(self.nk)]
+    self.h_glog = torch.empty(chunks, self.off[-1]).pin_memory()
+    self._scatter_to = None
     self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
     self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
     self.ev_cmp = [torch.cuda.Event() for _ in range(chunks)]
@@ -143,6 +153,8 @@ class HostPipelinedChain:
     H2D copies of the next step overlap this step's compute and D2H -- consecutive steps keep both
     PCIe directions busy without a fill / drain bubble per step."""
     cb = self.cb
+    if [int(l.shape[1]) for l in logits_list] != self.nk:
+      raise ValueError("logits_list[k] must be [B, %s] (one column per filter parameter)" % self.nk)
     cur = torch.cuda.current_stream()
     for s in (self.s_in, self.s_cmp, self.s_out):
       s.wait_stream(cur)
@@ -158,20 +170,26 @@ class HostPipelinedChain:
         if not self._first:
           self.s_cmp.wait_event(self.ev_out[c])         # previous step's D2H of this chunk's outputs is done
         y = ch.forward_resident([l[sl] for l in logits_list])
-        _, gl = ch.backward(gout[sl], need_input_grad=True)
+        ch.backward(gout[sl], need_input_grad=True)
         self.ev_cmp[c].record(self.s_cmp)
       with torch.cuda.stream(self.s_out):
         self.s_out.wait_event(self.ev_cmp[c])
         hy[sl].copy_(y, non_blocking=True)
-        for h, g in zip(hglogits, gl):
-          h[sl].copy_(g, non_blocking=True)
+        self.h_glog[c].copy_(ch._glog_flat, non_blocking=True)
         self.ev_out[c].record(self.s_out)
     self._first = False
+    self._scatter_to = hglogits
     if wait:
       self.wait()
 
   def wait(self):
-    """Block until every enqueued step has delivered its results to host memory."""
+    """Block until every enqueued step has delivered its results to host memory (hy of every step;
+    hglogits of the most recent step)."""
     cur = torch.cuda.current_stream()
     cur.wait_stream(self.s_out)
     cur.synchronize()
+    if self._scatter_to is not None:
+      cb = self.cb
+      for k, (h, n) in enumerate(zip(self._scatter_to, self.nk)):
+        h.view(self.chunks, cb, n).copy_(self.h_glog[:, self.off[k]:self.off[k + 1]].view(self.chunks, cb, n))
+      self._scatter_to = None

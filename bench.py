@@ -320,8 +320,20 @@ def run_native(args):
   tot_ms = sum(d["ms"] for d in per.values())
   tot_bytes = sum(d["bytes"] for d in per.values())
   dom = kernels[0]
+  # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this
+  # same command (profiles/filter_traffic.json, written by profiles/summarize.py traffic); only valid
+  # for the shape it was captured on
+  traffic, traffic_src = None, None
+  try:
+    tj = json.load(open(os.path.join(ROOT, "profiles", "filter_traffic.json")))
+    if tj.get("config") == "chain8 %dx%dx%dx3 fp32" % (B, H, W) and dom["kernel"] in tj["kernels"]:
+      traffic = tj["kernels"][dom["kernel"]]["traffic_bytes"]
+      traffic_src = "profiles/filter_traffic.json (%s): dram__bytes_read.sum + dram__bytes_write.sum of one launch" % tj["source"]
+  except (OSError, ValueError, KeyError):
+    pass
   roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
-              "unit": "GB/s", "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+              "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
+              "peak_source": peak_src,
               "share_of_step": dom["avg_ms"] * dom["launches"] / eager_ms if eager_ms else None,
               "chain": {"achieved": tot_bytes / tot_ms / 1e6, "frac": tot_bytes / tot_ms / 1e6 / peak,
                         "algorithmic_bytes_per_step": B * H * W * (FWD_B + BWD_B) * len(CHAIN_IDS),

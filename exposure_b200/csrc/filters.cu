@@ -25,8 +25,10 @@ constexpr int kMaxImages = 65536;
 constexpr size_t kCounterBytes = (size_t)kMaxImages * sizeof(unsigned);
 constexpr int kMaxPersistentCtas = 4096;  // upper bound on the TMA variant's grid
 
-// process-wide PDL switch (common.cuh launch_pdl): default on, EXPOSURE_PDL=0 or exp_set_pdl(0) turns it off
-static int g_pdl = [] { const char* e = getenv("EXPOSURE_PDL"); return e ? atoi(e) : 1; }();
+// process-wide PDL switch (common.cuh launch_pdl): default OFF -- measured on B200 the train iteration is
+// GPU-throughput bound (93 % busy, profiles/r1d_train_timeline.md), early-resident dependents only take
+// SM slots from the parallel graph branches (6.31 -> 6.51 ms); EXPOSURE_PDL=1 / exp_set_pdl(1) turns it on
+static int g_pdl = [] { const char* e = getenv("EXPOSURE_PDL"); return e ? atoi(e) : 0; }();
 bool pdl_enabled() { return g_pdl != 0; }
 void set_pdl(int on) { g_pdl = on; }
 

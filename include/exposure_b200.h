@@ -75,11 +75,12 @@ enum {
 int exp_version(void);               /* ABI version, currently 1                       */
 const char* exp_last_error(void);    /* thread-local message of the last failure       */
 int exp_num_filter_params(int filter_id); /* n of the table above, or EXP_ERR_INVALID_ARG */
-/* Programmatic dependent launch (process-wide; default on, environment EXPOSURE_PDL=0 turns it off):
+/* Programmatic dependent launch (process-wide; default OFF, environment EXPOSURE_PDL=1 turns it on):
  * the library's kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that
  * on a stream -- and inside a CUDA graph captured from it -- a kernel's prologue overlaps the tail of
  * its predecessor.  Every kernel waits (griddepcontrol.wait) before its first global-memory access,
- * so results are identical with the switch on or off. */
+ * so results are identical with the switch on or off.  Off by default because the measured train
+ * iteration is not launch-gap bound. */
 int exp_set_pdl(int enable);
 
 /* ---- filter_param_regressor (per image, tiny) -------------------------------------

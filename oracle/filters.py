@@ -5,8 +5,9 @@ tensors.  The same code runs in float32 (the reference's execution dtype; this i
 "CPU restatement of the reference TF graph") and in float64 (the arbiter used when the
 fp32 formula itself is ill-conditioned, e.g. ContrastFilter's ``-cos(pi*l)*0.5+0.5``).
 
-PARITY UNPINNED: nothing in the reference pins these numbers (no golden vectors, TF not
-runnable here).  Numerics that live in TensorFlow 1.6 rather than in the repo
+PARITY: pinned to the reference's own filters.py executed over a TF-1 API stand-in
+(tests/test_reference_golden.py; see oracle/__init__.py), not to TF binaries.
+Numerics that live in TensorFlow 1.6 rather than in the repo
 (``tf.image.rgb_to_hsv`` / ``hsv_to_rgb`` -- tensorflow/core/kernels/colorspace_op.h,
 ``tf.clip_by_value`` tie rules, ``tf.maximum``/``tf.minimum`` gradients) are restated
 from TF's published kernel definitions.

@@ -1,5 +1,6 @@
 """CPU oracle for the policy / critic / value networks -- TEST INFRASTRUCTURE ONLY
-(see oracle/__init__.py; PARITY UNPINNED).
+(see oracle/__init__.py: pinned to the reference's agent.py / critics.py executed over a TF-1
+API stand-in, tests/test_reference_golden.py; not to TF binaries).
 
 torch-CPU restatement of agent.py:11-37 (feature_extractor), critics.py:6-98 (cnn, critic),
 filters.py:28-44 (extract_parameters), pdf_sample_layer.py:5-10, agent.py:41-260 and the

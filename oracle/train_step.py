@@ -1,4 +1,5 @@
-"""CPU oracle of the train step -- TEST INFRASTRUCTURE ONLY (PARITY UNPINNED, see oracle/__init__.py).
+"""CPU oracle of the train step -- TEST INFRASTRUCTURE ONLY (parity: see oracle/__init__.py --
+pinned to the reference's Python over a TF-1 API stand-in, tests/test_reference_golden.py).
 
 torch-CPU restatement of the generator+value step and the critic step of net.py:56-199 with
 autograd supplying every gradient (tf.gradients), executed the way the reference executes it:

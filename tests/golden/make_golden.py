@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Generates tests/golden/filters_golden.npz from the oracle (fp64), seeded.
 
-PARITY UNPINNED: the reference ships no golden vectors and cannot run here, so these vectors pin
-the ORACLE (oracle/filters.py) against drift and give the CUDA kernels a fixed target that does
-not depend on re-running the oracle; they are not outputs of the TensorFlow reference.
+These vectors come from the ORACLE (oracle/filters.py), not from the reference: they guard the oracle
+against drift and give the CUDA kernels a fixed target that does not depend on re-running it.  The
+vectors that come from executing the reference's own Python are tests/golden/reference_golden.npz
+(make_reference_golden.py).
 
   python tests/golden/make_golden.py
 """

@@ -8,7 +8,9 @@ Tolerances (stated once, used everywhere below):
      result must also be no farther from the fp64 oracle than 4x the fp32 oracle is.
   image gradient   |gx - ref64| <= 1e-4 * max(|ref64|, 1e-3 * max|ref64|)
   param gradient   |gp - ref64| <= 1e-4 * max(|ref64|, 1e-3 * sum|terms|)
-ref32 / ref64 = oracle/filters.py in float32 / float64.  PARITY UNPINNED (see oracle/)."""
+ref32 / ref64 = oracle/filters.py in float32 / float64 (pinned to the reference's Python by
+tests/test_reference_golden.py; the CUDA path is also compared with that fixture directly in
+tests/test_reference_golden_gpu.py)."""
 import numpy as np
 import pytest
 import torch

@@ -1,5 +1,5 @@
 """Committed golden vectors (tests/golden/filters_golden.npz, made by tests/golden/make_golden.py
-from the fp64 oracle; PARITY UNPINNED -- they are not TensorFlow outputs):
+from the fp64 oracle -- oracle outputs, not reference outputs; those are in test_reference_golden*.py):
   CPU: the oracle still reproduces them (guards the oracle against drift);
   GPU: the CUDA kernels reproduce them through the C ABI."""
 import os

@@ -1,6 +1,6 @@
-"""CPU tests of the oracle itself (the oracle is test infrastructure; PARITY UNPINNED --
-the reference has no golden vectors, so the oracle is pinned by self-consistency:
-fp32-vs-fp64 agreement, autograd-vs-closed-form gradients, finite differences, invariants)."""
+"""CPU tests of the oracle itself (the oracle is test infrastructure): self-consistency --
+fp32-vs-fp64 agreement, autograd-vs-closed-form gradients, finite differences, invariants.  The pin
+against the reference's own Python is tests/test_reference_golden.py."""
 import numpy as np
 import pytest
 import torch

@@ -123,8 +123,8 @@ __device__ __forceinline__ void regress_image(int fid, const float* f, float* po
 // Executed by the first warp of a CTA; followed by __syncthreads() at the call site.
 // logits != 0: prow holds raw regressor logits; the regressed parameters are computed here
 // (fused filter_param_regressor) and the logits kept for the backward's chain rule.
-__device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits = 0) {
-  const int t = threadIdx.x;
+// `t` = lane of the warp doing the set-up (the fused-chain kernel gives every step its own warp).
+__device__ __forceinline__ void setup_consts_lane(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits, int t) {
   const int n = num_params(fid);
   if (logits) {
     if (t < EXP_MAX_FILTER_PARAMS) { sc.raw[t] = (t < n) ? prow[t] : 0.f; sc.p[t] = 0.f; }
@@ -163,6 +163,10 @@ __device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __re
     }
     sc.slope[t][2 * kCurveSteps + 3] = sc.p[t * kCurveSteps + kCurveSteps - 1] * scale;
   }
+}
+
+__device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits = 0) {
+  setup_consts_lane(sc, prow, fid, logits, (int)threadIdx.x);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }

@@ -420,6 +420,229 @@ __global__ void __launch_bounds__(kThreads) filter_chain_fwd_kernel(const ChainA
   }
 }
 
+// ---- whole chain forward + backward in ONE pass over the pixels ------------------------------
+// y = f_{S-1}(.. f_0(x)), gx = (dy/dx)^T gy and the parameter gradients of every step, from one read of
+// x and gy: 24 B/pixel in, 12 (+12 for y) out for the WHOLE chain instead of 60 B/pixel/step
+// (SURVEY 8d "fully chain-fused variant").  Per 1024-pixel tile: the forward sweeps the S steps with
+// the pixels in registers and parks every step's input in shared memory (S x 12 KiB); the backward
+// walks the steps in reverse, reading its input back from shared memory, so nothing but x, gy, gx (and
+// y) ever touches HBM and no step is recomputed.  The kernel is instruction-bound, not HBM-bound.
+// Filter ids are per image and per step (run time): the step loop is a `switch` over the per-filter
+// bodies, so the parameter-gradient accumulators cannot live in registers across steps.  They are
+// reduced per tile-step with a multi-value butterfly (N values in N-1+log.. shuffles instead of 5 N)
+// into per-warp shared-memory slots owned by one lane each -> deterministic; CTA partial records and
+// the last-CTA fixed-order fp64 finish are those of the per-step kernels.
+constexpr int kChainRec = kMaxChain * EXP_MAX_FILTER_PARAMS;   // floats per CTA partial record (worst case)
+struct ChainBwdArgs {
+  const float* x; const float* gy; float* y; float* gx;          // y, gx nullable
+  const float* params; const int* ids; float* gparams;           // [S][B][pstride], [S][B], [S][B][pstride]
+  float* partials; unsigned* counters;
+  int S, B, P, pstride, logits, nblk, ntiles;
+};
+
+// Sum N (power of two) per-lane values over the warp.  Afterwards the lanes with (lane & (32/N - 1)) == 0
+// ... hold the total of value index `idx` (returned); every stage halves the values a lane carries.
+template <int N>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[N], int lane, int& idx) {
+  idx = 0;
+  int n = N;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    if (n > 1) {
+      const bool up = (lane & d) != 0;
+      const int h = n >> 1;
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < h) {
+          const float send = up ? v[i] : v[i + h];
+          const float keep = up ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+      }
+      if (up) idx += h;
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+    }
+  }
+  return v[0];
+}
+
+template <int FID, int NPX>
+__device__ __forceinline__ void chain_bwd_step(const float (&px)[4][3], float (&g)[4][3], const FilterConsts& sc,
+                                               float* __restrict__ slots, int lane) {
+  constexpr int NACC = num_acc(FID);
+  float acc[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPX; ++i) {
+    float gx[3];
+    px_bwd<FID, true>(px[i], g[i], gx, acc, sc);
+    g[i][0] = gx[0]; g[i][1] = gx[1]; g[i][2] = gx[2];
+  }
+  // rows of <= 8 accumulators: one butterfly per row (E,G,S+,Ct,BW,V: 1 value; W: 3 -> 4; Le: 2; T: 8; C: 3 x 8)
+  constexpr int ROW = NACC >= 8 ? 8 : NACC == 3 ? 4 : NACC;
+  constexpr int ROWS = (NACC + ROW - 1) / ROW;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float v[ROW];
+#pragma unroll
+    for (int i = 0; i < ROW; ++i) v[i] = (r * ROW + i < NACC) ? acc[r * ROW + i] : 0.f;
+    int idx;
+    const float tot = warp_multi_sum<ROW>(v, lane, idx);
+    if ((lane & (32 / ROW - 1)) == 0 && r * ROW + idx < NACC) slots[r * ROW + idx] += tot;   // one owner lane per slot
+  }
+}
+
+template <int NPX>
+__device__ __forceinline__ void chain_bwd_any(int fid, const float (&px)[4][3], float (&g)[4][3], const FilterConsts& sc,
+                                              float* __restrict__ slots, int lane) {
+  switch (fid) {
+#define EXP_CASE(F) case F: chain_bwd_step<F, NPX>(px, g, sc, slots, lane); break;
+    EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7) EXP_CASE(8) EXP_CASE(9)
+#undef EXP_CASE
+    default:                                   // id -1: the output is black whatever the input -> zero gradient
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i][0] = g[i][1] = g[i][2] = 0.f;
+      break;
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const ChainBwdArgs A) {
+  constexpr int NPX = VEC ? 4 : 1;
+  extern __shared__ __align__(16) unsigned char chain_smem[];
+  __shared__ FilterConsts sc[kMaxChain];
+  __shared__ int fids[kMaxChain], off[kMaxChain + 1];
+  __shared__ float slots[kWarps][kChainRec];
+  // parked step inputs: [S][NPX * 3][kThreads] floats (as float4 [S][3][kThreads] when VEC)
+  float* const park = reinterpret_cast<float*>(chain_smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  for (int s = warp; s < A.S; s += kWarps) {               // one warp per step: the S set-ups run in parallel
+    const int f = A.ids[s * A.B + b];
+    if (lane == 0) fids[s] = (f >= 0 && f < EXP_NUM_FILTER_KINDS) ? f : -1;
+    if (f >= 0 && f < EXP_NUM_FILTER_KINDS)
+      setup_consts_lane(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits, lane);
+  }
+  for (int i = tid; i < kWarps * kChainRec; i += kThreads) (&slots[0][0])[i] = 0.f;
+  __syncthreads();
+  if (tid == 0) {
+    int o = 0;
+    for (int s = 0; s < A.S; ++s) { off[s] = o; o += fids[s] >= 0 ? num_acc(fids[s]) : 0; }
+    off[A.S] = o;
+  }
+  __syncthreads();
+
+  const size_t img = (size_t)b * A.P * 3;
+  const float* __restrict__ x = A.x + img;
+  const float* __restrict__ gy = A.gy + img;
+  float* __restrict__ y = A.y ? A.y + img : nullptr;
+  float* __restrict__ gxo = A.gx ? A.gx + img : nullptr;
+  const int t0 = (int)((long long)blockIdx.x * A.ntiles / A.nblk);
+  const int t1 = (int)((long long)(blockIdx.x + 1) * A.ntiles / A.nblk);
+  const int nq = VEC ? (A.P >> 2) : A.P;                   // work items (4-pixel groups or pixels) per image
+
+  for (int t = t0; t < t1; ++t) {
+    const int q = t * kThreads + tid;
+    const bool live = q < nq;                              // all lanes stay in the loop: the butterflies need the full warp
+    float px[4][3], g[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) px[i][0] = px[i][1] = px[i][2] = g[i][0] = g[i][1] = g[i][2] = 0.f;
+    if (live) {
+      if constexpr (VEC) {
+        unpack(load_px4(x, q), px);
+      } else {
+        px[0][0] = x[3 * (size_t)q]; px[0][1] = x[3 * (size_t)q + 1]; px[0][2] = x[3 * (size_t)q + 2];
+      }
+    }
+    // ---- forward sweep: park the input of every step ----
+    for (int s = 0; s < A.S; ++s) {
+      if constexpr (VEC) {
+        float4* pk = reinterpret_cast<float4*>(park) + (size_t)s * 3 * kThreads + tid;
+        const Px4 v = pack(px);
+        pk[0] = v.a; pk[kThreads] = v.b; pk[2 * kThreads] = v.c;
+      } else {
+        float* pk = park + (size_t)s * 3 * kThreads + tid;
+        pk[0] = px[0][0]; pk[kThreads] = px[0][1]; pk[2 * kThreads] = px[0][2];
+      }
+      chain_apply_any(fids[s], px, sc[s], NPX);
+    }
+    if (live) {
+      if constexpr (VEC) {
+        if (y) store_px4(y, q, pack(px));
+        unpack(load_px4(gy, q), g);
+      } else {
+        if (y) { y[3 * (size_t)q] = px[0][0]; y[3 * (size_t)q + 1] = px[0][1]; y[3 * (size_t)q + 2] = px[0][2]; }
+        g[0][0] = gy[3 * (size_t)q]; g[0][1] = gy[3 * (size_t)q + 1]; g[0][2] = gy[3 * (size_t)q + 2];
+      }
+    }
+    // ---- backward sweep (dead lanes carry g == 0: every accumulator term is a multiple of g) ----
+    for (int s = A.S - 1; s >= 0; --s) {
+      if constexpr (VEC) {
+        const float4* pk = reinterpret_cast<const float4*>(park) + (size_t)s * 3 * kThreads + tid;
+        Px4 v;
+        v.a = pk[0]; v.b = pk[kThreads]; v.c = pk[2 * kThreads];
+        unpack(v, px);
+      } else {
+        const float* pk = park + (size_t)s * 3 * kThreads + tid;
+        px[0][0] = pk[0]; px[0][1] = pk[kThreads]; px[0][2] = pk[2 * kThreads];
+      }
+      chain_bwd_any<NPX>(fids[s], px, g, sc[s], &slots[warp][off[s]], lane);
+    }
+    if (live && gxo) {
+      if constexpr (VEC) {
+        store_px4(gxo, q, pack(g));
+      } else {
+        gxo[3 * (size_t)q] = g[0][0]; gxo[3 * (size_t)q + 1] = g[0][1]; gxo[3 * (size_t)q + 2] = g[0][2];
+      }
+    }
+  }
+
+  // ---- CTA record (warps summed in fixed order), ticket, last CTA of the image finishes in fp64 ----
+  __syncthreads();
+  const int ntot = off[A.S];
+  float* rec = A.partials + ((size_t)b * A.nblk + blockIdx.x) * kChainRec;
+  for (int a = tid; a < ntot; a += kThreads) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) sum += slots[w][a];
+    rec[a] = sum;
+  }
+  __shared__ unsigned ticket;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(A.counters + b, 1u);
+  __syncthreads();
+  if (ticket != (unsigned)(A.nblk - 1)) return;
+  __threadfence();
+  constexpr int PARTS = 8;                                  // records summed in 8 interleaved fp64 streams, combined in order
+  double* part = reinterpret_cast<double*>(chain_smem);    // [ntot][PARTS]  (the parking area is free now)
+  __shared__ double tot[kChainRec];
+  const float* base = A.partials + (size_t)b * A.nblk * kChainRec;
+  for (int i = tid; i < ntot * PARTS; i += kThreads) {
+    const int a = i / PARTS, p = i - a * PARTS;
+    double sum = 0.0;
+    for (int r = p; r < A.nblk; r += PARTS) sum += (double)__ldcg(base + (size_t)r * kChainRec + a);
+    part[i] = sum;
+  }
+  __syncthreads();
+  for (int a = tid; a < ntot; a += kThreads) {
+    double sum = 0.0;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) sum += part[a * PARTS + p];
+    tot[a] = sum;
+  }
+  __syncthreads();
+  if (tid < A.S) {
+    float* out = A.gparams + ((size_t)tid * A.B + b) * A.pstride;
+    if (fids[tid] >= 0) finalize_grads(fids[tid], tot + off[tid], sc[tid], A.logits, out);
+    else for (int i = 0; i < EXP_MAX_FILTER_PARAMS; ++i) out[i] = 0.f;
+  }
+  if (tid == 0) A.counters[b] = 0u;
+}
+
 // ---- filter_param_regressor kernels (one thread per image; math in filter_math.cuh) ------
 template <bool BWD>
 __global__ void regress_kernel(const float* __restrict__ logits, int lstride, float* __restrict__ params,
@@ -610,6 +833,69 @@ int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstr
   if (vec) filter_chain_fwd_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
   else filter_chain_fwd_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
   EXP_CHECK_LAUNCH("exp_filter_chain_fwd");
+  return EXP_OK;
+}
+
+// CTAs per image of the fused chain: ~8 waves of 2 CTAs/SM over the whole batch, at most one per tile
+static int chain_nblk(int B, int ntiles) {
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int target = sms * 2 * 8;
+  int nblk = (target + B - 1) / B;
+  if (nblk > ntiles) nblk = ntiles;
+  if (nblk > 65535) nblk = 65535;
+  return nblk < 1 ? 1 : nblk;
+}
+static int chain_ntiles(int P, bool vec) { return ((vec ? (P >> 2) : P) + kThreads - 1) / kThreads; }
+
+size_t exp_filter_chain_fwd_bwd_workspace_bytes(int S, int B, int H, int W) {
+  if (S <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
+  const int P = H * W;
+  const int nblk = chain_nblk(B, chain_ntiles(P, (P & 3) == 0));     // the scalar variant never needs more records
+  const int nblk_s = chain_nblk(B, chain_ntiles(P, false));
+  return kCounterBytes + (size_t)B * (nblk > nblk_s ? nblk : nblk_s) * kChainRec * sizeof(float);
+}
+
+int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* gx, const float* params, int pstride,
+                             const int* ids, int S, int B, int H, int W, float* gparams, void* workspace,
+                             size_t workspace_bytes, int options, void* stream) {
+  EXP_CHECK_ARG(x && gy && params && ids && gparams && workspace, "null pointer");
+  EXP_CHECK_ARG(S >= 1 && S <= kMaxChain, "S must be in [1, %d] (got %d)", kMaxChain, S);
+  EXP_CHECK_ARG(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 29), "bad shape");
+  EXP_CHECK_ARG(pstride >= EXP_MAX_FILTER_PARAMS, "per-image ids need pstride >= %d (got %d)", EXP_MAX_FILTER_PARAMS, pstride);
+  const size_t need = exp_filter_chain_fwd_bwd_workspace_bytes(S, B, H, W);
+  if (workspace_bytes < need)
+    return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
+  if (!aligned16(workspace)) return set_error(EXP_ERR_ALIGNMENT, "workspace must be 16-byte aligned");
+  const int P = H * W;
+  bool vec;
+  int variant = options & 0xFF;
+  if (variant == EXP_VARIANT_TMA) variant = EXP_VARIANT_DIRECT;
+  int rc = pick_vec(variant, P, x, gy, gx, &vec);
+  if (rc) return rc;
+  if (vec && y && !aligned16(y)) {
+    if (variant == EXP_VARIANT_DIRECT) return set_error(EXP_ERR_ALIGNMENT, "y must be 16-byte aligned for the DIRECT variant");
+    vec = false;
+  }
+  ChainBwdArgs A{};
+  A.x = x; A.gy = gy; A.y = y; A.gx = gx; A.params = params; A.ids = ids; A.gparams = gparams;
+  A.counters = reinterpret_cast<unsigned*>(workspace);
+  A.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
+  A.S = S; A.B = B; A.P = P; A.pstride = pstride; A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
+  A.ntiles = chain_ntiles(P, vec);
+  A.nblk = chain_nblk(B, A.ntiles);
+  const size_t smem = (size_t)S * (vec ? 12 : 3) * kThreads * sizeof(float);
+  auto kern = vec ? filter_chain_fwd_bwd_kernel<true> : filter_chain_fwd_bwd_kernel<false>;
+  static bool attr_set[2][64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_error(EXP_ERR_CUDA, "cudaGetDevice failed");
+  if (!attr_set[vec][dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxChain * 12 * kThreads * sizeof(float)));
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[vec][dev] = true;
+  }
+  kern<<<dim3(A.nblk, B), kThreads, smem, (cudaStream_t)stream>>>(A);
+  EXP_CHECK_LAUNCH("exp_filter_chain_fwd_bwd");
   return EXP_OK;
 }
 

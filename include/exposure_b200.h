@@ -115,6 +115,24 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride,
 int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstride, const int* ids,
                          int S, int B, int H, int W, int options, void* stream);
 
+/* ---- whole chain forward + backward in ONE pass (SURVEY 8d "fully chain-fused variant") --------
+ * y = f_{ids[S-1]}( ... f_{ids[0]}(x) ... ), gx = (dy/dx)^T gy, and for every step s the parameter
+ * gradients gparams[s][b][:] = d<gy, y>/dparams[s][b] (or d/dlogits with EXP_OPT_LOGITS), computed from
+ * ONE read of x and gy: 24 B/pixel in, 12 B/pixel out for gx plus 12 for y (both nullable: pass NULL to
+ * skip the store) -- against 60 B/pixel/step for S separate exp_filter_fwd / exp_filter_bwd launches,
+ * which this call equals in results (same per-pixel functions, same deterministic reduction scheme).
+ * Step inputs are parked in shared memory, nothing is recomputed; the kernel is instruction-bound.
+ * Use when the S filters and their parameters are known up front (a recorded episode, the 8-filter
+ * chain of BASELINE configs[1] / [4]); the agent's step-by-step rollout keeps the per-step entry points
+ * because each action depends on the previous step's output (agent.py:41-125).  No masking.
+ * params / gparams: [S][B][pstride], ids int32 [S][B] (id -1 = black, zero gradients), S <= 8.
+ * workspace: exp_filter_chain_fwd_bwd_workspace_bytes(); same zero-once / self-cleaning rule as
+ * exp_filter_bwd, and the same buffer may be shared with it. */
+size_t exp_filter_chain_fwd_bwd_workspace_bytes(int S, int B, int H, int W);
+int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* gx, const float* params,
+                             int pstride, const int* ids, int S, int B, int H, int W, float* gparams,
+                             void* workspace, size_t workspace_bytes, int options, void* stream);
+
 /* Bytes of device workspace exp_filter_bwd needs for this shape: a fixed 256 KiB block of
  * per-image ticket counters followed by the partial-sum records of the per-image parameter
  * gradients.  The counter block must be zero-filled once before first use; every launch

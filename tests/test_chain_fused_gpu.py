@@ -1,0 +1,127 @@
+"""GPU parity of the whole-chain fused forward+backward (exp_filter_chain_fwd_bwd) against (a) the
+per-step kernels it replaces and (b) the CPU oracle.
+
+Tolerances: pixels and image gradients are produced by the same per-pixel device functions as the
+per-step kernels -> <= 2e-6 relative to them (separately compiled instantiations may contract FMAs
+differently); parameter gradients differ by reduction order only -> <= 1e-5 of max(|ref|, 1e-3 scale).
+Against the fp64 oracle: the per-step tests' bars (pixels 1e-5 through 8 steps -> 2e-4, gradients 2e-3)."""
+import pytest
+import torch
+
+from oracle import filters as F
+
+pytestmark = pytest.mark.gpu
+CHAIN = [F.E, F.G, F.W, F.SP, F.T, F.CT, F.BW, F.C]
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+  assert torch.cuda.is_available()
+  from exposure_b200 import ops as o
+  return o
+
+
+def _rel(a, b, floor=1e-3):
+  a, b = a.double().cpu(), b.double().cpu()
+  return float(((a - b).abs() / b.abs().clamp_min(floor * float(b.abs().max()) + 1e-30)).max())
+
+
+def _run_both(ids, B, H, W, seed, scale=0.5):
+  from exposure_b200.chain import FilterChain, FusedFilterChain
+  x = F.synth_images(B, H, W, seed=seed)
+  lgs = [F.synth_logits(f, B, seed=seed + 1 + k) * scale for k, f in enumerate(ids)]
+  gout = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(seed + 50))
+  ref = FilterChain(ids)
+  y0 = ref.forward(x.cuda(), [l.cuda() for l in lgs]).clone()
+  gx0, gl0 = ref.backward(gout.cuda())
+  gx0, gl0 = gx0.clone(), [g.clone() for g in gl0]
+  fused = FusedFilterChain(ids, B, torch.device("cuda"))
+  fused.set_logits([l.cuda() for l in lgs])
+  y1, gx1, _ = fused.forward_backward(x.cuda(), gout.cuda())
+  torch.cuda.synchronize()
+  return x, lgs, gout, (y0, gx0, gl0), (y1, gx1, fused.glogits_list())
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 64), (2, 33, 31), (3, 1, 1), (1, 7, 5), (2, 128, 96), (1, 512, 640)])
+def test_fused_chain_matches_per_step_kernels(ops, shape):
+  B, H, W = shape
+  _, _, _, (y0, gx0, gl0), (y1, gx1, gl1) = _run_both(CHAIN, B, H, W, seed=7)
+  assert _rel(y1, y0) < 2e-6
+  assert _rel(gx1, gx0) < 2e-6
+  for k, (a, b) in enumerate(zip(gl1, gl0)):
+    assert _rel(a, b[:, :a.shape[1]], floor=1e-2) < 1e-5, k
+
+
+def test_fused_chain_matches_oracle(ops):
+  B, H, W = 3, 48, 40
+  x, lgs, gout, _, (y1, gx1, gl1) = _run_both(CHAIN, B, H, W, seed=21)
+  y64, gx64, glg64 = F.chain_fwd_bwd(CHAIN, x.double(), [l.double() for l in lgs], gout.double())
+  assert _rel(y1, y64) < 2e-4
+  assert _rel(gx1, gx64) < 2e-3
+  for k, (a, b) in enumerate(zip(gl1, glg64)):
+    assert _rel(a, b, floor=1e-2) < 2e-3, k
+
+
+def test_fused_chain_per_image_ids_short_chains_and_black_step(ops):
+  """Per-image filter ids (each image its own episode), S < 8, repeated filters, and id -1 (the pdf_sample
+  u == 0 quirk: black output, zero gradients)."""
+  from exposure_b200.chain import FusedFilterChain
+  B, H, W = 5, 32, 24
+  g = torch.Generator().manual_seed(3)
+  for S in (1, 3, 5):
+    ids = torch.randint(0, 10, (S, B), generator=g).to(torch.int32)
+    x = F.synth_images(B, H, W, seed=40 + S)
+    gout = torch.randn(B, H, W, 3, generator=g)
+    logits = torch.randn(S, B, 24, generator=g) * 0.5
+    fused = FusedFilterChain([ids[s].cuda() for s in range(S)], B, torch.device("cuda"))
+    fused.logits.copy_(logits.cuda())
+    y, gx, gl = fused.forward_backward(x.cuda(), gout.cuda())
+    # reference: per-step kernels with per-image ids
+    acts, cur = [x.cuda()], x.cuda()
+    for s in range(S):
+      cur = ops.filter_fwd(cur, fused.logits[s].contiguous(), ids[s].cuda(), logits=True)
+      acts.append(cur)
+    assert _rel(y, acts[-1]) < 2e-6
+    gcur = gout.cuda()
+    for s in reversed(range(S)):
+      gcur, gp = ops.filter_bwd(acts[s], gcur, fused.logits[s].contiguous(), ids[s].cuda(), logits=True)
+      assert _rel(gl[s], gp, floor=1e-2) < 1e-5, (S, s)
+    assert _rel(gx, gcur) < 2e-6
+  # a black step in the middle
+  ids = torch.tensor([[0, 1, 2, 3, 4], [-1, 5, -1, 6, 7], [4, 4, 4, 4, 4]], dtype=torch.int32)
+  fused = FusedFilterChain([ids[s].cuda() for s in range(3)], B, torch.device("cuda"))
+  fused.logits.copy_((torch.randn(3, B, 24, generator=g) * 0.5).cuda())
+  x = F.synth_images(B, H, W, seed=77)
+  gout = torch.randn(B, H, W, 3, generator=g)
+  y, gx, gl = fused.forward_backward(x.cuda(), gout.cuda())
+  assert float(gx[0].abs().max()) == 0 and float(gx[2].abs().max()) == 0 and float(gx[1].abs().max()) > 0
+  assert float(gl[0][0].abs().max()) == 0 and float(gl[1][0].abs().max()) == 0       # nothing flows through a black step
+  zero = torch.zeros(1, H, W, 3, device="cuda")
+  want0 = ops.filter_fwd(zero, fused.logits[2][0:1].contiguous(), 4, logits=True)
+  assert _rel(y[0:1], want0) < 2e-6 or float((y[0:1] - want0).abs().max()) == 0
+
+
+def test_fused_chain_outputs_optional_and_graph(ops):
+  from exposure_b200.chain import FusedFilterChain
+  B, H, W = 4, 64, 64
+  x = F.synth_images(B, H, W, seed=5).cuda()
+  gout = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(6)).cuda()
+  fused = FusedFilterChain(CHAIN, B, torch.device("cuda"))
+  fused.set_logits([(F.synth_logits(f, B, seed=9) * 0.5).cuda() for f in CHAIN])
+  y, gx, gl = fused.forward_backward(x, gout)
+  y, gx, gl = y.clone(), gx.clone(), gl.clone()
+  y2, gx2, gl2 = fused.forward_backward(x, gout, need_output=False, need_input_grad=False)
+  assert y2 is None and gx2 is None and torch.equal(gl2, gl)                          # deterministic reduction
+  yg, gxg, glg = fused.capture(x, gout)
+  fused.replay()
+  torch.cuda.synchronize()
+  assert torch.equal(yg, y) and torch.equal(gxg, gx) and torch.equal(glg, gl)
+
+
+def test_fused_chain_rejects_bad_arguments(ops):
+  x = torch.zeros(2, 8, 8, 3, device="cuda")
+  ids = torch.zeros(9, 2, dtype=torch.int32, device="cuda")
+  with pytest.raises(RuntimeError):
+    ops.filter_chain_fwd_bwd(x, x, torch.zeros(9, 2, 24, device="cuda"), ids)          # S > 8
+  with pytest.raises(ValueError):
+    ops.filter_chain_fwd_bwd(x, x, torch.zeros(2, 2, 8, device="cuda"), ids[:2])       # wrong params shape

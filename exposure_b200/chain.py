@@ -178,22 +178,35 @@ class HostPipelinedChain:
 
   This is the public end-to-end entry point bench.py's `e2e` leg times."""
 
-  def __init__(self, ids, batch, height, width, device, chunks=4, variant=ops.VARIANT_AUTO):
+  def __init__(self, ids, batch, height, width, device, chunks=4, variant=ops.VARIANT_AUTO, fused=False):
+    """fused=True: every sub-batch runs the whole chain forward+backward as ONE kernel (FusedFilterChain)
+    instead of 2N per-step launches; results agree with the per-step path to reduction order."""
     assert batch % chunks == 0
     self.ids, self.chunks, self.cb = list(ids), chunks, batch // chunks
     self.device = device
-    self.sub = [FilterChain(ids, variant=variant) for _ in range(chunks)]
-    # the parameter gradients of all steps of a sub-batch live in ONE flat device buffer so that they
-    # leave in one D2H copy per sub-batch (a copy per step costs more in launch overhead than in bytes)
+    self.fused = fused
     self.nk = [ops.NUM_PARAMS[f] if isinstance(f, int) else ops.PSTRIDE for f in self.ids]
-    self.off = [0]
-    for n in self.nk:
-      self.off.append(self.off[-1] + self.cb * n)
-    for ch in self.sub:
-      ch.input_buffer((self.cb, height, width, 3), device)
-      ch._glog_flat = torch.zeros(self.off[-1], device=device)
-      ch._glog = [ch._glog_flat[self.off[k]:self.off[k + 1]].view(self.cb, n) for k, n in enumerate(self.nk)]
-    self.h_glog = torch.empty(chunks, self.off[-1]).pin_memory()
+    cb, n = self.cb, len(self.ids)
+    if fused:
+      self.sub = [FusedFilterChain(ids, cb, device) for _ in range(chunks)]
+      # regressor inputs of all sub-batches in the kernel's layout, packed once per step: [chunks][N][cb][24]
+      self._packed = torch.zeros(chunks, n, cb, ops.PSTRIDE, device=device)
+      for c, ch in enumerate(self.sub):
+        ch.logits = self._packed[c]
+        ch.x, ch.y, ch.gx = (torch.empty(cb, height, width, 3, device=device) for _ in range(3))
+      self.h_glog = torch.empty(chunks, n * cb * ops.PSTRIDE).pin_memory()
+    else:
+      self.sub = [FilterChain(ids, variant=variant) for _ in range(chunks)]
+      # the parameter gradients of all steps of a sub-batch live in ONE flat device buffer so that they
+      # leave in one D2H copy per sub-batch (a copy per step costs more in launch overhead than in bytes)
+      self.off = [0]
+      for k in self.nk:
+        self.off.append(self.off[-1] + cb * k)
+      for ch in self.sub:
+        ch.input_buffer((cb, height, width, 3), device)
+        ch._glog_flat = torch.zeros(self.off[-1], device=device)
+        ch._glog = [ch._glog_flat[self.off[k]:self.off[k + 1]].view(cb, k_n) for k, k_n in enumerate(self.nk)]
+      self.h_glog = torch.empty(chunks, self.off[-1]).pin_memory()
     self._scatter_to = None
     self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
     self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
@@ -213,24 +226,33 @@ class HostPipelinedChain:
     cur = torch.cuda.current_stream()
     for s in (self.s_in, self.s_cmp, self.s_out):
       s.wait_stream(cur)
+    if self.fused:
+      with torch.cuda.stream(self.s_cmp):               # after the previous step's kernels (same stream)
+        for k, (l, n) in enumerate(zip(logits_list, self.nk)):
+          self._packed[:, k, :, :n].copy_(l.view(self.chunks, cb, n))
     for c, ch in enumerate(self.sub):
       sl = slice(c * cb, (c + 1) * cb)
       with torch.cuda.stream(self.s_in):
         if not self._first:
           self.s_in.wait_event(self.ev_cmp[c])          # previous step's compute on this buffer is done
-        ch._acts[0].copy_(hx[sl], non_blocking=True)
+        (ch.x if self.fused else ch._acts[0]).copy_(hx[sl], non_blocking=True)
         self.ev_in[c].record(self.s_in)
       with torch.cuda.stream(self.s_cmp):
         self.s_cmp.wait_event(self.ev_in[c])
         if not self._first:
           self.s_cmp.wait_event(self.ev_out[c])         # previous step's D2H of this chunk's outputs is done
-        y = ch.forward_resident([l[sl] for l in logits_list])
-        ch.backward(gout[sl], need_input_grad=True)
+        if self.fused:
+          y, _, glog_flat = ch.forward_backward(ch.x, gout[sl], y_out=ch.y, gx_out=ch.gx)
+          glog_flat = glog_flat.view(-1)
+        else:
+          y = ch.forward_resident([l[sl] for l in logits_list])
+          ch.backward(gout[sl], need_input_grad=True)
+          glog_flat = ch._glog_flat
         self.ev_cmp[c].record(self.s_cmp)
       with torch.cuda.stream(self.s_out):
         self.s_out.wait_event(self.ev_cmp[c])
         hy[sl].copy_(y, non_blocking=True)
-        self.h_glog[c].copy_(ch._glog_flat, non_blocking=True)
+        self.h_glog[c].copy_(glog_flat, non_blocking=True)
         self.ev_out[c].record(self.s_out)
     self._first = False
     self._scatter_to = hglogits
@@ -245,6 +267,11 @@ class HostPipelinedChain:
     cur.synchronize()
     if self._scatter_to is not None:
       cb = self.cb
-      for k, (h, n) in enumerate(zip(self._scatter_to, self.nk)):
-        h.view(self.chunks, cb, n).copy_(self.h_glog[:, self.off[k]:self.off[k + 1]].view(self.chunks, cb, n))
+      if self.fused:
+        hg = self.h_glog.view(self.chunks, len(self.ids), cb, ops.PSTRIDE)
+        for k, (h, n) in enumerate(zip(self._scatter_to, self.nk)):
+          h.view(self.chunks, cb, n).copy_(hg[:, k, :, :n])
+      else:
+        for k, (h, n) in enumerate(zip(self._scatter_to, self.nk)):
+          h.view(self.chunks, cb, n).copy_(self.h_glog[:, self.off[k]:self.off[k + 1]].view(self.chunks, cb, n))
       self._scatter_to = None

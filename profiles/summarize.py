@@ -14,7 +14,7 @@ import sys
 def short(name):
   name = re.sub(r"^void ", "", name)
   m = re.match(r"(expo::)?(\w+)<([^>]*)>", name)
-  if m and ("filter_step" in name or "gemm_kernel" in name):
+  if m and ("filter_step" in name or "gemm_kernel" in name or "filter_chain" in name):
     return "%s<%s>" % (m.group(2), m.group(3))
   if "at::" in name or "templates::" in name:
     k = re.search(r"(\w+_kernel\w*)", name)
@@ -84,12 +84,25 @@ def traffic(src, dst, config):
   """DRAM bytes per launch of every filter_step_tma_kernel in an `ncu --set full` report ->
   the small JSON bench.py reads to fill roofline.traffic (keys = bench.py's kernel names)."""
   import json
-  out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-  rows = list(csv.reader(out.splitlines()))
+  raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+  rows = list(csv.reader(raw.splitlines()))
   hdr, units = rows[0], rows[1]
   idx = {h: i for i, h in enumerate(hdr)}
   res = {}
+  try:                                   # keep the kernels of an earlier capture of the same configuration
+    prev = json.load(open(dst))
+    if prev.get("config") == config:
+      res = prev["kernels"]
+      src = "%s + %s" % (prev["source"], src) if src not in prev["source"] else prev["source"]
+  except (OSError, ValueError, KeyError):
+    pass
   for r in rows[2:]:
+    if "filter_chain_fwd_bwd_kernel" in r[idx["Kernel Name"]]:
+      rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT[units[idx["dram__bytes_read.sum"]]]
+      wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
+      res["filter_chain_fwd_bwd"] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
+                                     "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]])}
+      continue
     m = re.search(r"filter_step_tma_kernel<(?:\(int\))?(\d+), (?:\(bool\))?(\w+), (?:\(bool\))?(\w+)", r[idx["Kernel Name"]])
     if not m:
       continue

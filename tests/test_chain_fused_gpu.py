@@ -125,3 +125,26 @@ def test_fused_chain_rejects_bad_arguments(ops):
     ops.filter_chain_fwd_bwd(x, x, torch.zeros(9, 2, 24, device="cuda"), ids)          # S > 8
   with pytest.raises(ValueError):
     ops.filter_chain_fwd_bwd(x, x, torch.zeros(2, 2, 8, device="cuda"), ids[:2])       # wrong params shape
+
+
+def test_host_pipelined_fused_chain_matches_resident(ops):
+  """HostPipelinedChain(fused=True): host buffers in, host buffers out, one kernel per sub-batch."""
+  from exposure_b200.chain import FilterChain, HostPipelinedChain
+  B, H, W = 8, 64, 64
+  x = F.synth_images(B, H, W, seed=31)
+  lgs = [(F.synth_logits(f, B, seed=7) * 0.5).cuda() for f in CHAIN]
+  gout = torch.randn(B, H, W, 3, device="cuda")
+  ref = FilterChain(CHAIN)
+  y = ref.forward(x.cuda(), lgs).clone()
+  _, gl = ref.backward(gout)
+  hx = x.pin_memory()
+  hy = torch.empty(B, H, W, 3).pin_memory()
+  hg = [torch.empty(B, F.NUM_PARAMS[f]).pin_memory() for f in CHAIN]
+  pipe = HostPipelinedChain(CHAIN, B, H, W, torch.device("cuda"), chunks=4, fused=True)
+  for wait in (True, True, False, False):
+    hy.zero_()
+    pipe.step(hx, lgs, gout, hy, hg, wait=wait)
+    pipe.wait()
+    assert _rel(hy, y) < 2e-6
+    for a, b in zip(hg, gl):
+      assert _rel(a, b, floor=1e-2) < 1e-5

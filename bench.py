@@ -50,6 +50,7 @@ def parse_args():
   ap.add_argument("--chain-impl", default="fused", choices=["fused", "steps"],
                   help="chain8: 'fused' = the whole chain fwd+bwd as ONE kernel per step (exp_filter_chain_fwd_bwd), "
                        "'steps' = one fused kernel per filter step and direction (2N launches)")
+  ap.add_argument("--e2e-chunks", type=int, default=0, help="chain8 e2e leg: sub-batches in flight (0 = 8 if it divides the batch)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-graphs", action="store_true", help="train workload: launch kernels eagerly instead of CUDA graphs")
   return ap.parse_args()
@@ -418,7 +419,8 @@ def run_native(args):
   # fetches fake_output every step) and of the parameter gradients, software-pipelined over
   # sub-batches on three streams (exposure_b200/chain.py HostPipelinedChain)
   from exposure_b200.chain import HostPipelinedChain
-  n_chunks = 8 if B % 8 == 0 else (4 if B % 4 == 0 else 1)
+  n_chunks = args.e2e_chunks if args.e2e_chunks > 0 and B % args.e2e_chunks == 0 else \
+      (8 if B % 8 == 0 else (4 if B % 4 == 0 else 1))
   del chain                                          # free the resident chain's activations first
   if fused_on:
     del fz, fy, fgx, y_steps

@@ -512,16 +512,60 @@ __device__ __forceinline__ void chain_bwd_any(int fid, const float (&px)[4][3], 
 // Instruction footprint: the hot loop (10 forward + 10 backward bodies x 4 pixels, ~100 KB) is three times
 // the 32 KB instruction cache (ncu: icc hit rate 83 %, stall_no_instruction 0.9 per issue).  A CTA barrier per
 // step, to keep the 8 warps inside the same body, was measured and is slower (0.87 vs 0.82 ms: hit rate only
-// 86 %, barrier stalls x3) -- the loop is re-streamed from L2 per tile either way.
-template <bool VEC>
+// 86 %, barrier stalls x3) -- the loop is re-streamed from L2 per tile either way.  Two pixels per thread
+// (half the code per body, 3 CTAs/SM) was measured too: hit rate 91 %, issue-active 63 -> 75 %, but the
+// per-thread fixed work (switch, butterflies, parking) is then paid per 2 pixels: +19 % instructions, 0.84 ms.
+// A thread's work item: NPX consecutive pixels = NPX*3 floats (4 -> 3 x float4, 1 -> 3 floats).
+template <int NPX>
+__device__ __forceinline__ void group_load(const float* __restrict__ base, size_t q, float (&px)[4][3]) {
+  if constexpr (NPX == 4) {
+    unpack(load_px4(base, q), px);
+  } else {
+    px[0][0] = base[3 * q]; px[0][1] = base[3 * q + 1]; px[0][2] = base[3 * q + 2];
+  }
+}
+template <int NPX>
+__device__ __forceinline__ void group_store(float* __restrict__ base, size_t q, const float (&px)[4][3]) {
+  if constexpr (NPX == 4) {
+    store_px4(base, q, pack(px));
+  } else {
+    base[3 * q] = px[0][0]; base[3 * q + 1] = px[0][1]; base[3 * q + 2] = px[0][2];
+  }
+}
+// parking area of one step: 3 columns of kThreads vectors (float4 / float), conflict-free
+template <int NPX>
+__device__ __forceinline__ void park_store(float* __restrict__ area, int tid, const float (&px)[4][3]) {
+  if constexpr (NPX == 4) {
+    float4* pk = reinterpret_cast<float4*>(area) + tid;
+    const Px4 v = pack(px);
+    pk[0] = v.a; pk[kThreads] = v.b; pk[2 * kThreads] = v.c;
+  } else {
+    float* pk = area + tid;
+    pk[0] = px[0][0]; pk[kThreads] = px[0][1]; pk[2 * kThreads] = px[0][2];
+  }
+}
+template <int NPX>
+__device__ __forceinline__ void park_load(const float* __restrict__ area, int tid, float (&px)[4][3]) {
+  if constexpr (NPX == 4) {
+    const float4* pk = reinterpret_cast<const float4*>(area) + tid;
+    Px4 v;
+    v.a = pk[0]; v.b = pk[kThreads]; v.c = pk[2 * kThreads];
+    unpack(v, px);
+  } else {
+    const float* pk = area + tid;
+    px[0][0] = pk[0]; px[0][1] = pk[kThreads]; px[0][2] = pk[2 * kThreads];
+  }
+}
+
+template <int NPX>
 __global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const ChainBwdArgs A) {
-  constexpr int NPX = VEC ? 4 : 1;
   extern __shared__ __align__(16) unsigned char chain_smem[];
   __shared__ FilterConsts sc[kMaxChain];
   __shared__ int fids[kMaxChain], off[kMaxChain + 1];
   __shared__ float slots[kWarps][kChainRec];
-  // parked step inputs: [S][NPX * 3][kThreads] floats (as float4 [S][3][kThreads] when VEC)
+  // parked step inputs: [S][3][kThreads] vectors of NPX floats
   float* const park = reinterpret_cast<float*>(chain_smem);
+  constexpr int kArea = 3 * NPX * kThreads;                // floats per step
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   for (int s = warp; s < A.S; s += kWarps) {               // one warp per step: the S set-ups run in parallel
@@ -546,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const
   float* __restrict__ gxo = A.gx ? A.gx + img : nullptr;
   const int t0 = (int)((long long)blockIdx.x * A.ntiles / A.nblk);
   const int t1 = (int)((long long)(blockIdx.x + 1) * A.ntiles / A.nblk);
-  const int nq = VEC ? (A.P >> 2) : A.P;                   // work items (4-pixel groups or pixels) per image
+  const int nq = A.P / NPX;                                // work items (NPX-pixel groups) per image
 
   for (int t = t0; t < t1; ++t) {
     const int q = t * kThreads + tid;
@@ -554,54 +598,22 @@ __global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const
     float px[4][3], g[4][3];
 #pragma unroll
     for (int i = 0; i < 4; ++i) px[i][0] = px[i][1] = px[i][2] = g[i][0] = g[i][1] = g[i][2] = 0.f;
-    if (live) {
-      if constexpr (VEC) {
-        unpack(load_px4(x, q), px);
-      } else {
-        px[0][0] = x[3 * (size_t)q]; px[0][1] = x[3 * (size_t)q + 1]; px[0][2] = x[3 * (size_t)q + 2];
-      }
-    }
+    if (live) group_load<NPX>(x, q, px);
     // ---- forward sweep: park the input of every step ----
     for (int s = 0; s < A.S; ++s) {
-      if constexpr (VEC) {
-        float4* pk = reinterpret_cast<float4*>(park) + (size_t)s * 3 * kThreads + tid;
-        const Px4 v = pack(px);
-        pk[0] = v.a; pk[kThreads] = v.b; pk[2 * kThreads] = v.c;
-      } else {
-        float* pk = park + (size_t)s * 3 * kThreads + tid;
-        pk[0] = px[0][0]; pk[kThreads] = px[0][1]; pk[2 * kThreads] = px[0][2];
-      }
+      park_store<NPX>(park + (size_t)s * kArea, tid, px);
       chain_apply_any(fids[s], px, sc[s], NPX);
     }
     if (live) {
-      if constexpr (VEC) {
-        if (y) store_px4(y, q, pack(px));
-        unpack(load_px4(gy, q), g);
-      } else {
-        if (y) { y[3 * (size_t)q] = px[0][0]; y[3 * (size_t)q + 1] = px[0][1]; y[3 * (size_t)q + 2] = px[0][2]; }
-        g[0][0] = gy[3 * (size_t)q]; g[0][1] = gy[3 * (size_t)q + 1]; g[0][2] = gy[3 * (size_t)q + 2];
-      }
+      if (y) group_store<NPX>(y, q, px);
+      group_load<NPX>(gy, q, g);
     }
     // ---- backward sweep (dead lanes carry g == 0: every accumulator term is a multiple of g) ----
     for (int s = A.S - 1; s >= 0; --s) {
-      if constexpr (VEC) {
-        const float4* pk = reinterpret_cast<const float4*>(park) + (size_t)s * 3 * kThreads + tid;
-        Px4 v;
-        v.a = pk[0]; v.b = pk[kThreads]; v.c = pk[2 * kThreads];
-        unpack(v, px);
-      } else {
-        const float* pk = park + (size_t)s * 3 * kThreads + tid;
-        px[0][0] = pk[0]; px[0][1] = pk[kThreads]; px[0][2] = pk[2 * kThreads];
-      }
+      park_load<NPX>(park + (size_t)s * kArea, tid, px);
       chain_bwd_any<NPX>(fids[s], px, g, sc[s], &slots[warp][off[s]], lane);
     }
-    if (live && gxo) {
-      if constexpr (VEC) {
-        store_px4(gxo, q, pack(g));
-      } else {
-        gxo[3 * (size_t)q] = g[0][0]; gxo[3 * (size_t)q + 1] = g[0][1]; gxo[3 * (size_t)q + 2] = g[0][2];
-      }
-    }
+    if (live && gxo) group_store<NPX>(gxo, q, g);
   }
 
   // ---- CTA record (warps summed in fixed order), ticket, last CTA of the image finishes in fp64 ----
@@ -850,14 +862,17 @@ static int chain_nblk(int B, int ntiles) {
   if (nblk > 65535) nblk = 65535;
   return nblk < 1 ? 1 : nblk;
 }
-static int chain_ntiles(int P, bool vec) { return ((vec ? (P >> 2) : P) + kThreads - 1) / kThreads; }
-
+static int chain_ntiles(int P, int npx) { return (P / npx + kThreads - 1) / kThreads; }
 size_t exp_filter_chain_fwd_bwd_workspace_bytes(int S, int B, int H, int W) {
   if (S <= 0 || B <= 0 || H <= 0 || W <= 0) return 0;
   const int P = H * W;
-  const int nblk = chain_nblk(B, chain_ntiles(P, (P & 3) == 0));     // the scalar variant never needs more records
-  const int nblk_s = chain_nblk(B, chain_ntiles(P, false));
-  return kCounterBytes + (size_t)B * (nblk > nblk_s ? nblk : nblk_s) * kChainRec * sizeof(float);
+  int nblk = 1;
+  for (int npx = 1; npx <= 4; npx *= 4) {                 // whichever variant the launch ends up using
+    if (P % npx) break;
+    const int n = chain_nblk(B, chain_ntiles(P, npx));
+    if (n > nblk) nblk = n;
+  }
+  return kCounterBytes + (size_t)B * nblk * kChainRec * sizeof(float);
 }
 
 int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* gx, const float* params, int pstride,
@@ -886,17 +901,18 @@ int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* g
   A.counters = reinterpret_cast<unsigned*>(workspace);
   A.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
   A.S = S; A.B = B; A.P = P; A.pstride = pstride; A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
-  A.ntiles = chain_ntiles(P, vec);
+  const int npx = vec ? 4 : 1;
+  A.ntiles = chain_ntiles(P, npx);
   A.nblk = chain_nblk(B, A.ntiles);
-  const size_t smem = (size_t)S * (vec ? 12 : 3) * kThreads * sizeof(float);
-  auto kern = vec ? filter_chain_fwd_bwd_kernel<true> : filter_chain_fwd_bwd_kernel<false>;
+  const size_t smem = (size_t)S * 3 * npx * kThreads * sizeof(float);
+  auto kern = npx == 4 ? filter_chain_fwd_bwd_kernel<4> : filter_chain_fwd_bwd_kernel<1>;
   static bool attr_set[2][64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_error(EXP_ERR_CUDA, "cudaGetDevice failed");
-  if (!attr_set[vec][dev]) {
+  if (!attr_set[npx >> 2][dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxChain * 12 * kThreads * sizeof(float)));
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set[vec][dev] = true;
+    attr_set[npx >> 2][dev] = true;
   }
   kern<<<dim3(A.nblk, B), kThreads, smem, (cudaStream_t)stream>>>(A);
   EXP_CHECK_LAUNCH("exp_filter_chain_fwd_bwd");

@@ -148,3 +148,38 @@ def test_host_pipelined_fused_chain_matches_resident(ops):
     assert _rel(hy, y) < 2e-6
     for a, b in zip(hg, gl):
       assert _rel(a, b, floor=1e-2) < 1e-5
+
+
+def test_fused_chain_full_size_properties(ops):
+  """BASELINE configs[1] full size (64x512x512x3), size-independent properties: pixels / image gradients
+  bit-identical to the 16 per-step kernels; the backward is exactly linear in dL/dy under power-of-two
+  scaling; parameter gradients of an image equal the sum over its two halves; launches are deterministic."""
+  from exposure_b200.chain import FilterChain, FusedFilterChain
+  B, H, W = 64, 512, 512
+  g = torch.Generator(device="cuda").manual_seed(2)
+  x = torch.exp(torch.randn(B, H, W, 3, device="cuda", generator=g) - 3.2).clamp_(0, 4)
+  gout = torch.randn(B, H, W, 3, device="cuda", generator=g)
+  lgs = [torch.randn(B, F.NUM_PARAMS[f], device="cuda", generator=g) * 0.5 for f in CHAIN]
+  ref = FilterChain(CHAIN)
+  y0 = ref.forward(x, lgs)
+  gx0, gl0 = ref.backward(gout)
+  fused = FusedFilterChain(CHAIN, B, torch.device("cuda"))
+  fused.set_logits(lgs)
+  y1, gx1, gl1 = fused.forward_backward(x, gout)
+  assert torch.equal(y1, y0) and torch.equal(gx1, gx0)
+  for k, (a, b) in enumerate(zip(fused.glogits_list(), gl0)):
+    assert _rel(a, b, floor=1e-2) < 2e-5, k
+  gl1 = gl1.clone()
+  del ref, y0, gx0
+  _, gx2, gl2 = fused.forward_backward(x, gout * 2.0, need_output=False)
+  assert torch.equal(gx2, gx1 * 2.0)
+  assert _rel(gl2, gl1 * 2.0, floor=1e-3) < 1e-5
+  _, _, gl3 = fused.forward_backward(x, gout, need_output=False, need_input_grad=False)
+  assert torch.equal(gl3, gl1)
+  # halves: the regressor chain rule is linear in the parameter gradient, so dL/dlogits adds up as well
+  top = FusedFilterChain(CHAIN, B, torch.device("cuda"))
+  top.logits.copy_(fused.logits)
+  _, _, ga = top.forward_backward(x[:, :256].contiguous(), gout[:, :256].contiguous(), need_output=False, need_input_grad=False)
+  ga = ga.clone()
+  _, _, gb = top.forward_backward(x[:, 256:].contiguous(), gout[:, 256:].contiguous(), need_output=False, need_input_grad=False)
+  assert _rel(ga + gb, gl1, floor=1e-2) < 1e-4

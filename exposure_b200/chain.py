@@ -45,7 +45,7 @@ class FilterChain:
 
   def _nparams(self, k):
     fid = self.ids[k]
-    return ops.NUM_PARAMS[fid] if isinstance(fid, int) else ops.PSTRIDE
+    return ops.NUM_PARAMS_ALL[fid] if isinstance(fid, int) else ops.PSTRIDE
 
   def forward(self, x, logits_list):
     """x: [B,H,W,3]; logits_list[k]: [B, >= n_k] raw regressor inputs.  Returns x_N."""
@@ -128,7 +128,7 @@ class FusedFilterChain:
   def __init__(self, ids, batch, device):
     """ids: list of N <= 8 entries, each an int (uniform) or a CUDA int32 tensor [B]."""
     self.n = len(ids)
-    self.nk = [ops.NUM_PARAMS[f] if isinstance(f, int) else ops.PSTRIDE for f in ids]
+    self.nk = [ops.NUM_PARAMS_ALL[f] if isinstance(f, int) else ops.PSTRIDE for f in ids]
     self.ids = torch.empty(self.n, batch, dtype=torch.int32, device=device)
     for k, f in enumerate(ids):
       self.ids[k] = f if isinstance(f, int) else f.to(device=device, dtype=torch.int32)
@@ -185,7 +185,7 @@ class HostPipelinedChain:
     self.ids, self.chunks, self.cb = list(ids), chunks, batch // chunks
     self.device = device
     self.fused = fused
-    self.nk = [ops.NUM_PARAMS[f] if isinstance(f, int) else ops.PSTRIDE for f in self.ids]
+    self.nk = [ops.NUM_PARAMS_ALL[f] if isinstance(f, int) else ops.PSTRIDE for f in self.ids]
     cb, n = self.cb, len(self.ids)
     if fused:
       self.sub = [FusedFilterChain(ids, cb, device) for _ in range(chunks)]

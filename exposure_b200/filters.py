@@ -141,11 +141,22 @@ class Filter:
     return ops.filter_mask(img.detach().contiguous(), ml.contiguous(), self.filter_id,
                            float(self.cfg.maximum_sharpness), float(self.cfg.minimum_strength), True)
 
+  # ---- visual debugger (host side, cv2; exposure_b200/visualize.py) ------------------------------
   def visualize_filter(self, debug_info, canvas):
-    raise NotImplementedError("visualisation is out of scope (DESIGN.md section 10)")
+    """Draw this filter's parameters onto `canvas` in place (filters.py:150-152 and the per-class
+    overrides): debug_info = {'filter_parameters': first image's regressed parameters (numpy), 'mask': ...}."""
+    from . import visualize
+    visualize.visualize_filter(self.get_short_name(), debug_info, canvas)
 
   def visualize_mask(self, debug_info, res):
-    raise NotImplementedError("visualisation is out of scope (DESIGN.md section 10)")
+    """filters.py:154-158."""
+    from . import visualize
+    return visualize.visualize_mask(debug_info, res)
+
+  def draw_high_res_text(self, text, canvas):
+    """filters.py:160-168."""
+    from . import visualize
+    return visualize.draw_high_res_text(text, canvas)
 
 
 class ExposureFilter(Filter):          # filters.py:170-182

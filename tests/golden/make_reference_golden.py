@@ -20,6 +20,7 @@ Sections (all inputs and random draws are stored next to the outputs):
   3. agent_generator: 5-step rollouts (argmax and sampled) + the high_res branch
   4. critic / value network
   5. critic loss with the WGAN-GP term and its double-backward; generator / value losses
+  6. the cv2 visual debugger: every Filter.visualize_filter / visualize_mask, agent_generator's debugger
 Sections 3-5 run twice: with the shipped pretrained checkpoint ("pre_": compact outputs; the weights
 do not travel, so only tests in the build container can use them) and with the name-seeded weights of
 tests/golden/seeded_weights.py ("seed_": full outputs, reproducible on the GPU box).
@@ -386,6 +387,52 @@ def section_losses(kind, P):
   tf.set_float_dtype(torch.float32)
 
 
+# 6. visual debugger: Filter.visualize_filter / visualize_mask (filters.py:150-168 + overrides) and the
+#    debugger closure of agent_generator (agent.py:141-204) -- host-side cv2 drawing on debug_info
+def section_visualize(P):
+  import cv2
+  if not hasattr(cv2, "cv2"):
+    cv2.cv2 = cv2            # filters.py:158 spells the constant cv2.cv2.INTER_NEAREST (old OpenCV wheels)
+  tf.set_float_dtype(torch.float32)
+  dummy = torch.zeros(1, 64, 64, 3)
+  g = np.random.RandomState(8000)
+  mask = g.rand(12, 16, 1).astype(np.float32)
+  for fid, cls in enumerate(FILTERS):
+    f = quiet(cls, dummy, cfg)
+    logits = torch.from_numpy(g.randn(1, f.get_num_filter_parameters()).astype(np.float32))
+    param = f.filter_param_regressor(logits)
+    dbg = {"filter_parameters": (param if f.debug_info_batched() else param[0]).numpy(), "mask": mask}
+    for size in (64, 256):
+      canvas = np.full((size, size, 3), 0.5, dtype=np.float32)
+      import warnings
+      with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)      # '%.2f' % one-element array (filters.py:210)
+        f.visualize_filter(dbg, canvas)
+      put("vz%d" % fid, **{"canvas%d" % size: canvas})
+    put("vz%d" % fid, param=dbg["filter_parameters"], maskimg=f.visualize_mask(dbg, (64, 64)))
+  OUT["vz_mask"] = mask
+  # the agent's debugger on one pretrained argmax step and one sampled step
+  img0 = torch.from_numpy(thumbnails())
+  for mode, is_train in (("argmax", 0), ("sample", 1)):
+    use_weights("pre", P, ("generator",))
+    tf.nn.dropout_source = Draws(8100 + is_train)
+    z = torch.rand(img0.shape[0], cfg.z_dim, generator=torch.Generator().manual_seed(8200 + is_train))
+    states = torch.zeros(img0.shape[0], cfg.num_state_dim)
+    with tf.variable_scope("generator"):
+      _, dbg, debugger = quiet(RA.agent_generator, [img0, z, states], is_train=is_train, progress=0.5, cfg=cfg)
+    host = {"state": dbg["state"].numpy(), "selected_filter_id": int(dbg["selected_filter_id"]),
+            "pdf": dbg["pdf"].detach().numpy(),
+            "filter_debug_info": [{"filter_parameters": d["filter_parameters"].detach().numpy(), "mask": d["mask"].detach().numpy()}
+                                  for d in dbg["filter_debug_info"]]}
+    combined = quiet(debugger, host, combined=True)
+    panels = quiet(debugger, host, combined=False)
+    pre = "vzdbg_" + mode
+    put(pre, selected=host["selected_filter_id"], pdf=host["pdf"], combined=combined, panel_pdf=panels[0],
+        panel_detail=panels[1], panel_mask=panels[2], width=debugger.width)
+    for j, d in enumerate(host["filter_debug_info"]):
+      put(pre, **{"param%d" % j: d["filter_parameters"], "mask%d" % j: d["mask"]})
+
+
 def main():
   torch.set_num_threads(max(1, os.cpu_count() or 1))
   section_filters()
@@ -395,6 +442,7 @@ def main():
     section_agent(kind, P)
     section_critic(kind, P)
     section_losses(kind, P)
+  section_visualize(P)
   OUT["provenance"] = np.array(
       "reference Python (yuanming-hu/exposure @ 7bb838a: filters.py, agent.py, critics.py, pdf_sample_layer.py, util.py, "
       "config_example.py) executed over tests/golden/tf1_shim (TF-1 API stand-in on torch CPU); not TensorFlow binaries")

@@ -49,9 +49,23 @@ def test_gan_train_save_restore_eval(built_lib, tmp_path, monkeypatch):
   img = torch.rand(B, 64, 64, 3, device=t.device) * 0.2
   z = torch.rand(B, cfg.z_dim, device=t.device)
   states = torch.zeros(B, cfg.num_state_dim, device=t.device)
-  (net, new_states, surrogate, penalty), info, _ = cfg.generator(inp=[img, z, states], is_train=0, progress=0.5, cfg=cfg)
+  (net, new_states, surrogate, penalty), info, debugger = cfg.generator(inp=[img, z, states], is_train=0, progress=0.5, cfg=cfg)
   assert net.shape == (B, 64, 64, 3) and new_states.shape == (B, 11) and surrogate.shape == (B, 1) and penalty.shape == (B, 1)
-  assert info["selected_filter_id"].shape == (B,)
+  assert info["selected_filter_ids"].shape == (B,)
+  # debug_info of the first image in the reference's structure (agent.py:131-137) + the cv2 debugger (agent.py:141-204)
+  assert info["selected_filter_id"] == int(info["selected_filter_ids"][0]) and info["pdf"].shape == (8,)
+  assert len(info["filter_debug_info"]) == 8 and info["filter_debug_info"][4]["filter_parameters"].shape == (1, 1, 1, 8)
+  assert info["filter_debug_info"][7]["filter_parameters"].shape == (1, 1, 3, 8) and info["filter_debug_info"][0]["mask"].shape == (1, 1, 1)
+  sel = info["selected_filter_id"]
+  want = t.policy  # the selected filter's parameters in debug_info are the ones the step applied
+  n = [1, 1, 3, 1, 8, 1, 1, 24][sel]
+  assert np.allclose(info["filter_debug_info"][sel]["filter_parameters"].reshape(-1),
+                     info["selected_filter_parameters"][0, :n].cpu().numpy(), rtol=1e-6, atol=1e-7)
+  assert debugger.width == 64
+  canvas = debugger(info)
+  assert canvas.shape == (64, 64, 3) and canvas.dtype == np.float32 and np.isfinite(canvas).all()
+  panels = debugger(info, combined=False)
+  assert len(panels) == 3 and all(p.shape == (64, 64, 3) for p in panels)
   logit, _, _ = cfg.critic(images=net, cfg=cfg)
   assert logit.shape == (B, 1) and torch.isfinite(logit).all()
   value, _, _ = cfg.value(images=net, cfg=cfg, states=new_states)

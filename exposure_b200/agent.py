@@ -17,6 +17,32 @@ forward + backward schedule of the same graph."""
 import torch
 
 
+def host_debug_info(c, net, states, filters, cfg, index=0):
+  """debug_info of image `index` in the reference's structure (agent.py:131-137, filters.py:79-87) as host
+  numpy values -- what sess.run hands to the debugger: every filter's regressed parameters (only the
+  selected filter was APPLIED, but all heads were evaluated), its mask, the pdf and the selected id.
+  c: PolicyNet.forward context.  A few small D2H copies; not on the training path."""
+  O = c.O[index]                                                       # [n_filters, ostride] raw fc2 outputs
+  masking = bool(getattr(cfg, "masking", False))
+  fdi = []
+  for j, f in enumerate(filters):
+    n = f.get_num_filter_parameters()
+    p = f.filter_param_regressor(O[j:j + 1, :n].contiguous())
+    nm = f.get_num_mask_parameters()
+    if masking or nm != 6:
+      mask = f.get_mask(net[index:index + 1], O[j:j + 1, n:n + nm].contiguous())
+    else:
+      mask = torch.ones(1, 1, 1, 1)                                    # filters.py:113
+    fdi.append({"filter_parameters": (p if f.debug_info_batched() else p[0]).detach().cpu().numpy(),
+                "mask": mask[0].detach().cpu().numpy()})
+  return {
+      "state": states,                                                 # agent.py:133
+      "selected_filter_id": int(c.ids[index]),                         # agent.py:134
+      "filter_debug_info": fdi,                                        # agent.py:135
+      "pdf": c.pdf[index].detach().cpu().numpy(),                      # agent.py:136
+  }
+
+
 def make_agent_generator(trainer):
   policy = trainer.policy
 
@@ -30,27 +56,10 @@ def make_agent_generator(trainer):
     prog = torch.full((1,), float(progress), device=dev)
     c = policy.forward(net.contiguous(), states.contiguous(), noise, drop_f, drop_s, int(is_train), prog, cfg,
                        high_res=high_res)
-    # debug_info of the FIRST image in the reference's structure (agent.py:131-137, filters.py:79-87), as host
-    # numpy values -- what sess.run hands to the debugger.  One small D2H copy; not on the training path.
     filters = [cls(net, cfg) for cls in cfg.filters]
-    O0 = c.O[0]                                                         # [n_filters, ostride] raw fc2 outputs
-    masking = bool(getattr(cfg, "masking", False))
-    fdi = []
-    for j, f in enumerate(filters):
-      n = f.get_num_filter_parameters()
-      p = f.filter_param_regressor(O0[j:j + 1, :n].contiguous())
-      nm = f.get_num_mask_parameters()
-      mask = f.get_mask(net[0:1], O0[j:j + 1, n:n + nm].contiguous()) if (masking or nm != 6) else torch.ones(1, 1, 1, 1)
-      fdi.append({"filter_parameters": (p if f.debug_info_batched() else p[0]).detach().cpu().numpy(),
-                  "mask": mask[0].detach().cpu().numpy()})
-    debug_info = {
-        "state": states,                                               # agent.py:133
-        "selected_filter_id": int(c.ids[0]),                           # agent.py:134
-        "filter_debug_info": fdi,                                      # agent.py:135
-        "pdf": c.pdf[0].detach().cpu().numpy(),                        # agent.py:136
-        # batch-wide extras (not in the reference's dict)
-        "selected_filter_ids": c.ids, "selected_filter_parameters": c.params, "penalty": c.penalty,
-    }
+    debug_info = host_debug_info(c, net, states, filters, cfg, 0)      # first image, like the reference
+    # batch-wide extras (not in the reference's dict)
+    debug_info.update(selected_filter_ids=c.ids, selected_filter_parameters=c.params, penalty=c.penalty)
     from .visualize import make_debugger
     debugger = make_debugger(filters, int(net.shape[1]))              # agent.py:141-204
 

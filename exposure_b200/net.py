@@ -99,6 +99,8 @@ class GAN:
   # ---- net.py:711-877 ------------------------------------------------------------------------
   def eval(self, spec_files=None, output_dir="./outputs", step_by_step=False, show_linear=True, show_input=True):
     """Retouch the listed image files (tif: ProPhoto linearisation; png/jpg: sRGB^2.2 / (2 max),
-    net.py:726-748) with cfg.test_steps policy steps and write `<name>.retouched.png`.  The
-    step_by_step / show_* debugging renderings of the reference are not produced."""
-    return evaluate_files(self.trainer, list(spec_files or []), output_dir=output_dir, generator=self.rng)
+    net.py:726-748) with cfg.test_steps policy steps and write what the reference writes per input:
+    `.retouched.png`, `.linear.png`, `.input_tone_mapped.png`, `.intermediateNN.png` (step_by_step),
+    `.steps.png` and `_debug.pkl` (exposure_b200/evaluate.py evaluate_files)."""
+    return evaluate_files(self.trainer, list(spec_files or []), output_dir=output_dir, generator=self.rng,
+                          step_by_step=step_by_step, show_linear=show_linear, show_input=show_input)

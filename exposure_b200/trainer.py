@@ -18,7 +18,10 @@ from .nets import CriticNet, ParamStore, PolicyNet
 def default_cfg():
   """The hot-path subset of config_example.py (same key names, same values)."""
   from .util import Dict
+  from . import filters as _f
   cfg = Dict()
+  cfg.filters = [_f.ExposureFilter, _f.GammaFilter, _f.ImprovedWhiteBalanceFilter, _f.SaturationPlusFilter,
+                 _f.ToneFilter, _f.ContrastFilter, _f.WNBFilter, _f.ColorFilter]       # config_example.py:22-25
   cfg.curve_steps = 8; cfg.gamma_range = 3; cfg.exposure_range = 3.5
   cfg.color_curve_range = (0.90, 1.10); cfg.tone_curve_range = (0.5, 2)
   cfg.masking = False; cfg.minimum_strength = 0.3; cfg.maximum_sharpness = 1; cfg.clamp = False

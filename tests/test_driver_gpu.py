@@ -57,7 +57,6 @@ def test_gan_train_save_restore_eval(built_lib, tmp_path, monkeypatch):
   assert len(info["filter_debug_info"]) == 8 and info["filter_debug_info"][4]["filter_parameters"].shape == (1, 1, 1, 8)
   assert info["filter_debug_info"][7]["filter_parameters"].shape == (1, 1, 3, 8) and info["filter_debug_info"][0]["mask"].shape == (1, 1, 1)
   sel = info["selected_filter_id"]
-  want = t.policy  # the selected filter's parameters in debug_info are the ones the step applied
   n = [1, 1, 3, 1, 8, 1, 1, 24][sel]
   assert np.allclose(info["filter_debug_info"][sel]["filter_parameters"].reshape(-1),
                      info["selected_filter_parameters"][0, :n].cpu().numpy(), rtol=1e-6, atol=1e-7)
@@ -73,3 +72,53 @@ def test_gan_train_save_restore_eval(built_lib, tmp_path, monkeypatch):
   hi = torch.rand(B, 96, 128, 3, device=t.device) * 0.2
   (net_h, _, hr), _, _ = cfg.generator(inp=[img, z, states], is_train=0, progress=0.5, cfg=cfg, high_res=hi)
   assert hr.shape == hi.shape
+
+
+def test_gan_eval_writes_the_reference_outputs(built_lib, tmp_path, monkeypatch):
+  """GAN.eval (net.py:711-877) per input file: retouched / linear / input_tone_mapped / intermediateNN /
+  steps montage / debug pickle; same-resolution files are batched; the step-by-step path ends on the same
+  pixels as the single fused full-resolution kernel."""
+  import pickle
+  import cv2
+  monkeypatch.chdir(tmp_path)
+  from exposure_b200.net import GAN
+  from exposure_b200.trainer import default_cfg
+  from exposure_b200.evaluate import evaluate_files
+  cfg = default_cfg()
+  cfg.name = "e"
+  cfg.batch_size = 8
+  cfg.replay_memory_size = 16
+  gan = GAN(cfg, seed=4)
+  rng = np.random.RandomState(0)
+  files = []
+  for k, (h, w) in enumerate(((90, 120), (90, 120), (70, 70))):
+    fn = str(tmp_path / ("in%d.png" % k))
+    cv2.imwrite(fn, (rng.rand(h, w, 3) * 255).astype(np.uint8))
+    files.append(fn)
+  out_dir = str(tmp_path / "outputs")
+  gan.rng.manual_seed(11)
+  ids = gan.eval(files, output_dir=out_dir, step_by_step=True)
+  S = cfg.test_steps
+  for fn in files:
+    base = os.path.join(out_dir, os.path.basename(fn))
+    for suffix in (".retouched.png", ".linear.png", ".input_tone_mapped.png", ".steps.png", "_debug.pkl"):
+      assert os.path.exists(base + suffix), suffix
+    assert [os.path.exists(base + ".intermediate%02d.png" % s) for s in range(S)] == [True] * (S - 1) + [False]
+    steps = cv2.imread(base + ".steps.png")
+    assert steps.shape == (68 * 4, 68 * (S + 1), 3)
+    infos = pickle.load(open(base + "_debug.pkl", "rb"))
+    assert len(infos) == S and [d["selected_filter_id"] for d in infos] == ids[fn]
+    assert len(infos[0]["filter_debug_info"]) == 8 and infos[0]["pdf"].shape == (8,)
+    ret = cv2.imread(base + ".retouched.png")
+    src = cv2.imread(fn)
+    assert ret.shape == src.shape
+  # the fused single-kernel path (no debug renderings) writes the same retouched pixels for the same draws
+  gan.rng.manual_seed(11)
+  out2 = str(tmp_path / "outputs2")
+  ids2 = evaluate_files(gan.trainer, files, output_dir=out2, generator=gan.rng, show_linear=False, show_input=False, debug=False)
+  assert ids2 == ids
+  for fn in files:
+    a = cv2.imread(os.path.join(out_dir, os.path.basename(fn) + ".retouched.png"))
+    b = cv2.imread(os.path.join(out2, os.path.basename(fn) + ".retouched.png"))
+    assert np.array_equal(a, b)
+    assert not os.path.exists(os.path.join(out2, os.path.basename(fn) + ".steps.png"))

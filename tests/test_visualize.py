@@ -55,3 +55,25 @@ def test_agent_debugger_is_pixel_exact(gold, filters, mode):
   panels = debugger(host, combined=False)
   for got, key in zip(panels, ("panel_pdf", "panel_detail", "panel_mask")):
     assert np.array_equal(got, gold[p + key]), key
+
+
+def test_steps_montage_layout():
+  """net.py:843-877: 4 rows x (steps+1) columns of 68-pixel cells; trajectory in row 0, the three debugger
+  panels of step i half a cell to the right of image i in rows 1-3 (with the reference's 2 / 4 pixel lifts)."""
+  from exposure_b200.evaluate import steps_montage
+  S = 3
+  traj = [np.full((64, 64, 3), 0.1 * (i + 1), dtype=np.float32) for i in range(S + 1)]
+  dec = [np.full((64, 64, 3), 0.5, dtype=np.float32)] * S
+  op = [np.full((64, 64, 3), 0.6, dtype=np.float32)] * S
+  msk = [np.full((64, 64, 3), 0.7, dtype=np.float32)] * S
+  m = steps_montage(traj, dec, op, msk)
+  assert m.shape == (272, 272, 3) and m.dtype == np.float32
+  for i in range(S + 1):
+    assert np.all(m[0:64, 68 * i:68 * i + 64] == np.float32(0.1 * (i + 1)))
+  assert np.all(m[0:64, 64:68] == 1.0)                                   # padding stays white
+  for i in range(S):
+    sx = 68 * i + 34
+    assert np.all(m[68:132, sx:sx + 64][:2] == 0.5)                      # rows 68..133 hold the decision, later rows are overdrawn
+    assert np.all(m[134:198, sx:sx + 64][:2] == 0.6)
+    assert np.all(m[200:264, sx:sx + 64] == 0.7)
+  assert np.all(m[:, 68 * S + 34 + 64:][64:] == 1.0)

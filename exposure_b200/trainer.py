@@ -58,8 +58,28 @@ class Trainer:
     self.cri.finalize(seed + 2)
     self.counter_g = self.counter_v = self.counter_c = 0        # net.py:216-241 global steps
     self._g_logit_cache = {}
+    # tf.train.ExponentialMovingAverage(decay=0.99, zero_debias=True) of c_average (net.py:119-120, 165-168;
+    # updated by every critic step, net.py:268-269): [debiased value, biased accumulator, local_step] on the
+    # device -- the checkpoint's mul_8/ExponentialMovingAverage{,/biased,/local_step}
+    self.ema_state = torch.zeros(3, device=self.device)
     self._hyper = {k: torch.zeros(1, device=self.device) for k in "gvc"}
     self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+  @property
+  def ema(self):
+    v = self.ema_state.tolist()
+    return {"value": v[0], "biased": v[1], "local_step": v[2]}
+
+  @ema.setter
+  def ema(self, d):
+    self.ema_state.copy_(torch.tensor([d["value"], d["biased"], d["local_step"]], dtype=torch.float32))
+
+  def _ema_update(self, c_average, decay=0.99):
+    """moving_averages._zero_debias: biased -= (biased - x)(1 - decay); step += 1; value = biased / (1 - decay^step)."""
+    st = self.ema_state
+    st[1:2].mul_(decay).add_(c_average.reshape(1), alpha=1.0 - decay)
+    st[2:3].add_(1.0)
+    st[0:1].copy_(st[1:2] / (1.0 - torch.pow(torch.full_like(st[2:3], decay), st[2:3])))
 
   # ---- optimizer --------------------------------------------------------------------------
   def _set_lr(self, key, lr, t):
@@ -86,6 +106,7 @@ class Trainer:
                     drop_s=z(B, 4, 4, 256), progress=z(1))
     self._ci = dict(real=z(B, 64, 64, 3), fake=z(B, 64, 64, 3), alpha=z(B))
     snap = [t.clone() for s in (self.gen, self.val, self.cri) for t in (s.flat, s.m, s.v)]
+    ema_snap = self.ema_state.clone()
     for k in "gvc":
       self._hyper[k].zero_()
     # world > 1: the graphs hold forward + backward only; the NCCL all-reduce and the fused Adam
@@ -117,6 +138,7 @@ class Trainer:
     for s in (self.gen, self.val, self.cri):
       for t in (s.flat, s.m, s.v):
         t.copy_(next(it))
+    self.ema_state.copy_(ema_snap)
     self._graph_B = B
 
   # ---- generator + value step (net.py:56-163, 222-239, 330) ---------------------------------
@@ -191,6 +213,7 @@ class Trainer:
       graph.replay()
       if not self._graph_apply:
         self._adam(self.cri, "c")
+        self._ema_update(self._cout["c_average"])                # rank-local shard mean (a logging statistic)
       return self._cout
     return self._critic_impl(real, fake, alpha, apply)
 
@@ -221,7 +244,11 @@ class Trainer:
     with K.fork(7):                                              # logging scalars: off the optimizer's path
       emd = logit[:B].mean() - logit[B:2 * B].mean()             # net.py:164  emd = -c_loss (before GP)
       gp = lam * (torch.clamp(norm - 1.0, min=0.0) ** 2).mean()
-      out = dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit)
+      c_average = (logit[:B].mean() + logit[B:2 * B].mean()) * 0.5  # net.py:165 (forward of this step, pre-update)
+      if apply:
+        self._ema_update(c_average)                                 # net.py:166, 268-269: part of opt_c
+      out = dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit,
+                 c_average=c_average)
     if apply:
       self._adam(self.cri, "c")
     K.join()

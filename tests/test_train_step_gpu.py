@@ -142,3 +142,28 @@ def test_cuda_graph_replay_matches_eager(built_lib):
   for sa, sb in ((a.gen, b.gen), (a.val, b.val), (a.cri, b.cri)):
     assert torch.allclose(sa.flat, sb.flat, rtol=1e-6, atol=1e-8), float((sa.flat - sb.flat).abs().max())
   assert b.graph_launches["generator"] > 50 and b.graph_launches["critic"] > 50
+
+
+def test_c_average_moving_average_follows_tf_zero_debias(built_lib):
+  """tf.train.ExponentialMovingAverage(decay=0.99, zero_debias=True) of c_average = mean(D(fake) + D(real)) / 2,
+  updated once per applied critic step (net.py:119-120, 165-168, 268-269); in the shipped checkpoint
+  mul_8/ExponentialMovingAverage/local_step == Variable_2 (critic steps) confirms the cadence."""
+  from exposure_b200.trainer import Trainer
+  t = Trainer(seed=2)
+  g = torch.Generator(device="cuda").manual_seed(4)
+  biased, want = 0.0, None
+  for k in range(1, 4):
+    real = torch.rand(8, 64, 64, 3, device="cuda", generator=g)
+    fake = torch.rand(8, 64, 64, 3, device="cuda", generator=g) * 0.3
+    alpha = torch.rand(8, device="cuda", generator=g)
+    out = t.critic_step(real, fake, alpha, lr_c=1e-5, apply=True)
+    c_avg = float(out["c_average"])
+    lg = out["logits"]
+    assert abs(c_avg - 0.5 * float(lg[:8].mean() + lg[8:16].mean())) < 1e-6
+    biased = biased - (biased - c_avg) * (1 - 0.99)
+    want = biased / (1 - 0.99 ** k)
+    e = t.ema
+    assert e["local_step"] == k and abs(e["biased"] - biased) < 1e-5 * (1 + abs(biased)) and abs(e["value"] - want) < 1e-4 * (1 + abs(want))
+  before = t.ema
+  t.critic_step(real, fake, alpha, lr_c=1e-5, apply=False)        # gradient-only call: opt_c not run, no update
+  assert t.ema == before

@@ -302,6 +302,33 @@ class FilterProcessFn(torch.autograd.Function):
     return gx, gparams[:, :params.shape[1]] if params.shape[1] != PSTRIDE else gparams, None
 
 
+class FilterChainFn(torch.autograd.Function):
+  """autograd node for a whole chain of S filter steps: (x, logits [S,B,24]) -> x_S with ids [S,B].
+  forward: exp_filter_chain_fwd (24 B/pixel for all S steps); backward: exp_filter_chain_fwd_bwd with the
+  output store skipped (36 B/pixel) -- 60 B/pixel per training step for the whole chain, no intermediate
+  image is ever saved for the backward (only x)."""
+
+  @staticmethod
+  def forward(ctx, x, logits, ids):
+    x, logits = x.contiguous(), logits.contiguous()
+    ctx.ids = ids
+    ctx.save_for_backward(x, logits)
+    return filter_chain_fwd(x, logits, ids, logits=True)
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, logits = ctx.saved_tensors
+    _, gx, glogits = filter_chain_fwd_bwd(x, gy.contiguous(), logits, ctx.ids, need_y=False,
+                                          need_gx=ctx.needs_input_grad[0], logits=True)
+    return gx, glogits, None
+
+
+def filter_chain(x, logits, ids):
+  """Differentiable S-step filter chain (torch autograd): x [B,H,W,3], logits [S,B,24] raw regressor inputs,
+  ids int32 [S,B]."""
+  return FilterChainFn.apply(x, logits, ids)
+
+
 class FilterRegressFn(torch.autograd.Function):
   """autograd node for filter_param_regressor: logits -> params[B,24]."""
 

@@ -183,3 +183,28 @@ def test_fused_chain_full_size_properties(ops):
   ga = ga.clone()
   _, _, gb = top.forward_backward(x[:, 256:].contiguous(), gout[:, 256:].contiguous(), need_output=False, need_input_grad=False)
   assert _rel(ga + gb, gl1, floor=1e-2) < 1e-4
+
+
+def test_filter_chain_autograd_node(ops):
+  """ops.filter_chain under torch autograd == composing the per-step autograd nodes."""
+  B, H, W, S = 3, 40, 36, 4
+  g = torch.Generator().manual_seed(12)
+  ids = torch.tensor([[0, 4, 7], [1, 5, 2], [3, 6, 4], [7, 0, 1]], dtype=torch.int32).cuda()
+  x = F.synth_images(B, H, W, seed=13).cuda().requires_grad_(True)
+  logits = (torch.randn(S, B, 24, generator=g) * 0.5).cuda().requires_grad_(True)
+  w = torch.randn(B, H, W, 3, generator=g).cuda()
+  y = ops.filter_chain(x, logits, ids)
+  (y * w).sum().backward()
+  gx, gl = x.grad.clone(), logits.grad.clone()
+  x2 = x.detach().clone().requires_grad_(True)
+  l2 = logits.detach().clone().requires_grad_(True)
+  cur = x2
+  for s in range(S):
+    p = ops.FilterRegressFn.apply(l2[s], ids[s])
+    cur = ops.FilterProcessFn.apply(cur, p, ids[s])
+  (cur * w).sum().backward()
+  assert _rel(y, cur) < 2e-6 and _rel(gx, x2.grad) < 2e-6
+  for s in range(S):
+    for b in range(B):
+      n = F.NUM_PARAMS[int(ids[s, b])]
+      assert _rel(gl[s, b, :n], l2.grad[s, b, :n], floor=1e-2) < 2e-5, (s, b)

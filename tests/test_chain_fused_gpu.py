@@ -22,7 +22,7 @@ def ops(built_lib):
 
 
 def _rel(a, b, floor=1e-3):
-  a, b = a.double().cpu(), b.double().cpu()
+  a, b = a.detach().double().cpu(), b.detach().double().cpu()
   return float(((a - b).abs() / b.abs().clamp_min(floor * float(b.abs().max()) + 1e-30)).max())
 
 

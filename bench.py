@@ -38,7 +38,7 @@ FWD_B, BWD_B = 24, 36                        # algorithmic bytes / pixel / step 
 def parse_args():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=200)
+  ap.add_argument("--steps", type=int, default=400)
   ap.add_argument("--warmup", type=int, default=10)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
   ap.add_argument("--workload", default="chain8", choices=["chain8", "train", "eval"])
@@ -180,7 +180,7 @@ class ClockSampler:
       os.close(fd)
       self.fh = open(self.path, "w")
       self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                    "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.fh,
                                    stderr=subprocess.DEVNULL)
     except Exception:
       self.proc = None

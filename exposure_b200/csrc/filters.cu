@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kThreads) filter_chain_fwd_kernel(const ChainA
 // y) ever touches HBM and no step is recomputed.  The kernel is instruction-bound, not HBM-bound.
 // Filter ids are per image and per step (run time): the step loop is a `switch` over the per-filter
 // bodies, so the parameter-gradient accumulators cannot live in registers across steps.  They are
-// reduced per tile-step with a multi-value butterfly (N values in N-1+log.. shuffles instead of 5 N)
+// reduced per tile-step with a multi-value butterfly (8 values in 4+2+1+1+1 = 9 shuffles instead of 40)
 // into per-warp shared-memory slots owned by one lane each -> deterministic; CTA partial records and
 // the last-CTA fixed-order fp64 finish are those of the per-step kernels.
 constexpr int kChainRec = kMaxChain * EXP_MAX_FILTER_PARAMS;   // floats per CTA partial record (worst case)
@@ -440,8 +440,11 @@ struct ChainBwdArgs {
   int S, B, P, pstride, logits, nblk, ntiles;
 };
 
-// Sum N (power of two) per-lane values over the warp.  Afterwards the lanes with (lane & (32/N - 1)) == 0
-// ... hold the total of value index `idx` (returned); every stage halves the values a lane carries.
+// Sum N (power of two) per-lane values over the warp: at every stage a lane keeps one half of its values
+// (which half is chosen by its lane bit), sends the other half to its partner and adds what it receives, so
+// the number of values it carries halves; once one is left the remaining stages are plain butterflies.
+// Afterwards every lane holds the warp total of value `idx` (lanes that differ only in their low
+// log2(32/N) bits hold the same one: the caller lets the lane with those bits zero write).  Fixed order.
 template <int N>
 __device__ __forceinline__ float warp_multi_sum(float (&v)[N], int lane, int& idx) {
   idx = 0;

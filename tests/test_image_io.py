@@ -19,3 +19,18 @@ def test_tif_and_png_linearisation(tmp_path):
   out = str(tmp_path / "x.png")
   save_png(out, np.clip(a * 4, 0, 1))
   assert os.path.getsize(out) > 1000
+
+
+def test_thumbnail_pipeline_matches_reference_code():
+  """load_linear_image + center_thumbnail against the thumbnails the reference's own util.py functions made
+  (linearize_ProPhotoRGB, get_image_center, cv2.resize(..., (64, 64)) as in net.py:726,779; stored as
+  `thumbs` in tests/golden/reference_golden.npz by make_reference_golden.py)."""
+  import torch
+  from exposure_b200.evaluate import center_thumbnail, load_linear_image
+  gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+  for k, name in enumerate(("A.tif", "H.tif")):
+    lin = load_linear_image(os.path.join(SAMPLES, name))
+    thumb = center_thumbnail(torch.from_numpy(lin)[None], 64)[0].numpy()
+    want = gold["thumbs"][k]
+    assert thumb.shape == want.shape == (64, 64, 3)
+    assert float(np.abs(thumb - want).max()) < 2e-6, name

@@ -124,6 +124,28 @@ def run_reference(args):
     return
   import torch
   from oracle import filters as F
+  if args.workload == "train":
+    iteration, sb, cores = _cpu_train_iteration(args.batch)
+    for _ in range(max(1, min(args.warmup, 2))):
+      iteration()
+    t0 = time.time()
+    for _ in range(args.steps):
+      iteration()
+    dt = time.time() - t0
+    val = sb * args.steps / dt
+    sample = ("each step = 1 generator+value step + 5 critic steps on a bounded sample of %d of the %d images; CPU "
+              "restatement of the reference TF graph (oracle/train_step.py port, torch-CPU autograd), %d threads" %
+              (sb, args.batch, cores))
+    print(json.dumps({
+        "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": train_config(args),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+    return
   cores = host_threads()
   torch.set_num_threads(cores)
   sample_b = 2
@@ -671,9 +693,10 @@ def run_train(args):
     print(json.dumps(out))
 
 
-def cpu_baseline_train(B, budget_s=25.0):
+def _cpu_train_iteration(B):
   """The reference's CPU path for one train iteration: oracle generator step + 5 critic steps
-  (autograd, all 8 filters + one-hot select), on a bounded sample of the batch."""
+  (autograd, all 8 filters + one-hot select), on a bounded sample of the batch.  Returns
+  (callable running one iteration, images in the sample, host threads used)."""
   import torch
   from oracle import filters as OF
   from oracle import train_step as OT
@@ -719,6 +742,11 @@ def cpu_baseline_train(B, budget_s=25.0):
     for _ in range(5):
       OT.critic_step(Pc, real, out["fake_output"], alpha, cfg)
 
+  return iteration, sb, cores
+
+
+def cpu_baseline_train(B, budget_s=25.0):
+  iteration, sb, cores = _cpu_train_iteration(B)
   iteration()
   times = []
   t_end = time.time() + budget_s

@@ -46,6 +46,7 @@ class Trainer:
 
   def __init__(self, cfg=None, device=None, seed=0):
     self.cfg = cfg or default_cfg()
+    self._check_cfg(self.cfg)
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.gen = ParamStore(self.device)
     self.policy = PolicyNet(self.gen, n_states=self.cfg.num_state_dim, scope="generator")
@@ -64,6 +65,30 @@ class Trainer:
     self.ema_state = torch.zeros(3, device=self.device)
     self._hyper = {k: torch.zeros(1, device=self.device) for k in "gvc"}
     self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+  @staticmethod
+  def _check_cfg(cfg):
+    """Config branches of the reference that this path does not implement fail loudly instead of training
+    something else: every shipped config (config_example.py, config_sintel.py) uses the values accepted here."""
+    g = lambda k, d: cfg[k] if k in cfg else d
+    unsupported = []
+    if g("gan", "w") != "w":
+      unsupported.append("cfg.gan == %r (LSGAN branch net.py:99-100,131-149; 'not supported' in config_example.py:95)" % cfg["gan"])
+    if g("supervised", False):
+      unsupported.append("cfg.supervised (net.py:96-97, 212-214)")
+    if not g("use_TD", True):
+      unsupported.append("cfg.use_TD == False (net.py:156-158: greedy single-step reward)")
+    if g("clamp", False):
+      unsupported.append("cfg.clamp (agent.py:235-236: clip the filtered image to [0, 5])")
+    if not g("shared_feature_extractor", True):
+      unsupported.append("cfg.shared_feature_extractor == False (agent.py:62-65: one CNN per filter)")
+    if not g("img_include_states", True):
+      unsupported.append("cfg.img_include_states == False (util.py:31-36)")
+    if g("gradient_penalty_lambda", 10) <= 0:
+      unsupported.append("cfg.gradient_penalty_lambda <= 0 (weight clamping, net.py:252-264)")
+    if unsupported:
+      raise NotImplementedError("exposure_b200 implements the shipped configuration of the hot path only; unsupported: "
+                                + "; ".join(unsupported))
 
   @property
   def ema(self):

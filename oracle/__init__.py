@@ -15,7 +15,9 @@ with name-seeded weights; the outputs are committed as tests/golden/reference_go
 and tests/test_reference_golden.py holds this oracle to them (<= 5e-6 in fp64, bounded by
 fp32 rounding of constants): every Filter subclass forward / gradients, masked apply,
 5-step agent_generator rollouts, critic / value, the generator / value / critic losses
-and their gradients including the WGAN-GP double backward.  So op order, constants,
+and their gradients including the WGAN-GP double backward (the same script also records the
+reference's cv2 debugger canvases, its thumbnails of the sample TIFFs and the draw sequences
+of its ReplayMemory, which pin the host-side mirrors in exposure_b200/).  So op order, constants,
 broadcasting, variable scopes and formulas are pinned to the reference source.  What
 stays restated from TF 1.6's published kernels, in the shim exactly as here: exp / pow /
 cos / tanh / sigmoid, clip_by_value / maximum / minimum tie rules, RGBToHSV / HSVToRGB

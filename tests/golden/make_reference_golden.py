@@ -3,7 +3,7 @@
 
   python tests/golden/make_reference_golden.py         ->  tests/golden/reference_golden.npz
 
-What runs: /root/reference/{filters,agent,critics,pdf_sample_layer,util,config_example}.py, imported
+What runs: /root/reference/{filters,agent,critics,pdf_sample_layer,util,config_example,replay_memory}.py, imported
 unmodified from where they lie (read-only), over tests/golden/tf1_shim -- an eager stand-in for the
 slice of the TensorFlow 1.x API those files call (TF 1.6 is not installable here).  So the op order,
 constants, broadcasting, variable scopes and every formula are the reference's; the TF primitives
@@ -21,6 +21,7 @@ Sections (all inputs and random draws are stored next to the outputs):
   4. critic / value network
   5. critic loss with the WGAN-GP term and its double-backward; generator / value losses
   6. the cv2 visual debugger: every Filter.visualize_filter / visualize_mask, agent_generator's debugger
+  7. ReplayMemory: the records every generator / critic batch draws over 40 iterations (replay_memory.py)
 Sections 3-5 run twice: with the shipped pretrained checkpoint ("pre_": compact outputs; the weights
 do not travel, so only tests in the build container can use them) and with the name-seeded weights of
 tests/golden/seeded_weights.py ("seed_": full outputs, reproducible on the GPU box).
@@ -433,6 +434,54 @@ def section_visualize(P):
       put(pre, **{"param%d" % j: d["filter_parameters"], "mask%d" % j: d["mask"]})
 
 
+# 7. ReplayMemory (replay_memory.py:8-282): which records each generator / critic batch draws, driven the way
+#    GAN.train drives it (net.py:325-362) with counting stand-ins for the data providers.  All randomness is
+#    Python's `random` (shuffle / random()), seeded.
+def section_replay():
+  import random
+  import replay_memory as RM  # noqa: E402  (reference)
+
+  class Counting:
+    """data-provider stand-in: image k is filled with the value k (so a record's identity survives)."""
+
+    def __init__(self, start):
+      self.n = start
+
+    def get_next_batch(self, bs):
+      ids = np.arange(self.n, self.n + bs, dtype=np.float32)
+      self.n += bs
+      return np.tile(ids[:, None, None, None], (1, 4, 4, 3)), np.zeros(bs, dtype=np.float32)
+
+  for tag, test_steps in (("a", 5), ("b", 9)):               # b: trajectories outlive maximum_trajectory_length = 7
+    c2 = util.Dict(dict(cfg))
+    c2.source_img_size = c2.real_img_size = 4
+    c2.replay_memory_size, c2.batch_size, c2.test_steps = 8, 4, test_steps     # pool = 2 x batch like config_example.py:53,131
+    c2.fake_data_provider = lambda: Counting(0)
+    c2.fake_data_provider_test = lambda: Counting(100000)
+    c2.real_data_provider = lambda: Counting(200000)
+    random.seed(4242)
+    mem = RM.ReplayMemory(c2, load=True)
+    B = c2.batch_size
+    kinds, ids, steps = [], [], []
+    for it in range(40):
+      images, states, features = mem.get_next_fake_batch(B)                       # net.py:326 -> replay_memory.py:230-246
+      kinds.append(0); ids.append(images[:, 0, 0, 0].copy()); steps.append(states[:, util.STATE_STEP_DIM].copy())
+      new_states = states.copy()                                                   # agent.py:208-222
+      last = (np.abs(states[:, util.STATE_STEP_DIM] + 1 - c2.test_steps) < 1e-4).astype(np.float32)
+      new_states[:, util.STATE_REWARD_DIM] = last
+      new_states[:, util.STATE_STOPPED_DIM] = last
+      new_states[:, util.STATE_STEP_DIM] = states[:, util.STATE_STEP_DIM] + 1
+      mem.replace_memory(mem.images_and_states_to_records(images, new_states, features))   # net.py:340-342
+      # the reference asserts when the pool holds no terminated record (hence its 100 warm-up generator steps,
+      # net.py:318-320); the driver here simply skips the critic batches of such an iteration
+      if any(r.state[util.STATE_STOPPED_DIM] > 0 for r in mem.image_pool):
+        for _ in range(2):
+          images, states, features = mem.replay_fake_batch(B)                    # net.py:357 -> replay_memory.py:249-273
+          kinds.append(1); ids.append(images[:, 0, 0, 0].copy()); steps.append(states[:, util.STATE_STEP_DIM].copy())
+    put("rp_" + tag, kinds=np.array(kinds, dtype=np.int32), ids=np.stack(ids).astype(np.int64), steps=np.stack(steps).astype(np.int32),
+        test_steps=test_steps, seed=4242, pool=8, batch=4)
+
+
 def main():
   torch.set_num_threads(max(1, os.cpu_count() or 1))
   section_filters()
@@ -443,6 +492,7 @@ def main():
     section_critic(kind, P)
     section_losses(kind, P)
   section_visualize(P)
+  section_replay()
   OUT["provenance"] = np.array(
       "reference Python (yuanming-hu/exposure @ 7bb838a: filters.py, agent.py, critics.py, pdf_sample_layer.py, util.py, "
       "config_example.py) executed over tests/golden/tf1_shim (TF-1 API stand-in on torch CPU); not TensorFlow binaries")

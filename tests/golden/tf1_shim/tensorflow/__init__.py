@@ -93,8 +93,18 @@ def ones(shape, dtype=float32):
   return torch.ones(tuple(shape), dtype=_dt(dtype))
 
 
-def placeholder(*a, **k):
-  raise NotImplementedError("eager shim: feed tensors directly")
+class _Placeholder:
+  """tf.placeholder: only its static shape is ever read by the code run here (replay_memory.py:16-40,112-116)."""
+
+  def __init__(self, dtype, shape=None, name=None):
+    self.dtype, self.shape, self.name = dtype, shape, name
+
+  def get_shape(self):
+    return self.shape
+
+
+def placeholder(dtype, shape=None, name=None):
+  return _Placeholder(dtype, shape, name)
 
 
 # --------------------------------------------------------------------------------------------

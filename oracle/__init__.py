@@ -8,7 +8,8 @@ PARITY: PINNED TO THE REFERENCE'S PYTHON, NOT TO TENSORFLOW BINARIES.  The refer
 (yuanming-hu/exposure @ 7bb838a) ships no golden vectors / known-answer tests and
 TensorFlow 1.6 cannot be installed in this image.  What can run here is the reference's
 own Python: tests/golden/make_reference_golden.py imports filters.py, agent.py,
-critics.py, pdf_sample_layer.py, util.py and config_example.py from /root/reference
+critics.py, pdf_sample_layer.py, util.py, config_example.py, replay_memory.py and net.py
+(GAN.__init__'s graph construction, run eagerly on pre-fed placeholders) from /root/reference
 unmodified and executes them over tests/golden/tf1_shim (an eager stand-in for the TF-1
 API subset they call, torch CPU underneath), with the shipped pretrained checkpoint and
 with name-seeded weights; the outputs are committed as tests/golden/reference_golden.npz

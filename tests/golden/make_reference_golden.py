@@ -3,7 +3,7 @@
 
   python tests/golden/make_reference_golden.py         ->  tests/golden/reference_golden.npz
 
-What runs: /root/reference/{filters,agent,critics,pdf_sample_layer,util,config_example,replay_memory}.py, imported
+What runs: /root/reference/{filters,agent,critics,pdf_sample_layer,util,config_example,replay_memory,net}.py, imported
 unmodified from where they lie (read-only), over tests/golden/tf1_shim -- an eager stand-in for the
 slice of the TensorFlow 1.x API those files call (TF 1.6 is not installable here).  So the op order,
 constants, broadcasting, variable scopes and every formula are the reference's; the TF primitives
@@ -11,15 +11,17 @@ underneath (exp, pow, clip tie rules, RGB<->HSV functors, moments, SAME conv, dr
 restatement of TF 1.6 on torch CPU, and torch autograd stands in for tf.gradients.  The only source
 patch: util.py:658-664 names a variable `async` (a keyword since Python 3.7) inside its self-test,
 which is renamed in memory before compiling; `skimage` / `tifffile` (util.py:484-485, image file I/O
-only) are stubbed.  net.py / replay_memory.py build a placeholder graph and cannot be executed this
-way; the few loss lines of net.py:92-194 used in section 5 are restated here and cited.
+only) are stubbed.  net.py's graph construction (GAN.__init__) is executed too (section 5b): its
+placeholders are handed the batch a sess.run would feed, so the graph-building code computes eagerly;
+section 5 keeps an independent line-by-line restatement of net.py:92-194 next to it.
 
 Sections (all inputs and random draws are stored next to the outputs):
   1. every Filter subclass: filter_param_regressor + process, fp64 and fp32 runs, autograd gradients
   2. Filter.apply with masking on (extract_parameters -> regressor -> get_mask -> lerp) + high_res
   3. agent_generator: 5-step rollouts (argmax and sampled) + the high_res branch
   4. critic / value network
-  5. critic loss with the WGAN-GP term and its double-backward; generator / value losses
+  5. critic loss with the WGAN-GP term and its double-backward; generator / value losses (restated lines)
+  5b. the same from net.py's own GAN.__init__ executed eagerly (losses, rewards, tf.gradients per optimizer)
   6. the cv2 visual debugger: every Filter.visualize_filter / visualize_mask, agent_generator's debugger
   7. ReplayMemory: the records every generator / critic batch draws over 40 iterations (replay_memory.py)
 Sections 3-5 run twice: with the shipped pretrained checkpoint ("pre_": compact outputs; the weights
@@ -388,6 +390,73 @@ def section_losses(kind, P):
   tf.set_float_dtype(torch.float32)
 
 
+# 5b. the same losses from net.py ITSELF: GAN.__init__ (net.py:20-284) builds its whole graph -- generator,
+#     critic x3, value x2, rewards, TD target, losses, gradient penalty, the three ly.optimize_loss -- and runs
+#     eagerly here because every tf.placeholder already holds the batch a sess.run would feed (tf.feeds).
+#     ly.optimize_loss records tf.gradients(loss, theta); nothing is stepped.
+def section_net_graph(kind, P):
+  import tempfile
+  import tensorflow.contrib.layers as ly
+  import net as RN  # noqa: E402  (reference net.py)
+  tf.set_float_dtype(torch.float64)
+  use_weights(kind, P, ("generator", "critic", "rl_value"))
+  draws = Draws(7000)
+  tf.nn.dropout_source = draws
+  g = torch.Generator().manual_seed(7001)
+  fake_input = torch.from_numpy(thumbnails()).double()
+  B = fake_input.shape[0]
+  real = (images(B, 64, 64, seed=7002) * 0.6).clamp(0, 1)
+  z = torch.rand(B, cfg.z_dim, generator=g, dtype=torch.float64)
+  states = torch.zeros(B, cfg.num_state_dim, dtype=torch.float64)
+  states[:, 2] = torch.tensor([0, 2, 4, 4], dtype=torch.float64)[:B]
+  alpha = torch.rand(B, 1, 1, 1, generator=g, dtype=torch.float64)          # same draws as section 5
+  progress = 0.4
+  if kind == "seed":
+    with torch.no_grad():
+      quiet(RC.critic, images=real, cfg=cfg, is_train=True)
+      tf.variables()["critic/fully_connected_1/weights"].mul_(40.0)
+    tf._store.counts.clear()                                                # as if the graph were built from scratch
+  tf.contrib.distributions.source = lambda shape: alpha.reshape(shape)
+  tf.contrib.distributions.log.clear()
+  ly.optimize_log.clear()
+  tf.feeds.clear()
+  tf.feeds.update(fake_input=fake_input, real_data=real, z=z, states=states, progress=torch.tensor(progress, dtype=torch.float64),
+                  is_train=torch.tensor(1, dtype=torch.int32), lr_g=torch.tensor(1e-5, dtype=torch.float64),
+                  lr_c=torch.tensor(1e-5, dtype=torch.float64))
+  c2 = util.Dict(dict(cfg))
+  c2.name = "golden"
+  c2.batch_size = B                                                         # alpha's shape (net.py:176)
+  c2.real_data_provider = lambda: None
+  cwd = os.getcwd()
+  with tempfile.TemporaryDirectory() as tmp:
+    os.chdir(tmp)
+    try:
+      gan = quiet(RN.GAN, c2, restore=True)
+    finally:
+      os.chdir(cwd)
+      tf.feeds.clear()
+  assert len(ly.optimize_log) == 3 and len(tf.contrib.distributions.log) == 1
+  opt_v, opt_g, opt_c = ly.optimize_log                                      # net.py:218, 231, 244 in this order
+  pre = kind + "_ng"
+  gp = gan.c_loss - tf.reduce_mean(gan.fake_logit - gan.real_logit)          # c_loss = emd part + penalty (net.py:151, 194)
+  put(pre, g_loss=gan.g_loss, v_loss=gan.v_loss, c_loss=gan.c_loss, emd=gan.emd, gradient_penalty=gp,
+      critic_gradient_norm=gan.critic_gradient_norm, fake_logit=gan.fake_logit, real_logit=gan.real_logit,
+      old_value=gan.old_value, new_value=gan.new_value, new_states=gan.new_states, surrogate=gan.surrogate_loss_addition,
+      penalty=gan.penalty, reward=gan.reward, q_value=gan.q_value, advantage=gan.advantage,
+      fake_output=gan.fake_output.float() if kind == "seed" else compact(gan.fake_output),
+      n_theta=np.array([len(gan.theta_g), len(gan.theta_v), len(gan.theta_c)]))
+  for rec in (opt_v, opt_g, opt_c):
+    for k, gk in rec["grads"].items():
+      small = k.endswith("biases") or "fully_connected_1" in k or "fc2" in k or k.endswith("Conv/weights")
+      if k.startswith("generator/") and k not in GRAD_NAMES:
+        continue
+      if small:
+        put(pre, **{"grad_" + k.replace("/", "."): gk})
+      else:
+        put(pre, **{"gradsample_" + k.replace("/", "."): gk.reshape(-1)[::997].clone(), "gradnorm_" + k.replace("/", "."): gk.norm()})
+  tf.set_float_dtype(torch.float32)
+
+
 # 6. visual debugger: Filter.visualize_filter / visualize_mask (filters.py:150-168 + overrides) and the
 #    debugger closure of agent_generator (agent.py:141-204) -- host-side cv2 drawing on debug_info
 def section_visualize(P):
@@ -491,6 +560,7 @@ def main():
     section_agent(kind, P)
     section_critic(kind, P)
     section_losses(kind, P)
+    section_net_graph(kind, P)
   section_visualize(P)
   section_replay()
   OUT["provenance"] = np.array(

@@ -103,8 +103,97 @@ class _Placeholder:
     return self.shape
 
 
+# Graph-construction code (net.py GAN.__init__) runs eagerly when its placeholders already hold the values
+# the session would be fed: `feeds[name]` -> the tensor returned for tf.placeholder(..., name=name).
+feeds = {}
+
+
 def placeholder(dtype, shape=None, name=None):
+  if name in feeds:
+    v = feeds[name]
+    return v if isinstance(v, torch.Tensor) else torch.tensor(v, dtype=_dt(dtype))
   return _Placeholder(dtype, shape, name)
+
+
+def equal(x, y):
+  return x == y
+
+
+class _Obj:
+  """attribute bag for configuration protos / handles nobody reads back"""
+
+  def __getattr__(self, k):
+    o = _Obj()
+    object.__setattr__(self, k, o)
+    return o
+
+
+def ConfigProto(**k):
+  return _Obj()
+
+
+class Session:
+
+  def __init__(self, config=None):
+    self.graph = None
+
+  def run(self, *a, **k):
+    return None
+
+
+class Variable:
+  """non-trainable counters (net.py:216, 229, 241); trainable variables come from get_variable"""
+
+  def __init__(self, initial_value=0, trainable=False, dtype=None, name=None):
+    self.value = initial_value
+
+
+class GraphKeys:
+  TRAINABLE_VARIABLES = "trainable_variables"
+
+
+def get_collection(key, scope=None):
+  assert key == GraphKeys.TRAINABLE_VARIABLES
+  return [_NamedVar(k, v) for k, v in _store.vars.items() if scope is None or k.startswith(scope + "/") or k == scope]
+
+
+class _NamedVar:
+  def __init__(self, name, tensor):
+    self.name, self.tensor = name, tensor
+
+
+@contextlib.contextmanager
+def control_dependencies(ops):
+  yield
+
+
+def group(*ops):
+  return ops
+
+
+def assign(var, value):
+  return ("assign", var, value)
+
+
+def global_variables_initializer():
+  return None
+
+
+class _Summary:
+  @staticmethod
+  def scalar(name, value):
+    return None
+
+  @staticmethod
+  def merge_all():
+    return None
+
+  @staticmethod
+  def FileWriter(*a, **k):
+    return _Obj()
+
+
+summary = _Summary
 
 
 # --------------------------------------------------------------------------------------------
@@ -391,11 +480,30 @@ class _Image:
 image = _Image
 
 
+class _EMA:
+  """tf.train.ExponentialMovingAverage(zero_debias=True): after its first update the debiased average IS the
+  value (0.01 x / (1 - 0.99)); only the visualisation reads it (net.py:167-168)."""
+
+  def __init__(self, decay, zero_debias=False):
+    self.decay = decay
+
+  def apply(self, values):
+    return ("ema_update", values)
+
+  def average(self, value):
+    return value.detach()
+
+
 class _Train:
+  ExponentialMovingAverage = _EMA
 
   @staticmethod
   def AdamOptimizer(*a, **k):
-    raise NotImplementedError("eager shim: optimizers are outside the golden-vector scope")
+    return ("adam", a, k)                    # never stepped here: ly.optimize_loss only records the gradients
+
+  @staticmethod
+  def Saver(*a, **k):
+    return _Obj()
 
 
 train = _Train

@@ -49,3 +49,16 @@ def fully_connected(inputs, num_outputs, activation_fn=_relu, weights_initialize
 
 def dropout(inputs, keep_prob=0.5, is_training=True, **k):
   return tf.nn.dropout(inputs, keep_prob) if is_training else inputs
+
+
+optimize_log = []      # one record per ly.optimize_loss call: the loss and d loss / d variable by name
+
+
+def optimize_loss(loss, learning_rate, optimizer, variables, global_step=None, summaries=None, **k):
+  """tf.contrib.layers.optimize_loss: here only its gradient computation (tf.gradients(loss, variables));
+  nothing is stepped."""
+  grads = torch.autograd.grad(loss, [v.tensor for v in variables], retain_graph=True, allow_unused=True)
+  rec = {"loss": loss.detach(), "grads": {v.name: (torch.zeros_like(v.tensor) if g is None else g.detach())
+                                          for v, g in zip(variables, grads)}}
+  optimize_log.append(rec)
+  return rec

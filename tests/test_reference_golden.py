@@ -1,6 +1,7 @@
 """The oracle (oracle/) against vectors produced by executing the REFERENCE'S OWN PYTHON
 (tests/golden/reference_golden.npz, made by tests/golden/make_reference_golden.py: the reference's
-filters.py / agent.py / critics.py / pdf_sample_layer.py / util.py run over a TF-1 API stand-in).
+filters.py / agent.py / critics.py / pdf_sample_layer.py / util.py / net.py (GAN.__init__) run over a TF-1
+API stand-in).
 This is what pins the oracle: op order, constants, scopes / variable names and formulas are the
 reference's; only the TF primitives underneath are restated (see the generating script's header).
 
@@ -250,11 +251,16 @@ def test_critic_and_value_match_reference_code(gold, kind):
 
 
 # 5. losses and their gradients (generator / value step and critic step with the WGAN-GP double backward)
+# src "ls": net.py:92-194 restated line by line in the generating script on top of the reference's callables;
+# src "ng": net.py's own GAN.__init__ executed eagerly (placeholders pre-fed), gradients as recorded by its three
+# ly.optimize_loss calls.  Same inputs; the two agree to the last bit, and the oracle must match both.
+@pytest.mark.parametrize("src", ["ls", "ng"])
 @pytest.mark.parametrize("kind", ["seed", "pre"])
-def test_train_step_losses_match_reference_code(gold, kind):
+def test_train_step_losses_match_reference_code(gold, kind, src):
   P = _weights(gold, kind)
   cfg = _cfg()
-  p = kind + "_ls_"
+  p = kind + "_ls_"                       # inputs and random draws (shared by both sources)
+  q = kind + "_" + src + "_"              # expected outputs
   if kind == "seed":
     P["critic/fully_connected_1/weights"] = P["critic/fully_connected_1/weights"] * 40.0
   Pg = {k: v for k, v in P.items() if k.startswith("generator/")}
@@ -264,15 +270,15 @@ def test_train_step_losses_match_reference_code(gold, kind):
   states = T(gold, p + "states")
   ref = OT.generator_step(Pg, Pv, Pc, fake_input, states, T(gold, p + "z0"), T(gold, p + "drop_f") / 0.5,
                           T(gold, p + "drop_s") / 0.5, float(gold[p + "progress"]), cfg)
-  assert torch.equal(ref["new_states"], T(gold, p + "new_states"))
-  assert err(_img_view(kind, ref["fake_output"]), T(gold, p + "fake_output")) < 5e-6
+  assert torch.equal(ref["new_states"], T(gold, q + "new_states"))
+  assert err(_img_view(kind, ref["fake_output"]), T(gold, q + "fake_output")) < 5e-6
   for k in ("fake_logit", "old_value", "new_value", "g_loss", "v_loss"):
-    assert err(ref[k], T(gold, p + k)) < 2e-5, k
+    assert err(ref[k], T(gold, q + k)) < 2e-5, k
   checked = 0
   for k in gold.files:
-    if not k.startswith(p + "grad"):
+    if not k.startswith(q + "grad"):
       continue
-    kind_, name = k[len(p):].split("_", 1)
+    kind_, name = k[len(q):].split("_", 1)
     name = name.replace(".", "/")
     src = ref["grads_g"] if name.startswith("generator/") else ref["grads_v"] if name.startswith("rl_value/") else None
     if src is None:
@@ -289,16 +295,25 @@ def test_train_step_losses_match_reference_code(gold, kind):
   # critic step: fake batch is a fed constant (net.py:362-368)
   fake = T(gold, p + "fake_output") if kind == "seed" else ref["fake_output"]
   cr = OT.critic_step(Pc, real, fake, T(gold, p + "alpha"), cfg)
-  assert float(gold[p + "gradient_penalty"]) > 0, "fixture set-up: penalty inactive"
+  assert float(gold[q + "gradient_penalty"]) > 0, "fixture set-up: penalty inactive"
   for k in ("c_loss", "emd", "gradient_penalty", "critic_gradient_norm"):
-    assert err(cr[k], T(gold, p + k)) < 2e-5, k
+    assert err(cr[k], T(gold, q + k)) < 2e-5, k
   n = 0
   for name, g in cr["grads_c"].items():
     key = name.replace("/", ".")
-    if p + "grad_" + key in gold.files:
-      assert err(g, T(gold, p + "grad_" + key)) < 5e-5, name
+    if q + "grad_" + key in gold.files:
+      assert err(g, T(gold, q + "grad_" + key)) < 5e-5, name
     else:
-      assert err(g.reshape(-1)[::997], T(gold, p + "gradsample_" + key)) < 5e-5, name
-      assert abs(float(g.norm()) - float(gold[p + "gradnorm_" + key])) < 5e-5 * float(gold[p + "gradnorm_" + key])
+      assert err(g.reshape(-1)[::997], T(gold, q + "gradsample_" + key)) < 5e-5, name
+      assert abs(float(g.norm()) - float(gold[q + "gradnorm_" + key])) < 5e-5 * float(gold[q + "gradnorm_" + key])
     n += 1
   assert n == 12
+
+
+def test_net_graph_has_the_checkpoint_variable_counts(gold):
+  """GAN.__init__'s tf.get_collection(TRAINABLE_VARIABLES, scope) over the shim's variable store: 52 generator,
+  12 value and 12 critic variables (net.py:205-213) -- the shipped checkpoint's non-optimizer tensors."""
+  for kind in ("seed", "pre"):
+    assert gold[kind + "_ng_n_theta"].tolist() == [52, 12, 12]
+    for k in ("g_loss", "v_loss", "c_loss", "emd", "critic_gradient_norm"):
+      assert float(gold["%s_ng_%s" % (kind, k)]) == float(gold["%s_ls_%s" % (kind, k)]), k     # restated lines == net.py

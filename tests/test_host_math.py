@@ -146,3 +146,90 @@ def test_masked_apply_math(hm, fid, shape, masking):
     eg = (torch.from_numpy(got).double() - ref).abs()
     scale = ref.abs().max(dim=1, keepdim=True).values.clamp_min(1e-6)
     assert (eg <= 2e-4 * scale).all(), (fid, float((eg / scale).max()))
+
+
+# ---- the same host-compiled device math against vectors made by the REFERENCE'S OWN CODE ---------------
+# (tests/golden/reference_golden.npz sections 1-2, see tests/test_reference_golden.py): the CUDA source's
+# per-pixel functions, regressors, finalisers and mask are held to filters.py directly, without a GPU and
+# without the oracle in between.  fp32 device math vs the fixture's fp64 run: pixels 1e-5 (north_star),
+# gradients 1e-4 of scale.
+@pytest.fixture(scope="module")
+def refgold():
+  return np.load(os.path.join(HERE, "golden", "reference_golden.npz"))
+
+
+def _rel(a, b, floor):
+  a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+  s = np.abs(b).max()
+  if s == 0:
+    return float(np.abs(a).max())
+  return float((np.abs(a - b) / np.maximum(np.abs(b), floor * s)).max())
+
+
+@pytest.mark.parametrize("fid", range(10))
+def test_device_math_matches_reference_code(hm, refgold, fid):
+  p = "f%d_" % fid
+  x, lg, gy = refgold[p + "x"], refgold[p + "logits"], refgold[p + "gy"]
+  B, H, W, _ = x.shape
+  n = lg.shape[1]
+  xs = np.ascontiguousarray(x, np.float32)
+  gys = np.ascontiguousarray(gy, np.float32)
+  lgs = np.zeros((B, PS), np.float32)
+  lgs[:, :n] = lg
+  y = np.empty((B, H, W, 3), np.float32)
+  assert hm.hm_fwd(fid, _p(xs), _p(y), _p(lgs), PS, B, H * W, 1) == 0
+  want = refgold[p + "y"]
+  if fid == F.CT:
+    xt = torch.from_numpy(x)
+    lum = F.rgb2lum(xt).clamp(0, 1).numpy()
+    prm = np.abs(refgold[p + "param"]).reshape(-1, 1, 1, 1)
+    tol = 1e-5 * np.maximum(np.abs(want), 1e-4) + prm * np.abs(x) / (lum + 1e-6) * (2 * 2.0 ** -24) + 1e-7 * np.abs(want).max()
+    assert (np.abs(y - want) <= tol).all()
+  else:
+    assert _rel(y, want, 1e-2) < 1e-5
+  gx = np.empty((B, H, W, 3), np.float32)
+  gl = np.zeros((B, PS), np.float32)
+  assert hm.hm_bwd(fid, _p(xs), _p(gys), _p(gx), _p(gl), _p(lgs), PS, B, H * W, 1) == 0
+  want_gx = refgold[p + "gx"]
+  if fid == F.SP:          # away from exact channel ties (TF 1.6 has no RGBToHSV gradient; tie conventions differ)
+    px = np.minimum(x, 1.0).reshape(-1, 3)
+    keep = (px[:, 0] != px[:, 1]) & (px[:, 1] != px[:, 2]) & (px[:, 0] != px[:, 2])
+    assert _rel(gx.reshape(-1, 3)[keep], want_gx.reshape(-1, 3)[keep], 1e-3) < 1e-4
+  else:
+    assert _rel(gx, want_gx, 1e-3) < 1e-4
+  assert _rel(gl[:, :n], refgold[p + "glogits"], 1e-2) < 2e-4
+
+
+@pytest.mark.parametrize("fid", range(10))
+def test_masked_device_math_matches_reference_code(hm, refgold, fid):
+  p = "m%d_" % fid
+  n = F.NUM_PARAMS[fid]
+  x, feat, gy = refgold[p + "x"], refgold[p + "feat"], refgold[p + "gy"]
+  W1, b1, W2, b2 = (refgold[p + k] for k in ("fc1_weights", "fc1_biases", "fc2_weights", "fc2_biases"))
+  h = feat @ W1 + b1
+  h = 0.6 * h + 0.4 * np.abs(h)
+  o = h @ W2 + b2                                    # extract_parameters on the host (fp64)
+  B, H, W, _ = x.shape
+  nm = o.shape[1] - n
+  xs, gys = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(gy, np.float32)
+  lgs = np.zeros((B, PS), np.float32)
+  lgs[:, :n] = o[:, :n]
+  mls = np.zeros((B, 6), np.float32)
+  mls[:, :nm] = o[:, n:]
+  y = np.empty((B, H, W, 3), np.float32)
+  mo = np.empty((B, H, W), np.float32)
+  assert hm.hm_masked_fwd(fid, _p(xs), _p(y), _p(mo), _p(lgs), PS, _p(mls), 6, B, H, W,
+                          ctypes.c_float(float(1)), ctypes.c_float(0.3), 1, 1) == 0        # cfg.maximum_sharpness = 1
+  assert _rel(mo, refgold[p + "mask"][..., 0], 1e-3) < 1e-5
+  assert _rel(y, refgold[p + "low"], 1e-2) < 2e-5
+  if fid == F.SP:
+    return
+  gx = np.empty((B, H, W, 3), np.float32)
+  gl = np.zeros((B, PS), np.float32)
+  gm = np.zeros((B, 6), np.float32)
+  assert hm.hm_masked_bwd(fid, _p(xs), _p(gys), _p(gx), _p(gl), _p(gm), _p(lgs), PS, _p(mls), 6, B, H, W,
+                          ctypes.c_float(float(1)), ctypes.c_float(0.3), 1, 1) == 0
+  assert _rel(gx, refgold[p + "gx"], 1e-3) < 1e-4
+  go = np.concatenate([gl[:, :n], gm[:, :nm]], axis=1).astype(np.float64)
+  assert _rel(go.sum(axis=0), refgold[p + "g_fc2_biases"], 1e-2) < 3e-4
+  assert _rel(h.T @ go, refgold[p + "g_fc2_weights"], 1e-2) < 3e-4

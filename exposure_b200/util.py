@@ -12,80 +12,63 @@ STATE_DROPOUT_BEGIN = 3
 
 
 class Dict(dict):
-  """Attribute dict used for cfg and replay records (util.py:40-72)."""
+  """Attribute-style dict for cfg and replay records (same behaviour as util.py:40-72: keys are readable,
+  writable and deletable as attributes; nested dict arguments are merged in)."""
 
-  def __init__(self, *args, **kwargs):
-    super(Dict, self).__init__(*args, **kwargs)
-    for arg in args:
-      if isinstance(arg, dict):
-        for k, v in arg.items():
-          self[k] = v
-    for k, v in kwargs.items():
-      self[k] = v
+  def __init__(self, *sources, **items):
+    dict.__init__(self)
+    for src in sources:
+      self.update(src)
+    self.update(items)
 
-  def __getattr__(self, attr):
-    try:
-      return self[attr]
-    except KeyError:
-      raise AttributeError(attr)
+  def __getattr__(self, name):
+    if name in self:
+      return self[name]
+    raise AttributeError(name)
 
-  def __setattr__(self, key, value):
-    self.__setitem__(key, value)
+  def __setattr__(self, name, value):
+    self[name] = value
 
-  def __setitem__(self, key, value):
-    super(Dict, self).__setitem__(key, value)
-    self.__dict__.update({key: value})
-
-  def __delattr__(self, item):
-    self.__delitem__(item)
-
-  def __delitem__(self, key):
-    super(Dict, self).__delitem__(key)
-    del self.__dict__[key]
+  def __delattr__(self, name):
+    if name not in self:
+      raise AttributeError(name)
+    del self[name]
 
 
 def lrelu(x, leak=0.2):
-  """util.py:225-229: 0.6 x + 0.4 |x| (derivative 0.6 at 0)."""
-  f1 = 0.5 * (1 + leak)
-  f2 = 0.5 * (1 - leak)
-  return f1 * x + f2 * torch.abs(x)
+  """util.py:225-229: leaky relu written as 0.5(1+leak) x + 0.5(1-leak) |x| (derivative 0.6 at 0 for leak 0.2)."""
+  return (0.5 * (1 + leak)) * x + (0.5 * (1 - leak)) * torch.abs(x)
+
+
+_LUM_WEIGHTS = (0.27, 0.67, 0.06)          # util.py:271-274
 
 
 def rgb2lum(image):
-  """util.py:271-274."""
-  lum = 0.27 * image[:, :, :, 0] + 0.67 * image[:, :, :, 1] + 0.06 * image[:, :, :, 2]
-  return lum[:, :, :, None]
+  """Luminance of an NHWC batch, kept as a trailing singleton channel (util.py:271-274)."""
+  r, g, b = image[..., 0], image[..., 1], image[..., 2]
+  return (_LUM_WEIGHTS[0] * r + _LUM_WEIGHTS[1] * g + _LUM_WEIGHTS[2] * b).unsqueeze(-1)
 
 
 def tanh01(x):
-  return torch.tanh(x) * 0.5 + 0.5
+  return 0.5 * torch.tanh(x) + 0.5
 
 
 def tanh_range(l, r, initial=None):
-  """util.py:281-294."""
-
-  def get_activation(left, right, initial):
-
-    def activation(x):
-      if initial is not None:
-        bias = math.atanh(2 * (initial - left) / (right - left) - 1)
-      else:
-        bias = 0
-      return tanh01(x + bias) * (right - left) + left
-
-    return activation
-
-  return get_activation(l, r, initial)
+  """util.py:281-294: x -> l + (r - l) tanh01(x + bias), with bias chosen so that x = 0 maps to `initial`."""
+  span = r - l
+  bias = 0 if initial is None else math.atanh(2 * (initial - l) / span - 1)
+  return lambda x: tanh01(x + bias) * span + l
 
 
 def lerp(a, b, l):
   """util.py:307-308."""
-  return (1 - l) * a + l * b
+  return a * (1 - l) + b * l
 
 
 def enrich_image_input(cfg, net, states):
   """util.py:31-36: tile the state vector over the image and concatenate as channels."""
-  if cfg.img_include_states:
-    B, H, W, _ = net.shape
-    net = torch.cat([net, states[:, None, None, :].expand(B, H, W, states.shape[1])], dim=3)
-  return net
+  if not cfg.img_include_states:
+    return net
+  B, H, W, _ = net.shape
+  tiled = states[:, None, None, :].expand(B, H, W, states.shape[1])
+  return torch.cat([net, tiled], dim=3)

@@ -138,3 +138,28 @@ def test_chain_grad_matches_autograd_end_to_end():
   assert (gimg - grads[0]).abs().max() <= 1e-5 * grads[0].abs().max()
   for a, b in zip(glg, grads[1:]):
     assert (a - b).abs().max() <= 1e-5 * b.abs().max() + 1e-12
+
+
+def test_hsv_functors_agree_with_an_independent_implementation():
+  """The RGB<->HSV functors are the one primitive restated from TF's kernel source
+  (tensorflow/core/kernels/colorspace_op.h) rather than from the reference repo.  Python's colorsys is an
+  independent implementation of the same hexcone model: 2000 random pixels + the tie / grey / black cases."""
+  import colorsys
+  g = torch.Generator().manual_seed(77)
+  px = torch.rand(2000, 3, generator=g, dtype=torch.float64)
+  px[0] = 0.0
+  px[1] = 0.37
+  px[2] = torch.tensor([0.5, 0.5, 0.2])
+  px[3] = torch.tensor([0.2, 0.7, 0.7])
+  px[4] = torch.tensor([0.9, 0.1, 0.9])
+  h, s, v = F.rgb_to_hsv(px.reshape(1, 1, -1, 3))
+  h, s, v = h.reshape(-1), s.reshape(-1), v.reshape(-1)
+  back = F.hsv_to_rgb(h.reshape(1, 1, -1, 1), s.reshape(1, 1, -1, 1), v.reshape(1, 1, -1, 1)).reshape(-1, 3)
+  for i in range(px.shape[0]):
+    r, gg, b = (float(t) for t in px[i])
+    hh, ss, vv = colorsys.rgb_to_hsv(r, gg, b)
+    assert abs(float(s[i]) - ss) < 1e-12 and abs(float(v[i]) - vv) < 1e-12
+    dh = abs(float(h[i]) - hh)
+    assert min(dh, 1 - dh) < 1e-7, (i, float(h[i]), hh)     # float32(1/6, 2/6, 4/6) constants, like TF's float kernel; hue is circular
+    rr, g2, bb = colorsys.hsv_to_rgb(float(h[i]), float(s[i]), float(v[i]))
+    assert max(abs(float(back[i, 0]) - rr), abs(float(back[i, 1]) - g2), abs(float(back[i, 2]) - bb)) < 1e-6

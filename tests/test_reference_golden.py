@@ -317,3 +317,17 @@ def test_net_graph_has_the_checkpoint_variable_counts(gold):
     assert gold[kind + "_ng_n_theta"].tolist() == [52, 12, 12]
     for k in ("g_loss", "v_loss", "c_loss", "emd", "critic_gradient_norm"):
       assert float(gold["%s_ng_%s" % (kind, k)]) == float(gold["%s_ls_%s" % (kind, k)]), k     # restated lines == net.py
+
+
+def test_pretrained_rollout_behaves_like_the_paper(gold):
+  """Layout sanity of the whole stack (HWIO kernels, NHWC flatten, variable scopes, filter order): the shipped
+  weights, run through the reference's own agent_generator, retouch the dark RAW thumbnail of A.tif the way
+  the paper and SURVEY Appendix B describe -- exposure first (confidently), then saturation / gamma / tone /
+  contrast -- and lift its mean from 0.04 to > 0.3.  A transposed kernel or a permuted flatten gives noise."""
+  ids = [int(gold["pre_ag_argmax_s%d_id0" % s]) for s in range(5)]
+  assert ids[0] == OF.E and float(gold["pre_ag_argmax_s0_pdf0"][OF.E]) > 0.5
+  assert len(set(ids)) == 5                                     # filter_usage_penalty: no filter is used twice
+  assert set(ids) <= {OF.E, OF.G, OF.SP, OF.T, OF.CT, OF.C, OF.W, OF.BW}
+  m0 = float(gold["thumbs"][0].mean())
+  m5 = float(gold["pre_ag_argmax_s4_out"][0].mean())
+  assert m0 < 0.05 and m5 > 0.3

@@ -126,6 +126,8 @@ int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstr
  * chain of BASELINE configs[1] / [4]); the agent's step-by-step rollout keeps the per-step entry points
  * because each action depends on the previous step's output (agent.py:41-125).  No masking.
  * params / gparams: [S][B][pstride], ids int32 [S][B] (id -1 = black, zero gradients), S <= 8.
+ * Of a gparams row only the first n = exp_num_filter_params(id) entries are written (all
+ * EXP_MAX_FILTER_PARAMS for id -1): hand in a zero-filled buffer if the ids change between calls.
  * workspace: exp_filter_chain_fwd_bwd_workspace_bytes(); same zero-once / self-cleaning rule as
  * exp_filter_bwd, and the same buffer may be shared with it. */
 size_t exp_filter_chain_fwd_bwd_workspace_bytes(int S, int B, int H, int W);

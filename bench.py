@@ -2,22 +2,28 @@
 """bench.py -- throughput of the Exposure hot path on B200 (driver contract: one JSON line).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
-                  [--workload chain8] [--batch B] [--size S]
+                  [--workload train|chain8|eval] [--batch B] [--size S]
 
-Workload `chain8` (default; BASELINE.json configs[1]): the 8-filter chain
-E,G,W,S+,T,Ct,BW,C applied in sequence to a batch of B x S x S x 3 fp32 linear-RGB images,
-forward + backward (image gradient and per-image parameter gradients), B=64, S=512 per GPU.
-A "step" is one such pass over one batch.  Multi-GPU: the batch shards by image, one
-process per GPU, no data-path collective (weak scaling: 64 images per GPU).
+Workload `train` (default; the configuration BASELINE.json's metric is quoted on, configs[3]): one
+iteration of GAN.train (net.py:307-370) = 1 generator+value step + 5 WGAN-GP critic steps on per-GPU
+batches of 64 x 64 x 64 x 3 fp32 images drawn from the device-resident replay memory, data parallel:
+one process per GPU, ONE NCCL all-reduce per optimizer step (weak scaling: 64 images per GPU).
+A "step" is one such iteration.  The same run also measures the filter chain the north star's roofline
+target is stated on (8-filter chain fwd+bwd at 256 x 512 x 512 x 3, as ONE fused kernel and as 16 per-step
+kernels) and reports it as `roofline`; the conv / FC tensor-core family of the train step is `tensor`.
+
+Workload `chain8` (configs[1] / configs[4]): the 8-filter chain E,G,W,S+,T,Ct,BW,C forward + backward on
+B x H x W x 3 batches, sharded by image (no data-path collective).  Workload `eval` (configs[2]):
+cfg.test_steps policy steps on 64x64 thumbnails + the selected filters applied in one fused pass.
 
 Reported:
   value     images/s, whole job, inputs resident in HBM (CUDA events, max over ranks)
-  e2e       images/s through the public API with HOST (pinned) buffers: H2D of the batch and
-            D2H of the filtered batch + parameter gradients inside the timed region
-  roofline  the dominant kernel's achieved algorithmic GB/s vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU restatement of the reference TF graph (oracle/, torch fp32,
-            op by op + autograd) on a bounded sample, all host threads
-`--impl reference` times only that CPU restatement (the TF-1.6 reference cannot run here).
+  e2e       images/s through the public API with HOST (pinned) buffers: every input of the step copied
+            H2D and every result copied D2H inside the timed region
+  roofline  the filter-chain kernels' achieved algorithmic GB/s vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU restatement of the reference TF graph (oracle/, torch fp32, op by op + autograd)
+            on the FULL batch of the same workload, all host threads
+`--impl reference` times only that CPU restatement (the TF-1.6 reference cannot run here), same config.
 """
 import argparse
 import json
@@ -38,10 +44,10 @@ FWD_B, BWD_B = 24, 36                        # algorithmic bytes / pixel / step 
 def parse_args():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=400)
+  ap.add_argument("--steps", type=int, default=0, help="timed steps (default: 50 for train, 400 for chain8, 50 for eval)")
   ap.add_argument("--warmup", type=int, default=10)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
-  ap.add_argument("--workload", default="chain8", choices=["chain8", "train", "eval"])
+  ap.add_argument("--workload", default="train", choices=["train", "chain8", "eval"])
   ap.add_argument("--batch", type=int, default=64, help="images per GPU")
   ap.add_argument("--size", type=int, default=512)
   ap.add_argument("--height", type=int, default=0, help="chain8: image height (default --size); 2160 for the 4K config")
@@ -53,7 +59,13 @@ def parse_args():
   ap.add_argument("--e2e-chunks", type=int, default=0, help="chain8 e2e leg: sub-batches in flight (0 = 8 if it divides the batch)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-graphs", action="store_true", help="train workload: launch kernels eagerly instead of CUDA graphs")
-  return ap.parse_args()
+  ap.add_argument("--roofline-batch", type=int, default=256,
+                  help="train workload: batch of the 512x512 filter chain measured for `roofline` (0 = skip)")
+  ap.add_argument("--cpu-batch", type=int, default=0, help="images in the CPU arm's step (0 = the full --batch)")
+  args = ap.parse_args()
+  if args.steps <= 0:
+    args.steps = {"train": 50, "chain8": 400, "eval": 50}[args.workload]
+  return args
 
 
 def host_threads():
@@ -93,14 +105,22 @@ def cpu_chain_step(x, logits, gout):
   return y
 
 
-def cpu_baseline(size, budget_s=20.0, batch=2):
-  import torch
+def _cpu_chain_inputs(args):
   from oracle import filters as F
+  import torch
+  B = args.cpu_batch or args.batch
+  H, W = args.height or args.size, args.width or args.size
+  x = F.synth_images(B, H, W, seed=1234, stress=False)
+  logits = [F.synth_logits(f, B) for f in CHAIN_IDS]
+  return B, H, W, x, logits, torch.ones_like(x)
+
+
+def cpu_baseline(args, budget_s=25.0):
+  """chain8 workload: the CPU restatement on the FULL batch of the same step (bounded by `budget_s`)."""
+  import torch
   cores = host_threads()
   torch.set_num_threads(cores)
-  x = F.synth_images(batch, size, size, seed=1234, stress=False)
-  logits = [F.synth_logits(f, batch) for f in CHAIN_IDS]
-  gout = torch.ones_like(x)
+  B, H, W, x, logits, gout = _cpu_chain_inputs(args)
   cpu_chain_step(x, logits, gout)                      # warm-up
   times = []
   t_end = time.time() + budget_s
@@ -110,63 +130,51 @@ def cpu_baseline(size, budget_s=20.0, batch=2):
     times.append(time.time() - t0)
   med = statistics.median(times)
   return {
-      "value": batch / med, "unit": "images/s", "cores": cores, "kind": "port",
-      "sample": "chain8 fwd+bwd on %dx%dx%dx3 fp32, median of %d reps (min %.3fs); CPU restatement of the "
+      "value": B / med, "unit": "images/s", "cores": cores, "kind": "port",
+      "sample": "chain8 fwd+bwd on the full %dx%dx%dx3 fp32 batch, median of %d reps (min %.3fs); CPU restatement of the "
                 "reference TF graph (oracle/filters.py, torch-CPU op-by-op + autograd), not TensorFlow" %
-                (batch, size, size, len(times), min(times)),
+                (B, H, W, len(times), min(times)),
   }
 
 
 def run_reference(args):
-  """--impl reference: the reference's CPU path (oracle port) on the host cores; rank 0 only."""
+  """--impl reference: the reference's CPU path (oracle port) on the host cores, on the SAME config as the
+  native arm (full batch per step); rank 0 only."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
   import torch
-  from oracle import filters as F
   if args.workload == "train":
-    iteration, sb, cores = _cpu_train_iteration(args.batch)
-    for _ in range(max(1, min(args.warmup, 2))):
-      iteration()
-    t0 = time.time()
-    for _ in range(args.steps):
-      iteration()
-    dt = time.time() - t0
-    val = sb * args.steps / dt
-    sample = ("each step = 1 generator+value step + 5 critic steps on a bounded sample of %d of the %d images; CPU "
-              "restatement of the reference TF graph (oracle/train_step.py port, torch-CPU autograd), %d threads" %
-              (sb, args.batch, cores))
-    print(json.dumps({
-        "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": train_config(args),
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
-    return
-  cores = host_threads()
-  torch.set_num_threads(cores)
-  sample_b = 2
-  x = F.synth_images(sample_b, args.size, args.size, seed=1234, stress=False)
-  logits = [F.synth_logits(f, sample_b) for f in CHAIN_IDS]
-  gout = torch.ones_like(x)
+    iteration, sb, cores = _cpu_train_iteration(args.cpu_batch or args.batch)
+    cfgd = train_config(args)
+    what = "1 generator+value step + 5 critic steps on %d images of 64x64x3 (oracle/train_step.py port, torch-CPU autograd)" % sb
+  elif args.workload == "eval":
+    iteration, sb, cores = _cpu_eval_iteration(args)
+    cfgd = eval_config(args)
+    what = "%d policy steps + filter apply on %d images (oracle port, torch-CPU)" % (EVAL_STEPS, sb)
+  else:
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    sb, H, W, x, logits, gout = _cpu_chain_inputs(args)
+    iteration = lambda: cpu_chain_step(x, logits, gout)
+    cfgd = workload_config(args)
+    what = "chain8 fwd+bwd on %d images of %dx%dx3 fp32 (oracle port, torch-CPU op-by-op + autograd)" % (sb, H, W)
   for _ in range(max(1, min(args.warmup, 2))):
-    cpu_chain_step(x, logits, gout)
+    iteration()
   t0 = time.time()
   for _ in range(args.steps):
-    cpu_chain_step(x, logits, gout)
+    iteration()
   dt = time.time() - t0
-  val = sample_b * args.steps / dt
-  sample = ("each step = chain8 fwd+bwd on a bounded sample of %d of the %d images (%dx%dx3 fp32); CPU "
-            "restatement of the reference TF graph (oracle port), torch-CPU, %d threads" %
-            (sample_b, args.batch, args.size, args.size, cores))
+  val = sb * args.steps / dt
+  full = sb == args.batch
+  sample = ("each step = %s%s; CPU restatement of the reference TF graph, not TensorFlow (TF 1.6 cannot be installed here), "
+            "%d threads" % (what, " = the full per-GPU batch of the native arm" if full else
+                            " (a bounded sample of the %d-image batch)" % args.batch, cores))
   print(json.dumps({
       "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s", "n_gpus": args.gpus,
       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": workload_config(args),
+      "config": cfgd,
       "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
       "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
@@ -178,6 +186,7 @@ def workload_config(args):
       "workload": "chain8: 8-filter chain E,G,W,S+,T,Ct,BW,C fwd+bwd (BASELINE.json configs[1])",
       "batch_per_gpu": args.batch, "height": args.height or args.size, "width": args.width or args.size, "channels": 3,
       "filters": "E,G,W,S+,T,Ct,BW,C", "parallelism": "dp%d (batch sharded by image, no data-path collective)" % args.gpus,
+      "chain_impl": args.chain_impl,
       "l2_policy": "working set (%s x %.0f MB) exceeds the 126 MB L2; no flush needed"
                    % ("x, dL/dy, y, dL/dx: 4" if args.chain_impl == "fused" else "9 activations + 2 gradient buffers: 11",
                       args.batch * (args.height or args.size) * (args.width or args.size) * 12 / 1e6),
@@ -247,11 +256,203 @@ class ClockSampler:
             "window": window}
 
 
+def _traffic(kernel, B, H, W):
+  """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this same command
+  (profiles/filter_traffic.json, written by profiles/summarize.py traffic); only valid for the shape it was
+  captured on."""
+  try:
+    tj = json.load(open(os.path.join(ROOT, "profiles", "filter_traffic.json")))
+    for ent in tj.get("captures", [tj]):
+      if ent.get("config") == "chain8 %dx%dx%dx3 fp32" % (B, H, W) and kernel in ent["kernels"]:
+        return (ent["kernels"][kernel]["traffic_bytes"],
+                "profiles/filter_traffic.json (%s): dram__bytes_read.sum + dram__bytes_write.sum of one launch" % ent["source"])
+  except (OSError, ValueError, KeyError):
+    pass
+  return None, None
+
+
+def synth_chain_inputs(dev, B, H, W, rank, chain):
+  """Synthetic linear-RGB batch generated on the device into the chain's input buffer."""
+  import torch
+  from exposure_b200 import ops
+  g = torch.Generator(device=dev).manual_seed(1234 + rank)
+  x0 = chain.input_buffer((B, H, W, 3), dev)
+  nb = max(1, min(B, 32))                             # generate in slices: bounded temporaries at batch 256
+  for b0 in range(0, B, nb):
+    sl = slice(b0, min(B, b0 + nb))
+    n = sl.stop - sl.start
+    v = torch.exp(torch.randn(n, H, W, 3, device=dev, generator=g) - 3.2).clamp_(0, 4)
+    stress = torch.rand(n, H, W, 3, device=dev, generator=g)
+    x0[sl].copy_(torch.where(stress < 0.01, 1 + 3 * torch.rand(n, H, W, 3, device=dev, generator=g), v))
+    del v, stress
+  gl = torch.Generator().manual_seed(4321)
+  logits = [torch.randn(B, ops.NUM_PARAMS[f], generator=gl).to(dev) for f in CHAIN_IDS]
+  gout = torch.empty(B, H, W, 3, device=dev)
+  for b0 in range(0, B, nb):
+    sl = slice(b0, min(B, b0 + nb))
+    gout[sl].copy_(torch.randn(sl.stop - sl.start, H, W, 3, device=dev, generator=g))
+  return x0, logits, gout
+
+
+def measure_chain(dev, B, H, W, steps, warmup, rank=0, world=1, variant=0, fused_on=True, graphs=True, barrier=None):
+  """The 8-filter chain fwd+bwd on a resident B x H x W x 3 batch: (1) as 2N per-step kernels -- eager with
+  CUDA events around every launch (per-kernel roofline), then the same steps replayed from one CUDA graph;
+  (2) as ONE fused kernel per step.  Returns a dict with both timings and a FLAT roofline object."""
+  import torch
+  import torch.distributed as dist
+  from exposure_b200 import ops
+  from exposure_b200.chain import FilterChain, FusedFilterChain
+
+  if barrier is None:
+    def barrier():
+      torch.cuda.synchronize()
+  chain = FilterChain(CHAIN_IDS, variant=variant)
+  x0, logits, gout = synth_chain_inputs(dev, B, H, W, rank, chain)
+
+  def step():
+    chain.forward_resident(logits)
+    return chain.backward(gout)
+
+  def maxed(ms):
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  for _ in range(max(warmup, 3)):
+    step()
+  barrier()
+  # ---- per-step kernels, eager + instrumented --------------------------------------------
+  ops.event_log = []
+  l0 = ops.launch_count
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  wall0 = time.time()
+  e0.record()
+  for _ in range(steps):
+    step()
+  e1.record()
+  barrier()
+  wall1 = time.time()
+  eager_ms = e0.elapsed_time(e1)
+  ps_ms = eager_ms
+  ps_launches = ops.launch_count - l0
+  log, ops.event_log = ops.event_log, None
+  graph_info = None
+  if graphs:
+    chain.capture(logits, gout)
+    for _ in range(3):
+      chain.replay()
+    barrier()
+    wall0 = time.time()
+    e0.record()
+    for _ in range(steps):
+      chain.replay()
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    ps_ms = e0.elapsed_time(e1)
+    ps_launches = steps * chain.graph_launches
+    graph_info = {"nodes_per_step": chain.graph_launches, "eager_ms_per_step": eager_ms / steps}
+  ps_ms = maxed(ps_ms)
+  per = {}
+  for name, nbytes, a, b in log:
+    d = per.setdefault(name, {"ms": 0.0, "bytes": 0, "n": 0})
+    d["ms"] += a.elapsed_time(b); d["bytes"] += nbytes; d["n"] += 1
+  peak, peak_src = peaks()
+  kernels = []
+  for name, d in sorted(per.items(), key=lambda kv: -kv[1]["ms"]):
+    kernels.append({"kernel": name, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
+                    "algorithmic_bytes_per_launch": d["bytes"] // d["n"],
+                    "achieved_gbs": d["bytes"] / d["ms"] / 1e6, "frac": d["bytes"] / d["ms"] / 1e6 / peak})
+  tot_ms = sum(d["ms"] for d in per.values())
+  tot_bytes = sum(d["bytes"] for d in per.values())
+  algo = B * H * W * (FWD_B + BWD_B) * len(CHAIN_IDS)        # SURVEY 8d: 60 B/pixel/step, N steps
+  worst = min(kernels, key=lambda k: k["frac"])
+  dom = kernels[0]
+  dtraffic, dsrc = _traffic(dom["kernel"], B, H, W)
+  out = {"B": B, "H": H, "W": W, "peak": peak, "peak_source": peak_src, "wall": (wall0, wall1),
+         "per_step": {"value_images_s": world * B * steps / (ps_ms / 1e3), "ms_per_step": ps_ms / steps,
+                      "gpu_launches": ps_launches, "kernels": kernels, "cuda_graph": graph_info,
+                      "eager_ms_total": eager_ms}}
+  flat = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+          "workload": "chain8 fwd+bwd %dx%dx%dx3 fp32 (E,G,W,S+,T,Ct,BW,C), resident in HBM; working set exceeds the 126 MB L2" % (B, H, W),
+          "algorithmic_bytes_per_step": algo,
+          # the 2N per-step kernels (the HBM-bound path the agent's rollout uses)
+          "per_step_ms_per_step": ps_ms / steps,
+          "per_step_achieved": algo / (ps_ms / steps) / 1e6, "per_step_frac": algo / (ps_ms / steps) / 1e6 / peak,
+          "per_step_kernel_sum_achieved": tot_bytes / tot_ms / 1e6, "per_step_kernel_sum_frac": tot_bytes / tot_ms / 1e6 / peak,
+          "per_step_worst_kernel": worst["kernel"], "per_step_worst_kernel_frac": worst["frac"],
+          "per_step_best_kernel_frac": max(k["frac"] for k in kernels),
+          "per_step_dominant_kernel": dom["kernel"], "per_step_dominant_kernel_frac": dom["frac"],
+          "per_step_dominant_kernel_traffic": dtraffic,
+          "per_step_launches_per_step": 2 * len(CHAIN_IDS),
+          "per_step_note": "kernel fractions: CUDA events around every launch of the eager K-step loop; per_step_frac: the "
+                           "same K steps replayed from one CUDA graph, 60 B/pixel/step x 8 steps over the step time"}
+  for k in kernels:
+    flat["k_" + k["kernel"] + "_frac"] = round(k["frac"], 4)
+  out["flat"] = flat
+  out["chain"], out["x0"], out["logits"], out["gout"] = chain, x0, logits, gout
+  if not fused_on:
+    flat.update({"kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "frac": dom["frac"], "traffic": dtraffic,
+                 "traffic_source": dsrc, "share_of_step": dom["avg_ms"] * dom["launches"] / eager_ms})
+    return out
+
+  # ---- the whole chain as ONE kernel per step (exp_filter_chain_fwd_bwd) ----------------------
+  y_steps = chain._acts[-1]
+  fz = FusedFilterChain(CHAIN_IDS, B, dev)
+  fz.set_logits(logits)
+  fy, fgx = torch.empty_like(x0), torch.empty_like(x0)
+  for _ in range(max(warmup, 3)):
+    fz.forward_backward(x0, gout, y_out=fy, gx_out=fgx)
+  barrier()
+  # same inputs, same outputs: largest relative deviation from the per-step kernels' result
+  agree = 0.0
+  nb = max(1, min(B, 32))
+  for b0 in range(0, B, nb):
+    a, r = fy[b0:b0 + nb], y_steps[b0:b0 + nb]
+    agree = max(agree, float(((a - r).abs() / r.abs().clamp_min(1e-3)).max()))
+  ops.event_log = []
+  for _ in range(min(steps, 50)):
+    fz.forward_backward(x0, gout, y_out=fy, gx_out=fgx)
+  barrier()
+  flog, ops.event_log = ops.event_log, None
+  f_launch_ms = sum(a.elapsed_time(b) for _, _, a, b in flog) / len(flog)
+  l0 = ops.launch_count
+  barrier()
+  wall0 = time.time()
+  e0.record()
+  for _ in range(steps):
+    fz.forward_backward(x0, gout, y_out=fy, gx_out=fgx)
+  e1.record()
+  barrier()
+  wall1 = time.time()
+  f_ms = maxed(e0.elapsed_time(e1))
+  actual = B * H * W * 48                                   # what the fused kernel moves: x, gy in; y, gx out
+  ftraffic, fsrc = _traffic("filter_chain_fwd_bwd", B, H, W)
+  flat.update({"kernel": "filter_chain_fwd_bwd (whole chain forward+backward, ONE launch)",
+               "achieved": algo / f_launch_ms / 1e6, "frac": algo / f_launch_ms / 1e6 / peak,
+               "traffic": ftraffic, "traffic_source": fsrc,
+               "share_of_step": f_launch_ms * steps / f_ms, "algorithmic_bytes_per_launch": algo,
+               "launch_ms": f_launch_ms, "fused_ms_per_step": f_ms / steps,
+               "hbm_bytes_moved_per_launch": actual, "hbm_frac_of_bytes_moved": actual / f_launch_ms / 1e6 / peak,
+               "fused_vs_per_step_max_rel_dev": agree,
+               "note": "`achieved` uses SURVEY 8d's definition of the path's algorithmic bytes (60 B/pixel/step x N steps), as it "
+                       "prescribes for the chain-fused variant; the kernel keeps the N-1 intermediate images on the SM and moves "
+                       "only 48 B/pixel for the whole chain, so frac > 1 against the per-step definition: it is instruction-issue "
+                       "bound, not HBM bound (hbm_frac_of_bytes_moved; ncu summary under profiles/).  per_step_* = the same "
+                       "chain as 2N per-step kernels (the HBM-bound path the agent's rollout uses), measured in the same run."})
+  out["fused"] = {"value_images_s": world * B * steps / (f_ms / 1e3), "ms_per_step": f_ms / steps,
+                  "gpu_launches": ops.launch_count - l0, "launch_ms": f_launch_ms}
+  out["wall"] = (wall0, wall1)
+  out["fz"], out["fy"], out["fgx"] = fz, fy, fgx
+  return out
+
+
 def run_native(args):
   import torch
   import torch.distributed as dist
   from exposure_b200 import ops
-  from exposure_b200.chain import FilterChain
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
@@ -265,22 +466,6 @@ def run_native(args):
   B, S = args.batch, args.size
   H, W = args.height or S, args.width or S
 
-  # synthetic linear-RGB batch, generated on the device for the resident leg
-  g = torch.Generator(device=dev).manual_seed(1234 + rank)
-  chain = FilterChain(CHAIN_IDS, variant=args.variant)
-  x0 = chain.input_buffer((B, H, W, 3), dev)
-  x0.copy_(torch.exp(torch.randn(B, H, W, 3, device=dev, generator=g) - 3.2).clamp_(0, 4))
-  stress = torch.rand(B, H, W, 3, device=dev, generator=g)
-  x0.copy_(torch.where(stress < 0.01, 1 + 3 * torch.rand(B, H, W, 3, device=dev, generator=g), x0))
-  del stress
-  gl = torch.Generator().manual_seed(4321)
-  logits = [torch.randn(B, ops.NUM_PARAMS[f], generator=gl).to(dev) for f in CHAIN_IDS]
-  gout = torch.randn(B, H, W, 3, device=dev, generator=g)
-
-  def step():
-    chain.forward_resident(logits)
-    return chain.backward(gout)
-
   def barrier():
     if world > 1:
       dist.barrier()
@@ -289,170 +474,36 @@ def run_native(args):
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
-  for _ in range(max(args.warmup, 3)):
-    step()
-  barrier()
-
-  # ---- timed region (device resident) -----------------------------------------------------
-  ops.event_log = []
-  l0 = ops.launch_count
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  barrier()
-  wall0 = time.time()
-  e0.record()
-  for _ in range(args.steps):
-    step()
-  e1.record()
-  barrier()
-  wall1 = time.time()
-  elapsed_ms = e0.elapsed_time(e1)
-  launches = ops.launch_count - l0
-  log, ops.event_log = ops.event_log, None
-  eager_ms = elapsed_ms
-  graph_info = None
-  if not args.no_graphs:
-    # the same K steps replayed from ONE CUDA graph (2N kernel nodes): this is the timed region
-    # `value` reports; the eager loop above is the instrumented pass for the per-kernel table
-    chain.capture(logits, gout)
-    for _ in range(3):
-      chain.replay()
-    barrier()
-    wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-      chain.replay()
-    e1.record()
-    barrier()
-    wall1 = time.time()
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = args.steps * chain.graph_launches
-    graph_info = {"nodes_per_step": chain.graph_launches, "eager_ms_per_step": eager_ms / args.steps}
-  t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-  if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  elapsed_ms = float(t.item())
-  value = world * B * args.steps / (elapsed_ms / 1e3)
-
-  # ---- per-kernel roofline from the events recorded inside the (eager) timed loop -----------
-  per = {}
-  for name, nbytes, a, b in log:
-    d = per.setdefault(name, {"ms": 0.0, "bytes": 0, "n": 0})
-    d["ms"] += a.elapsed_time(b); d["bytes"] += nbytes; d["n"] += 1
-  peak, peak_src = peaks()
-  kernels = []
-  for name, d in sorted(per.items(), key=lambda kv: -kv[1]["ms"]):
-    kernels.append({"kernel": name, "launches": d["n"], "avg_ms": d["ms"] / d["n"],
-                    "algorithmic_bytes_per_launch": d["bytes"] // d["n"],
-                    "achieved_gbs": d["bytes"] / d["ms"] / 1e6, "frac": d["bytes"] / d["ms"] / 1e6 / peak})
-  tot_ms = sum(d["ms"] for d in per.values())
-  tot_bytes = sum(d["bytes"] for d in per.values())
-  dom = kernels[0]
-  # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this
-  # same command (profiles/filter_traffic.json, written by profiles/summarize.py traffic); only valid
-  # for the shape it was captured on
-  traffic, traffic_src = None, None
-  try:
-    tj = json.load(open(os.path.join(ROOT, "profiles", "filter_traffic.json")))
-    if tj.get("config") == "chain8 %dx%dx%dx3 fp32" % (B, H, W) and dom["kernel"] in tj["kernels"]:
-      traffic = tj["kernels"][dom["kernel"]]["traffic_bytes"]
-      traffic_src = "profiles/filter_traffic.json (%s): dram__bytes_read.sum + dram__bytes_write.sum of one launch" % tj["source"]
-  except (OSError, ValueError, KeyError):
-    pass
-  roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
-              "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src,
-              "peak_source": peak_src,
-              "share_of_step": dom["avg_ms"] * dom["launches"] / eager_ms if eager_ms else None,
-              "chain": {"achieved": tot_bytes / tot_ms / 1e6, "frac": tot_bytes / tot_ms / 1e6 / peak,
-                        "algorithmic_bytes_per_step": B * H * W * (FWD_B + BWD_B) * len(CHAIN_IDS),
-                        "kernel_ms_per_step": tot_ms / args.steps,
-                        "step_frac": B * H * W * (FWD_B + BWD_B) * len(CHAIN_IDS) / (elapsed_ms / args.steps) / 1e6 / peak},
-              "note": "kernel durations: CUDA events around every launch of the eager K-step loop; `value` and "
-                      "chain.step_frac: the same K steps replayed from one CUDA graph" if graph_info else
-                      "kernel durations: CUDA events around every launch inside the timed region",
-              "cuda_graph": graph_info,
-              "kernels": kernels}
-
-  # ---- the whole chain as ONE kernel per step (exp_filter_chain_fwd_bwd) ----------------------
   fused_on = args.chain_impl == "fused"
-  if fused_on:
-    from exposure_b200.chain import FusedFilterChain
-    per_step = {"value": value, "ms_per_step": elapsed_ms / args.steps, "gpu_launches": launches, "roofline": roofline}
-    y_steps = chain._acts[-1]
-    fz = FusedFilterChain(CHAIN_IDS, B, dev)
-    fz.set_logits(logits)
-    fy, fgx = torch.empty_like(x0), torch.empty_like(x0)
-    for _ in range(max(args.warmup, 3)):
-      fz.forward_backward(x0, gout, y_out=fy, gx_out=fgx)
-    barrier()
-    # same inputs, same outputs: largest relative deviation from the per-step kernels' result
-    agree = float(((fy - y_steps).abs() / y_steps.abs().clamp_min(1e-3)).max())
-    ops.event_log = []
-    for _ in range(min(args.steps, 50)):
-      fz.forward_backward(x0, gout, y_out=fy, gx_out=fgx)
-    barrier()
-    flog, ops.event_log = ops.event_log, None
-    f_launch_ms = sum(a.elapsed_time(b) for _, _, a, b in flog) / len(flog)
-    l0 = ops.launch_count
-    barrier()
-    wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-      fz.forward_backward(x0, gout, y_out=fy, gx_out=fgx)
-    e1.record()
-    barrier()
-    wall1 = time.time()
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = ops.launch_count - l0
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-      dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms / 1e3)
-    algo = B * H * W * (FWD_B + BWD_B) * len(CHAIN_IDS)       # 60 B/pixel/step, N steps
-    actual = B * H * W * 48                                   # what the fused kernel moves: x, gy in; y, gx out
-    ftraffic, fsrc = None, None
-    try:
-      tj = json.load(open(os.path.join(ROOT, "profiles", "filter_traffic.json")))
-      if tj.get("config") == "chain8 %dx%dx%dx3 fp32" % (B, H, W) and "filter_chain_fwd_bwd" in tj["kernels"]:
-        ftraffic = tj["kernels"]["filter_chain_fwd_bwd"]["traffic_bytes"]
-        fsrc = "profiles/filter_traffic.json (%s): dram__bytes_read.sum + dram__bytes_write.sum of one launch" % tj["source"]
-    except (OSError, ValueError, KeyError):
-      pass
-    roofline = {"bound": "hbm", "kernel": "filter_chain_fwd_bwd", "achieved": algo / f_launch_ms / 1e6, "peak": peak,
-                "unit": "GB/s", "frac": algo / f_launch_ms / 1e6 / peak, "traffic": ftraffic, "traffic_source": fsrc,
-                "peak_source": peak_src, "share_of_step": f_launch_ms * args.steps / elapsed_ms,
-                "algorithmic_bytes_per_launch": algo, "launch_ms": f_launch_ms,
-                "hbm_bytes_moved_per_launch": actual, "hbm_frac_of_bytes_moved": actual / f_launch_ms / 1e6 / peak,
-                "fused_vs_per_step_max_rel_dev": agree,
-                "note": "`achieved` uses SURVEY 8d's definition of the path's algorithmic bytes (60 B/pixel/step x N steps), "
-                        "as it prescribes for the chain-fused variant; the kernel keeps the N-1 intermediate images in "
-                        "shared memory and moves only 48 B/pixel for the whole chain, so frac > 1 against the per-step "
-                        "definition and the kernel is instruction-issue bound, not HBM bound (hbm_frac_of_bytes_moved; "
-                        "ncu summary under profiles/).  per_step = the same chain as 2N per-step kernels (the HBM-bound "
-                        "path the agent's rollout uses), measured in the same run.",
-                "per_step": per_step}
+  m = measure_chain(dev, B, H, W, args.steps, args.warmup, rank, world, args.variant, fused_on, not args.no_graphs, barrier)
+  sel = m["fused"] if fused_on else m["per_step"]
+  value, ms_per_step, launches = sel["value_images_s"], sel["ms_per_step"], sel["gpu_launches"]
+  roofline = dict(m["flat"], per_step_kernels=m["per_step"]["kernels"], cuda_graph=m["per_step"]["cuda_graph"])
+  wall0, wall1 = m["wall"]
+  x0, logits, gout = m["x0"], m["logits"], m["gout"]
 
-  # ---- end-to-end leg: host (pinned) buffers through the public API ------------------------
-  hx = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
-  hx.copy_(x0.cpu())
-  hy = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
-  hg = [torch.empty(B, ops.NUM_PARAMS[f]).pin_memory() for f in CHAIN_IDS]
-  # public host-buffer API: H2D of the batch, chain fwd+bwd, D2H of the filtered batch (net.py:330
-  # fetches fake_output every step) and of the parameter gradients, software-pipelined over
-  # sub-batches on three streams (exposure_b200/chain.py HostPipelinedChain)
+  # ---- end-to-end leg: EVERY input from pinned host memory, EVERY output back ------------------
+  # H2D: the batch x and the upstream gradient dL/dy; D2H: the filtered batch y, the image gradient dL/dx
+  # and the parameter gradients -- software-pipelined over sub-batches on three streams
+  # (exposure_b200/chain.py HostPipelinedChain)
   from exposure_b200.chain import HostPipelinedChain
+  hx = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory(); hx.copy_(x0.cpu())
+  hgy = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory(); hgy.copy_(gout.cpu())
+  hy = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
+  hgx = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
+  hg = [torch.empty(B, ops.NUM_PARAMS[f]).pin_memory() for f in CHAIN_IDS]
   n_chunks = args.e2e_chunks if args.e2e_chunks > 0 and B % args.e2e_chunks == 0 else \
       (8 if B % 8 == 0 else (4 if B % 4 == 0 else 1))
-  del chain                                          # free the resident chain's activations first
-  if fused_on:
-    del fz, fy, fgx, y_steps
+  for k in ("chain", "fz", "fy", "fgx", "x0", "gout"):
+    m.pop(k, None)
+  del x0, gout                                         # free the resident chain's buffers first
   torch.cuda.empty_cache()
   pipe = HostPipelinedChain(CHAIN_IDS, B, H, W, dev, chunks=n_chunks, variant=args.variant, fused=fused_on)
 
   def e2e_step():
     # enqueue only: step i+1's H2D overlaps step i's compute and D2H (every step still copies its
-    # whole input batch in and its whole result out inside the timed region)
-    pipe.step(hx, logits, gout, hy, hg, wait=False)
+    # whole input batch + gradient in and its whole result out inside the timed region)
+    pipe.step(hx, logits, hgy, hy, hg, wait=False, hgx=hgx)
 
   e2e_steps = max(3, min(args.steps, 10))
   for _ in range(2):
@@ -473,23 +524,24 @@ def run_native(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
   e2e_ms = float(t.item())
   e2e = {"value": world * B * e2e_steps / (e2e_ms / 1e3), "unit": "images/s",
-         "h2d_bytes_per_step": hx.numel() * 4,
-         "d2h_bytes_per_step": hy.numel() * 4 + sum(h.numel() * 4 for h in hg), "steps": e2e_steps,
-         "ms_per_step": e2e_ms / e2e_steps}
+         "h2d_bytes_per_step": (hx.numel() + hgy.numel()) * 4,
+         "d2h_bytes_per_step": (hy.numel() + hgx.numel()) * 4 + sum(h.numel() * 4 for h in hg), "steps": e2e_steps,
+         "ms_per_step": e2e_ms / e2e_steps,
+         "note": "x and dL/dy from pinned host memory, y, dL/dx and the parameter gradients back to pinned host memory, every step"}
 
   clocks = sampler.stop(wall0, wall1) if rank == 0 else None
   out = None
   if rank == 0:
     out = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args), chain_impl=args.chain_impl), "clocks": clocks, "e2e": e2e,
+        "config": workload_config(args), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches,
         "roofline": roofline,
     }
     if world == 1 and not args.no_cpu_baseline:
-      out["cpu_baseline"] = cpu_baseline(S)
+      out["cpu_baseline"] = cpu_baseline(args)
     elif world == 1:
       out["cpu_baseline"] = None
   if world > 1:
@@ -506,8 +558,8 @@ def train_config(args):
       "batch_per_gpu": args.batch, "height": 64, "width": 64, "channels": 3, "filters": "E,G,W,S+,T,Ct,BW,C",
       "giters": 1, "citers": 5,
       "parallelism": "dp%d (batch sharded by image; one NCCL all-reduce per optimizer step)" % args.gpus,
-      "l2_policy": "working set is L2 resident by nature (3 MB batches); every iteration draws fresh replay "
-                   "batches, dropout masks and noise",
+      "l2_policy": "no flush: one iteration touches ~137 MB of parameters + gradients + Adam slots plus ~150 MB of "
+                   "activations (> the 126 MB L2); every iteration draws fresh replay batches, dropout masks and noise",
   }
 
 
@@ -627,13 +679,15 @@ def run_train(args):
            "3": "tc_gemm_ws_kernel family (warp-specialised register-gather tcgen05, 3xTF32)",
            "1": "gemm_kernel family (exact-fp32 CUDA-core engine)"}.get(backend, backend)
   n_timed_iters = 3 if graphs else args.steps
-  roofline = {"bound": "tensor", "kernel": kname, "gemm_backend": {"0": "auto (tcgen05-tma where supported)", "1": "cuda-cores", "2": "tcgen05", "3": "tcgen05-ws",
+  tensor = {"bound": "tensor", "kernel": kname, "gemm_backend": {"0": "auto (tcgen05-tma where supported)", "1": "cuda-cores", "2": "tcgen05", "3": "tcgen05-ws",
                                                                       "4": "tcgen05-tma"}.get(backend, backend),
               "achieved": tot_fl / tot_ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": tot_fl / tot_ms / 1e9 / peak_tf,
               "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16; the fp32-accurate "
                                               "3xTF32 path can reach at most 1/6 of it)",
               "share_of_step": (tot_ms / n_timed_iters) / (elapsed_ms / args.steps), "note": roof_note,
               "kernels": kernels}
+  for k in kernels:
+    tensor["k_" + k["kernel"] + "_tflops"] = round(k["tflops"], 2)
 
   # end-to-end leg: fresh RAW and real batches come from pinned host memory every step, the
   # filtered batch and the losses go back to the host (what net.py:330-342 does per sess.run)
@@ -642,21 +696,26 @@ def run_train(args):
   hout = torch.empty(B, 64, 64, 3).pin_memory()
   hloss = torch.empty(4).pin_memory()
 
+  h2d = [0]
+
   class HostProvider:
+    """dataset batches arrive from pinned host memory (the reference feeds numpy batches per sess.run)"""
     def __init__(self, h):
       self.h = h
     def get_next_batch(self, n):
+      h2d[0] += n * self.h[0].numel() * 4
       return self.h[:n].to(dev, non_blocking=True)
 
   mem.fake_dataset, mem.real_dataset = HostProvider(hraw), HostProvider(hreal)
-  h2d = [0]
+  hstates = torch.empty(B, cfg.num_state_dim).pin_memory()
 
   def e2e_iter():
     nonlocal it
     out = t.train_iteration(it, giters=1, citers=5)
     it += 1
     hloss.copy_(torch.stack([out["g_loss"], out["v_loss"], out["emd"], out["critic_gradient_norm"]]), non_blocking=True)
-    hout.copy_(mem.images[:B], non_blocking=True)
+    hout.copy_(out["fake_output"], non_blocking=True)          # net.py:330 fetches fake_output and new_states
+    hstates.copy_(out["new_states"], non_blocking=True)
     torch.cuda.current_stream().synchronize()
 
   for _ in range(2):
@@ -664,6 +723,7 @@ def run_train(args):
   barrier()
   n_e2e = max(3, min(args.steps, 20))
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  h2d[0] = 0
   a.record()
   for _ in range(n_e2e):
     e2e_iter()
@@ -674,16 +734,32 @@ def run_train(args):
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
   e2e_ms = float(tt.item())
   e2e = {"value": world * B * n_e2e / (e2e_ms / 1e3), "unit": "images/s",
-         "h2d_bytes_per_step": 6 * B * 64 * 64 * 3 * 4, "d2h_bytes_per_step": B * 64 * 64 * 3 * 4 + 16,
+         "h2d_bytes_per_step": h2d[0] // n_e2e, "d2h_bytes_per_step": (hout.numel() + hstates.numel() + hloss.numel()) * 4,
          "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
-         "note": "h2d upper bound: 5 real batches + up to 1 fresh RAW batch per iteration"}
+         "note": "H2D (counted): the 5 real batches of the critic steps + the fresh RAW batches that refill the replay memory, "
+                 "from pinned host memory; D2H: fake_output, new_states and the 4 loss scalars of every iteration "
+                 "(net.py:330-342, 362), then a stream synchronize"}
   clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+  # ---- roofline: the filter chain at the north star's shape (256 x 512 x 512 x 3), same run -----------
+  roofline = None
+  if args.roofline_batch > 0 and rank == 0:
+    del hraw, hreal
+    torch.cuda.empty_cache()
+    note("filter-chain roofline leg (%dx512x512x3)" % args.roofline_batch)
+    m = measure_chain(dev, args.roofline_batch, 512, 512, max(5, min(args.steps, 20)), 3)
+    roofline = m["flat"]
+    roofline["images_s_fused"] = m["fused"]["value_images_s"]
+    roofline["images_s_per_step"] = m["per_step"]["value_images_s"]
+    m.clear()
+    torch.cuda.empty_cache()
   if rank == 0:
     out = {"metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(args),
-           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-           "losses": {k: (float(v) if v is not None else None) for k, v in last.items()}}
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "tensor": tensor,
+           "kernel_launches_per_iteration": launches // args.steps,
+           "losses": {k: (float(v) if (v is not None and v.numel() == 1) else None) for k, v in last.items()
+                      if k in ("g_loss", "v_loss", "emd", "critic_gradient_norm")}}
     if world == 1:
       out["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline_train(B)
   if world > 1:
@@ -693,20 +769,10 @@ def run_train(args):
     print(json.dumps(out))
 
 
-def _cpu_train_iteration(B):
-  """The reference's CPU path for one train iteration: oracle generator step + 5 critic steps
-  (autograd, all 8 filters + one-hot select), on a bounded sample of the batch.  Returns
-  (callable running one iteration, images in the sample, host threads used)."""
+def _cpu_params(g):
+  """Random parameters under the reference checkpoint's variable names (shapes of SURVEY 8a)."""
   import torch
   from oracle import filters as OF
-  from oracle import train_step as OT
-  from exposure_b200.trainer import default_cfg
-  cores = host_threads()
-  torch.set_num_threads(cores)
-  cfg = default_cfg()
-  sb = min(B, 8)
-  g = torch.Generator().manual_seed(0)
-  shapes_c = {"critic": 6, "rl_value/critic": 17}
   def make(scope, cin):
     P = {}
     c = cin
@@ -730,6 +796,23 @@ def _cpu_train_iteration(B):
   Pg["generator/action_selection/selector_fc1/biases"] = torch.zeros(128)
   Pg["generator/action_selection/selector_fc2/weights"] = torch.randn(128, 8, generator=g) * 0.1
   Pg["generator/action_selection/selector_fc2/biases"] = torch.zeros(8)
+  return Pg, Pv, Pc
+
+
+def _cpu_train_iteration(B):
+  """The reference's CPU path for one train iteration: oracle generator step + 5 critic steps
+  (autograd, all 8 filters + one-hot select) on B images.  Returns
+  (callable running one iteration, images per iteration, host threads used)."""
+  import torch
+  from oracle import filters as OF
+  from oracle import train_step as OT
+  from exposure_b200.trainer import default_cfg
+  cores = host_threads()
+  torch.set_num_threads(cores)
+  cfg = default_cfg()
+  sb = B
+  g = torch.Generator().manual_seed(0)
+  Pg, Pv, Pc = _cpu_params(g)
   img = OF.synth_images(sb, 64, 64, stress=False)
   real = OF.synth_images(sb, 64, 64, seed=9, stress=False) * 4
   states = torch.zeros(sb, 11)
@@ -756,8 +839,61 @@ def cpu_baseline_train(B, budget_s=25.0):
     times.append(time.time() - t0)
   med = statistics.median(times)
   return {"value": sb / med, "unit": "images/s", "cores": cores, "kind": "port",
-          "sample": "1 generator+value step + 5 critic steps on %d of the %d images, median of %d reps; CPU restatement of "
-                    "the reference TF graph (oracle/train_step.py, torch-CPU autograd), not TensorFlow" % (sb, B, len(times))}
+          "sample": "1 generator+value step + 5 critic steps on the full batch of %d images (64x64x3), median of %d reps "
+                    "(min %.2fs); CPU restatement of the reference TF graph (oracle/train_step.py, torch-CPU autograd), "
+                    "not TensorFlow" % (sb, len(times), min(times))}
+
+
+# ------------------------------------------------------------------------------------------
+# eval workload (configs[2])
+# ------------------------------------------------------------------------------------------
+EVAL_STEPS = 5          # cfg.test_steps (config_example.py:118)
+
+
+def eval_config(args):
+  H, W = args.height or 64, args.width or 64
+  return {"workload": "eval: %d policy steps on 64x64 thumbnails + fused %d-step filter apply on the %dx%d batch "
+                      "(BASELINE.json configs[2]; net.py:796-820)" % (EVAL_STEPS, EVAL_STEPS, H, W),
+          "batch_per_gpu": args.batch, "height": H, "width": W, "policy_steps": EVAL_STEPS,
+          "parallelism": "dp%d (independent images, no collective)" % args.gpus,
+          "l2_policy": "fresh dropout masks every step; high-resolution batches exceed the L2 from 2 x 4K frames up, the "
+                       "64x64 configuration (12.6 MB) is L2-resident by nature"}
+
+
+def _cpu_eval_iteration(args):
+  """Reference eval path on the CPU: test_steps x agent_generator (all 8 filters + one-hot select, is_train = 0)
+  on the thumbnails, the selected filter applied to the full-resolution image per step (filters.py:89-96)."""
+  import torch
+  from oracle import filters as OF
+  from oracle import train_step as OT
+  from exposure_b200.trainer import default_cfg
+  cores = host_threads()
+  torch.set_num_threads(cores)
+  cfg = default_cfg()
+  B = args.cpu_batch or args.batch
+  H, W = args.height or 64, args.width or 64
+  g = torch.Generator().manual_seed(0)
+  Pg, _, _ = _cpu_params(g)
+  hi = OF.synth_images(B, H, W, stress=False)
+  import torch.nn.functional as Fn
+  def thumb_of(x):
+    s = min(H, W)
+    y0, x0 = (H - s) // 2, (W - s) // 2
+    c = x[:, y0:y0 + s, x0:x0 + s, :].permute(0, 3, 1, 2)
+    return Fn.interpolate(c, size=(64, 64), mode="bilinear", align_corners=False).permute(0, 2, 3, 1).contiguous()
+  dm = lambda: (torch.rand(B, 4, 4, 256, generator=g) < 0.5).float() * 2
+
+  def iteration():
+    with torch.no_grad():
+      img, states, big = thumb_of(hi), torch.zeros(B, 11), hi
+      for _ in range(EVAL_STEPS):
+        out, states, _, _, ids, _ = OT.agent_generator(Pg, img, states, torch.rand(B, generator=g), dm(), dm(), 0, 0.0, cfg,
+                                                       high_res=None if (H, W) == (64, 64) else big)
+        if (H, W) != (64, 64):
+          out, big = out
+        img = out
+
+  return iteration, B, cores
 
 
 def run_eval(args):
@@ -777,38 +913,76 @@ def run_eval(args):
   t = Trainer(device=dev, seed=0)
   g = torch.Generator(device=dev).manual_seed(77)
   hi = torch.exp(torch.randn(B, H, W, 3, device=dev, generator=g) - 3.2).clamp_(0, 4)
+  sampler = ClockSampler(local)
+  sampler.start()
   for _ in range(max(args.warmup, 3)):
     retouch(t, hi, generator=g)
   torch.cuda.synchronize()
   ops.event_log = []
   l0 = ops.launch_count
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  wall0 = time.time()
   e0.record()
   for _ in range(args.steps):
     out = retouch(t, hi, generator=g)
   e1.record()
   torch.cuda.synchronize()
+  wall1 = time.time()
   ms = e0.elapsed_time(e1)
+  launches = ops.launch_count - l0
   log, ops.event_log = ops.event_log, None
   fused = [(a.elapsed_time(b), nb) for name, nb, a, b in log if name.startswith("filter_chain_fwd")]
   peak, peak_src = peaks()
   fms = sum(x[0] for x in fused) / max(1, len(fused))
   fbytes = fused[0][1] if fused else 0
   S = int(out["ids"].shape[0])
-  print(json.dumps({
+  # end to end: the batch comes from pinned host memory and the retouched batch goes back, every step
+  hx = torch.empty(B, H, W, 3).pin_memory(); hx.copy_(hi.cpu())
+  hy = torch.empty(B, H, W, 3).pin_memory()
+  dx = torch.empty_like(hi)
+  def e2e_step():
+    dx.copy_(hx, non_blocking=True)
+    o = retouch(t, dx, generator=g)
+    hy.copy_(o["output"], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+  for _ in range(2):
+    e2e_step()
+  n_e2e = max(3, min(args.steps, 20))
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(n_e2e):
+    e2e_step()
+  b.record()
+  torch.cuda.synchronize()
+  e2e_ms = a.elapsed_time(b)
+  clocks = sampler.stop(wall0, wall1)
+  res = {
       "metric": "images/sec", "value": B * args.steps / (ms / 1e3), "unit": "images/s", "n_gpus": 1, "steps": args.steps,
       "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": "eval: %d policy steps on 64x64 thumbnails + fused %d-step filter apply on the %dx%d batch "
-                             "(BASELINE.json configs[2]; net.py:796-820)" % (S, S, H, W),
-                 "batch_per_gpu": B, "height": H, "width": W, "policy_steps": S},
-      "gpu_launches": ops.launch_count - l0,
+      "config": eval_config(args), "clocks": clocks,
+      "e2e": {"value": B * n_e2e / (e2e_ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": hx.numel() * 4,
+              "d2h_bytes_per_step": hy.numel() * 4, "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e},
+      "gpu_launches": launches,
       "roofline": {"bound": "hbm", "kernel": "filter_chain_fwd_kernel (all %d steps in one pass)" % S,
                    "achieved": fbytes / fms / 1e6 if fms else None, "peak": peak, "unit": "GB/s",
                    "frac": fbytes / fms / 1e6 / peak if fms else None, "traffic": None, "peak_source": peak_src,
                    "avg_ms": fms, "algorithmic_bytes_per_launch": fbytes,
+                   "share_of_step": fms * len(fused) / ms if ms else None,
                    "note": "24 B/pixel for the whole episode; the unfused schedule moves %d B/pixel" % (24 * S)},
-  }))
+  }
+  if not args.no_cpu_baseline:
+    iteration, sb, cores = _cpu_eval_iteration(args)
+    iteration()
+    times = []
+    t_end = time.time() + 25.0
+    while len(times) < 5 and (time.time() < t_end or len(times) < 2):
+      t0 = time.time(); iteration(); times.append(time.time() - t0)
+    res["cpu_baseline"] = {"value": sb / statistics.median(times), "unit": "images/s", "cores": cores, "kind": "port",
+                           "sample": "%d policy steps + filter apply on the full batch of %d images (%dx%d), median of %d reps; "
+                                     "CPU restatement of the reference TF graph (oracle port), not TensorFlow"
+                                     % (EVAL_STEPS, sb, H, W, len(times))}
+  print(json.dumps(res))
 
 
 def main():

@@ -208,21 +208,26 @@ class HostPipelinedChain:
         ch._glog = [ch._glog_flat[self.off[k]:self.off[k + 1]].view(cb, k_n) for k, k_n in enumerate(self.nk)]
       self.h_glog = torch.empty(chunks, self.off[-1]).pin_memory()
     self._scatter_to = None
+    self._gy = None                       # per-chunk device staging of dL/dx_N when it arrives from the host
     self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
     self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
     self.ev_cmp = [torch.cuda.Event() for _ in range(chunks)]
     self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
     self._first = True
 
-  def step(self, hx, logits_list, gout, hy, hglogits, wait=True):
-    """hx, hy: pinned host [B,H,W,3]; logits_list[k]: device [B,n_k]; gout: device [B,H,W,3];
-    hglogits[k]: pinned host [B,n_k].  Blocks until the results are in host memory, unless
+  def step(self, hx, logits_list, gout, hy, hglogits, wait=True, hgx=None):
+    """hx, hy: pinned host [B,H,W,3]; logits_list[k]: device [B,n_k]; gout = dL/dx_N: device [B,H,W,3] or
+    pinned host (then it is copied in per sub-batch like hx); hglogits[k]: pinned host [B,n_k]; hgx
+    (optional): pinned host [B,H,W,3] that receives dL/dx_0.  Blocks until the results are in host memory, unless
     wait=False: then the step is only enqueued (call wait() before reading hy / hglogits) and the
     H2D copies of the next step overlap this step's compute and D2H -- consecutive steps keep both
     PCIe directions busy without a fill / drain bubble per step."""
     cb = self.cb
     if [int(l.shape[1]) for l in logits_list] != self.nk:
       raise ValueError("logits_list[k] must be [B, %s] (one column per filter parameter)" % self.nk)
+    host_g = not gout.is_cuda
+    if host_g and self._gy is None:
+      self._gy = [torch.empty(cb, *hx.shape[1:], device=self.device) for _ in range(self.chunks)]
     cur = torch.cuda.current_stream()
     for s in (self.s_in, self.s_cmp, self.s_out):
       s.wait_stream(cur)
@@ -236,22 +241,27 @@ class HostPipelinedChain:
         if not self._first:
           self.s_in.wait_event(self.ev_cmp[c])          # previous step's compute on this buffer is done
         (ch.x if self.fused else ch._acts[0]).copy_(hx[sl], non_blocking=True)
+        if host_g:
+          self._gy[c].copy_(gout[sl], non_blocking=True)
         self.ev_in[c].record(self.s_in)
       with torch.cuda.stream(self.s_cmp):
         self.s_cmp.wait_event(self.ev_in[c])
         if not self._first:
           self.s_cmp.wait_event(self.ev_out[c])         # previous step's D2H of this chunk's outputs is done
+        gy_c = self._gy[c] if host_g else gout[sl]
         if self.fused:
-          y, _, glog_flat = ch.forward_backward(ch.x, gout[sl], y_out=ch.y, gx_out=ch.gx)
+          y, gx, glog_flat = ch.forward_backward(ch.x, gy_c, y_out=ch.y, gx_out=ch.gx)
           glog_flat = glog_flat.view(-1)
         else:
           y = ch.forward_resident([l[sl] for l in logits_list])
-          ch.backward(gout[sl], need_input_grad=True)
+          gx, _ = ch.backward(gy_c, need_input_grad=True)
           glog_flat = ch._glog_flat
         self.ev_cmp[c].record(self.s_cmp)
       with torch.cuda.stream(self.s_out):
         self.s_out.wait_event(self.ev_cmp[c])
         hy[sl].copy_(y, non_blocking=True)
+        if hgx is not None:
+          hgx[sl].copy_(gx, non_blocking=True)
         self.h_glog[c].copy_(glog_flat, non_blocking=True)
         self.ev_out[c].record(self.s_out)
     self._first = False

@@ -308,7 +308,8 @@ class Trainer:
       alpha = torch.rand(B, device=self.device, generator=self.rng)
       cout = self.critic_step(real, fake, alpha, cfg.lr_c(it))
     return dict(g_loss=out["g_loss"], v_loss=out["v_loss"], emd=cout["emd"] if cout else None,
-                critic_gradient_norm=cout["critic_gradient_norm"] if cout else None)
+                critic_gradient_norm=cout["critic_gradient_norm"] if cout else None,
+                fake_output=out["fake_output"], new_states=out["new_states"])
 
   # ---- random draws the reference makes per step (explicit so tests can inject them) -------
   def draw(self, B, generator=None):

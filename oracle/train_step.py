@@ -26,13 +26,15 @@ def critic_params(P, scope):
               fc2_w=P[scope + "/fully_connected_1/weights"], fc2_b=P[scope + "/fully_connected_1/biases"])
 
 
-def agent_generator(Pg, img, states, noise, drop_f, drop_s, is_train, progress, cfg):
+def agent_generator(Pg, img, states, noise, drop_f, drop_s, is_train, progress, cfg, high_res=None):
   """agent.py:41-260 -> (out, new_states, surrogate, penalty, ids, pdf).  drop_* are the
-  tf.nn.dropout multipliers (0 or 1/keep) on the NHWC-flattened 4096 features."""
+  tf.nn.dropout multipliers (0 or 1/keep) on the NHWC-flattened 4096 features.  With `high_res`
+  (agent.py:41, 126-129; filters.py:89-96) every filter is also applied to the full-resolution batch with the
+  same parameters and one-hot selected: `out` becomes the pair (out, high_res_out).  No masking on that path."""
   B = img.shape[0]
   w, b = _stack(Pg, "generator")
   feat = ON.cnn(ON.enrich(img, states), w, b) * drop_f.reshape(B, -1)
-  filtered = []
+  filtered, filtered_hi = [], []
   for j in range(8):
     n = OF.NUM_PARAMS[j]
     h = ON.fc(feat, Pg["generator/filter_%d/fc1/weights" % j], Pg["generator/filter_%d/fc1/biases" % j])
@@ -42,6 +44,8 @@ def agent_generator(Pg, img, states, noise, drop_f, drop_s, is_train, progress, 
                                       minimum_strength=cfg.minimum_strength))
     else:
       filtered.append(OF.apply_filter(j, img, o[:, :n]))
+      if high_res is not None:
+        filtered_hi.append(OF.apply_filter(j, high_res, o[:, :n]))
   filtered = torch.stack(filtered, dim=1)
   w, b = _stack(Pg, "generator/action_selection")
   sfeat = ON.cnn(ON.enrich(img, states), w, b) * drop_s.reshape(B, -1)
@@ -53,6 +57,8 @@ def agent_generator(Pg, img, states, noise, drop_f, drop_s, is_train, progress, 
   onehot[valid, ids[valid].long()] = 1.0
   out = (filtered * onehot[:, :, None, None, None]).sum(dim=1)
   penalty = (torch.clamp(out - 1, min=0) ** 2).mean(dim=(1, 2, 3))[:, None] + pen_head
+  if high_res is not None:
+    out = (out, (torch.stack(filtered_hi, dim=1) * onehot[:, :, None, None, None]).sum(dim=1))
   return out, new_states, surrogate, penalty, ids, pdf
 
 

@@ -672,15 +672,11 @@ def run_train(args):
   tot_ms = sum(d["ms"] for d in per.values()) or 1.0
   tot_fl = sum(d["flops"] for d in per.values())
   backend = os.environ.get("EXPOSURE_GEMM_BACKEND", "0")
-  kname = {"0": "tma_gemm_kernel family (conv fprop/dgrad/wgrad: TMA-fed tcgen05 kind::tf32, 3xTF32 split, TMEM "
-                "accumulators, cluster split-K) + CUDA-core FC / small-N kernels",
-           "4": "tma_gemm_kernel family (TMA-fed tcgen05, 3xTF32) + CUDA-core FC / small-N kernels",
-           "2": "tc_gemm_kernel family (register-gather tcgen05, 3xTF32)",
-           "3": "tc_gemm_ws_kernel family (warp-specialised register-gather tcgen05, 3xTF32)",
-           "1": "gemm_kernel family (exact-fp32 CUDA-core engine)"}.get(backend, backend)
+  kname = {"0": "tma_gemm_kernel family (conv fprop/dgrad/wgrad + FC: TMA-fed tcgen05 kind::tf32, 3xTF32 split, TMEM "
+                "accumulators, cluster split-K) + CUDA-core small-N kernels",
+           "1": "gemm_kernel family (exact-fp32 CUDA-core engine, A/B switch)"}.get(backend, backend)
   n_timed_iters = 3 if graphs else args.steps
-  tensor = {"bound": "tensor", "kernel": kname, "gemm_backend": {"0": "auto (tcgen05-tma where supported)", "1": "cuda-cores", "2": "tcgen05", "3": "tcgen05-ws",
-                                                                      "4": "tcgen05-tma"}.get(backend, backend),
+  tensor = {"bound": "tensor", "kernel": kname, "gemm_backend": {"0": "tcgen05-tma where supported", "1": "cuda-cores"}.get(backend, backend),
               "achieved": tot_fl / tot_ms / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": tot_fl / tot_ms / 1e9 / peak_tf,
               "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16; the fp32-accurate "
                                               "3xTF32 path can reach at most 1/6 of it)",

@@ -28,6 +28,8 @@ SIGNATURES = {
     "exp_last_error": (ctypes.c_char_p, []),
     "exp_num_filter_params": (_c_int, [_c_int]),
     "exp_set_pdl": (_c_int, [_c_int]),
+    "exp_set_filter_ranges": (_c_int, [_c_void_p, _c_int]),
+    "exp_get_filter_ranges": (_c_int, [_c_void_p]),
     "exp_filter_regress_fwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_void_p]),
     "exp_filter_regress_bwd": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "exp_filter_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
@@ -91,6 +93,32 @@ SIGNATURES = {
                           _c_size_t, _c_void_p]),
 }
 
+class FilterRanges(ctypes.Structure):
+  """exp_filter_ranges (include/exposure_b200.h)"""
+  _fields_ = [("exposure_range", _c_float), ("gamma_range", _c_float), ("tone_lo", _c_float), ("tone_hi", _c_float),
+              ("color_lo", _c_float), ("color_hi", _c_float)]
+
+
+def set_filter_ranges(cfg=None):
+  """Hand the regressor ranges of `cfg` (filters.py:179, 202, 261, 309 read cfg.exposure_range, cfg.gamma_range,
+  cfg.color_curve_range, cfg.tone_curve_range; cfg.curve_steps) to the library; None restores the defaults.
+  Keys a cfg does not carry keep their config_example.py value."""
+  if cfg is None:
+    check(lib().exp_set_filter_ranges(None, 8), "exp_set_filter_ranges")
+    return
+  g = lambda k, d: cfg[k] if k in cfg else d
+  tone, color = tuple(g("tone_curve_range", (0.5, 2))), tuple(g("color_curve_range", (0.90, 1.10)))
+  r = FilterRanges(float(g("exposure_range", 3.5)), float(g("gamma_range", 3)), float(tone[0]), float(tone[1]),
+                   float(color[0]), float(color[1]))
+  check(lib().exp_set_filter_ranges(ctypes.byref(r), int(g("curve_steps", 8))), "exp_set_filter_ranges")
+
+
+def get_filter_ranges():
+  r = FilterRanges()
+  check(lib().exp_get_filter_ranges(ctypes.byref(r)), "exp_get_filter_ranges")
+  return {k: getattr(r, k) for k, _ in FilterRanges._fields_}
+
+
 _lib = None
 
 
@@ -107,7 +135,7 @@ def lib():
       fn.restype = res
       fn.argtypes = args
     _lib = l
-    be = os.environ.get("EXPOSURE_GEMM_BACKEND")      # 0 auto, 1 CUDA cores, 2 tcgen05
+    be = os.environ.get("EXPOSURE_GEMM_BACKEND")      # 0 tcgen05 (TMA-fed) where supported, 1 CUDA cores
     if be:
       check(l.exp_set_gemm_backend(int(be)), "exp_set_gemm_backend")
   return _lib

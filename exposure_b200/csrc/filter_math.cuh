@@ -30,6 +30,20 @@ __host__ __device__ constexpr int num_acc(int fid) {
   return fid == EXP_FILTER_WB ? 3 : fid == EXP_FILTER_TONE ? 8 : fid == EXP_FILTER_COLOR ? 24 : fid == EXP_FILTER_LEVEL ? 2 : 1;
 }
 
+// cfg-driven ranges of the filter_param_regressors (filters.py:179 cfg.exposure_range, :202 cfg.gamma_range,
+// :261 cfg.color_curve_range, :309 cfg.tone_curve_range).  Set process-wide through exp_set_filter_ranges and
+// passed BY VALUE in every launch's arguments; the defaults are config_example.py:27-33.
+struct FilterRanges {
+  float exposure;            // tanh_range(-r, r, initial=0)
+  float gamma_log;           // ln(cfg.gamma_range)
+  float tone_lo, tone_hi;    // tanh_range(*cfg.tone_curve_range)
+  float color_lo, color_hi;  // tanh_range(*cfg.color_curve_range, initial=1)
+  float color_bias;          // atanh(2 (1 - lo)/(hi - lo) - 1)  (util.py:285-286); 0 for ranges centred on 1
+};
+__host__ __device__ inline FilterRanges default_ranges() {
+  return FilterRanges{3.5f, 1.0986123f /* float32(np.log(3)) */, 0.5f, 2.f, 0.90f, 1.10f, 0.f};
+}
+
 // Per-image constants, built once per CTA in shared memory from params[b, :].
 struct __align__(16) FilterConsts {
   float p[EXP_MAX_FILTER_PARAMS];   // regressed parameters
@@ -42,6 +56,7 @@ struct __align__(16) FilterConsts {
   float slope[3][2 * (kCurveSteps + 2)];
   float e;                          // Exposure: exp(p * ln2) ; Level: upper - lower + 1e-6
   float raw[EXP_MAX_FILTER_PARAMS]; // raw regressor logits (EXP_OPT_LOGITS mode only)
+  FilterRanges rg;                  // regressor ranges of this launch
 };
 
 // ---- filter_param_regressor of one image (filters.py:177-179, 201-203, 223-235, 256-262,
@@ -59,15 +74,16 @@ __device__ __forceinline__ float sigmoid_f(float f, float* d) {
 }
 // p[0..n) = regress(f[0..n)); BWD: gf[0..n) = J^T gp
 template <bool BWD>
-__device__ __forceinline__ void regress_image(int fid, const float* f, float* po, const float* gp, float* gf) {
+__device__ __forceinline__ void regress_image(int fid, const float* f, float* po, const float* gp, float* gf,
+                                              const FilterRanges& rg) {
   float d;
   switch (fid) {
     case EXP_FILTER_EXPOSURE: {
-      const float p = tanh_range_f(f[0], -3.5f, 3.5f, &d);
+      const float p = tanh_range_f(f[0], -rg.exposure, rg.exposure, &d);
       if (BWD) gf[0] = gp[0] * d; else po[0] = p;
     } break;
     case EXP_FILTER_GAMMA: {
-      const float lg = 1.0986123f;                   // float32(np.log(3))
+      const float lg = rg.gamma_log;                 // float32(np.log(cfg.gamma_range))
       const float g = expf(tanh_range_f(f[0], -lg, lg, &d));
       if (BWD) gf[0] = gp[0] * g * d; else po[0] = g;
     } break;
@@ -106,13 +122,13 @@ __device__ __forceinline__ void regress_image(int fid, const float* f, float* po
     } break;
     case EXP_FILTER_TONE:
       for (int i = 0; i < 8; ++i) {
-        const float p = tanh_range_f(f[i], 0.5f, 2.f, &d);
+        const float p = tanh_range_f(f[i], rg.tone_lo, rg.tone_hi, &d);
         if (BWD) gf[i] = gp[i] * d; else po[i] = p;
       }
       break;
     case EXP_FILTER_COLOR:
       for (int i = 0; i < 24; ++i) {
-        const float p = tanh_range_f(f[i], 0.90f, 1.10f, &d);
+        const float p = tanh_range_f(f[i] + rg.color_bias, rg.color_lo, rg.color_hi, &d);
         if (BWD) gf[i] = gp[i] * d; else po[i] = p;
       }
       break;
@@ -124,12 +140,14 @@ __device__ __forceinline__ void regress_image(int fid, const float* f, float* po
 // logits != 0: prow holds raw regressor logits; the regressed parameters are computed here
 // (fused filter_param_regressor) and the logits kept for the backward's chain rule.
 // `t` = lane of the warp doing the set-up (the fused-chain kernel gives every step its own warp).
-__device__ __forceinline__ void setup_consts_lane(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits, int t) {
+__device__ __forceinline__ void setup_consts_lane(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits, int t,
+                                                  const FilterRanges& rg = default_ranges()) {
   const int n = num_params(fid);
+  if (t == 0) sc.rg = rg;
   if (logits) {
     if (t < EXP_MAX_FILTER_PARAMS) { sc.raw[t] = (t < n) ? prow[t] : 0.f; sc.p[t] = 0.f; }
     __syncwarp();
-    if (t == 0) regress_image<false>(fid, sc.raw, sc.p, nullptr, nullptr);
+    if (t == 0) regress_image<false>(fid, sc.raw, sc.p, nullptr, nullptr, rg);
   } else {
     if (t < EXP_MAX_FILTER_PARAMS) sc.p[t] = (t < n) ? prow[t] : 0.f;
   }
@@ -165,8 +183,9 @@ __device__ __forceinline__ void setup_consts_lane(FilterConsts& sc, const float*
   }
 }
 
-__device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits = 0) {
-  setup_consts_lane(sc, prow, fid, logits, (int)threadIdx.x);
+__device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __restrict__ prow, int fid, int logits = 0,
+                                             const FilterRanges& rg = default_ranges()) {
+  setup_consts_lane(sc, prow, fid, logits, (int)threadIdx.x, rg);
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
@@ -464,7 +483,7 @@ __device__ __forceinline__ void finalize_grads(int fid, const double* sum, const
   }
   float gp[EXP_MAX_FILTER_PARAMS];
   finalize_gparams(fid, sum, sc.p, gp);
-  regress_image<true>(fid, sc.raw, nullptr, gp, out);
+  regress_image<true>(fid, sc.raw, nullptr, gp, out, sc.rg);
 }
 
 }  // namespace expo

@@ -7,6 +7,7 @@
 //
 // Replaces the unfused TF-1.6 Eigen launches behind filters.py process() (2..43 launches
 // per filter) and the 8-way stack/one_hot/reduce_sum select of agent.py:77,118-129.
+#include <cmath>
 #include <cstdlib>
 
 #include "filter_math.cuh"
@@ -31,6 +32,10 @@ constexpr int kMaxPersistentCtas = 4096;  // upper bound on the TMA variant's gr
 static int g_pdl = [] { const char* e = getenv("EXPOSURE_PDL"); return e ? atoi(e) : 0; }();
 bool pdl_enabled() { return g_pdl != 0; }
 void set_pdl(int on) { g_pdl = on; }
+
+// process-wide regressor ranges (exp_set_filter_ranges); copied by value into every launch's arguments
+static FilterRanges g_ranges = default_ranges();
+FilterRanges host_ranges() { return g_ranges; }
 
 static thread_local char g_err[512] = "";
 char* last_error_buf() { return g_err; }
@@ -61,6 +66,7 @@ struct FilterArgs {
   float* mask_out;            // [B][P] (forward, nullable)
   int mstride, H, W, uniform_id, masking;
   float max_sharp, min_strength;
+  FilterRanges rg;            // cfg-driven regressor ranges (exp_set_filter_ranges)
 };
 
 // ---- 4 pixels <-> 3 float4 ------------------------------------------------------------
@@ -147,7 +153,7 @@ __device__ __forceinline__ void filter_body(const FilterArgs& A) {
   __shared__ FilterConsts sc;
   __shared__ float red[BWD ? kWarps : 1][kAccStride];
   const int b = blockIdx.y;
-  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits);
+  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits, A.rg);
   __syncthreads();
 
   const size_t img = (size_t)b * A.P * 3;
@@ -200,6 +206,28 @@ __device__ __forceinline__ void filter_body(const FilterArgs& A) {
   if constexpr (BWD) reduce_and_finish<FID>(acc, A, sc, red, b, gridDim.x);
 }
 
+// id -1 (pdf_sample's u == 0 quirk, pdf_sample_layer.py:5-10: an all-zero one-hot row): the reference's
+// one-hot sum (agent.py:124-125) yields a BLACK image and no gradient.  The kernels write those zeros
+// themselves, so the caller's output buffers may be uninitialised.
+template <bool BWD, bool HAS_GX>
+__device__ __forceinline__ void zero_body(const FilterArgs& A) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * A.pix_per_block;
+  const int p1 = min(A.P, p0 + A.pix_per_block);
+  if constexpr (!BWD || HAS_GX) {
+    float* __restrict__ out = A.out + (size_t)b * A.P * 3;
+    for (int i = 3 * p0 + threadIdx.x; i < 3 * p1; i += kThreads) out[i] = 0.f;
+  }
+  if constexpr (BWD) {
+    if (blockIdx.x == 0) {
+      for (int i = threadIdx.x; i < A.pstride; i += kThreads) A.gparams[(size_t)b * A.pstride + i] = 0.f;
+      if (A.gmask) for (int i = threadIdx.x; i < A.mstride; i += kThreads) A.gmask[(size_t)b * A.mstride + i] = 0.f;
+    }
+  } else {
+    if (A.mask_out) for (int q = p0 + threadIdx.x; q < p1; q += kThreads) A.mask_out[(size_t)b * A.P + q] = 0.f;
+  }
+}
+
 // One kernel per filter for uniform steps (tight register allocation per filter) ...
 template <int FID, bool BWD, bool HAS_GX, bool VEC>
 __global__ void __launch_bounds__(kThreads) filter_step_kernel(const FilterArgs A) {
@@ -222,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) filter_step_select_kernel(const Filt
     case 7: filter_body<7, BWD, HAS_GX, VEC>(A); break;
     case 8: filter_body<8, BWD, HAS_GX, VEC>(A); break;
     case 9: filter_body<9, BWD, HAS_GX, VEC>(A); break;
-    default: break;   // id -1 (pdf_sample u==0 quirk, pdf_sample_layer.py:5-10): the caller pre-zeroes the output
+    default: zero_body<BWD, HAS_GX>(A); break;   // id -1: black output / zero gradients, written here
   }
 }
 
@@ -234,7 +262,7 @@ __device__ __forceinline__ void masked_body(const FilterArgs& A) {
   __shared__ MaskConsts mc;
   __shared__ float red[BWD ? kWarps : 1][kAccStride];
   const int b = blockIdx.y;
-  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits);
+  if (threadIdx.x < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits, A.rg);
   if (threadIdx.x == 32)
     setup_mask(mc, A.mask_logits ? A.mask_logits + (size_t)b * A.mstride : nullptr, FID, A.H, A.W, A.max_sharp,
                A.min_strength, A.masking);
@@ -302,7 +330,7 @@ __global__ void __launch_bounds__(kThreads) filter_step_masked_kernel(const Filt
 #define EXP_CASE(F) case F: masked_body<F, BWD, HAS_GX, VEC>(A); break;
     EXP_CASE(0) EXP_CASE(1) EXP_CASE(2) EXP_CASE(3) EXP_CASE(4) EXP_CASE(5) EXP_CASE(6) EXP_CASE(7) EXP_CASE(8) EXP_CASE(9)
 #undef EXP_CASE
-    default: break;   // id -1: the caller pre-zeroes the outputs
+    default: zero_body<BWD, HAS_GX>(A); break;   // id -1: black output / zero gradients, written here
   }
 }
 
@@ -354,6 +382,7 @@ constexpr int kMaxChain = 8;
 struct ChainArgs {
   const float* x; float* y; const float* params; const int* ids;   // params [S][B][pstride], ids [S][B]
   int S, B, P, pstride, pix_per_block, logits;
+  FilterRanges rg;
 };
 
 template <int FID>
@@ -395,7 +424,7 @@ __global__ void __launch_bounds__(kThreads) filter_chain_fwd_kernel(const ChainA
     const int f = A.ids ? A.ids[s * A.B + b] : -1;
     if (threadIdx.x == 0) fids[s] = f;
     if (threadIdx.x < 32 && f >= 0 && f < EXP_NUM_FILTER_KINDS)
-      setup_consts(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits);
+      setup_consts(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits, A.rg);
   }
   __syncthreads();
   const size_t img = (size_t)b * A.P * 3;
@@ -438,6 +467,7 @@ struct ChainBwdArgs {
   const float* params; const int* ids; float* gparams;           // [S][B][pstride], [S][B], [S][B][pstride]
   float* partials; unsigned* counters;
   int S, B, P, pstride, logits, nblk, ntiles;
+  FilterRanges rg;
 };
 
 // Sum N (power of two) per-lane values over the warp: at every stage a lane keeps one half of its values
@@ -575,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const
     const int f = A.ids[s * A.B + b];
     if (lane == 0) fids[s] = (f >= 0 && f < EXP_NUM_FILTER_KINDS) ? f : -1;
     if (f >= 0 && f < EXP_NUM_FILTER_KINDS)
-      setup_consts_lane(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits, lane);
+      setup_consts_lane(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits, lane, A.rg);
   }
   for (int i = tid; i < kWarps * kChainRec; i += kThreads) (&slots[0][0])[i] = 0.f;
   __syncthreads();
@@ -693,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const
 template <bool BWD>
 __global__ void regress_kernel(const float* __restrict__ logits, int lstride, float* __restrict__ params,
                                const float* __restrict__ gparams, int pstride, float* __restrict__ glogits,
-                               const int* __restrict__ ids, int uniform_id, int B) {
+                               const int* __restrict__ ids, int uniform_id, int B, const FilterRanges rg) {
   EXP_PDL_ENTRY();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -704,7 +734,7 @@ __global__ void regress_kernel(const float* __restrict__ logits, int lstride, fl
   float* gf = BWD ? glogits + (size_t)b * lstride : nullptr;
   if (BWD) for (int i = 0; i < lstride; ++i) gf[i] = 0.f;
   if (fid < 0 || fid >= EXP_NUM_FILTER_KINDS) return;
-  regress_image<BWD>(fid, f, po, gp, gf);
+  regress_image<BWD>(fid, f, po, gp, gf, rg);
 }
 
 // ---- host side of the persistent TMA variant ---------------------------------------------
@@ -749,6 +779,7 @@ static TmaArgs make_tma_args(const float* x, const float* gy, float* out, const 
                              int B, int P) {
   TmaArgs T{};
   T.x = x; T.gy = gy; T.out = out; T.params = params; T.pstride = pstride; T.P = P; T.B = B;
+  T.rg = host_ranges();
   T.tiles_per_image = (P + kTilePx - 1) / kTilePx;
   T.total_tiles = B * T.tiles_per_image;
   return T;
@@ -799,6 +830,30 @@ int exp_set_pdl(int enable) {
   return EXP_OK;
 }
 const char* exp_last_error(void) { return last_error_buf(); }
+int exp_set_filter_ranges(const exp_filter_ranges* r, int curve_steps) {
+  if (!r) { g_ranges = default_ranges(); return EXP_OK; }
+  if (curve_steps != kCurveSteps)
+    return set_error(EXP_ERR_UNSUPPORTED, "cfg.curve_steps = %d: the curve kernels are built for %d knots", curve_steps, kCurveSteps);
+  EXP_CHECK_ARG(r->exposure_range > 0.f && r->gamma_range > 1.f, "exposure_range must be > 0 and gamma_range > 1");
+  EXP_CHECK_ARG(r->tone_lo < r->tone_hi && r->color_lo < r->color_hi, "curve ranges must be (lo, hi) with lo < hi");
+  EXP_CHECK_ARG(r->color_lo < 1.f && 1.f < r->color_hi, "color_curve_range must contain its initial value 1 (util.py:285-286)");
+  FilterRanges g;
+  g.exposure = r->exposure_range;
+  g.gamma_log = (float)log((double)r->gamma_range);        // filters.py:202 np.log(cfg.gamma_range)
+  g.tone_lo = r->tone_lo; g.tone_hi = r->tone_hi;
+  g.color_lo = r->color_lo; g.color_hi = r->color_hi;
+  // util.py:285-286 (python doubles): bias = atanh(2 (initial - l)/(r - l) - 1), initial = 1
+  g.color_bias = (float)atanh(2.0 * (1.0 - (double)r->color_lo) / ((double)r->color_hi - (double)r->color_lo) - 1.0);
+  if (fabsf(g.color_bias) < 1e-7f) g.color_bias = 0.f;     // ranges centred on 1 (every shipped config)
+  g_ranges = g;
+  return EXP_OK;
+}
+int exp_get_filter_ranges(exp_filter_ranges* r) {
+  EXP_CHECK_ARG(r, "null pointer");
+  r->exposure_range = g_ranges.exposure; r->gamma_range = (float)exp((double)g_ranges.gamma_log);
+  r->tone_lo = g_ranges.tone_lo; r->tone_hi = g_ranges.tone_hi; r->color_lo = g_ranges.color_lo; r->color_hi = g_ranges.color_hi;
+  return EXP_OK;
+}
 int exp_num_filter_params(int fid) {
   if (fid < 0 || fid >= EXP_NUM_FILTER_KINDS) return set_error(EXP_ERR_INVALID_ARG, "bad filter id %d", fid);
   return num_params(fid);
@@ -811,7 +866,7 @@ int exp_filter_regress_fwd(const float* logits, int lstride, float* params, int 
   if (need < 0) return need;
   EXP_CHECK_ARG(lstride >= need && pstride >= need, "strides (%d,%d) < %d", lstride, pstride, need);
   launch_pdl(regress_kernel<false>, dim3((B + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
-      logits, lstride, params, nullptr, pstride, nullptr, ids, uniform_id, B);
+      logits, lstride, params, nullptr, pstride, nullptr, ids, uniform_id, B, host_ranges());
   EXP_CHECK_LAUNCH("exp_filter_regress_fwd");
   return EXP_OK;
 }
@@ -823,7 +878,7 @@ int exp_filter_regress_bwd(const float* logits, int lstride, const float* gparam
   if (need < 0) return need;
   EXP_CHECK_ARG(lstride >= need && pstride >= need, "strides (%d,%d) < %d", lstride, pstride, need);
   launch_pdl(regress_kernel<true>, dim3((B + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
-      logits, lstride, nullptr, gparams, pstride, glogits, ids, uniform_id, B);
+      logits, lstride, nullptr, gparams, pstride, glogits, ids, uniform_id, B, host_ranges());
   EXP_CHECK_LAUNCH("exp_filter_regress_bwd");
   return EXP_OK;
 }
@@ -851,6 +906,7 @@ int exp_filter_fwd(const float* x, float* y, const float* params, int pstride, c
     return EXP_OK;
   }
   FilterArgs A{};
+  A.rg = host_ranges();
   A.x = x; A.out = y; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockFwd;
   A.logits = logits;
@@ -873,6 +929,7 @@ int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstr
   int rc = pick_vec(variant, P, x, y, nullptr, &vec);
   if (rc) return rc;
   ChainArgs A{};
+  A.rg = host_ranges();
   A.x = x; A.y = y; A.params = params; A.ids = ids; A.S = S; A.B = B; A.P = P; A.pstride = pstride;
   A.pix_per_block = kPixPerBlockFwd; A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
   dim3 grid((P + kPixPerBlockFwd - 1) / kPixPerBlockFwd, B);
@@ -927,6 +984,7 @@ int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* g
     vec = false;
   }
   ChainBwdArgs A{};
+  A.rg = host_ranges();
   A.x = x; A.gy = gy; A.y = y; A.gx = gx; A.params = params; A.ids = ids; A.gparams = gparams;
   A.counters = reinterpret_cast<unsigned*>(workspace);
   A.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes);
@@ -989,6 +1047,7 @@ int exp_filter_bwd(const float* x, const float* gy, float* gx, float* gparams, c
   }
   const int nblk = (P + kPixPerBlockBwd - 1) / kPixPerBlockBwd;
   FilterArgs A{};
+  A.rg = host_ranges();
   A.x = x; A.gy = gy; A.out = gx; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockBwd;
   A.logits = logits;
@@ -1018,6 +1077,7 @@ int exp_filter_masked_fwd(const float* x, float* y, float* mask_out, const float
   if (!ids) EXP_CHECK_ARG(uniform_id >= 0 && uniform_id < EXP_NUM_FILTER_KINDS, "bad filter id %d", uniform_id);
   const int P = H * W;
   FilterArgs A{};
+  A.rg = host_ranges();
   A.x = x; A.out = y; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockFwd;
   A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
@@ -1062,6 +1122,7 @@ int exp_filter_masked_bwd(const float* x, const float* gy, float* gx, float* gpa
   if (rc) return rc;
   const int nblk = (P + kPixPerBlockBwd - 1) / kPixPerBlockBwd;
   FilterArgs A{};
+  A.rg = host_ranges();
   A.x = x; A.gy = gy; A.out = gx; A.params = params; A.pstride = pstride; A.ids = ids; A.P = P;
   A.pix_per_block = kPixPerBlockBwd;
   A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;

@@ -38,6 +38,7 @@ struct TmaArgs {
   unsigned* counters;     // [B]
   float* gparams;
   int logits;             // params are raw regressor logits (EXP_OPT_LOGITS)
+  FilterRanges rg;        // cfg-driven regressor ranges (exp_set_filter_ranges)
 };
 
 // Balanced static partition of the flat tile sequence: CTA i owns [floor(i*total/grid),
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kTmaThreads) filter_step_tma_kernel(const TmaA
         if (cur_b >= 0) tma_flush<FID>(acc, A, sc, red, tot, &ticket, cur_b);
       }
       __syncthreads();                                 // everyone done with the old constants
-      if (tid < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits);
+      if (tid < 32) setup_consts(sc, A.params + (size_t)b * A.pstride, FID, A.logits, A.rg);
       __syncthreads();
       cur_b = b;
     }

@@ -11,18 +11,16 @@
 // [4,4,Cin,Cout], FC weights [in,out], flatten order (h*4+w)*256+c.
 #include "gemm_engine.cuh"
 #include "gemm_engine_v4.cuh"
-#include "nn_tc.h"
+#include "nn_internal.h"
 
 namespace expo {
 
 static int g_gemm_backend = kBackendAuto;
 int gemm_backend() { return g_gemm_backend; }
-// AUTO resolves per call: the TMA-fed tcgen05 engine for the convolutions it supports (channel
-// counts that are multiples of 32: 2-3x faster than CUDA cores, profiles/r1_layer_bench_tma.md),
-// the exact-fp32 CUDA-core engine for everything else.  The register-gather tcgen05 engines
-// (backends 2, 3) stay opt-in: they are slower than both.
-bool use_tcgen05() { return g_gemm_backend == kBackendTcgen05 || g_gemm_backend == kBackendTcgen05Ws; }
-bool use_tma() { return g_gemm_backend == kBackendTcgen05Tma || g_gemm_backend == kBackendAuto; }
+// 0 (default): the TMA-fed tcgen05 engine for every contraction it supports (channel counts that are
+// multiples of 32; the first layer through its staging copy), the exact-fp32 CUDA-core engine for the rest.
+// 1: CUDA-core engine everywhere -- the A/B and bring-up switch of the tests, not a second product path.
+bool use_tma() { return g_gemm_backend == kBackendAuto; }
 
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
@@ -493,13 +491,6 @@ int exp_conv_fwd(const float* x, int Cx, const float* vec, int Cv, float shift, 
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_fwd[tma]: %s", cudaGetErrorString(e));
     return EXP_OK;
   }
-  if (use_tcgen05() && tc_conv_fwd_supported(Cout)) {
-    const cudaError_t e = tc_conv_fwd(x, Cx, vec, Cv, shift, W, bias, mask_ref, post_mul, y, y2, B, IH, IW, Cout, mode,
-                                      (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_fwd[tcgen05]: %s", cudaGetErrorString(e));
-    EXP_CHECK_LAUNCH("exp_conv_fwd[tcgen05]");
-    return EXP_OK;
-  }
   if (Cv == 0 && Cx % kBK4 == 0 && Cout % 4 == 0 && aligned16(x) && aligned16(W)) {   // 16-byte gathers
     // the deep layers have few output rows: prefer the narrow N tile while the 64-wide grid
     // would leave SMs idle (2 x 148 CTAs), A is simply re-gathered from L2 per N tile
@@ -537,12 +528,6 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[tma]: %s", cudaGetErrorString(e));
     return EXP_OK;
   }
-  if (use_tcgen05() && tc_conv_dgrad_supported(Cout) && aligned16(dy) && aligned16(W)) {
-    const cudaError_t e = tc_conv_dgrad(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[tcgen05]: %s", cudaGetErrorString(e));
-    EXP_CHECK_LAUNCH("exp_conv_dgrad[tcgen05]");
-    return EXP_OK;
-  }
   if (Cout % kBK4 == 0 && aligned16(dy) && aligned16(W)) {                             // 16-byte gathers
     const bool narrow = Cin <= 32 || 4 * ((M + kBM - 1) / kBM) * ((Cin + 63) / 64) < 296;
     if (narrow) launch_gemm_v4<ConvDgrad, 32, false, true>(p, M, Cin, 4, (cudaStream_t)stream);
@@ -555,9 +540,8 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
 
 size_t exp_conv_wgrad_workspace_bytes(int B, int IH, int IW, int Cin, int Cout) {
   if (B <= 0 || IH < 2 || IW < 2 || Cin <= 0 || Cout <= 0) return 0;
-  const int a = wgrad_splits(B, IH / 2, IW / 2, Cin, Cout), b = tc_wgrad_splits(B, IH / 2, IW / 2, Cin, Cout);
-  const int c = tma_wgrad_splits(B, IH / 2, IW / 2, Cin, Cout);
-  const int m = a > b ? (a > c ? a : c) : (b > c ? b : c);
+  const int a = wgrad_splits(B, IH / 2, IW / 2, Cin, Cout), c = tma_wgrad_splits(B, IH / 2, IW / 2, Cin, Cout);
+  const int m = a > c ? a : c;
   return (size_t)m * 16 * Cin * Cout * sizeof(float);
 }
 
@@ -567,27 +551,14 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
   EXP_CHECK_ARG(B > 0 && is_pow2(IH) && is_pow2(IW) && IH >= 2 && IW >= 2, "IH/IW must be powers of two >= 2");
   EXP_CHECK_ARG(Cx > 0 && Cv >= 0 && (Cv == 0 || vec) && Cout > 0, "bad channel counts");
   const int Cin = Cx + Cv, OH = IH / 2, OW = IW / 2;
-  const bool tcg = use_tcgen05();
   const bool tmab = use_tma() && tma_conv_wgrad_supported(x, Cx, Cv, shift, dy, Cout) && aligned16(workspace);
-  const int splits = tmab ? tma_wgrad_splits(B, OH, OW, Cin, Cout)
-                          : (tcg ? tc_wgrad_splits(B, OH, OW, Cin, Cout) : wgrad_splits(B, OH, OW, Cin, Cout));
+  const int splits = tmab ? tma_wgrad_splits(B, OH, OW, Cin, Cout) : wgrad_splits(B, OH, OW, Cin, Cout);
   const size_t need = (size_t)splits * 16 * Cin * Cout * sizeof(float);
   if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
   if (tmab) {
     const cudaError_t e = tma_conv_wgrad_partials(x, Cx, dy, reinterpret_cast<float*>(workspace), B, IH, IW, Cout, splits,
                                                   (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_wgrad[tma]: %s", cudaGetErrorString(e));
-    const size_t cnt = (size_t)16 * Cin * Cout;
-    launch_pdl(splitk_reduce_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
-        reinterpret_cast<float*>(workspace), splits, cnt, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
-    EXP_CHECK_LAUNCH("exp_conv_wgrad[reduce]");
-    return EXP_OK;
-  }
-  if (tcg) {
-    const cudaError_t e = tc_conv_wgrad_partials(x, Cx, vec, Cv, shift, dy, reinterpret_cast<float*>(workspace), B, IH, IW,
-                                                 Cout, splits, (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_wgrad[tcgen05]: %s", cudaGetErrorString(e));
-    EXP_CHECK_LAUNCH("exp_conv_wgrad[tcgen05]");
     const size_t cnt = (size_t)16 * Cin * Cout;
     launch_pdl(splitk_reduce_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         reinterpret_cast<float*>(workspace), splits, cnt, Cout, nullptr, nullptr, 0, 3, gW, Cout, accumulate);
@@ -617,13 +588,12 @@ int exp_conv_wgrad(const float* x, int Cx, const float* vec, int Cv, float shift
 
 size_t exp_fc_workspace_bytes(int M, int K, int N) {
   if (M <= 0 || K <= 0 || N <= 0) return 0;
-  const int a = fc_splits(M, K, N), b = tc_fc_splits(M, K, N);
-  return (size_t)(a > b ? a : b) * M * N * sizeof(float);
+  return (size_t)fc_splits(M, K, N) * M * N * sizeof(float);
 }
 
 int exp_set_gemm_backend(int backend) {
-  EXP_CHECK_ARG(backend >= kBackendAuto && backend <= kBackendTcgen05Tma,
-                "backend must be 0 (auto), 1 (cuda cores), 2 (tcgen05), 3 (tcgen05, warp-specialised) or 4 (tcgen05, TMA-fed)");
+  EXP_CHECK_ARG(backend == kBackendAuto || backend == kBackendSimt,
+                "backend must be 0 (TMA-fed tcgen05 where supported, default) or 1 (exact-fp32 CUDA cores everywhere)");
   g_gemm_backend = backend;
   return EXP_OK;
 }
@@ -633,21 +603,9 @@ int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const
   EXP_CHECK_ARG(x && W && y && workspace, "null pointer");
   EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "bad shape");
   EXP_CHECK_ARG(mode >= 0 && mode <= 3 && (mode != 1 || (mask_ref && ldmask >= N)), "bad mode");
-  const bool tcg = use_tcgen05() && N >= 16;
-  const int splits = tcg ? tc_fc_splits(M, K, N) : fc_splits(M, K, N);
+  const int splits = fc_splits(M, K, N);
   const size_t need = (size_t)splits * M * N * sizeof(float);
   if (workspace_bytes < need) return set_error(EXP_ERR_WORKSPACE, "workspace %zu B < required %zu B", workspace_bytes, need);
-  if (tcg) {
-    const cudaError_t e = tc_fc_fwd_partials(x, ldx, W, reinterpret_cast<float*>(workspace), M, K, N, splits,
-                                             (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_fc_fwd[tcgen05]: %s", cudaGetErrorString(e));
-    EXP_CHECK_LAUNCH("exp_fc_fwd[tcgen05]");
-    const size_t cnt = (size_t)M * N;
-    launch_pdl(splitk_reduce_kernel, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
-        reinterpret_cast<float*>(workspace), splits, cnt, N, bias, mask_ref, ldmask, mode, y, ldy, 0);
-    EXP_CHECK_LAUNCH("exp_fc_fwd[reduce]");
-    return EXP_OK;
-  }
   FcFwd p{};
   p.x = x; p.W = W; p.part = reinterpret_cast<float*>(workspace); p.M = M; p.K = K; p.N = N; p.ldx = ldx;
   int kps = (K + splits - 1) / splits;
@@ -671,13 +629,6 @@ int exp_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act,
   FcDgrad p{};
   p.dy = dy; p.W = W; p.mul_act = mul_act; p.mul_plain = mul_plain; p.dx = dx; p.M = M; p.K = K; p.N = N;
   p.ldy = ldy; p.lddx = lddx; p.ldmul = ldmul; p.accumulate = accumulate;
-  if (use_tcgen05() && K >= 16) {
-    const cudaError_t e = tc_fc_dgrad(dy, ldy, W, mul_act, mul_plain, ldmul, dx, lddx, M, K, N, accumulate,
-                                      (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_fc_dgrad[tcgen05]: %s", cudaGetErrorString(e));
-    EXP_CHECK_LAUNCH("exp_fc_dgrad[tcgen05]");
-    return EXP_OK;
-  }
   launch_gemm<FcDgrad, 64, false, true>(p, M, K, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_dgrad");
   return EXP_OK;
@@ -689,12 +640,6 @@ int exp_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, i
   EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "bad shape");
   FcWgrad p{};
   p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N; p.ldx = ldx; p.ldy = ldy; p.accumulate = accumulate;
-  if (use_tcgen05() && N >= 16) {
-    const cudaError_t e = tc_fc_wgrad(x, ldx, dy, ldy, gW, M, K, N, accumulate, (cudaStream_t)stream);
-    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_fc_wgrad[tcgen05]: %s", cudaGetErrorString(e));
-    EXP_CHECK_LAUNCH("exp_fc_wgrad[tcgen05]");
-    return EXP_OK;
-  }
   if (N <= 32) launch_gemm<FcWgrad, 32, true, false>(p, K, N, 1, (cudaStream_t)stream);
   else launch_gemm<FcWgrad, 64, true, false>(p, K, N, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_wgrad");

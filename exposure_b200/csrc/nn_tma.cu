@@ -18,7 +18,7 @@
 #include <mutex>
 
 #include "common.cuh"
-#include "nn_tc.h"
+#include "nn_internal.h"
 #include "tc_engine_tma_persistent.cuh"
 
 namespace expo {

@@ -32,7 +32,7 @@
 
 #include <cstdlib>
 
-#include "tc_engine.cuh"
+#include "tcgen05_ptx.cuh"
 
 namespace expo {
 namespace tma {

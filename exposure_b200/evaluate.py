@@ -34,7 +34,9 @@ def retouch(trainer, high_res, generator=None, steps=None, fused=True, trace=Fal
   cfg = trainer.cfg
   B = high_res.shape[0]
   dev = high_res.device
-  S = steps or cfg.test_steps
+  # net.py:796-820 loops cfg.test_steps times and breaks at the first step whose new state is STOPPED; every image
+  # of a batch stops at the same step (step + 1 == cfg.test_steps, agent.py:210-218), so more steps are never run
+  S = min(steps or cfg.test_steps, cfg.test_steps)
   thumb = center_thumbnail(high_res, cfg.source_img_size)
   states = torch.zeros(B, cfg.num_state_dim, device=dev)
   masking = bool(getattr(cfg, "masking", False))
@@ -63,7 +65,7 @@ def retouch(trainer, high_res, generator=None, steps=None, fused=True, trace=Fal
     out = high_res.contiguous()
     for s in range(S):
       out = ops.filter_masked_fwd(out, logits[s], mask_logits[s], ids[s], float(cfg.maximum_sharpness),
-                                  float(cfg.minimum_strength), True, out=torch.zeros_like(out), logits=True)
+                                  float(cfg.minimum_strength), True, logits=True)
       intermediate.append(out)
   elif fused and not trace:
     out = ops.filter_chain_fwd(high_res.contiguous(), logits, ids, logits=True)
@@ -85,7 +87,10 @@ def load_linear_image(path):
   jpg/png (sRGB: x^2.2 then / (2 max), net.py:739-747) into a float32 HxWx3 RGB array."""
   import cv2
   import numpy as np
-  img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+  # net.py:731-747: tiffs through util.read_tiff16 (full bit depth), every other format through the default
+  # cv2.imread(fn) = 8-bit 3-channel BGR (a 16-bit png is reduced to 8 bit first, like the reference)
+  is_tiff = path.lower().endswith((".tif", ".tiff"))
+  img = cv2.imread(path, cv2.IMREAD_UNCHANGED) if is_tiff else cv2.imread(path)
   if img is None:
     raise IOError("cannot read %s" % path)
   if img.ndim == 2:
@@ -93,7 +98,7 @@ def load_linear_image(path):
   img = img[:, :, :3][:, :, ::-1]
   depth = 16 if img.dtype == np.uint16 else 8
   img = img.astype(np.float32) * (1.0 / (2 ** depth - 1))          # util.read_tiff16
-  if path.lower().endswith((".tif", ".tiff")):
+  if is_tiff:
     return np.power(img, 1.8).astype(np.float32)
   lin = np.power(img, 2.2)
   return (lin / (2 * lin.max())).astype(np.float32)

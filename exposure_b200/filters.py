@@ -10,6 +10,7 @@ Parameter shapes follow the reference: `[B,1]` (E, G, S+, Ct, BW), `[B,3]` (W),
 `[B,1,1,1,8]` (T), `[B,1,1,3,8]` (C)."""
 import torch
 
+from . import _cabi
 from . import nn_ops as K
 from . import ops
 
@@ -22,6 +23,9 @@ class Filter:
 
   def __init__(self, net, cfg):
     self.cfg = cfg
+    # filters.py:179, 202, 261, 309 read cfg.exposure_range / gamma_range / color_curve_range /
+    # tone_curve_range / curve_steps: handed to the library (process-wide, like the reference's one cfg)
+    _cabi.set_filter_ranges(cfg)
     self.height, self.width, self.channels = list(map(int, net.shape[1:]))
     self.num_filter_parameters = None
     self.short_name = None
@@ -61,13 +65,24 @@ class Filter:
   def _param_shape(self, p):
     return p
 
-  def process(self, img, param):
-    """Whole-image filter, no masking (filters.py `process`).  img [B,H,W,3]."""
+  def _flat_params(self, img, param):
+    """[Bp, ...] parameter in the reference's shape -> [B, 24]; Bp == 1 broadcasts over the batch like the
+    reference's `param[:, None, None, :]` (filters.py:62-99 with specified_parameter), anything else must match."""
     B = img.shape[0]
-    flat = param.reshape(B, -1)
+    flat = param.reshape(param.shape[0], -1)
+    if flat.shape[0] != B:
+      if flat.shape[0] != 1:
+        raise ValueError("parameter batch %d does not match image batch %d" % (flat.shape[0], B))
+      flat = flat.expand(B, flat.shape[1])
+    if flat.shape[1] > ops.PSTRIDE:
+      raise ValueError("at most %d parameters per image, got %d" % (ops.PSTRIDE, flat.shape[1]))
     if flat.shape[1] != ops.PSTRIDE:
       flat = torch.nn.functional.pad(flat, (0, ops.PSTRIDE - flat.shape[1]))
-    return ops.FilterProcessFn.apply(img.contiguous(), flat.contiguous(), self.filter_id)
+    return flat.contiguous()
+
+  def process(self, img, param):
+    """Whole-image filter, no masking (filters.py `process`).  img [B,H,W,3]."""
+    return ops.FilterProcessFn.apply(img.contiguous(), self._flat_params(img, param), self.filter_id)
 
   def debug_info_batched(self):
     return False
@@ -111,13 +126,11 @@ class Filter:
     if not self._masks_pixels():
       return self.process(img, filter_parameters)
     B = img.shape[0]
-    flat = filter_parameters.reshape(B, -1)
-    if flat.shape[1] != ops.PSTRIDE:
-      flat = torch.nn.functional.pad(flat, (0, ops.PSTRIDE - flat.shape[1]))
+    flat = self._flat_params(img, filter_parameters)
     ml = mask_parameters.expand(B, mask_parameters.shape[1])
     if ml.shape[1] < ops.MASK_PARAMS:
       ml = torch.nn.functional.pad(ml, (0, ops.MASK_PARAMS - ml.shape[1]))
-    return ops.FilterMaskedFn.apply(img.contiguous(), flat.contiguous(), ml.contiguous(), self.filter_id,
+    return ops.FilterMaskedFn.apply(img.contiguous(), flat, ml.contiguous(), self.filter_id,
                                     float(self.cfg.maximum_sharpness), float(self.cfg.minimum_strength))
 
   def use_masking(self):
@@ -166,7 +179,6 @@ class ExposureFilter(Filter):          # filters.py:170-182
     Filter.__init__(self, net, cfg)
     self.short_name = "E"
     self.num_filter_parameters = 1
-    assert abs(cfg.exposure_range - 3.5) < 1e-9, "kernel constant: cfg.exposure_range == 3.5"
 
 
 class GammaFilter(Filter):             # filters.py:194-206
@@ -176,7 +188,6 @@ class GammaFilter(Filter):             # filters.py:194-206
     Filter.__init__(self, net, cfg)
     self.short_name = "G"
     self.num_filter_parameters = 1
-    assert cfg.gamma_range == 3, "kernel constant: cfg.gamma_range == 3"
 
 
 class ImprovedWhiteBalanceFilter(Filter):   # filters.py:215-238
@@ -206,7 +217,6 @@ class ToneFilter(Filter):              # filters.py:298-322
     self.curve_steps = cfg.curve_steps
     self.short_name = "T"
     self.num_filter_parameters = cfg.curve_steps
-    assert cfg.curve_steps == 8 and tuple(cfg.tone_curve_range) == (0.5, 2), "kernel constants"
 
   def _param_shape(self, p):
     return p.reshape(-1, 1, self.cfg.curve_steps)[:, None, None, :]
@@ -239,7 +249,6 @@ class ColorFilter(Filter):             # filters.py:247-273
     self.channels = int(net.shape[3])
     self.short_name = "C"
     self.num_filter_parameters = self.channels * cfg.curve_steps
-    assert cfg.curve_steps == 8 and tuple(cfg.color_curve_range) == (0.90, 1.10), "kernel constants"
 
   def _param_shape(self, p):
     return p.reshape(-1, self.channels, self.cfg.curve_steps)[:, None, None, :]

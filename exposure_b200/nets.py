@@ -320,7 +320,8 @@ class PolicyNet:
     # action selection (agent.py:100-122)
     c.pdf, c.ids, c.surrogate, c.entropy, c.pen_head, c.new_states = K.policy_head_fwd(
         c.sel_logits, noise, states, is_train, progress, cfg)
-    # only the selected filter is evaluated (agent.py:124-125 computes all 8 and one-hot sums)
+    # only the selected filter is evaluated (agent.py:124-125 computes all 8 and one-hot sums); an id of -1
+    # (pdf_sample with u == 0: all-zero one-hot row) makes the step kernels write a black image themselves
     safe = c.ids.clamp(min=0).long()
     c.logits_sel = c.O[torch.arange(B, device=img.device), safe][:, :F.PSTRIDE].contiguous()
     c.params = F.filter_regress_fwd(c.logits_sel, c.ids)
@@ -335,10 +336,9 @@ class PolicyNet:
       c.mask_idx = self._n_of_id[safe][:, None] + torch.arange(MASK_PARAMS, device=img.device)[None, :]
       c.mask_logits_sel = torch.gather(c.O[torch.arange(B, device=img.device), safe], 1, c.mask_idx).contiguous()
       c.mask_cfg = (float(cfg.maximum_sharpness), float(cfg.minimum_strength))
-      c.out = F.filter_masked_fwd(img, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True, out=torch.zeros_like(img))
+      c.out = F.filter_masked_fwd(img, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True)
       if high_res is not None:
-        c.high_res_out = F.filter_masked_fwd(high_res, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True,
-                                             out=torch.zeros_like(high_res))
+        c.high_res_out = F.filter_masked_fwd(high_res, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True)
     c.pen_img = K.overexposure_fwd(c.out)
     c.penalty = c.pen_img + c.pen_head
     return c

@@ -129,7 +129,7 @@ def _n(k=1):
 def _conv1_path(Cx, Cv, Cout):
   """First-layer tensor-core path (staging copy + padded weights, exp_conv1_*): used by the AUTO and
   TMA backends for inputs the generic TMA path cannot take (state channels / Cin not a multiple of 32)."""
-  if _backend not in (BACKEND_AUTO, BACKEND_TCGEN05_TMA):
+  if _backend != BACKEND_AUTO:
     return False
   if Cv == 0 and Cx % 32 == 0:
     return False
@@ -139,7 +139,7 @@ def _conv1_path(Cx, Cv, Cout):
 def _enrich32_path(Cx, Cv, Cout):
   """16 < Cin <= 32 (value network, 17 channels): enrich to 32 channels, pad the weights, then the
   generic TMA path (exp_conv_enrich32 / exp_conv_pad_weights32)."""
-  if _backend not in (BACKEND_AUTO, BACKEND_TCGEN05_TMA):
+  if _backend != BACKEND_AUTO:
     return False
   Cin = Cx + Cv
   return (Cv > 0 or Cx % 32 != 0) and 16 < Cin <= 32 and Cout % 32 == 0
@@ -462,7 +462,10 @@ def adam(params, grads, m, v, hyper, beta1, beta2, eps=1e-8, grad_scale=1.0):
   _n()
 
 
-BACKEND_AUTO, BACKEND_CUDA_CORES, BACKEND_TCGEN05, BACKEND_TCGEN05_WS, BACKEND_TCGEN05_TMA = 0, 1, 2, 3, 4
+# 0 = TMA-fed tcgen05 engine wherever the shape allows it (the product path); 1 = exact-fp32 CUDA-core engine
+# everywhere (the tests' A/B switch).  BACKEND_TCGEN05_TMA is the old name of 0.
+BACKEND_AUTO, BACKEND_CUDA_CORES = 0, 1
+BACKEND_TCGEN05_TMA = BACKEND_AUTO
 _backend = int(os.environ.get("EXPOSURE_GEMM_BACKEND") or 0)     # mirrors _cabi.lib()'s initial setting
 
 

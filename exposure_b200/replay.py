@@ -49,6 +49,7 @@ class ReplayMemory:
     self.image_pool = []                 # slot ids, in the reference's list order
     self.step = [0] * cap                # host mirror of states[:, STATE_STEP_DIM]
     self.stopped = [False] * cap         # host mirror of states[:, STATE_STOPPED_DIM]
+    self._outstanding = []               # slots handed out by get_next_fake_batch and not yet replaced
     self.fill_pool()
 
   def _idx(self, slots):
@@ -71,6 +72,11 @@ class ReplayMemory:
     self.image_pool = self.image_pool[:self.target_pool_size]
 
   def get_next_fake_batch(self, batch_size):     # replay_memory.py:230-246
+    # the reference's records simply leave the pool here; a caller that never hands them back through
+    # replace_memory (an eval / bench loop) must not leak their slots
+    if self._outstanding:
+      self._release(self._outstanding)
+      self._outstanding = []
     self.rng.shuffle(self.image_pool)
     batch = []
     while len(batch) < batch_size:
@@ -82,10 +88,14 @@ class ReplayMemory:
       else:
         self._release([slot])            # finished images are dropped here
     idx = self._idx(batch)
+    self._outstanding = list(batch)
     return self.images.index_select(0, idx), self.states.index_select(0, idx), batch
 
   def replace_memory(self, new_images, new_states, old_slots):    # replay_memory.py:187-196
     """new_images / new_states: device outputs of the generator step for the records `old_slots`."""
+    if sorted(old_slots) != sorted(self._outstanding):
+      raise ValueError("replace_memory() takes the slots of the most recent get_next_fake_batch()")
+    self._outstanding = []
     self.rng.shuffle(self.image_pool)
     keep_rows, keep_slots = [], []
     for row, slot in enumerate(old_slots):

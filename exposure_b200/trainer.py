@@ -47,6 +47,8 @@ class Trainer:
   def __init__(self, cfg=None, device=None, seed=0):
     self.cfg = cfg or default_cfg()
     self._check_cfg(self.cfg)
+    from . import _cabi
+    _cabi.set_filter_ranges(self.cfg)      # cfg.exposure_range / gamma_range / *_curve_range -> the kernels' regressors
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.gen = ParamStore(self.device)
     self.policy = PolicyNet(self.gen, n_states=self.cfg.num_state_dim, scope="generator")
@@ -86,6 +88,21 @@ class Trainer:
       unsupported.append("cfg.img_include_states == False (util.py:31-36)")
     if g("gradient_penalty_lambda", 10) <= 0:
       unsupported.append("cfg.gradient_penalty_lambda <= 0 (weight clamping, net.py:252-264)")
+    # the explicit schedules of nets.py are laid out for the shipped filter list and network sizes: the action
+    # index -> kernel id mapping, the fc2 widths and the state vector all follow cfg.filters (agent.py:43-59,
+    # util.py:13-16), so anything else is refused instead of silently training the shipped configuration
+    from . import filters as _f
+    if "filters" in cfg:
+      ids = [_f.FILTER_IDS.get(c, None) for c in cfg["filters"]]
+      if ids != list(range(8)):
+        unsupported.append("cfg.filters must be the shipped list [Exposure, Gamma, ImprovedWhiteBalance, SaturationPlus, Tone, "
+                           "Contrast, WNB, Color] in that order (config_example.py:22-25); got kernel ids %s" % ids)
+      if g("num_state_dim", 3 + len(ids)) != 3 + len(ids):
+        unsupported.append("cfg.num_state_dim must be 3 + len(cfg.filters) (config_example.py:63)")
+    for key, want in (("base_channels", 32), ("fc1_size", 128), ("feature_extractor_dims", 4096), ("source_img_size", 64),
+                      ("real_img_size", 64), ("curve_steps", 8), ("dropout_keep_prob", None)):
+      if want is not None and g(key, want) != want:
+        unsupported.append("cfg.%s == %r (the kernels and schedules are built for %r)" % (key, cfg[key], want))
     if unsupported:
       raise NotImplementedError("exposure_b200 implements the shipped configuration of the hot path only; unsupported: "
                                 + "; ".join(unsupported))

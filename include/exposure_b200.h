@@ -75,6 +75,25 @@ enum {
 int exp_version(void);               /* ABI version, currently 1                       */
 const char* exp_last_error(void);    /* thread-local message of the last failure       */
 int exp_num_filter_params(int filter_id); /* n of the table above, or EXP_ERR_INVALID_ARG */
+
+/* cfg-driven ranges of the filter_param_regressors.  Replaces the cfg reads of filters.py:179
+ * (cfg.exposure_range), :202 (cfg.gamma_range), :261 (cfg.color_curve_range, tanh_range(..., initial=1)) and
+ * :309 (cfg.tone_curve_range).  Process-wide host state (the reference has ONE global cfg, util.load_config
+ * util.py:326-329); every later launch carries a copy by value, so launches already enqueued or captured in a
+ * CUDA graph keep the ranges they were launched with.  r == NULL restores the defaults of
+ * config_example.py:27-33: 3.5, 3, (0.5, 2), (0.90, 1.10).  `curve_steps` is cfg.curve_steps
+ * (config_example.py:27): the curve kernels are built for EXP_CURVE_STEPS knots, anything else returns
+ * EXP_ERR_UNSUPPORTED instead of training a different curve.  (ImprovedWhiteBalanceFilter's range is the literal
+ * 0.5 of filters.py:224 -- cfg.wb_range is never read by the reference.) */
+#define EXP_CURVE_STEPS 8
+typedef struct {
+  float exposure_range;       /* p = tanh_range(-r, r)            */
+  float gamma_range;          /* gamma = exp(tanh_range(-ln g, ln g)) */
+  float tone_lo, tone_hi;     /* cfg.tone_curve_range             */
+  float color_lo, color_hi;   /* cfg.color_curve_range, must contain 1 */
+} exp_filter_ranges;
+int exp_set_filter_ranges(const exp_filter_ranges* ranges, int curve_steps);
+int exp_get_filter_ranges(exp_filter_ranges* ranges);
 /* Programmatic dependent launch (process-wide; default OFF, environment EXPOSURE_PDL=1 turns it on):
  * the library's kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, so that
  * on a stream -- and inside a CUDA graph captured from it -- a kernel's prologue overlaps the tail of
@@ -101,7 +120,9 @@ int exp_filter_regress_bwd(const float* logits, int lstride, const float* gparam
  * mask == ones(1,1,1,1)).  Also replaces the stack / one_hot / reduce_sum select of
  * agent.py:77,118-129 (only the selected filter is evaluated per image).
  * x, y: [B,H,W,3] fp32, 16-byte aligned for the DIRECT/TMA variants (else SCALAR).
- * x == y (in place) is allowed.  Algorithmic HBM traffic: 24 B / pixel. */
+ * x == y (in place) is allowed.  Algorithmic HBM traffic: 24 B / pixel.
+ * ids[b] == -1 (pdf_sample's u == 0 quirk, pdf_sample_layer.py:5-10: an all-zero one-hot row) writes a BLACK
+ * image y[b] = 0, and exp_filter_bwd writes gx[b] = 0, gparams[b, :] = 0: output buffers may be uninitialised. */
 int exp_filter_fwd(const float* x, float* y, const float* params, int pstride,
                    const int* ids, int uniform_id, int B, int H, int W, int options,
                    void* stream);
@@ -194,12 +215,10 @@ int exp_filter_masked_bwd(const float* x, const float* gy, float* gx, float* gpa
  * of the stored output (1, 0.2, or 0.6 at exactly 0).
  * ==================================================================================== */
 
-/* GEMM backend of the conv / FC primitives: 0 = auto, 1 = exact-fp32 CUDA-core engine,
- * 2 = tcgen05 tensor cores (kind::tf32 with 3xTF32 split accumulation, accumulators in TMEM)
- * for the primitives that have a tensor-core instantiation, 3 = the same with warp-specialised
- * producer / MMA-issuer roles, 4 = TMA-fed tcgen05 (im2col boxes by cp.async.bulk.tensor; the
- * convolutions whose channel counts are multiples of 32, the rest runs as backend 1).
- * Process-wide. */
+/* GEMM engine of the conv / FC primitives: 0 (default) = TMA-fed tcgen05 tensor cores (kind::tf32 with the
+ * 3xTF32 split, accumulators in TMEM; operands by cp.async.bulk.tensor im2col boxes) for every contraction
+ * whose shape the engine takes, the exact-fp32 CUDA-core engine for the rest; 1 = the CUDA-core engine
+ * everywhere (A/B switch of the tests).  Process-wide. */
 int exp_set_gemm_backend(int backend);
 
 /* y[B,IH/2,IW/2,Cout] = epi( conv4x4s2( concat(x[B,IH,IW,Cx], tile(vec[B,Cv])) - shift ) )

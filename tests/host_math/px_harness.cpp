@@ -48,11 +48,13 @@ static inline float warp_sum(float v) { return v; }
 
 using namespace expo;
 
+// regressor ranges the harness hands to setup_consts (hm_set_ranges; the kernels receive them as launch arguments)
+static FilterRanges g_hm_ranges = default_ranges();
 struct LaneArg { FilterConsts* sc; const float* prow; int fid, logits, lane; };
 static void* lane_main(void* p) {
   LaneArg* a = (LaneArg*)p;
   threadIdx.x = a->lane;
-  setup_consts(*a->sc, a->prow, a->fid, a->logits);
+  setup_consts(*a->sc, a->prow, a->fid, a->logits, g_hm_ranges);
   return nullptr;
 }
 static void host_setup(FilterConsts& sc, const float* prow, int fid, int logits) {
@@ -160,6 +162,17 @@ static void mbwd_t(const float* x, const float* gy, float* gx, float* gparams, f
   }
 
 extern "C" {
+// same arithmetic as exp_set_filter_ranges (csrc/filters.cu); exposure_range <= 0 restores the defaults
+void hm_set_ranges(float exposure_range, float gamma_range, float tone_lo, float tone_hi, float color_lo, float color_hi) {
+  if (exposure_range <= 0.f) { g_hm_ranges = default_ranges(); return; }
+  FilterRanges g;
+  g.exposure = exposure_range;
+  g.gamma_log = (float)log((double)gamma_range);
+  g.tone_lo = tone_lo; g.tone_hi = tone_hi; g.color_lo = color_lo; g.color_hi = color_hi;
+  g.color_bias = (float)atanh(2.0 * (1.0 - (double)color_lo) / ((double)color_hi - (double)color_lo) - 1.0);
+  if (fabsf(g.color_bias) < 1e-7f) g.color_bias = 0.f;
+  g_hm_ranges = g;
+}
 int hm_fwd(int fid, const float* x, float* y, const float* params, int pstride, int B, int P, int logits) {
 #define C_(F) fwd_t<F>(x, y, params, pstride, B, P, logits)
   DISPATCH(fid, C_)

@@ -88,3 +88,98 @@ def test_masking_level_and_vignet_through_the_registry(built_lib):
   # the `specified_parameter` branch asserts masking is off, like the reference (filters.py:72)
   with pytest.raises(AssertionError):
     FL.ExposureFilter(net, cfg).apply(net, specified_parameter=torch.zeros(B, 1).cuda())
+
+
+def test_cfg_ranges_reach_the_kernels(built_lib, monkeypatch):
+  """cfg.exposure_range / gamma_range / tone_curve_range / color_curve_range are read like the reference reads
+  them (filters.py:179, 202, 261, 309), not asserted equal to baked constants: a cfg with other ranges goes
+  through the registry and through the fused regressor of the step kernels (EXP_OPT_LOGITS)."""
+  from exposure_b200 import _cabi, ops
+  from exposure_b200 import filters as FL
+  from exposure_b200.trainer import default_cfg
+  cfg = default_cfg()
+  cfg.exposure_range = 2.0; cfg.gamma_range = 2.5; cfg.tone_curve_range = (0.25, 3.0); cfg.color_curve_range = (0.8, 1.3)
+  monkeypatch.setattr(OF, "EXPOSURE_RANGE", 2.0)
+  monkeypatch.setattr(OF, "GAMMA_RANGE", 2.5)
+  monkeypatch.setattr(OF, "TONE_CURVE_RANGE", (0.25, 3.0))
+  monkeypatch.setattr(OF, "COLOR_CURVE_RANGE", (0.8, 1.3))
+  B = 4
+  net = OF.synth_images(B, 32, 32, seed=12).cuda()
+  try:
+    for cls, j in ((FL.ExposureFilter, OF.E), (FL.GammaFilter, OF.G), (FL.ToneFilter, OF.T), (FL.ColorFilter, OF.C)):
+      f = cls(net, cfg)
+      logits = OF.synth_logits(j, B).cuda().requires_grad_(True)
+      param = f.filter_param_regressor(logits)
+      ref_p = OF.regress(j, logits.detach().cpu())
+      assert torch.allclose(param.detach().cpu().reshape(B, -1), ref_p, rtol=3e-6, atol=1e-7), j
+      low, _, _ = f.apply(net, specified_parameter=param)
+      ref = OF.process(j, net.cpu(), ref_p)
+      assert ((low.detach().cpu() - ref).abs() <= 1e-5 * ref.abs().clamp_min(1e-4)).all(), j
+      low.sum().backward()
+      gl = OF.regress_bwd(j, logits.detach().cpu().double(),
+                          OF.process_bwd_analytic(j, net.cpu().double(), ref_p.double(), torch.ones(B, 32, 32, 3, dtype=torch.float64))[1])
+      assert torch.allclose(logits.grad.cpu().double(), gl, rtol=2e-3, atol=2e-3 * float(gl.abs().max()) + 1e-9), j
+      # fused regressor inside the step kernels (the chain / train path)
+      lg = torch.zeros(B, ops.PSTRIDE, device="cuda"); lg[:, :logits.shape[1]] = logits.detach()
+      y = ops.filter_fwd(net, lg, j, logits=True)
+      assert ((y.cpu() - ref).abs() <= 1e-5 * ref.abs().clamp_min(1e-4)).all(), j
+      _, glk = ops.filter_bwd(net, torch.ones_like(net), lg, j, need_gx=False, logits=True)
+      assert torch.allclose(glk[:, :logits.shape[1]].cpu().double(), gl, rtol=2e-3, atol=2e-3 * float(gl.abs().max()) + 1e-9), j
+  finally:
+    _cabi.set_filter_ranges(None)
+
+
+def test_specified_parameter_of_batch_one_broadcasts(built_lib):
+  """apply(specified_parameter=[1, n]) broadcasts over the batch like the reference's
+  param[:, None, None, :] (filters.py:62-99); a mismatching batch raises instead of being reinterpreted."""
+  from exposure_b200 import filters as FL
+  from exposure_b200.trainer import default_cfg
+  cfg = default_cfg()
+  B = 4
+  net = OF.synth_images(B, 16, 16, seed=3).cuda()
+  f = FL.ToneFilter(net, cfg)
+  p1 = f.filter_param_regressor(OF.synth_logits(OF.T, 1).cuda())          # [1,1,1,1,8]
+  low, _, _ = f.apply(net, specified_parameter=p1)
+  ref = OF.process(OF.T, net.cpu(), p1.reshape(1, 8).cpu().expand(B, 8))
+  assert torch.allclose(low.cpu(), ref, rtol=1e-5, atol=1e-7)
+  p2 = f.filter_param_regressor(OF.synth_logits(OF.T, 2).cuda())
+  with pytest.raises(ValueError, match="batch"):
+    f.apply(net, specified_parameter=p2)
+
+
+def test_unselected_rows_are_black_without_prezeroing(built_lib):
+  """pdf_sample yields id -1 when the uniform draw is exactly 0 (pdf_sample_layer.py:5-10: all-zero
+  one-hot row -> the reference's one-hot sum is a black image).  The step kernels write those zeros themselves:
+  poisoned (NaN) output buffers come back clean, forward and backward, plain and masked."""
+  from exposure_b200 import ops
+  B, H, W = 6, 16, 16
+  x = OF.synth_images(B, H, W, seed=8).cuda()
+  ids = torch.tensor([0, -1, 4, -1, 7, 3], dtype=torch.int32, device="cuda")
+  params = torch.zeros(B, ops.PSTRIDE, device="cuda")
+  for j in (0, 2, 4, 5):
+    params[j] = ops.filter_regress_fwd(torch.zeros(1, ops.PSTRIDE, device="cuda"), int(ids[j]))[0]
+  nan = lambda *s: torch.full(s, float("nan"), device="cuda")
+  y = ops.filter_fwd(x, params, ids, out=nan(B, H, W, 3))
+  assert torch.isfinite(y).all() and float(y[1].abs().max()) == 0.0 and float(y[3].abs().max()) == 0.0
+  assert float(y[0].abs().max()) > 0
+  gx, gp = ops.filter_bwd(x, torch.ones_like(x), params, ids, gx_out=nan(B, H, W, 3), gparams_out=nan(B, ops.PSTRIDE))
+  assert torch.isfinite(gx).all() and float(gx[1].abs().max()) == 0.0 and float(gp[1].abs().max()) == 0.0
+  assert torch.isfinite(gp[[1, 3]]).all()
+  ym = ops.filter_masked_fwd(x, params, torch.zeros(B, 6, device="cuda"), ids, out=nan(B, H, W, 3))
+  assert torch.isfinite(ym).all() and float(ym[3].abs().max()) == 0.0
+
+
+def test_policy_forward_with_zero_noise_is_black_not_garbage(built_lib):
+  """The same quirk through PolicyNet.forward (agent.py:113-125): noise == 0 -> id -1 -> out row == 0."""
+  from exposure_b200.trainer import Trainer
+  t = Trainer(device=torch.device("cuda", 0), seed=0)
+  B = 4
+  img = OF.synth_images(B, 64, 64, seed=9).cuda()
+  states = torch.zeros(B, 11, device="cuda")
+  noise, drop_f, drop_s, _ = t.draw(B, torch.Generator(device="cuda").manual_seed(1))
+  noise[2] = 0.0
+  # poison the caching allocator's free blocks so that an unwritten output would show
+  junk = torch.full((B, 64, 64, 3), float("nan"), device="cuda"); del junk
+  c = t.policy.forward(img, states, noise, drop_f, drop_s, 1, 0.1, t.cfg)
+  assert int(c.ids[2]) == -1
+  assert torch.isfinite(c.out).all() and float(c.out[2].abs().max()) == 0.0

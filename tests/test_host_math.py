@@ -92,6 +92,48 @@ def test_backward_math(hm, fid):
   assert (eg <= 2e-4 * scale).all(), (fid, float((eg / scale).max()))
 
 
+@pytest.mark.parametrize("fid", [F.E, F.G, F.T, F.C])
+def test_cfg_driven_ranges_math(hm, fid, monkeypatch):
+  """cfg.exposure_range / gamma_range / tone_curve_range / color_curve_range (filters.py:179, 202, 261, 309) are
+  launch arguments of the kernels, not baked constants: non-default ranges -- incl. a colour range that is NOT
+  centred on its initial value 1, so util.tanh_range's bias is non-zero -- forward and backward vs the oracle."""
+  rng = dict(exposure_range=2.0, gamma_range=2.5, tone=(0.25, 3.0), color=(0.8, 1.3))
+  monkeypatch.setattr(F, "EXPOSURE_RANGE", rng["exposure_range"])
+  monkeypatch.setattr(F, "GAMMA_RANGE", rng["gamma_range"])
+  monkeypatch.setattr(F, "TONE_CURVE_RANGE", rng["tone"])
+  monkeypatch.setattr(F, "COLOR_CURVE_RANGE", rng["color"])
+  hm.hm_set_ranges.argtypes = [ctypes.c_float] * 6
+  hm.hm_set_ranges(rng["exposure_range"], rng["gamma_range"], *rng["tone"], *rng["color"])
+  try:
+    B, H, W = 3, 13, 11
+    x = F.synth_images(B, H, W, seed=70 + fid)
+    lg = F.synth_logits(fid, B)
+    gy = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(17 + fid))
+    p32 = F.regress(fid, lg)
+    ref = F.process(fid, x, p32)
+    y = np.empty((B, H, W, 3), np.float32)
+    xs, gys, lgs = _np(x), _np(gy), _pad(lg)
+    assert hm.hm_fwd(fid, _p(xs), _p(y), _p(lgs), PS, B, H * W, 1) == 0
+    err = (torch.from_numpy(y) - ref).abs()
+    tol = _fwd_tol(fid, x, p32, ref)
+    assert (err <= tol).all(), "fid %d max err/tol %.3g" % (fid, float((err / tol).max()))
+    p64 = F.regress(fid, lg.double())
+    gx64, gp64 = F.process_bwd_analytic(fid, x.double(), p64, gy.double())
+    gl64 = F.regress_bwd(fid, lg.double(), gp64)
+    gx = np.empty((B, H, W, 3), np.float32)
+    gl = np.zeros((B, PS), np.float32)
+    assert hm.hm_bwd(fid, _p(xs), _p(gys), _p(gx), _p(gl), _p(lgs), PS, B, H * W, 1) == 0
+    n = F.NUM_PARAMS[fid]
+    eg = (torch.from_numpy(gl[:, :n]).double() - gl64).abs()
+    scale = gl64.abs().max(dim=1, keepdim=True).values.clamp_min(1e-6)
+    assert (eg <= 2e-4 * scale).all(), (fid, float((eg / scale).max()))
+    # and the ranges really changed the result
+    monkeypatch.undo()
+    assert not torch.allclose(F.regress(fid, lg), p32)
+  finally:
+    hm.hm_set_ranges(0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
+
+
 def test_curve_knot_ties_follow_tf_clip(hm):
   """x exactly on knots / outside [0,1]: both neighbouring segments pass on a knot, none outside."""
   vals = [-0.5, -0.0, 0.0, 0.125, 0.25, 0.5, 0.875, 1.0, 1.0000001, 1.5, 0.3, 0.999]

@@ -37,6 +37,8 @@ SIGNATURES = {
     "exp_filter_chain_fwd_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "exp_filter_chain_fwd_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
                                           _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_void_p]),
+    "exp_filter_chain_fwd_bwd_uniform": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
+                                                  _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_size_t, _c_int, _c_void_p]),
     "exp_filter_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "exp_filter_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
                                 _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_int, _c_void_p]),

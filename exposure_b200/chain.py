@@ -125,10 +125,15 @@ class FusedFilterChain:
 
   Regressor inputs and gradients use the kernel's native layout: one [N, B, 24] tensor each."""
 
-  def __init__(self, ids, batch, device):
-    """ids: list of N <= 8 entries, each an int (uniform) or a CUDA int32 tensor [B]."""
+  def __init__(self, ids, batch, device, static_chain=True):
+    """ids: list of N <= 8 entries, each an int (uniform) or a CUDA int32 tensor [B].  When every entry is an int
+    the chain is the same for all images: it runs through exp_filter_chain_fwd_bwd_uniform, which has compile-time
+    instantiations for known sequences (the cfg.filters order E,G,W,S+,T,Ct,BW,C); static_chain=False keeps the
+    run-time kernel (A/B switch)."""
     self.n = len(ids)
     self.nk = [ops.NUM_PARAMS_ALL[f] if isinstance(f, int) else ops.PSTRIDE for f in ids]
+    self.uniform = [int(f) for f in ids] if all(isinstance(f, int) for f in ids) else None
+    self.static_chain = static_chain
     self.ids = torch.empty(self.n, batch, dtype=torch.int32, device=device)
     for k, f in enumerate(ids):
       self.ids[k] = f if isinstance(f, int) else f.to(device=device, dtype=torch.int32)
@@ -144,8 +149,9 @@ class FusedFilterChain:
 
   def forward_backward(self, x, gout, need_output=True, need_input_grad=True, y_out=None, gx_out=None):
     """Returns (x_N or None, dL/dx_0 or None, dL/dlogits [N,B,24]) for the logits in self.logits."""
-    y, gx, gl = ops.filter_chain_fwd_bwd(x, gout, self.logits, self.ids, need_y=need_output, need_gx=need_input_grad,
-                                         logits=True, y_out=y_out, gx_out=gx_out, gparams_out=self.glogits)
+    y, gx, gl = ops.filter_chain_fwd_bwd(x, gout, self.logits, self.uniform if self.uniform is not None else self.ids,
+                                         need_y=need_output, need_gx=need_input_grad, logits=True, y_out=y_out,
+                                         gx_out=gx_out, gparams_out=self.glogits, static_chain=self.static_chain)
     return y, gx, gl
 
   def glogits_list(self):

@@ -147,7 +147,15 @@ __device__ __forceinline__ void setup_consts_lane(FilterConsts& sc, const float*
   if (logits) {
     if (t < EXP_MAX_FILTER_PARAMS) { sc.raw[t] = (t < n) ? prow[t] : 0.f; sc.p[t] = 0.f; }
     __syncwarp();
-    if (t == 0) regress_image<false>(fid, sc.raw, sc.p, nullptr, nullptr, rg);
+    if (fid == EXP_FILTER_TONE || fid == EXP_FILTER_COLOR) {      // 8 / 24 independent tanh_range: one lane each
+      if (t < n) {
+        float d;
+        sc.p[t] = fid == EXP_FILTER_TONE ? tanh_range_f(sc.raw[t], rg.tone_lo, rg.tone_hi, &d)
+                                         : tanh_range_f(sc.raw[t] + rg.color_bias, rg.color_lo, rg.color_hi, &d);
+      }
+    } else if (t == 0) {
+      regress_image<false>(fid, sc.raw, sc.p, nullptr, nullptr, rg);
+    }
   } else {
     if (t < EXP_MAX_FILTER_PARAMS) sc.p[t] = (t < n) ? prow[t] : 0.f;
   }
@@ -189,6 +197,50 @@ __device__ __forceinline__ void setup_consts(FilterConsts& sc, const float* __re
 }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+// ---- pow(xc, g) of GammaFilter as exp2(g * log2 xc), xc >= 1e-3 (filters.py:205-206) ------------------
+// log2 by exponent split: xc = m 2^e with m in [0.75, 1.5), log2 xc = e + lg2(m) with ONE MUFU.LG2 whose
+// absolute error on that interval is <= 2^-22 (CUDA C Programming Guide, __log2f on [0.5, 2]); together with
+// the rounding of the sum the error of the logarithm is <= 7.2e-7 for |log2 xc| < 16, i.e. a relative error of
+// the power of <= ln2 * g * 7.2e-7 <= 1.5e-6 at g = 3 -- the same class as log2f's 1 ulp (9.5e-7 at |L| >= 8)
+// at a third of its instructions (log2f is a ~20-instruction software polynomial).  exp2 is MUFU.EX2; the
+// result is never denormal (>= 1e-9).
+// rcp_fast: MUFU.RCP (1 ulp, flush-to-zero) for the BACKWARD formulas, whose bar is 1e-4 (no bit tracking of
+// a reference op order there): `1.f / x` and __fdividef compile to 6-10 instructions with denormal checks and
+// a slow-path branch.  Callers guarantee a normal, non-zero argument.
+// cos_pi / sincos_pi: cos(pi x), sin(pi x) by exact range reduction in x (no Cody-Waite constants, no slow
+// path): half the instructions of cosf(pi_f * x) and within its rounding of it on [0, 1].
+#ifdef EXPO_HOST_MATH
+__device__ __forceinline__ float lg2_pos(float x) { return log2f(x); }
+__device__ __forceinline__ float ex2_fast(float t) { return exp2f(t); }
+__device__ __forceinline__ float rcp_fast(float x) { return 1.0f / x; }
+__device__ __forceinline__ float cos_pi(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
+__device__ __forceinline__ void sincos_pi(float x, float* s, float* c) {
+  *s = (float)sin(3.14159265358979323846 * (double)x);
+  *c = (float)cos(3.14159265358979323846 * (double)x);
+}
+#else
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float cos_pi(float x) { return cospif(x); }
+__device__ __forceinline__ void sincos_pi(float x, float* s, float* c) { sincospif(x, s, c); }
+__device__ __forceinline__ float lg2_pos(float x) {
+  const int ix = __float_as_int(x);
+  const int e = (ix - 0x3f400000) >> 23;                   // floor(log2(x / 0.75))
+  const float m = __int_as_float(ix - (e << 23));          // in [0.75, 1.5)
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m));
+  return (float)e + r;
+}
+__device__ __forceinline__ float ex2_fast(float t) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
+#endif
 
 // ---- monotone piecewise-linear curve (ToneFilter / ColorFilter) ---------------------
 // y = (L/S) * sum_i clip(x - i/L, 0, 1/L) * t_i ; evaluated through the prefix sums:
@@ -244,7 +296,7 @@ __device__ __forceinline__ void px_fwd(const float (&x)[3], float (&y)[3], const
   } else if constexpr (FID == EXP_FILTER_GAMMA) {      // filters.py:205-206  max(x,1e-3)^gamma
     const float gm = sc.p[0];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) y[c] = exp2f(gm * log2f(fmaxf(x[c], 0.001f)));
+    for (int c = 0; c < 3; ++c) y[c] = ex2_fast(gm * lg2_pos(fmaxf(x[c], 0.001f)));
   } else if constexpr (FID == EXP_FILTER_WB) {         // filters.py:237-238
 #pragma unroll
     for (int c = 0; c < 3; ++c) y[c] = x[c] * sc.p[c];
@@ -265,7 +317,9 @@ __device__ __forceinline__ void px_fwd(const float (&x)[3], float (&y)[3], const
     const float p = sc.p[0];
     const float lum = __fadd_rn(__fadd_rn(__fmul_rn(kLumR, x[0]), __fmul_rn(kLumG, x[1])), __fmul_rn(kLumB, x[2]));
     const float l = clamp01(lum);
-    const float cl = __fadd_rn(__fmul_rn(-cosf(__fmul_rn(kPi, l)), 0.5f), 0.5f);
+    // cos(pi l): the reference's fp32 constant pi_f = 3.14159274 differs from pi by 8.7e-8, which moves the
+    // cosine by < 1 ulp(1) on [0, 1] -- inside the allowance the tests give this formula's own cancellation
+    const float cl = __fadd_rn(__fmul_rn(-cos_pi(l), 0.5f), 0.5f);
     const float den = __fadd_rn(l, 1e-6f);
     const float q = __fsub_rn(1.f, p);
 #pragma unroll
@@ -293,9 +347,11 @@ __device__ __forceinline__ void px_fwd(const float (&x)[3], float (&y)[3], const
 // backward of one pixel: gx = (dy/dx)^T gy ; acc += per-parameter partial sums
 // (final transform of the sums is finalize_gparams()).
 // =======================================================================================
-template <int FID, bool HAS_GX>
+// HAS_Y: `yf` holds the forward output of this pixel (the whole-chain kernel has it in registers: it is the
+// next step's input); filters whose backward would recompute it (Gamma) read it instead -- same bits.
+template <int FID, bool HAS_GX, bool HAS_Y = false>
 __device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3], float (&gx)[3],
-                                       float* __restrict__ acc, const FilterConsts& sc) {
+                                       float* __restrict__ acc, const FilterConsts& sc, const float* yf = nullptr) {
   if constexpr (FID == EXP_FILTER_EXPOSURE) {
     // y = x e ; dy/dp = y ln2 (ln2 applied at finalize) ; dy/dx = e
     const float e = sc.e;
@@ -313,10 +369,10 @@ __device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3]
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float xc = fmaxf(x[c], 0.001f);
-      const float l2 = log2f(xc);
-      const float y = exp2f(gm * l2);
+      const float l2 = lg2_pos(xc);
+      const float y = HAS_Y ? yf[c] : ex2_fast(gm * l2);
       s = fmaf(gy[c] * y, l2, s);
-      if (HAS_GX) gx[c] = x[c] >= 0.001f ? gy[c] * gm * __fdividef(y, xc) : 0.f;
+      if (HAS_GX) gx[c] = x[c] >= 0.001f ? gy[c] * gm * (y * rcp_fast(xc)) : 0.f;
     }
     acc[0] = fmaf(s, kLn2, acc[0]);
   } else if constexpr (FID == EXP_FILTER_WB) {
@@ -343,8 +399,8 @@ __device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3]
     float gF[3] = {gy[0] * p, gy[1] * p, gy[2] * p};
     float gxm[3], gV, gm;
     float dp;   // sum_c gy_c (full_c - xm_c)
-    if (rng > 0.f) {
-      const float inv = 1.f / rng;
+    if (rng >= 1.17549435e-38f) {                    // a denormal range is a grey pixel (rcp_fast flushes it to zero)
+      const float inv = rcp_fast(rng);
       const float Q = k * m;
       float Tt = 0.f, sg = 0.f, sgy_u = 0.f;
 #pragma unroll
@@ -402,10 +458,10 @@ __device__ __forceinline__ void px_bwd(const float (&x)[3], const float (&gy)[3]
     const float lum = fmaf(kLumB, x[2], fmaf(kLumG, x[1], kLumR * x[0]));
     const float l = clamp01(lum);
     float sn, cs;
-    sincosf(0.5f * kPi * l, &sn, &cs);
+    sincos_pi(0.5f * l, &sn, &cs);
     const float cl = sn * sn;
     const float dcl = kPi * sn * cs;                 // 0.5 pi sin(pi l)
-    const float iden = 1.f / (l + 1e-6f);
+    const float iden = rcp_fast(l + 1e-6f);
     const float w = cl * iden;
     const float dw = (dcl - w) * iden;
     const float sgx = fmaf(gy[2], x[2], fmaf(gy[1], x[1], gy[0] * x[0]));

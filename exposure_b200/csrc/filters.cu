@@ -468,6 +468,7 @@ struct ChainBwdArgs {
   float* partials; unsigned* counters;
   int S, B, P, pstride, logits, nblk, ntiles;
   FilterRanges rg;
+  int uniform_ids[8];                                            // used when ids == nullptr (kMaxChain entries)
 };
 
 // Sum N (power of two) per-lane values over the warp: at every stage a lane keeps one half of its values
@@ -542,6 +543,54 @@ __device__ __forceinline__ void chain_bwd_any(int fid, const float (&px)[4][3], 
   }
 }
 
+// ---- CTA record (warps summed in fixed order), ticket, last CTA of the image finishes in fp64 ----
+// slots[w][a]: warp w's partial sum of accumulator a (a < off[S]); `scratch`: >= kChainRec * 8 doubles of
+// shared memory that is free by now (the parking area).  Shared by the run-time and the compile-time chain kernels.
+template <int SLOTS>
+__device__ __forceinline__ void chain_finish(const ChainBwdArgs& A, int b, const FilterConsts* sc, const int* fids,
+                                             const int* off, float (*slots)[SLOTS], unsigned char* scratch) {
+  const int tid = threadIdx.x;
+  const int ntot = off[A.S];
+  float* rec = A.partials + ((size_t)b * A.nblk + blockIdx.x) * kChainRec;
+  for (int a = tid; a < ntot; a += kThreads) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) sum += slots[w][a];
+    rec[a] = sum;
+  }
+  __shared__ unsigned ticket;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) ticket = atomicAdd(A.counters + b, 1u);
+  __syncthreads();
+  if (ticket != (unsigned)(A.nblk - 1)) return;
+  __threadfence();
+  constexpr int PARTS = 8;                                  // records summed in 8 interleaved fp64 streams, combined in order
+  double* part = reinterpret_cast<double*>(scratch);       // [ntot][PARTS]
+  __shared__ double tot[kChainRec];
+  const float* base = A.partials + (size_t)b * A.nblk * kChainRec;
+  for (int i = tid; i < ntot * PARTS; i += kThreads) {
+    const int a = i / PARTS, p = i - a * PARTS;
+    double sum = 0.0;
+    for (int r = p; r < A.nblk; r += PARTS) sum += (double)__ldcg(base + (size_t)r * kChainRec + a);
+    part[i] = sum;
+  }
+  __syncthreads();
+  for (int a = tid; a < ntot; a += kThreads) {
+    double sum = 0.0;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) sum += part[a * PARTS + p];
+    tot[a] = sum;
+  }
+  __syncthreads();
+  if (tid < A.S) {
+    float* out = A.gparams + ((size_t)tid * A.B + b) * A.pstride;
+    if (fids[tid] >= 0) finalize_grads(fids[tid], tot + off[tid], sc[tid], A.logits, out);
+    else for (int i = 0; i < EXP_MAX_FILTER_PARAMS; ++i) out[i] = 0.f;
+  }
+  if (tid == 0) A.counters[b] = 0u;
+}
+
 // Instruction footprint: the hot loop (10 forward + 10 backward bodies x 4 pixels, ~100 KB) is three times
 // the 32 KB instruction cache (ncu: icc hit rate 83 %, stall_no_instruction 0.9 per issue).  A CTA barrier per
 // step, to keep the 8 warps inside the same body, was measured and is slower (0.87 vs 0.82 ms: hit rate only
@@ -602,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   for (int s = warp; s < A.S; s += kWarps) {               // one warp per step: the S set-ups run in parallel
-    const int f = A.ids[s * A.B + b];
+    const int f = A.ids ? A.ids[s * A.B + b] : A.uniform_ids[s];
     if (lane == 0) fids[s] = (f >= 0 && f < EXP_NUM_FILTER_KINDS) ? f : -1;
     if (f >= 0 && f < EXP_NUM_FILTER_KINDS)
       setup_consts_lane(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits, lane, A.rg);
@@ -676,47 +725,250 @@ __global__ void __launch_bounds__(kThreads, 2) filter_chain_fwd_bwd_kernel(const
     if (live && gxo) group_store<NPX>(gxo, q, g);
   }
 
-  // ---- CTA record (warps summed in fixed order), ticket, last CTA of the image finishes in fp64 ----
   __syncthreads();
-  const int ntot = off[A.S];
-  float* rec = A.partials + ((size_t)b * A.nblk + blockIdx.x) * kChainRec;
-  for (int a = tid; a < ntot; a += kThreads) {
-    float sum = 0.f;
+  chain_finish<kChainRec>(A, b, sc, fids, off, slots, chain_smem);
+}
+
+// ---- the same whole-chain pass for a chain that is known at COMPILE time ---------------------------------
+// When every image runs the same filter sequence (the benchmark chain E,G,W,S+,T,Ct,BW,C of BASELINE configs[1] /
+// [4]; ids uniform over the batch) the sequence becomes a template pack and the generality the run-time kernel
+// pays for disappears (profiles/r1k_chain_fused_ncu.md: 1 117 instructions/pixel, 65 % issue-active, i-cache 83 %):
+//   * no `switch` per step and tile, no merge MOVs, a third of the code (8 + 8 bodies instead of 10 + 10 behind
+//     two jump tables);
+//   * the parameter-gradient accumulators (40 for the canonical chain) stay in REGISTERS across the whole tile
+//     loop; one multi-value butterfly per CTA instead of one per tile and step, no shared-memory slots;
+//   * the input of a step that follows a pure per-channel scale (Exposure, WhiteBalance) is not parked: it is
+//     recomputed from the scale's own parked input with the same 3 FMULs (bit-identical) -- 6 parking areas
+//     instead of 8 for the canonical chain;
+//   * a step's backward gets its forward OUTPUT for free (it is the next step's input, already in registers):
+//     Gamma's backward no longer recomputes the power.
+// Same px_fwd / px_bwd functions, same record / ticket / fp64 finish: y and gx are bit-identical to the
+// run-time kernel and to the per-step kernels; parameter gradients agree to reduction order.
+template <int... F> struct FidSeq {
+  static constexpr int n = sizeof...(F);
+  static constexpr int v[sizeof...(F) ? sizeof...(F) : 1] = {F...};
+};
+template <class Q> __host__ __device__ constexpr bool seq_is_scale(int i) {
+  return Q::v[i] == EXP_FILTER_EXPOSURE || Q::v[i] == EXP_FILTER_WB;
+}
+// step i's input is parked unless step i-1 is a per-channel scale whose own input is parked
+template <class Q> __host__ __device__ constexpr bool seq_parked(int i) {
+  return i == 0 || !(seq_is_scale<Q>(i - 1) && seq_parked<Q>(i - 1));
+}
+template <class Q> __host__ __device__ constexpr int seq_slot(int i) {          // parking area index of step i
+  int n = 0;
+  for (int k = 0; k < i; ++k) n += seq_parked<Q>(k) ? 1 : 0;
+  return n;
+}
+template <class Q> __host__ __device__ constexpr int seq_acc_off(int i) {       // first accumulator of step i (record order)
+  int n = 0;
+  for (int k = 0; k < i; ++k) n += num_acc(Q::v[k]);
+  return n;
+}
+// Accumulator placement: the curve filters carry 8 (Tone) / 24 (Color) sums -- pinned in registers next to the
+// 8 scalar ones they push the kernel past 128 registers (ptxas: 568 B of spills).  They live in per-thread
+// SHARED memory instead ([vector][thread] float4 columns, conflict free): a step sums its 4 pixels in temporary
+// registers and adds them with one LDS.128 / STS.128 pair per 4 sums and tile.  Sums of fewer than 8 stay in
+// registers for the whole tile loop.
+__host__ __device__ constexpr bool acc_in_smem(int fid) { return num_acc(fid) >= 8; }
+template <class Q> __host__ __device__ constexpr int seq_reg_off(int i) {       // register accumulators before step i
+  int n = 0;
+  for (int k = 0; k < i; ++k) n += acc_in_smem(Q::v[k]) ? 0 : num_acc(Q::v[k]);
+  return n;
+}
+template <class Q> __host__ __device__ constexpr int seq_sm_off4(int i) {       // float4 vectors of smem accumulators before step i
+  int n = 0;
+  for (int k = 0; k < i; ++k) n += acc_in_smem(Q::v[k]) ? num_acc(Q::v[k]) / 4 : 0;
+  return n;
+}
+
+template <class Q, int I, int NPX>
+__device__ __forceinline__ void static_fwd_sweep(float (&px)[4][3], float* __restrict__ park, int tid, const FilterConsts* sc) {
+  if constexpr (I < Q::n) {
+    if constexpr (seq_parked<Q>(I)) park_store<NPX>(park + (size_t)seq_slot<Q>(I) * (3 * NPX * kThreads), tid, px);
+    chain_apply<Q::v[I]>(px, sc[I], NPX);
+    static_fwd_sweep<Q, I + 1, NPX>(px, park, tid, sc);
+  }
+}
+// yn: the output of step I (= input of step I+1), g: gradient in / out, acc: register accumulators,
+// accsm: this thread's column of the shared-memory accumulators
+template <class Q, int I, int NPX>
+__device__ __forceinline__ void static_bwd_sweep(float (&yn)[4][3], float (&g)[4][3], float* __restrict__ acc,
+                                                 float4* __restrict__ accsm, const float* __restrict__ park, int tid,
+                                                 const FilterConsts* sc) {
+  if constexpr (I >= 0) {
+    constexpr int FID = Q::v[I];
+    float px[4][3];
+    if constexpr (seq_parked<Q>(I)) {
+      park_load<NPX>(park + (size_t)seq_slot<Q>(I) * (3 * NPX * kThreads), tid, px);
+    } else {                                               // x_I = scale(x_{I-1}): the same FMULs as the forward sweep
+      park_load<NPX>(park + (size_t)seq_slot<Q>(I - 1) * (3 * NPX * kThreads), tid, px);
+      chain_apply<Q::v[I - 1]>(px, sc[I - 1], NPX);
+    }
+    if constexpr (acc_in_smem(FID)) {
+      constexpr int NA = num_acc(FID);
+      float a[NA];
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) sum += slots[w][a];
-    rec[a] = sum;
-  }
-  __shared__ unsigned ticket;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) ticket = atomicAdd(A.counters + b, 1u);
-  __syncthreads();
-  if (ticket != (unsigned)(A.nblk - 1)) return;
-  __threadfence();
-  constexpr int PARTS = 8;                                  // records summed in 8 interleaved fp64 streams, combined in order
-  double* part = reinterpret_cast<double*>(chain_smem);    // [ntot][PARTS]  (the parking area is free now)
-  __shared__ double tot[kChainRec];
-  const float* base = A.partials + (size_t)b * A.nblk * kChainRec;
-  for (int i = tid; i < ntot * PARTS; i += kThreads) {
-    const int a = i / PARTS, p = i - a * PARTS;
-    double sum = 0.0;
-    for (int r = p; r < A.nblk; r += PARTS) sum += (double)__ldcg(base + (size_t)r * kChainRec + a);
-    part[i] = sum;
-  }
-  __syncthreads();
-  for (int a = tid; a < ntot; a += kThreads) {
-    double sum = 0.0;
+      for (int k = 0; k < NA; ++k) a[k] = 0.f;
 #pragma unroll
-    for (int p = 0; p < PARTS; ++p) sum += part[a * PARTS + p];
-    tot[a] = sum;
+      for (int i = 0; i < NPX; ++i) {
+        float gx[3];
+        px_bwd<FID, true, true>(px[i], g[i], gx, a, sc[I], yn[i]);
+        g[i][0] = gx[0]; g[i][1] = gx[1]; g[i][2] = gx[2];
+      }
+      float4* sa = accsm + (size_t)seq_sm_off4<Q>(I) * kThreads;
+#pragma unroll
+      for (int v = 0; v < NA / 4; ++v) {
+        float4 t = sa[(size_t)v * kThreads];
+        t.x += a[4 * v]; t.y += a[4 * v + 1]; t.z += a[4 * v + 2]; t.w += a[4 * v + 3];
+        sa[(size_t)v * kThreads] = t;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NPX; ++i) {
+        float gx[3];
+        px_bwd<FID, true, true>(px[i], g[i], gx, acc + seq_reg_off<Q>(I), sc[I], yn[i]);
+        g[i][0] = gx[0]; g[i][1] = gx[1]; g[i][2] = gx[2];
+      }
+    }
+    static_bwd_sweep<Q, I - 1, NPX>(px, g, acc, accsm, park, tid, sc);
+  }
+}
+// all accumulators of the chain in record order (registers + this thread's shared-memory column)
+template <class Q, int I>
+__device__ __forceinline__ void static_collect(float* __restrict__ all, const float* __restrict__ acc, const float4* __restrict__ accsm) {
+  if constexpr (I < Q::n) {
+    constexpr int FID = Q::v[I];
+    constexpr int NA = num_acc(FID);
+    if constexpr (acc_in_smem(FID)) {
+#pragma unroll
+      for (int v = 0; v < NA / 4; ++v) {
+        const float4 t = accsm[(size_t)(seq_sm_off4<Q>(I) + v) * kThreads];
+        all[seq_acc_off<Q>(I) + 4 * v] = t.x; all[seq_acc_off<Q>(I) + 4 * v + 1] = t.y;
+        all[seq_acc_off<Q>(I) + 4 * v + 2] = t.z; all[seq_acc_off<Q>(I) + 4 * v + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NA; ++k) all[seq_acc_off<Q>(I) + k] = acc[seq_reg_off<Q>(I) + k];
+    }
+    static_collect<Q, I + 1>(all, acc, accsm);
+  }
+}
+
+constexpr int kStaticSlots = 64;      // accumulators per warp record of the compile-time kernel (40 for the canonical chain)
+
+template <int NPX, bool PF, int... F>
+__global__ void __launch_bounds__(kThreads, 2) filter_chain_static_kernel(const ChainBwdArgs A) {
+  using Q = FidSeq<F...>;
+  constexpr int S = Q::n;
+  constexpr int NACC = seq_acc_off<Q>(S);
+  constexpr int NREG = seq_reg_off<Q>(S) > 0 ? seq_reg_off<Q>(S) : 1;
+  constexpr int NSM4 = seq_sm_off4<Q>(S);
+  constexpr int kArea = 3 * NPX * kThreads;
+  static_assert(NACC <= kStaticSlots, "warp record too small");
+  extern __shared__ __align__(16) unsigned char chain_smem[];
+  __shared__ FilterConsts sc[S];
+  __shared__ int fids[S], off[S + 1];
+  __shared__ float slots[kWarps][kStaticSlots];
+  float* const park = reinterpret_cast<float*>(chain_smem);
+  float4* const accsm = reinterpret_cast<float4*>(park + (size_t)seq_slot<Q>(S) * kArea) + threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int vf[S] = {F...};                                 // run-time indexable copy of the pack (prologue only)
+  for (int s = warp; s < S; s += kWarps)                    // one warp per step: the S set-ups run in parallel
+    setup_consts_lane(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, vf[s], A.logits, lane, A.rg);
+  if (tid <= S) {
+    int o = 0;
+    for (int s = 0; s < tid; ++s) o += num_acc(vf[s]);
+    off[tid] = o;
+    if (tid < S) fids[tid] = vf[tid];
+  }
+#pragma unroll
+  for (int v = 0; v < NSM4; ++v) accsm[(size_t)v * kThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  const size_t img = (size_t)b * A.P * 3;
+  const float* __restrict__ x = A.x + img;
+  const float* __restrict__ gy = A.gy + img;
+  float* __restrict__ y = A.y ? A.y + img : nullptr;
+  float* __restrict__ gxo = A.gx ? A.gx + img : nullptr;
+  const int t0 = (int)((long long)blockIdx.x * A.ntiles / A.nblk);
+  const int t1 = (int)((long long)(blockIdx.x + 1) * A.ntiles / A.nblk);
+  const int nq = A.P / NPX;
+
+  float acc[NREG];
+#pragma unroll
+  for (int a = 0; a < NREG; ++a) acc[a] = 0.f;
+
+  float nx[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) nx[i][0] = nx[i][1] = nx[i][2] = 0.f;
+  if constexpr (PF) {
+    const int q0 = t0 * kThreads + tid;
+    if (t0 < t1 && q0 < nq) group_load<NPX>(x, q0, nx);
+  }
+  for (int t = t0; t < t1; ++t) {
+    const int q = t * kThreads + tid;
+    const bool live = q < nq;
+    float px[4][3], g[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      px[i][0] = nx[i][0]; px[i][1] = nx[i][1]; px[i][2] = nx[i][2];
+      g[i][0] = g[i][1] = g[i][2] = 0.f;
+    }
+    if constexpr (!PF) {
+      if (live) group_load<NPX>(x, q, px);
+    }
+    if (live) group_load<NPX>(gy, q, g);                     // dL/dy and the NEXT tile's x are requested before the sweep
+    if constexpr (PF) {
+      const int qn = q + kThreads;
+      if (t + 1 < t1 && qn < nq) {
+        group_load<NPX>(x, qn, nx);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nx[i][0] = nx[i][1] = nx[i][2] = 0.f;
+      }
+    }
+    static_fwd_sweep<Q, 0, NPX>(px, park, tid, sc);
+    if (live && y) group_store<NPX>(y, q, px);
+    // dead lanes carry g == 0: every accumulator term is a multiple of g
+    static_bwd_sweep<Q, S - 1, NPX>(px, g, acc, accsm, park, tid, sc);
+    if (live && gxo) group_store<NPX>(gxo, q, g);
+  }
+
+  // ---- one multi-value butterfly per CTA: rows of <= 8 accumulators -> per-warp slots -> shared finish ----
+  float all[NACC];
+  static_collect<Q, 0>(all, acc, accsm);
+#pragma unroll
+  for (int r = 0; r < (NACC + 7) / 8; ++r) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (r * 8 + i < NACC) ? all[r * 8 + i] : 0.f;
+    int idx;
+    const float tot = warp_multi_sum<8>(v, lane, idx);
+    if ((lane & 3) == 0 && r * 8 + idx < NACC) slots[warp][r * 8 + idx] = tot;
   }
   __syncthreads();
-  if (tid < A.S) {
-    float* out = A.gparams + ((size_t)tid * A.B + b) * A.pstride;
-    if (fids[tid] >= 0) finalize_grads(fids[tid], tot + off[tid], sc[tid], A.logits, out);
-    else for (int i = 0; i < EXP_MAX_FILTER_PARAMS; ++i) out[i] = 0.f;
+  chain_finish<kStaticSlots>(A, b, sc, fids, off, slots, chain_smem);
+}
+
+// chains with a compile-time instantiation (the host falls back to the run-time kernel for everything else)
+template <int NPX, bool PF, int... F>
+static cudaError_t launch_chain_static(const ChainBwdArgs& A, cudaStream_t st) {
+  using Q = FidSeq<F...>;
+  constexpr size_t smem = (size_t)seq_slot<Q>(Q::n) * 3 * NPX * kThreads * sizeof(float) +
+                          (size_t)seq_sm_off4<Q>(Q::n) * kThreads * sizeof(float4);
+  auto kern = filter_chain_static_kernel<NPX, PF, F...>;
+  static bool attr_set[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
   }
-  if (tid == 0) A.counters[b] = 0u;
+  kern<<<dim3(A.nblk, A.B), kThreads, smem, st>>>(A);
+  return cudaGetLastError();
 }
 
 // ---- filter_param_regressor kernels (one thread per image; math in filter_math.cuh) ------
@@ -943,7 +1195,10 @@ int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstr
 static int chain_nblk(int B, int ntiles) {
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int target = sms * 2 * 8;      // measured at 64x512x512: 4 waves 0.844 ms (tail), 8 waves 0.810, 16 waves 0.907 (set-up per CTA)
+  static const int waves = [] { const char* e = getenv("EXPOSURE_CHAIN_WAVES"); return e && atoi(e) > 0 ? atoi(e) : 8; }();   // tuning aid
+  // measured at 64x512x512, run-time kernel (round 1): 4 waves 0.844 ms (tail), 8 waves 0.810, 16 waves 0.907 (set-up per
+  // CTA); compile-time kernel (round 2): 4 waves 0.534, 6 waves 0.524, 8 waves 0.523, 12 waves 0.554
+  const int target = sms * 2 * waves;
   int nblk = (target + B - 1) / B;
   if (nblk > ntiles) nblk = ntiles;
   if (nblk > 65535) nblk = 65535;
@@ -962,10 +1217,10 @@ size_t exp_filter_chain_fwd_bwd_workspace_bytes(int S, int B, int H, int W) {
   return kCounterBytes + (size_t)B * nblk * kChainRec * sizeof(float);
 }
 
-int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* gx, const float* params, int pstride,
-                             const int* ids, int S, int B, int H, int W, float* gparams, void* workspace,
-                             size_t workspace_bytes, int options, void* stream) {
-  EXP_CHECK_ARG(x && gy && params && ids && gparams && workspace, "null pointer");
+static int chain_fwd_bwd_impl(const float* x, const float* gy, float* y, float* gx, const float* params, int pstride,
+                              const int* ids, const int* ids_host, int S, int B, int H, int W, float* gparams,
+                              void* workspace, size_t workspace_bytes, int options, void* stream, const char* what) {
+  EXP_CHECK_ARG(x && gy && params && (ids || ids_host) && gparams && workspace, "null pointer");
   EXP_CHECK_ARG(S >= 1 && S <= kMaxChain, "S must be in [1, %d] (got %d)", kMaxChain, S);
   EXP_CHECK_ARG(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 29), "bad shape");
   EXP_CHECK_ARG(pstride >= EXP_MAX_FILTER_PARAMS, "per-image ids need pstride >= %d (got %d)", EXP_MAX_FILTER_PARAMS, pstride);
@@ -992,6 +1247,22 @@ int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* g
   const int npx = vec ? 4 : 1;
   A.ntiles = chain_ntiles(P, npx);
   A.nblk = chain_nblk(B, A.ntiles);
+  if (ids_host) {
+    bool canonical = S == EXP_NUM_FILTERS;
+    for (int s = 0; s < S; ++s) {
+      EXP_CHECK_ARG(ids_host[s] >= -1 && ids_host[s] < EXP_NUM_FILTER_KINDS, "bad filter id %d at step %d", ids_host[s], s);
+      A.uniform_ids[s] = ids_host[s];
+      canonical = canonical && ids_host[s] == s;
+    }
+    // the shipped cfg.filters order E,G,W,S+,T,Ct,BW,C (config_example.py:22-25) has a compile-time instantiation
+    if (canonical && vec && !(options & EXP_OPT_NO_STATIC_CHAIN)) {
+      // PF (next tile's x requested before the sweep, +12 live registers) measured on B200 at 64x512x512:
+      // 0.560 ms with, 0.523 ms without (128 registers either way; the prefetch costs spills) -> off
+      const cudaError_t e = launch_chain_static<4, false, 0, 1, 2, 3, 4, 5, 6, 7>(A, (cudaStream_t)stream);
+      if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "%s[static]: %s", what, cudaGetErrorString(e));
+      return EXP_OK;
+    }
+  }
   const size_t smem = (size_t)S * 3 * npx * kThreads * sizeof(float);
   auto kern = npx == 4 ? filter_chain_fwd_bwd_kernel<4, true> : filter_chain_fwd_bwd_kernel<1, false>;
   static bool attr_set[2][64];
@@ -1003,8 +1274,24 @@ int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* g
     attr_set[npx >> 2][dev] = true;
   }
   kern<<<dim3(A.nblk, B), kThreads, smem, (cudaStream_t)stream>>>(A);
-  EXP_CHECK_LAUNCH("exp_filter_chain_fwd_bwd");
+  EXP_CHECK_LAUNCH(what);
   return EXP_OK;
+}
+
+int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* gx, const float* params, int pstride,
+                             const int* ids, int S, int B, int H, int W, float* gparams, void* workspace,
+                             size_t workspace_bytes, int options, void* stream) {
+  EXP_CHECK_ARG(ids, "null ids pointer");
+  return chain_fwd_bwd_impl(x, gy, y, gx, params, pstride, ids, nullptr, S, B, H, W, gparams, workspace, workspace_bytes,
+                            options, stream, "exp_filter_chain_fwd_bwd");
+}
+
+int exp_filter_chain_fwd_bwd_uniform(const float* x, const float* gy, float* y, float* gx, const float* params, int pstride,
+                                     const int* ids_host, int S, int B, int H, int W, float* gparams, void* workspace,
+                                     size_t workspace_bytes, int options, void* stream) {
+  EXP_CHECK_ARG(ids_host, "null ids_host pointer");
+  return chain_fwd_bwd_impl(x, gy, y, gx, params, pstride, nullptr, ids_host, S, B, H, W, gparams, workspace,
+                            workspace_bytes, options, stream, "exp_filter_chain_fwd_bwd_uniform");
 }
 
 size_t exp_filter_bwd_workspace_bytes(int B, int H, int W) {

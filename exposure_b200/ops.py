@@ -146,29 +146,44 @@ def _workspace(dev, nbytes):
   return ws
 
 
+OPT_NO_STATIC_CHAIN = 0x200   # EXP_OPT_NO_STATIC_CHAIN: uniform chains never take a compile-time instantiation (tests)
+
+
 def filter_chain_fwd_bwd(x, gy, params, ids, need_y=True, need_gx=True, logits=False, y_out=None, gx_out=None,
-                         gparams_out=None):
-  """Whole chain forward + backward in ONE pass over the pixels (exp_filter_chain_fwd_bwd): x, gy [B,H,W,3];
-  params [S,B,24]; ids int32 [S,B].  Returns (y or None, gx or None, gparams [S,B,24])."""
+                         gparams_out=None, static_chain=True):
+  """Whole chain forward + backward in ONE pass over the pixels: x, gy [B,H,W,3]; params [S,B,24];
+  ids: CUDA int32 [S,B] (per-image filter ids, exp_filter_chain_fwd_bwd) or a list / tuple of S ints (the same
+  sequence for every image, exp_filter_chain_fwd_bwd_uniform: sequences with a compile-time instantiation run
+  the specialised kernel unless static_chain=False).  Returns (y or None, gx or None, gparams [S,B,24])."""
   global launch_count
   _chk_img(x, "x")
   _chk_img(gy, "gy")
   B, H, W, _ = x.shape
-  S = ids.shape[0]
+  uniform = isinstance(ids, (list, tuple))
+  S = len(ids) if uniform else ids.shape[0]
   if not (params.is_cuda and params.dtype == torch.float32 and params.is_contiguous() and tuple(params.shape) == (S, B, PSTRIDE)):
     raise ValueError("params must be a contiguous CUDA float32 [S,B,%d] tensor" % PSTRIDE)
-  if not (ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous() and tuple(ids.shape) == (S, B)):
-    raise ValueError("ids must be a contiguous CUDA int32 [S,B] tensor")
+  if not uniform and not (ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous() and tuple(ids.shape) == (S, B)):
+    raise ValueError("ids must be a contiguous CUDA int32 [S,B] tensor or a list of S ints")
   y = (torch.empty_like(x) if y_out is None else y_out) if need_y else None
   gx = (torch.empty_like(x) if gx_out is None else gx_out) if need_gx else None
   gparams = torch.zeros(S, B, PSTRIDE, device=x.device, dtype=torch.float32) if gparams_out is None else gparams_out
   l = _cabi.lib()
   ws = _workspace(x.device, l.exp_filter_chain_fwd_bwd_workspace_bytes(S, B, H, W))
+  opts = OPT_LOGITS if logits else 0
   with _Timed("filter_chain_fwd_bwd", "fused%d" % S, B * H * W * (24 + (12 if need_y else 0) + (12 if need_gx else 0))):
-    _cabi.check(l.exp_filter_chain_fwd_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr() if need_y else None,
-                                           gx.data_ptr() if need_gx else None, params.data_ptr(), PSTRIDE, ids.data_ptr(),
-                                           S, B, H, W, gparams.data_ptr(), ws.data_ptr(), ws.numel(),
-                                           OPT_LOGITS if logits else 0, _stream()), "exp_filter_chain_fwd_bwd")
+    if uniform:
+      import ctypes
+      ids_host = (ctypes.c_int * S)(*[int(i) for i in ids])
+      _cabi.check(l.exp_filter_chain_fwd_bwd_uniform(
+          x.data_ptr(), gy.data_ptr(), y.data_ptr() if need_y else None, gx.data_ptr() if need_gx else None,
+          params.data_ptr(), PSTRIDE, ctypes.cast(ids_host, ctypes.c_void_p), S, B, H, W, gparams.data_ptr(), ws.data_ptr(),
+          ws.numel(), opts | (0 if static_chain else OPT_NO_STATIC_CHAIN), _stream()), "exp_filter_chain_fwd_bwd_uniform")
+    else:
+      _cabi.check(l.exp_filter_chain_fwd_bwd(x.data_ptr(), gy.data_ptr(), y.data_ptr() if need_y else None,
+                                             gx.data_ptr() if need_gx else None, params.data_ptr(), PSTRIDE, ids.data_ptr(),
+                                             S, B, H, W, gparams.data_ptr(), ws.data_ptr(), ws.numel(), opts, _stream()),
+                  "exp_filter_chain_fwd_bwd")
   launch_count += 1
   return y, gx, gparams
 

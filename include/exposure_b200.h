@@ -70,6 +70,9 @@ enum {
  * filter_param_regressor in its prologue and exp_filter_bwd returns dL/dlogits in `gparams`
  * (regressor fused into the filter step: no separate per-image launches). */
 #define EXP_OPT_LOGITS 0x100
+/* exp_filter_chain_fwd_bwd_uniform only: never take a compile-time instantiation of the chain (A/B switch of the
+ * tests: the run-time kernel must give the same y / gx bit for bit). */
+#define EXP_OPT_NO_STATIC_CHAIN 0x200
 
 /* ---- library ------------------------------------------------------------------- */
 int exp_version(void);               /* ABI version, currently 1                       */
@@ -155,6 +158,16 @@ size_t exp_filter_chain_fwd_bwd_workspace_bytes(int S, int B, int H, int W);
 int exp_filter_chain_fwd_bwd(const float* x, const float* gy, float* y, float* gx, const float* params,
                              int pstride, const int* ids, int S, int B, int H, int W, float* gparams,
                              void* workspace, size_t workspace_bytes, int options, void* stream);
+/* The same pass when EVERY image runs the same filter sequence: `ids_host` is a HOST array of S filter ids
+ * (the benchmark chain of BASELINE configs[1] / [4]; a fixed retouching recipe applied to a whole batch).
+ * Sequences with a compile-time instantiation -- currently the shipped cfg.filters order E,G,W,S+,T,Ct,BW,C
+ * (config_example.py:22-25) on 16-byte aligned images with H*W % 4 == 0 -- run a kernel specialised for the
+ * sequence (no per-step dispatch, parameter-gradient accumulators in registers across the tile loop, scale
+ * steps recomputed instead of parked); every other sequence runs the kernel of exp_filter_chain_fwd_bwd.
+ * y and gx are bit-identical between the two, gparams agree to reduction order.  Same workspace. */
+int exp_filter_chain_fwd_bwd_uniform(const float* x, const float* gy, float* y, float* gx, const float* params,
+                                     int pstride, const int* ids_host, int S, int B, int H, int W, float* gparams,
+                                     void* workspace, size_t workspace_bytes, int options, void* stream);
 
 /* Bytes of device workspace exp_filter_bwd needs for this shape: a fixed 256 KiB block of
  * per-image ticket counters followed by the partial-sum records of the per-image parameter

@@ -168,7 +168,7 @@ def test_fused_chain_full_size_properties(ops):
   y1, gx1, gl1 = fused.forward_backward(x, gout)
   assert torch.equal(y1, y0) and torch.equal(gx1, gx0)
   for k, (a, b) in enumerate(zip(fused.glogits_list(), gl0)):
-    assert _rel(a, b, floor=1e-2) < 2e-5, k
+    assert _rel(a, b, floor=1e-2) < 5e-5, k     # reduction order only (per-thread sums over the tile loop)
   gl1 = gl1.clone()
   del ref, y0, gx0
   _, gx2, gl2 = fused.forward_backward(x, gout * 2.0, need_output=False)
@@ -208,3 +208,51 @@ def test_filter_chain_autograd_node(ops):
     for b in range(B):
       n = F.NUM_PARAMS[int(ids[s, b])]
       assert _rel(gl[s, b, :n], l2.grad[s, b, :n], floor=1e-2) < 2e-5, (s, b)
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 64), (2, 128, 96), (3, 512, 512), (1, 360, 644)])
+def test_compile_time_chain_equals_run_time_chain(ops, shape):
+  """exp_filter_chain_fwd_bwd_uniform: the kernel specialised for the cfg.filters order E,G,W,S+,T,Ct,BW,C
+  (template pack, accumulators in registers / per-thread shared memory, scale steps recomputed, Gamma's backward
+  fed with the forward output) against the run-time kernel on the same chain: y and dL/dx BIT-IDENTICAL, parameter
+  gradients equal to reduction order; and against the per-image-ids entry point."""
+  from exposure_b200.chain import FusedFilterChain
+  B, H, W = shape
+  x = F.synth_images(B, H, W, seed=91).cuda()
+  lgs = [(F.synth_logits(f, B, seed=92 + k) * 0.7).cuda() for k, f in enumerate(CHAIN)]
+  gout = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(93)).cuda()
+  outs = []
+  for ids, static in ((CHAIN, True), (CHAIN, False), ([torch.full((B,), f, dtype=torch.int32, device="cuda") for f in CHAIN], True)):
+    fz = FusedFilterChain(ids, B, torch.device("cuda"), static_chain=static)
+    fz.set_logits(lgs)
+    y, gx, _ = fz.forward_backward(x, gout)
+    torch.cuda.synchronize()
+    outs.append((y.clone(), gx.clone(), [g.clone() for g in fz.glogits_list()]))
+  (ys, gxs, gls), (yr, gxr, glr), (yt, gxt, glt) = outs
+  assert torch.equal(ys, yr) and torch.equal(gxs, gxr), "compile-time chain differs from the run-time kernel"
+  assert torch.equal(yr, yt) and torch.equal(gxr, gxt)
+  for k, (a, b) in enumerate(zip(gls, glr)):
+    assert _rel(a, b, floor=1e-2) < 1e-5, k
+  # optional outputs
+  fz = FusedFilterChain(CHAIN, B, torch.device("cuda"))
+  fz.set_logits(lgs)
+  y, gx, _ = fz.forward_backward(x, gout, need_output=False)
+  assert y is None and torch.equal(gx, gxs)
+  y, gx, _ = fz.forward_backward(x, gout, need_input_grad=False)
+  assert gx is None and torch.equal(y, ys)
+
+
+def test_compile_time_chain_repeated_launches_are_reproducible(ops):
+  """Deterministic reduction: two launches give bitwise equal parameter gradients; the workspace is left clean."""
+  from exposure_b200.chain import FusedFilterChain
+  B, H, W = 5, 256, 256
+  x = F.synth_images(B, H, W, seed=95).cuda()
+  lgs = [(F.synth_logits(f, B, seed=96 + k) * 0.7).cuda() for k, f in enumerate(CHAIN)]
+  gout = torch.randn(B, H, W, 3, generator=torch.Generator().manual_seed(97)).cuda()
+  fz = FusedFilterChain(CHAIN, B, torch.device("cuda"))
+  fz.set_logits(lgs)
+  fz.forward_backward(x, gout)
+  g1 = fz.glogits.clone()
+  fz.forward_backward(x, gout)
+  torch.cuda.synchronize()
+  assert torch.equal(g1, fz.glogits)

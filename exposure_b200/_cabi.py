@@ -91,6 +91,14 @@ SIGNATURES = {
                                _c_void_p, _c_void_p, _c_void_p]),
     "exp_interpolate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "exp_gp_scale": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int, _c_void_p]),
+    "exp_dp_ipc_handle_bytes": (_c_size_t, []),
+    "exp_dp_ipc_export": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
+    "exp_dp_ipc_open": (_c_int, [_c_void_p, _c_void_p]),
+    "exp_dp_ipc_close": (_c_int, [_c_void_p]),
+    "exp_dp_flag_bytes": (_c_size_t, []),
+    "exp_dp_max_world": (_c_int, []),
+    "exp_dp_allreduce_adam": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                       _c_void_p, _c_size_t, _c_void_p, _c_size_t, _c_float, _c_float, _c_float, _c_void_p]),
     "exp_adam": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_float, _c_float, _c_float,
                           _c_size_t, _c_void_p]),
 }

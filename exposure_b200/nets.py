@@ -37,14 +37,24 @@ class ParamStore:
     assert self.flat is None
     self.specs.append((name, tuple(shape), fan_in, fan_out))
 
-  def finalize(self, seed=0):
-    n = sum(int(math.prod(s[1])) for s in self.specs)
-    n_pad = (n + 3) // 4 * 4
+  ALIGN = 64      # floats: 4 * world divides the padded size for every world <= 16 (exp_dp_allreduce_adam slices)
+
+  def count(self):
+    return sum(int(math.prod(s[1])) for s in self.specs)
+
+  def padded(self):
+    return (self.count() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+
+  def finalize(self, seed=0, buffers=None):
+    """buffers: (flat, grad, m, v) views of padded() floats each inside a shared ParamArena (several optimizers,
+    one exchange); default: own buffers."""
+    n = self.count()
+    n_pad = self.padded()
     dev = self.device
-    self.flat = torch.zeros(n_pad, device=dev)
-    self.grad = torch.zeros(n_pad, device=dev)
-    self.m = torch.zeros(n_pad, device=dev)
-    self.v = torch.zeros(n_pad, device=dev)
+    if buffers is None:
+      buffers = tuple(torch.zeros(n_pad, device=dev) for _ in range(4))
+    self.flat, self.grad, self.m, self.v = buffers
+    assert all(b.numel() == n_pad for b in buffers)
     self.p, self.g, self.offsets = {}, {}, {}
     g = torch.Generator().manual_seed(seed)
     off = 0
@@ -74,6 +84,22 @@ def _add_conv_stack(store, scope, cin):
     names.append(base)
     c = co
   return names
+
+
+class ParamArena:
+  """Several ParamStores in ONE flat buffer (+ grads, Adam slots): the generator step trains theta_g and theta_v in
+  the same sess.run (net.py:330-331), so both optimizers share one gradient exchange (7.35 M floats)."""
+
+  def __init__(self, device, stores, seeds):
+    sizes = [s.padded() for s in stores]
+    total = sum(sizes)
+    self.flat, self.grad, self.m, self.v = (torch.zeros(total, device=device) for _ in range(4))
+    self.offsets, off = [], 0
+    for s, n, seed in zip(stores, sizes, seeds):
+      s.finalize(seed, buffers=tuple(b[off:off + n] for b in (self.flat, self.grad, self.m, self.v)))
+      self.offsets.append(off)
+      off += n
+    self.numel = total
 
 
 class _Ctx:

@@ -12,7 +12,8 @@ import torch
 import torch.distributed as dist
 
 from . import nn_ops as K
-from .nets import CriticNet, ParamStore, PolicyNet
+from . import dp as DP
+from .nets import CriticNet, ParamArena, ParamStore, PolicyNet
 
 
 def default_cfg():
@@ -52,10 +53,10 @@ class Trainer:
     self.device = device or torch.device("cuda", torch.cuda.current_device())
     self.gen = ParamStore(self.device)
     self.policy = PolicyNet(self.gen, n_states=self.cfg.num_state_dim, scope="generator")
-    self.gen.finalize(seed)
     self.val = ParamStore(self.device)
     self.value = CriticNet(self.val, "rl_value/critic", n_states=self.cfg.num_state_dim)
-    self.val.finalize(seed + 1)
+    # theta_g and theta_v are trained by the same sess.run (net.py:330-331): one flat buffer, one gradient exchange
+    self.gv = ParamArena(self.device, [self.gen, self.val], [seed, seed + 1])
     self.cri = ParamStore(self.device)
     self.critic = CriticNet(self.cri, "critic", n_states=0)
     self.cri.finalize(seed + 2)
@@ -67,6 +68,11 @@ class Trainer:
     self.ema_state = torch.zeros(3, device=self.device)
     self._hyper = {k: torch.zeros(1, device=self.device) for k in "gvc"}
     self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    # data-parallel transport (exposure_b200/dp.py): peer-memory all-reduce fused with Adam where the process group
+    # allows it (one kernel, graph-capturable), dist.all_reduce + Adam otherwise
+    self._peer = None
+    if self.world > 1 and DP.peer_exchange_possible(self.device):
+      self._peer = {"gv": DP.PeerExchange(self.gv.grad, self.device), "c": DP.PeerExchange(self.cri.grad, self.device)}
 
   @staticmethod
   def _check_cfg(cfg):
@@ -130,11 +136,22 @@ class Trainer:
     b1, b2 = self.cfg.adam_beta1, self.cfg.adam_beta2
     self._hyper[key].fill_(lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
 
-  def _adam(self, store, key):
+  def _apply(self, which):
+    """The optimizer step of one sess.run: which == "gv" (opt_g and opt_v, net.py:330-331) or "c" (opt_c, net.py:362).
+    world > 1: ONE gradient exchange over the flat buffer, the mean (1/world) folded into Adam."""
     b1, b2 = self.cfg.adam_beta1, self.cfg.adam_beta2
+    if which == "gv":
+      buf, parts = self.gv, ((self.gen, "g"), (self.val, "v"))
+    else:
+      buf, parts = self.cri, ((self.cri, "c"),)
+    if self._peer is not None:
+      second = self._hyper[parts[1][1]] if len(parts) > 1 else None
+      self._peer[which].allreduce_adam(buf.flat, buf.m, buf.v, self._hyper[parts[0][1]], parts[0][0].flat.numel(), second, b1, b2)
+      return
     if self.world > 1:
-      dist.all_reduce(store.grad)                                # ONE all-reduce per optimizer step
-    K.adam(store.flat, store.grad, store.m, store.v, self._hyper[key], b1, b2, 1e-8, 1.0 / self.world)
+      dist.all_reduce(buf.grad)                                  # ONE all-reduce per optimizer step
+    for store, key in parts:
+      K.adam(store.flat, store.grad, store.m, store.v, self._hyper[key], b1, b2, 1e-8, 1.0 / self.world)
 
   # ---- CUDA graphs: each step is a fixed launch sequence, captured once and replayed ---------
   def enable_graphs(self, B=None):
@@ -147,14 +164,14 @@ class Trainer:
     self._gi = dict(img=z(B, 64, 64, 3), states=z(B, self.cfg.num_state_dim), noise=z(B), drop_f=z(B, 4, 4, 256),
                     drop_s=z(B, 4, 4, 256), progress=z(1))
     self._ci = dict(real=z(B, 64, 64, 3), fake=z(B, 64, 64, 3), alpha=z(B))
-    snap = [t.clone() for s in (self.gen, self.val, self.cri) for t in (s.flat, s.m, s.v)]
+    snap = [t.clone() for s in (self.gv, self.cri) for t in (s.flat, s.m, s.v)]
     ema_snap = self.ema_state.clone()
     for k in "gvc":
       self._hyper[k].zero_()
-    # world > 1: the graphs hold forward + backward only; the NCCL all-reduce and the fused Adam
-    # are enqueued right after each replay (3 more launches per step) -- collectives inside a
-    # captured graph hung on this stack, and keeping NCCL out of the capture is always legal
-    self._graph_apply = self.world == 1
+    # world > 1 with the peer-memory transport: the exchange + Adam is ONE kernel node inside the graph.  With the
+    # dist.all_reduce fallback the graphs hold forward + backward only and the all-reduce + Adam are enqueued
+    # right after each replay (a process-group collective is not captured).
+    self._graph_apply = self.world == 1 or self._peer is not None
     ga = self._graph_apply
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
@@ -176,8 +193,10 @@ class Trainer:
     with torch.cuda.graph(self._cgraph):
       self._cout = self._critic_impl(self._ci["real"], self._ci["fake"], self._ci["alpha"], ga)
     self.graph_launches = {"generator": l1 - l0, "critic": _ops.launch_count - l1}   # own kernels per replay
+    if self.world > 1:
+      dist.barrier()                                             # the capture runs ran real exchanges: leave them together
     it = iter(snap)
-    for s in (self.gen, self.val, self.cri):
+    for s in (self.gv, self.cri):
       for t in (s.flat, s.m, s.v):
         t.copy_(next(it))
     self.ema_state.copy_(ema_snap)
@@ -204,8 +223,7 @@ class Trainer:
       gi["drop_f"].copy_(drop_f); gi["drop_s"].copy_(drop_s); gi["progress"].fill_(float(progress))
       graph.replay()
       if not self._graph_apply:
-        self._adam(self.gen, "g")
-        self._adam(self.val, "v")
+        self._apply("gv")
       return self._gout
     prog = torch.full((1,), float(progress), device=self.device)
     return self._generator_impl(fake_input, states, noise, drop_f, drop_s, prog, is_train, apply)
@@ -237,8 +255,7 @@ class Trainer:
     g_img = g_img + g_img_v
     self.policy.backward(c, g_img, seeds[4], seeds[3])
     if apply:
-      self._adam(self.gen, "g")
-      self._adam(self.val, "v")
+      self._apply("gv")
     return dict(fake_output=c.out, new_states=c.new_states, g_loss=losses[0], v_loss=losses[1], ctx=c,
                 fake_logit=cc_out.logit, old_value=v_old.logit, new_value=v_new.logit, seeds=seeds)
 
@@ -254,7 +271,7 @@ class Trainer:
       ci["real"].copy_(real); ci["fake"].copy_(fake); ci["alpha"].copy_(alpha)
       graph.replay()
       if not self._graph_apply:
-        self._adam(self.cri, "c")
+        self._apply("c")
         self._ema_update(self._cout["c_average"])                # rank-local shard mean (a logging statistic)
       return self._cout
     return self._critic_impl(real, fake, alpha, apply)
@@ -292,7 +309,7 @@ class Trainer:
       out = dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit,
                  c_average=c_average)
     if apply:
-      self._adam(self.cri, "c")
+      self._apply("c")
     K.join()
     return out
 

@@ -360,6 +360,37 @@ int exp_interpolate(const float* real, const float* fake, const float* alpha, fl
                     void* stream);
 int exp_gp_scale(const float* g, float* u, float* norm, float lambda, int B, int n, void* stream);
 
+/* ---- data-parallel optimizer step over NVLink peer memory (one process per GPU) -------------------------
+ * The reference is single-GPU; this is the collective of SURVEY 8e / C1: ONE exchange per
+ * optimizer step on the flat gradient buffer -- theta_g and theta_v together, both optimizers run in the same
+ * sess.run (net.py:330-331); theta_c in each critic step (net.py:362) -- fused with the Adam update.
+ * All-reduce (sum, fixed rank order) of `n` floats across `world` GPUs followed by Adam on the local replica
+ * with grad_scale = 1/world, in ONE kernel: reduce-scatter and all-gather through peer loads over NVLink, two
+ * flag barriers, no host involvement (the launch is a plain kernel node of the step's CUDA graph).
+ *   grads_host / red_host / flags_host: HOST arrays of `world` DEVICE pointers -- entry q is rank q's gradient
+ *     buffer [n], reduction scratch [n] and flag block (exp_dp_flag_bytes() bytes, zero-filled once), mapped into
+ *     this process (cudaIpcOpenMemHandle; entry `rank` is this rank's own memory).  Every rank must pass the
+ *     buffers in the same rank order and launch the same sequence of calls per flag block.
+ *   n % (4 * world) == 0; elements [0, n_a) use lr_t = hyper_a[0], elements [n_a, n) hyper_b[0] (device scalars,
+ *     as in exp_adam; n_a % 4 == 0; hyper_b may be NULL when n_a == n).
+ * The replicas stay bit-identical: each element is reduced by one rank and read by all.  world <= exp_dp_max_world().
+ *
+ * IPC plumbing (host side, once per buffer): exp_dp_ipc_export returns the CUDA IPC handle
+ * (exp_dp_ipc_handle_bytes() bytes) of the device allocation that contains `dev_ptr` and the offset of `dev_ptr`
+ * inside it; the peers receive both (any host channel), exp_dp_ipc_open maps the allocation into the calling
+ * process -- in the CURRENT device's context, with peer access to the owning GPU (cudaIpcMemLazyEnablePeerAccess)
+ * -- and returns its base; the buffer is at base + offset.  One open per handle and process; exp_dp_ipc_close
+ * unmaps.  These are the only calls of the library that touch the CUDA memory manager. */
+size_t exp_dp_ipc_handle_bytes(void);
+int exp_dp_ipc_export(const void* dev_ptr, void* handle_out, size_t* offset_out);
+int exp_dp_ipc_open(const void* handle, void** base_out);
+int exp_dp_ipc_close(void* base);
+size_t exp_dp_flag_bytes(void);
+int exp_dp_max_world(void);
+int exp_dp_allreduce_adam(float* params, float* m, float* v, const float* const* grads_host, float* const* red_host,
+                          unsigned* const* flags_host, int world, int rank, const float* hyper_a, size_t n_a,
+                          const float* hyper_b, size_t n, float beta1, float beta2, float eps, void* stream);
+
 /* Fused Adam over one flat buffer (tf.train.AdamOptimizer, config_example.py:158):
  * hyper[0] (device) = lr * sqrt(1-beta2^t) / (1-beta1^t); g is multiplied by grad_scale. */
 int exp_adam(float* params, const float* grads, float* m, float* v, const float* hyper, float beta1,

@@ -1,13 +1,15 @@
-"""CPU / gloo (world_size 2) coverage of the N>1 host logic: batch sharding, flat gradient
-all-reduce + mean factor, identical initial weights, distinct per-rank random streams and replay
-shards.  (The CUDA kernels are not involved: ParamStore and ReplayMemory are plain torch tensors.)"""
+"""gloo (world_size 2) coverage of the N > 1 path: batch sharding, ONE flat theta_g + theta_v buffer and its all-reduce,
+identical initial weights, distinct per-rank random streams and replay shards (CPU); the Trainer's own world > 1
+branch on two processes sharing cuda:0 (-m gpu); data-parallel equivalence of the oracle train step (CPU)."""
 import os
 
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from exposure_b200.dp import allreduce_grads, rank_seed, shard_range
+import pytest
+
+from exposure_b200.dp import rank_seed, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -25,19 +27,28 @@ def _worker(rank, world, port, q):
   os.environ["MASTER_PORT"] = str(port)
   dist.init_process_group("gloo", rank=rank, world_size=world)
   try:
-    from exposure_b200.nets import CriticNet, ParamStore
+    from exposure_b200.nets import CriticNet, ParamArena, ParamStore, PolicyNet
     from exposure_b200.replay import ReplayMemory, SyntheticProvider
     from exposure_b200.trainer import default_cfg
     dev = torch.device("cpu")
-    store = ParamStore(dev)
-    CriticNet(store, "critic", n_states=0)
-    store.finalize(seed=5)                       # same seed on every rank -> identical replicas
-    w = [torch.zeros_like(store.flat) for _ in range(world)]
-    dist.all_gather(w, store.flat)
+    # theta_g and theta_v share ONE flat buffer (one exchange per generator step, net.py:330-331)
+    gen, val = ParamStore(dev), ParamStore(dev)
+    PolicyNet(gen, n_states=11, scope="generator")
+    CriticNet(val, "rl_value/critic", n_states=11)
+    arena = ParamArena(dev, [gen, val], [5, 6])            # same seeds on every rank -> identical replicas
+    layout_ok = (gen.flat.data_ptr() == arena.flat.data_ptr() and
+                 val.flat.data_ptr() == arena.flat.data_ptr() + 4 * gen.padded() and
+                 arena.numel == gen.padded() + val.padded() and arena.numel % (4 * 16) == 0 and
+                 gen.count() == 6123680 and val.count() == 1221857)
+    w = [torch.zeros_like(arena.flat) for _ in range(world)]
+    dist.all_gather(w, arena.flat)
     same_init = all(torch.equal(w[0], t) for t in w)
-    store.grad.fill_(float(rank + 1))
-    scale = allreduce_grads(store)
-    ok_sum = bool(torch.all(store.grad == float(sum(range(1, world + 1)))))
+    gen.g["generator/Conv/weights"].fill_(float(rank + 1))
+    val.g["rl_value/critic/fully_connected_1/biases"].fill_(10.0 * (rank + 1))
+    dist.all_reduce(arena.grad)                            # what Trainer._apply("gv") does on the fallback transport
+    tot = float(sum(range(1, world + 1)))
+    ok_sum = bool(torch.all(gen.grad[:gen.g["generator/Conv/weights"].numel()] == tot)) and \
+        float(val.g["rl_value/critic/fully_connected_1/biases"]) == 10.0 * tot
     cfg = default_cfg()
     cfg.batch_size = 8
     cfg.replay_memory_size = 16
@@ -48,12 +59,12 @@ def _worker(rank, world, port, q):
     d = [torch.zeros(1) for _ in range(world)]
     dist.all_gather(d, digest)
     distinct = len({float(t) for t in d}) == world
-    q.put((rank, same_init, ok_sum, scale, distinct))
+    q.put((rank, layout_ok, same_init, ok_sum, distinct))
   finally:
     dist.destroy_process_group()
 
 
-def test_two_rank_gradient_allreduce_and_replicas():
+def test_two_rank_joint_buffer_allreduce_and_replicas():
   world = 2
   ctx = mp.get_context("spawn")
   q = ctx.Queue()
@@ -61,15 +72,106 @@ def test_two_rank_gradient_allreduce_and_replicas():
   procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
   for p in procs:
     p.start()
-  res = [q.get(timeout=120) for _ in range(world)]
+  res = [q.get(timeout=180) for _ in range(world)]
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
-  for rank, same_init, ok_sum, scale, distinct in res:
+  for rank, layout_ok, same_init, ok_sum, distinct in res:
+    assert layout_ok, "theta_g / theta_v are not two slices of one padded flat buffer"
     assert same_init, "weight replicas differ across ranks"
-    assert ok_sum, "all-reduce did not sum the flat gradient buffer"
-    assert scale == 0.5
+    assert ok_sum, "all-reduce did not sum the joint gradient buffer"
     assert distinct, "ranks drew identical replay batches"
+
+
+# ---- the Trainer's own world > 1 branch (graph replay -> exchange -> Adam with 1/world), two ranks --------------
+def _trainer_worker(rank, world, port, q):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  torch.cuda.set_device(0)
+  dist.init_process_group("gloo", rank=rank, world_size=world)       # both ranks share cuda:0: gloo moves CUDA tensors
+  try:
+    from oracle import filters as OF
+    from exposure_b200.trainer import Trainer
+    dev = torch.device("cuda", 0)
+    t = Trainer(device=dev, seed=3)
+    assert t.world == world and t._peer is None                       # not an NCCL group: dist.all_reduce transport
+    B = 8
+    g = torch.Generator().manual_seed(5)
+    img = (OF.synth_images(B, 64, 64, seed=21, stress=False) * 3).to(dev)
+    real = (OF.synth_images(B, 64, 64, seed=31, stress=False) * 6).clamp(0, 1.2).to(dev)
+    states = torch.zeros(B, 11, device=dev)
+    states[:, 2] = torch.tensor([0, 1, 2, 3, 4, 4, 6, 7.0], device=dev)
+    noise = torch.rand(B, generator=g).to(dev)
+    drop_f = ((torch.rand(B, 4, 4, 256, generator=g) < 0.5).float() * 2).to(dev)
+    drop_s = ((torch.rand(B, 4, 4, 256, generator=g) < 0.5).float() * 2).to(dev)
+    alpha = torch.rand(B, generator=g).to(dev)
+    with torch.no_grad():
+      t.cri.p["critic/fully_connected_1/weights"].mul_(40.0)          # gradient penalty active
+    p0 = [t.gv.flat.clone(), t.cri.flat.clone()]
+    b, e = shard_range(B, rank, world)
+    sl = slice(b, e)
+    out = t.generator_step(img[sl].contiguous(), states[sl].contiguous(), noise[sl].contiguous(), drop_f[sl].contiguous(),
+                           drop_s[sl].contiguous(), 0.3, lr_g=1e-5, apply=True)
+    fake = torch.cat([o.clone() for o in _gather(out["fake_output"], world)])    # the global batch of generator outputs
+    t.critic_step(real[sl].contiguous(), fake[sl].contiguous(), alpha[sl].contiguous(), lr_c=1e-5, apply=True)
+    torch.cuda.synchronize()
+    mean_gv, mean_c = t.gv.grad / world, t.cri.grad / world           # the exchanged SUM times the factor Adam applies
+    after = [t.gv.flat.clone(), t.cri.flat.clone()]
+    reps = [_gather(a, world) for a in after]
+    replicas_equal = all(torch.equal(r[0], x) for r in reps for x in r)
+    res = None
+    if rank == 0:
+      # the same two steps on the GLOBAL batch by a single-process trainer (world forced to 1)
+      ref = Trainer(device=dev, seed=3)
+      ref.world, ref._peer = 1, None
+      with torch.no_grad():
+        ref.cri.p["critic/fully_connected_1/weights"].mul_(40.0)
+      ref.generator_step(img, states, noise, drop_f, drop_s, 0.3, lr_g=1e-5, apply=True)
+      ref.critic_step(real, fake, alpha, lr_c=1e-5, apply=True)
+      torch.cuda.synchronize()
+      rel = lambda a, r: float((a - r).abs().max() / (r.abs().max() + 1e-30))
+      # parameters: a first Adam step moves every variable by ~lr * sign(g), so compare in units of that step and count
+      # outliers (a gradient that is pure rounding noise may flip sign between the two summation orders)
+      def off(a, r, p):
+        step = float((r - p).abs().max())
+        return float(((a - r).abs() > 0.05 * step).float().mean()), step
+      res = (rel(mean_gv, ref.gv.grad), rel(mean_c, ref.cri.grad), off(after[0], ref.gv.flat, p0[0]), off(after[1], ref.cri.flat, p0[1]))
+    q.put((rank, replicas_equal, res))
+    dist.barrier()
+  finally:
+    dist.destroy_process_group()
+
+
+def _gather(t, world):
+  out = [torch.zeros_like(t) for _ in range(world)]
+  dist.all_gather(out, t.contiguous())
+  return out
+
+
+@pytest.mark.gpu
+def test_trainer_two_ranks_equal_the_global_batch_step(built_lib):
+  """drives Trainer._apply itself with world_size 2 (two processes on cuda:0, gloo): shard
+  gradients exchanged over the joint theta_g + theta_v buffer and over theta_c, mean folded into Adam; replicas
+  stay identical and equal the single-process step on the global batch (gradients to 1e-4 of each buffer's max,
+  parameters to a fraction of one Adam step)."""
+  world = 2
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 29300 + os.getpid() % 500
+  procs = [ctx.Process(target=_trainer_worker, args=(r, world, port, q)) for r in range(world)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=300) for _ in range(world)]
+  for p in procs:
+    p.join(timeout=120)
+    assert p.exitcode == 0
+  for rank, replicas_equal, r in res:
+    assert replicas_equal, "replicas diverged after one data-parallel step"
+    if r is not None:
+      g_gv, g_c, (frac_gv, step_gv), (frac_c, step_c) = r
+      assert g_gv < 1e-4 and g_c < 1e-4, (g_gv, g_c)
+      assert step_gv > 0 and step_c > 0
+      assert frac_gv < 2e-3 and frac_c < 2e-3, r
 
 
 # ---- data-parallel equivalence of the train step (SURVEY 8e): every loss is a batch mean and nothing couples

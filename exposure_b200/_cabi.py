@@ -91,6 +91,17 @@ SIGNATURES = {
                                _c_void_p, _c_void_p, _c_void_p]),
     "exp_interpolate": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "exp_gp_scale": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int, _c_void_p]),
+    "exp_critic_inputs": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "exp_critic_scalars": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_float, _c_void_p, _c_float, _c_void_p, _c_void_p]),
+    "exp_heads_fc2_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int,
+                                   _c_void_p, _c_int, _c_int, _c_void_p]),
+    "exp_heads_select": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_int,
+                                  _c_void_p]),
+    "exp_heads_fc2_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int,
+                                   _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "exp_colsum_multi_workspace_bytes": (_c_size_t, [_c_void_p, _c_void_p, _c_int]),
+    "exp_colsum_multi": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
+    "exp_stats_bwd_gin": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
     "exp_dp_ipc_handle_bytes": (_c_size_t, []),
     "exp_dp_ipc_export": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
     "exp_dp_ipc_open": (_c_int, [_c_void_p, _c_void_p]),

@@ -125,7 +125,9 @@ class ConvStack:
     given ctx.feat = a4 * drop_mul (tf.nn.dropout, agent.py:36) else ctx.feat = a4 (flattened)."""
     c = _Ctx()
     c.img, c.vec = img, vec
-    a = K.conv_fwd(img, self.W(0), self.b(0), vec=vec, shift=0.5)
+    # ONE staging copy of the enriched first-layer input serves the forward and the weight gradient
+    c.staged = K.stage_first_layer(img, vec, 0.5, CONV_CH[0])
+    a = K.conv_fwd(img, self.W(0), self.b(0), vec=vec, shift=0.5, staged=c.staged)
     acts = [a]
     for i in (1, 2):
       a = K.conv_fwd(a, self.W(i), self.b(i))
@@ -140,44 +142,49 @@ class ConvStack:
     c.acts = acts
     return c
 
-  def backward(self, c, delta4, param_grads=True, accumulate=False, sl=None):
-    """delta4 [N,4,4,256] = dL/d(pre-activation of conv 4).  Fills c.deltas[0..3].  The weight / bias
-    gradients of layer i only need delta_i: they are forked onto side streams and overlap the rest of
-    the dgrad chain (parallel branches of the CUDA graph)."""
+  def backward(self, c, delta4, param_grads=True, accumulate=False, sl=None, bias_tasks=None):
+    """delta4 [N,4,4,256] = dL/d(pre-activation of conv 4).  Fills c.deltas[0..3].  The weight gradient of
+    layer i only needs delta_i: it is forked onto a side stream and overlaps the rest of the dgrad chain
+    (parallel branches of the CUDA graph).  The four bias gradients -- plus whatever column sums the caller
+    hands in through `bias_tasks` (its FC layers) -- are ONE launch at the end (exp_colsum_multi)."""
     d = delta4
     deltas = [None, None, None, d]
     c.deltas = deltas
     for i in (3, 2, 1):
       if param_grads:
         with K.fork(i & 1):
-          self._layer_grads(c, i, accumulate, sl)
+          self._layer_wgrad(c, i, accumulate, sl)
       a_in = c.acts[i - 1]
       d = K.conv_dgrad(d, self.W(i), tuple(a_in.shape), a_in=a_in)
       deltas[i - 1] = d
     if param_grads:
       with K.fork(0):
-        self._layer_grads(c, 0, accumulate, sl)
+        self._layer_wgrad(c, 0, accumulate, sl)
+      with K.fork(1):
+        K.colsum_multi(self._bias_tasks(c, accumulate, sl) + list(bias_tasks or []))
       K.join()
 
-  def _layer_grads(self, c, i, accumulate, sl):
+  def _layer_wgrad(self, c, i, accumulate, sl):
     s = sl if sl is not None else slice(None)
     g = self.store.g
     d = c.deltas[i][s]
     if i == 0:
-      K.conv_wgrad(c.img[s], d, vec=c.vec[s], shift=0.5, out=g[self.names[0] + "/weights"], accumulate=accumulate)
+      K.conv_wgrad(c.img[s], d, vec=c.vec[s], shift=0.5, out=g[self.names[0] + "/weights"], accumulate=accumulate,
+                   staged=c.staged[s] if c.staged is not None else None)
     else:
       K.conv_wgrad(c.acts[i - 1][s], d, out=g[self.names[i] + "/weights"], accumulate=accumulate)
-    gb = g[self.names[i] + "/biases"]
-    if accumulate:
-      gb += K.colsum(d)
-    else:
-      K.colsum(d, out=gb)
 
-  def param_grads(self, c, accumulate=False, sl=None):
+  def _bias_tasks(self, c, accumulate, sl):
+    s = sl if sl is not None else slice(None)
+    return [(c.deltas[i][s], self.store.g[self.names[i] + "/biases"], accumulate) for i in range(4)]
+
+  def param_grads(self, c, accumulate=False, sl=None, bias_tasks=None):
     """wgrad + bias grads from the samples in `sl` (a slice over the batch; default all)."""
     for i in range(4):
       with K.fork(i & 1):
-        self._layer_grads(c, i, accumulate, sl)
+        self._layer_wgrad(c, i, accumulate, sl)
+    with K.fork(1):
+      K.colsum_multi(self._bias_tasks(c, accumulate, sl) + list(bias_tasks or []))
     K.join()
 
   def input_grad(self, c, sl=None):
@@ -190,7 +197,8 @@ class ConvStack:
   def tangent(self, c, sl, t_img, t_vec):
     """Forward-mode tangents t1..t4 of the samples in sl for input tangent (t_img, t_vec)."""
     s = sl
-    t = K.conv_fwd(t_img, self.W(0), None, vec=t_vec, shift=0.0, mask_ref=c.acts[0][s])
+    c.t_staged = K.stage_first_layer(t_img, t_vec, 0.0, CONV_CH[0])
+    t = K.conv_fwd(t_img, self.W(0), None, vec=t_vec, shift=0.0, mask_ref=c.acts[0][s], staged=c.t_staged)
     ts = [t]
     for i in (1, 2, 3):
       t = K.conv_fwd(t, self.W(i), None, mask_ref=c.acts[i][s])
@@ -201,7 +209,8 @@ class ConvStack:
     """Accumulate d<u, dD/dx>/dW_k = wgrad(t_{k-1}, delta_k)."""
     g = self.store.g
     with K.fork(0):
-      K.conv_wgrad(t_img, c.deltas[0][sl], vec=t_vec, shift=0.0, out=g[self.names[0] + "/weights"], accumulate=True)
+      K.conv_wgrad(t_img, c.deltas[0][sl], vec=t_vec, shift=0.0, out=g[self.names[0] + "/weights"], accumulate=True,
+                   staged=getattr(c, "t_staged", None))
     for i in (1, 2, 3):
       with K.fork(i & 1):
         K.conv_wgrad(ts[i - 1], c.deltas[i][sl], out=g[self.names[i] + "/weights"], accumulate=True)
@@ -239,38 +248,37 @@ class CriticNet:
     c.d_h = K.fc_dgrad(c.d_fc2, p[self.fc2 + "/weights"], mul_act=c.h)
     if param_grads:
       with K.fork(2):
-        self._fc_grads(c, accumulate, sl)
+        self._fc_wgrads(c, accumulate, sl)
     d4 = K.fc_dgrad(c.d_h, p[self.fc1 + "/weights"], mul_act=c.feat)
-    self.conv.backward(c, d4.view(-1, 4, 4, CONV_CH[3]), param_grads=param_grads, accumulate=accumulate, sl=sl)
+    self.conv.backward(c, d4.view(-1, 4, 4, CONV_CH[3]), param_grads=param_grads, accumulate=accumulate, sl=sl,
+                       bias_tasks=self._fc_bias_tasks(c, accumulate, sl) if param_grads else None)
     K.join()
 
   def param_grads(self, c, accumulate=False, sl=None):
     with K.fork(2):
-      self._fc_grads(c, accumulate, sl)
-    self.conv.param_grads(c, accumulate=accumulate, sl=sl)
+      self._fc_wgrads(c, accumulate, sl)
+    self.conv.param_grads(c, accumulate=accumulate, sl=sl, bias_tasks=self._fc_bias_tasks(c, accumulate, sl))
     K.join()
 
-  def _fc_grads(self, c, accumulate, sl):
+  def _fc_wgrads(self, c, accumulate, sl):
     s = sl if sl is not None else slice(None)
     g = self.store.g
     K.fc_wgrad(c.feat[s], c.d_h[s], out=g[self.fc1 + "/weights"], accumulate=accumulate)
     K.fc_wgrad(c.h[s], c.d_fc2[s], out=g[self.fc2 + "/weights"], accumulate=accumulate)
-    for name, d in ((self.fc1, c.d_h[s]), (self.fc2, c.d_fc2[s])):
-      if accumulate:
-        g[name + "/biases"] += K.colsum(d)
-      else:
-        K.colsum(d, out=g[name + "/biases"])
+
+  def _fc_bias_tasks(self, c, accumulate, sl):
+    s = sl if sl is not None else slice(None)
+    g = self.store.g
+    return [(c.d_h[s], g[self.fc1 + "/biases"], accumulate), (c.d_fc2[s], g[self.fc2 + "/biases"], accumulate)]
 
   def image_grad(self, c, sl=None, g_direct_extra=None):
     """dL/dimages for the samples in sl: layer-1 dgrad, image channels + J_stats^T of the
     three statistic channels (tf.gradients through critics.py:48-87)."""
     s = sl if sl is not None else slice(None)
     g_in = self.conv.input_grad(c, sl)                         # [n,64,64,cin]
-    n = g_in.shape[0]
-    g_vec = K.colsum(g_in, batch=n).reshape(n, -1)             # per-image channel sums
-    g_stat = g_vec[:, -3:].contiguous()
-    g_img = g_in[..., :3].contiguous()
-    return K.stats_bwd(c.img[s], c.stats[s], g_stat, g_direct=g_img)
+    # image channels pass through, the three tiled statistic channels are summed per image and pulled back through
+    # J_stats^T -- one launch (exp_stats_bwd_gin)
+    return K.stats_bwd_gin(c.img[s], c.stats[s], g_in)
 
   def gradient_penalty_grads(self, c, sl, u):
     """Accumulate d<u, d logit/d image>/dtheta for the samples in sl (net.py:181-194):
@@ -318,7 +326,12 @@ class PolicyNet:
     store.add(self.sfc2 + "/weights", (FC1, self.n_filters), FC1, self.n_filters)
     store.add(self.sfc2 + "/biases", (self.n_filters,))
     self.ostride = max(self.out_dims)          # 30
-    self._n_of_id = torch.tensor(NUM_PARAMS, device=store.device, dtype=torch.long)
+    self._heads = None                         # K.HeadsLayout, built on first use (needs the finalized store)
+
+  def heads(self):
+    if self._heads is None:
+      self._heads = K.HeadsLayout(self.store, self.fc2, self.out_dims, list(NUM_PARAMS), FC1, MASK_PARAMS)
+    return self._heads
 
   def forward(self, img, states, noise, drop_f, drop_s, is_train, progress, cfg, high_res=None):
     """img [B,64,64,3], states [B,11], noise [B] (= z[:,0]), drop_* [B,4,4,256] in {0,2}.
@@ -337,30 +350,23 @@ class PolicyNet:
     c.f = self.fe.forward(img, states, drop_mul=drop_f)
     # filter heads (filters.py:28-44)
     c.H = K.fc_fwd(c.f.feat, p[self.fc1_all + "/weights"], p[self.fc1_all + "/biases"], mode=K.FC_LRELU)
-    c.O = torch.zeros(B, self.n_filters, self.ostride, device=img.device)
-    Oflat = c.O.view(B, -1)
-    for j, name in enumerate(self.fc2):
-      K.fc_fwd(c.H[:, j * FC1:(j + 1) * FC1], p[name + "/weights"], p[name + "/biases"], mode=K.FC_LINEAR,
-               out=Oflat[:, j * self.ostride:j * self.ostride + self.out_dims[j]])
+    c.O = K.heads_fc2_fwd(self.heads(), c.H)          # all 8 fc2 layers: [B, 8, 30], one launch
     K.join()
     # action selection (agent.py:100-122)
     c.pdf, c.ids, c.surrogate, c.entropy, c.pen_head, c.new_states = K.policy_head_fwd(
         c.sel_logits, noise, states, is_train, progress, cfg)
     # only the selected filter is evaluated (agent.py:124-125 computes all 8 and one-hot sums); an id of -1
     # (pdf_sample with u == 0: all-zero one-hot row) makes the step kernels write a black image themselves
-    safe = c.ids.clamp(min=0).long()
-    c.logits_sel = c.O[torch.arange(B, device=img.device), safe][:, :F.PSTRIDE].contiguous()
-    c.params = F.filter_regress_fwd(c.logits_sel, c.ids)
     c.masking = bool(getattr(cfg, "masking", False))
+    c.logits_sel, c.mask_logits_sel = K.heads_select(self.heads(), c.O, c.ids, F.PSTRIDE, c.masking)
+    c.params = F.filter_regress_fwd(c.logits_sel, c.ids)
     if not c.masking:
       c.out = F.filter_fwd(img, c.params, c.ids)
       if high_res is not None:
         c.high_res_out = F.filter_fwd(high_res, c.params, c.ids)
     else:
       # cfg.masking (filters.py:62-148): the 6 mask logits of the selected filter are its fc2
-      # outputs [n, n+6); the mask is evaluated inside the masked step kernel
-      c.mask_idx = self._n_of_id[safe][:, None] + torch.arange(MASK_PARAMS, device=img.device)[None, :]
-      c.mask_logits_sel = torch.gather(c.O[torch.arange(B, device=img.device), safe], 1, c.mask_idx).contiguous()
+      # outputs [n, n+6) (c.mask_logits_sel); the mask is evaluated inside the masked step kernel
       c.mask_cfg = (float(cfg.maximum_sharpness), float(cfg.minimum_strength))
       c.out = F.filter_masked_fwd(img, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True)
       if high_res is not None:
@@ -377,36 +383,22 @@ class PolicyNet:
     with K.fork(3):                      # the selector tower is independent of the filter-head tower
       self._selector_backward(c, g_surrogate, g_penalty)
     g_img = K.overexposure_bwd(c.out, g_penalty, g_in=g_out)
+    g_mask = None
     if not c.masking:
       _, g_params = F.filter_bwd(c.img, g_img, c.params, c.ids, need_gx=False)
     else:
       _, g_params, g_mask = F.filter_masked_bwd(c.img, g_img, c.params, c.mask_logits_sel, c.ids, *c.mask_cfg, True,
                                                 need_gx=False)
-    g_logits_sel = F.filter_regress_bwd(c.logits_sel, g_params, c.ids)           # [B,24]
-    G_O = torch.zeros_like(c.O)
-    safe = c.ids.clamp(min=0).long()
-    valid = (c.ids >= 0).to(g_logits_sel.dtype)[:, None]
-    if not c.masking:
-      G_O[torch.arange(B, device=c.img.device), safe, :F.PSTRIDE] = g_logits_sel * valid
-    else:
-      row = torch.zeros(B, self.ostride, device=c.img.device)
-      row[:, :F.PSTRIDE] = g_logits_sel * valid                                  # entries >= n are 0
-      row.scatter_add_(1, c.mask_idx, g_mask[:, :MASK_PARAMS] * valid)
-      G_O[torch.arange(B, device=c.img.device), safe] = row
-    G_Oflat = G_O.view(B, -1)
-    d_H = torch.empty_like(c.H)
-    for j, name in enumerate(self.fc2):
-      dy = G_Oflat[:, j * self.ostride:j * self.ostride + self.out_dims[j]]
-      Hj = c.H[:, j * FC1:(j + 1) * FC1]
-      with K.fork(j & 1):                 # the head's own gradients are leaves: off the dgrad chain
-        K.fc_wgrad(Hj, dy, out=g[name + "/weights"])
-        g[name + "/biases"].copy_(dy.sum(dim=0))
-      K.fc_dgrad(dy, p[name + "/weights"], mul_act=Hj, out=d_H[:, j * FC1:(j + 1) * FC1])
-    K.fc_wgrad(c.f.feat, d_H, out=g[self.fc1_all + "/weights"])
-    K.colsum(d_H, out=g[self.fc1_all + "/biases"])
+      g_mask = g_mask[:, :MASK_PARAMS].contiguous()
+    g_logits_sel = F.filter_regress_bwd(c.logits_sel, g_params, c.ids)           # [B,24], entries >= n are 0
+    # backward of the select + the 8 fc2 layers in one launch: only the head an image selected receives its
+    # gradient (an id of -1 none), dH comes back with lrelu' applied, fc2 weight / bias gradients are overwritten
+    d_H = K.heads_fc2_bwd(self.heads(), c.H, c.ids, g_logits_sel, g_mask)
+    with K.fork(2):
+      K.fc_wgrad(c.f.feat, d_H, out=g[self.fc1_all + "/weights"])
     a4f = c.f.acts[3].view(B, -1)
     d4 = K.fc_dgrad(d_H, p[self.fc1_all + "/weights"], mul_act=a4f, mul_plain=c.drop_f.view(B, -1))
-    self.fe.backward(c.f, d4.view(B, 4, 4, CONV_CH[3]))
+    self.fe.backward(c.f, d4.view(B, 4, 4, CONV_CH[3]), bias_tasks=[(d_H, g[self.fc1_all + "/biases"], False)])
     K.join()
 
   def _selector_backward(self, c, g_surrogate, g_penalty):
@@ -414,10 +406,9 @@ class PolicyNet:
     B = c.img.shape[0]
     g_sel = K.policy_head_bwd(c.sel_logits, c.ids, g_surrogate, g_penalty, c.progress, c.cfg)
     K.fc_wgrad(c.hs, g_sel, out=g[self.sfc2 + "/weights"])
-    K.colsum(g_sel, out=g[self.sfc2 + "/biases"])
     d_hs = K.fc_dgrad(g_sel, p[self.sfc2 + "/weights"], mul_act=c.hs)
     K.fc_wgrad(c.s.feat, d_hs, out=g[self.sfc1 + "/weights"])
-    K.colsum(d_hs, out=g[self.sfc1 + "/biases"])
     a4s = c.s.acts[3].view(B, -1)
     d4s = K.fc_dgrad(d_hs, p[self.sfc1 + "/weights"], mul_act=a4s, mul_plain=c.drop_s.view(B, -1))
-    self.se.backward(c.s, d4s.view(B, 4, 4, CONV_CH[3]))
+    self.se.backward(c.s, d4s.view(B, 4, 4, CONV_CH[3]),
+                     bias_tasks=[(g_sel, g[self.sfc2 + "/biases"], False), (d_hs, g[self.sfc1 + "/biases"], False)])

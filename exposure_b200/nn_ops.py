@@ -151,20 +151,73 @@ def _enrich32(x, vec, shift):
   xs = _scratch(x.device, "enrich32", B * IH * IW * 32)[:B * IH * IW * 32].view(B, IH, IW, 32)
   _cabi.check(_cabi.lib().exp_conv_enrich32(x.data_ptr(), Cx, _p(vec), Cv, float(shift), xs.data_ptr(), B, IH, IW, _stream()),
               "exp_conv_enrich32")
+  _n()
   return xs
 
 
-def _conv1_stage(x, vec, shift):
+def _conv1_stage(x, vec, shift, own=False):
   B, IH, IW, Cx = x.shape
   Cv = 0 if vec is None else vec.shape[1]
   l = _cabi.lib()
-  xp = _scratch(x.device, "conv1_xp", l.exp_conv1_padded_input_elems(B, IH, IW))
+  n = l.exp_conv1_padded_input_elems(B, IH, IW)
+  xp = torch.empty(n, device=x.device, dtype=torch.float32) if own else _scratch(x.device, "conv1_xp", n)
   _cabi.check(l.exp_conv1_pad_input(x.data_ptr(), Cx, _p(vec), Cv, float(shift), xp.data_ptr(), B, IH, IW, _stream()),
               "exp_conv1_pad_input")
+  _n()
   return xp
 
 
-def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None, out=None, out2=None):
+def stage_first_layer(x, vec, shift, Cout):
+  """The first-layer staging copy of concat(x, tile(vec)) - shift as a tensor of its own ([B, IH+2, IW+2, 16] for
+  Cin <= 16, [B, IH, IW, 32] for 16 < Cin <= 32), or None when the layer needs none.  Hand it to conv_fwd /
+  conv_wgrad as `staged=` (batch slices allowed) so that forward and weight gradient share ONE staging launch."""
+  B, IH, IW, Cx = x.shape
+  Cv = 0 if vec is None else vec.shape[1]
+  if _conv1_path(Cx, Cv, Cout):
+    return _conv1_stage(x, vec, shift, own=True).view(B, IH + 2, IW + 2, 16)
+  if _enrich32_path(Cx, Cv, Cout):
+    xs = torch.empty(B, IH, IW, 32, device=x.device, dtype=torch.float32)
+    _cabi.check(_cabi.lib().exp_conv_enrich32(x.data_ptr(), Cx, _p(vec), Cv, float(shift), xs.data_ptr(), B, IH, IW, _stream()),
+                "exp_conv_enrich32")
+    _n()
+    return xs
+  return None
+
+
+# Padded first-layer weights are a pure function of the weights: inside ONE optimizer step (between two Adam
+# updates) they are built once per weight tensor.  Only the step schedules know that window: they run inside
+# `with weight_cache():`; everywhere else every call pads afresh (a pointer is not an identity).
+_wpad_cache = None
+
+
+@contextlib.contextmanager
+def weight_cache():
+  global _wpad_cache
+  outer = _wpad_cache
+  _wpad_cache = {}
+  try:
+    yield
+  finally:
+    _wpad_cache = outer
+
+
+def _padded_weights(W, Cin, Cout, kind):
+  key = (W.data_ptr(), kind)
+  ent = _wpad_cache.get(key) if _wpad_cache is not None else None
+  if ent is not None:
+    return ent
+  l = _cabi.lib()
+  cp = 16 if kind == "conv1" else 32
+  Wp = torch.empty(16 * cp * Cout, device=W.device, dtype=torch.float32)
+  fn = l.exp_conv1_pad_weights if kind == "conv1" else l.exp_conv_pad_weights32
+  _cabi.check(fn(W.data_ptr(), Cin, Cout, Wp.data_ptr(), _stream()), "exp_conv_pad_weights")
+  _n()
+  if _wpad_cache is not None:
+    _wpad_cache[key] = Wp
+  return Wp
+
+
+def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None, out=None, out2=None, staged=None):
   """4x4 stride-2 SAME conv over concat(x, tile(vec)) - shift.  Forward (bias + lrelu) or,
   with mask_ref, the forward-mode tangent (no bias, times lrelu'(mask_ref)).
   Returns y, or (y, y * post_mul) when post_mul is given."""
@@ -183,22 +236,20 @@ def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None,
   if _conv1_path(Cx, Cv, Cout):
     l = _cabi.lib()
     with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
-      xp = _conv1_stage(x, vec, shift)
-      Wp = _scratch(x.device, "conv1_wp", 16 * 16 * Cout)
-      _cabi.check(l.exp_conv1_pad_weights(W.data_ptr(), Cx + Cv, Cout, Wp.data_ptr(), _stream()), "exp_conv1_pad_weights")
+      xp = staged if staged is not None else _conv1_stage(x, vec, shift)
+      Wp = _padded_weights(W, Cx + Cv, Cout, "conv1")
       _cabi.check(l.exp_conv1_fwd(xp.data_ptr(), Wp.data_ptr(), _p(bias), _p(mask_ref), _p(post_mul), y.data_ptr(), _p(y2),
                                   B, IH, IW, Cout, mode, _stream()), "exp_conv1_fwd")
-    _n(3)
+    _n()
     return y if post_mul is None else (y, y2)
   if _enrich32_path(Cx, Cv, Cout):
     l = _cabi.lib()
     with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
-      xs = _enrich32(x, vec, shift)
-      Wp = _scratch(x.device, "wp32", 16 * 32 * Cout)
-      _cabi.check(l.exp_conv_pad_weights32(W.data_ptr(), Cx + Cv, Cout, Wp.data_ptr(), _stream()), "exp_conv_pad_weights32")
+      xs = staged if staged is not None else _enrich32(x, vec, shift)
+      Wp = _padded_weights(W, Cx + Cv, Cout, "enrich32")
       _cabi.check(l.exp_conv_fwd(xs.data_ptr(), 32, None, 0, 0.0, Wp.data_ptr(), _p(bias), _p(mask_ref), _p(post_mul),
                                  y.data_ptr(), _p(y2), B, IH, IW, Cout, mode, _stream()), "exp_conv_fwd")
-    _n(3)
+    _n()
     return y if post_mul is None else (y, y2)
   with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
     _cabi.check(_cabi.lib().exp_conv_fwd(x.data_ptr(), Cx, _p(vec), Cv, float(shift), W.data_ptr(), _p(bias),
@@ -222,7 +273,7 @@ def conv_dgrad(dy, W, in_shape, a_in=None, out=None):
   return dx
 
 
-def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False):
+def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False, staged=None):
   """gW[4,4,Cin,Cout] (+= when accumulate) for the conv whose input was concat(x, tile(vec)) - shift."""
   _chk(x, "x", 4); _chk(dy, "dy", 4)
   B, IH, IW, Cx = x.shape
@@ -234,24 +285,24 @@ def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False):
   if _conv1_path(Cx, Cv, Cout):
     ws = _workspace(x.device, l.exp_conv1_wgrad_workspace_bytes(B, IH, IW, Cout))
     with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
-      xp = _conv1_stage(x, vec, shift)
+      xp = staged if staged is not None else _conv1_stage(x, vec, shift)
       _cabi.check(l.exp_conv1_wgrad(xp.data_ptr(), dy.data_ptr(), gW.data_ptr(), Cx + Cv, B, IH, IW, Cout, int(accumulate),
                                     ws.data_ptr(), ws.numel(), _stream()), "exp_conv1_wgrad")
-    _n(3)
+    _n(2)
     return gW
   if _enrich32_path(Cx, Cv, Cout):
     Cin = Cx + Cv
     ws = _workspace(x.device, l.exp_conv_wgrad_workspace_bytes(B, IH, IW, 32, Cout))
     gWp = _scratch(x.device, "gwp32", 16 * 32 * Cout)[:16 * 32 * Cout].view(4, 4, 32, Cout)
     with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * Cin):
-      xs = _enrich32(x, vec, shift)
+      xs = staged if staged is not None else _enrich32(x, vec, shift)
       _cabi.check(l.exp_conv_wgrad(xs.data_ptr(), 32, None, 0, 0.0, dy.data_ptr(), gWp.data_ptr(), B, IH, IW, Cout, 0,
                                    ws.data_ptr(), ws.numel(), _stream()), "exp_conv_wgrad")
       if accumulate:
         gW.add_(gWp[:, :, :Cin, :])
       else:
         gW.copy_(gWp[:, :, :Cin, :])
-    _n(4)
+    _n(3)
     return gW
   nbytes = l.exp_conv_wgrad_workspace_bytes(B, IH, IW, Cx + Cv, Cout)
   ws = _workspace(x.device, nbytes)
@@ -460,6 +511,126 @@ def adam(params, grads, m, v, hyper, beta1, beta2, eps=1e-8, grad_scale=1.0):
                                    float(beta1), float(beta2), float(eps), float(grad_scale), params.numel(), _stream()),
               "exp_adam")
   _n()
+
+
+# ---- fused bookkeeping kernels of the train step (csrc/train_glue.cu) -----------------------------------------
+import ctypes as _ct
+
+
+def _iarr(vals):
+  return (_ct.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def critic_inputs(real, fake, alpha, out=None):
+  """X [3B,...] = real | fake | real + alpha (fake - real) (net.py:174-179 + the batch concat), one launch."""
+  _chk(real, "real"); _chk(fake, "fake")
+  B = real.shape[0]
+  n = real.numel() // B
+  X = torch.empty((3 * B,) + tuple(real.shape[1:]), device=real.device, dtype=torch.float32) if out is None else out
+  _cabi.check(_cabi.lib().exp_critic_inputs(real.data_ptr(), fake.data_ptr(), alpha.data_ptr(), X.data_ptr(), B, n, _stream()),
+              "exp_critic_inputs")
+  _n()
+  return X
+
+
+def critic_scalars(logits, norm, lam, ema_state=None, decay=0.99):
+  """out[5] = emd, gradient penalty, critic_gradient_norm, c_loss, c_average; advances the zero-debiased moving
+  average in ema_state [3] when given (net.py:164-168, 185-187, 268-269)."""
+  B = norm.numel()
+  out = torch.empty(8, device=logits.device, dtype=torch.float32)
+  _cabi.check(_cabi.lib().exp_critic_scalars(logits.data_ptr(), norm.data_ptr(), B, float(lam), _p(ema_state), float(decay),
+                                             out.data_ptr(), _stream()), "exp_critic_scalars")
+  _n()
+  return out
+
+
+class HeadsLayout:
+  """Where the n_heads fc2 layers of the filter heads live inside the generator's flat parameter buffer."""
+
+  def __init__(self, store, names, dims, npar, fc1, nmask):
+    self.store, self.n = store, len(names)
+    self.w_off = _iarr([store.offsets[n + "/weights"][0] for n in names])
+    self.b_off = _iarr([store.offsets[n + "/biases"][0] for n in names])
+    self.dims, self.npar = _iarr(dims), _iarr(npar)
+    self.fc1, self.nmask, self.ostride = fc1, nmask, max(dims)
+
+
+def heads_fc2_fwd(L, H):
+  B = H.shape[0]
+  ldh = _mat(H, "H")
+  O = torch.empty(B, L.n, L.ostride, device=H.device, dtype=torch.float32)
+  _cabi.check(_cabi.lib().exp_heads_fc2_fwd(L.store.flat.data_ptr(), L.w_off, L.b_off, L.dims, L.npar, L.n, L.fc1, L.nmask,
+                                            H.data_ptr(), ldh, O.data_ptr(), L.ostride, B, _stream()), "exp_heads_fc2_fwd")
+  _n()
+  return O
+
+
+def heads_select(L, O, ids, selstride, want_mask):
+  B = O.shape[0]
+  sel = torch.empty(B, selstride, device=O.device, dtype=torch.float32)
+  msel = torch.empty(B, L.nmask, device=O.device, dtype=torch.float32) if want_mask else None
+  _cabi.check(_cabi.lib().exp_heads_select(O.data_ptr(), L.ostride, ids.data_ptr(), L.npar, L.n, L.nmask, sel.data_ptr(), selstride,
+                                           _p(msel), B, _stream()), "exp_heads_select")
+  _n()
+  return sel, msel
+
+
+def heads_fc2_bwd(L, H, ids, gsel, gmsel=None):
+  """Returns dH [B, n_heads * fc1]; overwrites the fc2 weight / bias gradients of every head in the store."""
+  B = H.shape[0]
+  ldh = _mat(H, "H")
+  _chk(gsel, "gsel", 2)
+  dH = torch.empty_like(H)
+  assert dH.stride(0) == ldh
+  _cabi.check(_cabi.lib().exp_heads_fc2_bwd(L.store.flat.data_ptr(), L.store.grad.data_ptr(), L.w_off, L.b_off, L.dims, L.npar, L.n,
+                                            L.fc1, L.nmask, H.data_ptr(), ldh, ids.data_ptr(), gsel.data_ptr(), gsel.shape[1],
+                                            _p(gmsel), dH.data_ptr(), B, _stream()), "exp_heads_fc2_bwd")
+  _n()
+  return dH
+
+
+_zero_ws = {}
+
+
+def _zero_workspace(dev, nbytes):
+  """Zero-initialised, self-cleaning workspace per (device, stream): ticket counters of exp_colsum_multi."""
+  key = (dev, torch.cuda.current_stream().cuda_stream)
+  ws = _zero_ws.get(key)
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=dev)
+    _zero_ws[key] = ws
+  return ws
+
+
+def colsum_multi(tasks):
+  """tasks: list of (src [rows, cols] (any leading dims), dst [cols], accumulate) -- up to 8 bias-gradient column sums per
+  launch (deterministic)."""
+  l = _cabi.lib()
+  for i in range(0, len(tasks), 8):
+    part = tasks[i:i + 8]
+    n = len(part)
+    rows = _iarr([t[0].numel() // t[0].shape[-1] for t in part])
+    cols = _iarr([t[0].shape[-1] for t in part])
+    acc = _iarr([1 if t[2] else 0 for t in part])
+    for t in part:
+      _chk(t[0], "colsum source")
+      assert t[1].is_contiguous() and t[1].numel() == t[0].shape[-1]
+    src = (_ct.c_void_p * n)(*[t[0].data_ptr() for t in part])
+    dst = (_ct.c_void_p * n)(*[t[1].data_ptr() for t in part])
+    ws = _zero_workspace(part[0][0].device, l.exp_colsum_multi_workspace_bytes(rows, cols, n))
+    _cabi.check(l.exp_colsum_multi(src, dst, rows, cols, acc, n, ws.data_ptr(), ws.numel(), _stream()), "exp_colsum_multi")
+    _n()
+
+
+def stats_bwd_gin(img, stats, g_in, out=None):
+  """dL/dimages from the layer-1 input gradient g_in [n,H,W,cin] (image channels + J_stats^T of the statistic channels)."""
+  _chk(img, "img", 4); _chk(g_in, "g_in", 4)
+  B, H, W, _ = img.shape
+  g = torch.empty_like(img) if out is None else out
+  _cabi.check(_cabi.lib().exp_stats_bwd_gin(img.data_ptr(), stats.data_ptr(), g_in.data_ptr(), g_in.shape[3], g.data_ptr(), B, H, W,
+                                            _stream()), "exp_stats_bwd_gin")
+  _n()
+  return g
 
 
 # 0 = TMA-fed tcgen05 engine wherever the shape allows it (the product path); 1 = exact-fp32 CUDA-core engine

@@ -228,7 +228,15 @@ class Trainer:
     prog = torch.full((1,), float(progress), device=self.device)
     return self._generator_impl(fake_input, states, noise, drop_f, drop_s, prog, is_train, apply)
 
-  def _generator_impl(self, fake_input, states, noise, drop_f, drop_s, progress, is_train, apply):
+  def _generator_impl(self, *a):
+    with K.weight_cache():                                       # padded first-layer weights: once per step and tensor
+      return self._generator_sched(*a)
+
+  def _critic_impl(self, *a):
+    with K.weight_cache():
+      return self._critic_sched(*a)
+
+  def _generator_sched(self, fake_input, states, noise, drop_f, drop_s, progress, is_train, apply):
     # the two passes over the INPUT batch do not depend on the policy: parallel graph branches
     with K.fork(4):
       cc_in = self.critic.forward(fake_input)                    # fake_input_logit (stop_gradient) net.py:72-73
@@ -276,11 +284,10 @@ class Trainer:
       return self._cout
     return self._critic_impl(real, fake, alpha, apply)
 
-  def _critic_impl(self, real, fake, alpha, apply):
+  def _critic_sched(self, real, fake, alpha, apply):
     B = real.shape[0]
     lam = float(self.cfg.gradient_penalty_lambda)
-    xhat = K.interpolate(real, fake, alpha)
-    X = torch.cat([real, fake, xhat], dim=0)
+    X = K.critic_inputs(real, fake, alpha)                         # real | fake | interpolated, one launch
     c = self.critic.forward(X)
     g_logit = self._g_logit_cache.get(B)                          # constant seeds: d c_loss / d logit
     if g_logit is None:
@@ -301,13 +308,10 @@ class Trainer:
         self.critic.gradient_penalty_grads(c, sl, u)
     logit = c.logit.view(-1)
     with K.fork(7):                                              # logging scalars: off the optimizer's path
-      emd = logit[:B].mean() - logit[B:2 * B].mean()             # net.py:164  emd = -c_loss (before GP)
-      gp = lam * (torch.clamp(norm - 1.0, min=0.0) ** 2).mean()
-      c_average = (logit[:B].mean() + logit[B:2 * B].mean()) * 0.5  # net.py:165 (forward of this step, pre-update)
-      if apply:
-        self._ema_update(c_average)                                 # net.py:166, 268-269: part of opt_c
-      out = dict(emd=emd, gradient_penalty=gp, critic_gradient_norm=norm.mean(), c_loss=-emd + gp, logits=logit,
-                 c_average=c_average)
+      # emd (net.py:164), gradient penalty (185-187), c_loss (151, 194), c_average (165, forward of this step,
+      # pre-update) and the moving average that is part of opt_c (166-168, 268-269): one launch
+      sc = K.critic_scalars(logit, norm, lam, self.ema_state if apply else None)
+      out = dict(emd=sc[0], gradient_penalty=sc[1], critic_gradient_norm=sc[2], c_loss=sc[3], c_average=sc[4], logits=logit)
     if apply:
       self._apply("c")
     K.join()

@@ -360,6 +360,57 @@ int exp_interpolate(const float* real, const float* fake, const float* alpha, fl
                     void* stream);
 int exp_gp_scale(const float* g, float* u, float* norm, float lambda, int B, int n, void* stream);
 
+/* ---- fused bookkeeping kernels of the train step (csrc/train_glue.cu) ---------------------------------------
+ * Each replaces a chain of element-wise / indexing launches of the TF graph (and of a tensor-library port of it).
+ *
+ * exp_critic_inputs: X[0:B] = real, X[B:2B] = fake, X[2B:3B] = real + alpha[b] (fake - real): the three batches the
+ *   critic step scores (net.py:68-71, 174-179) as ONE batch; n floats per image (n % 4 == 0, 16-byte aligned).
+ * exp_critic_scalars: from logits [3B] (real | fake | interpolated) and norm [B] (exp_gp_scale) writes out[0..4] =
+ *   emd (net.py:164), gradient penalty lambda mean(max(norm-1,0)^2) (net.py:185-187), critic_gradient_norm =
+ *   mean(norm), c_loss = -emd + gp (net.py:151,194), c_average (net.py:165) and, when ema_state != NULL, advances
+ *   tf.train.ExponentialMovingAverage(decay, zero_debias=True) of c_average (net.py:119-120, 166-168, 268-269):
+ *   ema_state = [debiased value, biased accumulator, local_step]. */
+int exp_critic_inputs(const float* real, const float* fake, const float* alpha, float* X, int B, int n, void* stream);
+int exp_critic_scalars(const float* logits, const float* norm, int B, float lambda, float* ema_state, float decay,
+                       float* out, void* stream);
+
+/* The fc2 layers of the n_heads filter heads (filters.py:39-44, one Filter per cfg.filters entry, agent.py:58-72) as
+ * single launches.  Head j's weights [fc1, dims[j]] and biases [dims[j]] live at float offsets w_off[j] / b_off[j]
+ * of the flat generator parameter buffer `params` (gradients at the same offsets of `grads`); dims[j] = npar[j]
+ * filter parameters + nmask mask parameters (filters.py:43-44 split).  *_host arrays are HOST arrays of n_heads ints.
+ *   exp_heads_fc2_fwd:  O[b, j, 0:dims[j]] = H[b, j*fc1 : (j+1)*fc1] W_j + bias_j, zeros up to ostride
+ *                       (H [B, ldh] = the lrelu outputs of the heads' fc1 layers, one column block per head)
+ *   exp_heads_select:   sel[b, 0:npar[id]] = O[b, id, 0:npar[id]] (zeros up to selstride), msel[b, 0:nmask] (nullable)
+ *                       = O[b, id, npar[id] : npar[id]+nmask], id = ids[b]; id -1 -> zeros.  This is the one-hot select
+ *                       of agent.py:113-125 applied to the head outputs instead of to 8 filtered images.
+ *   exp_heads_fc2_bwd:  from gsel [B, selstride] = dL/dsel and gmsel [B, nmask] (nullable) writes
+ *                       dH [B, ldh] = dL/d(fc1 pre-activation) (lrelu' applied; zero for the heads an image did not
+ *                       select) and OVERWRITES the fc2 weight / bias gradients of every head in `grads`. */
+int exp_heads_fc2_fwd(const float* params, const int* w_off_host, const int* b_off_host, const int* dims_host,
+                      const int* npar_host, int n_heads, int fc1, int nmask, const float* H, int ldh, float* O,
+                      int ostride, int B, void* stream);
+int exp_heads_select(const float* O, int ostride, const int* ids, const int* npar_host, int n_heads, int nmask,
+                     float* sel, int selstride, float* msel, int B, void* stream);
+int exp_heads_fc2_bwd(const float* params, float* grads, const int* w_off_host, const int* b_off_host,
+                      const int* dims_host, const int* npar_host, int n_heads, int fc1, int nmask, const float* H, int ldh,
+                      const int* ids, const float* gsel, int selstride, const float* gmsel, float* dH, int B,
+                      void* stream);
+
+/* Up to 8 column sums in ONE launch: dst_t[cols_t] (=|+= when accumulate_t) sum over rows of src_t[rows_t, cols_t]
+ * -- the bias gradients of a whole CNN backward (4 conv layers + 2 FC layers).  Deterministic: per-chunk partials,
+ * the last block to arrive for a column block adds them in chunk order.  *_host: HOST arrays of n entries.
+ * workspace: exp_colsum_multi_workspace_bytes() (0 = bad task list), zero-filled once: a fixed 4 KiB block of
+ * self-cleaning ticket counters followed by the partial sums, so one workspace serves any sequence of task lists. */
+size_t exp_colsum_multi_workspace_bytes(const int* rows_host, const int* cols_host, int n);
+int exp_colsum_multi(const float* const* src_host, float* const* dst_host, const int* rows_host, const int* cols_host,
+                     const int* accumulate_host, int n, void* workspace, size_t workspace_bytes, void* stream);
+
+/* exp_stats_bwd fed directly with the layer-1 input gradient g_in [B,H,W,cin] (exp_conv_dgrad into the enriched
+ * input): g_stat[b] = sum over pixels of the last three channels (the tiled statistics, critics.py:77-87),
+ * g_out[B,H,W,3] = g_in[..., 0:3] + J_stats^T g_stat.  One launch instead of colsum + two slices + exp_stats_bwd. */
+int exp_stats_bwd_gin(const float* img, const float* stats, const float* g_in, int cin, float* g_out, int B, int H,
+                      int W, void* stream);
+
 /* ---- data-parallel optimizer step over NVLink peer memory (one process per GPU) -------------------------
  * The reference is single-GPU; this is the collective of SURVEY 8e / C1: ONE exchange per
  * optimizer step on the flat gradient buffer -- theta_g and theta_v together, both optimizers run in the same

@@ -81,40 +81,45 @@ FNAMES = ("exposure", "gamma", "wb", "satplus", "tone", "contrast", "wnb", "colo
 
 
 def traffic(src, dst, config):
-  """DRAM bytes per launch of every filter_step_tma_kernel in an `ncu --set full` report ->
-  the small JSON bench.py reads to fill roofline.traffic (keys = bench.py's kernel names)."""
+  """DRAM bytes per launch of the filter kernels in an `ncu --set full` report -> the small JSON bench.py reads to
+  fill roofline.traffic (keys = bench.py's kernel names).  One entry per captured configuration
+  ({"captures": [{"config", "source", "kernels"}, ...]}); a capture of an already known configuration is merged."""
   import json
   raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
   rows = list(csv.reader(raw.splitlines()))
   hdr, units = rows[0], rows[1]
   idx = {h: i for i, h in enumerate(hdr)}
-  res = {}
-  try:                                   # keep the kernels of an earlier capture of the same configuration
-    prev = json.load(open(dst))
-    if prev.get("config") == config:
-      res = prev["kernels"]
-      src = "%s + %s" % (prev["source"], src) if src not in prev["source"] else prev["source"]
+  try:
+    doc = json.load(open(dst))
+    caps = doc["captures"] if "captures" in doc else [doc]
   except (OSError, ValueError, KeyError):
-    pass
-  for r in rows[2:]:
-    if "filter_chain_fwd_bwd_kernel" in r[idx["Kernel Name"]]:
-      rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT[units[idx["dram__bytes_read.sum"]]]
-      wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
-      res["filter_chain_fwd_bwd"] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
-                                     "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]])}
-      continue
-    m = re.search(r"filter_step_tma_kernel<(?:\(int\))?(\d+), (?:\(bool\))?(\w+), (?:\(bool\))?(\w+)", r[idx["Kernel Name"]])
-    if not m:
-      continue
-    fid, bwd, gx = int(m.group(1)), m.group(2) in ("1", "true"), m.group(3) in ("1", "true")
-    name = ("filter_bwd_" if bwd and gx else "filter_bwd_paramonly_" if bwd else "filter_fwd_") + FNAMES[fid]
+    caps = []
+  ent = next((c for c in caps if c.get("config") == config), None)
+  if ent is None:
+    ent = {"config": config, "source": src, "kernels": {}}
+    caps.append(ent)
+  elif src not in ent["source"]:
+    ent["source"] = "%s + %s" % (ent["source"], src)
+  res = ent["kernels"]
+
+  def put(name, r):
     rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT[units[idx["dram__bytes_read.sum"]]]
     wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
     res[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
-                 "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]])}
-  json.dump({"source": src, "config": config, "note": "ncu --set full --clock-control none, one launch each; "
-             "writes still in L2 at kernel end are not counted by dram__bytes_write", "kernels": res},
-            open(dst, "w"), indent=1, sort_keys=True)
+                 "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]]), "kernel": short(r[idx["Kernel Name"]])}
+
+  for r in rows[2:]:
+    kn = r[idx["Kernel Name"]]
+    if "filter_chain_static_kernel" in kn or "filter_chain_fwd_bwd_kernel" in kn:
+      put("filter_chain_fwd_bwd", r)          # bench.py's name of the whole-chain launch, whichever kernel serves it
+      continue
+    m = re.search(r"filter_step_tma_kernel<(?:\(int\))?(\d+), (?:\(bool\))?(\w+), (?:\(bool\))?(\w+)", kn)
+    if not m:
+      continue
+    fid, bwd, gx = int(m.group(1)), m.group(2) in ("1", "true"), m.group(3) in ("1", "true")
+    put(("filter_bwd_" if bwd and gx else "filter_bwd_paramonly_" if bwd else "filter_fwd_") + FNAMES[fid], r)
+  json.dump({"note": "ncu --set full --clock-control none, one launch each; writes still in L2 at kernel end are not "
+                     "counted by dram__bytes_write", "captures": caps}, open(dst, "w"), indent=1, sort_keys=True)
   print(open(dst).read()[:1500])
 
 

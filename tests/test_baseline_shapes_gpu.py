@@ -1,0 +1,172 @@
+"""GPU parity at the BASELINE.json shapes themselves, with a SAMPLED oracle: the CUDA path runs
+the full configuration, the CPU oracle (fp64) re-computes k randomly chosen images of it -- every filter is per pixel
+and every parameter per image (filters.py:62-99, param[:, None, None, :] broadcasting), so an image of a batch is
+checked exactly like a batch of one.
+
+  configs[1]  8-filter chain fwd+bwd, 64 x 512 x 512 x 3          -> 3 sampled images (fused kernel AND per-step kernels)
+  north star  the same chain at 256 x 512 x 512 x 3                -> 2 sampled images
+  configs[4]  one 4K frame (2160 x 3840), chain fwd+bwd            -> the whole frame
+  configs[2]  evaluate.py inference, 256 x 64 x 64, 5 policy steps -> the whole batch through the oracle's agent_generator
+  configs[3]  train step at batch 64 x 64 x 64                     -> the whole batch through the autograd oracle
+
+Tolerances are the per-filter bars of tests/test_filters_gpu.py compounded over 8 steps (stated there and in
+DESIGN.md section 9): pixels 2e-4 of max(|ref|, 1e-3 max), image gradients 2e-3, parameter gradients 2e-3 of the
+row's max; CNN logits 1e-4; train-step gradients 2e-3 of each variable's max."""
+import pytest
+import torch
+
+from oracle import filters as F
+from oracle import train_step as OT
+
+pytestmark = pytest.mark.gpu
+CHAIN = [F.E, F.G, F.W, F.SP, F.T, F.CT, F.BW, F.C]
+
+
+def _rel(a, b, floor=1e-3):
+  a, b = a.detach().double().cpu(), b.detach().double().cpu()
+  return float(((a - b).abs() / b.abs().clamp_min(floor * float(b.abs().max()) + 1e-30)).max())
+
+
+def _gpu_batch(B, H, W, seed):
+  """The bench's synthetic batch (SURVEY 8d statistics), generated on the device in slices."""
+  g = torch.Generator(device="cuda").manual_seed(seed)
+  x = torch.empty(B, H, W, 3, device="cuda")
+  gy = torch.empty(B, H, W, 3, device="cuda")
+  nb = max(1, min(B, 32))
+  for b0 in range(0, B, nb):
+    n = min(nb, B - b0)
+    v = torch.exp(torch.randn(n, H, W, 3, device="cuda", generator=g) - 3.2).clamp_(0, 4)
+    u = torch.rand(n, H, W, 3, device="cuda", generator=g)
+    hi = 1 + 3 * torch.rand(n, H, W, 3, device="cuda", generator=g)
+    v = torch.where(u < 0.010, hi, v)
+    v = torch.where((u >= 0.010) & (u < 0.011), torch.zeros_like(v), v)
+    v = torch.where((u >= 0.011) & (u < 0.012), torch.full_like(v, 0.001), v)
+    knot = torch.randint(0, 9, (n, H, W, 3), device="cuda", generator=g).float() / 8
+    x[b0:b0 + n] = torch.where((u >= 0.012) & (u < 0.013), knot, v)          # exact clamp / knot values: tie rules
+    gy[b0:b0 + n] = torch.randn(n, H, W, 3, device="cuda", generator=g)
+  return x, gy
+
+
+def _check_sampled(x, gy, lgs, y, gx, gls, picks):
+  for b in picks:
+    y64, gx64, gl64 = F.chain_fwd_bwd(CHAIN, x[b:b + 1].cpu().double(), [l[b:b + 1].cpu().double() for l in lgs],
+                                      gy[b:b + 1].cpu().double())
+    assert _rel(y[b:b + 1], y64) < 2e-4, ("pixels", b)
+    assert _rel(gx[b:b + 1], gx64) < 2e-3, ("image gradient", b)
+    for k, (a, r) in enumerate(zip(gls, gl64)):
+      assert _rel(a[b:b + 1, :r.shape[1]], r, floor=1e-2) < 2e-3, ("parameter gradient", b, k)
+
+
+@pytest.mark.parametrize("B,k", [(64, 3), (256, 2)])
+def test_chain8_at_512x512_against_sampled_oracle(built_lib, B, k):
+  from exposure_b200.chain import FilterChain, FusedFilterChain
+  H = W = 512
+  x, gy = _gpu_batch(B, H, W, seed=100 + B)
+  lgs = [(F.synth_logits(f, B, seed=200 + j) * 0.7).cuda() for j, f in enumerate(CHAIN)]
+  picks = sorted(torch.randperm(B, generator=torch.Generator().manual_seed(B))[:k].tolist())
+  fz = FusedFilterChain(CHAIN, B, torch.device("cuda"))
+  fz.set_logits(lgs)
+  y, gx, _ = fz.forward_backward(x, gy)
+  torch.cuda.synchronize()
+  _check_sampled(x, gy, lgs, y, gx, fz.glogits_list(), picks)
+  if B == 64:                                   # the per-step kernels (the rollout's path) on the same batch
+    ch = FilterChain(CHAIN)
+    y2 = ch.forward(x, lgs)
+    gx2, gl2 = ch.backward(gy)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y) and torch.equal(gx2, gx)       # same per-pixel functions: bit-identical
+    _check_sampled(x, gy, lgs, y2, gx2, gl2, picks[:1])
+
+
+def test_chain8_on_a_4k_frame_against_the_oracle(built_lib):
+  """configs[4]: 3840 x 2160, the whole frame through the fp64 oracle."""
+  from exposure_b200.chain import FusedFilterChain
+  x, gy = _gpu_batch(1, 2160, 3840, seed=77)
+  lgs = [(F.synth_logits(f, 1, seed=300 + j) * 0.7).cuda() for j, f in enumerate(CHAIN)]
+  fz = FusedFilterChain(CHAIN, 1, torch.device("cuda"))
+  fz.set_logits(lgs)
+  y, gx, _ = fz.forward_backward(x, gy)
+  torch.cuda.synchronize()
+  _check_sampled(x, gy, lgs, y, gx, fz.glogits_list(), [0])
+
+
+def test_eval_episode_at_256x64x64_against_the_oracle(built_lib):
+  """configs[2]: evaluate.py inference -- cfg.test_steps policy steps (argmax action, dropout on: agent.py:36,
+  114-116) + the selected filters, batch 256 x 64 x 64, against the oracle's agent_generator (all 8 filters + one-hot
+  select like the reference) fed with the SAME dropout draws."""
+  from exposure_b200.checkpoint import export_named
+  from exposure_b200.evaluate import retouch
+  from exposure_b200.trainer import Trainer
+  t = Trainer(device=torch.device("cuda", 0), seed=5)
+  cfg = t.cfg
+  B = 256
+  img = F.synth_images(B, 64, 64, seed=41, stress=False).cuda()
+  gen = torch.Generator(device="cuda").manual_seed(9)
+  out = retouch(t, img, generator=gen)
+  torch.cuda.synchronize()
+  gen = torch.Generator(device="cuda").manual_seed(9)               # replay the draws retouch() made, in its order
+  draws = [t.draw(B, gen) for _ in range(cfg.test_steps)]
+  P = {n: v.cpu() for n, v in export_named(t)["generator"].items()}
+  x, states = img.cpu(), torch.zeros(B, cfg.num_state_dim)
+  agree = torch.ones(B, dtype=torch.bool)
+  with torch.no_grad():
+    for s, (noise, df, ds, _) in enumerate(draws):
+      x, states, _, _, ids, _ = OT.agent_generator(P, x, states, noise.cpu(), df.cpu(), ds.cpu(), 0, 0.0, cfg)
+      agree &= ids.to(torch.int32) == out["ids"][s].cpu()
+  # an argmax between two nearly equal probabilities may flip between fp32 summation orders: rare, and counted
+  assert float(agree.float().mean()) >= 0.98, float(agree.float().mean())
+  e = (out["output"].cpu()[agree] - x[agree]).abs() / x[agree].abs().clamp_min(1e-3)
+  assert float(e.max()) < 2e-4, float(e.max())
+  assert torch.equal(out["states"].cpu()[agree], states[agree])
+
+
+def test_train_step_at_batch_64_against_the_oracle(built_lib):
+  """configs[3]: generator+value step and critic step at the bench's per-GPU batch (64 x 64 x 64 x 3)."""
+  from exposure_b200.checkpoint import export_named
+  from exposure_b200.trainer import Trainer
+  t = Trainer(device=torch.device("cuda", 0), seed=7)
+  cfg = t.cfg
+  B = 64
+  g = torch.Generator().manual_seed(5)
+  img = F.synth_images(B, 64, 64, seed=21, stress=False).double() * 3
+  states = torch.zeros(B, 11, dtype=torch.float64)
+  states[:, 2] = (torch.arange(B) % 8).double()
+  states[:, 3:] = (torch.rand(B, 8, generator=g) < 0.3).double()
+  noise = torch.rand(B, generator=g, dtype=torch.float64)
+  drop_f = (torch.rand(B, 4, 4, 256, generator=g) < 0.5).double() * 2
+  drop_s = (torch.rand(B, 4, 4, 256, generator=g) < 0.5).double() * 2
+  named = lambda grads=False: {k: {n: v.double().cpu() for n, v in d.items()} for k, d in export_named(t, grads=grads).items()}
+  P = named()
+  ref = OT.generator_step(P["generator"], P["rl_value"], P["critic"], img, states, noise, drop_f, drop_s, 0.3, cfg)
+  f = lambda a: a.float().cuda().contiguous()
+  out = t.generator_step(f(img), f(states), f(noise), f(drop_f), f(drop_s), 0.3, lr_g=1e-5, apply=False)
+  torch.cuda.synchronize()
+  same = out["ctx"].ids.cpu() == ref["ids"].to(torch.int32)
+  assert bool(same.all()), "selected filters differ from the oracle at %s" % (~same).nonzero().flatten().tolist()
+  rel = lambda a, b: float((a.double().cpu() - b).abs().max() / (b.abs().max() + 1e-30))
+  assert rel(out["fake_output"], ref["fake_output"]) < 1e-5
+  assert rel(out["fake_logit"], ref["fake_logit"]) < 1e-4 and rel(out["new_value"], ref["new_value"]) < 1e-4
+  assert abs(float(out["g_loss"]) - float(ref["g_loss"])) < 1e-4 * (1 + abs(float(ref["g_loss"])))
+  assert abs(float(out["v_loss"]) - float(ref["v_loss"])) < 1e-4 * (1 + abs(float(ref["v_loss"])))
+  G = named(grads=True)
+  bad = {}
+  for key, refg in (("generator", ref["grads_g"]), ("rl_value", ref["grads_v"])):
+    for name, gr in refg.items():
+      if float(gr.abs().max()) > 0 and rel(G[key][name], gr) > 2e-3:
+        bad[name] = rel(G[key][name], gr)
+  assert not bad, bad
+  # critic step on the generator's outputs, gradient penalty active
+  with torch.no_grad():
+    t.cri.p["critic/fully_connected_1/weights"].mul_(40.0)
+  P = named()
+  real = (F.synth_images(B, 64, 64, seed=31, stress=False) * 6).clamp(0, 1.2).double()
+  alpha = torch.rand(B, generator=g, dtype=torch.float64)
+  refc = OT.critic_step(P["critic"], real, ref["fake_output"], alpha, cfg)
+  outc = t.critic_step(f(real), f(ref["fake_output"]), f(alpha), lr_c=1e-5, apply=False)
+  torch.cuda.synchronize()
+  assert float(refc["gradient_penalty"]) > 0
+  assert abs(float(outc["emd"]) - float(refc["emd"])) < 1e-4 * (1 + abs(float(refc["emd"])))
+  assert abs(float(outc["gradient_penalty"]) - float(refc["gradient_penalty"])) < 1e-3 * float(refc["gradient_penalty"])
+  Gc = named(grads=True)["critic"]
+  badc = {n: rel(Gc[n], gr) for n, gr in refc["grads_c"].items() if rel(Gc[n], gr) > 2e-3}
+  assert not badc, badc

@@ -389,3 +389,24 @@ def test_errors_are_loud(ops):
     ops.filter_fwd(x, p, 0, variant=1)       # DIRECT needs H*W % 4 == 0
   with pytest.raises(ValueError):
     ops.filter_fwd(x.cpu(), p, 0)            # no CPU fallback
+
+
+def test_satplus_gradient_on_exact_channel_ties(ops):
+  """at pixels where two channels tie for the max / min, and at grey pixels, the CUDA backward
+  follows the documented rule (first channel in R, G, B order is THE max / min; grey = TF's hue-0 branch) -- the
+  oracle's analytic gradient, which tests/test_oracle_filters.py pins to one-sided derivatives of the
+  reference-pinned forward."""
+  px = []
+  for hi, lo in ((0.8, 0.3), (0.4, 0.1), (0.9, 0.6), (0.3, 0.05)):
+    px += [(hi, hi, lo), (hi, lo, hi), (lo, hi, hi), (hi, lo, lo), (lo, hi, lo), (lo, lo, hi), (hi, hi, hi)]
+  x = torch.tensor(px, dtype=torch.float32).reshape(1, 4, 7, 3)
+  lg = torch.tensor([[0.8]])
+  p32 = F.regress(F.SP, lg)
+  g = torch.Generator().manual_seed(3)
+  gy = torch.randn(x.shape, generator=g)
+  gx64, gp64 = F.process_bwd_analytic(F.SP, x.double(), p32.double(), gy.double())
+  params = torch.zeros(1, 24)
+  params[:, :1] = p32
+  gx, gp = ops.filter_bwd(x.cuda(), gy.cuda(), params.cuda(), F.SP)
+  assert ((gx.cpu().double() - gx64).abs() <= 1e-4 * gx64.abs().clamp_min(1e-3 * float(gx64.abs().max()))).all()
+  assert abs(float(gp[0, 0]) - float(gp64[0, 0])) <= 1e-4 * max(abs(float(gp64[0, 0])), 1e-3)

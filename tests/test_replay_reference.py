@@ -16,17 +16,29 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 class Counting:
   """image k is filled with the value k, like the generating script's stand-in provider"""
 
-  def __init__(self, start):
+  def __init__(self, start, device=torch.device("cpu")):
     self.n = start
+    self.device = device
 
   def get_next_batch(self, bs):
     ids = torch.arange(self.n, self.n + bs, dtype=torch.float32)
     self.n += bs
-    return ids[:, None, None, None].expand(bs, 4, 4, 3).contiguous()
+    return ids[:, None, None, None].expand(bs, 4, 4, 3).contiguous().to(self.device)
 
 
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_replay_memory_draws_the_reference_sequence(tag):
+  _run(tag, torch.device("cpu"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_replay_memory_draws_the_reference_sequence_on_the_device(tag):
+  """The same fixture with the pool resident in HBM (the product configuration): gathers / scatters on cuda:0."""
+  _run(tag, torch.device("cuda", 0))
+
+
+def _run(tag, device):
   from exposure_b200.replay import ReplayMemory
   from exposure_b200.trainer import default_cfg
   from exposure_b200.util import STATE_REWARD_DIM, STATE_STEP_DIM, STATE_STOPPED_DIM
@@ -36,7 +48,7 @@ def test_replay_memory_draws_the_reference_sequence(tag):
   cfg.source_img_size = cfg.real_img_size = 4
   cfg.replay_memory_size, cfg.batch_size = int(gold[p + "pool"]), int(gold[p + "batch"])
   cfg.test_steps = int(gold[p + "test_steps"])
-  mem = ReplayMemory(cfg, Counting(0), Counting(200000), torch.device("cpu"), seed=int(gold[p + "seed"]))
+  mem = ReplayMemory(cfg, Counting(0, device), Counting(200000, device), device, seed=int(gold[p + "seed"]))
   B = cfg.batch_size
   kinds, ids, steps = gold[p + "kinds"], gold[p + "ids"], gold[p + "steps"]
   e = 0

@@ -291,3 +291,65 @@ class HostPipelinedChain:
         for k, (h, n) in enumerate(zip(self._scatter_to, self.nk)):
           h.view(self.chunks, cb, n).copy_(self.h_glog[:, self.off[k]:self.off[k + 1]].view(self.chunks, cb, n))
       self._scatter_to = None
+
+
+def shard_plan(global_batch, height, rank, world):
+  """How a global batch of `global_batch` images of `height` rows is split over `world` ranks.
+
+  * global_batch >= world (and divisible): by IMAGE -- rank r owns global_batch / world whole images; filters and
+    per-image parameter gradients need no communication.
+  * global_batch < world (world divisible by it): by ROWS -- world / global_batch ranks share one image, each owns a
+    block of height / (world / global_batch) rows.  Every filter is per pixel, so the only cross-rank term is the
+    per-image parameter gradient: each rank produces the partial sums of its rows and ONE small all-reduce
+    (<= 8 steps x 24 floats per image) adds them.
+  Returns dict(mode, images=[first, count], rows=[first, count], group=ranks sharing my image)."""
+  if global_batch >= world:
+    if global_batch % world:
+      raise ValueError("global batch %d is not a multiple of %d ranks" % (global_batch, world))
+    per = global_batch // world
+    return dict(mode="image", images=(rank * per, per), rows=(0, height), group=[rank])
+  if world % global_batch:
+    raise ValueError("%d ranks cannot share %d images evenly" % (world, global_batch))
+  k = world // global_batch                     # ranks per image
+  if height % k:
+    raise ValueError("image height %d is not a multiple of %d row blocks" % (height, k))
+  img, blk = rank // k, rank % k
+  rows = height // k
+  return dict(mode="rows", images=(img, 1), rows=(blk * rows, rows), group=list(range(img * k, (img + 1) * k)))
+
+
+class ShardedFilterChain:
+  """The whole-chain forward + backward of a GLOBAL batch spread over the ranks of a process group (BASELINE
+  configs[4]: 4K frames, batch 1 -> 32, on 1 / 2 / 4 / 8 GPUs).  Each rank holds only its shard (whole images, or a
+  block of rows of one image when there are fewer images than ranks) and runs FusedFilterChain on it; with row
+  sharding the parameter gradients of an image are partial sums over each rank's rows -- they are linear in the
+  per-pixel terms (finalize + regressor chain rule included), so one all-reduce of the [S, global_batch, 24] gradient
+  tensor completes them (every rank writes only its own image's rows of that tensor)."""
+
+  def __init__(self, ids, global_batch, height, width, device, rank=0, world=1):
+    self.plan = shard_plan(global_batch, height, rank, world)
+    self.global_batch, self.world, self.rank = global_batch, world, rank
+    self.local_batch = self.plan["images"][1]
+    self.local_rows = self.plan["rows"][1]
+    self.width = width
+    self.chain = FusedFilterChain(ids, self.local_batch, device)
+    self.nk = self.chain.nk
+    self._gl_global = torch.zeros(len(ids), global_batch, ops.PSTRIDE, device=device) if self.plan["mode"] == "rows" else None
+
+  def set_logits(self, logits_global):
+    """logits_global[k]: [global_batch, n_k] (replicated on every rank: the parameters are per image, tiny)."""
+    b0, nb = self.plan["images"]
+    self.chain.set_logits([l[b0:b0 + nb] for l in logits_global])
+
+  def forward_backward(self, x_shard, gy_shard, y_out=None, gx_out=None):
+    """x_shard, gy_shard: [local_batch, local_rows, W, 3] -- this rank's part.  Returns (y_shard, gx_shard, glogits):
+    glogits [S, local_batch, 24] for image sharding, [S, global_batch, 24] (complete, identical on the ranks) for
+    row sharding."""
+    import torch.distributed as dist
+    y, gx, gl = self.chain.forward_backward(x_shard, gy_shard, y_out=y_out, gx_out=gx_out)
+    if self.plan["mode"] == "image":
+      return y, gx, gl
+    self._gl_global.zero_()
+    self._gl_global[:, self.plan["images"][0]] = gl[:, 0]
+    dist.all_reduce(self._gl_global)                       # <= 8 x 24 floats per image: the only exchange of the path
+    return y, gx, self._gl_global

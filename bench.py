@@ -59,6 +59,8 @@ def parse_args():
   ap.add_argument("--e2e-chunks", type=int, default=0, help="chain8 e2e leg: sub-batches in flight (0 = 8 if it divides the batch)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-graphs", action="store_true", help="train workload: launch kernels eagerly instead of CUDA graphs")
+  ap.add_argument("--host-replay", action="store_true",
+                  help="train workload: replay selection on host lists (reference-faithful draw sequence) instead of the device")
   ap.add_argument("--roofline-batch", type=int, default=256,
                   help="train workload: batch of the 512x512 filter chain measured for `roofline` (0 = skip)")
   ap.add_argument("--cpu-batch", type=int, default=0, help="images in the CPU arm's step (0 = the full --batch)")
@@ -555,6 +557,7 @@ def train_config(args):
   return {
       "workload": "train: 1 generator+value step + 5 WGAN-GP critic steps per iteration, replay memory on device "
                   "(BASELINE.json configs[3]; net.py:307-370)",
+      "replay": "host lists" if getattr(args, "host_replay", False) else "device (selection kernels, whole iteration one CUDA graph)",
       "batch_per_gpu": args.batch, "height": 64, "width": 64, "channels": 3, "filters": "E,G,W,S+,T,Ct,BW,C",
       "giters": 1, "citers": 5,
       "parallelism": "dp%d (batch sharded by image; one NCCL all-reduce per optimizer step)" % args.gpus,
@@ -568,7 +571,7 @@ def run_train(args):
   import torch
   import torch.distributed as dist
   from exposure_b200 import ops
-  from exposure_b200.replay import ReplayMemory, SyntheticProvider
+  from exposure_b200.replay import DeviceReplayMemory, ReplayMemory, SyntheticProvider
   from exposure_b200.trainer import Trainer, default_cfg
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -585,8 +588,8 @@ def run_train(args):
   cfg.replay_memory_size = 2 * args.batch
   B = args.batch
   t = Trainer(cfg, dev, seed=0)                       # identical initial weights on every rank
-  mem = ReplayMemory(cfg, SyntheticProvider(dev, "raw", 100 + rank), SyntheticProvider(dev, "real", 200 + rank), dev,
-                     seed=rank)
+  Mem = ReplayMemory if args.host_replay else DeviceReplayMemory     # selection logic on the device (product) / host lists (A/B)
+  mem = Mem(cfg, SyntheticProvider(dev, "raw", 100 + rank), SyntheticProvider(dev, "real", 200 + rank), dev, seed=rank)
   t.attach_memory(mem, torch.Generator(device=dev).manual_seed(300 + rank))
 
   def barrier():
@@ -603,10 +606,16 @@ def run_train(args):
   t.train_iteration(0, giters=2 * cfg.test_steps + 2, citers=1)
   torch.cuda.synchronize()
   note("bootstrap done")
+  one_graph = False
   if not args.no_graphs:
     t.enable_graphs(B)                              # each step = one CUDA-graph replay
     torch.cuda.synchronize()
     note("graphs captured (optimizer inside the graph: %s)" % t._graph_apply)
+    if not args.host_replay and t._graph_apply:
+      t.enable_iteration_graph()                    # the WHOLE iteration (replay draws included) = one graph replay
+      torch.cuda.synchronize()
+      one_graph = True
+      note("whole-iteration graph captured (%d kernels)" % t.graph_launches["iteration"])
   sampler = ClockSampler(local)
   if rank == 0:
     sampler.start()
@@ -636,9 +645,10 @@ def run_train(args):
   if graphs:
     # kernels replayed from a CUDA graph are not launched through Python: count them from the
     # capture, and time the kernel families in a short eager (non-graph) pass right after
-    launches = args.steps * (t.graph_launches["generator"] + 5 * t.graph_launches["critic"])
-    saved = (t._ggraph, t._cgraph)
-    t._ggraph = t._cgraph = None
+    launches = args.steps * (t.graph_launches["iteration"] if one_graph else
+                             t.graph_launches["generator"] + 5 * t.graph_launches["critic"])
+    saved = (t._ggraph, t._cgraph, getattr(t, "_itgraph", None))
+    t._ggraph = t._cgraph = t._itgraph = None
     ops.event_log = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -649,7 +659,7 @@ def run_train(args):
     ev1.record()
     torch.cuda.synchronize()
     log, ops.event_log = ops.event_log, None
-    t._ggraph, t._cgraph = saved
+    t._ggraph, t._cgraph, t._itgraph = saved
     probe_ms = ev0.elapsed_time(ev1)
     roof_note = ("timed region replays CUDA graphs; kernel families timed with CUDA events in %d eager iterations "
                  "right after it (%.2f ms/iteration eager)" % (n_probe, probe_ms / n_probe))
@@ -687,7 +697,8 @@ def run_train(args):
 
   # end-to-end leg: fresh RAW and real batches come from pinned host memory every step, the
   # filtered batch and the losses go back to the host (what net.py:330-342 does per sess.run)
-  hraw = torch.empty(B, 64, 64, 3).pin_memory(); hraw.copy_(mem.fake_dataset.get_next_batch(B).cpu())
+  n_raw = max(B, getattr(mem, "F", B))           # the device replay memory stages P + B fresh records per iteration
+  hraw = torch.empty(n_raw, 64, 64, 3).pin_memory(); hraw.copy_(mem.fake_dataset.get_next_batch(n_raw).cpu())
   hreal = torch.empty(B, 64, 64, 3).pin_memory(); hreal.copy_(mem.real_dataset.get_next_batch(B).cpu())
   hout = torch.empty(B, 64, 64, 3).pin_memory()
   hloss = torch.empty(4).pin_memory()

@@ -102,6 +102,13 @@ SIGNATURES = {
     "exp_colsum_multi_workspace_bytes": (_c_size_t, [_c_void_p, _c_void_p, _c_int]),
     "exp_colsum_multi": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_size_t, _c_void_p]),
     "exp_stats_bwd_gin": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p]),
+    "exp_replay_ctl_words": (_c_int, []),
+    "exp_replay_draw_generator": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, ctypes.c_ulonglong, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "exp_replay_replace": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, ctypes.c_ulonglong, _c_void_p, _c_void_p,
+                                    _c_void_p, _c_void_p]),
+    "exp_replay_draw_critic": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, ctypes.c_ulonglong, _c_void_p, _c_void_p, _c_void_p]),
+    "exp_gather_rows": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
+    "exp_train_draws": (_c_int, [ctypes.c_ulonglong, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_size_t, _c_float, _c_void_p]),
     "exp_dp_ipc_handle_bytes": (_c_size_t, []),
     "exp_dp_ipc_export": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
     "exp_dp_ipc_open": (_c_int, [_c_void_p, _c_void_p]),

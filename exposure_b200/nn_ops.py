@@ -633,6 +633,48 @@ def stats_bwd_gin(img, stats, g_in, out=None):
   return g
 
 
+# ---- device-side replay memory + per-step random draws (csrc/replay.cu) -------------------------------------------
+def replay_draw_generator(pool_states, B, seed, ctl, batch_src, rest_src):
+  P, S = pool_states.shape
+  _cabi.check(_cabi.lib().exp_replay_draw_generator(pool_states.data_ptr(), S, P, B, int(seed), ctl.data_ptr(), batch_src.data_ptr(),
+                                                    rest_src.data_ptr(), _stream()), "exp_replay_draw_generator")
+  _n()
+
+
+def replay_replace(new_states, P, max_traj_len, keep_prob, seed, ctl, rest_src, new_pool_src):
+  B, S = new_states.shape
+  _cabi.check(_cabi.lib().exp_replay_replace(new_states.data_ptr(), S, P, B, int(max_traj_len), float(keep_prob), int(seed),
+                                             ctl.data_ptr(), rest_src.data_ptr(), new_pool_src.data_ptr(), _stream()),
+              "exp_replay_replace")
+  _n()
+
+
+def replay_draw_critic(pool_states, B, seed, ctl, batch_src):
+  P, S = pool_states.shape
+  _cabi.check(_cabi.lib().exp_replay_draw_critic(pool_states.data_ptr(), S, P, B, int(seed), ctl.data_ptr(), batch_src.data_ptr(),
+                                                 _stream()), "exp_replay_draw_critic")
+  _n()
+
+
+def gather_rows(src, idx, out):
+  """out[i] = src[idx[i]] over the leading dimension (idx: CUDA int64 [n])."""
+  n = idx.numel()
+  row = src.numel() // src.shape[0]
+  assert src.is_contiguous() and out.is_contiguous() and out.numel() == n * row and idx.dtype == torch.int64
+  _cabi.check(_cabi.lib().exp_gather_rows(src.data_ptr(), idx.data_ptr(), out.data_ptr(), n, row, _stream()), "exp_gather_rows")
+  _n()
+  return out
+
+
+def train_draws(seed, ctl, uniform=None, mask=None, keep=0.5):
+  """uniform[...] ~ U[0,1), mask[...] = floor(keep + U) / keep (tf.nn.dropout multiplier), one launch (+ the counter bump)."""
+  nu = uniform.numel() if uniform is not None else 0
+  nm = mask.numel() if mask is not None else 0
+  _cabi.check(_cabi.lib().exp_train_draws(int(seed), ctl.data_ptr(), _p(uniform), nu, _p(mask), nm, float(keep), _stream()),
+              "exp_train_draws")
+  _n(2)
+
+
 # 0 = TMA-fed tcgen05 engine wherever the shape allows it (the product path); 1 = exact-fp32 CUDA-core engine
 # everywhere (the tests' A/B switch).  BACKEND_TCGEN05_TMA is the old name of 0.
 BACKEND_AUTO, BACKEND_CUDA_CORES = 0, 1

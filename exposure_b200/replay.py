@@ -32,6 +32,103 @@ class SyntheticProvider:
     return torch.exp(0.7 * z - 1.2).clamp_(0, 1)   # retouched targets: brighter, display range
 
 
+class DeviceReplayMemory:
+  """The replay memory with its SELECTION LOGIC on the device too (csrc/replay.cu): every operation
+  of replay_memory.py:187-273 is an index list computed by a one-thread kernel over the pool's 128 state rows plus a
+  gather, so a train iteration needs no host list handling and no index upload and can be captured as ONE CUDA graph
+  (Trainer.enable_iteration_graph).  Random choices come from Philox streams keyed by `seed` and a device-side call
+  counter: reproducible for a seed, but not the reference's Mersenne-Twister sequence -- ReplayMemory below keeps
+  reproducing THAT draw for draw (host mode, tests/test_replay_reference.py); tests/test_replay_logic.py shows both
+  produce the same pool statistics.
+
+  Records live in one buffer: [0, P) pool | [P, P+B) outputs of the last generator step | [P+B, 2P+2B) fresh RAW
+  records of this iteration.  Same method names as the reference class (get_next_fake_batch / replace_memory /
+  replay_fake_batch); the graph path uses stage_fresh / draw_generator / replace / draw_critic directly."""
+
+  def __init__(self, cfg, fake_provider, real_provider, device, seed=0):
+    from . import _cabi
+    self.cfg = cfg
+    self.fake_dataset, self.real_dataset = fake_provider, real_provider
+    self.device = device
+    self.seed = int(seed) * 2654435761 + 12345
+    self.P, self.B, self.S = int(cfg.replay_memory_size), int(cfg.batch_size), int(cfg.num_state_dim)
+    self.target_pool_size = self.P
+    P, B = self.P, self.B
+    self.F = P + B
+    s = cfg.source_img_size
+    total = P + B + self.F
+    self.images = torch.zeros(total, s, s, 3, device=device)
+    self.states = torch.zeros(total, self.S, device=device)       # the fresh region's states stay zero (get_initial_states)
+    self.ctl = torch.zeros(_cabi.lib().exp_replay_ctl_words(), dtype=torch.int32, device=device)
+    self.rest_src = torch.zeros(P, dtype=torch.int32, device=device)
+    self.batch_src = torch.zeros(B, dtype=torch.int64, device=device)
+    self.crit_src = torch.zeros(B, dtype=torch.int64, device=device)
+    self.pool_src = torch.zeros(P, dtype=torch.int64, device=device)
+    self._tmp_images = torch.empty(P, s, s, 3, device=device)
+    self._tmp_states = torch.empty(P, self.S, device=device)
+    self._gen_images = torch.empty(B, s, s, 3, device=device)
+    self._gen_states = torch.empty(B, self.S, device=device)
+    self._crit_images = torch.empty(B, s, s, 3, device=device)
+    self.stage_fresh()                                            # initial fill_pool (replay_memory.py:42-43)
+    self.images[:P].copy_(self.images[P + B:P + B + P])
+    self.states[:P].zero_()
+
+  # ---- device operations (no host synchronisation; all capturable) ------------------------------------------
+  def stage_fresh(self):
+    """Fresh RAW records of this iteration from the data provider (the only host-facing step; NOT inside a graph)."""
+    self.images[self.P + self.B:].copy_(self.fake_dataset.get_next_batch(self.F))
+
+  def draw_generator(self):
+    from . import nn_ops as K
+    K.replay_draw_generator(self.states[:self.P], self.B, self.seed, self.ctl, self.batch_src, self.rest_src)
+    K.gather_rows(self.images, self.batch_src, self._gen_images)
+    K.gather_rows(self.states, self.batch_src, self._gen_states)
+    return self._gen_images, self._gen_states
+
+  def replace(self, new_images, new_states):
+    from . import nn_ops as K
+    P, B = self.P, self.B
+    self.images[P:P + B].copy_(new_images)
+    self.states[P:P + B].copy_(new_states)
+    K.replay_replace(self.states[P:P + B], P, self.cfg.maximum_trajectory_length, self.cfg.over_length_keep_prob, self.seed,
+                     self.ctl, self.rest_src, self.pool_src)
+    K.gather_rows(self.images, self.pool_src, self._tmp_images)
+    K.gather_rows(self.states, self.pool_src, self._tmp_states)
+    self.images[:P].copy_(self._tmp_images)
+    self.states[:P].copy_(self._tmp_states)
+
+  def draw_critic(self):
+    from . import nn_ops as K
+    K.replay_draw_critic(self.states[:self.P], self.B, self.seed, self.ctl, self.crit_src)
+    return K.gather_rows(self.images, self.crit_src, self._crit_images)
+
+  def check(self):
+    """Host synchronisation: raises like the reference's assertion if a critic batch found no terminated record."""
+    if int(self.ctl[4]) != 0:
+      raise AssertionError("No terminated states discovered")          # replay_memory.py:258-259
+
+  # ---- the reference's method names (eager use: GAN.train, Trainer.train_iteration) ------------------------------
+  def get_next_fake_batch(self, batch_size):
+    assert batch_size == self.B
+    self.stage_fresh()
+    img, st = self.draw_generator()
+    return img, st, None
+
+  def replace_memory(self, new_images, new_states, old_slots=None):
+    self.replace(new_images, new_states)
+
+  def replay_fake_batch(self, batch_size):
+    assert batch_size == self.B
+    return self.draw_critic(), None
+
+  def fill_pool(self):
+    pass                                   # the pool is always full: replace() tops it up (replay_memory.py:196)
+
+  def debug(self):
+    st = self.states[:self.P]
+    return self.P, float(st[:, STATE_STEP_DIM].mean())
+
+
 class ReplayMemory:
 
   def __init__(self, cfg, fake_provider, real_provider, device, seed=0):

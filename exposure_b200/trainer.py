@@ -138,20 +138,23 @@ class Trainer:
 
   def _apply(self, which):
     """The optimizer step of one sess.run: which == "gv" (opt_g and opt_v, net.py:330-331) or "c" (opt_c, net.py:362).
-    world > 1: ONE gradient exchange over the flat buffer, the mean (1/world) folded into Adam."""
+    world > 1: ONE gradient exchange over the flat buffer, the mean (1/world) folded into Adam.
+    The lr_t scalars are read from self._hyper (device memory); the whole-iteration graph points the critic's entry at
+    a different scalar for each of its critic steps (self._hyper_override)."""
     b1, b2 = self.cfg.adam_beta1, self.cfg.adam_beta2
+    hyper = dict(self._hyper, **getattr(self, "_hyper_override", {}))
     if which == "gv":
       buf, parts = self.gv, ((self.gen, "g"), (self.val, "v"))
     else:
       buf, parts = self.cri, ((self.cri, "c"),)
     if self._peer is not None:
-      second = self._hyper[parts[1][1]] if len(parts) > 1 else None
-      self._peer[which].allreduce_adam(buf.flat, buf.m, buf.v, self._hyper[parts[0][1]], parts[0][0].flat.numel(), second, b1, b2)
+      second = hyper[parts[1][1]] if len(parts) > 1 else None
+      self._peer[which].allreduce_adam(buf.flat, buf.m, buf.v, hyper[parts[0][1]], parts[0][0].flat.numel(), second, b1, b2)
       return
     if self.world > 1:
       dist.all_reduce(buf.grad)                                  # ONE all-reduce per optimizer step
     for store, key in parts:
-      K.adam(store.flat, store.grad, store.m, store.v, self._hyper[key], b1, b2, 1e-8, 1.0 / self.world)
+      K.adam(store.flat, store.grad, store.m, store.v, hyper[key], b1, b2, 1e-8, 1.0 / self.world)
 
   # ---- CUDA graphs: each step is a fixed launch sequence, captured once and replayed ---------
   def enable_graphs(self, B=None):
@@ -201,6 +204,91 @@ class Trainer:
         t.copy_(next(it))
     self.ema_state.copy_(ema_snap)
     self._graph_B = B
+
+  # ---- the WHOLE iteration as one CUDA graph (device replay memory) -----------------------------------------
+  def enable_iteration_graph(self, citers=None):
+    """Capture one iteration of net.py:307-370 -- draw the generator batch from the device replay memory, random
+    draws, generator+value step, re-insert the outputs, then `citers` x (draw a critic batch, critic step) -- into ONE
+    CUDA graph.  Needs an attached DeviceReplayMemory and a capturable optimizer step (single GPU, or the peer-memory
+    transport).  Per replay the host only stages the provider's fresh RAW / real batches and three lr scalars."""
+    from .replay import DeviceReplayMemory
+    mem = self.memory
+    if not isinstance(mem, DeviceReplayMemory):
+      raise TypeError("the whole-iteration graph needs a DeviceReplayMemory (selection logic on the device)")
+    if not (self.world == 1 or self._peer is not None):
+      raise RuntimeError("the dist.all_reduce transport is not capturable: use the per-step graphs (enable_graphs)")
+    cfg, dev = self.cfg, self.device
+    B = cfg.batch_size
+    n_c = int(citers or cfg.citers)
+    s = cfg.source_img_size
+    self._it = dict(
+        real=torch.zeros(n_c, B, s, s, 3, device=dev), progress=torch.zeros(1, device=dev),
+        hyper=torch.zeros(2 + n_c, device=dev), uni=torch.zeros(B * (1 + n_c), device=dev),
+        masks=torch.zeros(2, B, 4, 4, 256, device=dev), citers=n_c)
+    I = self._it
+    seed = mem.seed ^ 0x5DEECE66D
+
+    def body():
+      img, states = mem.draw_generator()
+      K.train_draws(seed, mem.ctl, uniform=I["uni"], mask=I["masks"], keep=float(cfg.dropout_keep_prob))
+      self._hyper_override = {"g": I["hyper"][0:1], "v": I["hyper"][1:2]}
+      out = self._generator_impl(img, states, I["uni"][:B], I["masks"][0], I["masks"][1], I["progress"], 1, True)
+      mem.replace(out["fake_output"], out["new_states"])
+      cout = None
+      for k in range(n_c):
+        fake = mem.draw_critic()
+        self._hyper_override = {"c": I["hyper"][2 + k:3 + k]}
+        cout = self._critic_impl(I["real"][k], fake, I["uni"][B * (1 + k):B * (2 + k)], True)
+      self._hyper_override = {}
+      return dict(g_loss=out["g_loss"], v_loss=out["v_loss"], emd=cout["emd"], critic_gradient_norm=cout["critic_gradient_norm"],
+                  fake_output=out["fake_output"], new_states=out["new_states"])
+
+    snap = [t.clone() for st in (self.gv, self.cri) for t in (st.flat, st.m, st.v)]
+    msnap = [t.clone() for t in (mem.images, mem.states, mem.ctl, self.ema_state)]
+    I["hyper"].zero_()
+    mem.stage_fresh()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for _ in range(2):
+        body()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    from . import ops as _ops
+    l0 = _ops.launch_count
+    self._itgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self._itgraph):
+      self._itout = body()
+    self.graph_launches = dict(getattr(self, "graph_launches", {}), iteration=_ops.launch_count - l0)
+    if self.world > 1:
+      dist.barrier()
+    it = iter(snap)
+    for st in (self.gv, self.cri):
+      for t in (st.flat, st.m, st.v):
+        t.copy_(next(it))
+    for t, sv in zip((mem.images, mem.states, mem.ctl, self.ema_state), msnap):
+      t.copy_(sv)
+
+  def _iteration_replay(self, it):
+    cfg, I, mem = self.cfg, self._it, self.memory
+    B = cfg.batch_size
+    b1, b2 = cfg.adam_beta1, cfg.adam_beta2
+    lr_g, lr_c = cfg.lr_g(it), cfg.lr_c(it)
+    vals = []
+    self.counter_g += 1
+    self.counter_v += 1
+    vals.append(lr_g * math.sqrt(1.0 - b2 ** self.counter_g) / (1.0 - b1 ** self.counter_g))
+    vals.append(cfg.value_lr_mul * lr_g * math.sqrt(1.0 - b2 ** self.counter_v) / (1.0 - b1 ** self.counter_v))
+    for _ in range(I["citers"]):
+      self.counter_c += 1
+      vals.append(lr_c * math.sqrt(1.0 - b2 ** self.counter_c) / (1.0 - b1 ** self.counter_c))
+    I["hyper"].copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=True)
+    I["progress"].fill_(float(it) / cfg.max_iter_step)
+    mem.stage_fresh()
+    for k in range(I["citers"]):
+      I["real"][k].copy_(mem.real_dataset.get_next_batch(B))
+    self._itgraph.replay()
+    return self._itout
 
   # ---- generator + value step (net.py:56-163, 222-239, 330) ---------------------------------
   def generator_forward(self, fake_input, states, noise, drop_f, drop_s, progress, is_train=1):
@@ -332,6 +420,8 @@ class Trainer:
       citers = 100 if (it < cfg.critic_initialization or it % 500 == 0) else cfg.citers     # net.py:312-316
     if giters is None:
       giters = 100 if it == 0 else cfg.giters                                               # net.py:318-322
+    if (getattr(self, "_itgraph", None) is not None and lr_g is None and it > 0 and giters == 1 and citers == self._it["citers"]):
+      return self._iteration_replay(it)                                                      # the whole iteration: ONE graph
     lr_g = (0.0 if it == 0 else cfg.lr_g(it)) if lr_g is None else lr_g                      # net.py:327-328
     out = None
     for _ in range(giters):

@@ -411,6 +411,35 @@ int exp_colsum_multi(const float* const* src_host, float* const* dst_host, const
 int exp_stats_bwd_gin(const float* img, const float* stats, const float* g_in, int cin, float* g_out, int B, int H,
                       int W, void* stream);
 
+/* ---- device-side replay memory (csrc/replay.cu, csrc/replay_logic.cuh) -----------------------------------------
+ * Replaces the host list handling of replay_memory.py:187-273 (random.shuffle, list slicing, np.stack and a feed of
+ * every image per sess.run) by index lists computed on the device.  Records live in ONE buffer of three regions
+ * addressed by a flat index: [0, P) the pool (P = cfg.replay_memory_size), [P, P+B) the outputs of the last
+ * generator step (B = cfg.batch_size), [P+B, 2P+2B) the fresh RAW records of this iteration (states == 0).
+ *   exp_replay_draw_generator  get_next_fake_batch (230-246): batch_src int64 [B] = the first B non-terminated records
+ *       of a random pool order (terminated ones met on the way are dropped; a pool that runs dry is rebuilt from fresh
+ *       records, 64-75, 237-238); rest_src int32 [P] + ctl = the records that stay.
+ *   exp_replay_replace         replace_memory (187-196) + fill_pool: new_pool_src int64 [P] = the remaining records, the
+ *       generator outputs with step < max_traj_len (others with probability keep_prob), fresh records up to P.
+ *   exp_replay_draw_critic     replay_fake_batch (249-273): batch_src int64 [B] = terminated records in random order,
+ *       cycling when fewer than B exist; none at all sets ctl[4] (the reference asserts).
+ * pool_states / new_states: float [P or B][n_states] (STOPPED = column 1, STEP = column 2, util.py:13-16).
+ * ctl: int32 [exp_replay_ctl_words()], zero-filled once: 64-bit call counter of the Philox streams (a replayed CUDA
+ * graph draws new numbers each time), hand-over between draw_generator and replace, error flag.  `seed` keys the
+ * streams.  exp_gather_rows moves the records: dst[i, :] = src[idx[i], :] for rows of `row` floats.
+ * exp_train_draws: the per-step random inputs of the train step in one launch -- uniform[n_uniform] ~ U[0,1) (z[:,0],
+ * alpha) and mask[n_mask] = floor(keep + U) / keep (tf.nn.dropout, agent.py:36) -- from the same counter. */
+int exp_replay_ctl_words(void);
+int exp_replay_draw_generator(const float* pool_states, int n_states, int pool, int batch, unsigned long long seed,
+                              int* ctl, long long* batch_src, int* rest_src, void* stream);
+int exp_replay_replace(const float* new_states, int n_states, int pool, int batch, int max_traj_len, float keep_prob,
+                       unsigned long long seed, int* ctl, const int* rest_src, long long* new_pool_src, void* stream);
+int exp_replay_draw_critic(const float* pool_states, int n_states, int pool, int batch, unsigned long long seed,
+                           int* ctl, long long* batch_src, void* stream);
+int exp_gather_rows(const float* src, const long long* idx, float* dst, int n, int row, void* stream);
+int exp_train_draws(unsigned long long seed, int* ctl, float* uniform, int n_uniform, float* mask, size_t n_mask,
+                    float keep, void* stream);
+
 /* ---- data-parallel optimizer step over NVLink peer memory (one process per GPU) -------------------------
  * The reference is single-GPU; this is the collective of SURVEY 8e / C1: ONE exchange per
  * optimizer step on the flat gradient buffer -- theta_g and theta_v together, both optimizers run in the same

@@ -629,7 +629,9 @@ int exp_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act,
   FcDgrad p{};
   p.dy = dy; p.W = W; p.mul_act = mul_act; p.mul_plain = mul_plain; p.dx = dx; p.M = M; p.K = K; p.N = N;
   p.ldy = ldy; p.lddx = lddx; p.ldmul = ldmul; p.accumulate = accumulate;
-  launch_gemm<FcDgrad, 64, false, true>(p, M, K, 1, (cudaStream_t)stream);
+  // the 4096 x 128 heads at batch 64: 64-wide tiles give 64 CTAs on 148 SMs -> halve the tile until the grid fills them
+  if (((M + kBM - 1) / kBM) * ((K + 63) / 64) < 148) launch_gemm<FcDgrad, 32, false, true>(p, M, K, 1, (cudaStream_t)stream);
+  else launch_gemm<FcDgrad, 64, false, true>(p, M, K, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_dgrad");
   return EXP_OK;
 }

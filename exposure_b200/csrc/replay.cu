@@ -26,15 +26,28 @@ __device__ __forceinline__ uint64_t rl_next_call(int* ctl) {
   return c;
 }
 
+// random order of the pool: one thread per record (keys, then ranks); returns this launch's call number
+__device__ __forceinline__ uint64_t block_shuffle(int* perm, uint32_t* keys, int P, uint64_t seed, int* ctl, uint32_t stream) {
+  __shared__ uint64_t call_s;
+  if (threadIdx.x == 0) call_s = rl_next_call(ctl);
+  __syncthreads();
+  const uint64_t call = call_s;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = rl::shuffle_key(seed, call, stream, i);
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) perm[rl::shuffle_rank(keys, P, i)] = i;
+  __syncthreads();
+  return call;
+}
+
 __global__ void replay_draw_generator_kernel(const float* __restrict__ pool_states, int S, int P, int B, uint64_t seed,
                                              int* __restrict__ ctl, long long* __restrict__ batch_src, int* __restrict__ rest_src) {
   EXP_PDL_ENTRY();
   __shared__ int perm[kRlMaxPool];
+  __shared__ uint32_t keys[kRlMaxPool];
+  block_shuffle(perm, keys, P, seed, ctl, 1u);
   if (threadIdx.x != 0) return;
-  rl::Philox g;
-  rl::philox_init(g, seed, rl_next_call(ctl), 1u);
   int n_rest, fresh_used;
-  rl::draw_generator(pool_states, S, P, B, g, perm, batch_src, rest_src, &n_rest, &fresh_used);
+  rl::draw_generator(pool_states, S, P, B, perm, batch_src, rest_src, &n_rest, &fresh_used);
   ctl[kRlNRest] = n_rest;
   ctl[kRlFreshUsed] = fresh_used;
 }
@@ -54,10 +67,10 @@ __global__ void replay_draw_critic_kernel(const float* __restrict__ pool_states,
   EXP_PDL_ENTRY();
   __shared__ int perm[kRlMaxPool];
   __shared__ int term[kRlMaxPool];
+  __shared__ uint32_t keys[kRlMaxPool];
+  block_shuffle(perm, keys, P, seed, ctl, 3u);
   if (threadIdx.x != 0) return;
-  rl::Philox g;
-  rl::philox_init(g, seed, rl_next_call(ctl), 3u);
-  const int nt = rl::draw_critic(pool_states, S, P, B, g, perm, term, batch_src);
+  const int nt = rl::draw_critic(pool_states, S, P, B, perm, term, batch_src);
   ctl[kRlLastTerm] = nt;
   if (nt == 0) ctl[kRlError] = 1;
 }
@@ -122,7 +135,7 @@ int exp_replay_draw_generator(const float* pool_states, int n_states, int pool, 
                               long long* batch_src, int* rest_src, void* stream) {
   EXP_CHECK_ARG(pool_states && ctl && batch_src && rest_src, "null pointer");
   EXP_CHECK_ARG(pool > 0 && pool <= kRlMaxPool && batch > 0 && batch <= pool && n_states > rl::kStateStep, "bad sizes (pool <= %d, batch <= pool)", kRlMaxPool);
-  launch_pdl(replay_draw_generator_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, pool_states, n_states, pool, batch,
+  launch_pdl(replay_draw_generator_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, pool_states, n_states, pool, batch,
              (uint64_t)seed, ctl, batch_src, rest_src);
   EXP_CHECK_LAUNCH("exp_replay_draw_generator");
   return EXP_OK;
@@ -142,7 +155,7 @@ int exp_replay_draw_critic(const float* pool_states, int n_states, int pool, int
                            long long* batch_src, void* stream) {
   EXP_CHECK_ARG(pool_states && ctl && batch_src, "null pointer");
   EXP_CHECK_ARG(pool > 0 && pool <= kRlMaxPool && batch > 0 && n_states > rl::kStateStep, "bad sizes");
-  launch_pdl(replay_draw_critic_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, pool_states, n_states, pool, batch,
+  launch_pdl(replay_draw_critic_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, pool_states, n_states, pool, batch,
              (uint64_t)seed, ctl, batch_src);
   EXP_CHECK_LAUNCH("exp_replay_draw_critic");
   return EXP_OK;

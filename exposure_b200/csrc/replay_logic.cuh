@@ -73,21 +73,34 @@ EXPO_RL_HD uint32_t philox_next(Philox& g) {
 EXPO_RL_HD uint32_t philox_below(Philox& g, uint32_t n) { return (uint32_t)(((uint64_t)philox_next(g) * n) >> 32); }
 EXPO_RL_HD float philox_uniform(Philox& g) { return (float)(philox_next(g) >> 8) * (1.0f / 16777216.0f); }   // [0, 1)
 
-// Fisher-Yates on perm[0..n) = 0..n-1
-EXPO_RL_HD void shuffle(int* perm, int n, Philox& g) {
-  for (int i = 0; i < n; ++i) perm[i] = i;
-  for (int i = n - 1; i > 0; --i) {
-    const int j = (int)philox_below(g, (uint32_t)(i + 1));
-    const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
-  }
+// Random permutation by sorting random keys: record i draws key_i = Philox(seed, call, stream; counter i) and lands
+// at position rank(i) = #{j : key_j < key_i, ties by index}.  Every key and every rank is independent of the others,
+// so the device computes them with one thread per record (shuffle_key / shuffle_rank below, ~1 us for 128 records
+// instead of ~20 us for a serial Fisher-Yates on one thread); the host build loops over i.  Same permutation either way.
+EXPO_RL_HD uint32_t shuffle_key(uint64_t seed, uint64_t call, uint32_t stream, int i) {
+  Philox g;
+  philox_init(g, seed, call, stream);
+  g.ctr[0] = (uint32_t)i;
+  g.ctr[1] ^= 0x80000000u;                    // a counter space of its own, away from the sequential draws of the call
+  return philox_next(g);
+}
+EXPO_RL_HD int shuffle_rank(const uint32_t* keys, int n, int i) {
+  const uint32_t k = keys[i];
+  int r = 0;
+  for (int j = 0; j < n; ++j) r += (keys[j] < k || (keys[j] == k && j < i)) ? 1 : 0;
+  return r;
+}
+// serial form (host build, and any caller without a thread per record)
+EXPO_RL_HD void shuffle(int* perm, uint32_t* keys, int n, uint64_t seed, uint64_t call, uint32_t stream) {
+  for (int i = 0; i < n; ++i) keys[i] = shuffle_key(seed, call, stream, i);
+  for (int i = 0; i < n; ++i) perm[shuffle_rank(keys, n, i)] = i;
 }
 
-// get_next_fake_batch.  pool_states: [P][S] floats.  Outputs: batch_src[B] (flat indices), rest_src[<= P] and *n_rest
-// (the records that stay in the pool, flat indices), *fresh_used (fresh records consumed so far this iteration).
-// `perm` is scratch of P ints.
-EXPO_RL_HD void draw_generator(const float* pool_states, int S, int P, int B, Philox& g, int* perm, long long* batch_src,
+// get_next_fake_batch.  pool_states: [P][S] floats; perm: a random order of the pool (shuffle).  Outputs: batch_src[B]
+// (flat indices), rest_src[<= P] and *n_rest (the records that stay in the pool, flat indices), *fresh_used (fresh
+// records consumed so far this iteration).
+EXPO_RL_HD void draw_generator(const float* pool_states, int S, int P, int B, const int* perm, long long* batch_src,
                                int* rest_src, int* n_rest, int* fresh_used) {
-  shuffle(perm, P, g);
   int taken = 0, nr = 0;
   for (int i = 0; i < P; ++i) {
     const int r = perm[i];
@@ -127,9 +140,9 @@ EXPO_RL_HD void replace(const float* new_states, int S, int P, int B, int max_tr
   while (n < P) new_pool_src[n++] = fresh0 + fresh_used++;  // fill_pool: top up with fresh RAW records
 }
 
-// replay_fake_batch.  Returns the number of terminated records (0 = the reference's assertion would fire).
-EXPO_RL_HD int draw_critic(const float* pool_states, int S, int P, int B, Philox& g, int* perm, int* term, long long* batch_src) {
-  shuffle(perm, P, g);
+// replay_fake_batch.  perm: a random order of the pool.  Returns the number of terminated records (0 = the reference's
+// assertion would fire).
+EXPO_RL_HD int draw_critic(const float* pool_states, int S, int P, int B, const int* perm, int* term, long long* batch_src) {
   int nt = 0;
   for (int i = 0; i < P; ++i)
     if (pool_states[(long long)perm[i] * S + kStateStopped] > 0.f) term[nt++] = perm[i];

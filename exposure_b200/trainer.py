@@ -282,7 +282,8 @@ class Trainer:
     for _ in range(I["citers"]):
       self.counter_c += 1
       vals.append(lr_c * math.sqrt(1.0 - b2 ** self.counter_c) / (1.0 - b1 ** self.counter_c))
-    I["hyper"].copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=True)
+    for k, v in enumerate(vals):                       # scalar fills: no host buffer to keep alive, nothing to wait for
+      I["hyper"][k:k + 1].fill_(v)
     I["progress"].fill_(float(it) / cfg.max_iter_step)
     mem.stage_fresh()
     for k in range(I["citers"]):

@@ -13,10 +13,10 @@ extern "C" {
 int rl_draw_generator(const float* pool_states, int S, int P, int B, unsigned long long seed, unsigned long long call,
                       long long* batch_src, int* rest_src, int* fresh_used) {
   static int perm[1024];
-  Philox g;
-  philox_init(g, seed, call, 1u);
+  static uint32_t keys[1024];
+  shuffle(perm, keys, P, seed, call, 1u);
   int n_rest = 0;
-  draw_generator(pool_states, S, P, B, g, perm, batch_src, rest_src, &n_rest, fresh_used);
+  draw_generator(pool_states, S, P, B, perm, batch_src, rest_src, &n_rest, fresh_used);
   return n_rest;
 }
 void rl_replace(const float* new_states, int S, int P, int B, int max_len, float keep, unsigned long long seed,
@@ -28,9 +28,9 @@ void rl_replace(const float* new_states, int S, int P, int B, int max_len, float
 int rl_draw_critic(const float* pool_states, int S, int P, int B, unsigned long long seed, unsigned long long call,
                    long long* batch_src) {
   static int perm[1024], term[1024];
-  Philox g;
-  philox_init(g, seed, call, 3u);
-  return draw_critic(pool_states, S, P, B, g, perm, term, batch_src);
+  static uint32_t keys[1024];
+  shuffle(perm, keys, P, seed, call, 3u);
+  return draw_critic(pool_states, S, P, B, perm, term, batch_src);
 }
 void rl_uniforms(unsigned long long seed, unsigned long long call, float* out, int n) {
   Philox g;

@@ -124,7 +124,7 @@ def test_whole_iteration_as_one_graph(built_lib):
     t.enable_iteration_graph()
     p0 = t.gv.flat.clone()
     calls0 = int(mem.ctl[0])
-    outs = [t.train_iteration(it) for it in range(1, 5)]
+    outs = [t.train_iteration(it, giters=1, citers=5) for it in range(1, 5)]       # the default schedule runs 100 critic steps while it < 10
     torch.cuda.synchronize()
     mem.check()
     assert int(mem.ctl[0]) == calls0 + 4 * (2 + 1 + t._it["citers"])      # draw + replace + draws + 5 critic draws per iteration

@@ -44,22 +44,42 @@ __global__ void replay_draw_generator_kernel(const float* __restrict__ pool_stat
   EXP_PDL_ENTRY();
   __shared__ int perm[kRlMaxPool];
   __shared__ uint32_t keys[kRlMaxPool];
+  __shared__ float stopped[kRlMaxPool];
+  __shared__ int rest_s[kRlMaxPool];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) stopped[i] = pool_states[(size_t)i * S + rl::kStateStopped];
   block_shuffle(perm, keys, P, seed, ctl, 1u);
-  if (threadIdx.x != 0) return;
-  int n_rest, fresh_used;
-  rl::draw_generator(pool_states, S, P, B, perm, batch_src, rest_src, &n_rest, &fresh_used);
-  ctl[kRlNRest] = n_rest;
-  ctl[kRlFreshUsed] = fresh_used;
+  __shared__ int n_rest_s;
+  __shared__ long long batch_s[kRlMaxPool];
+  if (threadIdx.x == 0) {
+    int n_rest, fresh_used;
+    rl::draw_generator(stopped, P, B, perm, batch_s, rest_s, &n_rest, &fresh_used);
+    ctl[kRlNRest] = n_rest;
+    ctl[kRlFreshUsed] = fresh_used;
+    n_rest_s = n_rest;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) batch_src[i] = batch_s[i];
+  for (int i = threadIdx.x; i < n_rest_s; i += blockDim.x) rest_src[i] = rest_s[i];
 }
 
 __global__ void replay_replace_kernel(const float* __restrict__ new_states, int S, int P, int B, int max_traj_len, float keep_prob,
                                       uint64_t seed, int* __restrict__ ctl, const int* __restrict__ rest_src,
                                       long long* __restrict__ new_pool_src) {
   EXP_PDL_ENTRY();
-  if (threadIdx.x != 0) return;
-  rl::Philox g;
-  rl::philox_init(g, seed, rl_next_call(ctl), 2u);
-  rl::replace(new_states, S, P, B, max_traj_len, keep_prob, g, rest_src, ctl[kRlNRest], ctl[kRlFreshUsed], new_pool_src);
+  __shared__ float step[kRlMaxPool];
+  __shared__ int rest_s[kRlMaxPool];
+  __shared__ long long pool_s[kRlMaxPool];
+  const int n_rest = ctl[kRlNRest];
+  for (int i = threadIdx.x; i < B; i += blockDim.x) step[i] = new_states[(size_t)i * S + rl::kStateStep];
+  for (int i = threadIdx.x; i < n_rest; i += blockDim.x) rest_s[i] = rest_src[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    rl::Philox g;
+    rl::philox_init(g, seed, rl_next_call(ctl), 2u);
+    rl::replace(step, P, B, max_traj_len, keep_prob, g, rest_s, n_rest, ctl[kRlFreshUsed], pool_s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P; i += blockDim.x) new_pool_src[i] = pool_s[i];
 }
 
 __global__ void replay_draw_critic_kernel(const float* __restrict__ pool_states, int S, int P, int B, uint64_t seed,
@@ -68,11 +88,17 @@ __global__ void replay_draw_critic_kernel(const float* __restrict__ pool_states,
   __shared__ int perm[kRlMaxPool];
   __shared__ int term[kRlMaxPool];
   __shared__ uint32_t keys[kRlMaxPool];
+  __shared__ float stopped[kRlMaxPool];
+  __shared__ long long batch_s[kRlMaxPool];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) stopped[i] = pool_states[(size_t)i * S + rl::kStateStopped];
   block_shuffle(perm, keys, P, seed, ctl, 3u);
-  if (threadIdx.x != 0) return;
-  const int nt = rl::draw_critic(pool_states, S, P, B, perm, term, batch_src);
-  ctl[kRlLastTerm] = nt;
-  if (nt == 0) ctl[kRlError] = 1;
+  if (threadIdx.x == 0) {
+    const int nt = rl::draw_critic(stopped, P, B, perm, term, batch_s);
+    ctl[kRlLastTerm] = nt;
+    if (nt == 0) ctl[kRlError] = 1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) batch_src[i] = batch_s[i];
 }
 
 // out[i] for i < n_uniform: U[0,1);  then n_mask dropout multipliers floor(keep + U) / keep (tf.nn.dropout, agent.py:36)
@@ -145,7 +171,7 @@ int exp_replay_replace(const float* new_states, int n_states, int pool, int batc
                        unsigned long long seed, int* ctl, const int* rest_src, long long* new_pool_src, void* stream) {
   EXP_CHECK_ARG(new_states && ctl && rest_src && new_pool_src, "null pointer");
   EXP_CHECK_ARG(pool > 0 && pool <= kRlMaxPool && batch > 0 && batch <= pool && n_states > rl::kStateStep, "bad sizes");
-  launch_pdl(replay_replace_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, new_states, n_states, pool, batch, max_traj_len,
+  launch_pdl(replay_replace_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, new_states, n_states, pool, batch, max_traj_len,
              keep_prob, (uint64_t)seed, ctl, rest_src, new_pool_src);
   EXP_CHECK_LAUNCH("exp_replay_replace");
   return EXP_OK;
@@ -154,7 +180,7 @@ int exp_replay_replace(const float* new_states, int n_states, int pool, int batc
 int exp_replay_draw_critic(const float* pool_states, int n_states, int pool, int batch, unsigned long long seed, int* ctl,
                            long long* batch_src, void* stream) {
   EXP_CHECK_ARG(pool_states && ctl && batch_src, "null pointer");
-  EXP_CHECK_ARG(pool > 0 && pool <= kRlMaxPool && batch > 0 && n_states > rl::kStateStep, "bad sizes");
+  EXP_CHECK_ARG(pool > 0 && pool <= kRlMaxPool && batch > 0 && batch <= kRlMaxPool && n_states > rl::kStateStep, "bad sizes");
   launch_pdl(replay_draw_critic_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, pool_states, n_states, pool, batch,
              (uint64_t)seed, ctl, batch_src);
   EXP_CHECK_LAUNCH("exp_replay_draw_critic");

@@ -96,16 +96,17 @@ EXPO_RL_HD void shuffle(int* perm, uint32_t* keys, int n, uint64_t seed, uint64_
   for (int i = 0; i < n; ++i) perm[shuffle_rank(keys, n, i)] = i;
 }
 
-// get_next_fake_batch.  pool_states: [P][S] floats; perm: a random order of the pool (shuffle).  Outputs: batch_src[B]
-// (flat indices), rest_src[<= P] and *n_rest (the records that stay in the pool, flat indices), *fresh_used (fresh
-// records consumed so far this iteration).
-EXPO_RL_HD void draw_generator(const float* pool_states, int S, int P, int B, const int* perm, long long* batch_src,
+// get_next_fake_batch.  stopped[P]: the STOPPED column of the pool's states (the kernels stage it in shared memory --
+// the walk below is serial, and a dependent global load per record would cost more than everything else); perm: a
+// random order of the pool (shuffle).  Outputs: batch_src[B] (flat indices), rest_src[<= P] and *n_rest (the records
+// that stay in the pool, flat indices), *fresh_used (fresh records consumed so far this iteration).
+EXPO_RL_HD void draw_generator(const float* stopped, int P, int B, const int* perm, long long* batch_src,
                                int* rest_src, int* n_rest, int* fresh_used) {
   int taken = 0, nr = 0;
   for (int i = 0; i < P; ++i) {
     const int r = perm[i];
     if (taken < B) {
-      if (pool_states[(long long)r * S + kStateStopped] > 0.f) continue;      // finished records are dropped here
+      if (stopped[r] > 0.f) continue;                                         // finished records are dropped here
       batch_src[taken++] = r;
     } else {
       rest_src[nr++] = r;
@@ -124,14 +125,14 @@ EXPO_RL_HD void draw_generator(const float* pool_states, int S, int P, int B, co
   *fresh_used = used;
 }
 
-// replace_memory + fill_pool.  new_states: the generator's output states [B][S].  new_pool_src[P] = flat indices of
-// the records that form the pool from now on.
-EXPO_RL_HD void replace(const float* new_states, int S, int P, int B, int max_traj_len, float keep_prob, Philox& g,
+// replace_memory + fill_pool.  new_step[B]: the STEP column of the generator's output states.  new_pool_src[P] = flat
+// indices of the records that form the pool from now on.
+EXPO_RL_HD void replace(const float* new_step, int P, int B, int max_traj_len, float keep_prob, Philox& g,
                         const int* rest_src, int n_rest, int fresh_used, long long* new_pool_src) {
   int n = 0;
   for (int i = 0; i < n_rest && n < P; ++i) new_pool_src[n++] = rest_src[i];
   for (int j = 0; j < B; ++j) {
-    const float step = new_states[(long long)j * S + kStateStep];
+    const float step = new_step[j];
     // replay_memory.py:190-192: always draws the random number only when the step test fails (short-circuit `or`)
     const bool keep = step < (float)max_traj_len || philox_uniform(g) < keep_prob;
     if (keep && n < P) new_pool_src[n++] = P + j;           // beyond P the reference truncates (image_pool[:target])
@@ -142,10 +143,10 @@ EXPO_RL_HD void replace(const float* new_states, int S, int P, int B, int max_tr
 
 // replay_fake_batch.  perm: a random order of the pool.  Returns the number of terminated records (0 = the reference's
 // assertion would fire).
-EXPO_RL_HD int draw_critic(const float* pool_states, int S, int P, int B, const int* perm, int* term, long long* batch_src) {
+EXPO_RL_HD int draw_critic(const float* stopped, int P, int B, const int* perm, int* term, long long* batch_src) {
   int nt = 0;
   for (int i = 0; i < P; ++i)
-    if (pool_states[(long long)perm[i] * S + kStateStopped] > 0.f) term[nt++] = perm[i];
+    if (stopped[perm[i]] > 0.f) term[nt++] = perm[i];
   for (int i = 0; i < B; ++i) batch_src[i] = nt > 0 ? term[i % nt] : perm[i % P];
   return nt;
 }

@@ -237,9 +237,26 @@ __global__ void __launch_bounds__(kGlueThreads) colsum_multi_kernel(const Colsum
   __syncthreads();
   if (ticket != (unsigned)(chunks - 1)) return;
   __threadfence();
-  if (ry == 0 && col < cols) {                           // last block of this column block: fixed chunk order
+  // last block of this column block: row-lane ry adds chunks ry, ry + 8, ... (4 loads in flight), then the 8 lanes
+  // are added in lane order -- a fixed order for a given shape, so the result is reproducible
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+  if (col < cols) {
+    int c = ry;
+    for (; c + 24 < chunks; c += 32) {
+      v0 += __ldcg(part + (size_t)c * cols + col);
+      v1 += __ldcg(part + (size_t)(c + 8) * cols + col);
+      v2 += __ldcg(part + (size_t)(c + 16) * cols + col);
+      v3 += __ldcg(part + (size_t)(c + 24) * cols + col);
+    }
+    for (; c < chunks; c += 8) v0 += __ldcg(part + (size_t)c * cols + col);
+  }
+  __syncthreads();
+  red[ry][threadIdx.x & 31] = (v0 + v1) + (v2 + v3);
+  __syncthreads();
+  if (ry == 0 && col < cols) {
     float v = 0.f;
-    for (int c = 0; c < chunks; ++c) v += __ldcg(part + (size_t)c * cols + col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[i][threadIdx.x];
     float* o = T.dst[t] + col;
     *o = T.accumulate[t] ? *o + v : v;
   }

@@ -3,7 +3,8 @@
 the image): per-kernel start/end inside the CUDA-graph replays -> busy time (union of kernel
 intervals), idle gaps, concurrency, per-kernel totals, and the same split per graph replay.
 
-  python tools/train_timeline.py [--iters 5] [--batch 64] [--out gpurun_out/timeline.json]
+  python tools/train_timeline.py [--iters 5] [--batch 64] [--out gpurun_out/timeline.json] [--host-replay]
+  torchrun --nproc-per-node N tools/train_timeline.py ...     (data parallel: rank 0 records and writes its own timeline)
 
 A measurement aid only (numbers under a profiler are never bench values)."""
 import argparse
@@ -36,20 +37,29 @@ def main():
   ap.add_argument("--iters", type=int, default=5)
   ap.add_argument("--batch", type=int, default=64)
   ap.add_argument("--out", default="gpurun_out/timeline.json")
+  ap.add_argument("--host-replay", action="store_true")
   args = ap.parse_args()
   import torch
+  import torch.distributed as dist
   from torch.profiler import ProfilerActivity, profile
-  from exposure_b200.replay import ReplayMemory, SyntheticProvider
+  from exposure_b200.replay import DeviceReplayMemory, ReplayMemory, SyntheticProvider
   from exposure_b200.trainer import Trainer, default_cfg
-  dev = torch.device("cuda", 0)
+  world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
   cfg = default_cfg()
   cfg.batch_size = args.batch
   cfg.replay_memory_size = 2 * args.batch
   t = Trainer(cfg, dev, seed=0)
-  mem = ReplayMemory(cfg, SyntheticProvider(dev, "raw", 100), SyntheticProvider(dev, "real", 200), dev, seed=0)
-  t.attach_memory(mem, torch.Generator(device=dev).manual_seed(300))
+  Mem = ReplayMemory if args.host_replay else DeviceReplayMemory
+  mem = Mem(cfg, SyntheticProvider(dev, "raw", 100 + rank), SyntheticProvider(dev, "real", 200 + rank), dev, seed=rank)
+  t.attach_memory(mem, torch.Generator(device=dev).manual_seed(300 + rank))
   t.train_iteration(0, giters=2 * cfg.test_steps + 2, citers=1)
   t.enable_graphs(args.batch)
+  if not args.host_replay and t._graph_apply:
+    t.enable_iteration_graph()
   it = 1
   for _ in range(5):
     t.train_iteration(it, giters=1, citers=5)
@@ -60,6 +70,11 @@ def main():
       t.train_iteration(it, giters=1, citers=5)
       it += 1
     torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  if rank != 0:
+    dist.destroy_process_group()
+    return
   evs = []
   for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start:
@@ -114,7 +129,9 @@ def main():
   gaps.sort()
   big = [g for g in gaps if g > 20.0]
   res = {
-      "iters": args.iters, "batch": args.batch, "pdl": os.environ.get("EXPOSURE_PDL", "default"),
+      "iters": args.iters, "batch": args.batch, "pdl": os.environ.get("EXPOSURE_PDL", "default"), "n_gpus": world,
+      "replay": "host" if args.host_replay else "device, whole iteration one graph",
+      "transport": "peer-memory all-reduce + Adam kernel" if t._peer is not None else ("dist.all_reduce" if world > 1 else "single GPU"),
       "span_us_per_iter": span / args.iters, "busy_us_per_iter": busy / args.iters,
       "idle_us_per_iter": (span - busy) / args.iters, "kernel_sum_us_per_iter": ksum / args.iters,
       "avg_concurrency_when_busy": ksum / busy, "kernels_per_iter": len(evs) / args.iters,
@@ -133,6 +150,8 @@ def main():
   for k in res["top_kernels"][:40]:
     print("%-58s %7.1f %8.2f %9.1f %9.1f %9.1f" % (k["kernel"][:58], k["launches_per_iter"], k["avg_us"], k["us_per_iter"],
                                                     k["share_us_per_iter"], k["solo_us_per_iter"]))
+  if world > 1:
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -97,6 +97,36 @@ def main():
       say("replicas bit-identical after 5 graph-replayed iterations (%s):" % name, same,
           "finite:", bool(torch.isfinite(a).all()))
     ok &= bool(torch.isfinite(a).all())
+  # the exchange kernels alone (no profiler: CUDA events, 30 back-to-back launches, max over ranks): what one optimizer
+  # step adds at this world size -- compare with exp_adam alone (the single-GPU optimizer step)
+  if t2._peer is not None:
+    from exposure_b200 import nn_ops as K
+    res = {}
+    for which, buf in (("gv", t2.gv), ("c", t2.cri)):
+      for _ in range(3):
+        t2._apply(which)
+      dist.barrier()
+      torch.cuda.synchronize()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      for _ in range(30):
+        t2._apply(which)
+      e1.record()
+      torch.cuda.synchronize()
+      tt = torch.tensor([e0.elapsed_time(e1) / 30], device=dev, dtype=torch.float64)
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      e0.record()
+      for _ in range(30):
+        K.adam(buf.flat, buf.grad, buf.m, buf.v, t2._hyper["c"], 0.5, 0.9, 1e-8, 1.0)
+      e1.record()
+      torch.cuda.synchronize()
+      res[which] = (float(tt), e0.elapsed_time(e1) / 30, buf.grad.numel() * 4 / 1e6)
+    if rank == 0:
+      for which, (dp_ms, adam_ms, mb) in res.items():
+        say("exchange+Adam kernel, %s buffer (%.1f MB), world %d: %.1f us per launch (exp_adam alone: %.1f us) -> %.0f GB/s of "
+            "NVLink traffic per GPU" % (which, mb, world, dp_ms * 1e3, adam_ms * 1e3, 2 * (world - 1) / world * mb / dp_ms))
+      per_iter = res["gv"][0] + 5 * res["c"][0] - (res["gv"][1] + 5 * res["c"][1])
+      say("per iteration (1 generator + 5 critic steps) the exchange adds %.0f us over the single-GPU optimizer steps" % (per_iter * 1e3))
   flag = torch.tensor([1 if ok else 0], device=dev)
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   if rank == 0:

@@ -903,6 +903,18 @@ def _cpu_eval_iteration(args):
   return iteration, B, cores
 
 
+def _id_histogram(ids):
+  """{filter short name: how many (step, image) slots of the episode applied it}"""
+  from exposure_b200.ops import FILTER_NAMES
+  flat = ids.detach().reshape(-1).cpu().tolist()
+  names = {i: f for i, f in enumerate(FILTER_NAMES)}
+  hist = {}
+  for i in flat:
+    k = names.get(int(i), "none")
+    hist[k] = hist.get(k, 0) + 1
+  return hist
+
+
 def run_eval(args):
   """configs[2] (evaluate.py inference): cfg.test_steps policy steps on 64x64 thumbnails + the
   selected filters applied to the (optionally high-resolution) batch by ONE fused kernel."""
@@ -976,7 +988,11 @@ def run_eval(args):
                    "frac": fbytes / fms / 1e6 / peak if fms else None, "traffic": None, "peak_source": peak_src,
                    "avg_ms": fms, "algorithmic_bytes_per_launch": fbytes,
                    "share_of_step": fms * len(fused) / ms if ms else None,
-                   "note": "24 B/pixel for the whole episode; the unfused schedule moves %d B/pixel" % (24 * S)},
+                   "frac_of_unfused_schedule": fbytes * S / fms / 1e6 / peak if fms else None,
+                   "filters_applied": _id_histogram(out["ids"]),
+                   "note": "24 B/pixel for the whole episode; the unfused schedule (SURVEY 8d: one read + one write per "
+                           "step) moves %d B/pixel.  The kernel is instruction-issue bound: what it costs depends on "
+                           "WHICH filters the policy picked (filters_applied)" % (24 * S)},
   }
   if not args.no_cpu_baseline:
     iteration, sb, cores = _cpu_eval_iteration(args)

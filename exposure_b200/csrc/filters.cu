@@ -8,6 +8,7 @@
 // Replaces the unfused TF-1.6 Eigen launches behind filters.py process() (2..43 launches
 // per filter) and the 8-way stack/one_hot/reduce_sum select of agent.py:77,118-129.
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
 
 #include "filter_math.cuh"
@@ -419,12 +420,12 @@ template <bool VEC>
 __global__ void __launch_bounds__(kThreads) filter_chain_fwd_kernel(const ChainArgs A) {
   __shared__ FilterConsts sc[kMaxChain];
   __shared__ int fids[kMaxChain];
-  const int b = blockIdx.y;
-  for (int s = 0; s < A.S; ++s) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int s = warp; s < A.S; s += kWarps) {               // one warp per step: the S set-ups run in parallel
     const int f = A.ids ? A.ids[s * A.B + b] : -1;
-    if (threadIdx.x == 0) fids[s] = f;
-    if (threadIdx.x < 32 && f >= 0 && f < EXP_NUM_FILTER_KINDS)
-      setup_consts(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits, A.rg);
+    if (lane == 0) fids[s] = f;
+    if (f >= 0 && f < EXP_NUM_FILTER_KINDS)
+      setup_consts_lane(sc[s], A.params + ((size_t)s * A.B + b) * A.pstride, f, A.logits, lane, A.rg);
   }
   __syncthreads();
   const size_t img = (size_t)b * A.P * 3;
@@ -1183,8 +1184,15 @@ int exp_filter_chain_fwd(const float* x, float* y, const float* params, int pstr
   ChainArgs A{};
   A.rg = host_ranges();
   A.x = x; A.y = y; A.params = params; A.ids = ids; A.S = S; A.B = B; A.P = P; A.pstride = pstride;
-  A.pix_per_block = kPixPerBlockFwd; A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
-  dim3 grid((P + kPixPerBlockFwd - 1) / kPixPerBlockFwd, B);
+  A.logits = (options & EXP_OPT_LOGITS) ? 1 : 0;
+  // The per-CTA set-up (tanh_range of up to 24 parameters per step) costs as much as ~2000 pixels of filter math, so a
+  // CTA takes a long run of pixels: ~8 waves of resident CTAs over the whole batch, never less than kPixPerBlockFwd.
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_image = std::max(1, (sms * 8 * 4 + B - 1) / B);        // 8 CTAs of 40 registers per SM, ~4 waves
+  A.pix_per_block = (((P + per_image - 1) / per_image + 1023) / 1024) * 1024;
+  if (A.pix_per_block < kPixPerBlockFwd) A.pix_per_block = kPixPerBlockFwd;
+  dim3 grid((P + A.pix_per_block - 1) / A.pix_per_block, B);
   if (vec) filter_chain_fwd_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
   else filter_chain_fwd_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(A);
   EXP_CHECK_LAUNCH("exp_filter_chain_fwd");

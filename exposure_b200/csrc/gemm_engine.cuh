@@ -14,7 +14,10 @@
 //   void  store(int m, int n, float acc)  epilogue
 //
 // 64 x BN x 8 CTA tile, 256 threads, 4 x (BN/16) register micro-tile, double-buffered shared
-// memory with register prefetch (one __syncthreads per K step).  A_MFAST / B_KFAST pick which
+// memory with register prefetch (one __syncthreads per stage of KU K-steps).  KU = 1 keeps one
+// gather in flight, enough when many CTAs share an SM; the fully connected heads at batch 64 are a
+// handful of CTAs with 8-16 K-steps each, every step a full global-memory round trip (~0.7 us):
+// they run with KU = 4, i.e. 4 K-steps gathered per round trip (same summation order, same bits).  A_MFAST / B_KFAST pick which
 // index runs across the lanes of a warp when gathering, so that the global reads follow the
 // contiguous dimension of the operand.
 //
@@ -29,19 +32,20 @@ constexpr int kGemmThreads = 256;
 constexpr int kBM = 64;
 constexpr int kBK = 8;
 
-template <class P, int BN, bool A_MFAST, bool B_KFAST>
+template <class P, int BN, bool A_MFAST, bool B_KFAST, int KU = 1>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const P p_in) {
   EXP_PDL_ENTRY();
   constexpr int TN = BN / 16;
   constexpr int NB = (kBK * BN) / kGemmThreads;   // B elements per thread per K step (2 or 1)
-  __shared__ __align__(16) float As[2][kBK][kBM + 4];
-  __shared__ __align__(16) float Bs[2][kBK][BN + 4];
+  __shared__ __align__(16) float As[2][KU * kBK][kBM + 4];
+  __shared__ __align__(16) float Bs[2][KU * kBK][BN + 4];
 
   P p = p_in;
   p.init(blockIdx.z);
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
   const int KI = p.k_iters();
+  const int KG = (KI + KU - 1) / KU;              // stages of KU K-steps
 
   // gather mappings
   int a_m[2], a_k[2];
@@ -60,19 +64,33 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const P p_in) {
 #pragma unroll
   for (int j = 0; j < 2; ++j) ra[j] = p.row_a(m0 + a_m[j]);
 
-  float areg[2], breg[NB];
-  auto gather = [&](int ki) {
-    const typename P::KS ks = p.kstate(ki);
+  float areg[KU][2], breg[KU][NB];
+  auto gather = [&](int kg) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) areg[j] = p.load_a(ra[j], ks, a_k[j]);
+    for (int u = 0; u < KU; ++u) {
+      const int ki = kg * KU + u;
+      if (KU == 1 || ki < KI) {
+        const typename P::KS ks = p.kstate(ki);
 #pragma unroll
-    for (int j = 0; j < NB; ++j) breg[j] = p.load_b(ks, b_k[j], n0 + b_n[j]);
+        for (int j = 0; j < 2; ++j) areg[u][j] = p.load_a(ra[j], ks, a_k[j]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) breg[u][j] = p.load_b(ks, b_k[j], n0 + b_n[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) areg[u][j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) breg[u][j] = 0.f;
+      }
+    }
   };
   auto stash = [&](int buf) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) As[buf][a_k[j]][a_m[j]] = areg[j];
+    for (int u = 0; u < KU; ++u) {
 #pragma unroll
-    for (int j = 0; j < NB; ++j) Bs[buf][b_k[j]][b_n[j]] = breg[j];
+      for (int j = 0; j < 2; ++j) As[buf][u * kBK + a_k[j]][a_m[j]] = areg[u][j];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) Bs[buf][u * kBK + b_k[j]][b_n[j]] = breg[u][j];
+    }
   };
 
   const int tx = tid % 16, ty = tid / 16;
@@ -87,11 +105,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const P p_in) {
     stash(0);
   }
   __syncthreads();
-  for (int ki = 0; ki < KI; ++ki) {
-    const int buf = ki & 1;
-    if (ki + 1 < KI) gather(ki + 1);
+  for (int kg = 0; kg < KG; ++kg) {
+    const int buf = kg & 1;
+    if (kg + 1 < KG) gather(kg + 1);
 #pragma unroll
-    for (int kk = 0; kk < kBK; ++kk) {
+    for (int kk = 0; kk < KU * kBK; ++kk) {
       const float4 av = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
       float bv[TN];
       if constexpr (TN == 4) {
@@ -107,7 +125,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const P p_in) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a4[i], bv[j], acc[i][j]);
     }
-    if (ki + 1 < KI) stash(buf ^ 1);
+    if (kg + 1 < KG) stash(buf ^ 1);
     __syncthreads();
   }
 #pragma unroll
@@ -116,10 +134,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const P p_in) {
     for (int j = 0; j < TN; ++j) p.store(m0 + ty * 4 + i, n0 + tx * TN + j, acc[i][j]);
 }
 
-template <class P, int BN, bool A_MFAST, bool B_KFAST>
+template <class P, int BN, bool A_MFAST, bool B_KFAST, int KU = 1>
 inline void launch_gemm(const P& p, int M, int N, int Z, cudaStream_t st) {
   dim3 grid((M + kBM - 1) / kBM, (N + BN - 1) / BN, Z);
-  launch_pdl(gemm_kernel<P, BN, A_MFAST, B_KFAST>, dim3(grid), dim3(kGemmThreads), 0, st, p);
+  launch_pdl(gemm_kernel<P, BN, A_MFAST, B_KFAST, KU>, dim3(grid), dim3(kGemmThreads), 0, st, p);
 }
 
 __device__ __forceinline__ float lrelu_f(float v) { return 0.6f * v + 0.4f * fabsf(v); }   // util.py:225-229

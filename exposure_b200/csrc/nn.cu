@@ -386,63 +386,124 @@ static int colsum_chunks(int rows) {
 // ------------------------------------------------------------------------------------------
 // dgrad into a FEW input channels (first layer: Cin = 6 critic / 17 value network; the gradient
 // w.r.t. the image, critics.py:48-87 through tf.gradients).  A 64 x 32 GEMM tile wastes most of
-// its columns on N = 6, and the op is tiny (0.4 GFLOP, 15 MB): one thread per input pixel of a
-// parity class instead, the class's 4 x Cin x Cout weights broadcast from shared memory, the
-// deltas read as float4 over co.
+// its columns on N = 6 and the op is tiny (0.4 GFLOP, 15 MB).  One thread per 2 x 2 block of input
+// pixels (all four parity classes of the stride-2 4 x 4 transposed convolution): the 3 x 3
+// neighbourhood of deltas it needs is staged for the whole CTA in shared memory by coalesced
+// float4 loads (pixel pitch Cout + 4 floats: conflict-free float4 reads), the 16 x Cin x Cout
+// weights are broadcast from shared memory, and a thread stores 2 x Cin contiguous floats per row.
+// Round 1's kernel (one thread per input pixel of ONE class, deltas read from global memory at a
+// 128-byte stride per lane) spent its time in L1 tag look-ups: 61 us for the critic's layer, 124 us
+// for the value network's.
 // ------------------------------------------------------------------------------------------
+constexpr int kDgsThreads = 128;
+struct DgsTile { int tw, th; };                                   // tile of (a, c) positions: tw * th = 128 threads
+static DgsTile dgs_tile(int OH, int OW) {
+  DgsTile t;
+  t.tw = OW < 32 ? OW : 32;
+  t.th = kDgsThreads / t.tw;
+  if (t.th > OH) t.th = OH;
+  return t;
+}
+static size_t dgs_smem_bytes(int OH, int OW, int Cin, int Cout) {
+  const DgsTile t = dgs_tile(OH, OW);
+  return ((size_t)16 * Cin * Cout + (size_t)(t.th + 2) * (t.tw + 2) * (Cout + 4)) * sizeof(float);
+}
 template <int CMAX>
-__global__ void __launch_bounds__(256) conv_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ W,
-                                                               const float* __restrict__ a_in, float* __restrict__ dx,
-                                                               int B, int IH, int IW, int Cin, int Cout, int lgW2, int lgHW2) {
+__global__ void __launch_bounds__(kDgsThreads) conv_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                                                       const float* __restrict__ a_in, float* __restrict__ dx,
+                                                                       int IH, int IW, int Cin, int Cout, int tw, int th,
+                                                                       int tiles_x, int tiles_y) {
   EXP_PDL_ENTRY();
-  extern __shared__ float4 w_s4[];                       // [4 taps of the class][Cin][Cout]
-  float* w_s = reinterpret_cast<float*>(w_s4);
-  const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
-  const int OH = IH / 2, OW = IW / 2;
-  int oy_off[4], ox_off[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int j = t >> 1, l = t & 1;
-    const int ky = py == 0 ? (j == 0 ? 1 : 3) : (j == 0 ? 0 : 2);
-    const int kx = px == 0 ? (l == 0 ? 1 : 3) : (l == 0 ? 0 : 2);
-    oy_off[t] = py == 0 ? (j == 0 ? 0 : -1) : (j == 0 ? 1 : 0);
-    ox_off[t] = px == 0 ? (l == 0 ? 0 : -1) : (l == 0 ? 1 : 0);
-    const float* src = W + (size_t)(ky * 4 + kx) * Cin * Cout;
-    for (int i = threadIdx.x; i < Cin * Cout; i += blockDim.x) w_s[t * Cin * Cout + i] = __ldg(src + i);
+  extern __shared__ float4 dgs_smem4[];
+  float4* const w_s4 = dgs_smem4;                                   // [ky][kx][Cin][Cout / 4]
+  const int co4n = Cout >> 2, pitch4 = co4n + 1;
+  float4* const d_s4 = dgs_smem4 + 16 * Cin * co4n;                 // [(th + 2)][(tw + 2)][pitch4]
+  const int OH = IH >> 1, OW = IW >> 1;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int b = tile / tiles_y;
+  const int a0 = ty * th, c0 = tx * tw;
+  {
+    const float4* src = reinterpret_cast<const float4*>(W);
+    for (int i = threadIdx.x; i < 16 * Cin * co4n; i += kDgsThreads) w_s4[i] = __ldg(src + i);
+    const int hw = tw + 2, n4 = (th + 2) * hw * co4n;
+    for (int i = threadIdx.x; i < n4; i += kDgsThreads) {
+      const int q = i % co4n, pix = i / co4n;
+      const int hc = pix % hw, hr = pix / hw;
+      const int oy = a0 + hr - 1, ox = c0 + hc - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)oy < (unsigned)OH && (unsigned)ox < (unsigned)OW)
+        v = __ldg(reinterpret_cast<const float4*>(dy + ((size_t)(b * OH + oy) * OW + ox) * Cout) + q);
+      d_s4[pix * pitch4 + q] = v;
+    }
   }
   __syncthreads();
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= B * OH * OW) return;
-  const int b = m >> lgHW2, rem = m & ((1 << lgHW2) - 1);
-  const int a = rem >> lgW2, c = rem & (OW - 1);
-  float acc[CMAX];
+  const int r = threadIdx.x / tw, cc = threadIdx.x - r * tw;
+  const int a = a0 + r, c = c0 + cc;
+  if (r >= th || a >= OH || c >= OW) return;
+  float acc[4][CMAX];
 #pragma unroll
-  for (int ci = 0; ci < CMAX; ++ci) acc[ci] = 0.f;
-  const int co4n = Cout >> 2;
+  for (int k = 0; k < 4; ++k)
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int oy = a + oy_off[t], ox = c + ox_off[t];
-    if ((unsigned)oy >= (unsigned)OH || (unsigned)ox >= (unsigned)OW) continue;
-    const float4* dp = reinterpret_cast<const float4*>(dy + ((size_t)(b * OH + oy) * OW + ox) * Cout);
-    const float4* wp = w_s4 + (size_t)t * Cin * co4n;
-    for (int q = 0; q < co4n; ++q) {
-      const float4 d = __ldg(dp + q);
+    for (int ci = 0; ci < CMAX; ++ci) acc[k][ci] = 0.f;
+#pragma unroll
+  for (int dyy = -1; dyy <= 1; ++dyy)
+#pragma unroll
+    for (int dxx = -1; dxx <= 1; ++dxx) {
+      const float4* dp = d_s4 + ((r + 1 + dyy) * (tw + 2) + (cc + 1 + dxx)) * pitch4;
+      for (int q = 0; q < co4n; ++q) {
+        const float4 d = dp[q];
+        // input row 2a + py takes output row a + dyy through tap ky = py - 2 dyy + 1 (stride 2, pad 1)
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+          const int ky = py - 2 * dyy + 1;
+          if (ky < 0 || ky > 3) continue;
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            const int kx = px - 2 * dxx + 1;
+            if (kx < 0 || kx > 3) continue;
+            const float4* wp = w_s4 + (size_t)(ky * 4 + kx) * Cin * co4n + q;
+#pragma unroll
+            for (int ci = 0; ci < CMAX; ++ci)
+              if (ci < Cin) {
+                const float4 w = wp[ci * co4n];
+                acc[py * 2 + px][ci] = fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, fmaf(d.w, w.w, acc[py * 2 + px][ci]))));
+              }
+          }
+        }
+      }
+    }
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      const size_t base = ((size_t)(b * IH + 2 * a + py) * IW + 2 * c + px) * Cin;
 #pragma unroll
       for (int ci = 0; ci < CMAX; ++ci)
         if (ci < Cin) {
-          const float4 w = wp[ci * co4n + q];
-          acc[ci] = fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, fmaf(d.w, w.w, acc[ci]))));
+          float o = acc[py * 2 + px][ci];
+          if (a_in) o *= dlrelu_from_out(__ldg(a_in + base + ci));
+          dx[base + ci] = o;
         }
     }
+}
+template <int CMAX>
+static cudaError_t launch_dgrad_small(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH, int IW,
+                                      int Cin, int Cout, cudaStream_t stream) {
+  const int OH = IH / 2, OW = IW / 2;
+  const DgsTile t = dgs_tile(OH, OW);
+  const int tiles_x = (OW + t.tw - 1) / t.tw, tiles_y = (OH + t.th - 1) / t.th;
+  const size_t smem = dgs_smem_bytes(OH, OW, Cin, Cout);
+  static size_t opted = 0;                                       // per instantiation
+  if (smem > 48 * 1024 && smem > opted) {
+    const cudaError_t e = cudaFuncSetAttribute(conv_dgrad_small_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    opted = smem;
   }
-  const size_t base = ((size_t)(b * IH + 2 * a + py) * IW + 2 * c + px) * Cin;
-#pragma unroll
-  for (int ci = 0; ci < CMAX; ++ci)
-    if (ci < Cin) {
-      float o = acc[ci];
-      if (a_in) o *= dlrelu_from_out(__ldg(a_in + base + ci));
-      dx[base + ci] = o;
-    }
+  launch_pdl(conv_dgrad_small_kernel<CMAX>, dim3((unsigned)(B * tiles_x * tiles_y)), dim3(kDgsThreads), smem, stream, dy, W, a_in,
+             dx, IH, IW, Cin, Cout, t.tw, t.th, tiles_x, tiles_y);
+  return cudaSuccess;
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -457,6 +518,7 @@ static int wgrad_splits(int B, int OH, int OW, int Cin, int Cout) {
   if (s < 1) s = 1;
   return s;
 }
+constexpr int kFcKU = 4;      // K-steps gathered per global-memory round trip by the fully connected GEMMs (gemm_engine.cuh)
 static int fc_splits(int M, int K, int N) {
   const int tiles = ((M + kBM - 1) / kBM) * ((N + 63) / 64);
   int s = (296 + tiles - 1) / tiles;
@@ -513,13 +575,11 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
   p.OW = IW / 2; p.Cout = Cout; p.chunks = Cout / kBK;
   p.lgW2 = host_ilog2(IW / 2); p.lgHW2 = host_ilog2((IH / 2) * (IW / 2));
   const int M = B * (IH / 2) * (IW / 2);
-  if (use_tma() && Cin <= 20 && Cout % 4 == 0 && 4 * Cin * Cout * sizeof(float) <= 48 * 1024 && aligned16(dy)) {
-    const dim3 grid((M + 255) / 256, 1, 4);
-    const size_t smem = (size_t)4 * Cin * Cout * sizeof(float);
-    if (Cin <= 8)
-      launch_pdl(conv_dgrad_small_kernel<8>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
-    else
-      launch_pdl(conv_dgrad_small_kernel<20>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, dy, W, a_in, dx, B, IH, IW, Cin, Cout, p.lgW2, p.lgHW2);
+  if (use_tma() && Cin <= 20 && Cout % 4 == 0 && dgs_smem_bytes(IH / 2, IW / 2, Cin, Cout) <= 96 * 1024 && aligned16(dy) &&
+      aligned16(W) && (long long)B * (IH / 2) * (IW / 2) < (1ll << 31)) {
+    const cudaError_t e = Cin <= 8 ? launch_dgrad_small<8>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream)
+                                   : launch_dgrad_small<20>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[small]: %s", cudaGetErrorString(e));
     EXP_CHECK_LAUNCH("exp_conv_dgrad[small]");
     return EXP_OK;
   }
@@ -611,8 +671,8 @@ int exp_fc_fwd(const float* x, int ldx, const float* W, const float* bias, const
   int kps = (K + splits - 1) / splits;
   kps = ((kps + kBK - 1) / kBK) * kBK;
   p.k_per_split = kps;
-  if (N <= 32) launch_gemm<FcFwd, 32, false, false>(p, M, N, splits, (cudaStream_t)stream);
-  else launch_gemm<FcFwd, 64, false, false>(p, M, N, splits, (cudaStream_t)stream);
+  if (N <= 32) launch_gemm<FcFwd, 32, false, false, kFcKU>(p, M, N, splits, (cudaStream_t)stream);
+  else launch_gemm<FcFwd, 64, false, false, kFcKU>(p, M, N, splits, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_fwd");
   const size_t count = (size_t)M * N;
   launch_pdl(splitk_reduce_kernel, dim3((unsigned)((count + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
@@ -630,8 +690,8 @@ int exp_fc_dgrad(const float* dy, int ldy, const float* W, const float* mul_act,
   p.dy = dy; p.W = W; p.mul_act = mul_act; p.mul_plain = mul_plain; p.dx = dx; p.M = M; p.K = K; p.N = N;
   p.ldy = ldy; p.lddx = lddx; p.ldmul = ldmul; p.accumulate = accumulate;
   // the 4096 x 128 heads at batch 64: 64-wide tiles give 64 CTAs on 148 SMs -> halve the tile until the grid fills them
-  if (((M + kBM - 1) / kBM) * ((K + 63) / 64) < 148) launch_gemm<FcDgrad, 32, false, true>(p, M, K, 1, (cudaStream_t)stream);
-  else launch_gemm<FcDgrad, 64, false, true>(p, M, K, 1, (cudaStream_t)stream);
+  if (((M + kBM - 1) / kBM) * ((K + 63) / 64) < 148) launch_gemm<FcDgrad, 32, false, true, kFcKU>(p, M, K, 1, (cudaStream_t)stream);
+  else launch_gemm<FcDgrad, 64, false, true, kFcKU>(p, M, K, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_dgrad");
   return EXP_OK;
 }
@@ -642,8 +702,8 @@ int exp_fc_wgrad(const float* x, int ldx, const float* dy, int ldy, float* gW, i
   EXP_CHECK_ARG(M > 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "bad shape");
   FcWgrad p{};
   p.x = x; p.dy = dy; p.gW = gW; p.M = M; p.K = K; p.N = N; p.ldx = ldx; p.ldy = ldy; p.accumulate = accumulate;
-  if (N <= 32) launch_gemm<FcWgrad, 32, true, false>(p, K, N, 1, (cudaStream_t)stream);
-  else launch_gemm<FcWgrad, 64, true, false>(p, K, N, 1, (cudaStream_t)stream);
+  if (N <= 32) launch_gemm<FcWgrad, 32, true, false, kFcKU>(p, K, N, 1, (cudaStream_t)stream);
+  else launch_gemm<FcWgrad, 64, true, false, kFcKU>(p, K, N, 1, (cudaStream_t)stream);
   EXP_CHECK_LAUNCH("exp_fc_wgrad");
   return EXP_OK;
 }

@@ -77,6 +77,7 @@ def full(src, dst, note=""):
 
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+TIME_US = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6, "nsecond": 1e-3}
 FNAMES = ("exposure", "gamma", "wb", "satplus", "tone", "contrast", "wnb", "color", "level", "vignet")
 
 
@@ -106,7 +107,8 @@ def traffic(src, dst, config):
     rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT[units[idx["dram__bytes_read.sum"]]]
     wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
     res[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
-                 "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]]), "kernel": short(r[idx["Kernel Name"]])}
+                 "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]]) * TIME_US[units[idx["gpu__time_duration.sum"]]],
+                 "kernel": short(r[idx["Kernel Name"]])}
 
   for r in rows[2:]:
     kn = r[idx["Kernel Name"]]

@@ -20,6 +20,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
 ]
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
+# development builds only, e.g. EXPOSURE_NVCC_EXTRA=-DEXPO_TMA_TRACE (tools/tma_trace.py); part of the build digest
+NVCC_FLAGS += os.environ.get("EXPOSURE_NVCC_EXTRA", "").split()
 
 
 def _sources():

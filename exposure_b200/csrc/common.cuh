@@ -63,6 +63,77 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Same, as one thread-block cluster of `cluster_x` CTAs along x per (blockIdx.y, blockIdx.z).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, unsigned cluster_x,
+                                      cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+// Sum N doubles over every thread of every CTA of the cluster (of the CTA alone when the kernel was launched without
+// one): warp shuffles, one shared-memory pass per CTA, then EVERY CTA adds the per-CTA totals in rank order out of
+// distributed shared memory -- all CTAs of the cluster end up with the same bits.  sh: THREADS / 32 * N doubles,
+// xch: N doubles, both __shared__.  The per-image reductions of the critic statistics run on this with 8 CTAs per image:
+// one CTA per image is a serial walk of P / 256 dependent loads per thread (17 us for 64 x 64 pixels).
+template <int THREADS, int N>
+__device__ __forceinline__ void cluster_sum(double (&v)[N], double* sh, double* xch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) sh[warp * N + i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double t = 0.0;
+    for (int w = 0; w < THREADS / 32; ++w) t += sh[w * N + threadIdx.x];
+    xch[threadIdx.x] = t;
+  }
+  unsigned nb;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(nb));
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = 0.0;
+  const uint32_t local = (uint32_t)__cvta_generic_to_shared(xch);
+  for (unsigned r = 0; r < nb; ++r) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double t;
+      asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(t) : "r"(remote + 8u * i) : "memory");
+      v[i] += t;
+    }
+  }
+  // nobody may leave (or reuse xch) while a peer still reads its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank_x() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctaid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size_x() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(r)); return r; }
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

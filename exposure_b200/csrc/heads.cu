@@ -54,29 +54,35 @@ __device__ __forceinline__ float sat_of(const float* p, float* w /*nullable [3]*
   return sat;
 }
 
-// stats[b] = (mean lum, population variance of lum, mean saturation)   one CTA per image
+// stats[b] = (mean lum, population variance of lum, mean saturation)
+// grid (kStatsCluster, B), one cluster per image: CTA r takes the r-th slice of the pixels (cluster_sum, common.cuh)
+constexpr unsigned kStatsCluster = 8;
+__device__ __forceinline__ void stats_slice(int P, int& lo, int& hi) {
+  const unsigned r = cluster_rank_x(), n = cluster_size_x();
+  lo = (int)((long long)P * r / n);
+  hi = (int)((long long)P * (r + 1) / n);
+}
 __global__ void __launch_bounds__(256) stats_fwd_kernel(const float* __restrict__ img, float* __restrict__ stats, int P) {
   EXP_PDL_ENTRY();
-  __shared__ double sh[8];
-  const float* x = img + (size_t)blockIdx.x * P * 3;
-  double sl = 0.0, ss = 0.0;
-  for (int p = threadIdx.x; p < P; p += 256) {
-    sl += (double)lum_of(x + 3 * (size_t)p);
-    ss += (double)sat_of(x + 3 * (size_t)p, nullptr);
+  __shared__ double sh[8 * 3], xch[3];
+  const float* x = img + (size_t)blockIdx.y * P * 3;
+  int lo, hi;
+  stats_slice(P, lo, hi);
+  // one pass, one cluster reduction: sum l, sum l^2 (exact products in double), sum sat; the population variance is
+  // E[l^2] - E[l]^2 in double (l <= 4, P <= 2^29: the cancellation costs ~1e-16 mean^2 / var, far below float rounding)
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int p = lo + threadIdx.x; p < hi; p += 256) {
+    const double l = (double)lum_of(x + 3 * (size_t)p);
+    a[0] += l;
+    a[1] += l * l;
+    a[2] += (double)sat_of(x + 3 * (size_t)p, nullptr);
   }
-  sl = block_sum<256>(sl, sh);
-  ss = block_sum<256>(ss, sh);
-  const float mean = (float)(sl / P);
-  double sv = 0.0;
-  for (int p = threadIdx.x; p < P; p += 256) {
-    const float d = lum_of(x + 3 * (size_t)p) - mean;
-    sv += (double)(d * d);
-  }
-  sv = block_sum<256>(sv, sh);
-  if (threadIdx.x == 0) {
-    stats[blockIdx.x * 3 + 0] = mean;
-    stats[blockIdx.x * 3 + 1] = (float)(sv / P);
-    stats[blockIdx.x * 3 + 2] = (float)(ss / P);
+  cluster_sum<256, 3>(a, sh, xch);
+  if (threadIdx.x == 0 && cluster_rank_x() == 0) {
+    const double mean = a[0] / P, var = a[1] / P - mean * mean;
+    stats[blockIdx.y * 3 + 0] = (float)mean;
+    stats[blockIdx.y * 3 + 1] = (float)(var > 0.0 ? var : 0.0);
+    stats[blockIdx.y * 3 + 2] = (float)(a[2] / P);
   }
 }
 
@@ -101,30 +107,30 @@ __global__ void __launch_bounds__(256) stats_bwd_kernel(const float* __restrict_
   }
 }
 
-// dstat[b] = J_stats u   (forward-mode tangent)   one CTA per image
+// dstat[b] = J_stats u   (forward-mode tangent)   grid (kStatsCluster, B), one cluster per image
 __global__ void __launch_bounds__(256) stats_jvp_kernel(const float* __restrict__ img, const float* __restrict__ stats,
                                                         const float* __restrict__ u, float* __restrict__ dstat, int P) {
   EXP_PDL_ENTRY();
-  __shared__ double sh[8];
-  const size_t base = (size_t)blockIdx.x * P * 3;
-  const float mean = stats[blockIdx.x * 3];
-  double a = 0.0, v = 0.0, s = 0.0;
-  for (int p = threadIdx.x; p < P; p += 256) {
+  __shared__ double sh[8 * 3], xch[3];
+  const size_t base = (size_t)blockIdx.y * P * 3;
+  const float mean = stats[blockIdx.y * 3];
+  int lo, hi;
+  stats_slice(P, lo, hi);
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int p = lo + threadIdx.x; p < hi; p += 256) {
     const size_t o = base + 3 * (size_t)p;
     float w[3];
     sat_of(img + o, w);
     const float cu = kLR * u[o] + kLG * u[o + 1] + kLB * u[o + 2];
-    a += (double)cu;
-    v += (double)((lum_of(img + o) - mean) * cu);
-    s += (double)(w[0] * u[o] + w[1] * u[o + 1] + w[2] * u[o + 2]);
+    a[0] += (double)cu;
+    a[1] += (double)((lum_of(img + o) - mean) * cu);
+    a[2] += (double)(w[0] * u[o] + w[1] * u[o + 1] + w[2] * u[o + 2]);
   }
-  a = block_sum<256>(a, sh);
-  v = block_sum<256>(v, sh);
-  s = block_sum<256>(s, sh);
-  if (threadIdx.x == 0) {
-    dstat[blockIdx.x * 3 + 0] = (float)(a / P);
-    dstat[blockIdx.x * 3 + 1] = (float)(2.0 * v / P);
-    dstat[blockIdx.x * 3 + 2] = (float)(s / P);
+  cluster_sum<256, 3>(a, sh, xch);
+  if (threadIdx.x == 0 && cluster_rank_x() == 0) {
+    dstat[blockIdx.y * 3 + 0] = (float)(a[0] / P);
+    dstat[blockIdx.y * 3 + 1] = (float)(2.0 * a[1] / P);
+    dstat[blockIdx.y * 3 + 2] = (float)(a[2] / P);
   }
 }
 
@@ -337,8 +343,8 @@ using namespace expo;
 extern "C" {
 
 int exp_stats_fwd(const float* img, float* stats, int B, int H, int W, void* stream) {
-  EXP_CHECK_ARG(img && stats && B > 0 && H > 0 && W > 0, "bad args");
-  launch_pdl(stats_fwd_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, img, stats, H * W);
+  EXP_CHECK_ARG(img && stats && B > 0 && B <= 65535 && H > 0 && W > 0, "bad args");
+  launch_pdl_cluster(stats_fwd_kernel, dim3(kStatsCluster, B), dim3(256), 0, kStatsCluster, (cudaStream_t)stream, img, stats, H * W);
   EXP_CHECK_LAUNCH("exp_stats_fwd");
   return EXP_OK;
 }
@@ -352,8 +358,8 @@ int exp_stats_bwd(const float* img, const float* stats, const float* g_stat, con
   return EXP_OK;
 }
 int exp_stats_jvp(const float* img, const float* stats, const float* u, float* dstat, int B, int H, int W, void* stream) {
-  EXP_CHECK_ARG(img && stats && u && dstat && B > 0 && H > 0 && W > 0, "bad args");
-  launch_pdl(stats_jvp_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, img, stats, u, dstat, H * W);
+  EXP_CHECK_ARG(img && stats && u && dstat && B > 0 && B <= 65535 && H > 0 && W > 0, "bad args");
+  launch_pdl_cluster(stats_jvp_kernel, dim3(kStatsCluster, B), dim3(256), 0, kStatsCluster, (cudaStream_t)stream, img, stats, u, dstat, H * W);
   EXP_CHECK_LAUNCH("exp_stats_jvp");
   return EXP_OK;
 }

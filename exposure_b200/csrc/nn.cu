@@ -386,32 +386,38 @@ static int colsum_chunks(int rows) {
 // ------------------------------------------------------------------------------------------
 // dgrad into a FEW input channels (first layer: Cin = 6 critic / 17 value network; the gradient
 // w.r.t. the image, critics.py:48-87 through tf.gradients).  A 64 x 32 GEMM tile wastes most of
-// its columns on N = 6 and the op is tiny (0.4 GFLOP, 15 MB).  One thread per 2 x 2 block of input
-// pixels (all four parity classes of the stride-2 4 x 4 transposed convolution): the 3 x 3
-// neighbourhood of deltas it needs is staged for the whole CTA in shared memory by coalesced
-// float4 loads (pixel pitch Cout + 4 floats: conflict-free float4 reads), the 16 x Cin x Cout
-// weights are broadcast from shared memory, and a thread stores 2 x Cin contiguous floats per row.
-// Round 1's kernel (one thread per input pixel of ONE class, deltas read from global memory at a
-// 128-byte stride per lane) spent its time in L1 tag look-ups: 61 us for the critic's layer, 124 us
-// for the value network's.
+// its columns on N = 6 and the op is tiny (0.4 GFLOP, 15 MB).  One thread per INPUT pixel: a CTA
+// covers a tile of th x tw positions (a, c) of the stride-2 grid, thread (class, a, c) computes input
+// pixel (2a + py, 2c + px) of parity class (py, px) -- the class is uniform per warp, so its 4 taps
+// and their weights are warp-uniform.  The (th + 2) x (tw + 2) neighbourhood of deltas is staged in
+// shared memory by coalesced float4 loads (pixel pitch Cout + 4 floats: conflict-free float4 reads);
+// the 16 x Cin x Cout weights are broadcast from shared memory.
+// History: round 1 read the deltas from global memory at a 128-byte stride per lane (61 us for the
+// critic's layer at batch 64, 124 us for the value network's, all L1 tag look-ups); one thread per
+// 2 x 2 block of pixels with staged deltas: 40 / 132 us (14 warps per SM cannot hide the FMA chains).
 // ------------------------------------------------------------------------------------------
-constexpr int kDgsThreads = 128;
-struct DgsTile { int tw, th; };                                   // tile of (a, c) positions: tw * th = 128 threads
-static DgsTile dgs_tile(int OH, int OW) {
+// POS positions (a, c) per tile x 4 parity classes x CSPLIT slices of the input channels = 1024 threads per CTA:
+// 256 positions for Cin <= 8; 128 positions x 2 channel slices of 10 for Cin <= 20 (20 accumulators per thread
+// do not fit the 64 registers of a 1024-thread CTA)
+struct DgsTile { int tw, th; };
+static DgsTile dgs_tile(int OH, int OW, int pos) {
   DgsTile t;
   t.tw = OW < 32 ? OW : 32;
-  t.th = kDgsThreads / t.tw;
+  t.th = pos / t.tw;
   if (t.th > OH) t.th = OH;
   return t;
 }
+static int dgs_pos(int Cin) { return Cin <= 8 ? 256 : 128; }
 static size_t dgs_smem_bytes(int OH, int OW, int Cin, int Cout) {
-  const DgsTile t = dgs_tile(OH, OW);
-  return ((size_t)16 * Cin * Cout + (size_t)(t.th + 2) * (t.tw + 2) * (Cout + 4)) * sizeof(float);
+  const DgsTile t = dgs_tile(OH, OW, dgs_pos(Cin));
+  const size_t stage_in = (size_t)16 * Cin * Cout + (size_t)(t.th + 2) * (t.tw + 2) * (Cout + 4);
+  const size_t stage_out = (size_t)4 * t.th * t.tw * Cin;           // the dx tile reuses the same memory
+  return (stage_in > stage_out ? stage_in : stage_out) * sizeof(float);
 }
-template <int CMAX>
-__global__ void __launch_bounds__(kDgsThreads) conv_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+template <int CMAX, int POS, int CSPLIT>
+__global__ void __launch_bounds__(4 * POS * CSPLIT, 1) conv_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                                        const float* __restrict__ a_in, float* __restrict__ dx,
-                                                                       int IH, int IW, int Cin, int Cout, int tw, int th,
+                                                                       int IH, int IW, int Cin, int CinW, int Cout, int tw, int th,
                                                                        int tiles_x, int tiles_y) {
   EXP_PDL_ENTRY();
   extern __shared__ float4 dgs_smem4[];
@@ -425,10 +431,15 @@ __global__ void __launch_bounds__(kDgsThreads) conv_dgrad_small_kernel(const flo
   const int b = tile / tiles_y;
   const int a0 = ty * th, c0 = tx * tw;
   {
+    // the first Cin of the CinW input channels of every tap (CinW > Cin: exp_conv_first_dgrad, image channels only)
     const float4* src = reinterpret_cast<const float4*>(W);
-    for (int i = threadIdx.x; i < 16 * Cin * co4n; i += kDgsThreads) w_s4[i] = __ldg(src + i);
+    const int per = Cin * co4n;
+    for (int i = threadIdx.x; i < 16 * per; i += 4 * POS * CSPLIT) {
+      const int tap = i / per, rem = i - tap * per;
+      w_s4[i] = __ldg(src + (size_t)tap * CinW * co4n + rem);
+    }
     const int hw = tw + 2, n4 = (th + 2) * hw * co4n;
-    for (int i = threadIdx.x; i < n4; i += kDgsThreads) {
+    for (int i = threadIdx.x; i < n4; i += 4 * POS * CSPLIT) {
       const int q = i % co4n, pix = i / co4n;
       const int hc = pix % hw, hr = pix / hw;
       const int oy = a0 + hr - 1, ox = c0 + hc - 1;
@@ -439,71 +450,84 @@ __global__ void __launch_bounds__(kDgsThreads) conv_dgrad_small_kernel(const flo
     }
   }
   __syncthreads();
-  const int r = threadIdx.x / tw, cc = threadIdx.x - r * tw;
-  const int a = a0 + r, c = c0 + cc;
-  if (r >= th || a >= OH || c >= OW) return;
-  float acc[4][CMAX];
+  const int grp = threadIdx.x / POS, pos = threadIdx.x - grp * POS;      // grp is uniform per warp
+  const int cls = grp & 3, ci0 = (grp >> 2) * CMAX;                      // parity class, first input channel of the slice
+  const int py = cls >> 1, px = cls & 1;
+  const int r = pos / tw, cc = pos - r * tw;
+  const bool active = r < th;                       // OH, OW, th, tw are powers of two: every tile is full
+  float acc[CMAX];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int ci = 0; ci < CMAX; ++ci) acc[ci] = 0.f;
+  // input row 2a + py takes output row a + dyy through tap ky = py - 2 dyy + 1 (stride 2, pad 1): dyy = 0 and the
+  // neighbour on the side of the parity
+  if (active) {
 #pragma unroll
-    for (int ci = 0; ci < CMAX; ++ci) acc[k][ci] = 0.f;
+    for (int j = 0; j < 2; ++j) {
+      const int dyy = j == 0 ? 0 : (py ? 1 : -1);
+      const int ky = py - 2 * dyy + 1;
 #pragma unroll
-  for (int dyy = -1; dyy <= 1; ++dyy)
+      for (int l = 0; l < 2; ++l) {
+        const int dxx = l == 0 ? 0 : (px ? 1 : -1);
+        const int kx = px - 2 * dxx + 1;
+        const float4* dp = d_s4 + ((r + 1 + dyy) * (tw + 2) + (cc + 1 + dxx)) * pitch4;
+        const float4* wp = w_s4 + (size_t)(ky * 4 + kx) * Cin * co4n;
+#pragma unroll 2
+        for (int q = 0; q < co4n; ++q) {
+          const float4 d = dp[q];
 #pragma unroll
-    for (int dxx = -1; dxx <= 1; ++dxx) {
-      const float4* dp = d_s4 + ((r + 1 + dyy) * (tw + 2) + (cc + 1 + dxx)) * pitch4;
-      for (int q = 0; q < co4n; ++q) {
-        const float4 d = dp[q];
-        // input row 2a + py takes output row a + dyy through tap ky = py - 2 dyy + 1 (stride 2, pad 1)
-#pragma unroll
-        for (int py = 0; py < 2; ++py) {
-          const int ky = py - 2 * dyy + 1;
-          if (ky < 0 || ky > 3) continue;
-#pragma unroll
-          for (int px = 0; px < 2; ++px) {
-            const int kx = px - 2 * dxx + 1;
-            if (kx < 0 || kx > 3) continue;
-            const float4* wp = w_s4 + (size_t)(ky * 4 + kx) * Cin * co4n + q;
-#pragma unroll
-            for (int ci = 0; ci < CMAX; ++ci)
-              if (ci < Cin) {
-                const float4 w = wp[ci * co4n];
-                acc[py * 2 + px][ci] = fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, fmaf(d.w, w.w, acc[py * 2 + px][ci]))));
-              }
-          }
+          for (int ci = 0; ci < CMAX; ++ci)
+            if (ci0 + ci < Cin) {
+              const float4 w = wp[(ci0 + ci) * co4n + q];
+              acc[ci] = fmaf(d.x, w.x, fmaf(d.y, w.y, fmaf(d.z, w.z, fmaf(d.w, w.w, acc[ci]))));
+            }
         }
       }
     }
+  }
+  // The tile of dx is 2 th rows of 2 tw x Cin contiguous floats: staged in shared memory (over the deltas and weights,
+  // nobody needs them any more) and written out with full 128-byte lines -- a thread storing its own Cin floats
+  // touches a sector per float.
+  __syncthreads();
+  float* const o_s = reinterpret_cast<float*>(dgs_smem4);
+  const int rowlen = 2 * tw * Cin;
+  if (active) {
+    float* o = o_s + (2 * r + py) * rowlen + (2 * cc + px) * Cin + ci0;
 #pragma unroll
-  for (int py = 0; py < 2; ++py)
-#pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      const size_t base = ((size_t)(b * IH + 2 * a + py) * IW + 2 * c + px) * Cin;
-#pragma unroll
-      for (int ci = 0; ci < CMAX; ++ci)
-        if (ci < Cin) {
-          float o = acc[py * 2 + px][ci];
-          if (a_in) o *= dlrelu_from_out(__ldg(a_in + base + ci));
-          dx[base + ci] = o;
-        }
-    }
+    for (int ci = 0; ci < CMAX; ++ci)
+      if (ci0 + ci < Cin) o[ci] = acc[ci];
+  }
+  __syncthreads();
+  const int total = 2 * th * rowlen;
+  for (int i = threadIdx.x; i < total; i += 4 * POS * CSPLIT) {
+    const int row = i / rowlen, jj = i - row * rowlen;
+    const size_t g = ((size_t)(b * IH + 2 * a0 + row) * IW + 2 * c0) * Cin + jj;
+    float v = o_s[i];
+    if (a_in) v *= dlrelu_from_out(__ldg(a_in + g));
+    dx[g] = v;
+  }
 }
-template <int CMAX>
+template <int CMAX, int POS, int CSPLIT>
 static cudaError_t launch_dgrad_small(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH, int IW,
-                                      int Cin, int Cout, cudaStream_t stream) {
+                                      int Cin, int CinW, int Cout, cudaStream_t stream) {
   const int OH = IH / 2, OW = IW / 2;
-  const DgsTile t = dgs_tile(OH, OW);
+  const DgsTile t = dgs_tile(OH, OW, POS);
   const int tiles_x = (OW + t.tw - 1) / t.tw, tiles_y = (OH + t.th - 1) / t.th;
   const size_t smem = dgs_smem_bytes(OH, OW, Cin, Cout);
   static size_t opted = 0;                                       // per instantiation
   if (smem > 48 * 1024 && smem > opted) {
-    const cudaError_t e = cudaFuncSetAttribute(conv_dgrad_small_kernel<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const cudaError_t e = cudaFuncSetAttribute(conv_dgrad_small_kernel<CMAX, POS, CSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     opted = smem;
   }
-  launch_pdl(conv_dgrad_small_kernel<CMAX>, dim3((unsigned)(B * tiles_x * tiles_y)), dim3(kDgsThreads), smem, stream, dy, W, a_in,
-             dx, IH, IW, Cin, Cout, t.tw, t.th, tiles_x, tiles_y);
-  return cudaSuccess;
+  return launch_pdl(conv_dgrad_small_kernel<CMAX, POS, CSPLIT>, dim3((unsigned)(B * tiles_x * tiles_y)), dim3(4 * POS * CSPLIT), smem, stream, dy, W,
+                    a_in, dx, IH, IW, Cin, CinW, Cout, t.tw, t.th, tiles_x, tiles_y);
+}
+
+// dx[B,IH,IW,Cin] from the first Cin of CinW weight channels; the caller has checked dgs_smem_bytes / alignment / pow2 sizes
+cudaError_t conv_dgrad_small_launch(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH, int IW, int Cin,
+                                    int CinW, int Cout, cudaStream_t stream) {
+  return Cin <= 8 ? launch_dgrad_small<8, 256, 1>(dy, W, a_in, dx, B, IH, IW, Cin, CinW, Cout, stream)
+                  : launch_dgrad_small<10, 128, 2>(dy, W, a_in, dx, B, IH, IW, Cin, CinW, Cout, stream);
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -575,10 +599,9 @@ int exp_conv_dgrad(const float* dy, const float* W, const float* a_in, float* dx
   p.OW = IW / 2; p.Cout = Cout; p.chunks = Cout / kBK;
   p.lgW2 = host_ilog2(IW / 2); p.lgHW2 = host_ilog2((IH / 2) * (IW / 2));
   const int M = B * (IH / 2) * (IW / 2);
-  if (use_tma() && Cin <= 20 && Cout % 4 == 0 && dgs_smem_bytes(IH / 2, IW / 2, Cin, Cout) <= 96 * 1024 && aligned16(dy) &&
+  if (use_tma() && Cin <= 20 && Cout % 4 == 0 && dgs_smem_bytes(IH / 2, IW / 2, Cin, Cout) <= 110 * 1024 && aligned16(dy) &&
       aligned16(W) && (long long)B * (IH / 2) * (IW / 2) < (1ll << 31)) {
-    const cudaError_t e = Cin <= 8 ? launch_dgrad_small<8>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream)
-                                   : launch_dgrad_small<20>(dy, W, a_in, dx, B, IH, IW, Cin, Cout, (cudaStream_t)stream);
+    const cudaError_t e = conv_dgrad_small_launch(dy, W, a_in, dx, B, IH, IW, Cin, Cin, Cout, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(EXP_ERR_CUDA, "exp_conv_dgrad[small]: %s", cudaGetErrorString(e));
     EXP_CHECK_LAUNCH("exp_conv_dgrad[small]");
     return EXP_OK;

@@ -21,6 +21,24 @@ namespace tma {
 
 constexpr int kPersistThreads = 320;
 
+// Development aid (-DEXPO_TMA_TRACE, tools/tma_trace.py): SM-clock stamps of the ring hand-overs of the first CTAs.
+#ifdef EXPO_TMA_TRACE
+constexpr int kTraceCtas = 4, kTraceSteps = 96, kTraceTiles = 16;
+__device__ long long g_tma_trace[kTraceCtas][kTraceSteps][5];
+__device__ long long g_tma_trace_epi[kTraceCtas][kTraceTiles][3];
+#define EXPO_TRACE(it, slot)                                                                          \
+  do {                                                                                                \
+    if (blockIdx.x < kTraceCtas && (it) < kTraceSteps) g_tma_trace[blockIdx.x][(it)][(slot)] = clock64(); \
+  } while (0)
+#define EXPO_TRACE_EPI(j, slot)                                                                          \
+  do {                                                                                                   \
+    if (blockIdx.x < kTraceCtas && (j) < kTraceTiles) g_tma_trace_epi[blockIdx.x][(j)][(slot)] = clock64(); \
+  } while (0)
+#else
+#define EXPO_TRACE(it, slot) do {} while (0)
+#define EXPO_TRACE_EPI(j, slot) do {} while (0)
+#endif
+
 template <int BN>
 struct PersistCfg {
   static constexpr int kStages = BN >= 128 ? 3 : (BN == 64 ? 4 : 5);
@@ -86,6 +104,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
         for (int ki = 0; ki < KI; ++ki, ++it) {
           const int s = it % NS, use = it / NS;
           if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+          EXPO_TRACE(it, 0);
           unsigned char* a_raw = base + (size_t)s * C::kStageBytes;
           unsigned char* b_raw = a_raw + 2 * kTileA;
           mbar_expect_tx(&raw_full[s], (uint32_t)(kTileA + C::kTileB));
@@ -110,6 +129,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
         for (int ki = 0; ki < KI; ++ki, ++it) {
           const int s = it % NS, use = it / NS;
           mbar_wait(&conv_full[s], (uint32_t)(use & 1));
+          EXPO_TRACE(it, 3);
           tc::fence_after_sync();
           const uint32_t sa_hi = smem_u32(base + (size_t)s * C::kStageBytes), sa_lo = sa_hi + kTileA,
                          sb_hi = sa_lo + kTileA, sb_lo = sb_hi + C::kTileB;
@@ -125,6 +145,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
             tc::mma_tf32(acc, dal, dbh, idesc, 1u);
           }
           tc::mma_commit(&empty[s]);
+          EXPO_TRACE(it, 4);
         }
         tc::mma_commit(&acc_full[b]);                          // this tile's accumulator is complete
       }
@@ -142,6 +163,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
         const int s = it % NS, use = it / NS;
         unsigned char* a_raw = base + (size_t)s * C::kStageBytes;
         mbar_wait(&raw_full[s], (uint32_t)(use & 1));
+        if (tc_ == 0) EXPO_TRACE(it, 1);
 #pragma unroll
         for (int q = 0; q < C::kVecPerThread; ++q) {
           const int i = tc_ + kConverters * q;
@@ -157,6 +179,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
         }
         fence_proxy_async();
         mbar_arrive(&conv_full[s]);
+        if (tc_ == 0) EXPO_TRACE(it, 2);
       }
     }
   } else {
@@ -169,7 +192,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
       decode(t, m0, n0, z);
       const int KI = p.k_iters(z);
       const int b = j & 1, useb = j >> 1;
+      if (tid == 192) EXPO_TRACE_EPI(j, 0);
       mbar_wait(&acc_full[b], (uint32_t)(useb & 1));
+      if (tid == 192) EXPO_TRACE_EPI(j, 1);
       tc::fence_after_sync();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -183,6 +208,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) tma_gemm_persistent_kernel
       }
       tc::fence_before_sync();
       mbar_arrive(&acc_empty[b]);                              // buffer b may be overwritten
+      if (tid == 192) EXPO_TRACE_EPI(j, 2);
     }
   }
   tc::fence_before_sync();

@@ -213,16 +213,19 @@ __global__ void __launch_bounds__(kGlueThreads) colsum_multi_kernel(const Colsum
   const int col = cb * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
   const int r0 = chunk * kColsumChunk, r1 = min(rows, r0 + kColsumChunk);
   const float* a = T.src[t];
-  float s0 = 0.f, s1 = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (col < cols) {
     int r = r0 + ry;
-    for (; r + 8 < r1; r += 16) {
-      s0 += a[(size_t)r * cols + col];
-      s1 += a[(size_t)(r + 8) * cols + col];
+    for (; r + 56 < r1; r += 64) {                          // 8 loads in flight per thread
+      const float* q = a + (size_t)r * cols + col;
+      const float t0 = q[0], t1 = q[(size_t)8 * cols], t2 = q[(size_t)16 * cols], t3 = q[(size_t)24 * cols];
+      const float t4 = q[(size_t)32 * cols], t5 = q[(size_t)40 * cols], t6 = q[(size_t)48 * cols], t7 = q[(size_t)56 * cols];
+      s0 += t0; s1 += t1; s2 += t2; s3 += t3;
+      s0 += t4; s1 += t5; s2 += t6; s3 += t7;
     }
     for (; r < r1; r += 8) s0 += a[(size_t)r * cols + col];
   }
-  red[ry][threadIdx.x & 31] = s0 + s1;
+  red[ry][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   float* part = T.partials + (size_t)T.part0[t];         // task t's partial rows start at element offset part0[t]
   if (ry == 0 && col < cols) {
@@ -288,27 +291,26 @@ __device__ __forceinline__ float sat_w(const float* p, float* w) {
   return r / den;
 }
 
+// grid (kGinCluster, B), one cluster per image: CTA r sums and then writes the r-th slice of the pixels
+constexpr unsigned kGinCluster = 8;
 __global__ void __launch_bounds__(kGlueThreads) stats_bwd_gin_kernel(const float* __restrict__ img, const float* __restrict__ stats,
                                                                      const float* __restrict__ g_in, int cin,
                                                                      float* __restrict__ g_out, int P) {
   EXP_PDL_ENTRY();
-  __shared__ double sh[kGlueThreads / 32];
-  __shared__ float gst[3];
-  const int b = blockIdx.x;
+  __shared__ double sh[kGlueThreads / 32 * 3], xch[3];
+  const int b = blockIdx.y;
+  const unsigned r = cluster_rank_x(), n = cluster_size_x();
+  const int lo = (int)((long long)P * r / n), hi = (int)((long long)P * (r + 1) / n);
   const float* gi = g_in + (size_t)b * P * cin;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int p = threadIdx.x; p < P; p += kGlueThreads) {
+  double a[3] = {0.0, 0.0, 0.0};
+  for (int p = lo + threadIdx.x; p < hi; p += kGlueThreads) {
     const float* q = gi + (size_t)p * cin + (cin - 3);
-    a0 += (double)q[0]; a1 += (double)q[1]; a2 += (double)q[2];
+    a[0] += (double)q[0]; a[1] += (double)q[1]; a[2] += (double)q[2];
   }
-  a0 = block_sum_d<kGlueThreads>(a0, sh);
-  a1 = block_sum_d<kGlueThreads>(a1, sh);
-  a2 = block_sum_d<kGlueThreads>(a2, sh);
-  if (threadIdx.x == 0) { gst[0] = (float)a0; gst[1] = (float)a1; gst[2] = (float)a2; }
-  __syncthreads();
-  const float mean = stats[b * 3], gm = gst[0], gv = gst[1], gs = gst[2];
+  cluster_sum<kGlueThreads, 3>(a, sh, xch);
+  const float mean = stats[b * 3], gm = (float)a[0], gv = (float)a[1], gs = (float)a[2];
   const float invP = 1.0f / (float)P;
-  for (int p = threadIdx.x; p < P; p += kGlueThreads) {
+  for (int p = lo + threadIdx.x; p < hi; p += kGlueThreads) {
     const size_t o = ((size_t)b * P + p) * 3;
     float w[3];
     sat_w(img + o, w);
@@ -437,8 +439,8 @@ int exp_colsum_multi(const float* const* src_host, float* const* dst_host, const
 
 int exp_stats_bwd_gin(const float* img, const float* stats, const float* g_in, int cin, float* g_out, int B, int H, int W,
                       void* stream) {
-  EXP_CHECK_ARG(img && stats && g_in && g_out && B > 0 && H > 0 && W > 0 && cin >= 6, "bad args (cin >= 6: 3 image + 3 statistic channels)");
-  launch_pdl(stats_bwd_gin_kernel, dim3(B), dim3(kGlueThreads), 0, (cudaStream_t)stream, img, stats, g_in, cin, g_out, H * W);
+  EXP_CHECK_ARG(img && stats && g_in && g_out && B > 0 && B <= 65535 && H > 0 && W > 0 && cin >= 6, "bad args (cin >= 6: 3 image + 3 statistic channels)");
+  launch_pdl_cluster(stats_bwd_gin_kernel, dim3(kGinCluster, B), dim3(kGlueThreads), 0, kGinCluster, (cudaStream_t)stream, img, stats, g_in, cin, g_out, H * W);
   EXP_CHECK_LAUNCH("exp_stats_bwd_gin");
   return EXP_OK;
 }

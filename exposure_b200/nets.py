@@ -275,6 +275,12 @@ class CriticNet:
     """dL/dimages for the samples in sl: layer-1 dgrad, image channels + J_stats^T of the
     three statistic channels (tf.gradients through critics.py:48-87)."""
     s = sl if sl is not None else slice(None)
+    if K.first_layer_split(self.conv.cin):
+      # the image channels' gradient + the per-image pixel sums of the tiled channels' (exp_conv_first_dgrad); the three
+      # statistic channels go back through J_stats^T (exp_stats_bwd), the state channels have no producer
+      d1 = c.deltas[0][s]
+      g_img, g_vec = K.conv_first_dgrad(d1, self.conv.W(0), self.conv.cin - 3, (64, 64))
+      return K.stats_bwd(c.img[s], c.stats[s], g_vec[:, self.conv.cin - 6:].contiguous(), g_direct=g_img)
     g_in = self.conv.input_grad(c, sl)                         # [n,64,64,cin]
     # image channels pass through, the three tiled statistic channels are summed per image and pulled back through
     # J_stats^T -- one launch (exp_stats_bwd_gin)

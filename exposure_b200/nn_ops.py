@@ -167,12 +167,27 @@ def _conv1_stage(x, vec, shift, own=False):
   return xp
 
 
+def _first_path(Cx, Cv, Cout):
+  """The split first layer (csrc/conv_first.cu): image channels by an exact-fp32 direct kernel, the per-image constant
+  channels through a border-class table.  EXPOSURE_FIRST_LAYER=staged keeps the round-1 TMA staging path (A/B switch)."""
+  return _FIRST_SPLIT and bool(_cabi.lib().exp_conv_first_supported(Cx, Cv, Cout))
+
+
+_FIRST_SPLIT = os.environ.get("EXPOSURE_FIRST_LAYER", "split") != "staged"
+
+
+def first_layer_split(cin, Cout=32):
+  return _first_path(3, cin - 3, Cout)
+
+
 def stage_first_layer(x, vec, shift, Cout):
   """The first-layer staging copy of concat(x, tile(vec)) - shift as a tensor of its own ([B, IH+2, IW+2, 16] for
   Cin <= 16, [B, IH, IW, 32] for 16 < Cin <= 32), or None when the layer needs none.  Hand it to conv_fwd /
   conv_wgrad as `staged=` (batch slices allowed) so that forward and weight gradient share ONE staging launch."""
   B, IH, IW, Cx = x.shape
   Cv = 0 if vec is None else vec.shape[1]
+  if _first_path(Cx, Cv, Cout):
+    return None
   if _conv1_path(Cx, Cv, Cout):
     return _conv1_stage(x, vec, shift, own=True).view(B, IH + 2, IW + 2, 16)
   if _enrich32_path(Cx, Cv, Cout):
@@ -233,6 +248,13 @@ def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None,
   if post_mul is not None:
     y2 = torch.empty_like(y) if out2 is None else out2
   mode = 0 if mask_ref is None else 1
+  if staged is None and _first_path(Cx, Cv, Cout):
+    with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+      _cabi.check(_cabi.lib().exp_conv_first_fwd(x.data_ptr(), _p(vec), Cv, float(shift), W.data_ptr(), _p(bias), _p(mask_ref),
+                                                 _p(post_mul), y.data_ptr(), _p(y2), B, IH, IW, mode, _stream()),
+                  "exp_conv_first_fwd")
+    _n()
+    return y if post_mul is None else (y, y2)
   if _conv1_path(Cx, Cv, Cout):
     l = _cabi.lib()
     with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
@@ -273,6 +295,22 @@ def conv_dgrad(dy, W, in_shape, a_in=None, out=None):
   return dx
 
 
+def conv_first_dgrad(dy, W, Cv, in_hw, need_image=True, need_vec=True):
+  """Backward of the first layer w.r.t. its input, as its producers need it: (dx_img [B,IH,IW,3], gvec [B,Cv]) -- the
+  gradient of the image channels and, for every per-image constant channel, its gradient summed over the pixels."""
+  _chk(dy, "dy", 4); _chk(W, "W", 4)
+  B, OH, OW, Cout = dy.shape
+  IH, IW = in_hw
+  assert (OH, OW) == (IH // 2, IW // 2) and W.shape[2] == 3 + Cv and W.shape[3] == Cout
+  dx = torch.empty(B, IH, IW, 3, device=dy.device, dtype=torch.float32) if need_image else None
+  gv = torch.empty(B, Cv, device=dy.device, dtype=torch.float32) if need_vec and Cv else None
+  with _ops._Timed("conv_dgrad", "gemm", 2 * B * OH * OW * Cout * 16 * 3):
+    _cabi.check(_cabi.lib().exp_conv_first_dgrad(dy.data_ptr(), W.data_ptr(), Cv, _p(dx), _p(gv), B, IH, IW, _stream()),
+                "exp_conv_first_dgrad")
+  _n((1 if need_image else 0) + (1 if gv is not None else 0))
+  return dx, gv
+
+
 def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False, staged=None):
   """gW[4,4,Cin,Cout] (+= when accumulate) for the conv whose input was concat(x, tile(vec)) - shift."""
   _chk(x, "x", 4); _chk(dy, "dy", 4)
@@ -282,6 +320,13 @@ def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False, staged=No
   gW = torch.empty(4, 4, Cx + Cv, Cout, device=x.device, dtype=torch.float32) if out is None else out
   assert not accumulate or out is not None
   l = _cabi.lib()
+  if staged is None and _first_path(Cx, Cv, Cout):
+    ws = _workspace(x.device, l.exp_conv_first_wgrad_workspace_bytes(B, IH, IW))
+    with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+      _cabi.check(l.exp_conv_first_wgrad(x.data_ptr(), _p(vec), Cv, float(shift), dy.data_ptr(), gW.data_ptr(), B, IH, IW,
+                                         int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "exp_conv_first_wgrad")
+    _n(2)
+    return gW
   if _conv1_path(Cx, Cv, Cout):
     ws = _workspace(x.device, l.exp_conv1_wgrad_workspace_bytes(B, IH, IW, Cout))
     with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):

@@ -280,6 +280,28 @@ size_t exp_conv1_wgrad_workspace_bytes(int B, int IH, int IW, int Cout);
 int exp_conv1_wgrad(const float* xp, const float* dy, float* gW, int Cin, int B, int IH, int IW, int Cout,
                     int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* First convolution layer, constant channels split off (the product path for Cx = 3, Cout = 32; csrc/conv_first.cu).
+ * Only the image channels vary over the pixels; the Cv tiled channels (util.py:31-36 enrich_image_input: agent states,
+ * critics.py:51-87 statistics) are constants of an image, so their share of an output is one of <= 16 per-image values
+ * per output channel (which taps fall inside the image depends only on first / last row and column).  Exact-fp32
+ * CUDA-core kernels over the image itself, K = 48 instead of 16 (3 + Cv); same epilogue modes as exp_conv_fwd
+ * (agent.py:21-33 / critics.py:13-19 forward; mode 1 = forward-mode tangent for the gradient penalty, net.py:181-194).
+ *   exp_conv_first_fwd    y (and y2 = y * post_mul) [B, IH/2, IW/2, 32] from x [B,IH,IW,3], vec [B,Cv], W [4,4,3+Cv,32]
+ *   exp_conv_first_wgrad  gW [4,4,3+Cv,32] (=|+=), deterministic two-pass reduction through `workspace`
+ *   exp_conv_first_dgrad  dx_img [B,IH,IW,3] (nullable) = gradient w.r.t. the image channels, and gvec [B,Cv] (nullable)
+ *                         = the gradient of each constant channel SUMMED over the pixels -- what tf.gradients hands to
+ *                         the per-image producers of those channels (the statistics: exp_stats_bwd)
+ * IH, IW even (powers of two for dx_img); y / y2 / mask_ref / post_mul / dy / W / workspace 16-byte aligned. */
+int exp_conv_first_supported(int Cx, int Cv, int Cout);
+int exp_conv_first_fwd(const float* x, const float* vec, int Cv, float shift, const float* W, const float* bias,
+                       const float* mask_ref, const float* post_mul, float* y, float* y2, int B, int IH, int IW,
+                       int mode, void* stream);
+size_t exp_conv_first_wgrad_workspace_bytes(int B, int IH, int IW);
+int exp_conv_first_wgrad(const float* x, const float* vec, int Cv, float shift, const float* dy, float* gW, int B,
+                         int IH, int IW, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+int exp_conv_first_dgrad(const float* dy, const float* W, int Cv, float* dx_img, float* gvec, int B, int IH, int IW,
+                         void* stream);
+
 /* First layers with 16 < Cin <= 32 (value network: 17 channels): materialise the enriched input
  * out[B][IH][IW][32] = concat(x, tile(vec)) - shift, zero above Cin (exp_conv_enrich32) and the
  * weights padded to Wp[4][4][32][Cout] (exp_conv_pad_weights32); exp_conv_fwd / exp_conv_wgrad then

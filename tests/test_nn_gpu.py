@@ -85,6 +85,50 @@ def test_conv_forward_backward(nn, case):
   _close(t_out, t_ref, tol=1e-4)
 
 
+@pytest.mark.parametrize("case", [(3, 64, 11), (2, 64, 3), (2, 64, 14), (1, 128, 3), (2, 16, 3), (2, 4, 3), (1, 2, 5), (2, 64, 0)])
+def test_first_layer_split(nn, case):
+  """exp_conv_first_*: image channels by a direct kernel, per-image constant channels through the border-class table
+  (forward, tangent mode, weight gradient, and the input gradient as its producers need it)."""
+  B, IH, Cv = case
+  Cx, Cout = 3, 32
+  x = _rand(B, IH, IH, Cx, seed=11).abs() * 0.3
+  vec = _rand(B, Cv, seed=12) if Cv else None
+  W = _rand(4, 4, Cx + Cv, Cout, seed=13, scale=0.1)
+  b = _rand(Cout, seed=14, scale=0.1)
+  xin = (N.enrich(x, vec) if Cv else x).clone().requires_grad_(True)
+  Wr = W.clone().requires_grad_(True)
+  pre = N.conv4x4s2(xin - 0.5, Wr, b)
+  y = N.lrelu(pre)
+  f32 = lambda t: None if t is None else t.detach().float().cuda().contiguous()
+  assert nn.first_layer_split(Cx + Cv)
+  yd = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=0.5)
+  _close(yd, y.detach())
+  pm = (torch.rand(y.shape, generator=torch.Generator().manual_seed(9)) < 0.5).float() * 2
+  y1, y2 = nn.conv_fwd(f32(x), f32(W), f32(b), vec=f32(vec), shift=0.5, post_mul=pm.cuda())
+  assert torch.equal(y1, yd) and torch.equal(y2, yd * pm.cuda())
+  gy = _rand(*y.shape, seed=15)
+  gin, gW = torch.autograd.grad(y, [xin, Wr], grad_outputs=gy)
+  delta = (gy * torch.where(pre > 0, 1.0, torch.where(pre < 0, 0.2, 0.6))).detach()
+  gWd = nn.conv_wgrad(f32(x), f32(delta), vec=f32(vec), shift=0.5)
+  _close(gWd, gW)
+  acc = torch.full_like(gWd, 0.25)
+  nn.conv_wgrad(f32(x), f32(delta), vec=f32(vec), shift=0.5, out=acc, accumulate=True)
+  _close(acc - 0.25, gW, tol=2e-5)
+  dx, gv = nn.conv_first_dgrad(f32(delta), f32(W), Cv, (IH, IH))
+  _close(dx, gin[..., :Cx])
+  if Cv:
+    _close(gv, gin[..., Cx:].sum(dim=(1, 2)))
+  # bit-for-bit repeatable (fixed summation order)
+  assert torch.equal(gWd, nn.conv_wgrad(f32(x), f32(delta), vec=f32(vec), shift=0.5))
+  # tangent mode
+  t_in = _rand(B, IH, IH, Cx, seed=17)
+  tvec = _rand(B, Cv, seed=18) if Cv else None
+  ym = yd.cpu().double()
+  t_ref = N.conv4x4s2(N.enrich(t_in, tvec) if Cv else t_in, W) * torch.where(ym > 0, 1.0, torch.where(ym < 0, 0.2, 0.6))
+  t_out = nn.conv_fwd(f32(t_in), f32(W), None, vec=f32(tvec), shift=0.0, mask_ref=yd)
+  _close(t_out, t_ref, tol=1e-5)
+
+
 FC_CASES = [(64, 4096, 128), (192, 4096, 128), (64, 128, 8), (64, 128, 30), (64, 128, 1), (7, 100, 9)]
 
 

@@ -141,7 +141,7 @@ def test_cuda_graph_replay_matches_eager(built_lib):
     assert torch.allclose(ca["emd"], cb["emd"], rtol=1e-6, atol=1e-7)
   for sa, sb in ((a.gen, b.gen), (a.val, b.val), (a.cri, b.cri)):
     assert torch.allclose(sa.flat, sb.flat, rtol=1e-6, atol=1e-8), float((sa.flat - sb.flat).abs().max())
-  assert b.graph_launches["generator"] > 50 and b.graph_launches["critic"] > 50
+  assert b.graph_launches["generator"] > 50 and b.graph_launches["critic"] > 30
 
 
 def test_c_average_moving_average_follows_tf_zero_debias(built_lib):

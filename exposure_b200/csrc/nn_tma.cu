@@ -87,6 +87,8 @@ struct TmaConvFprop {
   int M, Cin, Cout, OW, lgOW, lgOHW, mode, splits;
   int first;   // 1: first layer on the zero-bordered 16-channel staging copy (see exp_conv1_pad_input)
   static constexpr bool kAMn = false, kBMn = true;
+  static constexpr bool kPlainRows = false;
+  __device__ float* row_ptr(int, int, int) const { return nullptr; }
   __host__ __device__ int k_iters(int) const { return 16 * Cin / tma::kBK; }
   template <int BN>
   __device__ void load(int ki, int, int m0, int n0, unsigned char* a_dst, unsigned char* b_dst, uint64_t* bar) const {
@@ -164,6 +166,8 @@ struct TmaConvDgrad {
   const float* a_in; float* dx;
   int M, IH, IW, Cin, Cout, lgW2, lgHW2, splits;
   static constexpr bool kAMn = false, kBMn = false;
+  static constexpr bool kPlainRows = false;
+  __device__ float* row_ptr(int, int, int) const { return nullptr; }
   __host__ __device__ int k_iters(int) const { return 4 * Cout / tma::kBK; }
   template <int BN>
   __device__ void load(int ki, int z, int m0, int n0, unsigned char* a_dst, unsigned char* b_dst, uint64_t* bar) const {
@@ -233,6 +237,10 @@ struct TmaConvWgrad {
   int Cin, Cout, OW, lgOW, lgOHW, steps_per_split, total_steps, splits;   // splits: cluster split-K, unused (= 1): z already splits K
   int first;   // 1: first layer on the zero-bordered 16-channel staging copy
   static constexpr bool kAMn = true, kBMn = true;
+  static constexpr bool kPlainRows = true;                     // partial tiles are stored as they are
+  __device__ float* row_ptr(int z, int m, int n0) const {
+    return (m < 16 * Cin && n0 < Cout) ? part + ((size_t)z * 16 * Cin + m) * Cout + n0 : nullptr;
+  }
   __host__ __device__ int k_iters(int z) const {
     const int left = total_steps - z * steps_per_split;
     return left < steps_per_split ? (left > 0 ? left : 0) : steps_per_split;
@@ -514,6 +522,10 @@ int exp_conv1_wgrad(const float* xp, const float* dy, float* gW, int Cin, int B,
 
 #ifdef EXPO_TMA_TRACE
 // development build only (tools/tma_trace.py): copies the stamps of the last persistent launch to the host
+int exp_debug_tma_trace_cta(long long* cta) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(cta, tma::g_tma_trace_cta, sizeof(tma::g_tma_trace_cta)) == cudaSuccess ? 0 : -1;
+}
 int exp_debug_tma_trace(long long* steps, long long* tiles) {
   cudaDeviceSynchronize();
   if (cudaMemcpyFromSymbol(steps, tma::g_tma_trace, sizeof(tma::g_tma_trace)) != cudaSuccess) return -1;

@@ -122,6 +122,31 @@ __device__ __forceinline__ float4 dsmem_sum4(uint32_t a) {
   return v;
 }
 
+// Development aid (-DEXPO_TMA_TRACE, tools/tma_trace.py): SM-clock stamps of the ring hand-overs of the first CTAs.
+#ifdef EXPO_TMA_TRACE
+constexpr int kTraceCtas = 4, kTraceSteps = 96, kTraceTiles = 16;
+__device__ long long g_tma_trace[kTraceCtas][kTraceSteps][5];
+__device__ long long g_tma_trace_epi[kTraceCtas][kTraceTiles][3];
+__device__ long long g_tma_trace_cta[kTraceCtas][8];      // one-tile kernel: entry, set-up done, accumulator ready, tile stored, exit
+#define EXPO_TRACE(it, slot)                                                                          \
+  do {                                                                                                \
+    if (blockIdx.x < kTraceCtas && (it) < kTraceSteps) g_tma_trace[blockIdx.x][(it)][(slot)] = clock64(); \
+  } while (0)
+#define EXPO_TRACE_EPI(j, slot)                                                                          \
+  do {                                                                                                   \
+    if (blockIdx.x < kTraceCtas && (j) < kTraceTiles) g_tma_trace_epi[blockIdx.x][(j)][(slot)] = clock64(); \
+  } while (0)
+#define EXPO_TRACE_CTA(slot)                                                                      \
+  do {                                                                                            \
+    const int cta__ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);             \
+    if (cta__ < kTraceCtas) g_tma_trace_cta[cta__][(slot)] = clock64();                           \
+  } while (0)
+#else
+#define EXPO_TRACE_CTA(slot) do {} while (0)
+#define EXPO_TRACE(it, slot) do {} while (0)
+#define EXPO_TRACE_EPI(j, slot) do {} while (0)
+#endif
+
 // Problem functor P (passed as a __grid_constant__ parameter: the CUtensorMaps inside it must stay
 // in parameter space):
 //   static constexpr bool kAMn, kBMn            operand majorness
@@ -150,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
 
   pdl_trigger();                                              // dependents may start their prologue now
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) EXPO_TRACE_CTA(0);
   const int S = p.splits;
   const int z = blockIdx.z / S;                               // problem slice
   const int rank = S > 1 ? (int)cluster_ctarank() : 0;       // == blockIdx.z % S
@@ -173,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
   __syncthreads();
   tc::fence_after_sync();
   pdl_wait();                                                 // prologue done; the predecessor's writes are visible from here
+  if (tid == 0) EXPO_TRACE_CTA(1);
   const uint32_t tmem_acc = tmem_base_s;
   const int KI_all = p.k_iters(z);
   const int per = (KI_all + S - 1) / S;
@@ -187,6 +214,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
       for (int ki = 0; ki < KI; ++ki) {
         const int s = ki % NS, use = ki / NS;
         if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+        if (blockIdx.y == 0 && blockIdx.z == 0) EXPO_TRACE(ki, 0);
         unsigned char* a_raw = base + (size_t)s * C::kStageBytes;
         unsigned char* b_raw = a_raw + 2 * kTileA;
         mbar_expect_tx(&raw_full[s], (uint32_t)(kTileA + C::kTileB));
@@ -201,6 +229,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
       for (int ki = 0; ki < KI; ++ki) {
         const int s = ki % NS, use = ki / NS;
         mbar_wait(&conv_full[s], (uint32_t)(use & 1));
+        if (blockIdx.y == 0 && blockIdx.z == 0) EXPO_TRACE(ki, 3);
         tc::fence_after_sync();
         const uint32_t sa_hi = smem_u32(base + (size_t)s * C::kStageBytes), sa_lo = sa_hi + kTileA,
                        sb_hi = sa_lo + kTileA, sb_lo = sb_hi + C::kTileB;
@@ -216,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
           tc::mma_tf32(tmem_acc, dal, dbh, idesc, 1u);
         }
         tc::mma_commit(&empty[s]);
+        if (blockIdx.y == 0 && blockIdx.z == 0) EXPO_TRACE(ki, 4);
       }
       tc::mma_commit(&accum);
     }
@@ -227,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
       const int s = ki % NS, use = ki / NS;
       unsigned char* a_raw = base + (size_t)s * C::kStageBytes;
       mbar_wait(&raw_full[s], (uint32_t)(use & 1));
+      if (t == 0 && blockIdx.y == 0 && blockIdx.z == 0) EXPO_TRACE(ki, 1);
 #pragma unroll
       for (int j = 0; j < C::kVecPerThread; ++j) {
         // flat 16-byte index over [A raw | A lo | B raw | B lo]: raw at off, lo at off + tile size
@@ -243,13 +274,20 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
       }
       fence_proxy_async();
       mbar_arrive(&conv_full[s]);
+      if (t == 0 && blockIdx.y == 0 && blockIdx.z == 0) EXPO_TRACE(ki, 2);
     }
     // ================================ epilogue ================================
+    // Every tile is first parked in shared memory (the stage ring is idle by now), row per thread as tcgen05.ld
+    // delivers it; the store pass below then walks it with consecutive threads on consecutive float4 of a row, so
+    // the functor's global loads (lrelu' mask, dropout multiplier) and stores are whole 128-byte lines, four
+    // independent float4 in flight per thread.  (Storing straight from the tcgen05.ld registers -- a thread per row,
+    // 16 bytes per lane at a row stride -- cost 4-8 k clocks per tile, a third of the kernel: profiles/r2t_tma_trace.md.)
     if (KI > 0) mbar_wait(&accum, 0u);
+    if (tid == 64) EXPO_TRACE_CTA(2);
     tc::fence_after_sync();
     const int q = warp & 3;
     const int row = q * 32 + lane;
-#pragma unroll 1
+#pragma unroll 2
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       if (KI > 0) tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -257,32 +295,61 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
-      if (S == 1) p.store16(z, m0 + row, n0 + c0, v);
-      else {
-        float4* dst = reinterpret_cast<float4*>(park + (size_t)row * kParkLd + c0);
+      float4* dst = reinterpret_cast<float4*>(park + (size_t)row * kParkLd + c0);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      for (int g = 0; g < 4; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    if constexpr (P::kPlainRows) {
+      // a functor that stores the tile as it is: every thread hands ITS parked row to the bulk-copy engine
+      // (one cp.async.bulk of BN * 4 bytes), no second pass and no barrier
+      if (S == 1) {
+        float* g = p.row_ptr(z, m0 + row, n0);
+        fence_proxy_async();
+        if (g) bulk_s2g(g, park + (size_t)row * kParkLd, BN * 4);
+        bulk_commit();
+        bulk_wait_read<0>();
       }
     }
+    if (S == 1) asm volatile("bar.sync 1, %0;" ::"n"(kConverters) : "memory");   // the four epilogue warps only
   }
-  if (S > 1) {
-    cluster_sync_all();                               // every CTA of the cluster has parked its partial tile
-    if (warp >= 2) {
-      // CTA `rank` owns columns [rank*W, (rank+1)*W): consecutive threads take consecutive float4 of a
-      // row chunk, so both the DSMEM reads and the global stores are contiguous runs of W*4 bytes
-      const int W = BN / S, lgW4 = 31 - __clz(W >> 2);
-      for (int idx = tid - 64; idx < (kBM << lgW4); idx += kConverters) {
-        const int row = idx >> lgW4, col = rank * W + ((idx & ((1 << lgW4) - 1)) << 2);
-        const uint32_t a = smem_u32(park + (size_t)row * kParkLd + col);
-        const float4 v = S == 2 ? dsmem_sum4<2>(a) : (S == 4 ? dsmem_sum4<4>(a) : dsmem_sum4<8>(a));   // fixed order: reproducible
-        p.store4(z, m0 + row, n0 + col, v);
+  if (tid == 64) EXPO_TRACE_CTA(3);
+  if (S > 1) cluster_sync_all();                      // every CTA of the cluster has parked its partial tile
+  if (warp >= 2 && !(P::kPlainRows && S == 1)) {
+    // CTA `rank` owns columns [rank*W, (rank+1)*W) (W = BN when the tile is not split): consecutive threads take
+    // consecutive float4 of a row chunk, so the (D)SMEM reads and the global accesses are contiguous runs of W*4 bytes
+    const int W = BN / S, lgW4 = 31 - __clz(W >> 2);
+    const int total = kBM << lgW4;
+#pragma unroll 1
+    for (int idx0 = tid - 64; idx0 < total; idx0 += 4 * kConverters) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * kConverters;
+        if (idx < total) {
+          const int r = idx >> lgW4, col = rank * W + ((idx & ((1 << lgW4) - 1)) << 2);
+          const float* src = park + (size_t)r * kParkLd + col;
+          if (S == 1) v[u] = *reinterpret_cast<const float4*>(src);
+          else {
+            const uint32_t a = smem_u32(src);
+            v[u] = S == 2 ? dsmem_sum4<2>(a) : (S == 4 ? dsmem_sum4<4>(a) : dsmem_sum4<8>(a));   // fixed order: reproducible
+          }
+        }
       }
+      if (tid == 64 && idx0 == 0) EXPO_TRACE_CTA(6);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * kConverters;
+        if (idx < total) p.store4(z, m0 + (idx >> lgW4), n0 + rank * W + ((idx & ((1 << lgW4) - 1)) << 2), v[u]);
+      }
+      if (tid == 64 && idx0 == 0) EXPO_TRACE_CTA(7);
     }
-    cluster_sync_all();                               // nobody leaves while its shared memory is still being read
   }
+  if (S > 1) cluster_sync_all();                      // nobody leaves while its shared memory is still being read
+  if (tid == 64) EXPO_TRACE_CTA(4);
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_acc, BN);
+  if (tid == 0) EXPO_TRACE_CTA(5);
 }
 
 template <class P, int BN, int NS_>

@@ -21,23 +21,6 @@ namespace tma {
 
 constexpr int kPersistThreads = 320;
 
-// Development aid (-DEXPO_TMA_TRACE, tools/tma_trace.py): SM-clock stamps of the ring hand-overs of the first CTAs.
-#ifdef EXPO_TMA_TRACE
-constexpr int kTraceCtas = 4, kTraceSteps = 96, kTraceTiles = 16;
-__device__ long long g_tma_trace[kTraceCtas][kTraceSteps][5];
-__device__ long long g_tma_trace_epi[kTraceCtas][kTraceTiles][3];
-#define EXPO_TRACE(it, slot)                                                                          \
-  do {                                                                                                \
-    if (blockIdx.x < kTraceCtas && (it) < kTraceSteps) g_tma_trace[blockIdx.x][(it)][(slot)] = clock64(); \
-  } while (0)
-#define EXPO_TRACE_EPI(j, slot)                                                                          \
-  do {                                                                                                   \
-    if (blockIdx.x < kTraceCtas && (j) < kTraceTiles) g_tma_trace_epi[blockIdx.x][(j)][(slot)] = clock64(); \
-  } while (0)
-#else
-#define EXPO_TRACE(it, slot) do {} while (0)
-#define EXPO_TRACE_EPI(j, slot) do {} while (0)
-#endif
 
 template <int BN>
 struct PersistCfg {

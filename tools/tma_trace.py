@@ -25,29 +25,41 @@ CTAS, STEPS, TILES = 4, 96, 16
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1)
 B = 64
-which = sys.argv[1] if len(sys.argv) > 1 else "fprop1"
-if which == "fprop1":
-  x = torch.randn(B, 64, 64, 14, device=dev, generator=g)
-  W = torch.randn(4, 4, 14, 32, device=dev, generator=g) * 0.05
-  b = torch.zeros(32, device=dev)
+which = sys.argv[1] if len(sys.argv) > 1 else "dgrad2"
+LAYERS = {"2": (32, 32, 64), "3": (16, 64, 128), "4": (8, 128, 256)}        # IH, Cin, Cout
+kind, layer = which[:-1], which[-1]
+IH, Cin, Cout = LAYERS[layer]
+x = torch.randn(B, IH, IH, Cin, device=dev, generator=g)
+W = torch.randn(4, 4, Cin, Cout, device=dev, generator=g) * 0.05
+b = torch.zeros(Cout, device=dev)
+dy = torch.randn(B, IH // 2, IH // 2, Cout, device=dev, generator=g)
+if kind == "fprop":
   run = lambda: K.conv_fwd(x, W, b)
-else:                                                  # layer-2 dgrad
-  x = torch.randn(B, 32, 32, 32, device=dev, generator=g)
-  W = torch.randn(4, 4, 32, 64, device=dev, generator=g) * 0.05
-  dy = torch.randn(B, 16, 16, 64, device=dev, generator=g)
+elif kind == "dgrad":
   run = lambda: K.conv_dgrad(dy, W, tuple(x.shape), a_in=x)
+else:
+  run = lambda: K.conv_wgrad(x, dy)
 for _ in range(3):
   run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
-print("launch: %.1f us (eager, includes the staging kernels of layer 1)" % (e0.elapsed_time(e1) * 1e3))
+print("%s: launch %.1f us (eager, CUDA events)" % (which, e0.elapsed_time(e1) * 1e3))
 steps = np.zeros((CTAS, STEPS, 5), dtype=np.int64)
 tiles = np.zeros((CTAS, TILES, 3), dtype=np.int64)
 fn = _cabi.lib().exp_debug_tma_trace
 fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 fn.restype = ctypes.c_int
 assert fn(steps.ctypes.data, tiles.ctypes.data) == 0
+cta = np.zeros((CTAS, 8), dtype=np.int64)
+fn2 = _cabi.lib().exp_debug_tma_trace_cta
+fn2.argtypes = [ctypes.c_void_p]
+fn2.restype = ctypes.c_int
+assert fn2(cta.ctypes.data) == 0
+print("one-tile kernel, per CTA (SM clocks since entry): set-up done, accumulator ready, tile stored / parked, after cluster exchange, exit")
+for c in range(CTAS):
+  print("   CTA %d: %s   first TMA issue at %d" % (c, " ".join("%7d" % (cta[c, i] - cta[c, 0]) for i in range(1, 6)), steps[c, 0, 0] - cta[c, 0]))
+  print("          first group of 4 float4 of the store pass: read at %d, stored at %d" % (cta[c, 6] - cta[c, 0], cta[c, 7] - cta[c, 0]))
 for c in range(2):
   t0 = steps[c, 0, 0]
   print("CTA %d   it:     P     C0     C1     M0     M1   | dP  (SM clocks since the CTA's first TMA issue)" % c)

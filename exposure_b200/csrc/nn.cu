@@ -523,9 +523,110 @@ static cudaError_t launch_dgrad_small(const float* dy, const float* W, const flo
                     a_in, dx, IH, IW, Cin, CinW, Cout, t.tw, t.th, tiles_x, tiles_y);
 }
 
+// Cin = 3 (the image gradient of the first layer, exp_conv_first_dgrad) on 8 x 32 tiles: warp = row of the tile, lane =
+// (parity class, l8), a thread owns positions l8 + 8 p (p < 4) of its row for its class: 4 x 3 accumulators, per tap and
+// 4 output channels 4 delta loads + 3 weight loads for 48 FMAs (the generic kernel above: 1 + 3 loads for 12 FMAs, and
+// at Cin = 3 it is bound by exactly those shared-memory loads: 27 us at batch 64).
+constexpr int kDg3Threads = 256, kDg3TH = 8, kDg3TW = 32;
+static size_t dg3_smem_bytes(int Cout) {
+  const size_t stage_in = (size_t)16 * 3 * Cout + (size_t)(kDg3TH + 2) * (kDg3TW + 2) * (Cout + 4);
+  const size_t stage_out = (size_t)4 * kDg3TH * kDg3TW * 3;
+  return (stage_in > stage_out ? stage_in : stage_out) * sizeof(float);
+}
+__global__ void __launch_bounds__(kDg3Threads) conv_dgrad_img3_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                                                      float* __restrict__ dx, int IH, int IW, int CinW, int Cout,
+                                                                      int tiles_x, int tiles_y) {
+  EXP_PDL_ENTRY();
+  extern __shared__ float4 dg3_smem4[];
+  constexpr int Cin = 3, tw = kDg3TW, th = kDg3TH;
+  float4* const w_s4 = dg3_smem4;                                   // [ky][kx][3][Cout / 4]
+  const int co4n = Cout >> 2, pitch4 = co4n + 1;
+  float4* const d_s4 = dg3_smem4 + 16 * Cin * co4n;                 // [(th + 2)][(tw + 2)][pitch4]
+  const int OH = IH >> 1, OW = IW >> 1;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x; tile /= tiles_x;
+  const int ty = tile % tiles_y;
+  const int b = tile / tiles_y;
+  const int a0 = ty * th, c0 = tx * tw;
+  {
+    const float4* src = reinterpret_cast<const float4*>(W);
+    const int per = Cin * co4n;
+    for (int i = threadIdx.x; i < 16 * per; i += kDg3Threads) {
+      const int tap = i / per, rem = i - tap * per;
+      w_s4[i] = __ldg(src + (size_t)tap * CinW * co4n + rem);
+    }
+    const int hw = tw + 2, n4 = (th + 2) * hw * co4n;
+    for (int i = threadIdx.x; i < n4; i += kDg3Threads) {
+      const int q = i % co4n, pix = i / co4n;
+      const int hc = pix % hw, hr = pix / hw;
+      const int oy = a0 + hr - 1, ox = c0 + hc - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((unsigned)oy < (unsigned)OH && (unsigned)ox < (unsigned)OW)
+        v = __ldg(reinterpret_cast<const float4*>(dy + ((size_t)(b * OH + oy) * OW + ox) * Cout) + q);
+      d_s4[pix * pitch4 + q] = v;
+    }
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 5, lane = threadIdx.x & 31, cls = lane >> 3, l8 = lane & 7;
+  const int py = cls >> 1, px = cls & 1;
+  float acc[4][3];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int dyy = j == 0 ? 0 : (py ? 1 : -1);
+    const int ky = py - 2 * dyy + 1;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      const int dxx = l == 0 ? 0 : (px ? 1 : -1);
+      const int kx = px - 2 * dxx + 1;
+      const float4* dp = d_s4 + ((r + 1 + dyy) * (tw + 2) + (l8 + 1 + dxx)) * pitch4;
+      const float4* wp = w_s4 + (size_t)(ky * 4 + kx) * Cin * co4n;
+#pragma unroll 2
+      for (int q = 0; q < co4n; ++q) {
+        const float4 w0 = wp[q], w1 = wp[co4n + q], w2 = wp[2 * co4n + q];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float4 d = dp[8 * p * pitch4 + q];
+          acc[p][0] = fmaf(d.x, w0.x, fmaf(d.y, w0.y, fmaf(d.z, w0.z, fmaf(d.w, w0.w, acc[p][0]))));
+          acc[p][1] = fmaf(d.x, w1.x, fmaf(d.y, w1.y, fmaf(d.z, w1.z, fmaf(d.w, w1.w, acc[p][1]))));
+          acc[p][2] = fmaf(d.x, w2.x, fmaf(d.y, w2.y, fmaf(d.z, w2.z, fmaf(d.w, w2.w, acc[p][2]))));
+        }
+      }
+    }
+  }
+  __syncthreads();                                   // deltas and weights are dead: the dx tile takes their place
+  float* const o_s = reinterpret_cast<float*>(dg3_smem4);
+  constexpr int rowlen = 2 * tw * Cin;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float* o = o_s + (2 * r + py) * rowlen + (2 * (l8 + 8 * p) + px) * Cin;
+    o[0] = acc[p][0]; o[1] = acc[p][1]; o[2] = acc[p][2];
+  }
+  __syncthreads();
+  constexpr int total = 2 * th * rowlen;
+  for (int i = threadIdx.x; i < total; i += kDg3Threads) {
+    const int row = i / rowlen, jj = i - row * rowlen;
+    dx[((size_t)(b * IH + 2 * a0 + row) * IW + 2 * c0) * Cin + jj] = o_s[i];
+  }
+}
+
 // dx[B,IH,IW,Cin] from the first Cin of CinW weight channels; the caller has checked dgs_smem_bytes / alignment / pow2 sizes
 cudaError_t conv_dgrad_small_launch(const float* dy, const float* W, const float* a_in, float* dx, int B, int IH, int IW, int Cin,
                                     int CinW, int Cout, cudaStream_t stream) {
+  const int OH = IH / 2, OW = IW / 2;
+  if (Cin == 3 && !a_in && OW % kDg3TW == 0 && OH % kDg3TH == 0 && dg3_smem_bytes(Cout) <= 100 * 1024) {
+    const size_t smem = dg3_smem_bytes(Cout);
+    static size_t opted = 0;
+    if (smem > 48 * 1024 && smem > opted) {
+      const cudaError_t e = cudaFuncSetAttribute(conv_dgrad_img3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      opted = smem;
+    }
+    const int tiles_x = OW / kDg3TW, tiles_y = OH / kDg3TH;
+    return launch_pdl(conv_dgrad_img3_kernel, dim3((unsigned)(B * tiles_x * tiles_y)), dim3(kDg3Threads), smem, stream, dy, W, dx, IH, IW,
+                      CinW, Cout, tiles_x, tiles_y);
+  }
   return Cin <= 8 ? launch_dgrad_small<8, 256, 1>(dy, W, a_in, dx, B, IH, IW, Cin, CinW, Cout, stream)
                   : launch_dgrad_small<10, 128, 2>(dy, W, a_in, dx, B, IH, IW, Cin, CinW, Cout, stream);
 }

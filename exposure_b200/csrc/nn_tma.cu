@@ -103,6 +103,30 @@ struct TmaConvFprop {
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) tma::tma_load_2d(b_dst + j * 4096, &tb, n0 + 32 * j, k, bar);
   }
+  // the epilogue of one float4 in two halves, so that the store pass can put the global loads of several elements in
+  // flight before it consumes any (tc_engine_tma.cuh): epi_load issues them, epi_store finishes the element
+  struct Aux { float4 a, b; };
+  __device__ Aux epi_load(int, int m, int n) const {
+    Aux x;
+    x.a = x.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m >= M || n >= Cout) return x;
+    const size_t idx = (size_t)m * Cout + n;
+    if (mode == 0) { if (bias) x.a = __ldg(reinterpret_cast<const float4*>(bias + n)); }
+    else x.a = __ldg(reinterpret_cast<const float4*>(mask_ref + idx));
+    if (y2) x.b = __ldg(reinterpret_cast<const float4*>(post_mul + idx));
+    return x;
+  }
+  __device__ void epi_store(int, int m, int n, float4 o, const Aux& x) const {
+    if (m >= M || n >= Cout) return;
+    const size_t idx = (size_t)m * Cout + n;
+    if (mode == 0) {
+      o.x = lrelu(o.x + x.a.x); o.y = lrelu(o.y + x.a.y); o.z = lrelu(o.z + x.a.z); o.w = lrelu(o.w + x.a.w);
+    } else {
+      o.x *= dlrelu(x.a.x); o.y *= dlrelu(x.a.y); o.z *= dlrelu(x.a.z); o.w *= dlrelu(x.a.w);
+    }
+    *reinterpret_cast<float4*>(y + idx) = o;
+    if (y2) *reinterpret_cast<float4*>(y2 + idx) = make_float4(o.x * x.b.x, o.y * x.b.y, o.z * x.b.z, o.w * x.b.w);
+  }
   __device__ void store4(int, int m, int n, float4 o) const {
     if (m >= M || n >= Cout) return;                           // Cout % 32 == 0: whole groups of 4
     const size_t idx = (size_t)m * Cout + n;
@@ -184,6 +208,24 @@ struct TmaConvDgrad {
     tma::tma_load_4d(a_dst, &ta, co0, c0 + ox_off, a0 + oy_off, b0, bar);
     tma::tma_load_3d(b_dst, &tb, co0, n0, ky * 4 + kx, bar);
   }
+  struct Aux { float4 a; size_t idx; };
+  __device__ Aux epi_load(int z, int m, int n) const {
+    Aux x;
+    x.a = make_float4(1.f, 1.f, 1.f, 1.f);
+    x.idx = 0;
+    if (m >= M || n >= Cin) return x;
+    const int py = z >> 1, px = z & 1;
+    const int b = m >> lgHW2, rem = m & ((1 << lgHW2) - 1);
+    const int iy = 2 * (rem >> lgW2) + py, ix = 2 * (rem & ((IW / 2) - 1)) + px;
+    x.idx = ((size_t)(b * IH + iy) * IW + ix) * Cin + n;
+    if (a_in) x.a = __ldg(reinterpret_cast<const float4*>(a_in + x.idx));
+    return x;
+  }
+  __device__ void epi_store(int, int m, int n, float4 o, const Aux& x) const {
+    if (m >= M || n >= Cin) return;
+    if (a_in) { o.x *= dlrelu(x.a.x); o.y *= dlrelu(x.a.y); o.z *= dlrelu(x.a.z); o.w *= dlrelu(x.a.w); }
+    *reinterpret_cast<float4*>(dx + x.idx) = o;
+  }
   __device__ void store4(int z, int m, int n, float4 o) const {
     if (m >= M || n >= Cin) return;                            // Cin % 4 == 0
     const int py = z >> 1, px = z & 1;
@@ -261,6 +303,9 @@ struct TmaConvWgrad {
 #pragma unroll
     for (int j = 0; j < BN / 32; ++j) tma::tma_load_2d(b_dst + j * 4096, &tb, n0 + 32 * j, p0, bar);
   }
+  struct Aux {};
+  __device__ Aux epi_load(int, int, int) const { return Aux{}; }
+  __device__ void epi_store(int z, int m, int n, float4 o, const Aux&) const { store4(z, m, n, o); }
   __device__ void store4(int z, int m, int n, float4 o) const {
     if (m >= 16 * Cin || n >= Cout) return;
     *reinterpret_cast<float4*>(part + ((size_t)z * 16 * Cin + m) * Cout + n) = o;

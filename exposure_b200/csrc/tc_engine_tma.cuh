@@ -160,7 +160,8 @@ __device__ long long g_tma_trace_cta[kTraceCtas][8];      // one-tile kernel: en
 //   void load<BN>(ki, slice, m0, n0, a_dst, b_dst, bar)   issue the TMA loads of K step ki
 //                                                (exactly kTileA + BN * 128 bytes in total)
 //   void store16(slice, m, n0, v[16])            C[m, n0..n0+15]
-//   void store4(slice, m, n, float4)             C[m, n..n+3]          (cluster split-K epilogue)
+//   void store4(slice, m, n, float4)             C[m, n..n+3]
+//   Aux  epi_load(slice, m, n); void epi_store(slice, m, n, float4, Aux)   the same in two halves (store pass)
 template <class P, int BN, int NS_ = 0>
 __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_kernel(const __grid_constant__ P p) {
   static_assert(BN == 32 || BN == 64 || BN == 128, "BN must be 32, 64 or 128");
@@ -322,6 +323,12 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
 #pragma unroll 1
     for (int idx0 = tid - 64; idx0 < total; idx0 += 4 * kConverters) {
       float4 v[4];
+      typename P::Aux aux[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                   // the functor's global operands (bias / mask / multiplier) first
+        const int idx = idx0 + u * kConverters;
+        if (idx < total) aux[u] = p.epi_load(z, m0 + (idx >> lgW4), n0 + rank * W + ((idx & ((1 << lgW4) - 1)) << 2));
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int idx = idx0 + u * kConverters;
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<BN, NS_>::kCtasPerSm) tma_gemm_k
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int idx = idx0 + u * kConverters;
-        if (idx < total) p.store4(z, m0 + (idx >> lgW4), n0 + rank * W + ((idx & ((1 << lgW4) - 1)) << 2), v[u]);
+        if (idx < total) p.epi_store(z, m0 + (idx >> lgW4), n0 + rank * W + ((idx & ((1 << lgW4) - 1)) << 2), v[u], aux[u]);
       }
       if (tid == 64 && idx0 == 0) EXPO_TRACE_CTA(7);
     }

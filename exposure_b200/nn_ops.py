@@ -304,9 +304,27 @@ def conv_first_dgrad(dy, W, Cv, in_hw, need_image=True, need_vec=True):
   assert (OH, OW) == (IH // 2, IW // 2) and W.shape[2] == 3 + Cv and W.shape[3] == Cout
   dx = torch.empty(B, IH, IW, 3, device=dy.device, dtype=torch.float32) if need_image else None
   gv = torch.empty(B, Cv, device=dy.device, dtype=torch.float32) if need_vec and Cv else None
+  l = _cabi.lib()
   with _ops._Timed("conv_dgrad", "gemm", 2 * B * OH * OW * Cout * 16 * 3):
-    _cabi.check(_cabi.lib().exp_conv_first_dgrad(dy.data_ptr(), W.data_ptr(), Cv, _p(dx), _p(gv), B, IH, IW, _stream()),
-                "exp_conv_first_dgrad")
+    if dx is not None and gv is not None and FORK_ENABLED:
+      # two independent kernels (image channels / per-image sums of the constant channels): side by side.  Both outputs
+      # were allocated on the current stream above; the explicit wait (not join(): that may be deferred) orders the
+      # consumer after the side stream.
+      parent = torch.cuda.current_stream()
+      key = (parent.device, "first_dgrad")
+      side = _side_streams.get(key)
+      if side is None:
+        side = _side_streams[key] = torch.cuda.Stream(device=parent.device)
+      side.wait_stream(parent)
+      with torch.cuda.stream(side):
+        _cabi.check(l.exp_conv_first_dgrad(dy.data_ptr(), W.data_ptr(), Cv, None, gv.data_ptr(), B, IH, IW, _stream()),
+                    "exp_conv_first_dgrad")
+      _cabi.check(l.exp_conv_first_dgrad(dy.data_ptr(), W.data_ptr(), Cv, dx.data_ptr(), None, B, IH, IW, _stream()),
+                  "exp_conv_first_dgrad")
+      parent.wait_stream(side)
+    else:
+      _cabi.check(l.exp_conv_first_dgrad(dy.data_ptr(), W.data_ptr(), Cv, _p(dx), _p(gv), B, IH, IW, _stream()),
+                  "exp_conv_first_dgrad")
   _n((1 if need_image else 0) + (1 if gv is not None else 0))
   return dx, gv
 

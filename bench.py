@@ -560,7 +560,7 @@ def train_config(args):
       "replay": "host lists" if getattr(args, "host_replay", False) else "device (selection kernels, whole iteration one CUDA graph)",
       "batch_per_gpu": args.batch, "height": 64, "width": 64, "channels": 3, "filters": "E,G,W,S+,T,Ct,BW,C",
       "giters": 1, "citers": 5,
-      "parallelism": "dp%d (batch sharded by image; one NCCL all-reduce per optimizer step)" % args.gpus,
+      "parallelism": "dp%d (batch sharded by image; one gradient all-reduce per optimizer step)" % args.gpus,
       "l2_policy": "no flush: one iteration touches ~137 MB of parameters + gradients + Adam slots plus ~150 MB of "
                    "activations (> the 126 MB L2); every iteration draws fresh replay batches, dropout masks and noise",
   }
@@ -765,6 +765,9 @@ def run_train(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": train_config(args),
            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "tensor": tensor,
            "kernel_launches_per_iteration": launches // args.steps,
+           "dp_transport": ("single GPU" if world == 1 else
+                            "exp_dp_allreduce_adam: all-reduce over NVLink peer memory fused with Adam, a node of the CUDA graph"
+                            if getattr(t, "_peer", None) is not None else "dist.all_reduce + exp_adam (outside the graph)"),
            "losses": {k: (float(v) if (v is not None and v.numel() == 1) else None) for k, v in last.items()
                       if k in ("g_loss", "v_loss", "emd", "critic_gradient_norm")}}
     if world == 1:

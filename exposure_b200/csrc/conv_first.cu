@@ -49,14 +49,19 @@ __device__ __forceinline__ Tile decode_tile(int t, int tiles_x, int tiles_y) {
 // (x - shift) of the tile's receptive field, zero outside the image: xs[row 2 (oy - oy0) + ky][col 2 (ox - ox0) + kx][c]
 __device__ __forceinline__ void load_input_tile(float* xs, const float* __restrict__ x, const Tile& t, int IH, int IW, float shift) {
   const int iy0 = 2 * t.oy0 - 1, ix0 = 2 * t.ox0 - 1;
-  for (int i = threadIdx.x; i < kInRows * kInCols * kCx; i += kThreads) {
-    const int r = i / (kInCols * kCx), j = i - r * (kInCols * kCx);
-    const int iy = iy0 + r, ix = ix0 + j / kCx;
-    float v = 0.f;
-    if ((unsigned)iy < (unsigned)IH && (unsigned)ix < (unsigned)IW)
-      v = __ldg(x + ((size_t)(t.b * IH + iy) * IW + ix0) * kCx + j) - shift;
-    xs[r * kPitch + j] = v;
-  }
+  batched_fill<7>(kInRows * kInCols * kCx, kThreads,
+                  [&](int i) {
+                    const int r = i / (kInCols * kCx), j = i - r * (kInCols * kCx);
+                    const int iy = iy0 + r, ix = ix0 + j / kCx;
+                    float v = 0.f;
+                    if ((unsigned)iy < (unsigned)IH && (unsigned)ix < (unsigned)IW)
+                      v = __ldg(x + ((size_t)(t.b * IH + iy) * IW + ix0) * kCx + j) - shift;
+                    return v;
+                  },
+                  [&](int i, float v) {
+                    const int r = i / (kInCols * kCx), j = i - r * (kInCols * kCx);
+                    xs[r * kPitch + j] = v;
+                  });
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -75,18 +80,27 @@ __global__ void __launch_bounds__(kThreads) conv_first_fwd_kernel(const FwdArgs 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int OH = A.IH >> 1, OW = A.IW >> 1, Cin = kCx + A.Cv;
   const Tile t = decode_tile(blockIdx.x, A.tiles_x, A.tiles_y);
-  for (int i = tid; i < kK * kCout; i += kThreads) {
-    const int co = i & 31, k = i >> 5, tap = k / kCx, c = k - tap * kCx;
-    ws[i] = __ldg(A.W + ((size_t)tap * Cin + c) * kCout + co);
-  }
+  batched_fill<6>(kK * kCout, kThreads,
+                  [&](int i) {
+                    const int co = i & 31, k = i >> 5, tap = k / kCx, c = k - tap * kCx;
+                    return __ldg(A.W + ((size_t)tap * Cin + c) * kCout + co);
+                  },
+                  [&](int i, float v) { ws[i] = v; });
   if (tid < A.Cv) vs[tid] = __ldg(A.vec + (size_t)t.b * A.Cv + tid) - A.shift;
   load_input_tile(xs, A.x, t, A.IH, A.IW, A.shift);
   __syncthreads();
-  for (int i = tid; i < 16 * kCout; i += kThreads) {                    // V[tap][co]
+  for (int i = tid; i < 16 * kCout; i += kThreads) {                    // V[tap][co], 8 weight loads in flight
     const int co = i & 31, tap = i >> 5;
     const float* w = A.W + ((size_t)tap * Cin + kCx) * kCout + co;
     float s = 0.f;
-    for (int c = 0; c < A.Cv; ++c) s = fmaf(vs[c], __ldg(w + (size_t)c * kCout), s);
+    for (int c0 = 0; c0 < A.Cv; c0 += 8) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = c0 + u < A.Cv ? __ldg(w + (size_t)(c0 + u) * kCout) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (c0 + u < A.Cv) s = fmaf(vs[c0 + u], wv[u], s);
+    }
     V[i] = s;
   }
   __syncthreads();
@@ -205,13 +219,16 @@ __global__ void __launch_bounds__(kThreads) conv_first_wgrad_kernel(const WgradA
   const int OH = A.IH >> 1, OW = A.IW >> 1;
   const Tile t = decode_tile(blockIdx.x, A.tiles_x, A.tiles_y);
   load_input_tile(xs, A.x, t, A.IH, A.IW, A.shift);
-  for (int i = tid; i < kTH * kTW * (kCout / 4); i += kThreads) {
-    const int q = i & 7, px = i >> 3, r = px / kTW, c = px - r * kTW;
-    const int oy = t.oy0 + r, ox = t.ox0 + c;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (oy < OH && ox < OW) v = __ldg(reinterpret_cast<const float4*>(A.dy + ((size_t)(t.b * OH + oy) * OW + ox) * kCout) + q);
-    reinterpret_cast<float4*>(dys)[i] = v;
-  }
+  batched_fill<8>(kTH * kTW * (kCout / 4), kThreads,
+                  [&](int i) {
+                    const int q = i & 7, px = i >> 3, r = px / kTW, c = px - r * kTW;
+                    const int oy = t.oy0 + r, ox = t.ox0 + c;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (oy < OH && ox < OW)
+                      v = __ldg(reinterpret_cast<const float4*>(A.dy + ((size_t)(t.b * OH + oy) * OW + ox) * kCout) + q);
+                    return v;
+                  },
+                  [&](int i, float4 v) { reinterpret_cast<float4*>(dys)[i] = v; });
   for (int i = tid; i < 16 * 8 * kCout; i += kThreads) bins[i] = 0.f;
   __syncthreads();
 

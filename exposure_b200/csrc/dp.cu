@@ -105,15 +105,33 @@ __global__ void __launch_bounds__(kDpThreads, 1) dp_allreduce_adam_kernel(const 
   dp_barrier(A, kDpSlot0, kDpGridA, e);
 
   // ---- phase 1: reduce-scatter of my slice, rank order ----
+  // A peer load is an NVLink round trip (~2 us) and the SM issues in order: a load whose value is consumed right
+  // away costs the whole trip.  So every thread first ISSUES its `world` loads of up to 2 elements, then adds them
+  // (in rank order: the result does not depend on the batching).
   const size_t chunk = A.n4 / A.world;                       // the host pads n to a multiple of 4 * world
   float* red_mine = A.red[A.rank];
-  for (size_t i = (size_t)A.rank * chunk + gtid; i < (size_t)(A.rank + 1) * chunk; i += gstride) {
-    float4 s = ld_sys_v4(A.grads[0] + 4 * i);
-    for (int q = 1; q < A.world; ++q) {
-      const float4 t = ld_sys_v4(A.grads[q] + 4 * i);
-      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+  {
+    const size_t lo = (size_t)A.rank * chunk, hi = lo + chunk;
+    for (size_t i = lo + gtid; i < hi; i += 2 * gstride) {
+      const size_t i1 = i + gstride;
+      const bool two = i1 < hi;
+      float4 t0[kDpMaxWorld], t1[kDpMaxWorld];
+#pragma unroll
+      for (int q = 0; q < kDpMaxWorld; ++q)
+        if (q < A.world) {
+          t0[q] = ld_sys_v4(A.grads[q] + 4 * i);
+          if (two) t1[q] = ld_sys_v4(A.grads[q] + 4 * i1);
+        }
+      float4 s0 = t0[0], s1 = two ? t1[0] : t0[0];
+#pragma unroll
+      for (int q = 1; q < kDpMaxWorld; ++q)
+        if (q < A.world) {
+          s0.x += t0[q].x; s0.y += t0[q].y; s0.z += t0[q].z; s0.w += t0[q].w;
+          if (two) { s1.x += t1[q].x; s1.y += t1[q].y; s1.z += t1[q].z; s1.w += t1[q].w; }
+        }
+      *reinterpret_cast<float4*>(red_mine + 4 * i) = s0;
+      if (two) *reinterpret_cast<float4*>(red_mine + 4 * i1) = s1;
     }
-    *reinterpret_cast<float4*>(red_mine + 4 * i) = s;
   }
   __threadfence_system();
   __syncthreads();
@@ -131,25 +149,42 @@ __global__ void __launch_bounds__(kDpThreads, 1) dp_allreduce_adam_kernel(const 
   // ---- phase 2: all-gather fused with Adam ----
   const float lr_a = A.hyper_a[0], lr_b = A.hyper_b ? A.hyper_b[0] : lr_a;
   const float b1 = A.beta1, b2 = A.beta2;
-  for (size_t i = gtid; i < A.n4; i += gstride) {
-    const int s = (int)(i / chunk);
-    float4 g = ld_sys_v4(A.red[s] + 4 * i);
-    const float lr_t = i < A.n4_a ? lr_a : lr_b;
-    float4 pm = *reinterpret_cast<float4*>(A.m + 4 * i), pv = *reinterpret_cast<float4*>(A.v + 4 * i);
-    float4 pp = *reinterpret_cast<float4*>(A.p + 4 * i);
-#define EXP_ADAM1(c)                                                    \
-    {                                                                   \
-      const float gi = g.c * A.inv_world;                               \
-      const float mi = b1 * pm.c + (1.f - b1) * gi;                     \
-      const float vi = b2 * pv.c + (1.f - b2) * gi * gi;                \
-      pm.c = mi; pv.c = vi;                                             \
-      pp.c -= lr_t * mi / (sqrtf(vi) + A.eps);                          \
+  // 4 elements per round: the 4 peer loads (and the 12 local ones) are in flight together
+  for (size_t i0 = gtid; i0 < A.n4; i0 += 4 * gstride) {
+    float4 g[4], pm[4], pv[4], pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + (size_t)u * gstride;
+      if (i < A.n4) g[u] = ld_sys_v4(A.red[(int)(i / chunk)] + 4 * i);
     }
-    EXP_ADAM1(x) EXP_ADAM1(y) EXP_ADAM1(z) EXP_ADAM1(w)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + (size_t)u * gstride;
+      if (i < A.n4) {
+        pm[u] = *reinterpret_cast<const float4*>(A.m + 4 * i);
+        pv[u] = *reinterpret_cast<const float4*>(A.v + 4 * i);
+        pp[u] = *reinterpret_cast<const float4*>(A.p + 4 * i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + (size_t)u * gstride;
+      if (i >= A.n4) continue;
+      const float lr_t = i < A.n4_a ? lr_a : lr_b;
+#define EXP_ADAM1(c)                                                    \
+      {                                                                 \
+        const float gi = g[u].c * A.inv_world;                          \
+        const float mi = b1 * pm[u].c + (1.f - b1) * gi;                \
+        const float vi = b2 * pv[u].c + (1.f - b2) * gi * gi;           \
+        pm[u].c = mi; pv[u].c = vi;                                     \
+        pp[u].c -= lr_t * mi / (sqrtf(vi) + A.eps);                     \
+      }
+      EXP_ADAM1(x) EXP_ADAM1(y) EXP_ADAM1(z) EXP_ADAM1(w)
 #undef EXP_ADAM1
-    *reinterpret_cast<float4*>(A.m + 4 * i) = pm;
-    *reinterpret_cast<float4*>(A.v + 4 * i) = pv;
-    *reinterpret_cast<float4*>(A.p + 4 * i) = pp;
+      *reinterpret_cast<float4*>(A.m + 4 * i) = pm[u];
+      *reinterpret_cast<float4*>(A.v + 4 * i) = pv[u];
+      *reinterpret_cast<float4*>(A.p + 4 * i) = pp[u];
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {

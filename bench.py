@@ -571,7 +571,7 @@ def run_train(args):
   import torch
   import torch.distributed as dist
   from exposure_b200 import ops
-  from exposure_b200.replay import DeviceReplayMemory, ReplayMemory, SyntheticProvider
+  from exposure_b200.replay import DeviceReplayMemory, ReplayMemory, ResidentProvider, SyntheticProvider
   from exposure_b200.trainer import Trainer, default_cfg
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -589,7 +589,11 @@ def run_train(args):
   B = args.batch
   t = Trainer(cfg, dev, seed=0)                       # identical initial weights on every rank
   Mem = ReplayMemory if args.host_replay else DeviceReplayMemory     # selection logic on the device (product) / host lists (A/B)
-  mem = Mem(cfg, SyntheticProvider(dev, "raw", 100 + rank), SyntheticProvider(dev, "real", 200 + rank), dev, seed=rank)
+  # the data providers' batches are resident in HBM before the timed region (rings of distinct seeded batches handed out
+  # round robin); the e2e leg below brings every batch from pinned host memory instead
+  fake_p = ResidentProvider(SyntheticProvider(dev, "raw", 100 + rank), slots=12)
+  real_p = ResidentProvider(SyntheticProvider(dev, "real", 200 + rank), slots=40)
+  mem = Mem(cfg, fake_p, real_p, dev, seed=rank)
   t.attach_memory(mem, torch.Generator(device=dev).manual_seed(300 + rank))
 
   def barrier():

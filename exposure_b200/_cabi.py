@@ -71,6 +71,7 @@ SIGNATURES = {
     "exp_conv1_wgrad_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "exp_conv1_wgrad": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                  _c_size_t, _c_void_p]),
+    "exp_set_floats": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p]),
     "exp_conv_first_supported": (_c_int, [_c_int, _c_int, _c_int]),
     "exp_conv_first_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, ctypes.c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                     _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),

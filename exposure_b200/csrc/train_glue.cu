@@ -322,11 +322,26 @@ __global__ void __launch_bounds__(kGlueThreads) stats_bwd_gin_kernel(const float
   }
 }
 
+// dst[0..n) = the n <= 16 values passed BY VALUE: one launch instead of n scalar fills, no host buffer to keep alive
+struct FloatVals { float v[16]; };
+__global__ void set_floats_kernel(float* __restrict__ dst, const FloatVals V, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = V.v[threadIdx.x];
+}
+
 }  // namespace expo
 
 using namespace expo;
 
 extern "C" {
+
+int exp_set_floats(float* dst, const float* host_vals, int n, void* stream) {
+  EXP_CHECK_ARG(dst && host_vals && n > 0 && n <= 16, "1..16 values (got %d)", n);
+  FloatVals V{};
+  for (int i = 0; i < n; ++i) V.v[i] = host_vals[i];
+  set_floats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dst, V, n);
+  EXP_CHECK_LAUNCH("exp_set_floats");
+  return EXP_OK;
+}
 
 int exp_critic_inputs(const float* real, const float* fake, const float* alpha, float* X, int B, int n, void* stream) {
   EXP_CHECK_ARG(real && fake && alpha && X && B > 0 && B <= 65535 && n > 0 && n % 4 == 0, "bad args (n must be a multiple of 4)");

@@ -685,6 +685,13 @@ def colsum_multi(tasks):
     _n()
 
 
+def set_floats(dst, values):
+  """dst[:len(values)] = values (<= 16 floats) in ONE launch, values passed by value (exp_set_floats)."""
+  vals = (_ct.c_float * len(values))(*[float(v) for v in values])
+  _cabi.check(_cabi.lib().exp_set_floats(dst.data_ptr(), _ct.cast(vals, _ct.c_void_p), len(values), _stream()), "exp_set_floats")
+  _n()
+
+
 def stats_bwd_gin(img, stats, g_in, out=None):
   """dL/dimages from the layer-1 input gradient g_in [n,H,W,cin] (image channels + J_stats^T of the statistic channels)."""
   _chk(img, "img", 4); _chk(g_in, "g_in", 4)

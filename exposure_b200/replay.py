@@ -32,6 +32,30 @@ class SyntheticProvider:
     return torch.exp(0.7 * z - 1.2).clamp_(0, 1)   # retouched targets: brighter, display range
 
 
+class ResidentProvider:
+  """`slots` batches of `inner` per batch size, generated once and kept in HBM, then handed out round robin: the
+  data-set side of a measurement whose inputs are resident when the timed region starts (bench.py; a provider that
+  draws new random batches costs ~25 small kernels per train iteration that are not part of the path)."""
+
+  def __init__(self, inner, slots=16):
+    self.inner, self.slots = inner, int(slots)
+    self._rings, self._next = {}, {}
+
+  def prefill(self, n):
+    ring = self._rings.setdefault(n, [])
+    while len(ring) < self.slots:
+      ring.append(self.inner.get_next_batch(n))
+
+  def get_next_batch(self, n):
+    ring = self._rings.setdefault(n, [])
+    k = self._next.get(n, 0)
+    self._next[n] = k + 1
+    if len(ring) < self.slots:
+      ring.append(self.inner.get_next_batch(n))
+      return ring[-1]
+    return ring[k % self.slots]
+
+
 class DeviceReplayMemory:
   """The replay memory with its SELECTION LOGIC on the device too (csrc/replay.cu): every operation
   of replay_memory.py:187-273 is an index list computed by a one-thread kernel over the pool's 128 state rows plus a

@@ -222,10 +222,11 @@ class Trainer:
     n_c = int(citers or cfg.citers)
     s = cfg.source_img_size
     self._it = dict(
-        real=torch.zeros(n_c, B, s, s, 3, device=dev), progress=torch.zeros(1, device=dev),
-        hyper=torch.zeros(2 + n_c, device=dev), uni=torch.zeros(B * (1 + n_c), device=dev),
+        real=torch.zeros(n_c, B, s, s, 3, device=dev),
+        hyper=torch.zeros(2 + n_c + 1, device=dev), uni=torch.zeros(B * (1 + n_c), device=dev),
         masks=torch.zeros(2, B, 4, 4, 256, device=dev), citers=n_c)
     I = self._it
+    I["progress"] = I["hyper"][2 + n_c:]              # lr_t of the 2 + n_c optimizer steps, then progress: one buffer, one launch
     seed = mem.seed ^ 0x5DEECE66D
 
     def body():
@@ -282,9 +283,12 @@ class Trainer:
     for _ in range(I["citers"]):
       self.counter_c += 1
       vals.append(lr_c * math.sqrt(1.0 - b2 ** self.counter_c) / (1.0 - b1 ** self.counter_c))
-    for k, v in enumerate(vals):                       # scalar fills: no host buffer to keep alive, nothing to wait for
-      I["hyper"][k:k + 1].fill_(v)
-    I["progress"].fill_(float(it) / cfg.max_iter_step)
+    vals.append(float(it) / cfg.max_iter_step)         # progress
+    if len(vals) <= 16:
+      K.set_floats(I["hyper"], vals)                   # by value: no host buffer to keep alive, nothing to wait for
+    else:
+      for k, v in enumerate(vals):
+        I["hyper"][k:k + 1].fill_(v)
     mem.stage_fresh()
     for k in range(I["citers"]):
       I["real"][k].copy_(mem.real_dataset.get_next_batch(B))

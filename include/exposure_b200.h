@@ -433,6 +433,11 @@ int exp_colsum_multi(const float* const* src_host, float* const* dst_host, const
 int exp_stats_bwd_gin(const float* img, const float* stats, const float* g_in, int cin, float* g_out, int B, int H,
                       int W, void* stream);
 
+/* dst[0..n) = host_vals[0..n), n <= 16, passed to the kernel BY VALUE: the per-iteration scalars of a captured train
+ * iteration (Adam's lr_t of every optimizer step, net.py:224; `progress`, agent.py:228-252) in one launch; the host
+ * array may be reused as soon as the call returns. */
+int exp_set_floats(float* dst, const float* host_vals, int n, void* stream);
+
 /* ---- device-side replay memory (csrc/replay.cu, csrc/replay_logic.cuh) -----------------------------------------
  * Replaces the host list handling of replay_memory.py:187-273 (random.shuffle, list slicing, np.stack and a feed of
  * every image per sess.run) by index lists computed on the device.  Records live in ONE buffer of three regions

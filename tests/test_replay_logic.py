@@ -165,3 +165,25 @@ def test_philox_uniforms_are_uniform_and_reproducible(rl):
   assert abs(a.mean() - 0.5) < 0.01 and abs(a.var() - 1 / 12) < 0.005
   rl.rl_uniforms(ctypes.c_ulonglong(3), ctypes.c_ulonglong(8), _p(b), 20000)
   assert (a != b).mean() > 0.99
+
+
+def test_resident_provider_cycles_pregenerated_batches():
+  """ResidentProvider: `slots` batches per size generated once, then handed out round robin (bench.py's data side)."""
+  import torch
+  from exposure_b200.replay import ResidentProvider
+
+  class Counting:
+    def __init__(self):
+      self.calls = 0
+    def get_next_batch(self, n):
+      self.calls += 1
+      return torch.full((n, 2), float(self.calls))
+
+  inner = Counting()
+  p = ResidentProvider(inner, slots=3)
+  p.prefill(4)
+  assert inner.calls == 3
+  got = [float(p.get_next_batch(4)[0, 0]) for _ in range(7)]
+  assert got == [1.0, 2.0, 3.0, 1.0, 2.0, 3.0, 1.0] and inner.calls == 3
+  first = [float(p.get_next_batch(5)[0, 0]) for _ in range(4)]          # another size: its own ring, filled lazily
+  assert first == [4.0, 5.0, 6.0, 5.0] or first == [4.0, 5.0, 6.0, 4.0]

@@ -147,3 +147,17 @@ def test_stats_bwd_gin_equals_the_composed_launches(K):
     ref = K.stats_bwd(img, stats, g_vec[:, -3:].contiguous(), g_direct=g_in[..., :3].contiguous())
     torch.cuda.synchronize()
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6 * float(ref.abs().max()))
+
+
+def test_set_floats(K):
+  """exp_set_floats: up to 16 scalars by value in one launch (the per-iteration lr_t / progress of the captured iteration)."""
+  dst = torch.full((20,), -1.0, device="cuda")
+  vals = [0.125 * i - 0.5 for i in range(16)]
+  K.set_floats(dst, vals)
+  torch.cuda.synchronize()
+  assert dst[:16].cpu().tolist() == vals and dst[16:].cpu().tolist() == [-1.0] * 4
+  K.set_floats(dst[3:], [7.0])
+  assert float(dst[3]) == 7.0 and float(dst[4]) == vals[4]
+  with pytest.raises(Exception):
+    K.set_floats(dst, [0.0] * 17)
+

@@ -560,6 +560,8 @@ def train_config(args):
       "replay": "host lists" if getattr(args, "host_replay", False) else "device (selection kernels, whole iteration one CUDA graph)",
       "batch_per_gpu": args.batch, "height": 64, "width": 64, "channels": 3, "filters": "E,G,W,S+,T,Ct,BW,C",
       "giters": 1, "citers": 5,
+      "providers": "seeded synthetic RAW / target batches (SURVEY 8d); device-timed value: rings of pre-generated batches "
+                   "resident in HBM (12 x 192 RAW, 40 x 64 target records per rank); e2e: every batch from pinned host memory",
       "parallelism": "dp%d (batch sharded by image; one gradient all-reduce per optimizer step)" % args.gpus,
       "l2_policy": "no flush: one iteration touches ~137 MB of parameters + gradients + Adam slots plus ~150 MB of "
                    "activations (> the 126 MB L2); every iteration draws fresh replay batches, dropout masks and noise",

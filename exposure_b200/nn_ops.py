@@ -249,7 +249,7 @@ def conv_fwd(x, W, bias=None, vec=None, shift=0.0, mask_ref=None, post_mul=None,
     y2 = torch.empty_like(y) if out2 is None else out2
   mode = 0 if mask_ref is None else 1
   if staged is None and _first_path(Cx, Cv, Cout):
-    with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+    with _ops._Timed("conv_fwd", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * Cx):     # the flops it executes (K = 48)
       _cabi.check(_cabi.lib().exp_conv_first_fwd(x.data_ptr(), _p(vec), Cv, float(shift), W.data_ptr(), _p(bias), _p(mask_ref),
                                                  _p(post_mul), y.data_ptr(), _p(y2), B, IH, IW, mode, _stream()),
                   "exp_conv_first_fwd")
@@ -340,7 +340,7 @@ def conv_wgrad(x, dy, vec=None, shift=0.0, out=None, accumulate=False, staged=No
   l = _cabi.lib()
   if staged is None and _first_path(Cx, Cv, Cout):
     ws = _workspace(x.device, l.exp_conv_first_wgrad_workspace_bytes(B, IH, IW))
-    with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * (Cx + Cv)):
+    with _ops._Timed("conv_wgrad", "gemm", 2 * B * (IH // 2) * (IW // 2) * Cout * 16 * Cx):
       _cabi.check(l.exp_conv_first_wgrad(x.data_ptr(), _p(vec), Cv, float(shift), dy.data_ptr(), gW.data_ptr(), B, IH, IW,
                                          int(accumulate), ws.data_ptr(), ws.numel(), _stream()), "exp_conv_first_wgrad")
     _n(2)

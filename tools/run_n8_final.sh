@@ -5,9 +5,8 @@ TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 mkdir -p gpurun_out
 timeout 200 $TR --nproc-per-node 8 --master-port 29711 tools/dp_check.py 2>&1 | grep dp_check > gpurun_out/r2final_dp_check_n8.log
 tail -6 gpurun_out/r2final_dp_check_n8.log
-for n in 8 4; do
-  timeout 300 $TR --nproc-per-node $n --master-port 2972$n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r2final_bench_train_n$n.json 2> gpurun_out/r2final_bench_train_n$n.err
-done
+timeout 300 $TR --nproc-per-node 8 --master-port 29728 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2final_bench_train_n8.json 2> gpurun_out/r2final_bench_train_n8.err
+timeout 300 $TR --nproc-per-node 4 --master-port 29724 bench.py --gpus 4 --steps 20 --warmup 5 --roofline-batch 0 > gpurun_out/r2final_bench_train_n4.json 2> gpurun_out/r2final_bench_train_n4.err
 for f in gpurun_out/r2final_bench_train_n8.json gpurun_out/r2final_bench_train_n4.json; do
   python -c "import json; d=json.load(open('$f')); print('$f', d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],4), round(d['e2e']['value'],1))"
 done

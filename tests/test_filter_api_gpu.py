@@ -28,6 +28,8 @@ def test_registry_apply_and_autograd(built_lib):
     low, high, dbg = f.apply(net, specified_parameter=param, high_res=net[:, :32].contiguous())
     ref = OF.process(j, net.cpu(), ref_p)
     tol = 1e-5 * ref.abs().clamp_min(1e-4) + (2e-4 * ref.abs() if j == OF.CT else 0)
+    if j == OF.SP:      # closed-form ramps vs the fp32 hue round trip of the restatement (tests/test_filters_gpu.py _fwd_tol)
+      tol = tol + 1e-6 * net.cpu().clamp(max=1.0).amax(dim=-1, keepdim=True).abs() * ref_p.abs().reshape(-1, 1, 1, 1)
     assert ((low.detach().cpu() - ref).abs() <= tol).all(), j
     assert high.shape == (B, 32, 64, 3) and "filter_parameters" in dbg and "mask" in dbg
     low.sum().backward()                                                              # tf.gradients through process + regressor

@@ -320,13 +320,13 @@ __device__ __forceinline__ void px_fwd(const float (&x)[3], float (&y)[3], const
     // cos(pi l): the reference's fp32 constant pi_f = 3.14159274 differs from pi by 8.7e-8, which moves the
     // cosine by < 1 ulp(1) on [0, 1] -- inside the allowance the tests give this formula's own cancellation
     const float cl = __fadd_rn(__fmul_rn(-cos_pi(l), 0.5f), 0.5f);
-    const float den = __fadd_rn(l, 1e-6f);
+    // x / (l + 1e-6) * cl as x * (cl * rcp(l + 1e-6)): one MUFU.RCP instead of three IEEE divisions; <= 3 ulp of
+    // x / (l + 1e-6) away from the op-by-op restatement, inside the slack the forward tests grant this formula for the
+    // cancellation in cl (tests/test_filters_gpu.py _fwd_tol)
+    const float w = __fmul_rn(cl, rcp_fast(__fadd_rn(l, 1e-6f)));
     const float q = __fsub_rn(1.f, p);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float ci = __fmul_rn(__fdiv_rn(x[c], den), cl);
-      y[c] = __fadd_rn(__fmul_rn(q, x[c]), __fmul_rn(p, ci));
-    }
+    for (int c = 0; c < 3; ++c) y[c] = __fadd_rn(__fmul_rn(q, x[c]), __fmul_rn(p, __fmul_rn(x[c], w)));
   } else if constexpr (FID == EXP_FILTER_LEVEL) {      // filters.py:459-464
     const float lo = sc.p[0], d = sc.e;
 #pragma unroll

@@ -7,7 +7,9 @@
 Workload `train` (default; the configuration BASELINE.json's metric is quoted on, configs[3]): one
 iteration of GAN.train (net.py:307-370) = 1 generator+value step + 5 WGAN-GP critic steps on per-GPU
 batches of 64 x 64 x 64 x 3 fp32 images drawn from the device-resident replay memory, data parallel:
-one process per GPU, ONE NCCL all-reduce per optimizer step (weak scaling: 64 images per GPU).
+one process per GPU, ONE gradient all-reduce per optimizer step -- a peer-memory kernel fused with Adam inside the
+iteration's CUDA graph on NCCL process groups, dist.all_reduce otherwise (weak scaling: 64 images per GPU).  The data
+providers' batches are resident in HBM (ResidentProvider); the e2e leg brings every batch from pinned host memory.
 A "step" is one such iteration.  The same run also measures the filter chain the north star's roofline
 target is stated on (8-filter chain fwd+bwd at 256 x 512 x 512 x 3, as ONE fused kernel and as 16 per-step
 kernels) and reports it as `roofline`; the conv / FC tensor-core family of the train step is `tensor`.
